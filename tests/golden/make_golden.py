@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (needs the read-only reference checkout):
+
+    python tests/golden/make_golden.py [--ref /root/reference] [--only case ...]
+
+What it does
+  1. Imports ``/root/reference/models/vilbert_dialog.py`` / ``visual_dialog_encoder.py`` /
+     ``utils/data_utils.py`` / ``utils/visdial_metrics.py`` as they are.  Two third-party modules the
+     reference imports but never uses on this path are absent offline and are stubbed
+     (``pytorch_transformers``, ``pytorch_pretrained_bert``); ``Tensor.cuda`` is a no-op on CPU
+     (the reference calls ``pe.cuda()`` on a buffer it never reads, models/vilbert_dialog.py:314).
+  2. Builds ``VisualDialogEncoder`` without its network download (``__new__`` + a directly constructed
+     ``BertForMultiModalPreTraining``) and loads ``unimm_b200.weights.random_state_dict`` through the
+     reference's own ``load_state_dict(strict=True)`` — which also pins the 535-key layout.
+  3. Builds inputs with the reference's own ``encode_input_gen/_dis/encode_input`` and
+     ``encode_image_input`` and asserts that ``oracle.encode_inputs`` reproduces them bit for bit.
+  4. Calls ``VisualDialogEncoder.forward`` with the keyword arguments ``train.forward`` uses
+     (train.py:142-161), applies val_lm.py:131-136 to the full logits, and saves inputs + outputs.
+
+Nothing here is imported by the product or by the GPU-side tests; the ``.npz`` files are.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import encode_inputs as enc            # noqa: E402
+from oracle import visdial_metrics as om           # noqa: E402
+from unimm_b200.config import DEFAULT_CONFIG_PATH, ViLBertConfig   # noqa: E402
+from unimm_b200.weights import PREFIX, random_state_dict            # noqa: E402
+
+
+def import_reference(ref_root: str):
+    for name in ("pytorch_transformers", "pytorch_transformers.modeling_bert", "pytorch_pretrained_bert",
+                 "pytorch_pretrained_bert.file_utils"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["pytorch_transformers.modeling_bert"].BertEmbeddings = object
+    sys.modules["pytorch_transformers"].modeling_bert = sys.modules["pytorch_transformers.modeling_bert"]
+    sys.modules["pytorch_pretrained_bert.file_utils"].cached_path = lambda *a, **k: None
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    sys.path.insert(0, ref_root)
+    import importlib
+    vd = importlib.import_module("models.vilbert_dialog")
+    vde = importlib.import_module("models.visual_dialog_encoder")
+    du = importlib.import_module("utils.data_utils")
+    vm = importlib.import_module("utils.visdial_metrics")
+    return vd, vde, du, vm
+
+
+def build_reference_encoder(vd, vde, ref_root, sd):
+    cfg = vd.BertConfig.from_json_file(os.path.join(ref_root, "config", "bert_base_6layer_6conect.json"))
+    model = vde.VisualDialogEncoder.__new__(vde.VisualDialogEncoder)
+    torch.nn.Module.__init__(model)
+    model.bert_pretrained = vd.BertForMultiModalPreTraining(cfg)
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert len(model.state_dict()) == 535
+    model.eval()
+    return model
+
+
+def ref_batch(du, context, answers, feats, loc, image_mask, fn, seed, **kw):
+    """The reference's encoders driven like dataloader_visdial.py:394-455."""
+    np.random.seed(seed)
+    cols = [[] for _ in range(8)]
+    for j, ans in enumerate(answers):
+        args = dict(max_seq_len=256, mask_prob=0, is_negtive=0)
+        args.update({k: (v[j] if isinstance(v, list) else v) for k, v in kw.items()})
+        out = fn(context + [ans], 1, enc.CLS, enc.SEP, enc.MASK, **args)
+        for c, o in zip(cols, out):
+            c.append(o)
+    tokens, segments, positions, sep_indices, labels, weights, att, co = (torch.cat(c, 0) for c in cols)
+    n, R = tokens.shape[0], feats.shape[0]
+    return {"tokens": tokens, "segments": segments, "positions": positions, "sep_indices": sep_indices,
+            "mask": labels, "weights": weights, "txt_attention_mask": att,
+            "co_attention_mask": co.unsqueeze(1).repeat(1, R, 1),
+            "image_feat": feats.unsqueeze(0).expand(n, -1, -1).contiguous(),
+            "image_loc": loc.unsqueeze(0).expand(n, -1, -1).contiguous(),
+            "image_mask": image_mask.unsqueeze(0).expand(n, -1).contiguous()}
+
+
+def oracle_batch(context, answers, feats, loc, image_mask, fn, seed, **kw):
+    rng = np.random.RandomState(seed)
+    cols = [[] for _ in range(8)]
+    for j, ans in enumerate(answers):
+        args = dict(max_seq_len=256, mask_prob=0, is_negative=0)
+        for k, v in kw.items():
+            k = "is_negative" if k == "is_negtive" else k
+            args[k] = v[j] if isinstance(v, list) else v
+        out = fn(context + [ans], 1, rng=rng, **args)
+        for c, o in zip(cols, out):
+            c.append(o)
+    return [torch.cat(c, 0) for c in cols]
+
+
+def assert_encoders_match(b, o):
+    names = ["tokens", "segments", "positions", "sep_indices", "mask", "weights", "txt_attention_mask"]
+    for n, t in zip(names, o[:7]):
+        assert b[n].dtype == t.dtype or n == "txt_attention_mask", (n, b[n].dtype, t.dtype)
+        assert torch.equal(b[n].long(), t.long()), f"oracle encoder mismatch in {n}"
+    assert torch.equal(b["co_attention_mask"][:, 0, :], o[7]), "oracle encoder mismatch in co mask"
+
+
+def call_reference(model, b, train_extras=None):
+    """VisualDialogEncoder.forward with train.forward's keyword set (train.py:142-161)."""
+    kw = dict(sep_indices=b["sep_indices"], sep_len=None, token_type_ids=b["segments"],
+              token_position_ids=b["positions"], masked_lm_labels=b["mask"], attention_mask=b["txt_attention_mask"],
+              next_sentence_label=None, output_nsp_scores=True, output_lm_scores=True,
+              image_attention_mask=b["image_mask"], co_attention_mask=b["co_attention_mask"], image_label=None,
+              image_target=None, nsp_weight=None, lm_weight=b["weights"])
+    if train_extras:
+        kw.update(train_extras)
+    with torch.no_grad():
+        return model(b["tokens"], b["image_feat"], b["image_loc"], **kw)
+
+
+def val_lm_scores(lm_scores, labels):
+    """val_lm.py:124-136."""
+    a, bb, c = lm_scores.size()
+    nll = F.cross_entropy(lm_scores.view(a * bb, c), labels.view(-1), ignore_index=-1, reduction="none").view(a, bb)
+    return -nll.sum(-1), nll
+
+
+def pack_inputs(b):
+    out = {k: v.numpy() for k, v in b.items() if k not in ("image_feat", "image_loc", "image_mask", "co_attention_mask",
+                                                           "txt_attention_mask")}
+    out["txt_attention_mask"] = np.packbits(b["txt_attention_mask"].bool().numpy(), axis=-1)
+    out["txt_attention_mask_is_long"] = np.array(b["txt_attention_mask"].dtype == torch.long)
+    out["co_txt_mask"] = b["co_attention_mask"][:, 0, :].numpy().astype(np.uint8)
+    return out
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+TAP_LAYERS = None
+
+
+def add_taps(model, store):
+    """Forward hooks on every encoder layer: keep a few rows of sequence 0 for bisecting."""
+    enc_mod = model.bert_pretrained.bert.encoder
+    hooks = []
+
+    def mk(name, is_conn):
+        def hook(_m, _inp, out):
+            if is_conn:
+                store[name + ".img"], store[name + ".txt"] = out[0][0].clone(), out[1][0].clone()
+            else:
+                store[name] = out[0][0].clone()
+        return hook
+    for i, l in enumerate(enc_mod.layer):
+        hooks.append(l.register_forward_hook(mk(f"t{i}", False)))
+    for i, l in enumerate(enc_mod.v_layer):
+        hooks.append(l.register_forward_hook(mk(f"v{i}", False)))
+    for i, l in enumerate(enc_mod.c_layer):
+        hooks.append(l.register_forward_hook(mk(f"c{i}", True)))
+    hooks.append(model.bert_pretrained.bert.embeddings.register_forward_hook(
+        lambda _m, _i, out: store.__setitem__("emb.txt", out[0].clone())))
+    hooks.append(model.bert_pretrained.bert.v_embeddings.register_forward_hook(
+        lambda _m, _i, out: store.__setitem__("emb.img", out[0].clone())))
+    return hooks
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    want = lambda n: args.only is None or n in args.only
+
+    vd, vde, du, vm = import_reference(args.ref)
+    cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
+    torch.set_num_threads(os.cpu_count())
+
+    rng = np.random.RandomState(1234)
+    context, answers = enc.synth_round(rng, n_candidates=100)
+    feats, loc, image_mask = enc.synth_image(rng)
+    # make sure the first 8 candidates cover the answer-length range 1..7 (+SEP → P in 2..8)
+    for j, n in enumerate([1, 2, 3, 4, 5, 6, 7, 4]):
+        answers[j] = rng.randint(1000, 30522, size=n).tolist()
+    image_np = dict(image_feat=feats.numpy(), image_loc=loc.numpy(), image_mask=image_mask.numpy())
+
+    models = {}
+
+    def get_model(seed, perturbed):
+        key = (seed, perturbed)
+        if key not in models:
+            models.clear()
+            models[key] = build_reference_encoder(vd, vde, args.ref, random_state_dict(cfg, seed, perturbed, prefix=PREFIX))
+        return models[key]
+
+    # ---------------------------------------------------------------- generative, 8 candidates
+    for name, seed, perturbed in (("gen8_default", 0, False), ("gen8_perturbed", 1, True)):
+        if not want(name):
+            continue
+        b = ref_batch(du, context, answers[:8], feats, loc, image_mask, du.encode_input_gen, seed=7)
+        assert_encoders_match(b, oracle_batch(context, answers[:8], feats, loc, image_mask, enc.encode_gen, seed=7))
+        model = get_model(seed, perturbed)
+        taps = {}
+        hooks = add_taps(model, taps) if perturbed else []
+        _, _, _, nsp, lm = call_reference(model, b)
+        for h in hooks:
+            h.remove()
+        score, nll = val_lm_scores(lm, b["mask"])
+        rows = (b["mask"] != -1).nonzero()
+        logits_rows = lm[rows[:, 0], rows[:, 1]]
+        lab = b["mask"][rows[:, 0], rows[:, 1]]
+        ul = torch.log(torch.clamp(1.0 - F.softmax(logits_rows, -1), min=1e-6)).gather(1, lab[:, None])[:, 0]
+        extra = {}
+        if taps:
+            # rows of sequence 0: CLS, first/last context, first/last A, first/last B, first pad
+            L = int((b["txt_attention_mask"][0, 0].sum() + b["co_attention_mask"][0, 0].sum() + 1) // 2)
+            T = int(b["txt_attention_mask"][0, 0].sum())
+            ctx = 2 * L - T
+            trow = [0, 1, ctx - 1, ctx, L - 1, L, T - 1, min(T, 255)]
+            extra["tap_txt_rows"] = np.array(trow)
+            extra["tap_img_rows"] = np.array([0, 17, 36])
+            for k, v in taps.items():
+                is_img = k.endswith(".img") or k.startswith("v")
+                extra["tap." + k] = v[[0, 17, 36]].numpy() if is_img else v[trow].numpy()
+        save(name, weight_seed=np.array(seed), perturbed=np.array(perturbed), **pack_inputs(b), **image_np,
+             seq_score=score.numpy(), nsp_scores=nsp.numpy(), token_rows=rows.numpy(),
+             token_logp=(-nll[rows[:, 0], rows[:, 1]]).numpy(), token_ul=ul.numpy(),
+             logits_row0_first64=lm[0, rows[0, 1], :64].numpy(), **extra)
+
+    # ---------------------------------------------------------------- discriminative, 8 candidates (val.py path)
+    if want("dis8_perturbed"):
+        b = ref_batch(du, context, answers[:8], feats, loc, image_mask, du.encode_input_dis, seed=11,
+                      mask_prob=0.15, vocab_size=30522)
+        assert_encoders_match(b, oracle_batch(context, answers[:8], feats, loc, image_mask, enc.encode_dis, seed=11,
+                                              mask_prob=0.15, vocab_size=30522))
+        model = get_model(1, True)
+        _, _, _, nsp, lm = call_reference(model, b)
+        score, nll = val_lm_scores(lm, b["mask"])
+        rows = (b["mask"] != -1).nonzero()
+        save("dis8_perturbed", weight_seed=np.array(1), perturbed=np.array(True), **pack_inputs(b), **image_np,
+             seq_score=score.numpy(), nsp_scores=nsp.numpy(), nsp_prob0=F.softmax(nsp, 1)[:, 0].numpy(),
+             token_rows=rows.numpy(), token_logp=(-nll[rows[:, 0], rows[:, 1]]).numpy())
+
+    # ---------------------------------------------------------------- train forward + losses (config 3 shape, B=6)
+    if want("train6_perturbed"):
+        np.random.seed(23)
+        random.seed(23)
+        neg = [0, 1, 1, 0, 1, 1]
+        cols = [[] for _ in range(8)]
+        for j in range(6):
+            out = du.encode_input(0.5, context + [answers[j]], 1, enc.CLS, enc.SEP, enc.MASK, max_seq_len=256,
+                                  mask_prob=0.15, is_negtive=neg[j], weight=1, vocab_size=30522)
+            for c, o in zip(cols, out):
+                c.append(o.long() if o.dim() == 3 else o)
+        o_rng = np.random.RandomState(23)
+        ocols = [[] for _ in range(8)]
+        for j in range(6):
+            out = enc.encode(0.5, context + [answers[j]], 1, rng=o_rng, max_seq_len=256, mask_prob=0.15,
+                             is_negative=neg[j], weight=1, vocab_size=30522)
+            for c, o in zip(ocols, out):
+                c.append(o.long() if o.dim() == 3 else o)
+        tokens, segments, positions, sep_indices, labels, weights, att, co = (torch.cat(c, 0) for c in cols)
+        for a_, b_ in zip((tokens, segments, positions, sep_indices, labels, weights, att, co),
+                          (torch.cat(c, 0) for c in ocols)):
+            assert torch.equal(a_, b_), "oracle encode() mismatch"
+        target = torch.from_numpy(np.random.dirichlet(np.ones(1601), size=37).astype(np.float32))
+        f2, l2, im2, tgt2, img_label = du.encode_image_input(feats.numpy(), 37, loc.numpy(), target.numpy(),
+                                                             max_regions=37, mask_prob=0.15)
+        b = {"tokens": tokens, "segments": segments, "positions": positions, "sep_indices": sep_indices, "mask": labels,
+             "weights": weights, "txt_attention_mask": att, "co_attention_mask": co.unsqueeze(1).repeat(1, 37, 1),
+             "image_feat": f2.unsqueeze(0).expand(6, -1, -1).contiguous(),
+             "image_loc": l2.unsqueeze(0).expand(6, -1, -1).contiguous(),
+             "image_mask": im2.unsqueeze(0).expand(6, -1).contiguous()}
+        nsl = torch.LongTensor(neg)
+        extras = dict(next_sentence_label=nsl, image_label=img_label.unsqueeze(0).expand(6, -1).contiguous(),
+                      image_target=tgt2.unsqueeze(0).expand(6, -1, -1).contiguous(),
+                      nsp_weight=torch.FloatTensor([[5.0, 1.0]]))
+        model = get_model(1, True)
+        lm_loss, img_loss, nsp_loss, nsp, lm = call_reference(model, b, extras)
+        save("train6_perturbed", weight_seed=np.array(1), perturbed=np.array(True), **pack_inputs(b),
+             image_feat=f2.numpy(), image_loc=l2.numpy(), image_mask=im2.numpy(),
+             next_sentence_label=nsl.numpy(), image_label=img_label.numpy(), image_target=tgt2.numpy(),
+             nsp_weight=np.array([[5.0, 1.0]], dtype=np.float32),
+             lm_loss=lm_loss.numpy(), img_loss=img_loss.numpy(), nsp_loss=nsp_loss.numpy(), nsp_scores=nsp.numpy())
+
+    # ---------------------------------------------------------------- config 1: 100 candidates, ranking metrics
+    for name, seed, perturbed in (("gen100_default", 0, False),):
+        if not want(name):
+            continue
+        b = ref_batch(du, context, answers, feats, loc, image_mask, du.encode_input_gen, seed=7)
+        model = get_model(seed, perturbed)
+        scores, nsps = [], []
+        for s in range(0, 100, 25):                                  # chunks of 25
+            bb = {k: v[s:s + 25] for k, v in b.items()}
+            _, _, _, nsp, lm = call_reference(model, bb)
+            scores.append(val_lm_scores(lm, bb["mask"])[0])
+            nsps.append(nsp)
+        score = torch.cat(scores)
+        ranks = vm.scores_to_ranks(score.view(1, 1, 100).clone())
+        sm = vm.SparseGTMetrics()
+        sm.observe(score.view(1, 1, 100), torch.zeros(1, 1, dtype=torch.long))   # gt option is index 0
+        rel = torch.from_numpy(np.random.RandomState(5).choice([0, 0, 0, 0.2, 0.4, 0.6, 0.8, 1.0], size=100)
+                               .astype(np.float32)).view(1, 100)
+        rel[0, 0] = 1.0
+        nd = vm.NDCG()
+        # NDCG.observe squeezes a batch of one away (visdial_metrics.py:145); val_lm feeds 2 images per batch
+        nd.observe(score.view(1, 100).repeat(2, 1), rel.repeat(2, 1))
+        metrics = {**{k: v for k, v in sm.retrieve().items() if "_round_" not in k}, **nd.retrieve()}
+        assert torch.equal(om.scores_to_ranks(score.view(1, 1, 100)), ranks)
+        mine = {**om.sparse_metrics(score.view(1, 1, 100), torch.zeros(1, 1, dtype=torch.long)),
+                "ndcg": om.ndcg(score.view(1, 100), rel)}
+        for k in metrics:
+            assert abs(metrics[k] - mine[k]) < 1e-6, (k, metrics[k], mine[k])
+        srt = score.sort(descending=True)[0]
+        print(name, "metrics", metrics, "min adjacent gap", float((srt[:-1] - srt[1:]).min()))
+        save(name, weight_seed=np.array(seed), perturbed=np.array(perturbed), **pack_inputs(b), **image_np,
+             seq_score=score.numpy(), nsp_scores=torch.cat(nsps).numpy(), ranks=ranks.view(100).numpy(),
+             relevance=rel.numpy(), metric_names=np.array(sorted(metrics)),
+             metric_values=np.array([metrics[k] for k in sorted(metrics)], dtype=np.float64))
+
+
+if __name__ == "__main__":
+    main()

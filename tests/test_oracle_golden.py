@@ -1,0 +1,100 @@
+"""CPU: the oracle restatement against fixtures produced by the unmodified reference (tests/golden/)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state_dict, load_golden
+from oracle import encode_inputs as enc
+from oracle import vilbert_oracle as vo
+from oracle import visdial_metrics as om
+
+# the oracle calls the same ATen CPU ops as the reference in the same order; only GEMM blocking may differ
+TOL = 2e-5
+
+
+def _run(cfg, g, batch, **kw):
+    sd = golden_state_dict(cfg, g["weight_seed"], g["perturbed"])
+    with torch.no_grad():
+        return vo.forward(sd, cfg, batch["tokens"], batch["image_feat"], batch["image_loc"], batch["segments"],
+                          batch["positions"], batch["txt_attention_mask"], batch["image_mask"],
+                          batch["co_attention_mask"], masked_lm_labels=batch["mask"], lm_weight=batch["weights"], **kw)
+
+
+@pytest.mark.parametrize("name", ["gen8_perturbed", "gen8_default"])
+def test_generative_scores_match_reference(full_cfg, name):
+    g, batch = load_golden(name)
+    taps = {}
+    out = _run(full_cfg, g, batch, taps=taps)
+    assert np.array_equal(out["token_rows"].numpy(), g["token_rows"])
+    np.testing.assert_allclose(out["token_logp"].numpy(), g["token_logp"], atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["token_ul"].numpy(), g["token_ul"], atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["seq_score"].numpy(), g["seq_score"], atol=5 * TOL, rtol=0)
+    np.testing.assert_allclose(out["nsp_scores"].numpy(), g["nsp_scores"], atol=TOL, rtol=0)
+    if "tap_txt_rows" in g:   # intermediate activations of sequence 0 (bisecting aid, pins every layer)
+        trows, irows = g["tap_txt_rows"], g["tap_img_rows"]
+        valid = trows < int(batch["txt_attention_mask"][0, 0].sum())      # pad rows are garbage-by-design
+        for k in [k for k in g if k.startswith("tap.") and k not in ("tap_txt_rows", "tap_img_rows")]:
+            key = k[4:]
+            if key.endswith(".img") or key.startswith("v"):
+                mine = taps[key if key.endswith(".img") else key + ".img"][0][irows]
+                ref = g[k]
+            else:
+                mine = taps[key if key.endswith(".txt") else key + ".txt"][0][trows][valid]
+                ref = g[k][valid]
+            np.testing.assert_allclose(mine.numpy(), ref, atol=1e-4, rtol=0, err_msg=k)
+
+
+def test_full_logits_path_equals_gathered_path(full_cfg):
+    g, batch = load_golden("gen8_perturbed")
+    b2 = {k: v[:2] for k, v in batch.items()}
+    sd = golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+    s_full, _, t_full = vo.score_candidates(sd, full_cfg, b2, chunk=2, full_logits=True)
+    np.testing.assert_allclose(s_full.numpy(), g["seq_score"][:2], atol=5 * TOL, rtol=0)
+
+
+def test_discriminative_nsp_matches_reference(full_cfg):
+    g, batch = load_golden("dis8_perturbed")
+    out = _run(full_cfg, g, batch)
+    np.testing.assert_allclose(out["nsp_scores"].numpy(), g["nsp_scores"], atol=TOL, rtol=0)
+    np.testing.assert_allclose(torch.softmax(out["nsp_scores"], 1)[:, 0].numpy(), g["nsp_prob0"], atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["token_logp"].numpy(), g["token_logp"], atol=TOL, rtol=0)
+
+
+def test_training_losses_match_reference(full_cfg):
+    g, batch = load_golden("train6_perturbed")
+    n = batch["tokens"].shape[0]
+    out = _run(full_cfg, g, batch,
+               next_sentence_label=torch.from_numpy(g["next_sentence_label"]),
+               image_label=torch.from_numpy(g["image_label"]).unsqueeze(0).expand(n, -1),
+               image_target=torch.from_numpy(g["image_target"]).unsqueeze(0).expand(n, -1, -1),
+               nsp_weight=torch.from_numpy(g["nsp_weight"]))
+    np.testing.assert_allclose(out["lm_loss"].item(), g["lm_loss"].item(), atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["nsp_loss"].item(), g["nsp_loss"].item(), atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["img_loss"].item(), g["img_loss"].item(), atol=TOL, rtol=0)
+
+
+def test_encoders_reproduce_reference_tensors():
+    """oracle.encode_inputs regenerates the committed reference-made inputs from the same RNG stream."""
+    g, batch = load_golden("gen8_default")
+    rng = np.random.RandomState(1234)
+    context, answers = enc.synth_round(rng, n_candidates=100)
+    feats, loc, image_mask = enc.synth_image(rng)
+    for j, n in enumerate([1, 2, 3, 4, 5, 6, 7, 4]):
+        answers[j] = rng.randint(1000, 30522, size=n).tolist()
+    r = np.random.RandomState(7)
+    b = enc.build_batch(context, answers[:8], feats, loc, image_mask, mode="gen", rng=r)
+    for k in ("tokens", "segments", "positions", "sep_indices", "mask", "weights"):
+        assert torch.equal(b[k], batch[k]), k
+    assert torch.equal(b["txt_attention_mask"].bool(), batch["txt_attention_mask"].bool())
+    assert torch.equal(b["co_attention_mask"], batch["co_attention_mask"])
+    np.testing.assert_array_equal(b["image_feat"][0].numpy(), g["image_feat"])
+
+
+def test_rank_metrics_on_golden_scores():
+    g, _ = load_golden("gen100_default")
+    score = torch.from_numpy(g["seq_score"])
+    assert np.array_equal(om.scores_to_ranks(score.view(1, 1, 100)).view(100).numpy(), g["ranks"])
+    mine = {**om.sparse_metrics(score.view(1, 1, 100), torch.zeros(1, 1, dtype=torch.long)),
+            "ndcg": om.ndcg(score.view(1, 100), torch.from_numpy(g["relevance"]))}
+    for k, v in zip(g["metric_names"], g["metric_values"]):
+        assert abs(mine[str(k)] - v) < 1e-6, k
