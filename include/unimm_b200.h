@@ -1,0 +1,150 @@
+/*
+ * unimm_b200 — C ABI of the B200 (sm_100a) generative-scoring hot path of UniMM-UL.
+ *
+ * This library replaces, behind the reference's own boundary, the body of
+ *   VisualDialogEncoder.forward                      (reference models/visual_dialog_encoder.py:18-50)
+ *   -> BertForMultiModalPreTraining.forward           (reference models/vilbert_dialog.py:1519-1626)
+ *   -> BertModel.forward / BertEncoder.forward        (reference models/vilbert_dialog.py:1359-1472, :817-937)
+ * plus the scoring rule of val_lm.py:131-137.  The reference has no FFI of its own (it is eager
+ * PyTorch); the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md, which is
+ * exactly what unimm_b200/_lib.py does.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure; unimm_last_error() then
+ * returns a thread-local message.  No exceptions cross the ABI.  All buffers are caller-owned.
+ * Pointers named d_* are device pointers on the engine's device, h_* are host pointers.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  One engine per device; an engine is
+ * not re-entrant (one forward at a time), distinct engines are independent.
+ */
+#ifndef UNIMM_B200_H
+#define UNIMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIMM_ABI_VERSION 1
+
+typedef struct unimm_engine unimm_engine_t;
+
+/* compute precision of the projections / attention */
+enum { UNIMM_PREC_FP32 = 0, /* CUDA-core fp32: the <=1e-4 parity mode            */
+       UNIMM_PREC_BF16 = 1  /* tcgen05 bf16 x bf16 -> fp32 (TMEM): throughput mode */ };
+
+/* Mirrors the fields of the reference's BertConfig that the hot path reads
+ * (models/vilbert_dialog.py:131-247, config/bert_base_6layer_6conect.json). */
+typedef struct {
+    int32_t vocab_size, hidden_size, num_hidden_layers, num_attention_heads, intermediate_size;
+    int32_t max_position_embeddings, type_vocab_size;
+    int32_t v_feature_size, v_target_size, v_hidden_size, v_num_hidden_layers, v_num_attention_heads, v_intermediate_size;
+    int32_t bi_hidden_size, bi_num_attention_heads;
+    int32_t num_connections;
+    int32_t v_biattention_id[16];
+    int32_t t_biattention_id[16];
+    int32_t seq_len;      /* S: text positions per sequence (reference max_seq_len, 256)  */
+    int32_t num_regions;  /* R: image regions per sequence incl. the global one (37)      */
+} unimm_config_t;
+
+/* The 4 integers per sequence that regenerate the reference's dense masks
+ * (utils/data_utils.py:149-210 generative, :353-354 discriminative):
+ * mode 0 = generative, 1 = discriminative; ctx = L - last_len; L = orig_length; last_len = answer length + 1. */
+typedef struct {
+    int32_t mode, ctx, L, last_len;
+} unimm_seq_desc_t;
+
+/* One forward call = one chunk of B sequences (B <= max_sequences given at creation).
+ * Argument meaning follows VisualDialogEncoder.forward (visual_dialog_encoder.py:18-20). */
+typedef struct {
+    int32_t B;
+    const int64_t* d_input_ids;        /* [B,S]                                                         */
+    const int64_t* d_token_type_ids;   /* [B,S]  segments                                               */
+    const int64_t* d_position_ids;     /* [B,S]  token_position_ids                                     */
+    const unimm_seq_desc_t* d_desc;    /* [B]    replaces attention_mask [B,S,S] + co_attention_mask     */
+    const float* d_image_feat;         /* [U,R,v_feature_size]                                          */
+    const float* d_image_loc;          /* [U,R,5]                                                       */
+    const float* d_image_mask;         /* [U,R]  image_attention_mask, values in {0,1}                  */
+    const int32_t* d_feat_index;       /* [B] sequence -> image slot u in [0,U); NULL = identity (U = B) */
+    const int64_t* d_masked_lm_labels; /* [B,S]  -1 = ignore; may be NULL when n_lm_rows == 0           */
+    const int32_t* d_lm_rows;          /* [n_lm_rows] sorted flat positions b*S+s with label != -1      */
+    int32_t n_lm_rows;
+    /* training targets: the loss branch runs iff labels, next_sentence_label and image_target are all
+     * non-NULL (visual_dialog_encoder.py:28-29) */
+    const int64_t* d_lm_weight;           /* [B,S] or NULL (plain masked-LM CE, vilbert_dialog.py:1601) */
+    const int64_t* d_next_sentence_label; /* [B] or NULL                                                */
+    const int64_t* d_image_label;         /* [B,R] or NULL                                              */
+    const float* d_image_target;          /* [B,R,v_target_size] or NULL                                */
+    const float* d_nsp_weight;            /* [2] or NULL (= [1,1])                                      */
+} unimm_batch_t;
+
+/* Every output pointer is optional (NULL = not wanted). */
+typedef struct {
+    float* d_seq_score;          /* [B]    sum of answer-token log-probs (val_lm.py:131-136)             */
+    float* d_token_logp;         /* [B,S]  log p(label) at labelled positions, 0 elsewhere (= -nll)      */
+    float* d_token_ul;           /* [B,S]  log(max(1-p(label),1e-6)) (vilbert_dialog.py:1587), 0 elsewhere */
+    float* d_nsp_scores;         /* [B,2]  seq_relationship_score                                        */
+    float* d_losses;             /* [8]    [0]=masked_lm_loss [1]=masked_img_loss [2]=nsp_loss, rest scratch */
+    float* d_sequence_output_t;  /* [B,S,hidden_size] final text hidden states                           */
+    float* d_sequence_output_v;  /* [B,R,v_hidden_size]                                                  */
+    float* d_prediction_scores_t;/* [B,S,vocab] full logits — compatibility path only, 31 MB / sequence  */
+} unimm_outputs_t;
+
+const char* unimm_last_error(void);
+int unimm_abi_version(void);
+
+int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_sequences, unimm_engine_t** out);
+int unimm_destroy(unimm_engine_t* e);
+/* Accepts the reference checkpoint keys (with or without the "bert_pretrained." prefix); h_data is fp32. */
+int unimm_load_weight(unimm_engine_t* e, const char* name, const float* h_data, const int64_t* shape, int ndim);
+/* Packs (QKV concatenation, bf16 casts) and verifies that every key the forward needs was loaded. */
+int unimm_finalize_weights(unimm_engine_t* e);
+int unimm_forward(unimm_engine_t* e, const unimm_batch_t* batch, const unimm_outputs_t* out, void* stream);
+
+/* Boundary helper: check that the caller's dense masks equal what the descriptors regenerate.
+ * d_txt_mask: [B,S,S] elements of txt_elem_bytes (1 = bool/uint8, 8 = int64); d_co_mask: [B,R,S] int64 or NULL.
+ * *d_mismatch (device int) is set to 1 on any difference. */
+int unimm_verify_masks(const unimm_seq_desc_t* d_desc, int B, int S, int R, const void* d_txt_mask, int txt_elem_bytes,
+                       const int64_t* d_co_mask, int* d_mismatch, void* stream);
+
+/* Host-buffer scoring entry (the end-to-end path of bench.py): stages the inputs through pinned memory,
+ * copies host->device, runs unimm_forward, copies seq_score [B] and nsp_scores [B,2] back, synchronises.
+ * Host arrays have the shapes of unimm_batch_t; U = number of distinct image slots. */
+typedef struct {
+    int32_t B, U;
+    const int64_t* h_input_ids;
+    const int64_t* h_token_type_ids;
+    const int64_t* h_position_ids;
+    const int64_t* h_masked_lm_labels;
+    const unimm_seq_desc_t* h_desc;
+    const float* h_image_feat;
+    const float* h_image_loc;
+    const float* h_image_mask;
+    const int32_t* h_feat_index; /* NULL = identity */
+} unimm_host_batch_t;
+int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream);
+
+/* counters for bench.py: kernels launched by this library since the last reset */
+int64_t unimm_launch_count(void);
+void unimm_reset_launch_count(void);
+
+/* ---- single-kernel entry points (used by tests/ to check each kernel against the oracle) ---- */
+int unimm_k_gemm_bf16(const void* d_A_bf16, int lda, const void* d_W_bf16, int ldw, int M, int N, int K, const float* d_bias,
+                      const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_bf16,
+                      int ldo_bf16, int tile_n, int max_ctas, void* stream);
+int unimm_k_gemm_f32(const float* d_A, int lda, const float* d_W, int ldw, int M, int N, int K, const float* d_bias,
+                     const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* stream);
+int unimm_k_lm_head_bf16(const void* d_H_bf16, int ldh, const void* d_E_bf16, int lde, int rows, int V, int K,
+                         const float* d_bias, const int32_t* d_labels, float* d_partials_scratch, float* d_label_logit_scratch,
+                         float* d_logp, float* d_ul, void* stream);
+int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
+                      void* d_y_bf16, void* stream);
+int unimm_k_cast_bf16(const float* d_src, void* d_dst_bf16, int64_t n, void* stream);
+/* is_bf16 = 0: fp32 tensors, 1: bf16 tensors.  impl: 0 = CUDA-core kernel, 1 = tensor-core kernel (bf16 only). */
+int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,
+                      int heads, int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc,
+                      const float* d_key_mask, int is_bf16, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIMM_B200_H */

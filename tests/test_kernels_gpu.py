@@ -1,0 +1,222 @@
+"""GPU: each CUDA kernel, called through the C ABI, against a plain PyTorch fp32 statement of the same op."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from unimm_b200 import _lib  # noqa: E402
+from unimm_b200._lib import check, lib, ptr  # noqa: E402
+from unimm_b200.descriptors import dense_co_mask, dense_text_mask  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+
+
+def gelu(x):
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ----------------------------------------------------------------------------------------------- fp32 GEMM
+@pytest.mark.parametrize("M,N,K,act,res", [(256, 768, 768, 0, True), (300, 3072, 768, 1, False), (37 * 3, 1024, 2048, 0, True),
+                                           (130, 1601, 1024, 0, False), (64, 30522, 768, 0, False)])
+def test_gemm_f32(M, N, K, act, res):
+    A, W, b = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3)
+    R = rnd(M, N, seed=4) if res else None
+    out = torch.empty(M, N, device=DEV)
+    check(lib.unimm_k_gemm_f32(ptr(A), K, ptr(W), K, M, N, K, ptr(b), ptr(R), N, act, ptr(out), N, stream()))
+    ref = A.double() @ W.double().t() + b.double()
+    if act == 1:
+        ref = gelu(ref)
+    if res:
+        ref = ref + R.double()
+    err = (out.double() - ref).abs().max().item()
+    print(f"gemm_f32 {M}x{N}x{K} act={act} res={res}: max abs err {err:.3e}")
+    assert err < 2e-4
+
+
+# ----------------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,act,res,tile_n", [
+    (128, 256, 64, 0, False, 256),       # one tile, one k-block: descriptor / swizzle sanity
+    (128, 128, 128, 0, False, 128),
+    (256, 768, 768, 0, True, 256),       # out-proj shape with residual
+    (512, 2304, 768, 0, False, 256),     # QKV
+    (300, 3072, 768, 1, False, 256),     # FFN-1 + GELU, ragged M
+    (256, 768, 3072, 0, True, 256),      # FFN-2, long K
+    (37 * 5, 1024, 2048, 0, True, 128),  # image embedding shape, ragged M
+    (130, 1601, 1024, 0, False, 128),    # image decoder: ragged N
+    (40000, 768, 768, 0, False, 256),    # many tiles per CTA: exercises ring + accumulator phases
+])
+def test_gemm_umma_bf16(M, N, K, act, res, tile_n):
+    A = rnd(M, K, seed=1).to(torch.bfloat16)
+    W = rnd(N, K, scale=0.05, seed=2).to(torch.bfloat16)
+    b = rnd(N, seed=3)
+    R = rnd(M, N, seed=4) if res else None
+    o32 = torch.zeros(M, N, device=DEV)
+    o16 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    check(lib.unimm_k_gemm_bf16(ptr(A), K, ptr(W), K, M, N, K, ptr(b), ptr(R), N, act, ptr(o32), N, ptr(o16), N, tile_n, 0,
+                                stream()))
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    if act == 1:
+        ref = gelu(ref)
+    if res:
+        ref = ref + R.double()
+    err = (o32.double() - ref).abs().max().item()
+    err16 = (o16.double() - ref).abs().max().item()
+    print(f"gemm_umma {M}x{N}x{K} act={act} res={res}: fp32-out err {err:.3e}, bf16-out err {err16:.3e}")
+    assert err < 2e-3 * max(1.0, math.sqrt(K / 768))     # operands are exactly representable: only fp32 accumulation order
+    assert err16 < 0.05 * max(1.0, ref.abs().max().item() / 4)
+
+
+def test_gemm_umma_persistent_few_ctas():
+    """Force 3 CTAs over 60 tiles so every CTA wraps the smem ring and both accumulators many times."""
+    M, N, K = 128 * 10, 256 * 6, 320
+    A, W = rnd(M, K, seed=5).to(torch.bfloat16), rnd(N, K, scale=0.05, seed=6).to(torch.bfloat16)
+    o32 = torch.zeros(M, N, device=DEV)
+    check(lib.unimm_k_gemm_bf16(ptr(A), K, ptr(W), K, M, N, K, None, None, 0, 0, ptr(o32), N, None, 0, 256, 3, stream()))
+    ref = A.double() @ W.double().t()
+    assert (o32.double() - ref).abs().max().item() < 2e-3
+
+
+def test_lm_head_lse_bf16():
+    rows, V, K = 200, 30522, 768
+    Hm = rnd(rows, K, seed=7).to(torch.bfloat16)
+    E = rnd(V, K, scale=0.02, seed=8).to(torch.bfloat16)
+    bias = rnd(V, scale=0.02, seed=9)
+    labels = torch.randint(0, V, (rows,), generator=torch.Generator().manual_seed(3)).to(torch.int32)
+    labels[0], labels[1] = 0, V - 1
+    labels = labels.to(DEV)
+    tiles = (V + 255) // 256
+    partials = torch.zeros(rows, tiles, 2, device=DEV)
+    lab_logit = torch.zeros(rows, device=DEV)
+    logp, ul = torch.zeros(rows, device=DEV), torch.zeros(rows, device=DEV)
+    check(lib.unimm_k_lm_head_bf16(ptr(Hm), K, ptr(E), K, rows, V, K, ptr(bias), ptr(labels), ptr(partials), ptr(lab_logit),
+                                   ptr(logp), ptr(ul), stream()))
+    logits = Hm.double() @ E.double().t() + bias.double()
+    ref = torch.log_softmax(logits, -1).gather(1, labels.long()[:, None])[:, 0]
+    ref_ul = torch.log(torch.clamp(1.0 - torch.softmax(logits, -1), min=1e-6)).gather(1, labels.long()[:, None])[:, 0]
+    print("lm head: logp err", (logp.double() - ref).abs().max().item(), "ul err", (ul.double() - ref_ul).abs().max().item())
+    assert (logp.double() - ref).abs().max().item() < 1e-4
+    assert (ul.double() - ref_ul).abs().max().item() < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("H", [768, 1024])
+def test_layernorm(H):
+    rows = 1000
+    x, g, b = rnd(rows, H, scale=3.0, seed=1) + 0.5, 1 + 0.1 * rnd(H, seed=2), 0.1 * rnd(H, seed=3)
+    y32 = torch.empty(rows, H, device=DEV)
+    y16 = torch.empty(rows, H, device=DEV, dtype=torch.bfloat16)
+    check(lib.unimm_k_layernorm(ptr(x), H, rows, H, ptr(g), ptr(b), ptr(y32), ptr(y16), stream()))
+    ref = torch.nn.functional.layer_norm(x.double(), (H,), g.double(), b.double(), 1e-12)
+    assert (y32.double() - ref).abs().max().item() < 2e-5
+    assert (y16.double() - ref).abs().max().item() < 0.03
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def ref_attention(q, k, v, heads, allow):
+    """softmax(QK^T/sqrt(d) + (1-allow)*-10000) V in fp64, exactly the reference's additive form."""
+    B, Sq, HD = q.shape
+    d = HD // heads
+    qh = q.double().view(B, Sq, heads, d).permute(0, 2, 1, 3)
+    kh = k.double().view(B, -1, heads, d).permute(0, 2, 1, 3)
+    vh = v.double().view(B, -1, heads, d).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(d) + (1.0 - allow.double())[:, None] * -10000.0
+    return (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B, Sq, HD)
+
+
+def make_desc():
+    # gen: (ctx, L, last) incl. T == 256 edge; dis rows
+    rows = [(0, 239, 247, 8), (0, 239, 241, 2), (0, 30, 35, 5), (0, 240, 248, 8), (1, 0, 200, 0), (1, 0, 256, 0), (0, 2, 4, 2)]
+    return torch.tensor(rows, dtype=torch.int32, device=DEV)
+
+
+@pytest.mark.parametrize("is_bf16,impl", [(0, 0), (1, 0), (1, 1)])
+def test_text_self_attention(is_bf16, impl):
+    desc = make_desc()
+    B, S, heads, d = desc.shape[0], 256, 12, 64
+    H = heads * d
+    qkv = rnd(B * S, 3 * H, seed=11)
+    allow = dense_text_mask(desc, S)
+    valid = allow.any(-1)                                  # padding rows are garbage-by-design in the reference
+    if is_bf16:
+        qkv = qkv.to(torch.bfloat16)
+    out = torch.zeros(B * S, H, device=DEV, dtype=qkv.dtype)
+    e = qkv.element_size()
+    base = qkv.data_ptr()
+    check(lib.unimm_k_attention(C.c_void_p(base), 3 * H, C.c_void_p(base + e * H), 3 * H, C.c_void_p(base + 2 * e * H), 3 * H,
+                                ptr(out), H, B, heads, d, S, S, _lib.MASK_TEXT_SELF, ptr(desc), None, is_bf16, impl, stream()))
+    q3 = qkv.view(B, S, 3 * H)
+    ref = ref_attention(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], heads, allow)
+    err = (out.view(B, S, H).double() - ref)[valid].abs().max().item()
+    print(f"text self-attention bf16={is_bf16} impl={impl}: max err on valid rows {err:.3e}")
+    assert err < (3e-2 if is_bf16 else 2e-5)
+    assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("is_bf16,impl", [(0, 0), (1, 0), (1, 1)])
+def test_cross_and_image_attention(is_bf16, impl):
+    desc = make_desc()
+    B, S, R, heads, d = desc.shape[0], 256, 37, 8, 128
+    H = heads * d
+    dt = torch.bfloat16 if is_bf16 else torch.float32
+    tol = 3e-2 if is_bf16 else 2e-5
+    qkv_t, qkv_v = rnd(B * S, 3 * H, seed=21).to(dt), rnd(B * R, 3 * H, seed=22).to(dt)
+    e = qkv_t.element_size()
+    img_mask = torch.ones(B, R, device=DEV)
+    img_mask[1, 30:] = 0
+    img_mask[2, 1:] = 0
+    # text -> image (key vector mask)
+    o1 = torch.zeros(B * S, H, device=DEV, dtype=dt)
+    check(lib.unimm_k_attention(ptr(qkv_t), 3 * H, C.c_void_p(qkv_v.data_ptr() + e * H), 3 * H,
+                                C.c_void_p(qkv_v.data_ptr() + 2 * e * H), 3 * H, ptr(o1), H, B, heads, d, S, R,
+                                _lib.MASK_KEY_VECTOR, None, ptr(img_mask), is_bf16, impl, stream()))
+    t3, v3 = qkv_t.view(B, S, 3 * H), qkv_v.view(B, R, 3 * H)
+    ref1 = ref_attention(t3[..., :H], v3[..., H:2 * H], v3[..., 2 * H:], heads, img_mask[:, None, :].expand(B, S, R))
+    err1 = (o1.view(B, S, H).double() - ref1).abs().max().item()
+    # image -> text (co interval)
+    o2 = torch.zeros(B * R, H, device=DEV, dtype=dt)
+    check(lib.unimm_k_attention(ptr(qkv_v), 3 * H, C.c_void_p(qkv_t.data_ptr() + e * H), 3 * H,
+                                C.c_void_p(qkv_t.data_ptr() + 2 * e * H), 3 * H, ptr(o2), H, B, heads, d, R, S,
+                                _lib.MASK_CO_INTERVAL, ptr(desc), None, is_bf16, impl, stream()))
+    co = dense_co_mask(desc, S).bool()
+    ref2 = ref_attention(v3[..., :H], t3[..., H:2 * H], t3[..., 2 * H:], heads, co[:, None, :].expand(B, R, S))
+    err2 = (o2.view(B, R, H).double() - ref2).abs().max().item()
+    # image self-attention
+    o3 = torch.zeros(B * R, H, device=DEV, dtype=dt)
+    check(lib.unimm_k_attention(ptr(qkv_v), 3 * H, C.c_void_p(qkv_v.data_ptr() + e * H), 3 * H,
+                                C.c_void_p(qkv_v.data_ptr() + 2 * e * H), 3 * H, ptr(o3), H, B, heads, d, R, R,
+                                _lib.MASK_KEY_VECTOR, None, ptr(img_mask), is_bf16, impl, stream()))
+    ref3 = ref_attention(v3[..., :H], v3[..., H:2 * H], v3[..., 2 * H:], heads, img_mask[:, None, :].expand(B, R, R))
+    err3 = (o3.view(B, R, H).double() - ref3).abs().max().item()
+    print(f"cross attention bf16={is_bf16} impl={impl}: t->i {err1:.3e}  i->t {err2:.3e}  i self {err3:.3e}")
+    assert max(err1, err2, err3) < tol
+
+
+def test_verify_masks_kernel():
+    desc = make_desc()
+    B, S, R = desc.shape[0], 256, 37
+    txt = dense_text_mask(desc, S).contiguous()
+    co = dense_co_mask(desc, S).unsqueeze(1).repeat(1, R, 1).contiguous()
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    check(lib.unimm_verify_masks(ptr(desc), B, S, R, ptr(txt.to(torch.uint8)), 1, ptr(co), ptr(flag), stream()))
+    assert flag.item() == 0
+    txt2 = txt.clone()
+    txt2[3, 100, 5] = ~txt2[3, 100, 5]
+    check(lib.unimm_verify_masks(ptr(desc), B, S, R, ptr(txt2.long().contiguous()), 8, ptr(co), ptr(flag), stream()))
+    assert flag.item() == 1

@@ -1,0 +1,169 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors the unmodified reference
+produced (tests/golden/) — fp32 mode to 1e-4, bf16 mode to 2e-2 (the tolerances BASELINE.json states) —
+and against the oracle on size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state_dict, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from unimm_b200.descriptors import descriptors_from_masks  # noqa: E402
+from unimm_b200.engine import Engine  # noqa: E402
+from unimm_b200.visual_dialog_encoder import VisualDialogEncoder  # noqa: E402
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}   # abs, per-candidate sequence log-likelihood (BASELINE.json north_star)
+_ENGINES = {}
+
+
+def get_engine(cfg, g, precision, max_sequences=128):
+    key = (int(g["weight_seed"]), bool(g["perturbed"]), precision)
+    if key not in _ENGINES:
+        for e in _ENGINES.values():
+            e.close()
+        _ENGINES.clear()
+        torch.cuda.empty_cache()
+        _ENGINES[key] = Engine(cfg, golden_state_dict(cfg, g["weight_seed"], g["perturbed"]), precision=precision,
+                               max_sequences=max_sequences)
+    return _ENGINES[key]
+
+
+def run_engine(eng, batch, want, **extra):
+    desc = descriptors_from_masks(batch["txt_attention_mask"], batch["co_attention_mask"])
+    return eng.forward(batch["tokens"], batch["segments"], batch["positions"], desc, batch["image_feat"], batch["image_loc"],
+                       batch["image_mask"], masked_lm_labels=batch["mask"], want=want, **extra)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["gen8_perturbed", "gen8_default"])
+def test_generative_scores(full_cfg, name, precision):
+    g, batch = load_golden(name)
+    eng = get_engine(full_cfg, g, precision)
+    o = run_engine(eng, batch, ("seq_score", "token_logp", "token_ul", "nsp_scores", "sequence_output_t", "sequence_output_v"))
+    seq = o["seq_score"].cpu().numpy()
+    rows = g["token_rows"]
+    tl = o["token_logp"].cpu().numpy()[rows[:, 0], rows[:, 1]]
+    tu = o["token_ul"].cpu().numpy()[rows[:, 0], rows[:, 1]]
+    if "tap.t11" in g:       # final-layer activations of sequence 0 (bisecting aid)
+        trows = g["tap_txt_rows"]
+        T = int(batch["txt_attention_mask"][0, 0].sum())
+        valid = trows < T
+        x = o["sequence_output_t"][0].cpu().numpy()[trows][valid]
+        print(f"[{precision}] final text hidden err {np.abs(x - g['tap.t11'][valid]).max():.3e}; image "
+              f"{np.abs(o['sequence_output_v'][0].cpu().numpy()[g['tap_img_rows']] - g['tap.v5']).max():.3e}")
+    print(f"[{precision}] {name}: seq_score err {np.abs(seq - g['seq_score']).max():.3e}  token_logp err "
+          f"{np.abs(tl - g['token_logp']).max():.3e}  nsp err {np.abs(o['nsp_scores'].cpu().numpy() - g['nsp_scores']).max():.3e}")
+    np.testing.assert_allclose(seq, g["seq_score"], atol=TOL[precision], rtol=0)
+    np.testing.assert_allclose(tl, g["token_logp"], atol=TOL[precision], rtol=0)
+    np.testing.assert_allclose(tu, g["token_ul"], atol=TOL[precision], rtol=0)
+    np.testing.assert_allclose(o["nsp_scores"].cpu().numpy(), g["nsp_scores"], atol=TOL[precision], rtol=0)
+    # positions without a label carry exactly 0 (val_lm's nll with ignore_index)
+    mask = np.ones_like(o["token_logp"].cpu().numpy(), dtype=bool)
+    mask[rows[:, 0], rows[:, 1]] = False
+    assert not o["token_logp"].cpu().numpy()[mask].any()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_discriminative_nsp(full_cfg, precision):
+    g, batch = load_golden("dis8_perturbed")
+    eng = get_engine(full_cfg, g, precision)
+    o = run_engine(eng, batch, ("seq_score", "token_logp", "nsp_scores"))
+    nsp = o["nsp_scores"].cpu()
+    print(f"[{precision}] dis8: nsp err {np.abs(nsp.numpy() - g['nsp_scores']).max():.3e}")
+    np.testing.assert_allclose(nsp.numpy(), g["nsp_scores"], atol=TOL[precision], rtol=0)
+    np.testing.assert_allclose(torch.softmax(nsp, 1)[:, 0].numpy(), g["nsp_prob0"], atol=TOL[precision], rtol=0)
+    rows = g["token_rows"]
+    np.testing.assert_allclose(o["token_logp"].cpu().numpy()[rows[:, 0], rows[:, 1]], g["token_logp"], atol=TOL[precision], rtol=0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_losses(full_cfg, precision):
+    g, batch = load_golden("train6_perturbed")
+    eng = get_engine(full_cfg, g, precision)
+    n = batch["tokens"].shape[0]
+    o = run_engine(eng, batch, ("losses", "nsp_scores"), lm_weight=batch["weights"],
+                   next_sentence_label=torch.from_numpy(g["next_sentence_label"]),
+                   image_label=torch.from_numpy(g["image_label"]).unsqueeze(0).expand(n, -1).contiguous(),
+                   image_target=torch.from_numpy(g["image_target"]).unsqueeze(0).expand(n, -1, -1).contiguous(),
+                   nsp_weight=torch.from_numpy(g["nsp_weight"]))
+    lm, img, nsp = o["losses"][:3].cpu().numpy()
+    print(f"[{precision}] losses lm {lm:.6f}/{g['lm_loss'].item():.6f} img {img:.6f}/{g['img_loss'].item():.6f} "
+          f"nsp {nsp:.6f}/{g['nsp_loss'].item():.6f}")
+    tol = TOL[precision]
+    assert abs(lm - g["lm_loss"].item()) < tol
+    assert abs(img - g["img_loss"].item()) < tol
+    assert abs(nsp - g["nsp_loss"].item()) < tol
+
+
+def test_config1_ranking_fp32(full_cfg):
+    """100 candidates of one round: scores within 1e-4 and ranks / MRR / R@k / NDCG identical in fp32 mode."""
+    from oracle import visdial_metrics as om
+    g, batch = load_golden("gen100_default")
+    eng = get_engine(full_cfg, g, "fp32")
+    o = run_engine(eng, batch, ("seq_score",))
+    score = o["seq_score"].cpu()
+    err = np.abs(score.numpy() - g["seq_score"]).max()
+    print(f"[fp32] config 1: max seq_score err over 100 candidates {err:.3e}")
+    assert err < TOL["fp32"]
+    assert np.array_equal(om.scores_to_ranks(score.view(1, 1, 100)).view(100).numpy(), g["ranks"])
+    mine = {**om.sparse_metrics(score.view(1, 1, 100), torch.zeros(1, 1, dtype=torch.long)),
+            "ndcg": om.ndcg(score.view(1, 100), torch.from_numpy(g["relevance"]))}
+    for k, v in zip(g["metric_names"], g["metric_values"]):
+        assert mine[str(k)] == pytest.approx(v, abs=1e-9), k
+
+
+def test_config1_scores_bf16(full_cfg):
+    g, batch = load_golden("gen100_default")
+    eng = get_engine(full_cfg, g, "bf16")
+    score = run_engine(eng, batch, ("seq_score",))["seq_score"].cpu().numpy()
+    err = np.abs(score - g["seq_score"])
+    print(f"[bf16] config 1: seq_score err max {err.max():.3e} mean {err.mean():.3e}")
+    assert err.max() < TOL["bf16"]
+
+
+def test_drop_in_module_matches_reference_outputs(full_cfg):
+    """VisualDialogEncoder with the reference's forward signature and a reference-layout state dict."""
+    import torch.nn.functional as F
+    g, batch = load_golden("gen8_perturbed")
+    enc = VisualDialogEncoder(full_cfg, precision="fp32", max_sequences=4)
+    sd = golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+    enc.load_state_dict({"bert_pretrained." + k: v for k, v in sd.items()}, strict=True)
+    b = {k: v[:4] for k, v in batch.items()}
+    out = enc(b["tokens"], b["image_feat"], b["image_loc"], sep_indices=b["sep_indices"], sep_len=None,
+              token_type_ids=b["segments"], token_position_ids=b["positions"], masked_lm_labels=b["mask"],
+              attention_mask=b["txt_attention_mask"], next_sentence_label=None, output_nsp_scores=True, output_lm_scores=True,
+              image_attention_mask=b["image_mask"], co_attention_mask=b["co_attention_mask"], image_label=None,
+              image_target=None, nsp_weight=None, lm_weight=b["weights"])
+    assert out[0] is None and out[1] is None and out[2] is None and len(out) == 5
+    nsp, lm = out[3], out[4]
+    assert tuple(lm.shape) == (4, 256, full_cfg.vocab_size)
+    # val_lm.py:131-136 applied to OUR full logits
+    nll = F.cross_entropy(lm.view(-1, lm.shape[-1]), b["mask"].view(-1).to(lm.device), ignore_index=-1, reduction="none").view(4, 256)
+    np.testing.assert_allclose((-nll.sum(-1)).cpu().numpy(), g["seq_score"][:4], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(nsp.cpu().numpy(), g["nsp_scores"][:4], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(lm[0, g["token_rows"][0, 1], :64].cpu().numpy(), g["logits_row0_first64"], atol=1e-4, rtol=0)
+    # fast entry agrees with the compatibility path
+    fast = enc.score(b["tokens"], b["image_feat"], b["image_loc"], b["segments"], b["positions"], b["mask"], b["image_mask"],
+                     attention_mask=b["txt_attention_mask"], co_attention_mask=b["co_attention_mask"])
+    np.testing.assert_allclose(fast["seq_score"].cpu().numpy(), g["seq_score"][:4], atol=1e-4, rtol=0)
+
+
+def test_host_buffer_scoring_and_unit_sharing(full_cfg):
+    """unimm_score_host (pinned host arrays, one image block per unit) == per-sequence expanded inputs."""
+    from unimm_b200.engine import HostArrays
+    g, batch = load_golden("gen8_default")
+    eng = get_engine(full_cfg, g, "fp32")
+    desc = descriptors_from_masks(batch["txt_attention_mask"], batch["co_attention_mask"])
+    pin = lambda t: t.contiguous().pin_memory()
+    hb = HostArrays(pin(batch["tokens"]), pin(batch["segments"]), pin(batch["positions"]), pin(batch["mask"]), pin(desc),
+                    pin(batch["image_feat"][:1]), pin(batch["image_loc"][:1]), pin(batch["image_mask"][:1]),
+                    pin(torch.zeros(8, dtype=torch.int32)))
+    score = torch.zeros(8).pin_memory()
+    nsp = torch.zeros(8, 2).pin_memory()
+    eng.score_host(hb, score, nsp)
+    np.testing.assert_allclose(score.numpy(), g["seq_score"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(nsp.numpy(), g["nsp_scores"], atol=1e-4, rtol=0)

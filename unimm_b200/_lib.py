@@ -1,0 +1,106 @@
+"""ctypes binding of ``libunimm_b200.so`` (declarations mirror ``include/unimm_b200.h`` one to one).
+
+There is no fallback: if the shared library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C unimm_b200/csrc``) importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libunimm_b200.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+MASK_TEXT_SELF, MASK_KEY_VECTOR, MASK_CO_INTERVAL = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "vocab_size", "hidden_size", "num_hidden_layers", "num_attention_heads", "intermediate_size",
+        "max_position_embeddings", "type_vocab_size", "v_feature_size", "v_target_size", "v_hidden_size",
+        "v_num_hidden_layers", "v_num_attention_heads", "v_intermediate_size", "bi_hidden_size",
+        "bi_num_attention_heads", "num_connections")] + [
+        ("v_biattention_id", C.c_int32 * 16), ("t_biattention_id", C.c_int32 * 16),
+        ("seq_len", C.c_int32), ("num_regions", C.c_int32)]
+
+
+class SeqDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("ctx", C.c_int32), ("L", C.c_int32), ("last_len", C.c_int32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32),
+        ("d_input_ids", C.c_void_p), ("d_token_type_ids", C.c_void_p), ("d_position_ids", C.c_void_p),
+        ("d_desc", C.c_void_p), ("d_image_feat", C.c_void_p), ("d_image_loc", C.c_void_p),
+        ("d_image_mask", C.c_void_p), ("d_feat_index", C.c_void_p), ("d_masked_lm_labels", C.c_void_p),
+        ("d_lm_rows", C.c_void_p), ("n_lm_rows", C.c_int32),
+        ("d_lm_weight", C.c_void_p), ("d_next_sentence_label", C.c_void_p), ("d_image_label", C.c_void_p),
+        ("d_image_target", C.c_void_p), ("d_nsp_weight", C.c_void_p)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_seq_score", "d_token_logp", "d_token_ul", "d_nsp_scores", "d_losses", "d_sequence_output_t",
+        "d_sequence_output_v", "d_prediction_scores_t")]
+
+
+class HostBatch(C.Structure):
+    _fields_ = [("B", C.c_int32), ("U", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "h_input_ids", "h_token_type_ids", "h_position_ids", "h_masked_lm_labels", "h_desc", "h_image_feat",
+        "h_image_loc", "h_image_mask", "h_feat_index")]
+
+
+# every symbol include/unimm_b200.h declares: name -> (restype, argtypes)
+_P, _I, _F = C.c_void_p, C.c_int, C.c_void_p
+SYMBOLS = {
+    "unimm_last_error": (C.c_char_p, []),
+    "unimm_abi_version": (C.c_int, []),
+    "unimm_create": (C.c_int, [C.POINTER(Config), _I, _I, _I, C.POINTER(C.c_void_p)]),
+    "unimm_destroy": (C.c_int, [_P]),
+    "unimm_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
+    "unimm_finalize_weights": (C.c_int, [_P]),
+    "unimm_forward": (C.c_int, [_P, C.POINTER(Batch), C.POINTER(Outputs), _P]),
+    "unimm_verify_masks": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "unimm_score_host": (C.c_int, [_P, C.POINTER(HostBatch), _P, _P, _P]),
+    "unimm_launch_count": (C.c_int64, []),
+    "unimm_reset_launch_count": (None, []),
+    "unimm_k_gemm_bf16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "unimm_k_gemm_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
+    "unimm_k_lm_head_bf16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "unimm_k_layernorm": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "unimm_k_cast_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "unimm_k_attention": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
+}
+
+
+class UnimmError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built. Run `make -C unimm_b200/csrc` "
+            "(or __graft_entry__.build()). unimm_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise UnimmError(lib.unimm_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device/host address of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

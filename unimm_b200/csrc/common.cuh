@@ -1,0 +1,135 @@
+// Shared device/host helpers for the unimm_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace unimm {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every C-ABI entry returns an int and leaves a message in a thread-local string
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define UNIMM_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::unimm::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));                          \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+#define UNIMM_CHECK(cond, msg)                                                                     \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            ::unimm::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +             \
+                               std::to_string(__LINE__));                                          \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+// after a kernel launch: count it (bench.py reports gpu_launches) and surface launch errors
+void count_launches(int n);
+#define UNIMM_LAUNCH_CHECK(n)                   \
+    do {                                        \
+        ::unimm::count_launches(n);             \
+        UNIMM_CUDA_CHECK(cudaGetLastError());   \
+    } while (0)
+
+#define UNIMM_TRY(expr)            \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != 0) return _rc;  \
+    } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// exact (erf) GELU, reference models/vilbert_dialog.py:115-121
+__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == ACT_GELU) return gelu_erf(x);
+    if (act == ACT_RELU) return fmaxf(x, 0.f);
+    return x;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sequence descriptor: the 4 integers that regenerate every dense attention mask of the reference
+// (utils/data_utils.py:149-210 generative, :353-354 discriminative).
+//   mode      0 = generative, 1 = discriminative
+//   ctx       first row of the visible answer copy (= L - last_len); generative only
+//   L         orig_length: number of tokens before the masked answer copy
+//   last_len  answer length + 1 ([SEP]); T = L + last_len is the number of real rows (generative)
+// ---------------------------------------------------------------------------------------------
+struct SeqDesc {
+    int mode, ctx, L, last_len;
+};
+
+// Allowed key interval [lo,hi) plus optional extra single column `self` (-1 = none) for text query row r.
+// An empty result (lo >= hi and self < 0) marks a padding row: the reference adds -10000 to every
+// column there, which leaves softmax over the raw scores — callers then attend to all S columns.
+__device__ __forceinline__ void text_row_interval(const SeqDesc& d, int r, int S, int& lo, int& hi, int& self) {
+    self = -1;
+    if (d.mode == 1) {  // discriminative: [0,L) x [0,L)
+        if (r < d.L) { lo = 0; hi = min(d.L, S); } else { lo = 0; hi = 0; }
+        return;
+    }
+    const int T = d.L + d.last_len;
+    if (r == 0) { lo = 0; hi = min(T, S); }
+    else if (r < d.ctx) { lo = 1; hi = min(d.ctx, S); }
+    else if (r < d.L) { lo = 1; hi = r + 1; }
+    else if (r < T) { lo = 1; hi = max(1, min(r - d.last_len, S)); self = r; }
+    else { lo = 0; hi = 0; }
+}
+
+// Allowed text columns for image queries (co-attention mask): gen [1,ctx), dis [0,L).
+__device__ __forceinline__ void co_interval(const SeqDesc& d, int S, int& lo, int& hi) {
+    if (d.mode == 1) { lo = 0; hi = min(d.L, S); } else { lo = 1; hi = min(d.ctx, S); }
+    if (hi <= lo) { lo = 0; hi = 0; }
+}
+
+}  // namespace unimm

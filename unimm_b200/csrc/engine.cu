@@ -1,0 +1,765 @@
+// Engine: owns the packed weights and the activation workspace of one device and runs the layer
+// schedule of the reference's BertEncoder.forward (models/vilbert_dialog.py:817-937) followed by the
+// heads (:1049-1073), the gathered LM head and the losses (:1559-1624) as a sequence of kernel
+// launches on the caller's stream.  C ABI in include/unimm_b200.h.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/unimm_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unimm {
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const char* get_error() { return g_error.c_str(); }
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+struct DevTensor {
+    float* p = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct Linear {
+    int N = 0, K = 0;
+    const float* w32 = nullptr;  // [N,K] fp32 (fp32 mode, and small heads)
+    const bf16* wlp = nullptr;   // [N,K] bf16 (bf16 mode)
+    const float* b = nullptr;    // [N]
+};
+struct LayerNormP {
+    const float* g = nullptr;
+    const float* b = nullptr;
+    int H = 0;
+};
+struct SelfLayer {  // BertLayer / BertImageLayer
+    Linear qkv, out, ffn1, ffn2;
+    LayerNormP ln1, ln2;
+};
+struct ConnLayer {  // BertConnectionLayer
+    Linear qkv_v, qkv_t, dense1, dense2, v_ffn1, v_ffn2, t_ffn1, t_ffn2;
+    LayerNormP ln1, ln2, v_ln, t_ln;
+};
+
+// activation matrix that exists as fp32 and/or bf16
+struct ActBuf {
+    float* f = nullptr;
+    bf16* h = nullptr;
+    int ld = 0;
+};
+
+}  // namespace
+}  // namespace unimm
+
+using namespace unimm;
+
+struct unimm_engine {
+    unimm_config_t cfg;
+    int device = 0;
+    int prec = UNIMM_PREC_FP32;
+    int Bmax = 0;
+    bool finalized = false;
+    std::map<std::string, DevTensor> raw;     // checkpoint tensors, fp32 on device
+    std::vector<void*> owned;                 // every cudaMalloc'ed block
+
+    // packed parameters
+    const float *word_emb = nullptr, *pos_emb = nullptr, *type_emb = nullptr, *type_ext_emb = nullptr;
+    LayerNormP emb_ln, vemb_ln, lm_ln, img_ln;
+    Linear img_emb, lm_transform, lm_decoder, img_transform, img_decoder;
+    const float *loc_w = nullptr, *loc_b = nullptr;
+    const float *tp_w = nullptr, *tp_b = nullptr, *vp_w = nullptr, *vp_b = nullptr, *nsp_w = nullptr, *nsp_b = nullptr;
+    std::vector<SelfLayer> t_layers, v_layers;
+    std::vector<ConnLayer> c_layers;
+
+    // workspace (sized for Bmax sequences)
+    ActBuf xt, xv;            // hidden states: fp32 master (+ bf16 shadow in bf16 mode)
+    float *pre_t = nullptr, *pre_v = nullptr;   // pre-LayerNorm fp32
+    void *qkv_t = nullptr, *qkv_v = nullptr, *ctx_t = nullptr, *ctx_v = nullptr, *ffn_t = nullptr, *ffn_v = nullptr;
+    void* feat_a = nullptr;        // gathered image features (GEMM operand)
+    ActBuf g_in, g_h;                 // LM head rows
+    float* g_t1 = nullptr;
+    int* g_labels = nullptr;
+    float2* partials = nullptr;
+    float *label_logit = nullptr, *row_logp = nullptr, *row_ul = nullptr;
+    float* logits_chunk = nullptr;  // fp32 mode: [kLogitRows, V]
+    float* vhead = nullptr;         // image head scratch [Mv, Hv]
+    ActBuf vhead_h;
+    float* v_logits = nullptr;
+    int* err_flag = nullptr;
+    // host staging for unimm_score_host
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    void* d_stage = nullptr;
+    size_t d_stage_bytes = 0;
+
+    static constexpr int kLogitRows = 2048;
+
+    template <typename T>
+    int dalloc(T** p, size_t count) {
+        void* q = nullptr;
+        UNIMM_CUDA_CHECK(cudaMalloc(&q, count * sizeof(T) + 256));
+        UNIMM_CUDA_CHECK(cudaMemset(q, 0, count * sizeof(T) + 256));
+        owned.push_back(q);
+        *p = static_cast<T*>(q);
+        return 0;
+    }
+    bool lp() const { return prec == UNIMM_PREC_BF16; }
+    size_t esz() const { return lp() ? 2 : 4; }
+
+    int get(const std::string& name, const DevTensor** out, std::vector<int64_t> shape) {
+        auto it = raw.find(name);
+        UNIMM_CHECK(it != raw.end(), "missing checkpoint key: " + name);
+        UNIMM_CHECK(it->second.shape == shape, "unexpected shape for checkpoint key: " + name);
+        *out = &it->second;
+        return 0;
+    }
+    int make_linear(const std::vector<std::string>& names, int N_each, int K, Linear* L, bool keep_f32_only = false);
+    int make_ln(const std::string& name, int H, LayerNormP* ln);
+    int finalize();
+    int alloc_workspace();
+
+    // y = act(x W^T + b) (+ residual); x/y selected by mode
+    int linear(const ActBuf& x, int M, const Linear& L, int act, const float* residual, int ldr, float* out_f32, int ldo_f32,
+               void* out_lp, int ldo_lp, cudaStream_t st);
+    int attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
+                  int D, int Sq, int Skv, int mask_kind, const SeqDesc* desc, const float* key_mask, cudaStream_t st);
+    int self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int B, int Sx, int heads,
+                   int mask_kind, const SeqDesc* desc, const float* key_mask, cudaStream_t st);
+    int conn_layer(const ConnLayer& L, int B, const SeqDesc* desc, const float* key_mask, cudaStream_t st);
+    int forward(const unimm_batch_t& in, const unimm_outputs_t& out, cudaStream_t st);
+};
+
+namespace {
+inline char* byte_ptr(void* p) { return static_cast<char*>(p); }
+}  // namespace
+
+int unimm_engine::make_ln(const std::string& name, int H, LayerNormP* ln) {
+    const DevTensor *g, *b;
+    UNIMM_TRY(get(name + ".weight", &g, {H}));
+    UNIMM_TRY(get(name + ".bias", &b, {H}));
+    ln->g = g->p; ln->b = b->p; ln->H = H;
+    return 0;
+}
+
+// Concatenate one or more nn.Linear weights along the output dimension ([sum N, K]) and, in bf16 mode,
+// cast the packed matrix once.
+int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each, int K, Linear* L, bool keep_f32_only) {
+    const int parts = static_cast<int>(names.size());
+    L->N = N_each * parts;
+    L->K = K;
+    float *w = nullptr, *b = nullptr;
+    if (parts == 1) {
+        const DevTensor *tw, *tb;
+        UNIMM_TRY(get(names[0] + ".weight", &tw, {N_each, K}));
+        UNIMM_TRY(get(names[0] + ".bias", &tb, {N_each}));
+        w = tw->p; b = tb->p;
+    } else {
+        UNIMM_TRY(dalloc(&w, static_cast<size_t>(L->N) * K));
+        UNIMM_TRY(dalloc(&b, static_cast<size_t>(L->N)));
+        for (int i = 0; i < parts; ++i) {
+            const DevTensor *tw, *tb;
+            UNIMM_TRY(get(names[i] + ".weight", &tw, {N_each, K}));
+            UNIMM_TRY(get(names[i] + ".bias", &tb, {N_each}));
+            UNIMM_CUDA_CHECK(cudaMemcpy(w + static_cast<size_t>(i) * N_each * K, tw->p, sizeof(float) * N_each * K, cudaMemcpyDeviceToDevice));
+            UNIMM_CUDA_CHECK(cudaMemcpy(b + static_cast<size_t>(i) * N_each, tb->p, sizeof(float) * N_each, cudaMemcpyDeviceToDevice));
+        }
+    }
+    L->w32 = w;
+    L->b = b;
+    if (lp() && !keep_f32_only) {
+        bf16* h = nullptr;
+        UNIMM_TRY(dalloc(&h, static_cast<size_t>(L->N) * K));
+        UNIMM_TRY(cast_f32_to_bf16(w, h, static_cast<size_t>(L->N) * K, 0));
+        L->wlp = h;
+    }
+    return 0;
+}
+
+int unimm_engine::finalize() {
+    UNIMM_CHECK(!finalized, "weights already finalized");
+    const unimm_config_t& c = cfg;
+    const int H = c.hidden_size, Hv = c.v_hidden_size, Hb = c.bi_hidden_size, I = c.intermediate_size, Iv = c.v_intermediate_size;
+    const DevTensor* t;
+    UNIMM_TRY(get("bert.embeddings.word_embeddings.weight", &t, {c.vocab_size, H})); word_emb = t->p;
+    UNIMM_TRY(get("bert.embeddings.position_embeddings.weight", &t, {c.max_position_embeddings, H})); pos_emb = t->p;
+    UNIMM_TRY(get("bert.embeddings.token_type_embeddings.weight", &t, {c.type_vocab_size, H})); type_emb = t->p;
+    UNIMM_TRY(get("bert.embeddings.token_type_embeddings_extension.weight", &t, {10, H})); type_ext_emb = t->p;
+    UNIMM_TRY(make_ln("bert.embeddings.LayerNorm", H, &emb_ln));
+    UNIMM_TRY(make_linear({"bert.v_embeddings.image_embeddings"}, Hv, c.v_feature_size, &img_emb));
+    UNIMM_TRY(get("bert.v_embeddings.image_location_embeddings.weight", &t, {Hv, 5})); loc_w = t->p;
+    UNIMM_TRY(get("bert.v_embeddings.image_location_embeddings.bias", &t, {Hv})); loc_b = t->p;
+    UNIMM_TRY(make_ln("bert.v_embeddings.LayerNorm", Hv, &vemb_ln));
+
+    t_layers.resize(c.num_hidden_layers);
+    for (int i = 0; i < c.num_hidden_layers; ++i) {
+        const std::string p = "bert.encoder.layer." + std::to_string(i) + ".";
+        SelfLayer& L = t_layers[i];
+        UNIMM_TRY(make_linear({p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, H, H, &L.qkv));
+        UNIMM_TRY(make_linear({p + "attention.output.dense"}, H, H, &L.out));
+        UNIMM_TRY(make_ln(p + "attention.output.LayerNorm", H, &L.ln1));
+        UNIMM_TRY(make_linear({p + "intermediate.dense"}, I, H, &L.ffn1));
+        UNIMM_TRY(make_linear({p + "output.dense"}, H, I, &L.ffn2));
+        UNIMM_TRY(make_ln(p + "output.LayerNorm", H, &L.ln2));
+    }
+    v_layers.resize(c.v_num_hidden_layers);
+    for (int i = 0; i < c.v_num_hidden_layers; ++i) {
+        const std::string p = "bert.encoder.v_layer." + std::to_string(i) + ".";
+        SelfLayer& L = v_layers[i];
+        UNIMM_TRY(make_linear({p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, Hv, Hv, &L.qkv));
+        UNIMM_TRY(make_linear({p + "attention.output.dense"}, Hv, Hv, &L.out));
+        UNIMM_TRY(make_ln(p + "attention.output.LayerNorm", Hv, &L.ln1));
+        UNIMM_TRY(make_linear({p + "intermediate.dense"}, Iv, Hv, &L.ffn1));
+        UNIMM_TRY(make_linear({p + "output.dense"}, Hv, Iv, &L.ffn2));
+        UNIMM_TRY(make_ln(p + "output.LayerNorm", Hv, &L.ln2));
+    }
+    c_layers.resize(c.num_connections);
+    for (int i = 0; i < c.num_connections; ++i) {
+        const std::string p = "bert.encoder.c_layer." + std::to_string(i) + ".";
+        ConnLayer& L = c_layers[i];
+        UNIMM_TRY(make_linear({p + "biattention.query1", p + "biattention.key1", p + "biattention.value1"}, Hb, Hv, &L.qkv_v));
+        UNIMM_TRY(make_linear({p + "biattention.query2", p + "biattention.key2", p + "biattention.value2"}, Hb, H, &L.qkv_t));
+        UNIMM_TRY(make_linear({p + "biOutput.dense1"}, Hv, Hb, &L.dense1));
+        UNIMM_TRY(make_ln(p + "biOutput.LayerNorm1", Hv, &L.ln1));
+        UNIMM_TRY(make_linear({p + "biOutput.dense2"}, H, Hb, &L.dense2));
+        UNIMM_TRY(make_ln(p + "biOutput.LayerNorm2", H, &L.ln2));
+        UNIMM_TRY(make_linear({p + "v_intermediate.dense"}, Iv, Hv, &L.v_ffn1));
+        UNIMM_TRY(make_linear({p + "v_output.dense"}, Hv, Iv, &L.v_ffn2));
+        UNIMM_TRY(make_ln(p + "v_output.LayerNorm", Hv, &L.v_ln));
+        UNIMM_TRY(make_linear({p + "t_intermediate.dense"}, I, H, &L.t_ffn1));
+        UNIMM_TRY(make_linear({p + "t_output.dense"}, H, I, &L.t_ffn2));
+        UNIMM_TRY(make_ln(p + "t_output.LayerNorm", H, &L.t_ln));
+    }
+    UNIMM_TRY(get("bert.t_pooler.dense.weight", &t, {Hb, H})); tp_w = t->p;
+    UNIMM_TRY(get("bert.t_pooler.dense.bias", &t, {Hb})); tp_b = t->p;
+    UNIMM_TRY(get("bert.v_pooler.dense.weight", &t, {Hb, Hv})); vp_w = t->p;
+    UNIMM_TRY(get("bert.v_pooler.dense.bias", &t, {Hb})); vp_b = t->p;
+    UNIMM_TRY(get("cls.bi_seq_relationship.weight", &t, {2, Hb})); nsp_w = t->p;
+    UNIMM_TRY(get("cls.bi_seq_relationship.bias", &t, {2})); nsp_b = t->p;
+
+    UNIMM_TRY(make_linear({"cls.predictions.transform.dense"}, H, H, &lm_transform));
+    UNIMM_TRY(make_ln("cls.predictions.transform.LayerNorm", H, &lm_ln));
+    // tied decoder (reference :1020): accept either key, insist they agree when both are present
+    {
+        lm_decoder.N = c.vocab_size;
+        lm_decoder.K = H;
+        lm_decoder.w32 = word_emb;
+        auto it = raw.find("cls.predictions.decoder.weight");
+        if (it != raw.end()) {
+            UNIMM_CHECK(it->second.numel == static_cast<size_t>(c.vocab_size) * H, "bad decoder weight shape");
+            lm_decoder.w32 = it->second.p;  // identical to word_emb in every reference checkpoint
+        }
+        UNIMM_TRY(get("cls.predictions.bias", &t, {c.vocab_size}));
+        lm_decoder.b = t->p;
+        if (lp()) {
+            bf16* h = nullptr;
+            UNIMM_TRY(dalloc(&h, static_cast<size_t>(c.vocab_size) * H));
+            UNIMM_TRY(cast_f32_to_bf16(lm_decoder.w32, h, static_cast<size_t>(c.vocab_size) * H, 0));
+            lm_decoder.wlp = h;
+        }
+    }
+    UNIMM_TRY(make_linear({"cls.imagePredictions.transform.dense"}, Hv, Hv, &img_transform));
+    UNIMM_TRY(make_ln("cls.imagePredictions.transform.LayerNorm", Hv, &img_ln));
+    UNIMM_TRY(make_linear({"cls.imagePredictions.decoder"}, c.v_target_size, Hv, &img_decoder));
+    UNIMM_CUDA_CHECK(cudaDeviceSynchronize());
+    UNIMM_TRY(alloc_workspace());
+    finalized = true;
+    return 0;
+}
+
+int unimm_engine::alloc_workspace() {
+    const unimm_config_t& c = cfg;
+    const size_t Mt = static_cast<size_t>(Bmax) * c.seq_len, Mv = static_cast<size_t>(Bmax) * c.num_regions;
+    const int H = c.hidden_size, Hv = c.v_hidden_size, Hb = c.bi_hidden_size;
+    const size_t wt = std::max(std::max(3 * H, 3 * Hb), c.intermediate_size);  // widest text-row buffer
+    const size_t wv = std::max(std::max(3 * Hv, 3 * Hb), c.v_intermediate_size);
+    UNIMM_TRY(dalloc(&xt.f, Mt * H)); xt.ld = H;
+    UNIMM_TRY(dalloc(&xv.f, Mv * Hv)); xv.ld = Hv;
+    if (lp()) { UNIMM_TRY(dalloc(&xt.h, Mt * H)); UNIMM_TRY(dalloc(&xv.h, Mv * Hv)); }
+    UNIMM_TRY(dalloc(&pre_t, Mt * H));
+    UNIMM_TRY(dalloc(&pre_v, Mv * Hv));
+    char* p;
+    UNIMM_TRY(dalloc(&p, Mt * wt * esz())); qkv_t = p;
+    UNIMM_TRY(dalloc(&p, Mv * wv * esz())); qkv_v = p;
+    UNIMM_TRY(dalloc(&p, Mt * std::max(H, Hb) * esz())); ctx_t = p;
+    UNIMM_TRY(dalloc(&p, Mv * std::max(Hv, Hb) * esz())); ctx_v = p;
+    UNIMM_TRY(dalloc(&p, Mt * wt * esz())); ffn_t = p;
+    UNIMM_TRY(dalloc(&p, Mv * wv * esz())); ffn_v = p;
+    UNIMM_TRY(dalloc(&p, Mv * c.v_feature_size * esz())); feat_a = p;
+    // LM head rows: worst case every text position is labelled
+    UNIMM_TRY(dalloc(&g_in.f, lp() ? 4 : Mt * H)); g_in.ld = H;
+    UNIMM_TRY(dalloc(&g_h.f, Mt * H)); g_h.ld = H;
+    if (lp()) { UNIMM_TRY(dalloc(&g_in.h, Mt * H)); UNIMM_TRY(dalloc(&g_h.h, Mt * H)); }
+    UNIMM_TRY(dalloc(&g_t1, Mt * H));
+    UNIMM_TRY(dalloc(&g_labels, Mt));
+    UNIMM_TRY(dalloc(&label_logit, Mt));
+    UNIMM_TRY(dalloc(&row_logp, Mt));
+    UNIMM_TRY(dalloc(&row_ul, Mt));
+    if (lp()) UNIMM_TRY(dalloc(&partials, Mt * gemm_umma_lse_tiles(c.vocab_size)));
+    else UNIMM_TRY(dalloc(&logits_chunk, static_cast<size_t>(kLogitRows) * c.vocab_size));
+    UNIMM_TRY(dalloc(&vhead, Mv * Hv));
+    vhead_h.ld = Hv;
+    UNIMM_TRY(dalloc(&vhead_h.f, Mv * Hv));
+    if (lp()) UNIMM_TRY(dalloc(&vhead_h.h, Mv * Hv));
+    UNIMM_TRY(dalloc(&v_logits, Mv * c.v_target_size));
+    UNIMM_TRY(dalloc(&err_flag, 4));
+    return 0;
+}
+
+int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const float* residual, int ldr, float* out_f32,
+                         int ldo_f32, void* out_lp, int ldo_lp, cudaStream_t st) {
+    GemmEpilogue ep;
+    ep.bias = L.b;
+    ep.residual = residual;
+    ep.ldr = ldr;
+    ep.act = act;
+    if (lp()) {
+        ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
+        ep.out_bf16 = static_cast<bf16*>(out_lp); ep.ldo_bf16 = ldo_lp;
+        UNIMM_CHECK(x.h != nullptr && L.wlp != nullptr, "bf16 operand missing");
+        return gemm_umma_bf16(x.h, x.ld, L.wlp, L.K, M, L.N, L.K, ep, 0, 0, st);
+    }
+    // fp32 mode: the "low precision" output slot is an fp32 tensor as well
+    UNIMM_CHECK(!(out_f32 && out_lp), "fp32 mode writes one output");
+    ep.out_f32 = out_f32 ? out_f32 : static_cast<float*>(out_lp);
+    ep.ldo_f32 = out_f32 ? ldo_f32 : ldo_lp;
+    return gemm_simt_f32(x.f, x.ld, L.w32, L.K, M, L.N, L.K, ep, st);
+}
+
+int unimm_engine::attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
+                            int heads, int D, int Sq, int Skv, int mask_kind, const SeqDesc* desc, const float* key_mask,
+                            cudaStream_t st) {
+    AttnArgs a;
+    a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.o = o; a.ldo = ldo;
+    a.B = B; a.heads = heads; a.D = D; a.Sq = Sq; a.Skv = Skv;
+    a.mask_kind = mask_kind; a.desc = desc; a.key_mask = key_mask;
+    a.scale = 1.0f / sqrtf(static_cast<float>(D));
+    return lp() ? attention_mma_bf16(a, st) : attention_simt_f32(a, st);
+}
+
+// BertLayer / BertImageLayer: QKV -> attention -> out-proj + residual -> LN -> FFN1+GELU -> FFN2 + residual -> LN
+int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int B, int Sx, int heads,
+                             int mask_kind, const SeqDesc* desc, const float* key_mask, cudaStream_t st) {
+    const int M = B * Sx, H = x.ld, D = H / heads;
+    const size_t e = esz();
+    UNIMM_TRY(linear(x, M, L.qkv, ACT_NONE, nullptr, 0, nullptr, 0, qkv, 3 * H, st));
+    UNIMM_TRY(attention(qkv, 3 * H, byte_ptr(qkv) + e * H, 3 * H, byte_ptr(qkv) + e * 2 * H, 3 * H, ctx, H, B, heads, D, Sx, Sx,
+                        mask_kind, desc, key_mask, st));
+    ActBuf c;
+    c.f = lp() ? nullptr : static_cast<float*>(ctx); c.h = lp() ? static_cast<bf16*>(ctx) : nullptr; c.ld = H;
+    UNIMM_TRY(linear(c, M, L.out, ACT_NONE, x.f, H, pre, H, nullptr, 0, st));
+    UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln1.g, L.ln1.b, x.f, x.h, st));
+    const int I = L.ffn1.N;
+    UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st));
+    ActBuf f;
+    f.f = lp() ? nullptr : static_cast<float*>(ffn); f.h = lp() ? static_cast<bf16*>(ffn) : nullptr; f.ld = I;
+    UNIMM_TRY(linear(f, M, L.ffn2, ACT_NONE, x.f, H, pre, H, nullptr, 0, st));
+    UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln2.g, L.ln2.b, x.f, x.h, st));
+    return 0;
+}
+
+// BertConnectionLayer (reference :770-783): stream 1 = image, stream 2 = text
+int unimm_engine::conn_layer(const ConnLayer& L, int B, const SeqDesc* desc, const float* key_mask, cudaStream_t st) {
+    const unimm_config_t& c = cfg;
+    const int S = c.seq_len, R = c.num_regions, H = c.hidden_size, Hv = c.v_hidden_size, Hb = c.bi_hidden_size;
+    const int heads = c.bi_num_attention_heads, D = Hb / heads;
+    const int Mt = B * S, Mv = B * R;
+    const size_t e = esz();
+    UNIMM_TRY(linear(xv, Mv, L.qkv_v, ACT_NONE, nullptr, 0, nullptr, 0, qkv_v, 3 * Hb, st));
+    UNIMM_TRY(linear(xt, Mt, L.qkv_t, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
+    // text queries over image keys/values, image padding mask only (:681-698)
+    UNIMM_TRY(attention(qkv_t, 3 * Hb, byte_ptr(qkv_v) + e * Hb, 3 * Hb, byte_ptr(qkv_v) + e * 2 * Hb, 3 * Hb, ctx_t, Hb, B, heads,
+                        D, S, R, MASK_KEY_VECTOR, nullptr, key_mask, st));
+    // image queries over text keys/values, co-attention column interval only (:701-721)
+    UNIMM_TRY(attention(qkv_v, 3 * Hb, byte_ptr(qkv_t) + e * Hb, 3 * Hb, byte_ptr(qkv_t) + e * 2 * Hb, 3 * Hb, ctx_v, Hb, B, heads,
+                        D, R, S, MASK_CO_INTERVAL, desc, nullptr, st));
+    ActBuf cv, ct;
+    cv.f = lp() ? nullptr : static_cast<float*>(ctx_v); cv.h = lp() ? static_cast<bf16*>(ctx_v) : nullptr; cv.ld = Hb;
+    ct.f = lp() ? nullptr : static_cast<float*>(ctx_t); ct.h = lp() ? static_cast<bf16*>(ctx_t) : nullptr; ct.ld = Hb;
+    // BertBiOutput (:744-754): image rows take the image-query context through dense1, text rows the other through dense2
+    UNIMM_TRY(linear(cv, Mv, L.dense1, ACT_NONE, xv.f, Hv, pre_v, Hv, nullptr, 0, st));
+    UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.ln1.g, L.ln1.b, xv.f, xv.h, st));
+    UNIMM_TRY(linear(ct, Mt, L.dense2, ACT_NONE, xt.f, H, pre_t, H, nullptr, 0, st));
+    UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.ln2.g, L.ln2.b, xt.f, xt.h, st));
+    // image FFN, text FFN (:777-781)
+    const int Iv = L.v_ffn1.N, I = L.t_ffn1.N;
+    UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st));
+    ActBuf fv;
+    fv.f = lp() ? nullptr : static_cast<float*>(ffn_v); fv.h = lp() ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
+    UNIMM_TRY(linear(fv, Mv, L.v_ffn2, ACT_NONE, xv.f, Hv, pre_v, Hv, nullptr, 0, st));
+    UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.v_ln.g, L.v_ln.b, xv.f, xv.h, st));
+    UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st));
+    ActBuf ft;
+    ft.f = lp() ? nullptr : static_cast<float*>(ffn_t); ft.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; ft.ld = I;
+    UNIMM_TRY(linear(ft, Mt, L.t_ffn2, ACT_NONE, xt.f, H, pre_t, H, nullptr, 0, st));
+    UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.t_ln.g, L.t_ln.b, xt.f, xt.h, st));
+    return 0;
+}
+
+int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, cudaStream_t st) {
+    UNIMM_CHECK(finalized, "weights not finalized");
+    const unimm_config_t& c = cfg;
+    const int B = in.B, S = c.seq_len, R = c.num_regions, H = c.hidden_size, Hv = c.v_hidden_size;
+    UNIMM_CHECK(B > 0 && B <= Bmax, "batch size out of range for this engine");
+    UNIMM_CHECK(in.d_input_ids && in.d_token_type_ids && in.d_position_ids && in.d_desc && in.d_image_feat && in.d_image_loc &&
+                    in.d_image_mask, "required input pointer is NULL");
+    const int Mt = B * S, Mv = B * R;
+    const SeqDesc* desc = reinterpret_cast<const SeqDesc*>(in.d_desc);
+
+    // ---- embeddings (reference :326-356, :1487-1493)
+    UNIMM_TRY(embed_text_ln(in.d_input_ids, in.d_token_type_ids, in.d_position_ids, Mt, H, c.vocab_size, c.max_position_embeddings,
+                            c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h,
+                            err_flag, st));
+    UNIMM_TRY(gather_features(in.d_image_feat, in.d_feat_index, B, R, c.v_feature_size, lp() ? nullptr : static_cast<float*>(feat_a),
+                              lp() ? static_cast<bf16*>(feat_a) : nullptr, st));
+    UNIMM_TRY(image_loc_embed(in.d_image_loc, in.d_feat_index, B, R, Hv, loc_w, loc_b, pre_v, st));
+    {
+        ActBuf fa;
+        fa.f = lp() ? nullptr : static_cast<float*>(feat_a); fa.h = lp() ? static_cast<bf16*>(feat_a) : nullptr; fa.ld = c.v_feature_size;
+        UNIMM_TRY(linear(fa, Mv, img_emb, ACT_NONE, pre_v, Hv, pre_v, Hv, nullptr, 0, st));
+        UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, vemb_ln.g, vemb_ln.b, xv.f, xv.h, st));
+    }
+    // key mask per sequence: image_mask[feat_index[b]] — expand once when an index is used
+    const float* key_mask = in.d_image_mask;
+    if (in.d_feat_index != nullptr) {
+        // reuse vhead as scratch for the expanded [B,R] mask (F = R floats per row; R may not be a multiple of 4)
+        float* km = vhead;
+        UNIMM_TRY(expand_key_mask(in.d_image_mask, in.d_feat_index, B, R, km, st));
+        key_mask = km;
+    }
+
+    // ---- encoder schedule (reference :842-929)
+    int v_start = 0, t_start = 0;
+    auto run_v = [&](int i) {
+        return self_layer(v_layers[i], xv, pre_v, qkv_v, ctx_v, ffn_v, B, R, c.v_num_attention_heads, MASK_KEY_VECTOR, nullptr,
+                          key_mask, st);
+    };
+    auto run_t = [&](int i) {
+        return self_layer(t_layers[i], xt, pre_t, qkv_t, ctx_t, ffn_t, B, S, c.num_attention_heads, MASK_TEXT_SELF, desc, nullptr,
+                          st);
+    };
+    for (int k = 0; k < c.num_connections; ++k) {
+        for (int i = v_start; i < c.v_biattention_id[k]; ++i) UNIMM_TRY(run_v(i));
+        for (int i = t_start; i < c.t_biattention_id[k]; ++i) UNIMM_TRY(run_t(i));
+        UNIMM_TRY(conn_layer(c_layers[k], B, desc, key_mask, st));
+        v_start = c.v_biattention_id[k];
+        t_start = c.t_biattention_id[k];
+    }
+    for (int i = v_start; i < c.v_num_hidden_layers; ++i) UNIMM_TRY(run_v(i));
+    for (int i = t_start; i < c.num_hidden_layers; ++i) UNIMM_TRY(run_t(i));
+
+    if (out.d_sequence_output_t)
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(out.d_sequence_output_t, xt.f, sizeof(float) * Mt * H, cudaMemcpyDeviceToDevice, st));
+    if (out.d_sequence_output_v)
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(out.d_sequence_output_v, xv.f, sizeof(float) * Mv * Hv, cudaMemcpyDeviceToDevice, st));
+
+    // ---- poolers + NSP head (reference :946-967, :1062-1070); always fp32
+    const bool training = in.d_masked_lm_labels && in.d_next_sentence_label && in.d_image_target;
+    float* nsp = out.d_nsp_scores;
+    if (nsp == nullptr && training) nsp = label_logit;  // scratch (B*2 <= Mt)
+    if (nsp != nullptr)
+        UNIMM_TRY(pooler_nsp(xt.f, S * H, xv.f, R * Hv, B, H, Hv, c.bi_hidden_size, tp_w, tp_b, vp_w, vp_b, nsp_w, nsp_b, nsp, st));
+    if (training && out.d_losses)
+        UNIMM_TRY(nsp_ce_loss(nsp, in.d_next_sentence_label, B, in.d_nsp_weight, out.d_losses + 2, st));
+
+    // ---- gathered LM head (reference :982-986, :1023-1026 on the labelled rows only) + scores
+    const int n = in.n_lm_rows;
+    UNIMM_CHECK(n >= 0 && n <= Mt, "n_lm_rows out of range");
+    if (n > 0) {
+        UNIMM_CHECK(in.d_lm_rows && in.d_masked_lm_labels, "lm rows given without labels");
+        UNIMM_TRY(gather_labels(in.d_masked_lm_labels, in.d_lm_rows, n, g_labels, st));
+        UNIMM_TRY(gather_rows(lp() ? nullptr : xt.f, lp() ? xt.h : nullptr, in.d_lm_rows, n, H, lp() ? nullptr : g_in.f,
+                              lp() ? g_in.h : nullptr, st));
+        UNIMM_TRY(linear(g_in, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
+        UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, st));
+        if (lp()) {
+            GemmEpilogue ep;
+            ep.bias = lm_decoder.b;
+            ep.labels = g_labels;
+            ep.partials = partials;
+            ep.label_logit = label_logit;
+            UNIMM_TRY(gemm_umma_bf16(g_h.h, H, lm_decoder.wlp, H, n, c.vocab_size, H, ep, 256, 0, st));
+            UNIMM_TRY(lse_from_partials(partials, gemm_umma_lse_tiles(c.vocab_size), label_logit, n, row_logp, row_ul, st));
+        } else {
+            for (int r0 = 0; r0 < n; r0 += kLogitRows) {
+                const int nr = std::min(kLogitRows, n - r0);
+                GemmEpilogue ep;
+                ep.bias = lm_decoder.b;
+                ep.out_f32 = logits_chunk;
+                ep.ldo_f32 = c.vocab_size;
+                UNIMM_TRY(gemm_simt_f32(g_h.f + static_cast<size_t>(r0) * H, H, lm_decoder.w32, H, nr, c.vocab_size, H, ep, st));
+                UNIMM_TRY(lse_from_logits(logits_chunk, c.vocab_size, nr, c.vocab_size, g_labels + r0, row_logp + r0, row_ul + r0, st));
+            }
+        }
+    }
+    if (out.d_seq_score || out.d_token_logp || out.d_token_ul)
+        UNIMM_TRY(scatter_scores(row_logp, row_ul, in.d_lm_rows, n, B, S, out.d_token_logp, out.d_token_ul, out.d_seq_score, st));
+
+    // ---- losses (reference :1559-1624)
+    if (training && out.d_losses) {
+        if (in.d_lm_weight) UNIMM_TRY(lm_ul_loss(row_logp, row_ul, in.d_lm_rows, n, in.d_lm_weight, Mt, out.d_losses, st));
+        else UNIMM_TRY(lm_ce_loss(row_logp, n, out.d_losses, st));
+        // image head (:1085-1088) + masked KL (:1569-1574)
+        UNIMM_CHECK(in.d_image_label != nullptr, "image_label required with image_target");
+        UNIMM_TRY(linear(xv, Mv, img_transform, ACT_GELU, nullptr, 0, vhead, Hv, nullptr, 0, st));
+        UNIMM_TRY(layernorm_rows(vhead, Hv, Mv, Hv, img_ln.g, img_ln.b, vhead_h.f, vhead_h.h, st));
+        UNIMM_TRY(linear(vhead_h, Mv, img_decoder, ACT_NONE, nullptr, 0, v_logits, c.v_target_size, nullptr, 0, st));
+        // d_losses[1] = loss, [3..4] scratch
+        float* kl = out.d_losses + 3;
+        UNIMM_TRY(image_kl_loss(v_logits, c.v_target_size, in.d_image_target, in.d_image_label, Mv, c.v_target_size, kl, st));
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(out.d_losses + 1, kl, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+
+    // ---- compatibility: full-vocabulary logits for every text row (reference :1025 as written)
+    if (out.d_prediction_scores_t) {
+        UNIMM_TRY(linear(xt, Mt, lm_transform, ACT_GELU, nullptr, 0, pre_t, H, nullptr, 0, st));
+        ActBuf hh;
+        hh.f = pre_t; hh.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; hh.ld = H;
+        UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, lm_ln.g, lm_ln.b, hh.f, hh.h, st));
+        UNIMM_TRY(linear(hh, Mt, lm_decoder, ACT_NONE, nullptr, 0, out.d_prediction_scores_t, c.vocab_size, nullptr, 0, st));
+    }
+    return 0;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// device-side staging of unimm_score_host (allocated on first use, sized for Bmax)
+struct HostPath {
+    int64_t *ids = nullptr, *types = nullptr, *pos = nullptr, *labels = nullptr;
+    unimm_seq_desc_t* desc = nullptr;
+    float *feat = nullptr, *loc = nullptr, *mask = nullptr, *score = nullptr, *nsp = nullptr;
+    int32_t *index = nullptr, *rows = nullptr;
+    int32_t* h_rows = nullptr;  // pinned
+};
+std::map<unimm_engine*, HostPath> g_host_paths;
+}  // namespace
+
+extern "C" {
+
+const char* unimm_last_error(void) { return unimm::get_error(); }
+int unimm_abi_version(void) { return UNIMM_ABI_VERSION; }
+int64_t unimm_launch_count(void) { return g_launches.load(); }
+void unimm_reset_launch_count(void) { g_launches.store(0); }
+
+int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_sequences, unimm_engine_t** out) {
+    UNIMM_CHECK(cfg != nullptr && out != nullptr, "null argument");
+    UNIMM_CHECK(precision == UNIMM_PREC_FP32 || precision == UNIMM_PREC_BF16, "unknown precision");
+    UNIMM_CHECK(max_sequences > 0, "max_sequences must be positive");
+    UNIMM_CHECK(cfg->hidden_size == 768 || cfg->hidden_size == 1024, "hidden_size must be 768 or 1024");
+    UNIMM_CHECK(cfg->v_hidden_size == 768 || cfg->v_hidden_size == 1024, "v_hidden_size must be 768 or 1024");
+    UNIMM_CHECK(cfg->num_connections >= 0 && cfg->num_connections <= 16, "too many connection layers");
+    const int d = cfg->hidden_size / cfg->num_attention_heads, dv = cfg->v_hidden_size / cfg->v_num_attention_heads,
+              db = cfg->bi_hidden_size / cfg->bi_num_attention_heads;
+    UNIMM_CHECK((d == 64 || d == 128) && (dv == 64 || dv == 128) && (db == 64 || db == 128), "head dims must be 64 or 128");
+    UNIMM_CHECK(cfg->seq_len > 0 && cfg->seq_len <= 256 && cfg->num_regions > 0 && cfg->num_regions <= 256,
+                "seq_len / num_regions must be in (0, 256]");
+    int ndev = 0;
+    UNIMM_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    UNIMM_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+    cudaDeviceProp prop;
+    UNIMM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    UNIMM_CHECK(prop.major == 10, "unimm_b200 kernels are built for sm_100a (B200) only");
+    DeviceGuard g(device);
+    unimm_engine* e = new unimm_engine();
+    e->cfg = *cfg;
+    e->device = device;
+    e->prec = precision;
+    e->Bmax = max_sequences;
+    *out = e;
+    return 0;
+}
+
+int unimm_destroy(unimm_engine_t* e) {
+    if (e == nullptr) return 0;
+    DeviceGuard g(e->device);
+    cudaDeviceSynchronize();
+    auto it = g_host_paths.find(e);
+    if (it != g_host_paths.end()) {
+        if (it->second.h_rows) cudaFreeHost(it->second.h_rows);
+        g_host_paths.erase(it);
+    }
+    for (void* p : e->owned) cudaFree(p);
+    delete e;
+    return 0;
+}
+
+int unimm_load_weight(unimm_engine_t* e, const char* name, const float* h_data, const int64_t* shape, int ndim) {
+    UNIMM_CHECK(e && name && h_data && shape && ndim > 0 && ndim <= 4, "bad argument");
+    UNIMM_CHECK(!e->finalized, "weights already finalized");
+    DeviceGuard g(e->device);
+    std::string key(name);
+    const std::string prefix = "bert_pretrained.";
+    if (key.compare(0, prefix.size(), prefix) == 0) key = key.substr(prefix.size());
+    DevTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) {
+        t.shape.push_back(shape[i]);
+        t.numel *= static_cast<size_t>(shape[i]);
+    }
+    UNIMM_CHECK(t.numel > 0, "empty tensor");
+    // keep every buffer 16-byte sized so 128-bit casts/gathers never read past the end
+    UNIMM_TRY(e->dalloc(&t.p, (t.numel + 3) & ~size_t(3)));
+    UNIMM_CUDA_CHECK(cudaMemcpy(t.p, h_data, t.numel * sizeof(float), cudaMemcpyHostToDevice));
+    e->raw[key] = t;
+    return 0;
+}
+
+int unimm_finalize_weights(unimm_engine_t* e) {
+    UNIMM_CHECK(e != nullptr, "null engine");
+    DeviceGuard g(e->device);
+    return e->finalize();
+}
+
+int unimm_forward(unimm_engine_t* e, const unimm_batch_t* batch, const unimm_outputs_t* out, void* stream) {
+    UNIMM_CHECK(e && batch && out, "null argument");
+    DeviceGuard g(e->device);
+    return e->forward(*batch, *out, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_verify_masks(const unimm_seq_desc_t* d_desc, int B, int S, int R, const void* d_txt_mask, int txt_elem_bytes,
+                       const int64_t* d_co_mask, int* d_mismatch, void* stream) {
+    UNIMM_CHECK(d_desc && d_txt_mask && d_mismatch && B > 0, "bad argument");
+    return verify_masks(reinterpret_cast<const SeqDesc*>(d_desc), B, S, R, d_txt_mask, txt_elem_bytes, 0, d_co_mask, d_mismatch,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream) {
+    UNIMM_CHECK(e && hb && h_seq_score, "null argument");
+    UNIMM_CHECK(e->finalized, "weights not finalized");
+    const unimm_config_t& c = e->cfg;
+    const int B = hb->B, U = hb->U, S = c.seq_len, R = c.num_regions, F = c.v_feature_size;
+    UNIMM_CHECK(B > 0 && B <= e->Bmax && U > 0 && U <= e->Bmax, "batch size out of range for this engine");
+    UNIMM_CHECK(hb->h_feat_index != nullptr || U == B, "feat_index required when U != B");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    HostPath& hp = g_host_paths[e];
+    if (hp.ids == nullptr) {
+        const size_t n = static_cast<size_t>(e->Bmax);
+        UNIMM_TRY(e->dalloc(&hp.ids, n * S)); UNIMM_TRY(e->dalloc(&hp.types, n * S)); UNIMM_TRY(e->dalloc(&hp.pos, n * S));
+        UNIMM_TRY(e->dalloc(&hp.labels, n * S)); UNIMM_TRY(e->dalloc(&hp.desc, n));
+        UNIMM_TRY(e->dalloc(&hp.feat, n * R * F)); UNIMM_TRY(e->dalloc(&hp.loc, n * R * 5)); UNIMM_TRY(e->dalloc(&hp.mask, n * R));
+        UNIMM_TRY(e->dalloc(&hp.index, n)); UNIMM_TRY(e->dalloc(&hp.rows, n * S));
+        UNIMM_TRY(e->dalloc(&hp.score, n)); UNIMM_TRY(e->dalloc(&hp.nsp, 2 * n));
+        UNIMM_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&hp.h_rows), sizeof(int32_t) * n * S));
+    }
+    // labelled positions (label != -1), in order: the rows the LM head runs on
+    int n_rows = 0;
+    if (hb->h_masked_lm_labels != nullptr) {
+        const int64_t* lab = hb->h_masked_lm_labels;
+        for (int i = 0; i < B * S; ++i)
+            if (lab[i] != -1) hp.h_rows[n_rows++] = i;
+    }
+    const size_t bs = static_cast<size_t>(B) * S;
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.ids, hb->h_input_ids, bs * 8, cudaMemcpyHostToDevice, st));
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.types, hb->h_token_type_ids, bs * 8, cudaMemcpyHostToDevice, st));
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.pos, hb->h_position_ids, bs * 8, cudaMemcpyHostToDevice, st));
+    if (n_rows > 0) {
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.labels, hb->h_masked_lm_labels, bs * 8, cudaMemcpyHostToDevice, st));
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.rows, hp.h_rows, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, st));
+    }
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.desc, hb->h_desc, sizeof(unimm_seq_desc_t) * B, cudaMemcpyHostToDevice, st));
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.feat, hb->h_image_feat, sizeof(float) * U * R * F, cudaMemcpyHostToDevice, st));
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.loc, hb->h_image_loc, sizeof(float) * U * R * 5, cudaMemcpyHostToDevice, st));
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.mask, hb->h_image_mask, sizeof(float) * U * R, cudaMemcpyHostToDevice, st));
+    if (hb->h_feat_index) UNIMM_CUDA_CHECK(cudaMemcpyAsync(hp.index, hb->h_feat_index, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+
+    unimm_batch_t in;
+    std::memset(&in, 0, sizeof(in));
+    in.B = B;
+    in.d_input_ids = hp.ids; in.d_token_type_ids = hp.types; in.d_position_ids = hp.pos;
+    in.d_desc = hp.desc; in.d_image_feat = hp.feat; in.d_image_loc = hp.loc; in.d_image_mask = hp.mask;
+    in.d_feat_index = hb->h_feat_index ? hp.index : nullptr;
+    in.d_masked_lm_labels = n_rows > 0 ? hp.labels : nullptr;
+    in.d_lm_rows = hp.rows;
+    in.n_lm_rows = n_rows;
+    unimm_outputs_t out;
+    std::memset(&out, 0, sizeof(out));
+    out.d_seq_score = hp.score;
+    out.d_nsp_scores = h_nsp_scores ? hp.nsp : nullptr;
+    UNIMM_TRY(e->forward(in, out, st));
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_seq_score, hp.score, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+    if (h_nsp_scores) UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_nsp_scores, hp.nsp, sizeof(float) * 2 * B, cudaMemcpyDeviceToHost, st));
+    UNIMM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- kernel-level entry points
+int unimm_k_gemm_bf16(const void* d_A, int lda, const void* d_W, int ldw, int M, int N, int K, const float* d_bias,
+                      const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_bf16, int ldo_bf16,
+                      int tile_n, int max_ctas, void* stream) {
+    GemmEpilogue ep;
+    ep.bias = d_bias; ep.residual = d_residual; ep.ldr = ldr; ep.act = act;
+    ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32; ep.out_bf16 = static_cast<bf16*>(d_out_bf16); ep.ldo_bf16 = ldo_bf16;
+    return gemm_umma_bf16(static_cast<const bf16*>(d_A), lda, static_cast<const bf16*>(d_W), ldw, M, N, K, ep, tile_n, max_ctas,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_gemm_f32(const float* d_A, int lda, const float* d_W, int ldw, int M, int N, int K, const float* d_bias,
+                     const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* stream) {
+    GemmEpilogue ep;
+    ep.bias = d_bias; ep.residual = d_residual; ep.ldr = ldr; ep.act = act;
+    ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32;
+    return gemm_simt_f32(d_A, lda, d_W, ldw, M, N, K, ep, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_lm_head_bf16(const void* d_H, int ldh, const void* d_E, int lde, int rows, int V, int K, const float* d_bias,
+                         const int32_t* d_labels, float* d_partials_scratch, float* d_label_logit_scratch, float* d_logp,
+                         float* d_ul, void* stream) {
+    GemmEpilogue ep;
+    ep.bias = d_bias;
+    ep.labels = d_labels;
+    ep.partials = reinterpret_cast<float2*>(d_partials_scratch);
+    ep.label_logit = d_label_logit_scratch;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    UNIMM_TRY(gemm_umma_bf16(static_cast<const bf16*>(d_H), ldh, static_cast<const bf16*>(d_E), lde, rows, V, K, ep, 256, 0, st));
+    return lse_from_partials(ep.partials, gemm_umma_lse_tiles(V), d_label_logit_scratch, rows, d_logp, d_ul, st);
+}
+
+int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
+                      void* d_y_bf16, void* stream) {
+    return layernorm_rows(d_x, ldx, rows, H, d_gamma, d_beta, d_y_f32, static_cast<bf16*>(d_y_bf16), static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_cast_bf16(const float* d_src, void* d_dst, int64_t n, void* stream) {
+    return cast_f32_to_bf16(d_src, static_cast<bf16*>(d_dst), static_cast<size_t>(n), static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,
+                      int heads, int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc, const float* d_key_mask,
+                      int is_bf16, int impl, void* stream) {
+    AttnArgs a;
+    a.q = d_q; a.ldq = ldq; a.k = d_k; a.ldk = ldk; a.v = d_v; a.ldv = ldv; a.o = d_o; a.ldo = ldo;
+    a.B = B; a.heads = heads; a.D = D; a.Sq = Sq; a.Skv = Skv; a.mask_kind = mask_kind;
+    a.desc = reinterpret_cast<const SeqDesc*>(d_desc); a.key_mask = d_key_mask;
+    a.scale = 1.0f / sqrtf(static_cast<float>(D));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!is_bf16) {
+        UNIMM_CHECK(impl == 0, "the tensor-core attention takes bf16 tensors");
+        return attention_simt_f32(a, st);
+    }
+    return impl == 0 ? attention_simt_bf16(a, st) : attention_mma_bf16(a, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:   C[M,N] = act(A[M,K] · W[N,K]^T + bias) (+ residual)
+//
+// Replaces the reference's nn.Linear call sites on the hot path (models/vilbert_dialog.py:386-388 QKV,
+// :423 out-proj, :453 FFN-1, :466 FFN-2, :659-672 co-attention projections, :745-748 biOutput dense,
+// :983 LM transform, :1025 tied decoder).  A is the activation matrix (bf16, K contiguous), W is the
+// nn.Linear weight exactly as stored in the checkpoint ([out,in] = [N,K], K contiguous) cast to bf16,
+// so both operands are "K-major" and no transpose is ever materialised.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0   TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (W) bf16 boxes, 128B swizzle,
+//            into a kStages-deep shared-memory ring, completion on mbarriers
+//   warp 1   one elected thread issues tcgen05.mma (M=128, N=BN, K=16) with the fp32 accumulator in
+//            TMEM; tcgen05.commit releases ring slots and publishes finished accumulators
+//   warp 2   TMEM allocator (2 x BN columns: the accumulator is double buffered so the epilogue of
+//            tile i overlaps the main loop of tile i+1)
+//   warps 4-7 epilogue: tcgen05.ld (each thread owns one accumulator row), + bias, GELU/ReLU,
+//            + fp32 residual, stores fp32 and/or bf16;  or, in LSE mode (the fused LM head), an
+//            online log-sum-exp over the tile's vocabulary columns and the label-logit pick, so the
+//            [rows, 30522] logits never reach HBM.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace unimm {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;      // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;  // fixed for 16-bit inputs
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool LSE>
+__global__ void __launch_bounds__(256, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 GemmEpilogue ep) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled tiles need 1024-byte aligned bases
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::kStages;
+    uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m = (M + BM - 1) / BM;
+    const int num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_k = K / BK;
+
+    if (warp == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && ptx::elect_one()) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tfull_bar[a], 1);
+            ptx::mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * BM;
+                const int n0 = (tile % num_n) * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
+                    ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * Cfg::kABytes));
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+                        ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tn = tile % num_n;
+            const int m0 = (tile / num_n) * BM;
+            const int n0 = tn * BN;
+            const int row = m0 + ew * 32 + lane;
+            const bool row_ok = row < M;
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr0 = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+
+            float run_max = -INFINITY, run_sum = 0.f, lab_logit = 0.f;
+            int label = -1;
+            if (LSE && row_ok) label = ep.labels[row];
+
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= N) break;  // warp-uniform
+                const int ncols = min(32, N - col0);
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(taddr0 + c * 32, v);
+                ptx::tmem_ld_wait();
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                if (ep.bias != nullptr) {
+                    if (ncols == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                            x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) x[j] += __ldg(ep.bias + col0 + j);
+                    }
+                }
+                if (LSE) {
+                    float cmax = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) cmax = fmaxf(cmax, x[j]);
+                    const float nmax = fmaxf(run_max, cmax);
+                    float s = run_sum * expf(run_max - nmax);  // exp(-inf) = 0 on the first chunk
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) {
+                            s += expf(x[j] - nmax);
+                            if (col0 + j == label) lab_logit = x[j];
+                        }
+                    run_max = nmax;
+                    run_sum = s;
+                    continue;
+                }
+                if (ep.act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], ep.act);
+                }
+                if (!row_ok) continue;
+                if (ep.residual != nullptr) {
+                    const float* r = ep.residual + static_cast<size_t>(row) * ep.ldr + col0;
+                    if (ncols == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(r + j);
+                            x[j] += r4.x; x[j + 1] += r4.y; x[j + 2] += r4.z; x[j + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) x[j] += r[j];
+                    }
+                }
+                if (ep.out_f32 != nullptr) {
+                    float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
+                    if (ncols == 32 && (ep.ldo_f32 & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) o[j] = x[j];
+                    }
+                }
+                if (ep.out_bf16 != nullptr) {
+                    bf16* o = ep.out_bf16 + static_cast<size_t>(row) * ep.ldo_bf16 + col0;
+                    if (ncols == 32 && (ep.ldo_bf16 & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 p;
+                            p.x = pack_bf16x2(x[j], x[j + 1]);
+                            p.y = pack_bf16x2(x[j + 2], x[j + 3]);
+                            p.z = pack_bf16x2(x[j + 4], x[j + 5]);
+                            p.w = pack_bf16x2(x[j + 6], x[j + 7]);
+                            *reinterpret_cast<uint4*>(o + j) = p;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) o[j] = __float2bfloat16_rn(x[j]);
+                    }
+                }
+            }
+            if (LSE && row_ok) {
+                ep.partials[static_cast<size_t>(row) * num_n + tn] = make_float2(run_max, run_sum);
+                if (label >= n0 && label < min(n0 + BN, N)) ep.label_logit[row] = lab_logit;
+            }
+            // hand the accumulator back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched through the runtime, so the library
+// does not link libcuda) and a small cache keyed by (pointer, shape, stride, box).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    int rows, cols, ld, box_rows;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (size_t)k.ld * 0x165667B19E3779F9ull +
+             (size_t)k.box_rows;
+        return h;
+    }
+};
+
+int make_map_bf16(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    MapKey key{ptr, rows, cols, ld, box_rows};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    UNIMM_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+    UNIMM_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0, "TMA operand must be 16-byte aligned");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UNIMM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int BN, bool LSE>
+int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int max_ctas,
+           cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap tmA, tmB;
+    UNIMM_TRY(make_map_bf16(A, M, K, lda, BM, &tmA));
+    UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN, &tmB));
+    static bool attr_set = false;
+    if (!attr_set) {
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    umma_gemm_kernel<BN, LSE><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+}  // namespace
+
+int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int tile_n,
+                   int max_ctas, cudaStream_t stream) {
+    UNIMM_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "umma gemm: K must be a positive multiple of 64");
+    const bool lse = ep.partials != nullptr;
+    if (tile_n == 0) tile_n = (N % 256 == 0 || N > 2048) ? 256 : 128;
+    if (lse) {
+        UNIMM_CHECK(tile_n == 256, "LSE epilogue uses 256-wide vocabulary tiles");
+        return launch<256, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+    }
+    if (tile_n == 256) return launch<256, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+    UNIMM_CHECK(tile_n == 128, "umma gemm: tile_n must be 128 or 256");
+    return launch<128, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+}
+
+int gemm_umma_lse_tiles(int N) { return (N + 255) / 256; }
+
+}  // namespace unimm

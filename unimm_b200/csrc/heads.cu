@@ -1,0 +1,317 @@
+// Heads, score assembly and losses: pooler + NSP head, log-sum-exp tails of the LM head,
+// val_lm-style per-sequence scores, likelihood / unlikelihood, NSP and image-KL losses, and the
+// boundary check that the caller's dense masks really are what the descriptors regenerate.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unimm {
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float t = (threadIdx.x < nw) ? scratch[threadIdx.x] : 0.f;
+    if (warp == 0) t = warp_sum(t);
+    if (threadIdx.x == 0) scratch[0] = t;
+    __syncthreads();
+    return scratch[0];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+    v = warp_max(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float t = (threadIdx.x < nw) ? scratch[threadIdx.x] : -INFINITY;
+    if (warp == 0) t = warp_max(t);
+    if (threadIdx.x == 0) scratch[0] = t;
+    __syncthreads();
+    return scratch[0];
+}
+
+// one CTA per sequence: pooled_t = relu(Wt x_t[b,0] + bt), pooled_v = relu(Wv x_v[b,0] + bv),
+// nsp = Wn (pooled_t * pooled_v) + bn   (reference models/vilbert_dialog.py:946-967, :1065-1070)
+__global__ void __launch_bounds__(256)
+pooler_nsp_kernel(const float* __restrict__ xt, int ldt_seq, const float* __restrict__ xv, int ldv_seq, int Ht, int Hv, int Hb,
+                  const float* __restrict__ Wt, const float* __restrict__ bt, const float* __restrict__ Wv,
+                  const float* __restrict__ bv, const float* __restrict__ Wn, const float* __restrict__ bn,
+                  float* __restrict__ nsp) {
+    extern __shared__ float sm[];
+    float* st = sm;            // [Ht]
+    float* sv = st + Ht;       // [Hv]
+    float* sz = sv + Hv;       // [Hb]
+    __shared__ float scratch[32];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    for (int i = tid; i < Ht; i += blockDim.x) st[i] = xt[static_cast<size_t>(b) * ldt_seq + i];
+    for (int i = tid; i < Hv; i += blockDim.x) sv[i] = xv[static_cast<size_t>(b) * ldv_seq + i];
+    __syncthreads();
+    for (int j = warp; j < Hb; j += nw) {
+        float a = 0.f, c = 0.f;
+        const float* wt = Wt + static_cast<size_t>(j) * Ht;
+        const float* wv = Wv + static_cast<size_t>(j) * Hv;
+        for (int i = lane; i < Ht; i += 32) a = fmaf(__ldg(wt + i), st[i], a);
+        for (int i = lane; i < Hv; i += 32) c = fmaf(__ldg(wv + i), sv[i], c);
+        a = warp_sum(a);
+        c = warp_sum(c);
+        if (lane == 0) sz[j] = fmaxf(a + bt[j], 0.f) * fmaxf(c + bv[j], 0.f);
+    }
+    __syncthreads();
+    for (int o = 0; o < 2; ++o) {
+        float a = 0.f;
+        for (int i = tid; i < Hb; i += blockDim.x) a = fmaf(__ldg(Wn + o * Hb + i), sz[i], a);
+        a = block_sum(a, scratch);
+        if (tid == 0) nsp[b * 2 + o] = a + bn[o];
+    }
+}
+
+// log p(label) and log(max(1 - p(label), 1e-6)) from one row of materialised fp32 logits
+__global__ void __launch_bounds__(256)
+lse_logits_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ labels, float* __restrict__ logp,
+                  float* __restrict__ ul) {
+    __shared__ float scratch[32];
+    const int row = blockIdx.x;
+    const float* x = logits + static_cast<size_t>(row) * ld;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
+    mx = block_max(mx, scratch);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - mx);
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) {
+        const int lab = labels[row];
+        const float lp = (lab >= 0 && lab < V) ? (x[lab] - mx) - logf(s) : 0.f;
+        logp[row] = lp;
+        ul[row] = logf(fmaxf(1.0f - expf(lp), 1e-6f));  // reference :1587, clamp_min = 1e-6
+    }
+}
+
+__global__ void lse_partials_kernel(const float2* __restrict__ partials, int tiles, const float* __restrict__ label_logit,
+                                    int rows, float* __restrict__ logp, float* __restrict__ ul) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float2* p = partials + static_cast<size_t>(row) * tiles;
+    float mx = -INFINITY;
+    for (int i = lane; i < tiles; i += 32) mx = fmaxf(mx, p[i].x);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < tiles; i += 32) s += p[i].y * expf(p[i].x - mx);
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float lp = (label_logit[row] - mx) - logf(s);
+        logp[row] = lp;
+        ul[row] = logf(fmaxf(1.0f - expf(lp), 1e-6f));
+    }
+}
+
+__global__ void scatter_scores_kernel(const float* __restrict__ logp, const float* __restrict__ ul,
+                                      const int* __restrict__ flat_rows, int n, float* token_logp, float* token_ul) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (token_logp) token_logp[flat_rows[i]] = logp[i];
+    if (token_ul) token_ul[flat_rows[i]] = ul[i];
+}
+// deterministic per-sequence sum: flat_rows is sorted, so sequence b owns a contiguous run
+__global__ void seq_score_kernel(const float* __restrict__ logp, const int* __restrict__ flat_rows, int n, int B, int S,
+                                 float* __restrict__ seq_score) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    // lower bound of b*S in flat_rows
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (flat_rows[mid] < b * S) lo = mid + 1; else hi = mid;
+    }
+    float s = 0.f;
+    for (int i = lo; i < n && flat_rows[i] < (b + 1) * S; ++i) s += logp[i];
+    seq_score[b] = s;
+}
+
+// (sum_l w*(-logp) + sum_ul (-ul)) / #(lm_weight != 0)      (reference :1577-1595)
+__global__ void __launch_bounds__(256)
+lm_ul_loss_kernel(const float* __restrict__ logp, const float* __restrict__ ul, const int* __restrict__ flat_rows, int n,
+                  const int64_t* __restrict__ lm_weight, int BS, float* __restrict__ out) {
+    __shared__ float scratch[32];
+    float acc = 0.f, cnt = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long w = lm_weight[flat_rows[i]];
+        if (w > 0) acc += -logp[i] * static_cast<float>(w);
+        else if (w == -1) acc += -ul[i];
+    }
+    for (int i = threadIdx.x; i < BS; i += blockDim.x) cnt += (lm_weight[i] != 0) ? 1.f : 0.f;
+    acc = block_sum(acc, scratch);
+    cnt = block_sum(cnt, scratch);
+    if (threadIdx.x == 0) out[0] = acc / cnt;
+}
+
+__global__ void __launch_bounds__(256) lm_ce_loss_kernel(const float* __restrict__ logp, int n, float* __restrict__ out) {
+    __shared__ float scratch[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += -logp[i];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) out[0] = acc / static_cast<float>(n);
+}
+
+// F.cross_entropy(weight=w/w[0], reduction='mean') = sum_i w[y_i] * nll_i / sum_i w[y_i]   (reference :1605-1621)
+__global__ void __launch_bounds__(256)
+nsp_ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int B,
+                   const float* __restrict__ nsp_weight, float* __restrict__ out) {
+    __shared__ float scratch[32];
+    float w0 = 1.f, w1 = 1.f;
+    if (nsp_weight != nullptr) { w0 = 1.f; w1 = nsp_weight[1] / nsp_weight[0]; }
+    float num = 0.f, den = 0.f;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const float a = logits[2 * i], b = logits[2 * i + 1];
+        const float mx = fmaxf(a, b);
+        const float lse = mx + logf(expf(a - mx) + expf(b - mx));
+        const long long y = labels[i];
+        const float w = (y == 0) ? w0 : w1;
+        num += w * (lse - (y == 0 ? a : b));
+        den += w;
+    }
+    num = block_sum(num, scratch);
+    den = block_sum(den, scratch);
+    if (threadIdx.x == 0) out[0] = num / den;
+}
+
+// per selected (image_label == 1) region: sum_c t_c (log t_c - log_softmax(x)_c); atomics into acc[0], count in acc[1]
+__global__ void __launch_bounds__(256)
+image_kl_kernel(const float* __restrict__ v_logits, int ld, const float* __restrict__ target,
+                const int64_t* __restrict__ image_label, int C, float* __restrict__ acc) {
+    __shared__ float scratch[32];
+    const int row = blockIdx.x;
+    if (image_label[row] != 1) return;  // block-uniform
+    const float* x = v_logits + static_cast<size_t>(row) * ld;
+    const float* t = target + static_cast<size_t>(row) * C;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) mx = fmaxf(mx, x[i]);
+    mx = block_max(mx, scratch);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s += expf(x[i] - mx);
+    s = block_sum(s, scratch);
+    const float lse = mx + logf(s);
+    float kl = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        const float ti = t[i];
+        if (ti > 0.f) kl += ti * (logf(ti) - (x[i] - lse));  // kl_div(input=logp, target): xlogy(t,t) - t*input
+    }
+    kl = block_sum(kl, scratch);
+    if (threadIdx.x == 0) {
+        atomicAdd(acc, kl);
+        atomicAdd(acc + 1, 1.0f);
+    }
+}
+__global__ void image_kl_finish_kernel(const float* acc, float* out) { out[0] = acc[0] / acc[1]; }
+
+// dense-mask check: one CTA per (sequence, row); compares the caller's mask row with the descriptor's
+__global__ void __launch_bounds__(256)
+verify_masks_kernel(const SeqDesc* __restrict__ desc, int S, int R, const void* __restrict__ txt_mask, int elem_bytes,
+                    int is_2d, const int64_t* __restrict__ co_mask, int* __restrict__ mismatch) {
+    const int b = blockIdx.y, r = blockIdx.x;
+    const SeqDesc d = desc[b];
+    int bad = 0;
+    if (r < S) {
+        int lo, hi, self;
+        text_row_interval(d, r, S, lo, hi, self);
+        for (int c = threadIdx.x; c < S; c += blockDim.x) {
+            const int want = ((c >= lo && c < hi) || c == self) ? 1 : 0;
+            long long got;
+            const size_t idx = is_2d ? static_cast<size_t>(b) * S + c : (static_cast<size_t>(b) * S + r) * S + c;
+            if (elem_bytes == 1) got = static_cast<const uint8_t*>(txt_mask)[idx];
+            else got = static_cast<const int64_t*>(txt_mask)[idx];
+            bad |= (got != want);
+        }
+    } else if (co_mask != nullptr) {  // rows S .. S+R-1 check the co-attention mask rows
+        const int rr = r - S;
+        int lo, hi;
+        if (d.mode == 1) { lo = 0; hi = min(d.L, S); } else { lo = 1; hi = min(d.ctx, S); }
+        for (int c = threadIdx.x; c < S; c += blockDim.x) {
+            const int want = (c >= lo && c < hi) ? 1 : 0;
+            bad |= (co_mask[(static_cast<size_t>(b) * R + rr) * S + c] != want);
+        }
+    }
+    if (bad) atomicExch(mismatch, 1);
+}
+
+}  // namespace
+
+int pooler_nsp(const float* xt, int ldt_seq, const float* xv, int ldv_seq, int B, int Ht, int Hv, int Hb, const float* Wt,
+               const float* bt, const float* Wv, const float* bv, const float* Wn, const float* bn, float* nsp_logits,
+               cudaStream_t stream) {
+    const size_t smem = sizeof(float) * (Ht + Hv + Hb);
+    pooler_nsp_kernel<<<B, 256, smem, stream>>>(xt, ldt_seq, xv, ldv_seq, Ht, Hv, Hb, Wt, bt, Wv, bv, Wn, bn, nsp_logits);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int lse_from_logits(const float* logits, int ld, int rows, int V, const int* labels, float* logp, float* ul,
+                    cudaStream_t stream) {
+    if (rows == 0) return 0;
+    lse_logits_kernel<<<rows, 256, 0, stream>>>(logits, ld, V, labels, logp, ul);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int lse_from_partials(const float2* partials, int tiles, const float* label_logit, int rows, float* logp, float* ul,
+                      cudaStream_t stream) {
+    if (rows == 0) return 0;
+    lse_partials_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(partials, tiles, label_logit, rows, logp, ul);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int scatter_scores(const float* logp, const float* ul, const int* flat_rows, int n, int B, int S, float* token_logp,
+                   float* token_ul, float* seq_score, cudaStream_t stream) {
+    if (token_logp) UNIMM_CUDA_CHECK(cudaMemsetAsync(token_logp, 0, sizeof(float) * B * S, stream));
+    if (token_ul) UNIMM_CUDA_CHECK(cudaMemsetAsync(token_ul, 0, sizeof(float) * B * S, stream));
+    if (n > 0 && (token_logp || token_ul))
+        scatter_scores_kernel<<<(n + 255) / 256, 256, 0, stream>>>(logp, ul, flat_rows, n, token_logp, token_ul);
+    if (seq_score) seq_score_kernel<<<(B + 127) / 128, 128, 0, stream>>>(logp, flat_rows, n, B, S, seq_score);
+    UNIMM_LAUNCH_CHECK(2);
+    return 0;
+}
+
+int lm_ul_loss(const float* logp, const float* ul, const int* flat_rows, int n, const int64_t* lm_weight, int BS,
+               float* out, cudaStream_t stream) {
+    lm_ul_loss_kernel<<<1, 256, 0, stream>>>(logp, ul, flat_rows, n, lm_weight, BS, out);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int lm_ce_loss(const float* logp, int n, float* out, cudaStream_t stream) {
+    lm_ce_loss_kernel<<<1, 256, 0, stream>>>(logp, n, out);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int nsp_ce_loss(const float* nsp_logits, const int64_t* labels, int B, const float* nsp_weight, float* out,
+                cudaStream_t stream) {
+    nsp_ce_loss_kernel<<<1, 256, 0, stream>>>(nsp_logits, labels, B, nsp_weight, out);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int image_kl_loss(const float* v_logits, int ld, const float* target, const int64_t* image_label, int rows, int C, float* out,
+                  cudaStream_t stream) {
+    // out[1..2] is scratch for (sum, count)
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(out + 1, 0, 2 * sizeof(float), stream));
+    image_kl_kernel<<<rows, 256, 0, stream>>>(v_logits, ld, target, image_label, C, out + 1);
+    image_kl_finish_kernel<<<1, 1, 0, stream>>>(out + 1, out);
+    UNIMM_LAUNCH_CHECK(2);
+    return 0;
+}
+
+int verify_masks(const SeqDesc* desc, int B, int S, int R, const void* txt_mask, int txt_elem_bytes, int txt_is_2d,
+                 const int64_t* co_mask, int* mismatch_flag, cudaStream_t stream) {
+    UNIMM_CHECK(txt_elem_bytes == 1 || txt_elem_bytes == 8, "attention_mask must be bool/uint8 or int64");
+    UNIMM_CHECK(!txt_is_2d, "2-D attention masks are not produced by the reference encoders");
+    dim3 grid(S + (co_mask ? R : 0), B);
+    verify_masks_kernel<<<grid, 256, 0, stream>>>(desc, S, R, txt_mask, txt_elem_bytes, txt_is_2d, co_mask, mismatch_flag);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+}  // namespace unimm

@@ -1,0 +1,110 @@
+// Internal launcher declarations shared by the .cu translation units of libunimm_b200.so.
+// Every launcher returns 0 on success and records a message via set_error() otherwise.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace unimm {
+
+// Epilogue description shared by the tcgen05 and the SIMT GEMMs.  Plain mode: out = act(acc + bias)
+// (+ residual), written as fp32 and/or bf16.  LSE mode (partials != nullptr, tcgen05 only): per row and
+// per 256-wide column tile the pair (max, sum exp(x - max)) of x = acc + bias, and the logit at
+// labels[row]; nothing else is written.
+struct GemmEpilogue {
+    const float* bias = nullptr;      // [N]
+    const float* residual = nullptr;  // [M, ldr] fp32, added after the activation
+    int ldr = 0;
+    float* out_f32 = nullptr;
+    int ldo_f32 = 0;
+    bf16* out_bf16 = nullptr;
+    int ldo_bf16 = 0;
+    int act = ACT_NONE;
+    const int* labels = nullptr;   // LSE mode: [M]
+    float2* partials = nullptr;    // LSE mode: [M, ceil(N/256)]
+    float* label_logit = nullptr;  // LSE mode: [M]
+};
+
+// C = A[M,K] · W[N,K]^T, bf16 operands, fp32 accumulation in TMEM (gemm_umma.cu).
+// tile_n: 0 = auto, 128 or 256.  max_ctas: 0 = one persistent CTA per SM.
+int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int tile_n,
+                   int max_ctas, cudaStream_t stream);
+int gemm_umma_lse_tiles(int N);
+
+// Same contraction in fp32 on the CUDA cores (gemm_simt.cu) — the fp32 parity mode.
+int gemm_simt_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                  cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------ rowwise.cu
+// text embeddings: word + position + (type | type-extension) gather, sum, LayerNorm (ref :326-356)
+int embed_text_ln(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int rows, int H, int vocab,
+                  int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
+                  const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
+                  bf16* out_bf16, int* err_flag, cudaStream_t stream);
+// y = LayerNorm(x) * gamma + beta, eps 1e-12 inside the sqrt, biased variance; x may alias y_f32.
+int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma, const float* beta, float* y_f32,
+                   bf16* y_bf16, cudaStream_t stream);
+// image location term: out[r, :] = loc[idx(r), 0:5] · Wloc[H,5]^T + bloc  (fp32, K = 5)
+int image_loc_embed(const float* loc, const int* feat_index, int B, int R, int H, const float* Wloc, const float* bloc,
+                    float* out, cudaStream_t stream);
+// gather image features into the (optionally bf16) GEMM operand: dst[b*R + r] = feat[feat_index[b]*R + r]
+int gather_features(const float* feat, const int* feat_index, int B, int R, int F, float* dst_f32, bf16* dst_bf16,
+                    cudaStream_t stream);
+int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int n, int H, float* dst_f32, bf16* dst_bf16,
+                cudaStream_t stream);
+int cast_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream);
+int gather_labels(const int64_t* labels, const int* rows, int n, int* out, cudaStream_t stream);
+int expand_key_mask(const float* mask, const int* index, int B, int R, float* out, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------ attention.cu
+enum MaskKind : int {
+    MASK_TEXT_SELF = 0,  // per-row interval (+ self) from the sequence descriptor (gen / dis text self-attention)
+    MASK_KEY_VECTOR = 1, // float key mask [B, Skv] (image padding mask): text->image and image self-attention
+    MASK_CO_INTERVAL = 2 // column interval from the descriptor (image->text co-attention)
+};
+struct AttnArgs {
+    const void* q; int ldq;   // [B*Sq, ...] rows; head h at column h*D
+    const void* k; int ldk;   // [B*Skv, ...]
+    const void* v; int ldv;
+    void* o; int ldo;         // [B*Sq, heads*D]
+    int B, heads, D, Sq, Skv;
+    int mask_kind;
+    const SeqDesc* desc;      // [B]
+    const float* key_mask;    // [B, Skv] (MASK_KEY_VECTOR)
+    float scale;              // 1/sqrt(D)
+};
+int attention_simt_f32(const AttnArgs& a, cudaStream_t stream);
+int attention_simt_bf16(const AttnArgs& a, cudaStream_t stream);
+int attention_mma_bf16(const AttnArgs& a, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------ heads.cu
+// poolers + 'mul' fusion + NSP linear (ref :946-967, :1062-1070), all fp32
+int pooler_nsp(const float* xt, int ldt_seq, const float* xv, int ldv_seq, int B, int Ht, int Hv, int Hb, const float* Wt,
+               const float* bt, const float* Wv, const float* bv, const float* Wn, const float* bn, float* nsp_logits,
+               cudaStream_t stream);
+// fp32 LM head tail: per row log-softmax pick from materialised logits (fp32 mode only)
+int lse_from_logits(const float* logits, int ld, int rows, int V, const int* labels, float* logp, float* ul,
+                    cudaStream_t stream);
+// tcgen05 LM head tail: merge the per-tile (max, sum) partials
+int lse_from_partials(const float2* partials, int tiles, const float* label_logit, int rows, float* logp, float* ul,
+                      cudaStream_t stream);
+// scatter the compact per-row results to dense [B,S] (zero elsewhere) and sum per sequence (val_lm.py:131-136)
+int scatter_scores(const float* logp, const float* ul, const int* flat_rows, int n, int B, int S, float* token_logp,
+                   float* token_ul, float* seq_score, cudaStream_t stream);
+// likelihood / unlikelihood loss (ref :1577-1595); out[0] = loss
+int lm_ul_loss(const float* logp, const float* ul, const int* flat_rows, int n, const int64_t* lm_weight, int BS,
+               float* out, cudaStream_t stream);
+// mean CE over rows when lm_weight is None (ref :1601-1604)
+int lm_ce_loss(const float* logp, int n, float* out, cudaStream_t stream);
+// weighted NSP cross entropy (ref :1605-1621)
+int nsp_ce_loss(const float* nsp_logits, const int64_t* labels, int B, const float* nsp_weight, float* out,
+                cudaStream_t stream);
+// masked image KL (ref :1569-1574)
+int image_kl_loss(const float* v_logits, int ld, const float* target, const int64_t* image_label, int rows, int C, float* out,
+                  cudaStream_t stream);
+// regenerate the dense masks from descriptors and compare with the caller's dense tensors (boundary check)
+int verify_masks(const SeqDesc* desc, int B, int S, int R, const void* txt_mask, int txt_elem_bytes, int txt_is_2d,
+                 const int64_t* co_mask, int* mismatch_flag, cudaStream_t stream);
+
+}  // namespace unimm

@@ -1,0 +1,247 @@
+// HBM-bound row kernels: embedding gather + LayerNorm, LayerNorm, feature/row gathers, casts.
+// One warp per row, 128-bit lane-interleaved accesses, warp-shuffle reductions, fp32 statistics.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unimm {
+namespace {
+
+constexpr float kLnEps = 1e-12f;  // BertLayerNorm eps (reference models/vilbert_dialog.py:322)
+
+template <int NV>
+__device__ __forceinline__ void ln_normalise_store(float4 (&x)[NV], int lane, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float* y_f32, bf16* y_bf16) {
+    constexpr int H = NV * 128;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    const float mean = warp_sum(s) * (1.0f / H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + kLnEps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 y;
+        y.x = (x[i].x - mean) * rstd * g.x + b.x;
+        y.y = (x[i].y - mean) * rstd * g.y + b.y;
+        y.z = (x[i].z - mean) * rstd * g.z + b.z;
+        y.w = (x[i].w - mean) * rstd * g.w + b.w;
+        if (y_f32 != nullptr) *reinterpret_cast<float4*>(y_f32 + c) = y;
+        if (y_bf16 != nullptr) {
+            uint2 p;
+            p.x = pack_bf16x2(y.x, y.y);
+            p.y = pack_bf16x2(y.z, y.w);
+            *reinterpret_cast<uint2*>(y_bf16 + c) = p;
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_kernel(const float* __restrict__ x, int ldx, int rows, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* y_f32, bf16* y_bf16) {
+    constexpr int H = NV * 128;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + static_cast<size_t>(row) * ldx;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
+    ln_normalise_store<NV>(v, lane, gamma, beta, y_f32 ? y_f32 + static_cast<size_t>(row) * H : nullptr,
+                           y_bf16 ? y_bf16 + static_cast<size_t>(row) * H : nullptr);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+embed_text_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
+                     const int64_t* __restrict__ pos_ids, int rows, int vocab, int max_pos, int type_vocab, int type_ext,
+                     const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
+                     const float* __restrict__ type_emb, const float* __restrict__ type_ext_emb,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float* out_f32, bf16* out_bf16,
+                     int* err_flag) {
+    constexpr int H = NV * 128;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    long long id = ids[row], ty = type_ids[row], pos = pos_ids[row];
+    if (id < 0 || id >= vocab || pos < 0 || pos >= max_pos || ty < 0 || ty >= type_vocab + type_ext) {
+        if (lane == 0) atomicExch(err_flag, 1);  // the reference would raise an index error here
+        id = min(max(id, 0LL), (long long)vocab - 1);
+        pos = min(max(pos, 0LL), (long long)max_pos - 1);
+        ty = min(max(ty, 0LL), (long long)(type_vocab + type_ext - 1));
+    }
+    const float* w = word_emb + static_cast<size_t>(id) * H;
+    const float* p = pos_emb + static_cast<size_t>(pos) * H;
+    // ids >= type_vocab_size select the extension table (reference :337-350)
+    const float* t = (ty < type_vocab) ? type_emb + static_cast<size_t>(ty) * H
+                                       : type_ext_emb + static_cast<size_t>(ty - type_vocab) * H;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p + c));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(t + c));
+        v[i] = make_float4((a.x + b.x) + d.x, (a.y + b.y) + d.y, (a.z + b.z) + d.z, (a.w + b.w) + d.w);
+    }
+    ln_normalise_store<NV>(v, lane, gamma, beta, out_f32 ? out_f32 + static_cast<size_t>(row) * H : nullptr,
+                           out_bf16 ? out_bf16 + static_cast<size_t>(row) * H : nullptr);
+}
+
+__global__ void image_loc_kernel(const float* __restrict__ loc, const int* __restrict__ feat_index, int R, int H,
+                                 const float* __restrict__ Wloc, const float* __restrict__ bloc, float* __restrict__ out) {
+    const int row = blockIdx.x;  // b*R + r
+    const int b = row / R, r = row % R;
+    const int src = (feat_index ? feat_index[b] : b) * R + r;
+    float l[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) l[j] = __ldg(loc + static_cast<size_t>(src) * 5 + j);
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc = fmaf(l[j], __ldg(Wloc + h * 5 + j), acc);
+        out[static_cast<size_t>(row) * H + h] = acc + __ldg(bloc + h);
+    }
+}
+
+__global__ void gather_features_kernel(const float* __restrict__ feat, const int* __restrict__ feat_index, int R, int F,
+                                       float* dst_f32, bf16* dst_bf16) {
+    const int row = blockIdx.x;
+    const int b = row / R, r = row % R;
+    const float* s = feat + (static_cast<size_t>(feat_index ? feat_index[b] : b) * R + r) * F;
+    for (int c = threadIdx.x * 4; c < F; c += blockDim.x * 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s + c));
+        if (dst_f32) *reinterpret_cast<float4*>(dst_f32 + static_cast<size_t>(row) * F + c) = v;
+        if (dst_bf16) {
+            uint2 p;
+            p.x = pack_bf16x2(v.x, v.y);
+            p.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(dst_bf16 + static_cast<size_t>(row) * F + c) = p;
+        }
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src_f32, const bf16* __restrict__ src_bf16,
+                                   const int* __restrict__ rows, int H, float* dst_f32, bf16* dst_bf16) {
+    const int i = blockIdx.x;
+    const size_t s = static_cast<size_t>(rows[i]) * H, d = static_cast<size_t>(i) * H;
+    for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+        if (dst_f32) *reinterpret_cast<float4*>(dst_f32 + d + c) = *reinterpret_cast<const float4*>(src_f32 + s + c);
+        if (dst_bf16) *reinterpret_cast<uint2*>(dst_bf16 + d + c) = *reinterpret_cast<const uint2*>(src_bf16 + s + c);
+    }
+}
+
+__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4) {
+    size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        uint2 p;
+        p.x = pack_bf16x2(v.x, v.y);
+        p.y = pack_bf16x2(v.z, v.w);
+        reinterpret_cast<uint2*>(dst)[i] = p;
+    }
+}
+
+__global__ void gather_labels_kernel(const int64_t* __restrict__ labels, const int* __restrict__ rows, int n,
+                                     int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = static_cast<int>(labels[rows[i]]);
+}
+
+__global__ void expand_key_mask_kernel(const float* __restrict__ mask, const int* __restrict__ index, int B, int R,
+                                       float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * R) out[i] = mask[static_cast<size_t>(index[i / R]) * R + (i % R)];
+}
+
+}  // namespace
+
+int gather_labels(const int64_t* labels, const int* rows, int n, int* out, cudaStream_t stream) {
+    if (n == 0) return 0;
+    gather_labels_kernel<<<(n + 255) / 256, 256, 0, stream>>>(labels, rows, n, out);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int expand_key_mask(const float* mask, const int* index, int B, int R, float* out, cudaStream_t stream) {
+    expand_key_mask_kernel<<<(B * R + 255) / 256, 256, 0, stream>>>(mask, index, B, R, out);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma, const float* beta, float* y_f32,
+                   bf16* y_bf16, cudaStream_t stream) {
+    UNIMM_CHECK(rows > 0, "layernorm: no rows");
+    UNIMM_CHECK((ldx & 3) == 0, "layernorm: ldx must be a multiple of 4");
+    const int grid = (rows + 3) / 4;
+    if (H == 768) layernorm_kernel<6><<<grid, 128, 0, stream>>>(x, ldx, rows, gamma, beta, y_f32, y_bf16);
+    else if (H == 1024) layernorm_kernel<8><<<grid, 128, 0, stream>>>(x, ldx, rows, gamma, beta, y_f32, y_bf16);
+    else UNIMM_CHECK(false, "layernorm: hidden size must be 768 or 1024");
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int embed_text_ln(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int rows, int H, int vocab,
+                  int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
+                  const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
+                  bf16* out_bf16, int* err_flag, cudaStream_t stream) {
+    UNIMM_CHECK(rows > 0, "embed: no rows");
+    const int grid = (rows + 3) / 4;
+    if (H == 768)
+        embed_text_ln_kernel<6><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext,
+                                                          word_emb, pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32,
+                                                          out_bf16, err_flag);
+    else if (H == 1024)
+        embed_text_ln_kernel<8><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext,
+                                                          word_emb, pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32,
+                                                          out_bf16, err_flag);
+    else UNIMM_CHECK(false, "embed: hidden size must be 768 or 1024");
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int image_loc_embed(const float* loc, const int* feat_index, int B, int R, int H, const float* Wloc, const float* bloc,
+                    float* out, cudaStream_t stream) {
+    image_loc_kernel<<<B * R, 256, 0, stream>>>(loc, feat_index, R, H, Wloc, bloc, out);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int gather_features(const float* feat, const int* feat_index, int B, int R, int F, float* dst_f32, bf16* dst_bf16,
+                    cudaStream_t stream) {
+    UNIMM_CHECK((F & 3) == 0, "feature size must be a multiple of 4");
+    gather_features_kernel<<<B * R, 256, 0, stream>>>(feat, feat_index, R, F, dst_f32, dst_bf16);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int n, int H, float* dst_f32, bf16* dst_bf16,
+                cudaStream_t stream) {
+    if (n == 0) return 0;
+    UNIMM_CHECK((H & 3) == 0, "gather_rows: H must be a multiple of 4");
+    gather_rows_kernel<<<n, 192, 0, stream>>>(src_f32, src_bf16, rows, H, dst_f32, dst_bf16);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int cast_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream) {
+    UNIMM_CHECK((n & 3) == 0, "cast: element count must be a multiple of 4");
+    const size_t n4 = n / 4;
+    int grid = static_cast<int>((n4 + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    cast_kernel<<<grid, 256, 0, stream>>>(src, dst, n4);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+}  // namespace unimm

@@ -1,0 +1,132 @@
+"""Synthetic VisDial-shaped inputs for the bench and the property tests (no datasets offline).
+
+Builds exactly what the reference's val pipeline would hand to the encoder for generative ranking
+(reference dataloader/dataloader_visdial.py:322-457 driving utils/data_utils.py:encode_input_gen with
+``mask_prob=0``), but directly as token/segment/position/label arrays plus the 4-integer descriptor —
+no dense ``[S,S]`` mask is ever materialised.  Layout of one sequence (S = 256):
+
+    [CLS] caption [SEP] u1 [SEP] ... question [SEP] | answer [SEP] | [MASK]*len(answer) [MASK] | pad
+    └──────────── context rows [0,ctx) ───────────┘ └ A: [ctx,L) ┘ └────── B: [L,T) ──────┘
+
+labels are -1 except on the B copy (answer tokens + [SEP]); B repeats A's position ids; segments
+alternate per utterance starting at 1 (reference pruneRounds / encode_input_gen).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+CLS, SEP, MASK = 101, 102, 103
+S_MAX = 256
+
+
+@dataclass
+class Round:
+    """One (image, round) unit: n candidate sequences that share context and image."""
+    tokens: np.ndarray      # [n,S] int64
+    segments: np.ndarray    # [n,S] int64
+    positions: np.ndarray   # [n,S] int64
+    labels: np.ndarray      # [n,S] int64, -1 = ignore
+    desc: np.ndarray        # [n,4] int32 (mode, ctx, L, last_len)
+
+
+def encode_round_gen(context: Sequence[Sequence[int]], answers: Sequence[Sequence[int]], start_segment: int = 1,
+                     S: int = S_MAX) -> Round:
+    n = len(answers)
+    tokens = np.zeros((n, S), np.int64)
+    segments = np.zeros((n, S), np.int64)
+    positions = np.zeros((n, S), np.int64)
+    labels = np.full((n, S), -1, np.int64)
+    desc = np.zeros((n, 4), np.int32)
+    ctx_tok, ctx_seg = [CLS], [start_segment]
+    seg = start_segment
+    for u in context:
+        ctx_tok += list(u) + [SEP]
+        ctx_seg += [seg] * (len(u) + 1)
+        seg ^= 1
+    ctx = len(ctx_tok)
+    ctx_tok, ctx_seg = np.asarray(ctx_tok, np.int64), np.asarray(ctx_seg, np.int64)
+    for j, ans in enumerate(answers):
+        a = np.asarray(list(ans) + [SEP], np.int64)
+        last = len(a)
+        L, T = ctx + last, ctx + 2 * last
+        if T > S:
+            raise ValueError("synthetic sequence exceeds max_seq_len; shorten the dialog")
+        tokens[j, :ctx] = ctx_tok
+        tokens[j, ctx:L] = a
+        tokens[j, L:T] = MASK
+        segments[j, :ctx] = ctx_seg
+        segments[j, ctx:T] = seg
+        positions[j, :L] = np.arange(L)
+        positions[j, L:T] = np.arange(ctx, L)
+        labels[j, L:T] = a
+        desc[j] = (0, ctx, L, last)
+    return Round(tokens, segments, positions, labels, desc)
+
+
+def encode_round_dis(context, answers, start_segment: int = 1, S: int = S_MAX) -> Round:
+    """Discriminative layout (encode_input_dis with mask_prob=0): no masked copy, no labels."""
+    n = len(answers)
+    r = Round(np.zeros((n, S), np.int64), np.zeros((n, S), np.int64), np.zeros((n, S), np.int64),
+              np.full((n, S), -1, np.int64), np.zeros((n, 4), np.int32))
+    ctx_tok, ctx_seg = [CLS], [start_segment]
+    seg = start_segment
+    for u in context:
+        ctx_tok += list(u) + [SEP]
+        ctx_seg += [seg] * (len(u) + 1)
+        seg ^= 1
+    ctx = len(ctx_tok)
+    for j, ans in enumerate(answers):
+        a = list(ans) + [SEP]
+        L = ctx + len(a)
+        r.tokens[j, :ctx], r.tokens[j, ctx:L] = ctx_tok, a
+        r.segments[j, :ctx], r.segments[j, ctx:L] = ctx_seg, seg
+        r.positions[j, :L] = np.arange(L)
+        r.desc[j] = (1, 0, L, 0)
+    return r
+
+
+def _draw(rng, n, vocab=(1000, 30522)) -> List[int]:
+    return rng.randint(vocab[0], vocab[1], size=n).tolist()
+
+
+def synth_context(rng: np.random.RandomState, round_id: int = 10, caption_len: int = 20, utt_len: int = 10,
+                  question_len: int = 7) -> List[List[int]]:
+    """Caption + (round_id-1) question/answer pairs + the current question.  ``round_id=10`` with one extra
+    history utterance is SURVEY.md §8(d)'s config 1 (239 context positions)."""
+    hist = 2 * (round_id - 1) + (1 if round_id == 10 else 0)
+    return [_draw(rng, caption_len)] + [_draw(rng, utt_len) for _ in range(hist)] + [_draw(rng, question_len)]
+
+
+def synth_answers(rng: np.random.RandomState, n: int = 100, len_range=(1, 7)) -> List[List[int]]:
+    return [_draw(rng, int(rng.randint(len_range[0], len_range[1] + 1))) for _ in range(n)]
+
+
+def synth_image(rng: np.random.RandomState, n_boxes: int = 36, feat_dim: int = 2048):
+    """[37,2048] features with the global mean row prepended, [37,5] boxes, [37] mask
+    (reference utils/image_features_reader.py:85-88,102)."""
+    f = rng.randn(n_boxes, feat_dim).astype(np.float32)
+    f = np.concatenate([f.mean(0, keepdims=True), f], 0)
+    loc = rng.rand(n_boxes + 1, 5).astype(np.float32)
+    loc[0] = [0, 0, 1, 1, 1]
+    return f, loc, np.ones(n_boxes + 1, np.float32)
+
+
+def synth_dialog_rounds(image_id: int, rounds: Sequence[int] = tuple(range(1, 11)), n_candidates: int = 100):
+    """All requested rounds of one synthetic image (seed = image id): (image arrays, [Round, ...])."""
+    rng = np.random.RandomState(100003 + image_id)
+    img = synth_image(rng)
+    out = []
+    for r in rounds:
+        out.append(encode_round_gen(synth_context(rng, r), synth_answers(rng, n_candidates)))
+    return img, out
+
+
+def stack_rounds(rounds: Sequence[Round]):
+    """Concatenate units into flat torch tensors + a feat_index (sequence -> unit) vector."""
+    cat = lambda f: torch.from_numpy(np.concatenate([getattr(r, f) for r in rounds], 0))
+    index = np.concatenate([np.full(len(r.tokens), u, np.int32) for u, r in enumerate(rounds)])
+    return cat("tokens"), cat("segments"), cat("positions"), cat("labels"), cat("desc"), torch.from_numpy(index)

@@ -1,0 +1,143 @@
+"""Drop-in for the reference's ``VisualDialogEncoder`` (reference models/visual_dialog_encoder.py:8-50).
+
+Same constructor argument (the model JSON), same ``forward`` keyword set and return tuple, same 535-key
+``state_dict`` under the ``bert_pretrained.`` prefix — so ``train.forward`` (reference train.py:142-161)
+and a reference checkpoint work unchanged — but the body runs in ``libunimm_b200.so``.
+
+Differences that are deliberate and visible:
+  * inference only (forward + losses); no autograd graph is built (SURVEY.md §8f lists backward as next);
+  * dropout is the identity (the reference's ``.eval()`` behaviour);
+  * dense masks are converted to 4-integer descriptors and verified; other mask patterns raise;
+  * ``score()`` is the fast entry: per-sequence log-likelihoods without the [B,S,30522] logits that
+    ``output_lm_scores=True`` has to materialise for compatibility.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .config import ViLBertConfig
+from .descriptors import descriptors_from_masks
+from .engine import Engine
+from .weights import TIED, param_shapes
+
+
+def _build_param_tree(root: nn.Module, cfg: ViLBertConfig) -> None:
+    """Register parameters under exactly the reference's dotted names (order included)."""
+    made = {}
+    for name, shape in param_shapes(cfg).items():
+        *path, leaf = name.split(".")
+        mod = root
+        for p in path:
+            if p not in mod._modules:
+                mod.add_module(p, nn.Module())
+            mod = mod._modules[p]
+        if name in TIED:
+            param = made[TIED[name]]          # decoder.weight is the word-embedding Parameter (ref :1020)
+        else:
+            param = nn.Parameter(torch.zeros(shape), requires_grad=False)
+        made[name] = param
+        mod.register_parameter(leaf, param)
+
+
+class VisualDialogEncoder(nn.Module):
+    def __init__(self, config_path, precision: str = "fp32", max_sequences: int = 128, device: Optional[int] = None,
+                 verify_masks: bool = True):
+        super().__init__()
+        self.config = config_path if isinstance(config_path, ViLBertConfig) else ViLBertConfig.from_json_file(config_path)
+        self.bert_pretrained = nn.Module()
+        _build_param_tree(self.bert_pretrained, self.config)
+        self.precision, self.max_sequences, self.device_index = precision, max_sequences, device
+        self.verify_masks = verify_masks
+        self._engine: Optional[Engine] = None
+        self._dirty = True
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._dirty = True
+        return r
+
+    def engine(self) -> Engine:
+        if self._engine is None or self._dirty:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(self.config, self.state_dict(), precision=self.precision,
+                                  max_sequences=self.max_sequences, device=self.device_index)
+            self._dirty = False
+        return self._engine
+
+    # ------------------------------------------------------------------ fast entry
+    @torch.no_grad()
+    def score(self, input_ids, image_feat, image_loc, token_type_ids, token_position_ids, masked_lm_labels,
+              image_attention_mask, desc=None, attention_mask=None, co_attention_mask=None, feat_index=None,
+              want=("seq_score", "nsp_scores")):
+        """Per-sequence generative scores (val_lm.py:131-136) and NSP logits; chunks internally."""
+        eng = self.engine()
+        if desc is None:
+            desc = descriptors_from_masks(attention_mask, co_attention_mask, verify=self.verify_masks)
+        B = input_ids.shape[0]
+        outs = {k: [] for k in want}
+        for s in range(0, B, eng.max_sequences):
+            e = min(B, s + eng.max_sequences)
+            sl = slice(s, e)
+            if feat_index is None:
+                f, l, m, fi = image_feat[sl], image_loc[sl], image_attention_mask[sl], None
+            else:
+                f, l, m, fi = image_feat, image_loc, image_attention_mask, feat_index[sl]
+            o = eng.forward(input_ids[sl], token_type_ids[sl], token_position_ids[sl], desc[sl], f, l, m, feat_index=fi,
+                            masked_lm_labels=masked_lm_labels[sl], want=want)
+            for k in want:
+                outs[k].append(o[k])
+        return {k: torch.cat(v, 0) for k, v in outs.items()}
+
+    # ------------------------------------------------------------------ reference signature
+    @torch.no_grad()
+    def forward(self, input_ids, image_feat, image_loc, sep_indices=None, sep_len=None, token_type_ids=None,
+                token_position_ids=None, attention_mask=None, masked_lm_labels=None, next_sentence_label=None,
+                head_mask=None, random_round_indices=None, output_nsp_scores=False, output_lm_scores=False,
+                image_attention_mask=None, co_attention_mask=None, image_label=None, image_target=None, nsp_weight=None,
+                lm_weight=None):
+        eng = self.engine()
+        B, S = input_ids.shape
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        if token_position_ids is None:
+            token_position_ids = torch.arange(S, dtype=torch.long, device=input_ids.device).unsqueeze(0).expand(B, S)
+        if image_attention_mask is None:
+            image_attention_mask = torch.ones(image_feat.shape[:2])
+        if attention_mask is None or co_attention_mask is None:
+            raise ValueError("attention_mask and co_attention_mask are required (the reference callers always pass them)")
+        desc = descriptors_from_masks(attention_mask, co_attention_mask, verify=self.verify_masks)
+        training = next_sentence_label is not None and masked_lm_labels is not None and image_target is not None
+        want = []
+        if output_nsp_scores:
+            want.append("nsp_scores")
+        if output_lm_scores:
+            want.append("prediction_scores_t")
+        if training:
+            if B > eng.max_sequences:
+                raise ValueError(f"the loss branch needs the whole batch in one chunk: construct with max_sequences >= {B}")
+            want.append("losses")
+            o = eng.forward(input_ids, token_type_ids, token_position_ids, desc, image_feat, image_loc, image_attention_mask,
+                            masked_lm_labels=masked_lm_labels, lm_weight=lm_weight, next_sentence_label=next_sentence_label,
+                            image_label=image_label, image_target=image_target, nsp_weight=nsp_weight, want=tuple(want))
+            losses = o["losses"]
+            out = (losses[0:1].clone(), losses[1:2].clone(), losses[2:3].clone())
+            chunks = [o]
+        else:
+            out = (None, None, None)
+            chunks = []
+            for s in range(0, B, eng.max_sequences):
+                sl = slice(s, min(B, s + eng.max_sequences))
+                chunks.append(eng.forward(input_ids[sl], token_type_ids[sl], token_position_ids[sl], desc[sl], image_feat[sl],
+                                          image_loc[sl], image_attention_mask[sl],
+                                          masked_lm_labels=None if masked_lm_labels is None else masked_lm_labels[sl],
+                                          want=tuple(want)))
+        if output_nsp_scores:
+            out = out + (torch.cat([c["nsp_scores"] for c in chunks], 0),)
+        if output_lm_scores:
+            out = out + (torch.cat([c["prediction_scores_t"] for c in chunks], 0),)
+        return out
