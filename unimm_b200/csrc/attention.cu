@@ -228,7 +228,4 @@ int attention_simt_bf16(const AttnArgs& a, cudaStream_t stream) {
     return a.D == 64 ? launch_simt<bf16, 64>(a, stream) : launch_simt<bf16, 128>(a, stream);
 }
 
-// Tensor-core attention entry; until the mma kernel lands it runs the CUDA-core kernel on bf16 tensors.
-int attention_mma_bf16(const AttnArgs& a, cudaStream_t stream) { return attention_simt_bf16(a, stream); }
-
 }  // namespace unimm
