@@ -29,8 +29,11 @@ extern "C" {
 typedef struct unimm_engine unimm_engine_t;
 
 /* compute precision of the projections / attention */
-enum { UNIMM_PREC_FP32 = 0, /* CUDA-core fp32: the <=1e-4 parity mode            */
-       UNIMM_PREC_BF16 = 1  /* tcgen05 bf16 x bf16 -> fp32 (TMEM): throughput mode */ };
+enum { UNIMM_PREC_FP32 = 0, /* CUDA-core fp32: the <=1e-4 parity mode                              */
+       UNIMM_PREC_BF16 = 1, /* tcgen05 bf16 x bf16 -> fp32 (TMEM)                                  */
+       UNIMM_PREC_FP16 = 2  /* tcgen05 fp16 x fp16 -> fp32 (TMEM): same rate, 8x finer rounding    */ };
+/* 16-bit encodings of the single-kernel entry points below */
+enum { UNIMM_LP_BF16 = 0, UNIMM_LP_FP16 = 1 };
 
 /* Mirrors the fields of the reference's BertConfig that the hot path reads
  * (models/vilbert_dialog.py:131-247, config/bert_base_6layer_6conect.json). */
@@ -123,26 +126,34 @@ typedef struct {
 } unimm_host_batch_t;
 int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream);
 
+/* Per-kernel-class device timing for bench.py: between begin and end every GEMM / attention / LayerNorm /
+ * LM-head launch of this engine is bracketed by CUDA events on its launch stream.  end() synchronises and
+ * returns, for classes 0 = tcgen05 or fp32 GEMM, 1 = attention, 2 = LayerNorm rows, 3 = fused LM-head GEMM,
+ * 4 = other: summed milliseconds, summed algorithmic work (FLOPs; bytes for class 2) and launch counts.
+ * ncat must be >= 5. */
+int unimm_profile_begin(unimm_engine_t* e);
+int unimm_profile_end(unimm_engine_t* e, double* ms, double* work, int64_t* launches, int ncat);
+
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t unimm_launch_count(void);
 void unimm_reset_launch_count(void);
 
 /* ---- single-kernel entry points (used by tests/ to check each kernel against the oracle) ---- */
-int unimm_k_gemm_bf16(const void* d_A_bf16, int lda, const void* d_W_bf16, int ldw, int M, int N, int K, const float* d_bias,
-                      const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_bf16,
-                      int ldo_bf16, int tile_n, int max_ctas, void* stream);
+int unimm_k_gemm_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias,
+                    const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp,
+                    int tile_n, int max_ctas, int lp_kind, void* stream);
 int unimm_k_gemm_f32(const float* d_A, int lda, const float* d_W, int ldw, int M, int N, int K, const float* d_bias,
                      const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* stream);
-int unimm_k_lm_head_bf16(const void* d_H_bf16, int ldh, const void* d_E_bf16, int lde, int rows, int V, int K,
-                         const float* d_bias, const int32_t* d_labels, float* d_partials_scratch, float* d_label_logit_scratch,
-                         float* d_logp, float* d_ul, void* stream);
+int unimm_k_lm_head_lp(const void* d_H_lp, int ldh, const void* d_E_lp, int lde, int rows, int V, int K,
+                       const float* d_bias, const int32_t* d_labels, float* d_partials_scratch, float* d_label_logit_scratch,
+                       float* d_logp, float* d_ul, int lp_kind, void* stream);
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
-                      void* d_y_bf16, void* stream);
-int unimm_k_cast_bf16(const float* d_src, void* d_dst_bf16, int64_t n, void* stream);
-/* is_bf16 = 0: fp32 tensors, 1: bf16 tensors.  impl: 0 = CUDA-core kernel, 1 = tensor-core kernel (bf16 only). */
+                      void* d_y_lp, int lp_kind, void* stream);
+int unimm_k_cast_lp(const float* d_src, void* d_dst_lp, int64_t n, int lp_kind, void* stream);
+/* elem_kind = 0: fp32 tensors, 1: bf16, 2: fp16.  impl: 0 = CUDA-core kernel, 1 = tensor-core kernel (16-bit only). */
 int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,
                       int heads, int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc,
-                      const float* d_key_mask, int is_bf16, int impl, void* stream);
+                      const float* d_key_mask, int elem_kind, int impl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,10 @@ def test_gemm_f32(M, N, K, act, res):
 
 
 # ----------------------------------------------------------------------------------------------- tcgen05 GEMM
+LP = {"bf16": (torch.bfloat16, 0), "fp16": (torch.float16, 1)}
+
+
+@pytest.mark.parametrize("lp", ["bf16", "fp16"])
 @pytest.mark.parametrize("M,N,K,act,res,tile_n", [
     (128, 256, 64, 0, False, 256),       # one tile, one k-block: descriptor / swizzle sanity
     (128, 128, 128, 0, False, 128),
@@ -61,15 +65,16 @@ def test_gemm_f32(M, N, K, act, res):
     (130, 1601, 1024, 0, False, 128),    # image decoder: ragged N
     (40000, 768, 768, 0, False, 256),    # many tiles per CTA: exercises ring + accumulator phases
 ])
-def test_gemm_umma_bf16(M, N, K, act, res, tile_n):
-    A = rnd(M, K, seed=1).to(torch.bfloat16)
-    W = rnd(N, K, scale=0.05, seed=2).to(torch.bfloat16)
+def test_gemm_umma(M, N, K, act, res, tile_n, lp):
+    dt, kind = LP[lp]
+    A = rnd(M, K, seed=1).to(dt)
+    W = rnd(N, K, scale=0.05, seed=2).to(dt)
     b = rnd(N, seed=3)
     R = rnd(M, N, seed=4) if res else None
     o32 = torch.zeros(M, N, device=DEV)
-    o16 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-    check(lib.unimm_k_gemm_bf16(ptr(A), K, ptr(W), K, M, N, K, ptr(b), ptr(R), N, act, ptr(o32), N, ptr(o16), N, tile_n, 0,
-                                stream()))
+    o16 = torch.zeros(M, N, device=DEV, dtype=dt)
+    check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(W), K, M, N, K, ptr(b), ptr(R), N, act, ptr(o32), N, ptr(o16), N, tile_n, 0, kind,
+                              stream()))
     torch.cuda.synchronize()
     ref = A.double() @ W.double().t() + b.double()
     if act == 1:
@@ -78,7 +83,7 @@ def test_gemm_umma_bf16(M, N, K, act, res, tile_n):
         ref = ref + R.double()
     err = (o32.double() - ref).abs().max().item()
     err16 = (o16.double() - ref).abs().max().item()
-    print(f"gemm_umma {M}x{N}x{K} act={act} res={res}: fp32-out err {err:.3e}, bf16-out err {err16:.3e}")
+    print(f"gemm_umma[{lp}] {M}x{N}x{K} act={act} res={res}: fp32-out err {err:.3e}, 16-bit-out err {err16:.3e}")
     assert err < 2e-3 * max(1.0, math.sqrt(K / 768))     # operands are exactly representable: only fp32 accumulation order
     assert err16 < 0.05 * max(1.0, ref.abs().max().item() / 4)
 
@@ -88,15 +93,17 @@ def test_gemm_umma_persistent_few_ctas():
     M, N, K = 128 * 10, 256 * 6, 320
     A, W = rnd(M, K, seed=5).to(torch.bfloat16), rnd(N, K, scale=0.05, seed=6).to(torch.bfloat16)
     o32 = torch.zeros(M, N, device=DEV)
-    check(lib.unimm_k_gemm_bf16(ptr(A), K, ptr(W), K, M, N, K, None, None, 0, 0, ptr(o32), N, None, 0, 256, 3, stream()))
+    check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(W), K, M, N, K, None, None, 0, 0, ptr(o32), N, None, 0, 256, 3, 0, stream()))
     ref = A.double() @ W.double().t()
     assert (o32.double() - ref).abs().max().item() < 2e-3
 
 
-def test_lm_head_lse_bf16():
+@pytest.mark.parametrize("lp", ["bf16", "fp16"])
+def test_lm_head_lse(lp):
+    dt, kind = LP[lp]
     rows, V, K = 200, 30522, 768
-    Hm = rnd(rows, K, seed=7).to(torch.bfloat16)
-    E = rnd(V, K, scale=0.02, seed=8).to(torch.bfloat16)
+    Hm = rnd(rows, K, seed=7).to(dt)
+    E = rnd(V, K, scale=0.02, seed=8).to(dt)
     bias = rnd(V, scale=0.02, seed=9)
     labels = torch.randint(0, V, (rows,), generator=torch.Generator().manual_seed(3)).to(torch.int32)
     labels[0], labels[1] = 0, V - 1
@@ -105,8 +112,8 @@ def test_lm_head_lse_bf16():
     partials = torch.zeros(rows, tiles, 2, device=DEV)
     lab_logit = torch.zeros(rows, device=DEV)
     logp, ul = torch.zeros(rows, device=DEV), torch.zeros(rows, device=DEV)
-    check(lib.unimm_k_lm_head_bf16(ptr(Hm), K, ptr(E), K, rows, V, K, ptr(bias), ptr(labels), ptr(partials), ptr(lab_logit),
-                                   ptr(logp), ptr(ul), stream()))
+    check(lib.unimm_k_lm_head_lp(ptr(Hm), K, ptr(E), K, rows, V, K, ptr(bias), ptr(labels), ptr(partials), ptr(lab_logit),
+                                 ptr(logp), ptr(ul), kind, stream()))
     logits = Hm.double() @ E.double().t() + bias.double()
     ref = torch.log_softmax(logits, -1).gather(1, labels.long()[:, None])[:, 0]
     ref_ul = torch.log(torch.clamp(1.0 - torch.softmax(logits, -1), min=1e-6)).gather(1, labels.long()[:, None])[:, 0]
@@ -122,10 +129,13 @@ def test_layernorm(H):
     x, g, b = rnd(rows, H, scale=3.0, seed=1) + 0.5, 1 + 0.1 * rnd(H, seed=2), 0.1 * rnd(H, seed=3)
     y32 = torch.empty(rows, H, device=DEV)
     y16 = torch.empty(rows, H, device=DEV, dtype=torch.bfloat16)
-    check(lib.unimm_k_layernorm(ptr(x), H, rows, H, ptr(g), ptr(b), ptr(y32), ptr(y16), stream()))
+    check(lib.unimm_k_layernorm(ptr(x), H, rows, H, ptr(g), ptr(b), ptr(y32), ptr(y16), 0, stream()))
+    yh = torch.empty(rows, H, device=DEV, dtype=torch.float16)
+    check(lib.unimm_k_layernorm(ptr(x), H, rows, H, ptr(g), ptr(b), None, ptr(yh), 1, stream()))
     ref = torch.nn.functional.layer_norm(x.double(), (H,), g.double(), b.double(), 1e-12)
     assert (y32.double() - ref).abs().max().item() < 2e-5
     assert (y16.double() - ref).abs().max().item() < 0.03
+    assert (yh.double() - ref).abs().max().item() < 0.004
 
 
 # ----------------------------------------------------------------------------------------------- attention
@@ -146,36 +156,38 @@ def make_desc():
     return torch.tensor(rows, dtype=torch.int32, device=DEV)
 
 
-@pytest.mark.parametrize("is_bf16,impl", [(0, 0), (1, 0), (1, 1)])
-def test_text_self_attention(is_bf16, impl):
+ELEM = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}
+ATOL = {0: 2e-5, 1: 3e-2, 2: 4e-3}
+
+
+@pytest.mark.parametrize("kind,impl", [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1)])
+def test_text_self_attention(kind, impl):
     desc = make_desc()
     B, S, heads, d = desc.shape[0], 256, 12, 64
     H = heads * d
     qkv = rnd(B * S, 3 * H, seed=11)
     allow = dense_text_mask(desc, S)
     valid = allow.any(-1)                                  # padding rows are garbage-by-design in the reference
-    if is_bf16:
-        qkv = qkv.to(torch.bfloat16)
+    qkv = qkv.to(ELEM[kind])
     out = torch.zeros(B * S, H, device=DEV, dtype=qkv.dtype)
     e = qkv.element_size()
     base = qkv.data_ptr()
     check(lib.unimm_k_attention(C.c_void_p(base), 3 * H, C.c_void_p(base + e * H), 3 * H, C.c_void_p(base + 2 * e * H), 3 * H,
-                                ptr(out), H, B, heads, d, S, S, _lib.MASK_TEXT_SELF, ptr(desc), None, is_bf16, impl, stream()))
+                                ptr(out), H, B, heads, d, S, S, _lib.MASK_TEXT_SELF, ptr(desc), None, kind, impl, stream()))
     q3 = qkv.view(B, S, 3 * H)
     ref = ref_attention(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], heads, allow)
     err = (out.view(B, S, H).double() - ref)[valid].abs().max().item()
-    print(f"text self-attention bf16={is_bf16} impl={impl}: max err on valid rows {err:.3e}")
-    assert err < (3e-2 if is_bf16 else 2e-5)
+    print(f"text self-attention kind={kind} impl={impl}: max err on valid rows {err:.3e}")
+    assert err < ATOL[kind]
     assert torch.isfinite(out.float()).all()
 
 
-@pytest.mark.parametrize("is_bf16,impl", [(0, 0), (1, 0), (1, 1)])
-def test_cross_and_image_attention(is_bf16, impl):
+@pytest.mark.parametrize("kind,impl", [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1)])
+def test_cross_and_image_attention(kind, impl):
     desc = make_desc()
     B, S, R, heads, d = desc.shape[0], 256, 37, 8, 128
     H = heads * d
-    dt = torch.bfloat16 if is_bf16 else torch.float32
-    tol = 3e-2 if is_bf16 else 2e-5
+    dt, tol = ELEM[kind], ATOL[kind]
     qkv_t, qkv_v = rnd(B * S, 3 * H, seed=21).to(dt), rnd(B * R, 3 * H, seed=22).to(dt)
     e = qkv_t.element_size()
     img_mask = torch.ones(B, R, device=DEV)
@@ -185,7 +197,7 @@ def test_cross_and_image_attention(is_bf16, impl):
     o1 = torch.zeros(B * S, H, device=DEV, dtype=dt)
     check(lib.unimm_k_attention(ptr(qkv_t), 3 * H, C.c_void_p(qkv_v.data_ptr() + e * H), 3 * H,
                                 C.c_void_p(qkv_v.data_ptr() + 2 * e * H), 3 * H, ptr(o1), H, B, heads, d, S, R,
-                                _lib.MASK_KEY_VECTOR, None, ptr(img_mask), is_bf16, impl, stream()))
+                                _lib.MASK_KEY_VECTOR, None, ptr(img_mask), kind, impl, stream()))
     t3, v3 = qkv_t.view(B, S, 3 * H), qkv_v.view(B, R, 3 * H)
     ref1 = ref_attention(t3[..., :H], v3[..., H:2 * H], v3[..., 2 * H:], heads, img_mask[:, None, :].expand(B, S, R))
     err1 = (o1.view(B, S, H).double() - ref1).abs().max().item()
@@ -193,7 +205,7 @@ def test_cross_and_image_attention(is_bf16, impl):
     o2 = torch.zeros(B * R, H, device=DEV, dtype=dt)
     check(lib.unimm_k_attention(ptr(qkv_v), 3 * H, C.c_void_p(qkv_t.data_ptr() + e * H), 3 * H,
                                 C.c_void_p(qkv_t.data_ptr() + 2 * e * H), 3 * H, ptr(o2), H, B, heads, d, R, S,
-                                _lib.MASK_CO_INTERVAL, ptr(desc), None, is_bf16, impl, stream()))
+                                _lib.MASK_CO_INTERVAL, ptr(desc), None, kind, impl, stream()))
     co = dense_co_mask(desc, S).bool()
     ref2 = ref_attention(v3[..., :H], t3[..., H:2 * H], t3[..., 2 * H:], heads, co[:, None, :].expand(B, R, S))
     err2 = (o2.view(B, R, H).double() - ref2).abs().max().item()
@@ -201,10 +213,10 @@ def test_cross_and_image_attention(is_bf16, impl):
     o3 = torch.zeros(B * R, H, device=DEV, dtype=dt)
     check(lib.unimm_k_attention(ptr(qkv_v), 3 * H, C.c_void_p(qkv_v.data_ptr() + e * H), 3 * H,
                                 C.c_void_p(qkv_v.data_ptr() + 2 * e * H), 3 * H, ptr(o3), H, B, heads, d, R, R,
-                                _lib.MASK_KEY_VECTOR, None, ptr(img_mask), is_bf16, impl, stream()))
+                                _lib.MASK_KEY_VECTOR, None, ptr(img_mask), kind, impl, stream()))
     ref3 = ref_attention(v3[..., :H], v3[..., H:2 * H], v3[..., 2 * H:], heads, img_mask[:, None, :].expand(B, R, R))
     err3 = (o3.view(B, R, H).double() - ref3).abs().max().item()
-    print(f"cross attention bf16={is_bf16} impl={impl}: t->i {err1:.3e}  i->t {err2:.3e}  i self {err3:.3e}")
+    print(f"cross attention kind={kind} impl={impl}: t->i {err1:.3e}  i->t {err2:.3e}  i self {err3:.3e}")
     assert max(err1, err2, err3) < tol
 
 

@@ -11,7 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libunimm_b200.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+LP_BF16, LP_FP16 = 0, 1
 MASK_TEXT_SELF, MASK_KEY_VECTOR, MASK_CO_INTERVAL = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
@@ -65,13 +66,15 @@ SYMBOLS = {
     "unimm_forward": (C.c_int, [_P, C.POINTER(Batch), C.POINTER(Outputs), _P]),
     "unimm_verify_masks": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "unimm_score_host": (C.c_int, [_P, C.POINTER(HostBatch), _P, _P, _P]),
+    "unimm_profile_begin": (C.c_int, [_P]),
+    "unimm_profile_end": (C.c_int, [_P, _P, _P, _P, _I]),
     "unimm_launch_count": (C.c_int64, []),
     "unimm_reset_launch_count": (None, []),
-    "unimm_k_gemm_bf16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "unimm_k_gemm_lp": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "unimm_k_gemm_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
-    "unimm_k_lm_head_bf16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "unimm_k_layernorm": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "unimm_k_cast_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "unimm_k_lm_head_lp": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "unimm_k_layernorm": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "unimm_k_cast_lp": (C.c_int, [_P, _P, C.c_int64, _I, _P]),
     "unimm_k_attention": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
 }
 

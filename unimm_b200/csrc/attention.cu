@@ -30,6 +30,8 @@ template <>
 __device__ __forceinline__ float attn_exp<float>(float x) { return expf(x); }
 template <>
 __device__ __forceinline__ float attn_exp<bf16>(float x) { return __expf(x); }
+template <>
+__device__ __forceinline__ float attn_exp<fp16>(float x) { return __expf(x); }
 
 template <typename T, int D>
 __global__ void __launch_bounds__(NW * 32)
@@ -223,8 +225,9 @@ int attention_simt_f32(const AttnArgs& a, cudaStream_t stream) {
     return a.D == 64 ? launch_simt<float, 64>(a, stream) : launch_simt<float, 128>(a, stream);
 }
 
-int attention_simt_bf16(const AttnArgs& a, cudaStream_t stream) {
+int attention_simt_lp(const AttnArgs& a, cudaStream_t stream) {
     UNIMM_TRY(check_args(a));
+    if (a.lp_kind == LP_FP16) return a.D == 64 ? launch_simt<fp16, 64>(a, stream) : launch_simt<fp16, 128>(a, stream);
     return a.D == 64 ? launch_simt<bf16, 64>(a, stream) : launch_simt<bf16, 128>(a, stream);
 }
 

@@ -32,18 +32,26 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool FP16>
+__device__ __forceinline__ void mma_lp(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if (FP16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return FP16 ? pack_fp16x2(lo, hi) : pack_bf16x2(lo, hi); }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
-template <int D>
+template <int D, bool FP16>
 __global__ void __launch_bounds__(128)
 attn_mma_kernel(AttnArgs a, int kv_rows_max) {
     constexpr int LD = D + PADE;       // smem row stride in elements
@@ -149,8 +157,8 @@ attn_mma_kernel(AttnArgs a, int kv_rows_max) {
             for (int nb2 = 0; nb2 < 4; ++nb2) {
                 uint32_t kb[4];
                 ldsm_x4(kb, k_tile + (nb2 * 16 + (lane & 7) + 8 * (lane >> 4)) * LD + ks * 16 + 8 * ((lane >> 3) & 1));
-                mma_bf16(s[2 * nb2], qa, kb[0], kb[1]);
-                mma_bf16(s[2 * nb2 + 1], qa, kb[2], kb[3]);
+                mma_lp<FP16>(s[2 * nb2], qa, kb[0], kb[1]);
+                mma_lp<FP16>(s[2 * nb2 + 1], qa, kb[2], kb[3]);
             }
         }
         // scale (folded into the exp2 argument) + mask
@@ -199,16 +207,16 @@ attn_mma_kernel(AttnArgs a, int kv_rows_max) {
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
             uint32_t pa[4];
-            pa[0] = pack_bf16x2(s[2 * kc][0], s[2 * kc][1]);
-            pa[1] = pack_bf16x2(s[2 * kc][2], s[2 * kc][3]);
-            pa[2] = pack_bf16x2(s[2 * kc + 1][0], s[2 * kc + 1][1]);
-            pa[3] = pack_bf16x2(s[2 * kc + 1][2], s[2 * kc + 1][3]);
+            pa[0] = pack2<FP16>(s[2 * kc][0], s[2 * kc][1]);
+            pa[1] = pack2<FP16>(s[2 * kc][2], s[2 * kc][3]);
+            pa[2] = pack2<FP16>(s[2 * kc + 1][0], s[2 * kc + 1][1]);
+            pa[3] = pack2<FP16>(s[2 * kc + 1][2], s[2 * kc + 1][3]);
 #pragma unroll
             for (int db2 = 0; db2 < D / 16; ++db2) {
                 uint32_t vb[4];
                 ldsm_x4_trans(vb, v_tile + (kc * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + db2 * 16 + 8 * (lane >> 4));
-                mma_bf16(o[2 * db2], pa, vb[0], vb[1]);
-                mma_bf16(o[2 * db2 + 1], pa, vb[2], vb[3]);
+                mma_lp<FP16>(o[2 * db2], pa, vb[0], vb[1]);
+                mma_lp<FP16>(o[2 * db2 + 1], pa, vb[2], vb[3]);
             }
         }
     }
@@ -224,34 +232,35 @@ attn_mma_kernel(AttnArgs a, int kv_rows_max) {
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {
         const int col = i * 8 + 2 * t;
-        if (row0 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row0) * a.ldo + col) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
-        if (row1 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row1) * a.ldo + col) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+        if (row0 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row0) * a.ldo + col) = pack2<FP16>(o[i][0] * inv0, o[i][1] * inv0);
+        if (row1 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row1) * a.ldo + col) = pack2<FP16>(o[i][2] * inv1, o[i][3] * inv1);
     }
 }
 
-template <int D>
+template <int D, bool FP16>
 int launch_mma(const AttnArgs& a, cudaStream_t stream) {
     const int kv_rows_max = ((a.Skv + MKT - 1) / MKT) * MKT;
     const size_t smem = sizeof(bf16) * (MQT + 2 * static_cast<size_t>(kv_rows_max)) * (D + PADE) + sizeof(float) * kv_rows_max;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel<D, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     dim3 grid((a.Sq + MQT - 1) / MQT, a.heads, a.B);
-    attn_mma_kernel<D><<<grid, 128, smem, stream>>>(a, kv_rows_max);
+    attn_mma_kernel<D, FP16><<<grid, 128, smem, stream>>>(a, kv_rows_max);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
 
 }  // namespace
 
-int attention_mma_bf16(const AttnArgs& a, cudaStream_t stream) {
+int attention_mma_lp(const AttnArgs& a, cudaStream_t stream) {
     UNIMM_CHECK(a.B > 0 && a.B <= 65535 && a.heads > 0 && a.Sq > 0 && a.Skv > 0 && a.Skv <= 256, "attention: bad problem size");
     UNIMM_CHECK(a.D == 64 || a.D == 128, "attention: head dim must be 64 or 128");
     UNIMM_CHECK((a.ldq % 8) == 0 && (a.ldk % 8) == 0 && (a.ldv % 8) == 0 && (a.ldo % 2) == 0, "attention: rows must be 16-byte aligned");
     UNIMM_CHECK(a.mask_kind == MASK_KEY_VECTOR ? a.key_mask != nullptr : a.desc != nullptr, "attention: mask operand missing");
-    return a.D == 64 ? launch_mma<64>(a, stream) : launch_mma<128>(a, stream);
+    if (a.lp_kind == LP_FP16) return a.D == 64 ? launch_mma<64, true>(a, stream) : launch_mma<128, true>(a, stream);
+    return a.D == 64 ? launch_mma<64, false>(a, stream) : launch_mma<128, false>(a, stream);
 }
 
 }  // namespace unimm

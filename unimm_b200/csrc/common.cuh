@@ -97,6 +97,35 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// The tensor-core path stores activations / weights in one of two 16-bit encodings chosen per engine.
+// Buffers are typed bf16* throughout (storage only); `kind` says how the 16 bits are to be read.
+//   LP_BF16  8-bit exponent, 7-bit mantissa
+//   LP_FP16  5-bit exponent, 10-bit mantissa (8x finer rounding; values saturate at +-65504 instead of
+//            overflowing — every tensor stored this way is LayerNorm-bounded, a GELU output, a QKV
+//            projection or an attention context, far inside that range)
+enum LpKind : int { LP_BF16 = 0, LP_FP16 = 1 };
+typedef __half fp16;
+
+template <>
+__device__ __forceinline__ float to_f32<fp16>(fp16 v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ fp16 from_f32<fp16>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+
+__device__ __forceinline__ uint32_t pack_fp16x2(float lo, float hi) {
+    __half2 p = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ uint32_t pack_lp2(float lo, float hi, int kind) {
+    return kind == LP_FP16 ? pack_fp16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ bf16 lp_from_f32(float v, int kind) {
+    if (kind == LP_FP16) {
+        const fp16 h = from_f32<fp16>(v);
+        return *reinterpret_cast<const bf16*>(&h);
+    }
+    return __float2bfloat16_rn(v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sequence descriptor: the 4 integers that regenerate every dense attention mask of the reference
 // (utils/data_utils.py:149-210 generative, :353-354 discriminative).

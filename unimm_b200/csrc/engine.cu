@@ -103,6 +103,24 @@ struct unimm_engine {
 
     static constexpr int kLogitRows = 2048;
 
+    // optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline numbers)
+    enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ROWWISE = 2, CAT_LMHEAD = 3, CAT_OTHER = 4, NCAT = 5 };
+    struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+    bool profiling = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    cudaEvent_t prof_event() {
+        if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    struct Prof {   // RAII: event before / after whatever is launched in its scope
+        unimm_engine* e; cudaStream_t st; ProfRec r; bool on;
+        Prof(unimm_engine* e_, int cat, double work, cudaStream_t st_) : e(e_), st(st_), on(e_->profiling) {
+            if (on) { r.a = e->prof_event(); r.b = e->prof_event(); r.cat = cat; r.work = work; cudaEventRecord(r.a, st); }
+        }
+        ~Prof() { if (on) { cudaEventRecord(r.b, st); e->prof_recs.push_back(r); } }
+    };
+
     template <typename T>
     int dalloc(T** p, size_t count) {
         void* q = nullptr;
@@ -112,7 +130,8 @@ struct unimm_engine {
         *p = static_cast<T*>(q);
         return 0;
     }
-    bool lp() const { return prec == UNIMM_PREC_BF16; }
+    bool lp() const { return prec == UNIMM_PREC_BF16 || prec == UNIMM_PREC_FP16; }
+    int lp_kind() const { return prec == UNIMM_PREC_FP16 ? LP_FP16 : LP_BF16; }
     size_t esz() const { return lp() ? 2 : 4; }
 
     int get(const std::string& name, const DevTensor** out, std::vector<int64_t> shape) {
@@ -178,7 +197,7 @@ int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each,
     if (lp() && !keep_f32_only) {
         bf16* h = nullptr;
         UNIMM_TRY(dalloc(&h, static_cast<size_t>(L->N) * K));
-        UNIMM_TRY(cast_f32_to_bf16(w, h, static_cast<size_t>(L->N) * K, 0));
+        UNIMM_TRY(cast_f32_to_lp(w, h, static_cast<size_t>(L->N) * K, lp_kind(), 0));
         L->wlp = h;
     }
     return 0;
@@ -262,7 +281,7 @@ int unimm_engine::finalize() {
         if (lp()) {
             bf16* h = nullptr;
             UNIMM_TRY(dalloc(&h, static_cast<size_t>(c.vocab_size) * H));
-            UNIMM_TRY(cast_f32_to_bf16(lm_decoder.w32, h, static_cast<size_t>(c.vocab_size) * H, 0));
+            UNIMM_TRY(cast_f32_to_lp(lm_decoder.w32, h, static_cast<size_t>(c.vocab_size) * H, lp_kind(), 0));
             lm_decoder.wlp = h;
         }
     }
@@ -321,6 +340,8 @@ int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const
     ep.residual = residual;
     ep.ldr = ldr;
     ep.act = act;
+    ep.lp_kind = lp_kind();
+    Prof prof(this, CAT_GEMM, 2.0 * M * L.N * L.K, st);
     if (lp()) {
         ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
         ep.out_bf16 = static_cast<bf16*>(out_lp); ep.ldo_bf16 = ldo_lp;
@@ -342,7 +363,9 @@ int unimm_engine::attention(const void* q, int ldq, const void* k, int ldk, cons
     a.B = B; a.heads = heads; a.D = D; a.Sq = Sq; a.Skv = Skv;
     a.mask_kind = mask_kind; a.desc = desc; a.key_mask = key_mask;
     a.scale = 1.0f / sqrtf(static_cast<float>(D));
-    return lp() ? attention_mma_bf16(a, st) : attention_simt_f32(a, st);
+    a.lp_kind = lp_kind();
+    Prof prof(this, CAT_ATTN, 4.0 * B * heads * static_cast<double>(Sq) * Skv * D, st);
+    return lp() ? attention_mma_lp(a, st) : attention_simt_f32(a, st);
 }
 
 // BertLayer / BertImageLayer: QKV -> attention -> out-proj + residual -> LN -> FFN1+GELU -> FFN2 + residual -> LN
@@ -356,13 +379,13 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
     ActBuf c;
     c.f = lp() ? nullptr : static_cast<float*>(ctx); c.h = lp() ? static_cast<bf16*>(ctx) : nullptr; c.ld = H;
     UNIMM_TRY(linear(c, M, L.out, ACT_NONE, x.f, H, pre, H, nullptr, 0, st));
-    UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln1.g, L.ln1.b, x.f, x.h, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (M) * (H), st); UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln1.g, L.ln1.b, x.f, x.h, lp_kind(), st)); }
     const int I = L.ffn1.N;
     UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st));
     ActBuf f;
     f.f = lp() ? nullptr : static_cast<float*>(ffn); f.h = lp() ? static_cast<bf16*>(ffn) : nullptr; f.ld = I;
     UNIMM_TRY(linear(f, M, L.ffn2, ACT_NONE, x.f, H, pre, H, nullptr, 0, st));
-    UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln2.g, L.ln2.b, x.f, x.h, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (M) * (H), st); UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln2.g, L.ln2.b, x.f, x.h, lp_kind(), st)); }
     return 0;
 }
 
@@ -386,21 +409,21 @@ int unimm_engine::conn_layer(const ConnLayer& L, int B, const SeqDesc* desc, con
     ct.f = lp() ? nullptr : static_cast<float*>(ctx_t); ct.h = lp() ? static_cast<bf16*>(ctx_t) : nullptr; ct.ld = Hb;
     // BertBiOutput (:744-754): image rows take the image-query context through dense1, text rows the other through dense2
     UNIMM_TRY(linear(cv, Mv, L.dense1, ACT_NONE, xv.f, Hv, pre_v, Hv, nullptr, 0, st));
-    UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.ln1.g, L.ln1.b, xv.f, xv.h, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.ln1.g, L.ln1.b, xv.f, xv.h, lp_kind(), st)); }
     UNIMM_TRY(linear(ct, Mt, L.dense2, ACT_NONE, xt.f, H, pre_t, H, nullptr, 0, st));
-    UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.ln2.g, L.ln2.b, xt.f, xt.h, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mt) * (H), st); UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.ln2.g, L.ln2.b, xt.f, xt.h, lp_kind(), st)); }
     // image FFN, text FFN (:777-781)
     const int Iv = L.v_ffn1.N, I = L.t_ffn1.N;
     UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st));
     ActBuf fv;
     fv.f = lp() ? nullptr : static_cast<float*>(ffn_v); fv.h = lp() ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
     UNIMM_TRY(linear(fv, Mv, L.v_ffn2, ACT_NONE, xv.f, Hv, pre_v, Hv, nullptr, 0, st));
-    UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.v_ln.g, L.v_ln.b, xv.f, xv.h, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.v_ln.g, L.v_ln.b, xv.f, xv.h, lp_kind(), st)); }
     UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st));
     ActBuf ft;
     ft.f = lp() ? nullptr : static_cast<float*>(ffn_t); ft.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; ft.ld = I;
     UNIMM_TRY(linear(ft, Mt, L.t_ffn2, ACT_NONE, xt.f, H, pre_t, H, nullptr, 0, st));
-    UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.t_ln.g, L.t_ln.b, xt.f, xt.h, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mt) * (H), st); UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.t_ln.g, L.t_ln.b, xt.f, xt.h, lp_kind(), st)); }
     return 0;
 }
 
@@ -417,15 +440,15 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     // ---- embeddings (reference :326-356, :1487-1493)
     UNIMM_TRY(embed_text_ln(in.d_input_ids, in.d_token_type_ids, in.d_position_ids, Mt, H, c.vocab_size, c.max_position_embeddings,
                             c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h,
-                            err_flag, st));
+                            lp_kind(), err_flag, st));
     UNIMM_TRY(gather_features(in.d_image_feat, in.d_feat_index, B, R, c.v_feature_size, lp() ? nullptr : static_cast<float*>(feat_a),
-                              lp() ? static_cast<bf16*>(feat_a) : nullptr, st));
+                              lp() ? static_cast<bf16*>(feat_a) : nullptr, lp_kind(), st));
     UNIMM_TRY(image_loc_embed(in.d_image_loc, in.d_feat_index, B, R, Hv, loc_w, loc_b, pre_v, st));
     {
         ActBuf fa;
         fa.f = lp() ? nullptr : static_cast<float*>(feat_a); fa.h = lp() ? static_cast<bf16*>(feat_a) : nullptr; fa.ld = c.v_feature_size;
         UNIMM_TRY(linear(fa, Mv, img_emb, ACT_NONE, pre_v, Hv, pre_v, Hv, nullptr, 0, st));
-        UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, vemb_ln.g, vemb_ln.b, xv.f, xv.h, st));
+        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, vemb_ln.g, vemb_ln.b, xv.f, xv.h, lp_kind(), st)); }
     }
     // key mask per sequence: image_mask[feat_index[b]] — expand once when an index is used
     const float* key_mask = in.d_image_mask;
@@ -479,13 +502,15 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
         UNIMM_TRY(gather_rows(lp() ? nullptr : xt.f, lp() ? xt.h : nullptr, in.d_lm_rows, n, H, lp() ? nullptr : g_in.f,
                               lp() ? g_in.h : nullptr, st));
         UNIMM_TRY(linear(g_in, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
-        UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, st));
+        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, lp_kind(), st)); }
         if (lp()) {
             GemmEpilogue ep;
             ep.bias = lm_decoder.b;
             ep.labels = g_labels;
             ep.partials = partials;
             ep.label_logit = label_logit;
+            ep.lp_kind = lp_kind();
+            Prof prof(this, CAT_LMHEAD, 2.0 * n * c.vocab_size * H, st);
             UNIMM_TRY(gemm_umma_bf16(g_h.h, H, lm_decoder.wlp, H, n, c.vocab_size, H, ep, 256, 0, st));
             UNIMM_TRY(lse_from_partials(partials, gemm_umma_lse_tiles(c.vocab_size), label_logit, n, row_logp, row_ul, st));
         } else {
@@ -510,7 +535,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
         // image head (:1085-1088) + masked KL (:1569-1574)
         UNIMM_CHECK(in.d_image_label != nullptr, "image_label required with image_target");
         UNIMM_TRY(linear(xv, Mv, img_transform, ACT_GELU, nullptr, 0, vhead, Hv, nullptr, 0, st));
-        UNIMM_TRY(layernorm_rows(vhead, Hv, Mv, Hv, img_ln.g, img_ln.b, vhead_h.f, vhead_h.h, st));
+        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(vhead, Hv, Mv, Hv, img_ln.g, img_ln.b, vhead_h.f, vhead_h.h, lp_kind(), st)); }
         UNIMM_TRY(linear(vhead_h, Mv, img_decoder, ACT_NONE, nullptr, 0, v_logits, c.v_target_size, nullptr, 0, st));
         // d_losses[1] = loss, [3..4] scratch
         float* kl = out.d_losses + 3;
@@ -523,7 +548,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
         UNIMM_TRY(linear(xt, Mt, lm_transform, ACT_GELU, nullptr, 0, pre_t, H, nullptr, 0, st));
         ActBuf hh;
         hh.f = pre_t; hh.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; hh.ld = H;
-        UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, lm_ln.g, lm_ln.b, hh.f, hh.h, st));
+        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mt) * (H), st); UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, lm_ln.g, lm_ln.b, hh.f, hh.h, lp_kind(), st)); }
         UNIMM_TRY(linear(hh, Mt, lm_decoder, ACT_NONE, nullptr, 0, out.d_prediction_scores_t, c.vocab_size, nullptr, 0, st));
     }
     return 0;
@@ -565,7 +590,7 @@ void unimm_reset_launch_count(void) { g_launches.store(0); }
 
 int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_sequences, unimm_engine_t** out) {
     UNIMM_CHECK(cfg != nullptr && out != nullptr, "null argument");
-    UNIMM_CHECK(precision == UNIMM_PREC_FP32 || precision == UNIMM_PREC_BF16, "unknown precision");
+    UNIMM_CHECK(precision == UNIMM_PREC_FP32 || precision == UNIMM_PREC_BF16 || precision == UNIMM_PREC_FP16, "unknown precision");
     UNIMM_CHECK(max_sequences > 0, "max_sequences must be positive");
     UNIMM_CHECK(cfg->hidden_size == 768 || cfg->hidden_size == 1024, "hidden_size must be 768 or 1024");
     UNIMM_CHECK(cfg->v_hidden_size == 768 || cfg->v_hidden_size == 1024, "v_hidden_size must be 768 or 1024");
@@ -705,13 +730,37 @@ int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_s
     return 0;
 }
 
+int unimm_profile_begin(unimm_engine_t* e) {
+    UNIMM_CHECK(e != nullptr, "null engine");
+    e->profiling = true;
+    return 0;
+}
+
+// Synchronises the device, then sums per class: elapsed ms, work units (FLOPs, or bytes for CAT_ROWWISE), launches.
+int unimm_profile_end(unimm_engine_t* e, double* ms, double* work, int64_t* launches, int ncat) {
+    UNIMM_CHECK(e && ms && work && launches && ncat >= unimm_engine::NCAT, "bad argument");
+    DeviceGuard g(e->device);
+    e->profiling = false;
+    UNIMM_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < ncat; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+    for (auto& r : e->prof_recs) {
+        float t = 0.f;
+        UNIMM_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cat] += t; work[r.cat] += r.work; launches[r.cat] += 1;
+        e->prof_pool.push_back(r.a); e->prof_pool.push_back(r.b);
+    }
+    e->prof_recs.clear();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------- kernel-level entry points
-int unimm_k_gemm_bf16(const void* d_A, int lda, const void* d_W, int ldw, int M, int N, int K, const float* d_bias,
-                      const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_bf16, int ldo_bf16,
-                      int tile_n, int max_ctas, void* stream) {
+int unimm_k_gemm_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, int N, int K, const float* d_bias,
+                    const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp,
+                    int tile_n, int max_ctas, int lp_kind, void* stream) {
     GemmEpilogue ep;
+    ep.lp_kind = lp_kind;
     ep.bias = d_bias; ep.residual = d_residual; ep.ldr = ldr; ep.act = act;
-    ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32; ep.out_bf16 = static_cast<bf16*>(d_out_bf16); ep.ldo_bf16 = ldo_bf16;
+    ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32; ep.out_bf16 = static_cast<bf16*>(d_out_lp); ep.ldo_bf16 = ldo_lp;
     return gemm_umma_bf16(static_cast<const bf16*>(d_A), lda, static_cast<const bf16*>(d_W), ldw, M, N, K, ep, tile_n, max_ctas,
                           static_cast<cudaStream_t>(stream));
 }
@@ -724,10 +773,11 @@ int unimm_k_gemm_f32(const float* d_A, int lda, const float* d_W, int ldw, int M
     return gemm_simt_f32(d_A, lda, d_W, ldw, M, N, K, ep, static_cast<cudaStream_t>(stream));
 }
 
-int unimm_k_lm_head_bf16(const void* d_H, int ldh, const void* d_E, int lde, int rows, int V, int K, const float* d_bias,
-                         const int32_t* d_labels, float* d_partials_scratch, float* d_label_logit_scratch, float* d_logp,
-                         float* d_ul, void* stream) {
+int unimm_k_lm_head_lp(const void* d_H, int ldh, const void* d_E, int lde, int rows, int V, int K, const float* d_bias,
+                       const int32_t* d_labels, float* d_partials_scratch, float* d_label_logit_scratch, float* d_logp,
+                       float* d_ul, int lp_kind, void* stream) {
     GemmEpilogue ep;
+    ep.lp_kind = lp_kind;
     ep.bias = d_bias;
     ep.labels = d_labels;
     ep.partials = reinterpret_cast<float2*>(d_partials_scratch);
@@ -738,28 +788,29 @@ int unimm_k_lm_head_bf16(const void* d_H, int ldh, const void* d_E, int lde, int
 }
 
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
-                      void* d_y_bf16, void* stream) {
-    return layernorm_rows(d_x, ldx, rows, H, d_gamma, d_beta, d_y_f32, static_cast<bf16*>(d_y_bf16), static_cast<cudaStream_t>(stream));
+                      void* d_y_lp, int lp_kind, void* stream) {
+    return layernorm_rows(d_x, ldx, rows, H, d_gamma, d_beta, d_y_f32, static_cast<bf16*>(d_y_lp), lp_kind, static_cast<cudaStream_t>(stream));
 }
 
-int unimm_k_cast_bf16(const float* d_src, void* d_dst, int64_t n, void* stream) {
-    return cast_f32_to_bf16(d_src, static_cast<bf16*>(d_dst), static_cast<size_t>(n), static_cast<cudaStream_t>(stream));
+int unimm_k_cast_lp(const float* d_src, void* d_dst, int64_t n, int lp_kind, void* stream) {
+    return cast_f32_to_lp(d_src, static_cast<bf16*>(d_dst), static_cast<size_t>(n), lp_kind, static_cast<cudaStream_t>(stream));
 }
 
 int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,
                       int heads, int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc, const float* d_key_mask,
-                      int is_bf16, int impl, void* stream) {
+                      int elem_kind, int impl, void* stream) {
     AttnArgs a;
     a.q = d_q; a.ldq = ldq; a.k = d_k; a.ldk = ldk; a.v = d_v; a.ldv = ldv; a.o = d_o; a.ldo = ldo;
     a.B = B; a.heads = heads; a.D = D; a.Sq = Sq; a.Skv = Skv; a.mask_kind = mask_kind;
     a.desc = reinterpret_cast<const SeqDesc*>(d_desc); a.key_mask = d_key_mask;
     a.scale = 1.0f / sqrtf(static_cast<float>(D));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!is_bf16) {
-        UNIMM_CHECK(impl == 0, "the tensor-core attention takes bf16 tensors");
+    if (elem_kind == 0) {
+        UNIMM_CHECK(impl == 0, "the tensor-core attention takes 16-bit tensors");
         return attention_simt_f32(a, st);
     }
-    return impl == 0 ? attention_simt_bf16(a, st) : attention_mma_bf16(a, st);
+    a.lp_kind = elem_kind == 2 ? LP_FP16 : LP_BF16;
+    return impl == 0 ? attention_simt_lp(a, st) : attention_mma_lp(a, st);
 }
 
 }  // extern "C"

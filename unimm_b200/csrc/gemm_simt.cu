@@ -110,7 +110,7 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
                 bf16* o = ep.out_bf16 + static_cast<size_t>(r) * ep.ldo_bf16 + c0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (c0 + j < N) o[j] = __float2bfloat16_rn(x[j]);
+                    if (c0 + j < N) o[j] = lp_from_f32(x[j], ep.lp_kind);
             }
         }
     }

@@ -109,7 +109,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+            const uint32_t idesc = ptx::make_idesc_f16(BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -233,16 +233,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 p;
-                            p.x = pack_bf16x2(x[j], x[j + 1]);
-                            p.y = pack_bf16x2(x[j + 2], x[j + 3]);
-                            p.z = pack_bf16x2(x[j + 4], x[j + 5]);
-                            p.w = pack_bf16x2(x[j + 6], x[j + 7]);
+                            p.x = pack_lp2(x[j], x[j + 1], ep.lp_kind);
+                            p.y = pack_lp2(x[j + 2], x[j + 3], ep.lp_kind);
+                            p.z = pack_lp2(x[j + 4], x[j + 5], ep.lp_kind);
+                            p.w = pack_lp2(x[j + 6], x[j + 7], ep.lp_kind);
                             *reinterpret_cast<uint4*>(o + j) = p;
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (j < ncols) o[j] = __float2bfloat16_rn(x[j]);
+                            if (j < ncols) o[j] = lp_from_f32(x[j], ep.lp_kind);
                     }
                 }
             }
@@ -316,6 +316,7 @@ int make_map_bf16(const void* ptr, int rows, int cols, int ld, int box_rows, CUt
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
+    // bf16 and fp16 tiles are both plain 2-byte elements to TMA (no arithmetic, zero OOB fill)
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -21,6 +21,7 @@ struct GemmEpilogue {
     bf16* out_bf16 = nullptr;
     int ldo_bf16 = 0;
     int act = ACT_NONE;
+    int lp_kind = LP_BF16;         // encoding of the 16-bit operands and of out_bf16 (LP_BF16 / LP_FP16)
     const int* labels = nullptr;   // LSE mode: [M]
     float2* partials = nullptr;    // LSE mode: [M, ceil(N/256)]
     float* label_logit = nullptr;  // LSE mode: [M]
@@ -41,19 +42,19 @@ int gemm_simt_f32(const float* A, int lda, const float* W, int ldw, int M, int N
 int embed_text_ln(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int rows, int H, int vocab,
                   int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
                   const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
-                  bf16* out_bf16, int* err_flag, cudaStream_t stream);
+                  bf16* out_bf16, int lp_kind, int* err_flag, cudaStream_t stream);
 // y = LayerNorm(x) * gamma + beta, eps 1e-12 inside the sqrt, biased variance; x may alias y_f32.
 int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma, const float* beta, float* y_f32,
-                   bf16* y_bf16, cudaStream_t stream);
+                   bf16* y_bf16, int lp_kind, cudaStream_t stream);
 // image location term: out[r, :] = loc[idx(r), 0:5] · Wloc[H,5]^T + bloc  (fp32, K = 5)
 int image_loc_embed(const float* loc, const int* feat_index, int B, int R, int H, const float* Wloc, const float* bloc,
                     float* out, cudaStream_t stream);
 // gather image features into the (optionally bf16) GEMM operand: dst[b*R + r] = feat[feat_index[b]*R + r]
 int gather_features(const float* feat, const int* feat_index, int B, int R, int F, float* dst_f32, bf16* dst_bf16,
-                    cudaStream_t stream);
+                    int lp_kind, cudaStream_t stream);
 int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int n, int H, float* dst_f32, bf16* dst_bf16,
                 cudaStream_t stream);
-int cast_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream);
+int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream);
 int gather_labels(const int64_t* labels, const int* rows, int n, int* out, cudaStream_t stream);
 int expand_key_mask(const float* mask, const int* index, int B, int R, float* out, cudaStream_t stream);
 
@@ -73,10 +74,11 @@ struct AttnArgs {
     const SeqDesc* desc;      // [B]
     const float* key_mask;    // [B, Skv] (MASK_KEY_VECTOR)
     float scale;              // 1/sqrt(D)
+    int lp_kind;              // encoding of 16-bit q/k/v/o (ignored by the fp32 kernel)
 };
 int attention_simt_f32(const AttnArgs& a, cudaStream_t stream);
-int attention_simt_bf16(const AttnArgs& a, cudaStream_t stream);
-int attention_mma_bf16(const AttnArgs& a, cudaStream_t stream);
+int attention_simt_lp(const AttnArgs& a, cudaStream_t stream);
+int attention_mma_lp(const AttnArgs& a, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ heads.cu
 // poolers + 'mul' fusion + NSP linear (ref :946-967, :1062-1070), all fp32

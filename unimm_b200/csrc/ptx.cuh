@@ -180,11 +180,12 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+// Instruction descriptor for kind::f16: (fp16 | bf16) x same -> fp32, both operands K-major.
+// fmt: 0 = F16, 1 = BF16 (cute::UMMA::F16F32Format).
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t fmt) {
     return (1u << 4)            // D format = F32
-           | (1u << 7)          // A format = BF16
-           | (1u << 10)         // B format = BF16
+           | (fmt << 7)         // A format
+           | (fmt << 10)        // B format
            | ((N >> 3) << 17)   // N / 8
            | ((M >> 4) << 24);  // M / 16
 }

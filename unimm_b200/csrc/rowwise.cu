@@ -10,7 +10,7 @@ constexpr float kLnEps = 1e-12f;  // BertLayerNorm eps (reference models/vilbert
 
 template <int NV>
 __device__ __forceinline__ void ln_normalise_store(float4 (&x)[NV], int lane, const float* __restrict__ gamma,
-                                                   const float* __restrict__ beta, float* y_f32, bf16* y_bf16) {
+                                                   const float* __restrict__ beta, float* y_f32, bf16* y_bf16, int lp_kind) {
     constexpr int H = NV * 128;
     float s = 0.f;
 #pragma unroll
@@ -36,8 +36,8 @@ __device__ __forceinline__ void ln_normalise_store(float4 (&x)[NV], int lane, co
         if (y_f32 != nullptr) *reinterpret_cast<float4*>(y_f32 + c) = y;
         if (y_bf16 != nullptr) {
             uint2 p;
-            p.x = pack_bf16x2(y.x, y.y);
-            p.y = pack_bf16x2(y.z, y.w);
+            p.x = pack_lp2(y.x, y.y, lp_kind);
+            p.y = pack_lp2(y.z, y.w, lp_kind);
             *reinterpret_cast<uint2*>(y_bf16 + c) = p;
         }
     }
@@ -46,7 +46,7 @@ __device__ __forceinline__ void ln_normalise_store(float4 (&x)[NV], int lane, co
 template <int NV>
 __global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, int ldx, int rows, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float* y_f32, bf16* y_bf16) {
+                 const float* __restrict__ beta, float* y_f32, bf16* y_bf16, int lp_kind) {
     constexpr int H = NV * 128;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -56,7 +56,7 @@ layernorm_kernel(const float* __restrict__ x, int ldx, int rows, const float* __
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
     ln_normalise_store<NV>(v, lane, gamma, beta, y_f32 ? y_f32 + static_cast<size_t>(row) * H : nullptr,
-                           y_bf16 ? y_bf16 + static_cast<size_t>(row) * H : nullptr);
+                           y_bf16 ? y_bf16 + static_cast<size_t>(row) * H : nullptr, lp_kind);
 }
 
 template <int NV>
@@ -66,7 +66,7 @@ embed_text_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict_
                      const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
                      const float* __restrict__ type_emb, const float* __restrict__ type_ext_emb,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float* out_f32, bf16* out_bf16,
-                     int* err_flag) {
+                     int lp_kind, int* err_flag) {
     constexpr int H = NV * 128;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -93,7 +93,7 @@ embed_text_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict_
         v[i] = make_float4((a.x + b.x) + d.x, (a.y + b.y) + d.y, (a.z + b.z) + d.z, (a.w + b.w) + d.w);
     }
     ln_normalise_store<NV>(v, lane, gamma, beta, out_f32 ? out_f32 + static_cast<size_t>(row) * H : nullptr,
-                           out_bf16 ? out_bf16 + static_cast<size_t>(row) * H : nullptr);
+                           out_bf16 ? out_bf16 + static_cast<size_t>(row) * H : nullptr, lp_kind);
 }
 
 __global__ void image_loc_kernel(const float* __restrict__ loc, const int* __restrict__ feat_index, int R, int H,
@@ -113,7 +113,7 @@ __global__ void image_loc_kernel(const float* __restrict__ loc, const int* __res
 }
 
 __global__ void gather_features_kernel(const float* __restrict__ feat, const int* __restrict__ feat_index, int R, int F,
-                                       float* dst_f32, bf16* dst_bf16) {
+                                       float* dst_f32, bf16* dst_bf16, int lp_kind) {
     const int row = blockIdx.x;
     const int b = row / R, r = row % R;
     const float* s = feat + (static_cast<size_t>(feat_index ? feat_index[b] : b) * R + r) * F;
@@ -122,8 +122,8 @@ __global__ void gather_features_kernel(const float* __restrict__ feat, const int
         if (dst_f32) *reinterpret_cast<float4*>(dst_f32 + static_cast<size_t>(row) * F + c) = v;
         if (dst_bf16) {
             uint2 p;
-            p.x = pack_bf16x2(v.x, v.y);
-            p.y = pack_bf16x2(v.z, v.w);
+            p.x = pack_lp2(v.x, v.y, lp_kind);
+            p.y = pack_lp2(v.z, v.w, lp_kind);
             *reinterpret_cast<uint2*>(dst_bf16 + static_cast<size_t>(row) * F + c) = p;
         }
     }
@@ -139,14 +139,14 @@ __global__ void gather_rows_kernel(const float* __restrict__ src_f32, const bf16
     }
 }
 
-__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4) {
+__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4, int lp_kind) {
     size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (; i < n4; i += stride) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
         uint2 p;
-        p.x = pack_bf16x2(v.x, v.y);
-        p.y = pack_bf16x2(v.z, v.w);
+        p.x = pack_lp2(v.x, v.y, lp_kind);
+        p.y = pack_lp2(v.z, v.w, lp_kind);
         reinterpret_cast<uint2*>(dst)[i] = p;
     }
 }
@@ -179,12 +179,12 @@ int expand_key_mask(const float* mask, const int* index, int B, int R, float* ou
 }
 
 int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma, const float* beta, float* y_f32,
-                   bf16* y_bf16, cudaStream_t stream) {
+                   bf16* y_bf16, int lp_kind, cudaStream_t stream) {
     UNIMM_CHECK(rows > 0, "layernorm: no rows");
     UNIMM_CHECK((ldx & 3) == 0, "layernorm: ldx must be a multiple of 4");
     const int grid = (rows + 3) / 4;
-    if (H == 768) layernorm_kernel<6><<<grid, 128, 0, stream>>>(x, ldx, rows, gamma, beta, y_f32, y_bf16);
-    else if (H == 1024) layernorm_kernel<8><<<grid, 128, 0, stream>>>(x, ldx, rows, gamma, beta, y_f32, y_bf16);
+    if (H == 768) layernorm_kernel<6><<<grid, 128, 0, stream>>>(x, ldx, rows, gamma, beta, y_f32, y_bf16, lp_kind);
+    else if (H == 1024) layernorm_kernel<8><<<grid, 128, 0, stream>>>(x, ldx, rows, gamma, beta, y_f32, y_bf16, lp_kind);
     else UNIMM_CHECK(false, "layernorm: hidden size must be 768 or 1024");
     UNIMM_LAUNCH_CHECK(1);
     return 0;
@@ -193,17 +193,17 @@ int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma,
 int embed_text_ln(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int rows, int H, int vocab,
                   int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
                   const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
-                  bf16* out_bf16, int* err_flag, cudaStream_t stream) {
+                  bf16* out_bf16, int lp_kind, int* err_flag, cudaStream_t stream) {
     UNIMM_CHECK(rows > 0, "embed: no rows");
     const int grid = (rows + 3) / 4;
     if (H == 768)
         embed_text_ln_kernel<6><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext,
                                                           word_emb, pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32,
-                                                          out_bf16, err_flag);
+                                                          out_bf16, lp_kind, err_flag);
     else if (H == 1024)
         embed_text_ln_kernel<8><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext,
                                                           word_emb, pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32,
-                                                          out_bf16, err_flag);
+                                                          out_bf16, lp_kind, err_flag);
     else UNIMM_CHECK(false, "embed: hidden size must be 768 or 1024");
     UNIMM_LAUNCH_CHECK(1);
     return 0;
@@ -217,9 +217,9 @@ int image_loc_embed(const float* loc, const int* feat_index, int B, int R, int H
 }
 
 int gather_features(const float* feat, const int* feat_index, int B, int R, int F, float* dst_f32, bf16* dst_bf16,
-                    cudaStream_t stream) {
+                    int lp_kind, cudaStream_t stream) {
     UNIMM_CHECK((F & 3) == 0, "feature size must be a multiple of 4");
-    gather_features_kernel<<<B * R, 256, 0, stream>>>(feat, feat_index, R, F, dst_f32, dst_bf16);
+    gather_features_kernel<<<B * R, 256, 0, stream>>>(feat, feat_index, R, F, dst_f32, dst_bf16, lp_kind);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -233,13 +233,13 @@ int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int
     return 0;
 }
 
-int cast_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream) {
+int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream) {
     UNIMM_CHECK((n & 3) == 0, "cast: element count must be a multiple of 4");
     const size_t n4 = n / 4;
     int grid = static_cast<int>((n4 + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
-    cast_kernel<<<grid, 256, 0, stream>>>(src, dst, n4);
+    cast_kernel<<<grid, 256, 0, stream>>>(src, dst, n4, lp_kind);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -15,7 +15,7 @@ from ._lib import Batch, Config, HostBatch, Outputs, check, lib, ptr
 from .config import ViLBertConfig
 from .weights import strip_prefix
 
-PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 
 
 def c_config(cfg: ViLBertConfig, seq_len: int = 256, num_regions: int = 37) -> Config:
@@ -153,6 +153,19 @@ class Engine:
         check(lib.unimm_forward(self._h, C.byref(b), C.byref(o), C.c_void_p(stream)))
         out["_keepalive"] = keep
         return out
+
+    # ------------------------------------------------------------------------------------------ profiling
+    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "lm_head", "other")
+
+    def profile_begin(self) -> None:
+        check(lib.unimm_profile_begin(self._h))
+
+    def profile_end(self) -> Dict[str, Dict[str, float]]:
+        """{class: {ms, work, launches}}; work = FLOPs (bytes for layernorm); synchronises the device."""
+        n = len(self.PROFILE_CLASSES)
+        ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        check(lib.unimm_profile_end(self._h, ms, work, cnt, n))
+        return {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
 
     # ------------------------------------------------------------------------------------------ host path
     def score_host(self, hb: "HostArrays", seq_score: torch.Tensor, nsp_scores: Optional[torch.Tensor] = None) -> None:
