@@ -72,6 +72,30 @@ __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + e
 
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
+// erf-GELU for the tensor-core epilogues, where the accurate erff (~30 issue slots) would make the
+// FFN-1 epilogue slower than its K=768 main loop.  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7)
+// with the two SFU ops (rcp, ex2): |gelu_fast - gelu_erf| < 1e-6 |x|, far below the 16-bit rounding of
+// the stored result.  The fp32 parity mode keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float ax = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+    const float erf_abs = fmaf(-p, e, 1.0f);
+    const float h = 0.5f * x;
+    return fmaf(h, copysignf(erf_abs, x), h);
+}
+__device__ __forceinline__ float apply_act_fast(float x, int act) {
+    if (act == ACT_GELU) return gelu_fast(x);
+    if (act == ACT_RELU) return fmaxf(x, 0.f);
+    return x;
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == ACT_GELU) return gelu_erf(x);
     if (act == ACT_RELU) return fmaxf(x, 0.f);

@@ -41,7 +41,7 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 4096 /*epilogue staging*/;
 };
 
 template <int BN, bool LSE>
@@ -60,6 +60,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float4* stage_all = reinterpret_cast<float4*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // 4 warps x 32x32 fp32
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,6 +140,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
         const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        float4* stage = stage_all + ew * 256;
+        // 128-bit global accesses need 16-byte aligned rows
+        const bool fast_ok = (ep.out_f32 == nullptr || ((ep.ldo_f32 & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0)) &&
+                             (ep.out_bf16 == nullptr || ((ep.ldo_bf16 & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0)) &&
+                             (ep.residual == nullptr || ((ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0)) &&
+                             (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -166,20 +173,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                if (ep.bias != nullptr) {
-                    if (ncols == 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-                            x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
-                        }
-                    } else {
+                if (LSE) {
+                    if (ep.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (j < ncols) x[j] += __ldg(ep.bias + col0 + j);
                     }
-                }
-                if (LSE) {
                     float cmax = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -196,54 +195,73 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     run_sum = s;
                     continue;
                 }
+                if (fast_ok && ncols == 32) {
+                    // ---- coalesced path: transpose the warp's 32x32 fp32 block through swizzled shared memory so that
+                    // 8 lanes cover 128 contiguous bytes of one output row (4 rows per warp instruction)
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8)
+                        stage[lane * 8 + (c8 ^ (lane & 7))] = make_float4(x[4 * c8], x[4 * c8 + 1], x[4 * c8 + 2], x[4 * c8 + 3]);
+                    __syncwarp();
+                    const int ch = lane & 7;
+                    const int cc = col0 + ch * 4;
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cc));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = (lane >> 3) + 4 * i;
+                        const int grow = m0 + ew * 32 + r;
+                        float4 y = stage[r * 8 + (ch ^ (r & 7))];
+                        y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
+                        if (ep.act != ACT_NONE) {
+                            y.x = apply_act_fast(y.x, ep.act); y.y = apply_act_fast(y.y, ep.act);
+                            y.z = apply_act_fast(y.z, ep.act); y.w = apply_act_fast(y.w, ep.act);
+                        }
+                        if (grow < M) {
+                            if (ep.residual != nullptr) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ldr + cc);
+                                y.x += r4.x; y.y += r4.y; y.z += r4.z; y.w += r4.w;
+                            }
+                            if (ep.out_f32 != nullptr)
+                                *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc) = y;
+                            if (ep.out_bf16 != nullptr) {
+                                uint2 p;
+                                p.x = pack_lp2(y.x, y.y, ep.lp_kind);
+                                p.y = pack_lp2(y.z, y.w, ep.lp_kind);
+                                *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + cc) = p;
+                            }
+                        }
+                    }
+                    __syncwarp();   // the staging block is rewritten by the next chunk
+                    continue;
+                }
+                // ---- generic path (ragged last columns, unaligned leading dimensions): one row per thread
+                if (ep.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) x[j] += __ldg(ep.bias + col0 + j);
+                }
                 if (ep.act != ACT_NONE) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], ep.act);
+                    for (int j = 0; j < 32; ++j) x[j] = apply_act_fast(x[j], ep.act);
                 }
                 if (!row_ok) continue;
                 if (ep.residual != nullptr) {
                     const float* r = ep.residual + static_cast<size_t>(row) * ep.ldr + col0;
-                    if (ncols == 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(r + j);
-                            x[j] += r4.x; x[j + 1] += r4.y; x[j + 2] += r4.z; x[j + 3] += r4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols) x[j] += r[j];
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) x[j] += r[j];
                 }
                 if (ep.out_f32 != nullptr) {
                     float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
-                    if (ncols == 32 && (ep.ldo_f32 & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols) o[j] = x[j];
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) o[j] = x[j];
                 }
                 if (ep.out_bf16 != nullptr) {
                     bf16* o = ep.out_bf16 + static_cast<size_t>(row) * ep.ldo_bf16 + col0;
-                    if (ncols == 32 && (ep.ldo_bf16 & 7) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 p;
-                            p.x = pack_lp2(x[j], x[j + 1], ep.lp_kind);
-                            p.y = pack_lp2(x[j + 2], x[j + 3], ep.lp_kind);
-                            p.z = pack_lp2(x[j + 4], x[j + 5], ep.lp_kind);
-                            p.w = pack_lp2(x[j + 6], x[j + 7], ep.lp_kind);
-                            *reinterpret_cast<uint4*>(o + j) = p;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols) o[j] = lp_from_f32(x[j], ep.lp_kind);
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) o[j] = lp_from_f32(x[j], ep.lp_kind);
                 }
             }
             if (LSE && row_ok) {
