@@ -138,7 +138,8 @@ int unimm_profile_end(unimm_engine_t* e, double* ms, double* work, int64_t* laun
 int64_t unimm_launch_count(void);
 void unimm_reset_launch_count(void);
 
-/* ---- single-kernel entry points (used by tests/ to check each kernel against the oracle) ---- */
+/* ---- single-kernel entry points (used by tests/ to check each kernel against the oracle) ----
+ * unimm_k_lm_head_lp scratch: d_partials_scratch holds rows * 2*ceil(V/256) float2, d_label_logit_scratch rows floats. */
 int unimm_k_gemm_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias,
                     const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp,
                     int tile_n, int max_ctas, int lp_kind, void* stream);

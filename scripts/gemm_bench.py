@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Per-shape timing of the tcgen05 GEMM through the C ABI (CUDA events, L2 flushed between launches),
+next to torch.matmul (cuBLAS) on the same shapes.  Usage: python scripts/gemm_bench.py [M]"""
+import ctypes as C
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from unimm_b200._lib import check, lib, ptr  # noqa: E402
+
+dev = torch.device("cuda", 0)
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 64000
+MODES = len(sys.argv) > 2      # also time the epilogue ablations: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue
+st = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+# (name, N, K, act, residual+fp32 out, 16-bit out)
+SHAPES = [("qkv", 2304, 768, 0, False, True), ("out_proj", 768, 768, 0, True, False), ("ffn1_gelu", 3072, 768, 1, False, True),
+          ("ffn2", 768, 3072, 0, True, False), ("bi_qkv_t", 3072, 768, 0, False, True), ("bi_dense2", 768, 1024, 0, True, False),
+          ("plain_4096", 4096, 4096, 0, False, True)]
+
+
+def timeit(fn, iters=8):
+    ts = []
+    for _ in range(iters + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts = sorted(ts[2:])
+    return ts[len(ts) // 2]
+
+
+for name, N, K, act, res, lp_out in SHAPES:
+    m = M if name != "plain_4096" else 16384
+    A = (torch.randn(m, K, device=dev) * 0.5).half()
+    W = (torch.randn(N, K, device=dev) * 0.05).half()
+    bias = torch.randn(N, device=dev)
+    R = torch.randn(m, N, device=dev) if res else None
+    o32 = torch.empty(m, N, device=dev) if res else None
+    o16 = torch.empty(m, N, device=dev, dtype=torch.float16) if lp_out else None
+    fn = lambda: check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(W), K, m, N, K, ptr(bias), ptr(R), N, act, ptr(o32), N, ptr(o16), N, 0, 0, 1, st()))
+    t = timeit(fn)
+    t_ref = timeit(lambda: torch.matmul(A, W.t()))
+    fl = 2.0 * m * N * K
+    extra = ""
+    if MODES:
+        for mode in (1, 2, 3):
+            fm = lambda: check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(W), K, m, N, K, ptr(bias), ptr(R), N, act, ptr(o32), N, ptr(o16), N,
+                                                    1000 * mode, 0, 1, st()))
+            extra += f" | mode{mode} {fl/timeit(fm)/1e9:6.0f}"
+    print(f"{name:12s} M={m:6d} N={N:5d} K={K:5d} act={act} res={int(res)}: ours {t*1e3:8.1f} us {fl/t/1e9:7.1f} TFLOP/s | "
+          f"cuBLAS (no epilogue) {t_ref*1e3:8.1f} us {fl/t_ref/1e9:7.1f} TFLOP/s{extra}", flush=True)

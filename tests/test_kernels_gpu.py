@@ -108,7 +108,7 @@ def test_lm_head_lse(lp):
     labels = torch.randint(0, V, (rows,), generator=torch.Generator().manual_seed(3)).to(torch.int32)
     labels[0], labels[1] = 0, V - 1
     labels = labels.to(DEV)
-    tiles = (V + 255) // 256
+    tiles = 2 * ((V + 255) // 256)      # two column halves per 256-wide vocabulary tile
     partials = torch.zeros(rows, tiles, 2, device=DEV)
     lab_logit = torch.zeros(rows, device=DEV)
     logp, ul = torch.zeros(rows, device=DEV), torch.zeros(rows, device=DEV)

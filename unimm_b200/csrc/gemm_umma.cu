@@ -41,11 +41,11 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 4096 /*epilogue staging*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
 template <int BN, bool LSE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue ep) {
     using Cfg = GemmCfg<BN>;
@@ -60,7 +60,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float4* stage_all = reinterpret_cast<float4*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // 4 warps x 32x32 fp32
+    float4* stage_all = reinterpret_cast<float4*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // 8 warps x 32x32 fp32
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -80,7 +80,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+            ptx::mbar_init(&tempty_bar[a], 8);  // one arrival per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -138,41 +138,52 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue
-        const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
-        float4* stage = stage_all + ew * 256;
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        // TMEM lane quarter = warp % 4; the two warps of a quarter split the tile's columns in halves.  With one
+        // warp per scheduler the TMEM-load / shared-memory / global-load latencies of a chunk are exposed, two per
+        // scheduler plus the one-chunk-ahead TMEM load below hide them.
+        const int ew = (warp - 4) & 3;
+        const int half = (warp - 4) >> 2;
+        constexpr int HALF_N = BN / 2;
+        constexpr int NCH = HALF_N / 32;
+        float4* stage = stage_all + (warp - 4) * 256;
         // 128-bit global accesses need 16-byte aligned rows
         const bool fast_ok = (ep.out_f32 == nullptr || ((ep.ldo_f32 & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0)) &&
                              (ep.out_bf16 == nullptr || ((ep.ldo_bf16 & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0)) &&
                              (ep.residual == nullptr || ((ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0)) &&
                              (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+        // 16-bit-only output with 128-byte aligned row segments: the paired-chunk path (needs N % 64 == 0 so pairs never split)
+        const bool lp_only = fast_ok && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && (N % 64) == 0 &&
+                             (ep.ldo_bf16 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tn = tile % num_n;
             const int m0 = (tile / num_n) * BM;
-            const int n0 = tn * BN;
+            const int n0 = tn * BN + half * HALF_N;
             const int row = m0 + ew * 32 + lane;
             const bool row_ok = row < M;
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
-            const uint32_t taddr0 = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
+            const uint32_t taddr0 = tmem_base + acc * BN + half * HALF_N + (static_cast<uint32_t>(ew * 32) << 16);
 
             float run_max = -INFINITY, run_sum = 0.f, lab_logit = 0.f;
             int label = -1;
             if (LSE && row_ok) label = ep.labels[row];
 
+            uint32_t v[32];
+            if (ep.debug_mode == 3) goto tile_done;
+            if (n0 < N) ptx::tmem_ld_32x32b_x32(taddr0, v);      // chunk 0 in flight
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 const int col0 = n0 + c * 32;
                 if (col0 >= N) break;  // warp-uniform
                 const int ncols = min(32, N - col0);
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(taddr0 + c * 32, v);
                 ptx::tmem_ld_wait();
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                if (c + 1 < NCH && col0 + 32 < N) ptx::tmem_ld_32x32b_x32(taddr0 + (c + 1) * 32, v);   // next chunk in flight
                 if (LSE) {
                     if (ep.bias != nullptr) {
 #pragma unroll
@@ -195,43 +206,110 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     run_sum = s;
                     continue;
                 }
-                if (fast_ok && ncols == 32) {
+                if (ep.debug_mode == 2) { if (x[0] == 1.2345e30f) ep.out_f32[0] = x[5]; continue; }
+                if (lp_only && ncols == 32 && ep.debug_mode != 1) {
+                    // ---- 16-bit-only outputs (QKV, FFN-1): bias + activation in the row-per-thread layout, pack to 16 bit,
+                    // stage TWO chunks (64 columns = 128 bytes per row) so every global store writes whole 128-byte lines
+                    if (ep.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                            x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
+                        }
+                    }
+                    // activation hoisted out of the element loop: a branch-free body lets the 32 independent chains interleave
+                    if (ep.act == ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
+                    } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                    }
+                    uint4* stage16 = reinterpret_cast<uint4*>(stage);
+                    const int slot0 = (c & 1) * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 pk;
+                        pk.x = pack_lp2(x[8 * q], x[8 * q + 1], ep.lp_kind); pk.y = pack_lp2(x[8 * q + 2], x[8 * q + 3], ep.lp_kind);
+                        pk.z = pack_lp2(x[8 * q + 4], x[8 * q + 5], ep.lp_kind); pk.w = pack_lp2(x[8 * q + 6], x[8 * q + 7], ep.lp_kind);
+                        stage16[lane * 8 + ((slot0 + q) ^ (lane & 7))] = pk;
+                    }
+                    if (c & 1) {
+                        __syncwarp();
+                        const int sl = lane & 7;
+                        const int cc = col0 - 32 + sl * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = (lane >> 3) + 4 * i;
+                            const int grow = m0 + ew * 32 + r;
+                            const uint4 pk = stage16[r * 8 + (sl ^ (r & 7))];
+                            if (grow < M) *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + cc) = pk;
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
+                if (fast_ok && ncols == 32 && ep.debug_mode != 1) {
                     // ---- coalesced path: transpose the warp's 32x32 fp32 block through swizzled shared memory so that
                     // 8 lanes cover 128 contiguous bytes of one output row (4 rows per warp instruction)
+                    const int ch = lane & 7;
+                    const int cc = col0 + ch * 4;
+                    const int r0 = m0 + ew * 32 + (lane >> 3);
+                    // residual / bias loads do not depend on the accumulator: issue all of them first (8 independent
+                    // 128-bit loads in flight per thread) so their latency overlaps the shared-memory transpose
+                    float4 res[8];
+                    if (ep.residual != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int grow = r0 + 4 * i;
+                            res[i] = (grow < M) ? *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ldr + cc)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cc));
 #pragma unroll
                     for (int c8 = 0; c8 < 8; ++c8)
                         stage[lane * 8 + (c8 ^ (lane & 7))] = make_float4(x[4 * c8], x[4 * c8 + 1], x[4 * c8 + 2], x[4 * c8 + 3]);
                     __syncwarp();
-                    const int ch = lane & 7;
-                    const int cc = col0 + ch * 4;
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cc));
+                    float4 y[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = (lane >> 3) + 4 * i;
-                        const int grow = m0 + ew * 32 + r;
-                        float4 y = stage[r * 8 + (ch ^ (r & 7))];
-                        y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
-                        if (ep.act != ACT_NONE) {
-                            y.x = apply_act_fast(y.x, ep.act); y.y = apply_act_fast(y.y, ep.act);
-                            y.z = apply_act_fast(y.z, ep.act); y.w = apply_act_fast(y.w, ep.act);
+                        y[i] = stage[r * 8 + (ch ^ (r & 7))];
+                    }
+                    __syncwarp();   // the staging block is rewritten by the next chunk
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { y[i].x += b4.x; y[i].y += b4.y; y[i].z += b4.z; y[i].w += b4.w; }
+                    if (ep.act == ACT_GELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            y[i].x = gelu_fast(y[i].x); y[i].y = gelu_fast(y[i].y); y[i].z = gelu_fast(y[i].z); y[i].w = gelu_fast(y[i].w);
                         }
+                    } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            y[i].x = fmaxf(y[i].x, 0.f); y[i].y = fmaxf(y[i].y, 0.f); y[i].z = fmaxf(y[i].z, 0.f); y[i].w = fmaxf(y[i].w, 0.f);
+                        }
+                    }
+                    if (ep.residual != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { y[i].x += res[i].x; y[i].y += res[i].y; y[i].z += res[i].z; y[i].w += res[i].w; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int grow = r0 + 4 * i;
                         if (grow < M) {
-                            if (ep.residual != nullptr) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(grow) * ep.ldr + cc);
-                                y.x += r4.x; y.y += r4.y; y.z += r4.z; y.w += r4.w;
-                            }
                             if (ep.out_f32 != nullptr)
-                                *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc) = y;
+                                *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc) = y[i];
                             if (ep.out_bf16 != nullptr) {
-                                uint2 p;
-                                p.x = pack_lp2(y.x, y.y, ep.lp_kind);
-                                p.y = pack_lp2(y.z, y.w, ep.lp_kind);
-                                *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + cc) = p;
+                                uint2 pk;
+                                pk.x = pack_lp2(y[i].x, y[i].y, ep.lp_kind);
+                                pk.y = pack_lp2(y[i].z, y[i].w, ep.lp_kind);
+                                *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + cc) = pk;
                             }
                         }
                     }
-                    __syncwarp();   // the staging block is rewritten by the next chunk
                     continue;
                 }
                 // ---- generic path (ragged last columns, unaligned leading dimensions): one row per thread
@@ -240,9 +318,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) x[j] += __ldg(ep.bias + col0 + j);
                 }
-                if (ep.act != ACT_NONE) {
+                if (ep.act == ACT_GELU) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = apply_act_fast(x[j], ep.act);
+                    for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
+                } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
                 }
                 if (!row_ok) continue;
                 if (ep.residual != nullptr) {
@@ -253,20 +334,39 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (ep.out_f32 != nullptr) {
                     float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
+                    if (fast_ok && ncols == 32) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncols) o[j] = x[j];
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) o[j] = x[j];
+                    }
                 }
                 if (ep.out_bf16 != nullptr) {
                     bf16* o = ep.out_bf16 + static_cast<size_t>(row) * ep.ldo_bf16 + col0;
+                    if (fast_ok && ncols == 32 && (ep.ldo_bf16 & 7) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncols) o[j] = lp_from_f32(x[j], ep.lp_kind);
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            pk.x = pack_lp2(x[j], x[j + 1], ep.lp_kind); pk.y = pack_lp2(x[j + 2], x[j + 3], ep.lp_kind);
+                            pk.z = pack_lp2(x[j + 4], x[j + 5], ep.lp_kind); pk.w = pack_lp2(x[j + 6], x[j + 7], ep.lp_kind);
+                            *reinterpret_cast<uint4*>(o + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) o[j] = lp_from_f32(x[j], ep.lp_kind);
+                    }
                 }
             }
-            if (LSE && row_ok) {
-                ep.partials[static_cast<size_t>(row) * num_n + tn] = make_float2(run_max, run_sum);
-                if (label >= n0 && label < min(n0 + BN, N)) ep.label_logit[row] = lab_logit;
+        tile_done:
+            ptx::tmem_ld_wait();   // no TMEM load may be outstanding when the accumulator is handed back
+            if (LSE && row_ok && n0 < N) {
+                ep.partials[static_cast<size_t>(row) * (2 * num_n) + 2 * tn + half] = make_float2(run_max, run_sum);
+                if (label >= n0 && label < min(n0 + HALF_N, N)) ep.label_logit[row] = lab_logit;
+            } else if (LSE && row_ok) {
+                ep.partials[static_cast<size_t>(row) * (2 * num_n) + 2 * tn + half] = make_float2(-INFINITY, 0.f);
             }
             // hand the accumulator back to the MMA warp
             ptx::tc_fence_before();
@@ -370,7 +470,7 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int grid = tiles < num_sms() ? tiles : num_sms();
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    umma_gemm_kernel<BN, LSE><<<grid, 256, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+    umma_gemm_kernel<BN, LSE><<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -391,6 +491,6 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     return launch<128, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
 }
 
-int gemm_umma_lse_tiles(int N) { return (N + 255) / 256; }
+int gemm_umma_lse_tiles(int N) { return 2 * ((N + 255) / 256); }   // two column halves per 256-wide tile
 
 }  // namespace unimm

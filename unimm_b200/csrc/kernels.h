@@ -21,9 +21,10 @@ struct GemmEpilogue {
     bf16* out_bf16 = nullptr;
     int ldo_bf16 = 0;
     int act = ACT_NONE;
+    int debug_mode = 0;            // microbenchmark only: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue work
     int lp_kind = LP_BF16;         // encoding of the 16-bit operands and of out_bf16 (LP_BF16 / LP_FP16)
     const int* labels = nullptr;   // LSE mode: [M]
-    float2* partials = nullptr;    // LSE mode: [M, ceil(N/256)]
+    float2* partials = nullptr;    // LSE mode: [M, gemm_umma_lse_tiles(N)]
     float* label_logit = nullptr;  // LSE mode: [M]
 };
 
