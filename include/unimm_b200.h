@@ -103,6 +103,47 @@ int unimm_load_weight(unimm_engine_t* e, const char* name, const float* h_data, 
 int unimm_finalize_weights(unimm_engine_t* e);
 int unimm_forward(unimm_engine_t* e, const unimm_batch_t* batch, const unimm_outputs_t* out, void* stream);
 
+/* ---- prefix-shared generative scoring --------------------------------------------------------------------
+ * In generative mode the context rows [1,ctx) and the image rows are identical for the 100 candidates of a
+ * dialog round (they attend only context + image; utils/data_utils.py:199-210), so a unit = (image, round)
+ * stores them once and each candidate contributes only its own rows [CLS, A_0..A_{last-1}, B_0..B_{last-1}].
+ * Text rows are packed: all units' context rows, then all candidates' rows.  Attention is described by job
+ * lists over packed rows (8 int32 per job: q_start, q_len, kv_start, kv_len, win, mask_row, 0, 0) and, for
+ * candidate rows, by row_iv[r] = (lo, hi, self, 0): the packed rows of its own candidate it may attend
+ * besides the whole context.  unimm_b200/packing.py builds all of this. */
+typedef struct {
+    int32_t n_units, n_cands, n_text_rows;       /* U, C, M                                                   */
+    const int32_t* d_input_ids;                  /* [M]                                                        */
+    const int32_t* d_token_type_ids;             /* [M]                                                        */
+    const int32_t* d_position_ids;               /* [M]                                                        */
+    const int32_t* d_row_iv;                     /* [M,4]                                                      */
+    const float* d_image_feat;                   /* [U,R,v_feature_size]                                       */
+    const float* d_image_loc;                    /* [U,R,5]                                                    */
+    const float* d_image_mask;                   /* [U,R]                                                      */
+    const int32_t* d_jobs_text_self;             /* [n,8] context-self jobs and candidate jobs (win = 1)       */
+    int32_t n_jobs_text_self, max_q_text_self;
+    const int32_t* d_jobs_t2i;                   /* [n,8] text rows of a unit over its image rows              */
+    int32_t n_jobs_t2i, max_q_t2i;
+    const int32_t* d_jobs_i2t;                   /* [U,8] image rows over the unit's context rows              */
+    int32_t n_jobs_i2t;
+    const int32_t* d_jobs_img_self;              /* [U,8]                                                      */
+    int32_t n_jobs_img_self;
+    int32_t kv_cap_text;                         /* multiple of 64, >= longest context, <= 256                  */
+    int32_t win_cap;                             /* multiple of 64, >= 128 + 2*(longest candidate row count)    */
+    const int32_t* d_lm_rows;                    /* [n_lm] packed rows of the masked copy, grouped by candidate */
+    const int32_t* d_lm_labels;                  /* [n_lm]                                                      */
+    int32_t n_lm_rows;
+    const int32_t* d_cand_lm_off;                /* [C+1] offsets into lm rows                                  */
+    const int32_t* d_cand_cls_row;               /* [C]   packed row of each candidate's [CLS]                  */
+    const int32_t* d_cand_img_row;               /* [C]   unit * R                                              */
+    double pairs_text_self, pairs_i2t;           /* sum over jobs of q_len * keys (profiling only)             */
+} unimm_packed_batch_t;
+/* outputs (each optional): seq_score [C], nsp_scores [C,2], token_logp [n_lm] */
+int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, float* d_seq_score, float* d_nsp_scores,
+                         float* d_token_logp, void* stream);
+/* Same with every pointer of `hb` (and the outputs) in HOST memory: H2D + forward + D2H + sync inside the call. */
+int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream);
+
 /* Boundary helper: check that the caller's dense masks equal what the descriptors regenerate.
  * d_txt_mask: [B,S,S] elements of txt_elem_bytes (1 = bool/uint8, 8 = int64); d_co_mask: [B,R,S] int64 or NULL.
  * *d_mismatch (device int) is set to 1 on any difference. */

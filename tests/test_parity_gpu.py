@@ -175,3 +175,65 @@ def test_host_buffer_scoring_and_unit_sharing(full_cfg):
     eng.score_host(hb, score, nsp)
     np.testing.assert_allclose(score.numpy(), g["seq_score"], atol=1e-4, rtol=0)
     np.testing.assert_allclose(nsp.numpy(), g["nsp_scores"], atol=1e-4, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------------ prefix-shared path
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+def test_prefix_shared_scores_match_reference(full_cfg, precision):
+    """Packed layout (context + image rows once per round, candidates contribute only CLS/A/B rows) == the reference."""
+    from oracle import visdial_metrics as om
+    from unimm_b200.packing import pack_units, units_from_flat
+    g, batch = load_golden("gen100_default")
+    eng = get_engine(full_cfg, g, precision)
+    desc = descriptors_from_masks(batch["txt_attention_mask"], batch["co_attention_mask"])
+    units = units_from_flat(batch["tokens"], batch["segments"], batch["positions"], batch["mask"], desc, np.zeros(100, np.int64))
+    pb = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None])
+    assert pb.n_text_rows < 0.07 * 100 * 256                 # ~1.4 k packed rows instead of 25.6 k dense rows
+    out = eng.forward_packed(pb.to(eng.device), want=("seq_score", "nsp_scores", "token_logp"))
+    score = out["seq_score"].cpu()
+    err = np.abs(score.numpy() - g["seq_score"]).max()
+    nerr = np.abs(out["nsp_scores"].cpu().numpy() - g["nsp_scores"]).max()
+    flips = int((om.scores_to_ranks(score.view(1, 1, 100)).view(100).numpy() != g["ranks"]).sum())
+    print(f"[{precision}] prefix-shared config 1: seq_score err {err:.3e}  nsp err {nerr:.3e}  rank changes {flips}/100  "
+          f"({pb.n_text_rows} packed text rows)")
+    assert err < TIGHT[precision] and nerr < TIGHT[precision]
+    if precision == "fp32":
+        assert flips == 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_prefix_shared_equals_dense_path_multi_unit(full_cfg, precision):
+    """Several rounds of different context lengths in one packed forward vs the dense per-sequence forward."""
+    from unimm_b200 import synthetic as syn
+    from unimm_b200.packing import pack_units, units_from_rounds
+    g, _ = load_golden("gen8_default")
+    eng = get_engine(full_cfg, g, precision)
+    rng = np.random.RandomState(11)
+    imgs = [syn.synth_image(rng) for _ in range(2)]
+    rounds = [syn.encode_round_gen(syn.synth_context(rng, r), syn.synth_answers(rng, n)) for r, n in ((1, 9), (4, 14), (10, 11), (7, 3))]
+    slots = [0, 0, 1, 1]
+    feat, loc, mask = (np.stack([im[i] for im in imgs]) for i in range(3))
+    pb = pack_units(units_from_rounds(rounds, slots), feat, loc, mask)
+    packed = eng.forward_packed(pb.to(eng.device), want=("seq_score", "nsp_scores"))
+    tokens, segments, positions, labels, desc, index = syn.stack_rounds(rounds)
+    index = torch.tensor(np.concatenate([np.full(len(r.tokens), s, np.int32) for r, s in zip(rounds, slots)]))
+    dense = eng.forward(tokens, segments, positions, desc, torch.from_numpy(feat), torch.from_numpy(loc), torch.from_numpy(mask),
+                        feat_index=index, masked_lm_labels=labels, want=("seq_score", "nsp_scores"))
+    d1 = (packed["seq_score"] - dense["seq_score"]).abs().max().item()
+    d2 = (packed["nsp_scores"] - dense["nsp_scores"]).abs().max().item()
+    print(f"[{precision}] packed vs dense, 4 units / 37 candidates: seq_score diff {d1:.3e}  nsp diff {d2:.3e}")
+    tol = 5e-5 if precision == "fp32" else 6e-3
+    assert d1 < tol and d2 < tol
+
+
+def test_prefix_shared_host_path(full_cfg):
+    from unimm_b200.packing import pack_units, units_from_flat
+    g, batch = load_golden("gen8_default")
+    eng = get_engine(full_cfg, g, "fp32")
+    desc = descriptors_from_masks(batch["txt_attention_mask"], batch["co_attention_mask"])
+    units = units_from_flat(batch["tokens"], batch["segments"], batch["positions"], batch["mask"], desc, np.zeros(8, np.int64))
+    pb = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None]).pin()
+    score, nsp = torch.zeros(8).pin_memory(), torch.zeros(8, 2).pin_memory()
+    eng.score_packed_host(pb, score, nsp)
+    np.testing.assert_allclose(score.numpy(), g["seq_score"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(nsp.numpy(), g["nsp_scores"], atol=1e-4, rtol=0)

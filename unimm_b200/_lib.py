@@ -54,6 +54,21 @@ class HostBatch(C.Structure):
         "h_image_loc", "h_image_mask", "h_feat_index")]
 
 
+class PackedBatchStruct(C.Structure):
+    _fields_ = [
+        ("n_units", C.c_int32), ("n_cands", C.c_int32), ("n_text_rows", C.c_int32),
+        ("d_input_ids", C.c_void_p), ("d_token_type_ids", C.c_void_p), ("d_position_ids", C.c_void_p), ("d_row_iv", C.c_void_p),
+        ("d_image_feat", C.c_void_p), ("d_image_loc", C.c_void_p), ("d_image_mask", C.c_void_p),
+        ("d_jobs_text_self", C.c_void_p), ("n_jobs_text_self", C.c_int32), ("max_q_text_self", C.c_int32),
+        ("d_jobs_t2i", C.c_void_p), ("n_jobs_t2i", C.c_int32), ("max_q_t2i", C.c_int32),
+        ("d_jobs_i2t", C.c_void_p), ("n_jobs_i2t", C.c_int32),
+        ("d_jobs_img_self", C.c_void_p), ("n_jobs_img_self", C.c_int32),
+        ("kv_cap_text", C.c_int32), ("win_cap", C.c_int32),
+        ("d_lm_rows", C.c_void_p), ("d_lm_labels", C.c_void_p), ("n_lm_rows", C.c_int32),
+        ("d_cand_lm_off", C.c_void_p), ("d_cand_cls_row", C.c_void_p), ("d_cand_img_row", C.c_void_p),
+        ("pairs_text_self", C.c_double), ("pairs_i2t", C.c_double)]
+
+
 # every symbol include/unimm_b200.h declares: name -> (restype, argtypes)
 _P, _I, _F = C.c_void_p, C.c_int, C.c_void_p
 SYMBOLS = {
@@ -64,6 +79,8 @@ SYMBOLS = {
     "unimm_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
     "unimm_finalize_weights": (C.c_int, [_P]),
     "unimm_forward": (C.c_int, [_P, C.POINTER(Batch), C.POINTER(Outputs), _P]),
+    "unimm_forward_packed": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _P, _P, _P, _P]),
+    "unimm_score_packed_host": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _P, _P, _P]),
     "unimm_verify_masks": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "unimm_score_host": (C.c_int, [_P, C.POINTER(HostBatch), _P, _P, _P]),
     "unimm_profile_begin": (C.c_int, [_P]),

@@ -151,10 +151,23 @@ struct unimm_engine {
                void* out_lp, int ldo_lp, cudaStream_t st);
     int attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
                   int D, int Sq, int Skv, int mask_kind, const SeqDesc* desc, const float* key_mask, cudaStream_t st);
-    int self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int B, int Sx, int heads,
-                   int mask_kind, const SeqDesc* desc, const float* key_mask, cudaStream_t st);
-    int conn_layer(const ConnLayer& L, int B, const SeqDesc* desc, const float* key_mask, cudaStream_t st);
+    // which attention a layer runs: dense [B,S]/[B,R] rows with descriptor masks, or jobs over packed rows
+    struct AttnCtx {
+        const unimm_packed_batch_t* pk = nullptr;   // non-null = packed (prefix-shared) layout
+        int B = 0;
+        const SeqDesc* desc = nullptr;
+        const float* key_mask = nullptr;
+    };
+    int attention_packed(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int heads, int D,
+                         const int* jobs, int n_jobs, int max_q, int kv_cap, int win_cap, double qk_pairs, const AttnCtx& ac,
+                         cudaStream_t st);
+    int self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int M, int heads, bool text,
+                   const AttnCtx& ac, cudaStream_t st);
+    int conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& ac, cudaStream_t st);
+    int run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st);
+    int lm_head_rows(const int* d_rows, const int* d_labels, int n, cudaStream_t st);
     int forward(const unimm_batch_t& in, const unimm_outputs_t& out, cudaStream_t st);
+    int forward_packed(const unimm_packed_batch_t& in, float* d_seq_score, float* d_nsp_scores, float* d_token_logp, cudaStream_t st);
 };
 
 namespace {
@@ -368,14 +381,36 @@ int unimm_engine::attention(const void* q, int ldq, const void* k, int ldk, cons
     return lp() ? attention_mma_lp(a, st) : attention_simt_f32(a, st);
 }
 
+int unimm_engine::attention_packed(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int heads,
+                                   int D, const int* jobs, int n_jobs, int max_q, int kv_cap, int win_cap, double qk_pairs,
+                                   const AttnCtx& ac, cudaStream_t st) {
+    AttnJobsArgs a;
+    a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.o = o; a.ldo = ldo;
+    a.heads = heads; a.D = D; a.jobs = jobs; a.n_jobs = n_jobs; a.max_q_len = max_q; a.kv_cap = kv_cap; a.win_cap = win_cap;
+    a.row_iv = ac.pk->d_row_iv; a.key_mask = ac.pk->d_image_mask; a.key_mask_ld = cfg.num_regions;
+    a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind();
+    Prof prof(this, CAT_ATTN, 4.0 * heads * D * qk_pairs, st);
+    return attention_jobs(a, !lp(), st);
+}
+
 // BertLayer / BertImageLayer: QKV -> attention -> out-proj + residual -> LN -> FFN1+GELU -> FFN2 + residual -> LN
-int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int B, int Sx, int heads,
-                             int mask_kind, const SeqDesc* desc, const float* key_mask, cudaStream_t st) {
-    const int M = B * Sx, H = x.ld, D = H / heads;
+int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int M, int heads, bool text,
+                             const AttnCtx& ac, cudaStream_t st) {
+    const int H = x.ld, D = H / heads;
     const size_t e = esz();
     UNIMM_TRY(linear(x, M, L.qkv, ACT_NONE, nullptr, 0, nullptr, 0, qkv, 3 * H, st));
-    UNIMM_TRY(attention(qkv, 3 * H, byte_ptr(qkv) + e * H, 3 * H, byte_ptr(qkv) + e * 2 * H, 3 * H, ctx, H, B, heads, D, Sx, Sx,
-                        mask_kind, desc, key_mask, st));
+    const void *qp = qkv, *kp = byte_ptr(qkv) + e * H, *vp = byte_ptr(qkv) + e * 2 * H;
+    if (ac.pk != nullptr) {
+        const unimm_packed_batch_t& pk = *ac.pk;
+        if (text) UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_text_self, pk.n_jobs_text_self,
+                                             pk.max_q_text_self, pk.kv_cap_text, pk.win_cap, pk.pairs_text_self, ac, st));
+        else UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_img_self, pk.n_jobs_img_self,
+                                        cfg.num_regions, 64, 0, static_cast<double>(pk.n_units) * cfg.num_regions * cfg.num_regions, ac, st));
+    } else {
+        const int Sx = text ? cfg.seq_len : cfg.num_regions;
+        UNIMM_TRY(attention(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, ac.B, heads, D, Sx, Sx, text ? MASK_TEXT_SELF : MASK_KEY_VECTOR,
+                            text ? ac.desc : nullptr, text ? nullptr : ac.key_mask, st));
+    }
     ActBuf c;
     c.f = lp() ? nullptr : static_cast<float*>(ctx); c.h = lp() ? static_cast<bf16*>(ctx) : nullptr; c.ld = H;
     UNIMM_TRY(linear(c, M, L.out, ACT_NONE, x.f, H, pre, H, nullptr, 0, st));
@@ -390,20 +425,29 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
 }
 
 // BertConnectionLayer (reference :770-783): stream 1 = image, stream 2 = text
-int unimm_engine::conn_layer(const ConnLayer& L, int B, const SeqDesc* desc, const float* key_mask, cudaStream_t st) {
+int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& ac, cudaStream_t st) {
     const unimm_config_t& c = cfg;
     const int S = c.seq_len, R = c.num_regions, H = c.hidden_size, Hv = c.v_hidden_size, Hb = c.bi_hidden_size;
     const int heads = c.bi_num_attention_heads, D = Hb / heads;
-    const int Mt = B * S, Mv = B * R;
     const size_t e = esz();
     UNIMM_TRY(linear(xv, Mv, L.qkv_v, ACT_NONE, nullptr, 0, nullptr, 0, qkv_v, 3 * Hb, st));
     UNIMM_TRY(linear(xt, Mt, L.qkv_t, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
-    // text queries over image keys/values, image padding mask only (:681-698)
-    UNIMM_TRY(attention(qkv_t, 3 * Hb, byte_ptr(qkv_v) + e * Hb, 3 * Hb, byte_ptr(qkv_v) + e * 2 * Hb, 3 * Hb, ctx_t, Hb, B, heads,
-                        D, S, R, MASK_KEY_VECTOR, nullptr, key_mask, st));
-    // image queries over text keys/values, co-attention column interval only (:701-721)
-    UNIMM_TRY(attention(qkv_v, 3 * Hb, byte_ptr(qkv_t) + e * Hb, 3 * Hb, byte_ptr(qkv_t) + e * 2 * Hb, 3 * Hb, ctx_v, Hb, B, heads,
-                        D, R, S, MASK_CO_INTERVAL, desc, nullptr, st));
+    if (ac.pk != nullptr) {
+        const unimm_packed_batch_t& pk = *ac.pk;
+        // text queries (shared + candidate rows of a unit) over the unit's image keys/values (:681-698)
+        UNIMM_TRY(attention_packed(qkv_t, 3 * Hb, byte_ptr(qkv_v) + e * Hb, 3 * Hb, byte_ptr(qkv_v) + e * 2 * Hb, 3 * Hb, ctx_t, Hb, heads, D,
+                                   pk.d_jobs_t2i, pk.n_jobs_t2i, pk.max_q_t2i, 64, 0, static_cast<double>(Mt) * R, ac, st));
+        // image queries over the unit's context rows = the co-attention interval [1,ctx) (:701-721)
+        UNIMM_TRY(attention_packed(qkv_v, 3 * Hb, byte_ptr(qkv_t) + e * Hb, 3 * Hb, byte_ptr(qkv_t) + e * 2 * Hb, 3 * Hb, ctx_v, Hb, heads, D,
+                                   pk.d_jobs_i2t, pk.n_jobs_i2t, R, pk.kv_cap_text, 0, pk.pairs_i2t, ac, st));
+    } else {
+        // text queries over image keys/values, image padding mask only (:681-698)
+        UNIMM_TRY(attention(qkv_t, 3 * Hb, byte_ptr(qkv_v) + e * Hb, 3 * Hb, byte_ptr(qkv_v) + e * 2 * Hb, 3 * Hb, ctx_t, Hb, ac.B, heads,
+                            D, S, R, MASK_KEY_VECTOR, nullptr, ac.key_mask, st));
+        // image queries over text keys/values, co-attention column interval only (:701-721)
+        UNIMM_TRY(attention(qkv_v, 3 * Hb, byte_ptr(qkv_t) + e * Hb, 3 * Hb, byte_ptr(qkv_t) + e * 2 * Hb, 3 * Hb, ctx_v, Hb, ac.B, heads,
+                            D, R, S, MASK_CO_INTERVAL, ac.desc, nullptr, st));
+    }
     ActBuf cv, ct;
     cv.f = lp() ? nullptr : static_cast<float*>(ctx_v); cv.h = lp() ? static_cast<bf16*>(ctx_v) : nullptr; cv.ld = Hb;
     ct.f = lp() ? nullptr : static_cast<float*>(ctx_t); ct.h = lp() ? static_cast<bf16*>(ctx_t) : nullptr; ct.ld = Hb;
@@ -460,24 +504,9 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     }
 
     // ---- encoder schedule (reference :842-929)
-    int v_start = 0, t_start = 0;
-    auto run_v = [&](int i) {
-        return self_layer(v_layers[i], xv, pre_v, qkv_v, ctx_v, ffn_v, B, R, c.v_num_attention_heads, MASK_KEY_VECTOR, nullptr,
-                          key_mask, st);
-    };
-    auto run_t = [&](int i) {
-        return self_layer(t_layers[i], xt, pre_t, qkv_t, ctx_t, ffn_t, B, S, c.num_attention_heads, MASK_TEXT_SELF, desc, nullptr,
-                          st);
-    };
-    for (int k = 0; k < c.num_connections; ++k) {
-        for (int i = v_start; i < c.v_biattention_id[k]; ++i) UNIMM_TRY(run_v(i));
-        for (int i = t_start; i < c.t_biattention_id[k]; ++i) UNIMM_TRY(run_t(i));
-        UNIMM_TRY(conn_layer(c_layers[k], B, desc, key_mask, st));
-        v_start = c.v_biattention_id[k];
-        t_start = c.t_biattention_id[k];
-    }
-    for (int i = v_start; i < c.v_num_hidden_layers; ++i) UNIMM_TRY(run_v(i));
-    for (int i = t_start; i < c.num_hidden_layers; ++i) UNIMM_TRY(run_t(i));
+    AttnCtx ac;
+    ac.B = B; ac.desc = desc; ac.key_mask = key_mask;
+    UNIMM_TRY(run_encoder(Mt, Mv, ac, st));
 
     if (out.d_sequence_output_t)
         UNIMM_CUDA_CHECK(cudaMemcpyAsync(out.d_sequence_output_t, xt.f, sizeof(float) * Mt * H, cudaMemcpyDeviceToDevice, st));
@@ -499,31 +528,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     if (n > 0) {
         UNIMM_CHECK(in.d_lm_rows && in.d_masked_lm_labels, "lm rows given without labels");
         UNIMM_TRY(gather_labels(in.d_masked_lm_labels, in.d_lm_rows, n, g_labels, st));
-        UNIMM_TRY(gather_rows(lp() ? nullptr : xt.f, lp() ? xt.h : nullptr, in.d_lm_rows, n, H, lp() ? nullptr : g_in.f,
-                              lp() ? g_in.h : nullptr, st));
-        UNIMM_TRY(linear(g_in, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
-        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, lp_kind(), st)); }
-        if (lp()) {
-            GemmEpilogue ep;
-            ep.bias = lm_decoder.b;
-            ep.labels = g_labels;
-            ep.partials = partials;
-            ep.label_logit = label_logit;
-            ep.lp_kind = lp_kind();
-            Prof prof(this, CAT_LMHEAD, 2.0 * n * c.vocab_size * H, st);
-            UNIMM_TRY(gemm_umma_bf16(g_h.h, H, lm_decoder.wlp, H, n, c.vocab_size, H, ep, 256, 0, st));
-            UNIMM_TRY(lse_from_partials(partials, gemm_umma_lse_tiles(c.vocab_size), label_logit, n, row_logp, row_ul, st));
-        } else {
-            for (int r0 = 0; r0 < n; r0 += kLogitRows) {
-                const int nr = std::min(kLogitRows, n - r0);
-                GemmEpilogue ep;
-                ep.bias = lm_decoder.b;
-                ep.out_f32 = logits_chunk;
-                ep.ldo_f32 = c.vocab_size;
-                UNIMM_TRY(gemm_simt_f32(g_h.f + static_cast<size_t>(r0) * H, H, lm_decoder.w32, H, nr, c.vocab_size, H, ep, st));
-                UNIMM_TRY(lse_from_logits(logits_chunk, c.vocab_size, nr, c.vocab_size, g_labels + r0, row_logp + r0, row_ul + r0, st));
-            }
-        }
+        UNIMM_TRY(lm_head_rows(in.d_lm_rows, g_labels, n, st));
     }
     if (out.d_seq_score || out.d_token_logp || out.d_token_ul)
         UNIMM_TRY(scatter_scores(row_logp, row_ul, in.d_lm_rows, n, B, S, out.d_token_logp, out.d_token_ul, out.d_seq_score, st));
@@ -554,6 +559,91 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     return 0;
 }
 
+// encoder layer schedule (reference BertEncoder.forward :842-929) over whichever row layout `ac` describes
+int unimm_engine::run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st) {
+    const unimm_config_t& c = cfg;
+    int v_start = 0, t_start = 0;
+    auto run_v = [&](int i) { return self_layer(v_layers[i], xv, pre_v, qkv_v, ctx_v, ffn_v, Mv, c.v_num_attention_heads, false, ac, st); };
+    auto run_t = [&](int i) { return self_layer(t_layers[i], xt, pre_t, qkv_t, ctx_t, ffn_t, Mt, c.num_attention_heads, true, ac, st); };
+    for (int k = 0; k < c.num_connections; ++k) {
+        for (int i = v_start; i < c.v_biattention_id[k]; ++i) UNIMM_TRY(run_v(i));
+        for (int i = t_start; i < c.t_biattention_id[k]; ++i) UNIMM_TRY(run_t(i));
+        UNIMM_TRY(conn_layer(c_layers[k], Mt, Mv, ac, st));
+        v_start = c.v_biattention_id[k];
+        t_start = c.t_biattention_id[k];
+    }
+    for (int i = v_start; i < c.v_num_hidden_layers; ++i) UNIMM_TRY(run_v(i));
+    for (int i = t_start; i < c.num_hidden_layers; ++i) UNIMM_TRY(run_t(i));
+    return 0;
+}
+
+// gathered LM head (reference :982-986, :1023-1026 on the labelled rows only): fills row_logp / row_ul [n]
+int unimm_engine::lm_head_rows(const int* d_rows, const int* d_labels, int n, cudaStream_t st) {
+    const unimm_config_t& c = cfg;
+    const int H = c.hidden_size;
+    UNIMM_TRY(gather_rows(lp() ? nullptr : xt.f, lp() ? xt.h : nullptr, d_rows, n, H, lp() ? nullptr : g_in.f, lp() ? g_in.h : nullptr, st));
+    UNIMM_TRY(linear(g_in, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, lp_kind(), st)); }
+    if (lp()) {
+        GemmEpilogue ep;
+        ep.bias = lm_decoder.b;
+        ep.labels = d_labels;
+        ep.partials = partials;
+        ep.label_logit = label_logit;
+        ep.lp_kind = lp_kind();
+        Prof prof(this, CAT_LMHEAD, 2.0 * n * c.vocab_size * H, st);
+        UNIMM_TRY(gemm_umma_bf16(g_h.h, H, lm_decoder.wlp, H, n, c.vocab_size, H, ep, 256, 0, st));
+        UNIMM_TRY(lse_from_partials(partials, gemm_umma_lse_tiles(c.vocab_size), label_logit, n, row_logp, row_ul, st));
+    } else {
+        for (int r0 = 0; r0 < n; r0 += kLogitRows) {
+            const int nr = std::min(kLogitRows, n - r0);
+            GemmEpilogue ep;
+            ep.bias = lm_decoder.b;
+            ep.out_f32 = logits_chunk;
+            ep.ldo_f32 = c.vocab_size;
+            UNIMM_TRY(gemm_simt_f32(g_h.f + static_cast<size_t>(r0) * H, H, lm_decoder.w32, H, nr, c.vocab_size, H, ep, st));
+            UNIMM_TRY(lse_from_logits(logits_chunk, c.vocab_size, nr, c.vocab_size, d_labels + r0, row_logp + r0, row_ul + r0, st));
+        }
+    }
+    return 0;
+}
+
+// Prefix-shared generative scoring over packed rows (see attention_jobs.cu and unimm_b200/packing.py)
+int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_score, float* d_nsp_scores, float* d_token_logp,
+                                 cudaStream_t st) {
+    UNIMM_CHECK(finalized, "weights not finalized");
+    const unimm_config_t& c = cfg;
+    const int U = in.n_units, C = in.n_cands, M = in.n_text_rows, R = c.num_regions, H = c.hidden_size, Hv = c.v_hidden_size;
+    UNIMM_CHECK(U > 0 && C > 0 && M > 0, "empty packed batch");
+    UNIMM_CHECK(static_cast<long long>(M) <= static_cast<long long>(Bmax) * c.seq_len && U <= Bmax, "packed batch exceeds the engine workspace");
+    UNIMM_CHECK(in.kv_cap_text > 0 && in.kv_cap_text <= 256 && in.kv_cap_text % 64 == 0 && in.win_cap % 64 == 0, "bad staging capacities");
+    UNIMM_CHECK(in.n_lm_rows >= 0 && in.n_lm_rows <= M, "n_lm_rows out of range");
+    const int Mv = U * R;
+    UNIMM_TRY(embed_text_ln_i32(in.d_input_ids, in.d_token_type_ids, in.d_position_ids, M, H, c.vocab_size, c.max_position_embeddings,
+                                c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h, lp_kind(),
+                                err_flag, st));
+    UNIMM_TRY(gather_features(in.d_image_feat, nullptr, U, R, c.v_feature_size, lp() ? nullptr : static_cast<float*>(feat_a),
+                              lp() ? static_cast<bf16*>(feat_a) : nullptr, lp_kind(), st));
+    UNIMM_TRY(image_loc_embed(in.d_image_loc, nullptr, U, R, Hv, loc_w, loc_b, pre_v, st));
+    {
+        ActBuf fa;
+        fa.f = lp() ? nullptr : static_cast<float*>(feat_a); fa.h = lp() ? static_cast<bf16*>(feat_a) : nullptr; fa.ld = c.v_feature_size;
+        UNIMM_TRY(linear(fa, Mv, img_emb, ACT_NONE, pre_v, Hv, pre_v, Hv, nullptr, 0, st));
+        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, vemb_ln.g, vemb_ln.b, xv.f, xv.h, lp_kind(), st)); }
+    }
+    AttnCtx ac;
+    ac.pk = &in;
+    UNIMM_TRY(run_encoder(M, Mv, ac, st));
+    if (d_nsp_scores)
+        UNIMM_TRY(pooler_nsp_indexed(xt.f, H, in.d_cand_cls_row, xv.f, Hv, in.d_cand_img_row, C, H, Hv, c.bi_hidden_size, tp_w, tp_b, vp_w, vp_b,
+                                     nsp_w, nsp_b, d_nsp_scores, st));
+    const int n = in.n_lm_rows;
+    if (n > 0) UNIMM_TRY(lm_head_rows(in.d_lm_rows, in.d_lm_labels, n, st));
+    if (d_seq_score) UNIMM_TRY(segment_sum(row_logp, in.d_cand_lm_off, C, d_seq_score, st));
+    if (d_token_logp && n > 0) UNIMM_CUDA_CHECK(cudaMemcpyAsync(d_token_logp, row_logp, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -579,6 +669,15 @@ struct HostPath {
     int32_t* h_rows = nullptr;  // pinned
 };
 std::map<unimm_engine*, HostPath> g_host_paths;
+
+// device staging of unimm_score_packed_host: one int32 and one fp32 arena per engine
+struct PackedStage {
+    int32_t* i32 = nullptr;
+    size_t i32_cap = 0;
+    float* f32 = nullptr;
+    size_t f32_cap = 0;
+};
+std::map<unimm_engine*, PackedStage> g_packed_stage;
 }  // namespace
 
 extern "C" {
@@ -620,6 +719,7 @@ int unimm_destroy(unimm_engine_t* e) {
     if (e == nullptr) return 0;
     DeviceGuard g(e->device);
     cudaDeviceSynchronize();
+    g_packed_stage.erase(e);
     auto it = g_host_paths.find(e);
     if (it != g_host_paths.end()) {
         if (it->second.h_rows) cudaFreeHost(it->second.h_rows);
@@ -661,6 +761,76 @@ int unimm_forward(unimm_engine_t* e, const unimm_batch_t* batch, const unimm_out
     UNIMM_CHECK(e && batch && out, "null argument");
     DeviceGuard g(e->device);
     return e->forward(*batch, *out, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, float* d_seq_score, float* d_nsp_scores,
+                         float* d_token_logp, void* stream) {
+    UNIMM_CHECK(e && batch, "null argument");
+    DeviceGuard g(e->device);
+    return e->forward_packed(*batch, d_seq_score, d_nsp_scores, d_token_logp, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream) {
+    UNIMM_CHECK(e && hb && h_seq_score, "null argument");
+    UNIMM_CHECK(e->finalized, "weights not finalized");
+    const unimm_config_t& c = e->cfg;
+    const int U = hb->n_units, C = hb->n_cands, M = hb->n_text_rows, R = c.num_regions, F = c.v_feature_size;
+    UNIMM_CHECK(U > 0 && C > 0 && M > 0 && static_cast<long long>(M) <= static_cast<long long>(e->Bmax) * c.seq_len && U <= e->Bmax &&
+                    C <= e->Bmax * c.seq_len, "packed batch exceeds the engine workspace");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PackedStage& ps = g_packed_stage[e];
+    if (ps.i32 == nullptr) {
+        const size_t rows = static_cast<size_t>(e->Bmax) * c.seq_len;
+        // ids, types, pos (3M) + row_iv (4M) + lm rows/labels (2M) + cand arrays (3C+1 <= 3M+1) + jobs (6U*8)
+        ps.i32_cap = rows * 12 + static_cast<size_t>(e->Bmax) * 48 + 64;
+        UNIMM_TRY(e->dalloc(&ps.i32, ps.i32_cap));
+        ps.f32_cap = static_cast<size_t>(e->Bmax) * R * (F + 6) + rows * 3 + 64;
+        UNIMM_TRY(e->dalloc(&ps.f32, ps.f32_cap));
+    }
+    // carve the device staging buffers and copy each host array behind the previous one
+    unimm_packed_batch_t d = *hb;
+    size_t io = 0, fo = 0;
+    auto put_i = [&](const int32_t* h, size_t n, const int32_t** out) -> int {
+        *out = nullptr;
+        if (h == nullptr || n == 0) return 0;
+        UNIMM_CHECK(io + n <= ps.i32_cap, "packed host batch larger than the staging buffer");
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(ps.i32 + io, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        *out = ps.i32 + io;
+        io += (n + 3) & ~size_t(3);
+        return 0;
+    };
+    auto put_f = [&](const float* h, size_t n, const float** out) -> int {
+        UNIMM_CHECK(h != nullptr && fo + n <= ps.f32_cap, "packed host batch larger than the staging buffer");
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(ps.f32 + fo, h, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        *out = ps.f32 + fo;
+        fo += (n + 3) & ~size_t(3);
+        return 0;
+    };
+    UNIMM_TRY(put_i(hb->d_input_ids, M, &d.d_input_ids));
+    UNIMM_TRY(put_i(hb->d_token_type_ids, M, &d.d_token_type_ids));
+    UNIMM_TRY(put_i(hb->d_position_ids, M, &d.d_position_ids));
+    UNIMM_TRY(put_i(hb->d_row_iv, static_cast<size_t>(M) * 4, &d.d_row_iv));
+    UNIMM_TRY(put_i(hb->d_jobs_text_self, static_cast<size_t>(hb->n_jobs_text_self) * 8, &d.d_jobs_text_self));
+    UNIMM_TRY(put_i(hb->d_jobs_t2i, static_cast<size_t>(hb->n_jobs_t2i) * 8, &d.d_jobs_t2i));
+    UNIMM_TRY(put_i(hb->d_jobs_i2t, static_cast<size_t>(hb->n_jobs_i2t) * 8, &d.d_jobs_i2t));
+    UNIMM_TRY(put_i(hb->d_jobs_img_self, static_cast<size_t>(hb->n_jobs_img_self) * 8, &d.d_jobs_img_self));
+    UNIMM_TRY(put_i(hb->d_lm_rows, hb->n_lm_rows, &d.d_lm_rows));
+    UNIMM_TRY(put_i(hb->d_lm_labels, hb->n_lm_rows, &d.d_lm_labels));
+    UNIMM_TRY(put_i(hb->d_cand_lm_off, static_cast<size_t>(C) + 1, &d.d_cand_lm_off));
+    UNIMM_TRY(put_i(hb->d_cand_cls_row, C, &d.d_cand_cls_row));
+    UNIMM_TRY(put_i(hb->d_cand_img_row, C, &d.d_cand_img_row));
+    UNIMM_TRY(put_f(hb->d_image_feat, static_cast<size_t>(U) * R * F, &d.d_image_feat));
+    UNIMM_TRY(put_f(hb->d_image_loc, static_cast<size_t>(U) * R * 5, &d.d_image_loc));
+    UNIMM_TRY(put_f(hb->d_image_mask, static_cast<size_t>(U) * R, &d.d_image_mask));
+    float* d_score = ps.f32 + fo;
+    float* d_nsp = d_score + ((C + 3) & ~3);
+    UNIMM_CHECK(fo + static_cast<size_t>(C) * 3 + 8 <= ps.f32_cap, "packed host batch larger than the staging buffer");
+    UNIMM_TRY(e->forward_packed(d, d_score, h_nsp_scores ? d_nsp : nullptr, nullptr, st));
+    UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_seq_score, d_score, sizeof(float) * C, cudaMemcpyDeviceToHost, st));
+    if (h_nsp_scores) UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_nsp_scores, d_nsp, sizeof(float) * 2 * C, cudaMemcpyDeviceToHost, st));
+    UNIMM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int unimm_verify_masks(const unimm_seq_desc_t* d_desc, int B, int S, int R, const void* d_txt_mask, int txt_elem_bytes,

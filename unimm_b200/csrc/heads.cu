@@ -67,6 +67,50 @@ pooler_nsp_kernel(const float* __restrict__ xt, int ldt_seq, const float* __rest
     }
 }
 
+// packed-layout variant: explicit row indices for the pooled text / image rows
+__global__ void __launch_bounds__(256)
+pooler_nsp_indexed_kernel(const float* __restrict__ xt, int ldt, const int* __restrict__ cls_row, const float* __restrict__ xv,
+                          int ldv, const int* __restrict__ img_row, int Ht, int Hv, int Hb, const float* __restrict__ Wt,
+                          const float* __restrict__ bt, const float* __restrict__ Wv, const float* __restrict__ bv,
+                          const float* __restrict__ Wn, const float* __restrict__ bn, float* __restrict__ nsp) {
+    extern __shared__ float sm[];
+    float* st = sm;
+    float* sv = st + Ht;
+    float* sz = sv + Hv;
+    __shared__ float scratch[32];
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const float* rt = xt + static_cast<size_t>(cls_row[c]) * ldt;
+    const float* rv = xv + static_cast<size_t>(img_row[c]) * ldv;
+    for (int i = tid; i < Ht; i += blockDim.x) st[i] = rt[i];
+    for (int i = tid; i < Hv; i += blockDim.x) sv[i] = rv[i];
+    __syncthreads();
+    for (int j = warp; j < Hb; j += nw) {
+        float a = 0.f, d = 0.f;
+        const float* wt = Wt + static_cast<size_t>(j) * Ht;
+        const float* wv = Wv + static_cast<size_t>(j) * Hv;
+        for (int i = lane; i < Ht; i += 32) a = fmaf(__ldg(wt + i), st[i], a);
+        for (int i = lane; i < Hv; i += 32) d = fmaf(__ldg(wv + i), sv[i], d);
+        a = warp_sum(a);
+        d = warp_sum(d);
+        if (lane == 0) sz[j] = fmaxf(a + bt[j], 0.f) * fmaxf(d + bv[j], 0.f);
+    }
+    __syncthreads();
+    for (int o = 0; o < 2; ++o) {
+        float a = 0.f;
+        for (int i = tid; i < Hb; i += blockDim.x) a = fmaf(__ldg(Wn + o * Hb + i), sz[i], a);
+        a = block_sum(a, scratch);
+        if (tid == 0) nsp[c * 2 + o] = a + bn[o];
+    }
+}
+
+__global__ void segment_sum_kernel(const float* __restrict__ vals, const int* __restrict__ off, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int i = off[c]; i < off[c + 1]; ++i) s += vals[i];
+    out[c] = s;
+}
+
 // log p(label) and log(max(1 - p(label), 1e-6)) from one row of materialised fp32 logits
 __global__ void __launch_bounds__(256)
 lse_logits_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ labels, float* __restrict__ logp,
@@ -243,6 +287,23 @@ int pooler_nsp(const float* xt, int ldt_seq, const float* xv, int ldv_seq, int B
                cudaStream_t stream) {
     const size_t smem = sizeof(float) * (Ht + Hv + Hb);
     pooler_nsp_kernel<<<B, 256, smem, stream>>>(xt, ldt_seq, xv, ldv_seq, Ht, Hv, Hb, Wt, bt, Wv, bv, Wn, bn, nsp_logits);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int pooler_nsp_indexed(const float* xt, int ldt, const int* cls_row, const float* xv, int ldv, const int* img_row, int C, int Ht,
+                       int Hv, int Hb, const float* Wt, const float* bt, const float* Wv, const float* bv, const float* Wn,
+                       const float* bn, float* nsp_logits, cudaStream_t stream) {
+    if (C == 0) return 0;
+    const size_t smem = sizeof(float) * (Ht + Hv + Hb);
+    pooler_nsp_indexed_kernel<<<C, 256, smem, stream>>>(xt, ldt, cls_row, xv, ldv, img_row, Ht, Hv, Hb, Wt, bt, Wv, bv, Wn, bn, nsp_logits);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int segment_sum(const float* vals, const int* off, int C, float* out, cudaStream_t stream) {
+    if (C == 0) return 0;
+    segment_sum_kernel<<<(C + 127) / 128, 128, 0, stream>>>(vals, off, C, out);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -44,6 +44,10 @@ int embed_text_ln(const int64_t* ids, const int64_t* type_ids, const int64_t* po
                   int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
                   const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
                   bf16* out_bf16, int lp_kind, int* err_flag, cudaStream_t stream);
+int embed_text_ln_i32(const int32_t* ids, const int32_t* type_ids, const int32_t* pos_ids, int rows, int H, int vocab,
+                      int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
+                      const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
+                      bf16* out_bf16, int lp_kind, int* err_flag, cudaStream_t stream);
 // y = LayerNorm(x) * gamma + beta, eps 1e-12 inside the sqrt, biased variance; x may alias y_f32.
 int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma, const float* beta, float* y_f32,
                    bf16* y_bf16, int lp_kind, cudaStream_t stream);
@@ -81,7 +85,34 @@ int attention_simt_f32(const AttnArgs& a, cudaStream_t stream);
 int attention_simt_lp(const AttnArgs& a, cudaStream_t stream);
 int attention_mma_lp(const AttnArgs& a, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------ attention_jobs.cu
+// Prefix-shared layout: attention as a list of jobs over packed rows (see attention_jobs.cu).
+struct AttnJobsArgs {
+    const void* q; int ldq;
+    const void* k; int ldk;
+    const void* v; int ldv;
+    void* o; int ldo;
+    int heads, D;
+    const int* jobs;       // [n_jobs, 8] = q_start, q_len, kv_start, kv_len, win, mask_row, -, -
+    int n_jobs;
+    int max_q_len;         // longest q_len among the jobs (grid sizing)
+    int kv_cap;            // staged rows for the shared range, multiple of 64, >= every kv_len
+    int win_cap;           // staged rows for the per-CTA window, multiple of 64 (0 when no job has win)
+    const int* row_iv;     // [rows, 4] = lo, hi, self, - (packed row indices) for rows of win jobs
+    const float* key_mask; // [units, key_mask_ld] for jobs with mask_row >= 0
+    int key_mask_ld;
+    float scale;
+    int lp_kind;
+};
+int attention_jobs(const AttnJobsArgs& a, bool fp32, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------ heads.cu
+// packed layout: text pooled row = xt[cls_row[c]], image pooled row = xv[unit[c] * R]
+int pooler_nsp_indexed(const float* xt, int ldt, const int* cls_row, const float* xv, int ldv, const int* img_row, int C, int Ht,
+                       int Hv, int Hb, const float* Wt, const float* bt, const float* Wv, const float* bv, const float* Wn,
+                       const float* bn, float* nsp_logits, cudaStream_t stream);
+// per-candidate sum of the compact per-row log-probs: rows [off[c], off[c+1])
+int segment_sum(const float* vals, const int* off, int C, float* out, cudaStream_t stream);
 // poolers + 'mul' fusion + NSP linear (ref :946-967, :1062-1070), all fp32
 int pooler_nsp(const float* xt, int ldt_seq, const float* xv, int ldv_seq, int B, int Ht, int Hv, int Hb, const float* Wt,
                const float* bt, const float* Wv, const float* bv, const float* Wn, const float* bn, float* nsp_logits,

@@ -59,10 +59,10 @@ layernorm_kernel(const float* __restrict__ x, int ldx, int rows, const float* __
                            y_bf16 ? y_bf16 + static_cast<size_t>(row) * H : nullptr, lp_kind);
 }
 
-template <int NV>
+template <int NV, typename IdT>
 __global__ void __launch_bounds__(128)
-embed_text_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
-                     const int64_t* __restrict__ pos_ids, int rows, int vocab, int max_pos, int type_vocab, int type_ext,
+embed_text_ln_kernel(const IdT* __restrict__ ids, const IdT* __restrict__ type_ids,
+                     const IdT* __restrict__ pos_ids, int rows, int vocab, int max_pos, int type_vocab, int type_ext,
                      const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
                      const float* __restrict__ type_emb, const float* __restrict__ type_ext_emb,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float* out_f32, bf16* out_bf16,
@@ -190,23 +190,38 @@ int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma,
     return 0;
 }
 
+template <typename IdT>
+static int embed_text_ln_t(const IdT* ids, const IdT* type_ids, const IdT* pos_ids, int rows, int H, int vocab, int max_pos,
+                           int type_vocab, int type_ext, const float* word_emb, const float* pos_emb, const float* type_emb,
+                           const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32, bf16* out_bf16,
+                           int lp_kind, int* err_flag, cudaStream_t stream) {
+    UNIMM_CHECK(rows > 0, "embed: no rows");
+    const int grid = (rows + 3) / 4;
+    if (H == 768)
+        embed_text_ln_kernel<6, IdT><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext, word_emb,
+                                                               pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32, out_bf16, lp_kind, err_flag);
+    else if (H == 1024)
+        embed_text_ln_kernel<8, IdT><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext, word_emb,
+                                                               pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32, out_bf16, lp_kind, err_flag);
+    else UNIMM_CHECK(false, "embed: hidden size must be 768 or 1024");
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
 int embed_text_ln(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int rows, int H, int vocab,
                   int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
                   const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
                   bf16* out_bf16, int lp_kind, int* err_flag, cudaStream_t stream) {
-    UNIMM_CHECK(rows > 0, "embed: no rows");
-    const int grid = (rows + 3) / 4;
-    if (H == 768)
-        embed_text_ln_kernel<6><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext,
-                                                          word_emb, pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32,
-                                                          out_bf16, lp_kind, err_flag);
-    else if (H == 1024)
-        embed_text_ln_kernel<8><<<grid, 128, 0, stream>>>(ids, type_ids, pos_ids, rows, vocab, max_pos, type_vocab, type_ext,
-                                                          word_emb, pos_emb, type_emb, type_ext_emb, gamma, beta, out_f32,
-                                                          out_bf16, lp_kind, err_flag);
-    else UNIMM_CHECK(false, "embed: hidden size must be 768 or 1024");
-    UNIMM_LAUNCH_CHECK(1);
-    return 0;
+    return embed_text_ln_t<int64_t>(ids, type_ids, pos_ids, rows, H, vocab, max_pos, type_vocab, type_ext, word_emb, pos_emb, type_emb,
+                                    type_ext_emb, gamma, beta, out_f32, out_bf16, lp_kind, err_flag, stream);
+}
+
+int embed_text_ln_i32(const int32_t* ids, const int32_t* type_ids, const int32_t* pos_ids, int rows, int H, int vocab,
+                      int max_pos, int type_vocab, int type_ext, const float* word_emb, const float* pos_emb,
+                      const float* type_emb, const float* type_ext_emb, const float* gamma, const float* beta, float* out_f32,
+                      bf16* out_bf16, int lp_kind, int* err_flag, cudaStream_t stream) {
+    return embed_text_ln_t<int32_t>(ids, type_ids, pos_ids, rows, H, vocab, max_pos, type_vocab, type_ext, word_emb, pos_emb, type_emb,
+                                    type_ext_emb, gamma, beta, out_f32, out_bf16, lp_kind, err_flag, stream);
 }
 
 int image_loc_embed(const float* loc, const int* feat_index, int B, int R, int H, const float* Wloc, const float* bloc,

@@ -154,6 +154,35 @@ class Engine:
         out["_keepalive"] = keep
         return out
 
+    # ------------------------------------------------------------------------------------------ prefix-shared path
+    def forward_packed(self, pb, want=("seq_score", "nsp_scores")) -> Dict[str, torch.Tensor]:
+        """Prefix-shared generative scoring of a ``packing.PackedBatch`` whose tensors are on this device."""
+        dev = self.device
+        for k, t in pb.tensors().items():
+            if t.device != dev:
+                raise ValueError(f"packed tensor {k} is on {t.device}, expected {dev} (use PackedBatch.to)")
+        out = {}
+        if "seq_score" in want:
+            out["seq_score"] = torch.zeros(pb.n_cands, device=dev)
+        if "nsp_scores" in want:
+            out["nsp_scores"] = torch.zeros(pb.n_cands, 2, device=dev)
+        if "token_logp" in want:
+            out["token_logp"] = torch.zeros(pb.lm_rows.shape[0], device=dev)
+        s = pb.c_struct()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.unimm_forward_packed(self._h, C.byref(s), ptr(out.get("seq_score")), ptr(out.get("nsp_scores")),
+                                       ptr(out.get("token_logp")), C.c_void_p(stream)))
+        return out
+
+    def score_packed_host(self, pb, seq_score: torch.Tensor, nsp_scores: Optional[torch.Tensor] = None) -> None:
+        """End to end from (pinned) host tensors: H2D of the packed arrays + forward + D2H of the scores + sync."""
+        for k, t in pb.tensors().items():
+            if t.device.type != "cpu":
+                raise ValueError(f"packed tensor {k} must be a host tensor")
+        s = pb.c_struct()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib.unimm_score_packed_host(self._h, C.byref(s), ptr(seq_score), ptr(nsp_scores), C.c_void_p(stream)))
+
     # ------------------------------------------------------------------------------------------ profiling
     PROFILE_CLASSES = ("gemm", "attention", "layernorm", "lm_head", "other")
 

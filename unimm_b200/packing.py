@@ -1,0 +1,208 @@
+"""Prefix-shared ("packed") input layout for generative ranking.
+
+In generative mode (reference utils/data_utils.py:199-210) the context rows ``[1, ctx)`` attend only the
+context, and the image rows attend only the context (co-attention mask ``[1, ctx)``), so for the 100 candidate
+answers of one dialog round they are bit-identical.  A *unit* = (image, round) therefore stores
+
+    shared rows      original positions 1 .. ctx-1            (once per unit)
+    candidate rows   [CLS] (position 0), the visible answer copy A (positions ctx .. L-1) and the masked copy B
+                     (positions L .. T-1)                      (once per candidate: 1 + 2*last_len rows)
+
+Text rows of a forward are packed as ``[all units' shared rows | all candidates' rows]``.  This module turns the
+reference-format per-sequence arrays (tokens / segments / positions / labels ``[n,256]`` + descriptors, i.e. what
+``encode_input_gen`` produces and ``unimm_b200.synthetic`` generates) into that layout plus the attention job
+lists and per-row intervals ``libunimm_b200`` consumes (include/unimm_b200.h: ``unimm_packed_batch_t``).
+
+Which keys a packed row attends (equals the dense mask restricted to real rows):
+    shared row          all shared rows of its unit
+    [CLS]               shared rows + all rows of its own candidate            (dense: [0, T))
+    A_k                 shared rows + A_0..A_k                                  (dense: [1, i])
+    B_k                 shared rows + A_0..A_{k-1} + itself                     (dense: [1, j-last) U {j})
+    image region        the unit's image rows (self) / the unit's shared rows (co-attention)
+    any text row        the unit's image rows in the text->image co-attention
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+R_DEFAULT = 37
+Q_TILE = 128          # query rows per CTA of the candidate attention (csrc/attention_jobs.cu, NW = 8)
+
+
+@dataclass
+class UnitArrays:
+    """One (image, round): dense reference-format arrays of its n candidates (all share the context)."""
+    tokens: np.ndarray      # [n,S]
+    segments: np.ndarray    # [n,S]
+    positions: np.ndarray   # [n,S]
+    labels: np.ndarray      # [n,S]
+    desc: np.ndarray        # [n,4] (mode, ctx, L, last_len)
+    image_slot: int = 0     # which feature block of the batch this unit uses
+
+
+class PackedBatch:
+    """Host-side packed batch (torch CPU tensors, optionally pinned) + counts."""
+
+    INT_FIELDS = ("input_ids", "token_type_ids", "position_ids", "row_iv", "jobs_text_self", "jobs_t2i", "jobs_i2t",
+                  "jobs_img_self", "lm_rows", "lm_labels", "cand_lm_off", "cand_cls_row", "cand_img_row")
+    FLOAT_FIELDS = ("image_feat", "image_loc", "image_mask")
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def tensors(self):
+        return {k: getattr(self, k) for k in self.INT_FIELDS + self.FLOAT_FIELDS}
+
+    def pin(self) -> "PackedBatch":
+        for k, t in self.tensors().items():
+            setattr(self, k, t.contiguous().pin_memory())
+        return self
+
+    def to(self, device) -> "PackedBatch":
+        out = PackedBatch(**self.__dict__)
+        for k, t in self.tensors().items():
+            setattr(out, k, t.to(device, non_blocking=True))
+        return out
+
+    def bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors().values())
+
+    def c_struct(self):
+        from ._lib import PackedBatchStruct
+        s = PackedBatchStruct()
+        s.n_units, s.n_cands, s.n_text_rows = self.n_units, self.n_cands, self.n_text_rows
+        for k in self.INT_FIELDS + self.FLOAT_FIELDS:
+            setattr(s, "d_" + k, C.c_void_p(getattr(self, k).data_ptr()))
+        s.n_jobs_text_self, s.max_q_text_self = self.jobs_text_self.shape[0], self.max_q_text_self
+        s.n_jobs_t2i, s.max_q_t2i = self.jobs_t2i.shape[0], self.max_q_t2i
+        s.n_jobs_i2t, s.n_jobs_img_self = self.jobs_i2t.shape[0], self.jobs_img_self.shape[0]
+        s.kv_cap_text, s.win_cap = self.kv_cap_text, self.win_cap
+        s.n_lm_rows = self.lm_rows.shape[0]
+        s.pairs_text_self, s.pairs_i2t = float(self.pairs_text_self), float(self.pairs_i2t)
+        return s
+
+
+def _roundup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: np.ndarray, image_mask: np.ndarray,
+               R: int = R_DEFAULT, verify_shared: bool = True) -> PackedBatch:
+    """Pack generative-mode units.  ``image_*`` hold one block per *slot* ([n_slots,R,...]); a unit's image rows are
+    gathered from ``unit.image_slot`` (so the 10 rounds of an image can share one host copy)."""
+    U = len(units)
+    sh_len, n_cand, cand_rows = [], [], []
+    for u in units:
+        d = u.desc
+        if (d[:, 0] != 0).any():
+            raise ValueError("prefix sharing applies to generative-mode sequences only")
+        ctx = int(d[0, 1])
+        if (d[:, 1] != ctx).any() or ctx < 2:
+            raise ValueError("all candidates of a unit must share one context of at least one token")
+        if verify_shared and len(d) > 1:
+            same = (u.tokens[:, 1:ctx] == u.tokens[0, 1:ctx]).all() and (u.segments[:, 1:ctx] == u.segments[0, 1:ctx]).all() \
+                and (u.positions[:, 1:ctx] == u.positions[0, 1:ctx]).all()
+            if not same:
+                raise ValueError("candidates of a unit differ in their context rows: cannot share the prefix")
+        sh_len.append(ctx - 1)
+        n_cand.append(len(d))
+        cand_rows.append(1 + 2 * d[:, 3].astype(np.int64))
+    sh_start = np.concatenate([[0], np.cumsum(sh_len)])
+    n_shared = int(sh_start[-1])
+    all_rows = np.concatenate(cand_rows)
+    C_tot = int(all_rows.shape[0])
+    c_start = n_shared + np.concatenate([[0], np.cumsum(all_rows)])     # [C+1] absolute start row of every candidate
+    M = int(c_start[-1])
+    ids = np.zeros(M, np.int32)
+    segs = np.zeros(M, np.int32)
+    pos = np.zeros(M, np.int32)
+    row_iv = np.zeros((M, 4), np.int32)
+    row_iv[:, 2] = -1
+    lm_rows, lm_labels, cand_lm_off = [], [], [0]
+    cls_row = np.zeros(C_tot, np.int32)
+    img_row = np.zeros(C_tot, np.int32)
+    jobs_ts, jobs_t2i, jobs_i2t, jobs_img = [], [], [], []
+    pairs_ts = pairs_i2t = 0
+    ci = 0
+    max_cand_q = 1
+    for ui, u in enumerate(units):
+        ctx = sh_len[ui] + 1
+        s0 = int(sh_start[ui])
+        ids[s0:s0 + ctx - 1] = u.tokens[0, 1:ctx]
+        segs[s0:s0 + ctx - 1] = u.segments[0, 1:ctx]
+        pos[s0:s0 + ctx - 1] = u.positions[0, 1:ctx]
+        n = n_cand[ui]
+        last = u.desc[:, 3].astype(np.int64)
+        L = u.desc[:, 2].astype(np.int64)
+        cs = c_start[ci:ci + n]                                   # absolute first row of each candidate
+        rows_u = int(c_start[ci + n] - c_start[ci])
+        # per-candidate row index inside the candidate: 0 = CLS, 1..last = A, last+1..2last = B
+        rep = 1 + 2 * last
+        owner = np.repeat(np.arange(n), rep)
+        idx = np.arange(rows_u) - np.repeat(cs - cs[0], rep)
+        src_col = np.where(idx == 0, 0, ctx + idx - 1)            # dense column this packed row comes from
+        dst = int(cs[0]) + np.arange(rows_u)
+        ids[dst] = u.tokens[owner, src_col]
+        segs[dst] = u.segments[owner, src_col]
+        pos[dst] = u.positions[owner, src_col]
+        s_abs = np.repeat(cs, rep)
+        last_r = np.repeat(last, rep)
+        is_cls, is_a, is_b = idx == 0, (idx >= 1) & (idx <= last_r), idx > last_r
+        lo = np.where(is_cls, s_abs, s_abs + 1)
+        hi = np.where(is_cls, s_abs + 1 + 2 * last_r, np.where(is_a, s_abs + idx + 1, s_abs + idx - last_r))
+        row_iv[dst, 0], row_iv[dst, 1] = lo, hi
+        row_iv[dst, 2] = np.where(is_b, dst, -1)
+        own_keys = np.where(is_cls, 1 + 2 * last_r, np.where(is_a, idx, idx - last_r))   # own-candidate keys incl. self
+        pairs_ts += (ctx - 1) ** 2 + int(((ctx - 1) + own_keys).sum())
+        pairs_i2t += R * (ctx - 1)
+        lm_rows.append(dst[is_b])
+        lm_labels.append(u.labels[owner[is_b], (L[owner] + idx - last_r - 1)[is_b]])
+        cand_lm_off.extend((cand_lm_off[-1] + np.cumsum(last)).tolist())
+        cls_row[ci:ci + n] = cs
+        img_row[ci:ci + n] = ui * R
+        jobs_ts.append((s0, ctx - 1, s0, ctx - 1, 0, -1, 0, 0))
+        jobs_ts.append((int(cs[0]), rows_u, s0, ctx - 1, 1, -1, 0, 0))
+        jobs_t2i.append((s0, ctx - 1, ui * R, R, 0, ui, 0, 0))
+        jobs_t2i.append((int(cs[0]), rows_u, ui * R, R, 0, ui, 0, 0))
+        jobs_i2t.append((ui * R, R, s0, ctx - 1, 0, -1, 0, 0))
+        jobs_img.append((ui * R, R, ui * R, R, 0, ui, 0, 0))
+        max_cand_q = max(max_cand_q, rows_u)
+        ci += n
+    lm_labels = np.concatenate(lm_labels).astype(np.int32)
+    if (lm_labels < 0).any():
+        raise ValueError("a masked-copy position carries no label")
+    slots = np.asarray([u.image_slot for u in units])
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt))
+    max_rows_per_cand = int(all_rows.max())
+    return PackedBatch(
+        n_units=U, n_cands=C_tot, n_text_rows=M,
+        input_ids=t(ids, np.int32), token_type_ids=t(segs, np.int32), position_ids=t(pos, np.int32), row_iv=t(row_iv, np.int32),
+        jobs_text_self=t(np.asarray(jobs_ts), np.int32), jobs_t2i=t(np.asarray(jobs_t2i), np.int32),
+        jobs_i2t=t(np.asarray(jobs_i2t), np.int32), jobs_img_self=t(np.asarray(jobs_img), np.int32),
+        lm_rows=t(np.concatenate(lm_rows), np.int32), lm_labels=t(lm_labels, np.int32),
+        cand_lm_off=t(np.asarray(cand_lm_off), np.int32), cand_cls_row=t(cls_row, np.int32), cand_img_row=t(img_row, np.int32),
+        image_feat=t(image_feat[slots], np.float32), image_loc=t(image_loc[slots], np.float32), image_mask=t(image_mask[slots], np.float32),
+        max_q_text_self=max(max_cand_q, max(sh_len)), max_q_t2i=max(max_cand_q, max(sh_len)),
+        kv_cap_text=_roundup(max(sh_len), 64), win_cap=_roundup(Q_TILE + 2 * (max_rows_per_cand - 1), 64),
+        pairs_text_self=pairs_ts, pairs_i2t=pairs_i2t, n_dense_rows=C_tot * units[0].tokens.shape[1])
+
+
+def units_from_rounds(rounds, image_slots: Optional[List[int]] = None) -> List[UnitArrays]:
+    """``unimm_b200.synthetic.Round`` objects -> units (one image slot per round unless given)."""
+    return [UnitArrays(r.tokens, r.segments, r.positions, r.labels, r.desc, (image_slots[i] if image_slots else i))
+            for i, r in enumerate(rounds)]
+
+
+def units_from_flat(tokens, segments, positions, labels, desc, unit_index) -> List[UnitArrays]:
+    """Reference-format flat batch ([B,S] tensors + descriptors) grouped by ``unit_index`` [B] (non-decreasing)."""
+    tok, seg, pos, lab, d, ui = (np.asarray(x) for x in (tokens, segments, positions, labels, desc, unit_index))
+    out = []
+    for u in np.unique(ui):
+        m = ui == u
+        out.append(UnitArrays(tok[m], seg[m], pos[m], lab[m], d[m], int(u)))
+    return out
