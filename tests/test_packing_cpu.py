@@ -1,0 +1,71 @@
+"""CPU: the prefix-shared packer against the dense reference masks and arrays."""
+import numpy as np
+import torch
+
+from conftest import load_golden
+from unimm_b200 import synthetic as syn
+from unimm_b200.descriptors import dense_text_mask, descriptors_from_masks
+from unimm_b200.packing import pack_units, units_from_flat, units_from_rounds
+
+
+def _check(pb, rounds):
+    iv, jobs = pb.row_iv.numpy(), pb.jobs_text_self.numpy()
+    lab, off = pb.lm_labels.numpy(), pb.cand_lm_off.numpy()
+    c = 0
+    for ui, r in enumerate(rounds):
+        ctx = int(r.desc[0, 1])
+        sh, cj = jobs[2 * ui], jobs[2 * ui + 1]
+        assert sh[1] == ctx - 1 and tuple(sh[:2]) == tuple(sh[2:4]) and sh[4] == 0          # context attends itself
+        assert cj[3] == ctx - 1 and cj[2] == sh[0] and cj[4] == 1                           # candidates see the context + window
+        assert (pb.input_ids[sh[0]:sh[0] + ctx - 1].numpy() == r.tokens[0, 1:ctx]).all()
+        dm = dense_text_mask(torch.from_numpy(r.desc), 256).numpy()
+        row = int(cj[0])
+        for j in range(len(r.desc)):
+            L, last = int(r.desc[j, 2]), int(r.desc[j, 3])
+            assert pb.cand_cls_row[c] == row
+            for idx in range(1 + 2 * last):
+                col = 0 if idx == 0 else ctx + idx - 1
+                allowed = set(range(1, ctx))
+                lo, hi, sf = iv[row, :3]
+                for a in list(range(lo, hi)) + ([sf] if sf >= 0 else []):
+                    k = a - (row - idx)
+                    assert 0 <= k <= 2 * last, "a row may only see rows of its own candidate"
+                    allowed.add(0 if k == 0 else ctx + k - 1)
+                assert allowed == set(np.nonzero(dm[j, col])[0].tolist()), (ui, j, idx)
+                assert pb.input_ids[row] == r.tokens[j, col] and pb.position_ids[row] == r.positions[j, col]
+                assert pb.token_type_ids[row] == r.segments[j, col]
+                row += 1
+            assert (lab[off[c]:off[c + 1]] == r.labels[j, L:L + last]).all()
+            c += 1
+    assert c == pb.n_cands and pb.win_cap % 64 == 0 and pb.kv_cap_text % 64 == 0 and pb.kv_cap_text <= 256
+
+
+def test_packed_rows_reproduce_dense_masks_and_tokens():
+    rng = np.random.RandomState(0)
+    img = syn.synth_image(rng)
+    rounds = [syn.encode_round_gen(syn.synth_context(rng, r), syn.synth_answers(rng, n)) for r, n in ((1, 7), (3, 12), (10, 9))]
+    pb = pack_units(units_from_rounds(rounds, [0, 0, 0]), img[0][None], img[1][None], img[2][None])
+    _check(pb, rounds)
+    assert pb.n_text_rows == sum(int(r.desc[0, 1]) - 1 + int((1 + 2 * r.desc[:, 3]).sum()) for r in rounds)
+
+
+def test_packing_the_reference_made_inputs():
+    g, batch = load_golden("gen100_default")
+    desc = descriptors_from_masks(batch["txt_attention_mask"], batch["co_attention_mask"])
+    units = units_from_flat(batch["tokens"], batch["segments"], batch["positions"], batch["mask"], desc, np.zeros(100, np.int64))
+    pb = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None])
+    r = syn.Round(batch["tokens"].numpy(), batch["segments"].numpy(), batch["positions"].numpy(), batch["mask"].numpy(), desc.numpy())
+    _check(pb, [r])
+    assert pb.n_text_rows == 238 + int((1 + 2 * desc[:, 3]).sum())
+
+
+def test_packer_rejects_units_that_do_not_share_a_context():
+    rng = np.random.RandomState(1)
+    img = syn.synth_image(rng)
+    r = syn.encode_round_gen(syn.synth_context(rng, 2), syn.synth_answers(rng, 4))
+    r.tokens[2, 5] += 1
+    try:
+        pack_units(units_from_rounds([r]), img[0][None], img[1][None], img[2][None])
+    except ValueError:
+        return
+    raise AssertionError("differing contexts must be rejected")
