@@ -120,8 +120,10 @@ typedef struct {
     const float* d_image_feat;                   /* [U,R,v_feature_size]                                       */
     const float* d_image_loc;                    /* [U,R,5]                                                    */
     const float* d_image_mask;                   /* [U,R]                                                      */
-    const int32_t* d_jobs_text_self;             /* [n,8] context-self jobs and candidate jobs (win = 1)       */
-    int32_t n_jobs_text_self, max_q_text_self;
+    const int32_t* d_jobs_text_self;             /* [n,8] first the context-self jobs, then the candidate jobs */
+    int32_t n_jobs_text_self, max_q_text_self;   /*       (win = 1)                                            */
+    int32_t n_jobs_text_ctx;                     /* how many of them are context-self jobs                     */
+    int32_t cand_halo;                           /* longest candidate's row count - 1                          */
     const int32_t* d_jobs_t2i;                   /* [n,8] text rows of a unit over its image rows              */
     int32_t n_jobs_t2i, max_q_t2i;
     const int32_t* d_jobs_i2t;                   /* [U,8] image rows over the unit's context rows              */

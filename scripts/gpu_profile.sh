@@ -1,14 +1,13 @@
-# ncu evidence for profiles/: (1) every launch with its device time, (2) one full capture of the top kernel.
+# ncu evidence for profiles/: (1) every launch with its device time, (2) full captures of the top kernels.
 mkdir -p gpurun_out
-set -x
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --precision ${PREC:-fp16}"
+rm -f gpurun_out/prof_*.ncu-rep gpurun_out/launches.csv
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --precision ${PREC:-fp16} --mode ${MODE:-packed} --images-per-step ${IPS:-8}"
 $CMD > gpurun_out/prof_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
-tail -2 gpurun_out/ncu_launches.log
+ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-400} -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+tail -1 gpurun_out/ncu_launches.log | cut -c1-200
 $CMD > gpurun_out/prof_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:umma_gemm -s 40 -c 4 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
-tail -2 gpurun_out/ncu_gemm.log
+ncu --set full --clock-control none --import-source on -k regex:umma_gemm -s 60 -c 6 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
+tail -1 gpurun_out/ncu_gemm.log | cut -c1-200
 $CMD > gpurun_out/prof_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:attn_mma -s 8 -c 3 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1
-tail -2 gpurun_out/ncu_attn.log
-ls -la gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:attn_jobs -s 4 -c 5 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1
+tail -1 gpurun_out/ncu_attn.log | cut -c1-200

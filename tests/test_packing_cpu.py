@@ -14,7 +14,7 @@ def _check(pb, rounds):
     c = 0
     for ui, r in enumerate(rounds):
         ctx = int(r.desc[0, 1])
-        sh, cj = jobs[2 * ui], jobs[2 * ui + 1]
+        sh, cj = jobs[ui], jobs[pb.n_jobs_text_ctx + ui]
         assert sh[1] == ctx - 1 and tuple(sh[:2]) == tuple(sh[2:4]) and sh[4] == 0          # context attends itself
         assert cj[3] == ctx - 1 and cj[2] == sh[0] and cj[4] == 1                           # candidates see the context + window
         assert (pb.input_ids[sh[0]:sh[0] + ctx - 1].numpy() == r.tokens[0, 1:ctx]).all()

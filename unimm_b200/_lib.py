@@ -60,6 +60,7 @@ class PackedBatchStruct(C.Structure):
         ("d_input_ids", C.c_void_p), ("d_token_type_ids", C.c_void_p), ("d_position_ids", C.c_void_p), ("d_row_iv", C.c_void_p),
         ("d_image_feat", C.c_void_p), ("d_image_loc", C.c_void_p), ("d_image_mask", C.c_void_p),
         ("d_jobs_text_self", C.c_void_p), ("n_jobs_text_self", C.c_int32), ("max_q_text_self", C.c_int32),
+        ("n_jobs_text_ctx", C.c_int32), ("cand_halo", C.c_int32),
         ("d_jobs_t2i", C.c_void_p), ("n_jobs_t2i", C.c_int32), ("max_q_t2i", C.c_int32),
         ("d_jobs_i2t", C.c_void_p), ("n_jobs_i2t", C.c_int32),
         ("d_jobs_img_self", C.c_void_p), ("n_jobs_img_self", C.c_int32),

@@ -242,6 +242,242 @@ attn_jobs_kernel(AttnJobsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Candidate rows of a unit over  context U own rows  (text self-attention, D = 64): persistent over the
+// unit's query tiles.  The context K/V (the big, shared part) is staged ONCE per CTA; per 128-row query tile
+// only the Q rows and the window  [tile - halo, tile + 128 + halo)  (halo = longest candidate - 1 rows, so it
+// contains every row's own-candidate interval) are loaded, double-buffered with cp.async so that the loads of
+// tile i+1 overlap the tensor-core work of tile i.
+// ------------------------------------------------------------------------------------------------
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+attn_cand_kernel(AttnJobsArgs a, int halo) {
+    constexpr int D = 64, NW = 8, MQT = 128, LD = D + PADE, NT = 256, CH = D / 8;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    bf16* Ks0 = reinterpret_cast<bf16*>(smem_raw);                       // [kv_cap][LD]  context keys
+    bf16* Vs0 = Ks0 + static_cast<size_t>(a.kv_cap) * LD;               // [kv_cap][LD]
+    bf16* buf0 = Vs0 + static_cast<size_t>(a.kv_cap) * LD;              // 2 x { Q [MQT][LD], Kw [win_cap][LD], Vw [win_cap][LD] }
+    const size_t buf_elems = static_cast<size_t>(MQT + 2 * a.win_cap) * LD;
+
+    const int* job = a.jobs + static_cast<size_t>(blockIdx.z) * 8;
+    const int q_start = job[0], q_len = job[1], kv_start = job[2], kv_len = job[3];
+    const int h = blockIdx.y;
+    const int n_tiles = (q_len + MQT - 1) / MQT;
+    if (static_cast<int>(blockIdx.x) >= n_tiles) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const bf16* Q = static_cast<const bf16*>(a.q) + h * D;
+    const bf16* K = static_cast<const bf16*>(a.k) + h * D;
+    const bf16* V = static_cast<const bf16*>(a.v) + h * D;
+    bf16* O = static_cast<bf16*>(a.o) + h * D;
+    const int n1p = ((kv_len + MKT - 1) / MKT) * MKT;
+    const int q_end = q_start + q_len;                                   // packed-row end of the job
+
+    // context K/V: once
+    for (int i = tid; i < n1p * CH; i += NT) {
+        const int r = i / CH, c = (i % CH) * 8;
+        if (r < kv_len) {
+            cp_async16(Ks0 + r * LD + c, K + static_cast<size_t>(kv_start + r) * a.ldk + c);
+            cp_async16(Vs0 + r * LD + c, V + static_cast<size_t>(kv_start + r) * a.ldv + c);
+        } else {
+            *reinterpret_cast<uint4*>(Ks0 + r * LD + c) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(Vs0 + r * LD + c) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    auto window_of = [&](int tile, int& w_lo, int& n2) {
+        const int r0 = q_start + tile * MQT;
+        w_lo = max(q_start, r0 - halo);
+        n2 = min(min(q_end, r0 + MQT + halo) - w_lo, a.win_cap);
+    };
+    auto prefetch = [&](int tile, int b) {
+        bf16* Qs = buf0 + b * buf_elems;
+        bf16* Kw = Qs + MQT * LD;
+        bf16* Vw = Kw + static_cast<size_t>(a.win_cap) * LD;
+        const int r0 = q_start + tile * MQT;
+        for (int i = tid; i < MQT * CH; i += NT) {
+            const int r = i / CH, c = (i % CH) * 8;
+            if (r0 + r < q_end) cp_async16(Qs + r * LD + c, Q + static_cast<size_t>(r0 + r) * a.ldq + c);
+            else *reinterpret_cast<uint4*>(Qs + r * LD + c) = make_uint4(0, 0, 0, 0);
+        }
+        int w_lo, n2;
+        window_of(tile, w_lo, n2);
+        const int n2p = ((n2 + MKT - 1) / MKT) * MKT;
+        for (int i = tid; i < n2p * CH; i += NT) {
+            const int r = i / CH, c = (i % CH) * 8;
+            if (r < n2) {
+                cp_async16(Kw + r * LD + c, K + static_cast<size_t>(w_lo + r) * a.ldk + c);
+                cp_async16(Vw + r * LD + c, V + static_cast<size_t>(w_lo + r) * a.ldv + c);
+            } else {
+                *reinterpret_cast<uint4*>(Kw + r * LD + c) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(Vw + r * LD + c) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const float sl = a.scale * 1.4426950408889634f;
+    int b = 0;
+    prefetch(blockIdx.x, 0);                                             // group 0 = context K/V + first tile
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, b ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) {
+            prefetch(next, b ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the newest group has landed
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        // this thread's two rows: own-candidate intervals (global loads overlap the barrier below)
+        const int r0 = q_start + tile * MQT;
+        const int ra = min(r0 + warp * 16 + g, q_end - 1), rb = min(r0 + warp * 16 + g + 8, q_end - 1);
+        const int4 ia = *reinterpret_cast<const int4*>(a.row_iv + static_cast<size_t>(ra) * 4);
+        const int4 ib = *reinterpret_cast<const int4*>(a.row_iv + static_cast<size_t>(rb) * 4);
+        __syncthreads();
+        const bf16* Qs = buf0 + b * buf_elems;
+        const bf16* Kw = Qs + MQT * LD;
+        const bf16* Vw = Kw + static_cast<size_t>(a.win_cap) * LD;
+        int w_lo, n2;
+        window_of(tile, w_lo, n2);
+        // window-buffer coordinates of the two rows' intervals, and the warp's window tile range
+        const int lo0 = ia.x - w_lo, hi0 = ia.y - w_lo, sf0 = ia.z >= 0 ? ia.z - w_lo : -1;
+        const int lo1 = ib.x - w_lo, hi1 = ib.y - w_lo, sf1 = ib.z >= 0 ? ib.z - w_lo : -1;
+        int wmin = min(min(lo0, lo1), min(sf0 >= 0 ? sf0 : lo0, sf1 >= 0 ? sf1 : lo1));
+        int wmax = max(max(hi0, hi1), max(sf0 + 1, sf1 + 1));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+            wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        }
+        const int wt_begin = (max(wmin, 0) / MKT) * MKT;
+        const int wt_end = min(((max(wmax, 0) + MKT - 1) / MKT) * MKT, ((n2 + MKT - 1) / MKT) * MKT);
+
+        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+        float o[D / 8][4];
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        const bf16* q_base = Qs + (warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + 8 * (lane >> 4);
+
+        auto process = [&](const bf16* k_tile, const bf16* v_tile, unsigned long long m0, unsigned long long m1) {
+            float s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+                uint32_t qa[4];
+                ldsm_x4(qa, q_base + ks * 16);
+#pragma unroll
+                for (int nb2 = 0; nb2 < 4; ++nb2) {
+                    uint32_t kb[4];
+                    ldsm_x4(kb, k_tile + (nb2 * 16 + (lane & 7) + 8 * (lane >> 4)) * LD + ks * 16 + 8 * ((lane >> 3) & 1));
+                    mma_lp<FP16>(s[2 * nb2], qa, kb[0], kb[1]);
+                    mma_lp<FP16>(s[2 * nb2 + 1], qa, kb[2], kb[3]);
+                }
+            }
+            if (!__all_sync(0xffffffffu, (m0 & m1) == ~0ull)) {
+                m0 >>= 2 * t;
+                m1 >>= 2 * t;
+                const uint32_t a0 = static_cast<uint32_t>(m0), a1 = static_cast<uint32_t>(m0 >> 32);
+                const uint32_t b0 = static_cast<uint32_t>(m1), b1 = static_cast<uint32_t>(m1 >> 32);
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) {
+                    const uint32_t wa = nb < 4 ? a0 : a1, wb = nb < 4 ? b0 : b1;
+                    const int sh = (nb & 3) * 8;
+                    if (!((wa >> sh) & 1u)) s[nb][0] = -INFINITY;
+                    if (!((wa >> (sh + 1)) & 1u)) s[nb][1] = -INFINITY;
+                    if (!((wb >> sh) & 1u)) s[nb][2] = -INFINITY;
+                    if (!((wb >> (sh + 1)) & 1u)) s[nb][3] = -INFINITY;
+                }
+            }
+            float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                tmax[0] = fmaxf(tmax[0], fmaxf(s[nb][0], s[nb][1]));
+                tmax[1] = fmaxf(tmax[1], fmaxf(s[nb][2], s[nb][3]));
+            }
+            float corr[2], msl[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
+                tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
+                const float m_new = fmaxf(m_run[r], tmax[r]);
+                corr[r] = (m_new == -INFINITY) ? 1.f : fast_exp2((m_run[r] - m_new) * sl);
+                m_run[r] = m_new;
+                msl[r] = (m_new == -INFINITY) ? 0.f : m_new * sl;
+                l_run[r] *= corr[r];
+            }
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                s[nb][0] = fast_exp2(fmaf(s[nb][0], sl, -msl[0]));
+                s[nb][1] = fast_exp2(fmaf(s[nb][1], sl, -msl[0]));
+                s[nb][2] = fast_exp2(fmaf(s[nb][2], sl, -msl[1]));
+                s[nb][3] = fast_exp2(fmaf(s[nb][3], sl, -msl[1]));
+                l_run[0] += s[nb][0] + s[nb][1];
+                l_run[1] += s[nb][2] + s[nb][3];
+            }
+            if (__any_sync(0xffffffffu, corr[0] != 1.f || corr[1] != 1.f)) {
+#pragma unroll
+                for (int i = 0; i < D / 8; ++i) {
+                    o[i][0] *= corr[0]; o[i][1] *= corr[0];
+                    o[i][2] *= corr[1]; o[i][3] *= corr[1];
+                }
+            }
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                uint32_t pa[4];
+                pa[0] = pack2<FP16>(s[2 * kc][0], s[2 * kc][1]);
+                pa[1] = pack2<FP16>(s[2 * kc][2], s[2 * kc][3]);
+                pa[2] = pack2<FP16>(s[2 * kc + 1][0], s[2 * kc + 1][1]);
+                pa[3] = pack2<FP16>(s[2 * kc + 1][2], s[2 * kc + 1][3]);
+#pragma unroll
+                for (int db2 = 0; db2 < D / 16; ++db2) {
+                    uint32_t vb[4];
+                    ldsm_x4_trans(vb, v_tile + (kc * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + db2 * 16 + 8 * (lane >> 4));
+                    mma_lp<FP16>(o[2 * db2], pa, vb[0], vb[1]);
+                    mma_lp<FP16>(o[2 * db2 + 1], pa, vb[2], vb[3]);
+                }
+            }
+        };
+        if (r0 + warp * 16 < q_end) {                                    // warps past the job's last row have nothing to do
+            for (int t0 = 0; t0 < n1p; t0 += MKT) {                      // context: every real key allowed
+                const unsigned long long m = tile_mask(0, kv_len, -1, t0);
+                process(Ks0 + static_cast<size_t>(t0) * LD, Vs0 + static_cast<size_t>(t0) * LD, m, m);
+            }
+            for (int t0 = wt_begin; t0 < wt_end; t0 += MKT)              // own candidate: interval + self
+                process(Kw + static_cast<size_t>(t0) * LD, Vw + static_cast<size_t>(t0) * LD, tile_mask(lo0, hi0, sf0, t0),
+                        tile_mask(lo1, hi1, sf1, t0));
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+                l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+            }
+            const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+            const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+            const int row0 = r0 + warp * 16 + g, row1 = row0 + 8;
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) {
+                const int col = i * 8 + 2 * t;
+                if (row0 < q_end) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row0) * a.ldo + col) = pack2<FP16>(o[i][0] * inv0, o[i][1] * inv0);
+                if (row1 < q_end) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row1) * a.ldo + col) = pack2<FP16>(o[i][2] * inv1, o[i][3] * inv1);
+            }
+        }
+        __syncthreads();   // buffer b is refilled by the prefetch issued in the next iteration
+    }
+}
+
+template <bool FP16>
+int launch_cand(const AttnJobsArgs& a, int halo, cudaStream_t stream) {
+    const size_t smem = sizeof(bf16) * (2 * static_cast<size_t>(a.kv_cap) + 2 * (128 + 2 * static_cast<size_t>(a.win_cap))) * (64 + PADE);
+    UNIMM_CHECK(smem <= 227 * 1024, "candidate attention: staging does not fit shared memory");
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cand_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int max_tiles = (a.max_q_len + 127) / 128;
+    dim3 grid(max_tiles < 2 ? max_tiles : 2, a.heads, a.n_jobs);     // two CTAs share a unit's tiles: ~2 x heads x units CTAs
+    attn_cand_kernel<FP16><<<grid, 256, smem, stream>>>(a, halo);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 CUDA-core version of the same job semantics (fp32 parity mode; simple, one warp per query row)
 // ------------------------------------------------------------------------------------------------
 template <int D>
@@ -326,6 +562,15 @@ int dispatch_jobs(const AttnJobsArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// candidate jobs (win = 1 for every job, D = 64) through the persistent double-buffered kernel
+int attention_candidates(const AttnJobsArgs& a, int halo, cudaStream_t stream) {
+    UNIMM_CHECK(a.n_jobs > 0 && a.n_jobs <= 65535 && a.D == 64 && a.win_cap % 64 == 0 && a.kv_cap % 64 == 0 && a.kv_cap <= 256,
+                "candidate attention: bad arguments");
+    UNIMM_CHECK(a.win_cap >= 128 + 2 * halo, "candidate attention: window capacity smaller than tile + 2 * halo");
+    UNIMM_CHECK((a.ldq % 8) == 0 && (a.ldk % 8) == 0 && (a.ldv % 8) == 0 && (a.ldo % 2) == 0, "attention jobs: rows must be 16-byte aligned");
+    return a.lp_kind == LP_FP16 ? launch_cand<true>(a, halo, stream) : launch_cand<false>(a, halo, stream);
+}
 
 int attention_jobs(const AttnJobsArgs& a, bool fp32, cudaStream_t stream) {
     UNIMM_CHECK(a.n_jobs > 0 && a.n_jobs <= 65535 && a.heads > 0 && a.max_q_len > 0, "attention jobs: bad problem size");

@@ -67,6 +67,13 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// 2^x on the SFU (ex2.approx.ftz: ~2 ulp, exact 0 for -inf)
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // exact (erf) GELU, reference models/vilbert_dialog.py:115-121
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
 

@@ -402,8 +402,21 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
     const void *qp = qkv, *kp = byte_ptr(qkv) + e * H, *vp = byte_ptr(qkv) + e * 2 * H;
     if (ac.pk != nullptr) {
         const unimm_packed_batch_t& pk = *ac.pk;
-        if (text) UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_text_self, pk.n_jobs_text_self,
-                                             pk.max_q_text_self, pk.kv_cap_text, pk.win_cap, pk.pairs_text_self, ac, st));
+        if (text && lp() && D == 64) {
+            // context rows attend their context (plain jobs); candidate rows run the persistent double-buffered kernel
+            const int n_ctx = pk.n_jobs_text_ctx, n_cand = pk.n_jobs_text_self - pk.n_jobs_text_ctx;
+            UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_text_self, n_ctx, pk.kv_cap_text,
+                                       pk.kv_cap_text, 0, 0.0, ac, st));
+            AttnJobsArgs a;
+            a.q = qp; a.ldq = 3 * H; a.k = kp; a.ldk = 3 * H; a.v = vp; a.ldv = 3 * H; a.o = ctx; a.ldo = H;
+            a.heads = heads; a.D = D; a.jobs = pk.d_jobs_text_self + static_cast<size_t>(n_ctx) * 8; a.n_jobs = n_cand;
+            a.max_q_len = pk.max_q_text_self; a.kv_cap = pk.kv_cap_text; a.win_cap = pk.win_cap;
+            a.row_iv = pk.d_row_iv; a.key_mask = nullptr; a.key_mask_ld = 0;
+            a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind();
+            Prof prof(this, CAT_ATTN, 4.0 * heads * D * pk.pairs_text_self, st);
+            UNIMM_TRY(attention_candidates(a, pk.cand_halo, st));
+        } else if (text) UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_text_self, pk.n_jobs_text_self,
+                                                    pk.max_q_text_self, pk.kv_cap_text, pk.win_cap, pk.pairs_text_self, ac, st));
         else UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_img_self, pk.n_jobs_img_self,
                                         cfg.num_regions, 64, 0, static_cast<double>(pk.n_units) * cfg.num_regions * cfg.num_regions, ac, st));
     } else {

@@ -195,11 +195,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) cmax = fmaxf(cmax, x[j]);
                     const float nmax = fmaxf(run_max, cmax);
-                    float s = run_sum * expf(run_max - nmax);  // exp(-inf) = 0 on the first chunk
+                    constexpr float kLog2e = 1.4426950408889634f;
+                    const float nm2 = nmax * kLog2e;
+                    float s = run_sum * fast_ex2((run_max - nmax) * kLog2e);  // 2^-inf = 0 on the first chunk
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) {
-                            s += expf(x[j] - nmax);
+                            s += fast_ex2(fmaf(x[j], kLog2e, -nm2));           // one FFMA + one SFU op per logit
                             if (col0 + j == label) lab_logit = x[j];
                         }
                     run_max = nmax;

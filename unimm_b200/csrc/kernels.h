@@ -105,6 +105,9 @@ struct AttnJobsArgs {
     int lp_kind;
 };
 int attention_jobs(const AttnJobsArgs& a, bool fp32, cudaStream_t stream);
+// jobs that all have win = 1 (candidate rows over context + own rows), D = 64, 16-bit: persistent double-buffered kernel.
+// halo = (longest candidate's row count - 1): rows of a candidate lie within +-halo of any of its rows.
+int attention_candidates(const AttnJobsArgs& a, int halo, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ heads.cu
 // packed layout: text pooled row = xt[cls_row[c]], image pooled row = xv[unit[c] * R]

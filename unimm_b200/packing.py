@@ -79,6 +79,7 @@ class PackedBatch:
         for k in self.INT_FIELDS + self.FLOAT_FIELDS:
             setattr(s, "d_" + k, C.c_void_p(getattr(self, k).data_ptr()))
         s.n_jobs_text_self, s.max_q_text_self = self.jobs_text_self.shape[0], self.max_q_text_self
+        s.n_jobs_text_ctx, s.cand_halo = self.n_jobs_text_ctx, self.cand_halo
         s.n_jobs_t2i, s.max_q_t2i = self.jobs_t2i.shape[0], self.max_q_t2i
         s.n_jobs_i2t, s.n_jobs_img_self = self.jobs_i2t.shape[0], self.jobs_img_self.shape[0]
         s.kv_cap_text, s.win_cap = self.kv_cap_text, self.win_cap
@@ -126,7 +127,7 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
     lm_rows, lm_labels, cand_lm_off = [], [], [0]
     cls_row = np.zeros(C_tot, np.int32)
     img_row = np.zeros(C_tot, np.int32)
-    jobs_ts, jobs_t2i, jobs_i2t, jobs_img = [], [], [], []
+    jobs_ctx, jobs_cand, jobs_t2i, jobs_i2t, jobs_img = [], [], [], [], []
     pairs_ts = pairs_i2t = 0
     ci = 0
     max_cand_q = 1
@@ -165,8 +166,8 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
         cand_lm_off.extend((cand_lm_off[-1] + np.cumsum(last)).tolist())
         cls_row[ci:ci + n] = cs
         img_row[ci:ci + n] = ui * R
-        jobs_ts.append((s0, ctx - 1, s0, ctx - 1, 0, -1, 0, 0))
-        jobs_ts.append((int(cs[0]), rows_u, s0, ctx - 1, 1, -1, 0, 0))
+        jobs_ctx.append((s0, ctx - 1, s0, ctx - 1, 0, -1, 0, 0))
+        jobs_cand.append((int(cs[0]), rows_u, s0, ctx - 1, 1, -1, 0, 0))
         jobs_t2i.append((s0, ctx - 1, ui * R, R, 0, ui, 0, 0))
         jobs_t2i.append((int(cs[0]), rows_u, ui * R, R, 0, ui, 0, 0))
         jobs_i2t.append((ui * R, R, s0, ctx - 1, 0, -1, 0, 0))
@@ -182,7 +183,7 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
     return PackedBatch(
         n_units=U, n_cands=C_tot, n_text_rows=M,
         input_ids=t(ids, np.int32), token_type_ids=t(segs, np.int32), position_ids=t(pos, np.int32), row_iv=t(row_iv, np.int32),
-        jobs_text_self=t(np.asarray(jobs_ts), np.int32), jobs_t2i=t(np.asarray(jobs_t2i), np.int32),
+        jobs_text_self=t(np.asarray(jobs_ctx + jobs_cand), np.int32), n_jobs_text_ctx=len(jobs_ctx), cand_halo=max_rows_per_cand - 1, jobs_t2i=t(np.asarray(jobs_t2i), np.int32),
         jobs_i2t=t(np.asarray(jobs_i2t), np.int32), jobs_img_self=t(np.asarray(jobs_img), np.int32),
         lm_rows=t(np.concatenate(lm_rows), np.int32), lm_labels=t(lm_labels, np.int32),
         cand_lm_off=t(np.asarray(cand_lm_off), np.int32), cand_cls_row=t(cls_row, np.int32), cand_img_row=t(img_row, np.int32),
