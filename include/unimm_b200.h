@@ -177,6 +177,13 @@ int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_s
 int unimm_profile_begin(unimm_engine_t* e);
 int unimm_profile_end(unimm_engine_t* e, double* ms, double* work, int64_t* launches, int ncat);
 
+/* Ranking metrics of the reference's utils/visdial_metrics.py on the device: d_scores [rows, n_opt]; optional d_gt_index
+ * [rows] (sparse metrics), d_relevance [rows, n_opt] (NDCG), d_ranks [rows, n_opt] out (1-based, stable on ties).
+ * d_sums: 9 doubles, zeroed by the caller, accumulated: rows, #rank<=1, #rank<=5, #rank<=10, sum rank, sum 1/rank,
+ * sum ndcg, #ndcg rows, #tied pairs. */
+int unimm_rank_metrics(const float* d_scores, int rows, int n_opt, const int32_t* d_gt_index, const float* d_relevance,
+                       int32_t* d_ranks, double* d_sums, void* stream);
+
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t unimm_launch_count(void);
 void unimm_reset_launch_count(void);

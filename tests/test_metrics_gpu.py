@@ -1,0 +1,45 @@
+"""GPU: ranking metrics kernel against the oracle restatement of the reference's visdial_metrics classes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from oracle import visdial_metrics as om  # noqa: E402
+from unimm_b200.metrics import rank_metrics  # noqa: E402
+
+
+def test_rank_metrics_match_oracle_on_random_scores():
+    g = torch.Generator().manual_seed(0)
+    scores = torch.randn(6, 10, 100, generator=g)
+    gt = torch.randint(0, 100, (6, 10), generator=g)
+    rel_rows = torch.tensor(np.random.RandomState(1).choice([0, 0, 0, 0.2, 0.5, 1.0], size=(6, 100)).astype(np.float32))
+    rel_rows[:, 0] = 1.0
+    out = rank_metrics(scores.cuda(), gt.cuda())
+    want = om.sparse_metrics(scores, gt)
+    for k, v in want.items():
+        assert out[k] == pytest.approx(v, abs=1e-6), k
+    assert out["ties"] == 0
+    assert torch.equal(out["ranks"].cpu().long(), om.scores_to_ranks(scores))
+    round_scores = scores[:, 3, :]
+    nd = rank_metrics(round_scores.cuda(), relevance=rel_rows.cuda(), return_ranks=False)
+    assert nd["ndcg"] == pytest.approx(om.ndcg(round_scores, rel_rows), abs=1e-6)
+
+
+def test_rank_metrics_on_golden_config1():
+    g, _ = load_golden("gen100_default")
+    score = torch.from_numpy(g["seq_score"]).view(1, 100).cuda()
+    out = rank_metrics(score, torch.zeros(1, dtype=torch.long).cuda(), torch.from_numpy(g["relevance"]).cuda())
+    assert np.array_equal(out["ranks"].view(100).cpu().numpy(), g["ranks"])
+    for k, v in zip(g["metric_names"], g["metric_values"]):
+        assert out[str(k)] == pytest.approx(v, abs=1e-6), k
+
+
+def test_ties_are_reported_and_ranked_stably():
+    s = torch.tensor([[0.5, 0.7, 0.5, 0.1]]).cuda()
+    out = rank_metrics(s, torch.tensor([2]).cuda())
+    assert out["ties"] == 1 and out["ranks"].view(-1).tolist() == [2, 1, 3, 4]

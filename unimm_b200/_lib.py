@@ -84,6 +84,7 @@ SYMBOLS = {
     "unimm_score_packed_host": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _P, _P, _P]),
     "unimm_verify_masks": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "unimm_score_host": (C.c_int, [_P, C.POINTER(HostBatch), _P, _P, _P]),
+    "unimm_rank_metrics": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "unimm_profile_begin": (C.c_int, [_P]),
     "unimm_profile_end": (C.c_int, [_P, _P, _P, _P, _I]),
     "unimm_launch_count": (C.c_int64, []),

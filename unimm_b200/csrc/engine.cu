@@ -913,6 +913,12 @@ int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_s
     return 0;
 }
 
+int unimm_rank_metrics(const float* d_scores, int rows, int n_opt, const int32_t* d_gt_index, const float* d_relevance,
+                       int32_t* d_ranks, double* d_sums, void* stream) {
+    UNIMM_CHECK(d_scores != nullptr, "null scores");
+    return rank_metrics(d_scores, rows, n_opt, d_gt_index, d_relevance, d_ranks, d_sums, static_cast<cudaStream_t>(stream));
+}
+
 int unimm_profile_begin(unimm_engine_t* e) {
     UNIMM_CHECK(e != nullptr, "null engine");
     e->profiling = true;

@@ -140,6 +140,9 @@ int nsp_ce_loss(const float* nsp_logits, const int64_t* labels, int B, const flo
 // masked image KL (ref :1569-1574)
 int image_kl_loss(const float* v_logits, int ld, const float* target, const int64_t* image_label, int rows, int C, float* out,
                   cudaStream_t stream);
+// GPU ranking metrics (metrics.cu); sums is a zero-initialised double[9]
+int rank_metrics(const float* scores, int rows, int n_opt, const int* gt_index, const float* relevance, int* ranks, double* sums,
+                 cudaStream_t stream);
 // regenerate the dense masks from descriptors and compare with the caller's dense tensors (boundary check)
 int verify_masks(const SeqDesc* desc, int B, int S, int R, const void* txt_mask, int txt_elem_bytes, int txt_is_2d,
                  const int64_t* co_mask, int* mismatch_flag, cudaStream_t stream);
