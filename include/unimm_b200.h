@@ -193,6 +193,15 @@ void unimm_reset_launch_count(void);
 int unimm_k_gemm_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias,
                     const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp,
                     int tile_n, int max_ctas, int lp_kind, void* stream);
+/* LayerNorm(A W^T + bias + residual) * gamma + beta in one cluster-fused tcgen05 kernel (N = 768 or 1024; replaces the
+ * reference's dense -> "+ input_tensor" -> LayerNorm tails, models/vilbert_dialog.py:422-426, :465-469, :745-752).
+ * The residual is either fp32 (d_residual, may alias d_out_f32) or, when d_residual_lp is non-NULL, the 16-bit activation
+ * copy itself (may alias d_out_lp), which the kernel adds on the tensor core.  d_W_lp must be the row-permuted copy made by unimm_k_permute_w_ln (the engine
+ * makes it once at weight-load time). */
+int unimm_k_permute_w_ln(const void* d_W_lp, void* d_Wp_lp, int N, int K, void* stream);
+int unimm_k_gemm_ln_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias,
+                       const float* d_residual, int ldr, const void* d_residual_lp, int ldr_lp, const float* d_gamma,
+                       const float* d_beta, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp, int lp_kind, void* stream);
 int unimm_k_gemm_f32(const float* d_A, int lda, const float* d_W, int ldw, int M, int N, int K, const float* d_bias,
                      const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* stream);
 int unimm_k_lm_head_lp(const void* d_H_lp, int ldh, const void* d_E_lp, int lde, int rows, int V, int K,

@@ -11,7 +11,7 @@ from unimm_b200._lib import check, lib, ptr  # noqa: E402
 
 dev = torch.device("cuda", 0)
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 64000
-MODES = len(sys.argv) > 2      # also time the epilogue ablations: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue
+MODES = len(sys.argv) > 2 and sys.argv[2] == "modes"     # also time the epilogue ablations: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue
 st = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -49,9 +49,38 @@ for name, N, K, act, res, lp_out in SHAPES:
     fl = 2.0 * m * N * K
     extra = ""
     if MODES:
-        for mode in (1, 2, 3):
+        for mode in (1, 2, 3, 4, 7):
             fm = lambda: check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(W), K, m, N, K, ptr(bias), ptr(R), N, act, ptr(o32), N, ptr(o16), N,
                                                     1000 * mode, 0, 1, st()))
             extra += f" | mode{mode} {fl/timeit(fm)/1e9:6.0f}"
     print(f"{name:12s} M={m:6d} N={N:5d} K={K:5d} act={act} res={int(res)}: ours {t*1e3:8.1f} us {fl/t/1e9:7.1f} TFLOP/s | "
           f"cuBLAS (no epilogue) {t_ref*1e3:8.1f} us {fl/t_ref/1e9:7.1f} TFLOP/s{extra}", flush=True)
+
+
+# LayerNorm-fused cluster GEMM against the unfused pair (GEMM with fp32 residual epilogue + LayerNorm kernel)
+print("# fused = one cluster kernel; unfused = umma GEMM (+residual, fp32 out) followed by layernorm_rows", flush=True)
+for name, N, K in (("out_proj+ln", 768, 768), ("ffn2+ln", 768, 3072), ("bi_dense2+ln", 768, 1024), ("img_out+ln", 1024, 1024)):
+    for m in (M, 98176):
+        A = (torch.randn(m, K, device=dev) * 0.5).half()
+        W = (torch.randn(N, K, device=dev) * 0.05).half()
+        bias, gamma, beta = torch.randn(N, device=dev), torch.rand(N, device=dev) + 0.5, torch.randn(N, device=dev)
+        X = torch.randn(m, N, device=dev)
+        pre = torch.empty(m, N, device=dev)
+        o16 = torch.empty(m, N, device=dev, dtype=torch.float16)
+        Wp = torch.empty_like(W)
+        check(lib.unimm_k_permute_w_ln(ptr(W), ptr(Wp), N, K, st()))
+        X16 = X.half()
+        fused = lambda: check(lib.unimm_k_gemm_ln_lp(ptr(A), K, ptr(Wp), K, m, N, K, ptr(bias), ptr(X), N, None, 0, ptr(gamma), ptr(beta), ptr(X), N,
+                                                     ptr(o16), N, 1, st()))
+        fused16 = lambda: check(lib.unimm_k_gemm_ln_lp(ptr(A), K, ptr(Wp), K, m, N, K, ptr(bias), None, 0, ptr(X16), N, ptr(gamma), ptr(beta), None, 0,
+                                                       ptr(X16), N, 1, st()))
+
+        def unfused():
+            check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(W), K, m, N, K, ptr(bias), ptr(X), N, 0, ptr(pre), N, None, 0, 0, 0, 1, st()))
+            check(lib.unimm_k_layernorm(ptr(pre), N, m, N, ptr(gamma), ptr(beta), ptr(X), ptr(o16), 1, st()))
+        tf, t16, tu = timeit(fused), timeit(fused16), timeit(unfused)
+        fl = 2.0 * m * N * K
+        hbm = m * N * (4 + 4 + 2) + m * K * 2
+        hbm16 = m * N * (2 + 2) + m * K * 2
+        print(f"{name:13s} M={m:6d} N={N:5d} K={K:5d}: fused/fp32-residual {tf*1e3:7.1f} us {fl/tf/1e9:6.1f} TFLOP/s {hbm/tf/1e6:5.0f} GB/s | "
+              f"fused/16-bit-residual {t16*1e3:7.1f} us {fl/t16/1e9:6.1f} TFLOP/s {hbm16/t16/1e6:5.0f} GB/s | unfused {tu*1e3:7.1f} us", flush=True)

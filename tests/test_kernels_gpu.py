@@ -99,6 +99,50 @@ def test_gemm_umma_persistent_few_ctas():
 
 
 @pytest.mark.parametrize("lp", ["bf16", "fp16"])
+@pytest.mark.parametrize("res16", [False, True])
+@pytest.mark.parametrize("M,N,K,inplace", [
+    (128, 768, 64, False),         # one row block, one k-block, 3-CTA cluster
+    (128, 1024, 128, False),       # 4-CTA cluster
+    (300, 768, 768, True),         # out-proj shape, ragged M, residual stream updated in place
+    (37 * 7, 1024, 1024, True),    # image stream
+    (256, 768, 3072, False),       # FFN-2: long K
+    (128 * 150 + 5, 768, 768, True),   # more row blocks than clusters: accumulator / statistics-slot phases wrap many times
+    (128 * 101, 1024, 1024, False),
+])
+def test_gemm_ln_cluster(M, N, K, inplace, res16, lp):
+    """LayerNorm(A W^T + b + R) * gamma + beta from the cluster-fused kernel vs float64 torch (reference :422-426).
+    res16: the residual is a 16-bit tensor added on the tensor core (identity k-blocks) instead of an fp32 one."""
+    dt, kind = LP[lp]
+    A = rnd(M, K, seed=1).to(dt)
+    W = rnd(N, K, scale=0.05, seed=2).to(dt)
+    b = rnd(N, seed=3)
+    R = rnd(M, N, seed=4) + 0.3          # non-zero row mean
+    R[:, 5] += 8.0                       # an outlier feature column, as trained BERT residual streams have
+    if res16:
+        R = R.to(dt).float()             # exactly representable, so the reference sees the same residual
+    gamma, beta = 1.0 + 0.1 * rnd(N, seed=5), 0.1 * rnd(N, seed=6)
+    ref = torch.nn.functional.layer_norm(A.double() @ W.double().t() + b.double() + R.double(), (N,), gamma.double(), beta.double(),
+                                         eps=1e-12)
+    Wp = torch.empty_like(W)     # rows in the order the fused kernel's TMEM fragments want (done once at weight-load time)
+    check(lib.unimm_k_permute_w_ln(ptr(W), ptr(Wp), N, K, stream()))
+    o32 = R.clone() if (inplace and not res16) else torch.zeros(M, N, device=DEV)
+    o16 = R.to(dt) if (inplace and res16) else torch.zeros(M, N, device=DEV, dtype=dt)
+    R16 = o16 if inplace else R.to(dt)
+    if res16:
+        check(lib.unimm_k_gemm_ln_lp(ptr(A), K, ptr(Wp), K, M, N, K, ptr(b), None, 0, ptr(R16), N, ptr(gamma), ptr(beta),
+                                     ptr(o32), N, ptr(o16), N, kind, stream()))
+    else:
+        check(lib.unimm_k_gemm_ln_lp(ptr(A), K, ptr(Wp), K, M, N, K, ptr(b), ptr(o32) if inplace else ptr(R), N, None, 0, ptr(gamma),
+                                     ptr(beta), ptr(o32), N, ptr(o16), N, kind, stream()))
+    torch.cuda.synchronize()
+    err = (o32.double() - ref).abs().max().item()
+    err16 = (o16.double() - ref).abs().max().item()
+    print(f"gemm_ln[{lp}] {M}x{N}x{K} inplace={inplace} res16={res16}: fp32-out err {err:.3e}, 16-bit-out err {err16:.3e}")
+    assert err < 2e-3 * max(1.0, math.sqrt(K / 768))
+    assert err16 < 0.05
+
+
+@pytest.mark.parametrize("lp", ["bf16", "fp16"])
 def test_lm_head_lse(lp):
     dt, kind = LP[lp]
     rows, V, K = 200, 30522, 768

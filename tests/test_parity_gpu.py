@@ -21,7 +21,7 @@ from unimm_b200.visual_dialog_encoder import VisualDialogEncoder  # noqa: E402
 # (measured max 2.07e-2 over the 100 candidates of config 1, 1.8e-2 over 8), so it is checked against 3e-2 and its
 # measured error is printed — see DESIGN.md "Precision modes".
 TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 3e-2}
-TIGHT = {"fp32": 1e-4, "fp16": 6e-3, "bf16": 3e-2}     # what we actually expect to hold
+TIGHT = {"fp32": 1e-4, "fp16": 1e-2, "bf16": 3e-2}     # what we actually expect to hold (fp16: 16-bit residual stream, measured 6e-3)
 _ENGINES = {}
 
 

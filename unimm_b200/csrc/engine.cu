@@ -4,6 +4,7 @@
 // launches on the caller's stream.  C ABI in include/unimm_b200.h.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -34,6 +35,7 @@ struct Linear {
     int N = 0, K = 0;
     const float* w32 = nullptr;  // [N,K] fp32 (fp32 mode, and small heads)
     const bf16* wlp = nullptr;   // [N,K] bf16 (bf16 mode)
+    const bf16* wlp_ln = nullptr;  // [N,K] rows permuted for the LayerNorm-fused cluster GEMM (gemm_umma_ln.cu)
     const float* b = nullptr;    // [N]
 };
 struct LayerNormP {
@@ -143,12 +145,20 @@ struct unimm_engine {
     }
     int make_linear(const std::vector<std::string>& names, int N_each, int K, Linear* L, bool keep_f32_only = false);
     int make_ln(const std::string& name, int H, LayerNormP* ln);
+    int make_ln_weight(Linear* L);
     int finalize();
     int alloc_workspace();
 
     // y = act(x W^T + b) (+ residual); x/y selected by mode
     int linear(const ActBuf& x, int M, const Linear& L, int act, const float* residual, int ldr, float* out_f32, int ldo_f32,
                void* out_lp, int ldo_lp, cudaStream_t st);
+    // out = LayerNorm(x W^T + b + residual): one cluster-fused kernel in the 16-bit modes, GEMM + LayerNorm kernel otherwise
+    int linear_ln(const ActBuf& x, int M, const Linear& L, const float* residual, int ldr, const LayerNormP& ln, float* pre,
+                  ActBuf& out, cudaStream_t st);
+    bool fuse_ln = true;
+    // fp16 mode keeps the residual stream in 16 bits between sub-layers (the fused kernel adds it on the tensor core);
+    // bf16's 8-bit mantissa cannot afford that, it keeps the fp32 master.  xt.f / xv.f are refreshed after the encoder.
+    bool res16 = false;
     int attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
                   int D, int Sq, int Skv, int mask_kind, const SeqDesc* desc, const float* key_mask, cudaStream_t st);
     // which attention a layer runs: dense [B,S]/[B,R] rows with descriptor masks, or jobs over packed rows
@@ -213,6 +223,16 @@ int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each,
         UNIMM_TRY(cast_f32_to_lp(w, h, static_cast<size_t>(L->N) * K, lp_kind(), 0));
         L->wlp = h;
     }
+    return 0;
+}
+
+// second 16-bit copy of a weight whose output feeds a residual + LayerNorm, in the row order the fused kernel wants
+int unimm_engine::make_ln_weight(Linear* L) {
+    if (!lp() || !fuse_ln || L->wlp == nullptr || (L->N != 768 && L->N != 1024) || L->K % 64 != 0) return 0;
+    bf16* h = nullptr;
+    UNIMM_TRY(dalloc(&h, static_cast<size_t>(L->N) * L->K));
+    UNIMM_TRY(permute_weight_rows_ln(L->wlp, h, L->N, L->K, 0));
+    L->wlp_ln = h;
     return 0;
 }
 
@@ -301,6 +321,13 @@ int unimm_engine::finalize() {
     UNIMM_TRY(make_linear({"cls.imagePredictions.transform.dense"}, Hv, Hv, &img_transform));
     UNIMM_TRY(make_ln("cls.imagePredictions.transform.LayerNorm", Hv, &img_ln));
     UNIMM_TRY(make_linear({"cls.imagePredictions.decoder"}, c.v_target_size, Hv, &img_decoder));
+    UNIMM_TRY(make_ln_weight(&img_emb));
+    for (auto& L : t_layers) { UNIMM_TRY(make_ln_weight(&L.out)); UNIMM_TRY(make_ln_weight(&L.ffn2)); }
+    for (auto& L : v_layers) { UNIMM_TRY(make_ln_weight(&L.out)); UNIMM_TRY(make_ln_weight(&L.ffn2)); }
+    for (auto& L : c_layers) {
+        UNIMM_TRY(make_ln_weight(&L.dense1)); UNIMM_TRY(make_ln_weight(&L.dense2));
+        UNIMM_TRY(make_ln_weight(&L.v_ffn2)); UNIMM_TRY(make_ln_weight(&L.t_ffn2));
+    }
     UNIMM_CUDA_CHECK(cudaDeviceSynchronize());
     UNIMM_TRY(alloc_workspace());
     finalized = true;
@@ -368,6 +395,27 @@ int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const
     return gemm_simt_f32(x.f, x.ld, L.w32, L.K, M, L.N, L.K, ep, st);
 }
 
+int unimm_engine::linear_ln(const ActBuf& x, int M, const Linear& L, const float* residual, int ldr, const LayerNormP& ln, float* pre,
+                            ActBuf& out, cudaStream_t st) {
+    if (lp() && fuse_ln) {
+        GemmLnEpilogue ep;
+        ep.bias = L.b; ep.residual = residual; ep.ldr = ldr; ep.gamma = ln.g; ep.beta = ln.b;
+        ep.out_f32 = out.f; ep.ldo_f32 = out.ld; ep.out_lp = out.h; ep.ldo_lp = out.ld; ep.lp_kind = lp_kind();
+        if (res16 && residual == out.f && ldr == out.ld) {   // the stream's own previous value: use (and update) its 16-bit copy only
+            ep.residual = nullptr; ep.residual_lp = out.h; ep.ldr_lp = out.ld; ep.out_f32 = nullptr;
+        }
+        if (L.wlp_ln != nullptr && gemm_umma_ln_supported(L.N, L.K, ep)) {
+            UNIMM_CHECK(x.h != nullptr, "16-bit operand missing");
+            Prof prof(this, CAT_GEMM, 2.0 * M * L.N * L.K, st);
+            return gemm_umma_ln(x.h, x.ld, L.wlp_ln, L.K, M, L.N, L.K, ep, st);
+        }
+    }
+    UNIMM_CHECK(!(lp() && fuse_ln && res16), "16-bit residual stream needs the LayerNorm-fused GEMM (N = 768 or 1024, K % 64 == 0)");
+    UNIMM_TRY(linear(x, M, L, ACT_NONE, residual, ldr, pre, L.N, nullptr, 0, st));
+    Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * M * L.N, st);
+    return layernorm_rows(pre, L.N, M, L.N, ln.g, ln.b, out.f, out.h, lp_kind(), st);
+}
+
 int unimm_engine::attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
                             int heads, int D, int Sq, int Skv, int mask_kind, const SeqDesc* desc, const float* key_mask,
                             cudaStream_t st) {
@@ -426,14 +474,12 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
     }
     ActBuf c;
     c.f = lp() ? nullptr : static_cast<float*>(ctx); c.h = lp() ? static_cast<bf16*>(ctx) : nullptr; c.ld = H;
-    UNIMM_TRY(linear(c, M, L.out, ACT_NONE, x.f, H, pre, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (M) * (H), st); UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln1.g, L.ln1.b, x.f, x.h, lp_kind(), st)); }
+    UNIMM_TRY(linear_ln(c, M, L.out, x.f, H, L.ln1, pre, x, st));
     const int I = L.ffn1.N;
     UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st));
     ActBuf f;
     f.f = lp() ? nullptr : static_cast<float*>(ffn); f.h = lp() ? static_cast<bf16*>(ffn) : nullptr; f.ld = I;
-    UNIMM_TRY(linear(f, M, L.ffn2, ACT_NONE, x.f, H, pre, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (M) * (H), st); UNIMM_TRY(layernorm_rows(pre, H, M, H, L.ln2.g, L.ln2.b, x.f, x.h, lp_kind(), st)); }
+    UNIMM_TRY(linear_ln(f, M, L.ffn2, x.f, H, L.ln2, pre, x, st));
     return 0;
 }
 
@@ -465,22 +511,18 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
     cv.f = lp() ? nullptr : static_cast<float*>(ctx_v); cv.h = lp() ? static_cast<bf16*>(ctx_v) : nullptr; cv.ld = Hb;
     ct.f = lp() ? nullptr : static_cast<float*>(ctx_t); ct.h = lp() ? static_cast<bf16*>(ctx_t) : nullptr; ct.ld = Hb;
     // BertBiOutput (:744-754): image rows take the image-query context through dense1, text rows the other through dense2
-    UNIMM_TRY(linear(cv, Mv, L.dense1, ACT_NONE, xv.f, Hv, pre_v, Hv, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.ln1.g, L.ln1.b, xv.f, xv.h, lp_kind(), st)); }
-    UNIMM_TRY(linear(ct, Mt, L.dense2, ACT_NONE, xt.f, H, pre_t, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mt) * (H), st); UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.ln2.g, L.ln2.b, xt.f, xt.h, lp_kind(), st)); }
+    UNIMM_TRY(linear_ln(cv, Mv, L.dense1, xv.f, Hv, L.ln1, pre_v, xv, st));
+    UNIMM_TRY(linear_ln(ct, Mt, L.dense2, xt.f, H, L.ln2, pre_t, xt, st));
     // image FFN, text FFN (:777-781)
     const int Iv = L.v_ffn1.N, I = L.t_ffn1.N;
     UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st));
     ActBuf fv;
     fv.f = lp() ? nullptr : static_cast<float*>(ffn_v); fv.h = lp() ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
-    UNIMM_TRY(linear(fv, Mv, L.v_ffn2, ACT_NONE, xv.f, Hv, pre_v, Hv, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, L.v_ln.g, L.v_ln.b, xv.f, xv.h, lp_kind(), st)); }
+    UNIMM_TRY(linear_ln(fv, Mv, L.v_ffn2, xv.f, Hv, L.v_ln, pre_v, xv, st));
     UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st));
     ActBuf ft;
     ft.f = lp() ? nullptr : static_cast<float*>(ffn_t); ft.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; ft.ld = I;
-    UNIMM_TRY(linear(ft, Mt, L.t_ffn2, ACT_NONE, xt.f, H, pre_t, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mt) * (H), st); UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, L.t_ln.g, L.t_ln.b, xt.f, xt.h, lp_kind(), st)); }
+    UNIMM_TRY(linear_ln(ft, Mt, L.t_ffn2, xt.f, H, L.t_ln, pre_t, xt, st));
     return 0;
 }
 
@@ -504,8 +546,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     {
         ActBuf fa;
         fa.f = lp() ? nullptr : static_cast<float*>(feat_a); fa.h = lp() ? static_cast<bf16*>(feat_a) : nullptr; fa.ld = c.v_feature_size;
-        UNIMM_TRY(linear(fa, Mv, img_emb, ACT_NONE, pre_v, Hv, pre_v, Hv, nullptr, 0, st));
-        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, vemb_ln.g, vemb_ln.b, xv.f, xv.h, lp_kind(), st)); }
+        UNIMM_TRY(linear_ln(fa, Mv, img_emb, pre_v, Hv, vemb_ln, pre_v, xv, st));
     }
     // key mask per sequence: image_mask[feat_index[b]] — expand once when an index is used
     const float* key_mask = in.d_image_mask;
@@ -587,6 +628,11 @@ int unimm_engine::run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st
     }
     for (int i = v_start; i < c.v_num_hidden_layers; ++i) UNIMM_TRY(run_v(i));
     for (int i = t_start; i < c.num_hidden_layers; ++i) UNIMM_TRY(run_t(i));
+    if (lp() && fuse_ln && res16) {   // the poolers and the optional sequence outputs read the fp32 view
+        Prof prof(this, CAT_ROWWISE, 6.0 * (static_cast<double>(Mt) * xt.ld + static_cast<double>(Mv) * xv.ld), st);
+        UNIMM_TRY(cast_lp_to_f32(xt.h, xt.f, static_cast<size_t>(Mt) * xt.ld, lp_kind(), st));
+        UNIMM_TRY(cast_lp_to_f32(xv.h, xv.f, static_cast<size_t>(Mv) * xv.ld, lp_kind(), st));
+    }
     return 0;
 }
 
@@ -641,8 +687,7 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
     {
         ActBuf fa;
         fa.f = lp() ? nullptr : static_cast<float*>(feat_a); fa.h = lp() ? static_cast<bf16*>(feat_a) : nullptr; fa.ld = c.v_feature_size;
-        UNIMM_TRY(linear(fa, Mv, img_emb, ACT_NONE, pre_v, Hv, pre_v, Hv, nullptr, 0, st));
-        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(pre_v, Hv, Mv, Hv, vemb_ln.g, vemb_ln.b, xv.f, xv.h, lp_kind(), st)); }
+        UNIMM_TRY(linear_ln(fa, Mv, img_emb, pre_v, Hv, vemb_ln, pre_v, xv, st));
     }
     AttnCtx ac;
     ac.pk = &in;
@@ -724,6 +769,9 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     e->device = device;
     e->prec = precision;
     e->Bmax = max_sequences;
+    if (const char* f = getenv("UNIMM_FUSE_LN")) e->fuse_ln = atoi(f) != 0;   // A/B switches for bench.py; defaults: on
+    e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
+    if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;
     return 0;
 }
@@ -954,6 +1002,21 @@ int unimm_k_gemm_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, i
     ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32; ep.out_bf16 = static_cast<bf16*>(d_out_lp); ep.ldo_bf16 = ldo_lp;
     return gemm_umma_bf16(static_cast<const bf16*>(d_A), lda, static_cast<const bf16*>(d_W), ldw, M, N, K, ep, tile_n, max_ctas,
                           static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_permute_w_ln(const void* d_W_lp, void* d_Wp_lp, int N, int K, void* stream) {
+    return permute_weight_rows_ln(static_cast<const bf16*>(d_W_lp), static_cast<bf16*>(d_Wp_lp), N, K, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_gemm_ln_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, int N, int K, const float* d_bias,
+                       const float* d_residual, int ldr, const void* d_residual_lp, int ldr_lp, const float* d_gamma, const float* d_beta,
+                       float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp, int lp_kind, void* stream) {
+    GemmLnEpilogue ep;
+    ep.bias = d_bias; ep.residual = d_residual; ep.ldr = ldr; ep.gamma = d_gamma; ep.beta = d_beta;
+    ep.residual_lp = static_cast<const bf16*>(d_residual_lp); ep.ldr_lp = ldr_lp;
+    ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32; ep.out_lp = static_cast<bf16*>(d_out_lp); ep.ldo_lp = ldo_lp; ep.lp_kind = lp_kind;
+    return gemm_umma_ln(static_cast<const bf16*>(d_A), lda, static_cast<const bf16*>(d_W), ldw, M, N, K, ep,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int unimm_k_gemm_f32(const float* d_A, int lda, const float* d_W, int ldw, int M, int N, int K, const float* d_bias,

@@ -23,6 +23,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "gemm_common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -34,9 +35,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;      // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;  // fixed for 16-bit inputs
 
-template <int BN>
+template <int BN, int ST = 0>
 struct GemmCfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kStages = ST > 0 ? ST : ((BN == 256) ? 4 : 6);
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -44,11 +45,11 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
-template <int BN, bool LSE>
+template <int BN, bool LSE, int ST = 0>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue ep) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, ST>;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte aligned bases
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -216,13 +217,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-                            x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
+                            f32x2::unpack(f32x2::add(f32x2::pack(x[j], x[j + 1]), f32x2::pack(b4.x, b4.y)), x[j], x[j + 1]);
+                            f32x2::unpack(f32x2::add(f32x2::pack(x[j + 2], x[j + 3]), f32x2::pack(b4.z, b4.w)), x[j + 2], x[j + 3]);
                         }
                     }
                     // activation hoisted out of the element loop: a branch-free body lets the 32 independent chains interleave
                     if (ep.act == ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
+                        for (int j = 0; j < 32; j += 2) gelu_fast2(x[j], x[j + 1]);
                     } else if (ep.act == ACT_RELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
@@ -286,7 +288,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (ep.act == ACT_GELU) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            y[i].x = gelu_fast(y[i].x); y[i].y = gelu_fast(y[i].y); y[i].z = gelu_fast(y[i].z); y[i].w = gelu_fast(y[i].w);
+                            gelu_fast2(y[i].x, y[i].y); gelu_fast2(y[i].z, y[i].w);
                         }
                     } else if (ep.act == ACT_RELU) {
 #pragma unroll
@@ -457,27 +459,32 @@ int num_sms() {
     return n;
 }
 
-template <int BN, bool LSE>
+template <int BN, bool LSE, int ST = 0>
 int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int max_ctas,
            cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, ST>;
     CUtensorMap tmA, tmB;
     UNIMM_TRY(make_map_bf16(A, M, K, lda, BM, &tmA));
     UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN, &tmB));
     static bool attr_set = false;
     if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN, LSE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int grid = tiles < num_sms() ? tiles : num_sms();
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    umma_gemm_kernel<BN, LSE><<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+    umma_gemm_kernel<BN, LSE, ST><<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
 
 }  // namespace
+
+int gemm_make_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+    return make_map_bf16(ptr, rows, cols, ld, box_rows, out);
+}
+int gemm_num_sms() { return num_sms(); }
 
 int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int tile_n,
                    int max_ctas, cudaStream_t stream) {
@@ -487,6 +494,11 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     if (lse) {
         UNIMM_CHECK(tile_n == 256, "LSE epilogue uses 256-wide vocabulary tiles");
         return launch<256, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+    }
+    if (tile_n == 256 && ep.debug_mode >= 4) {   // microbenchmark: 3-stage ring, epilogue mode = debug_mode - 4
+        GemmEpilogue e2 = ep;
+        e2.debug_mode -= 4;
+        return launch<256, false, 3>(A, lda, W, ldw, M, N, K, e2, max_ctas, stream);
     }
     if (tile_n == 256) return launch<256, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     UNIMM_CHECK(tile_n == 128, "umma gemm: tile_n must be 128 or 256");

@@ -34,6 +34,28 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
                    int max_ctas, cudaStream_t stream);
 int gemm_umma_lse_tiles(int N);
 
+// X = LayerNorm(A · W^T + bias + residual) * gamma + beta with the row statistics exchanged across a thread-block
+// cluster (gemm_umma_ln.cu).  N must be 768 or 1024; residual may alias out_f32, residual_lp may alias out_lp (in-place residual stream).
+struct GemmLnEpilogue {
+    const float* bias = nullptr;      // [N]
+    const float* residual = nullptr;  // [M, ldr] fp32 residual (precharged into the accumulator by the epilogue warps), or
+    int ldr = 0;
+    const bf16* residual_lp = nullptr;  // [M, ldr_lp] 16-bit residual (added by the tensor core as identity k-blocks); wins if set
+    int ldr_lp = 0;
+    const float* gamma = nullptr;     // [N]
+    const float* beta = nullptr;      // [N]
+    float* out_f32 = nullptr;         // [M, ldo_f32] fp32 master copy (optional)
+    int ldo_f32 = 0;
+    bf16* out_lp = nullptr;           // [M, ldo_lp] 16-bit GEMM-operand copy (optional)
+    int ldo_lp = 0;
+    int lp_kind = LP_BF16;
+};
+// W must be the row-permuted copy produced by permute_weight_rows_ln (see gemm_umma_ln.cu: the permutation makes each
+// thread's tcgen05.ld fragment 8 consecutive output columns).
+int permute_weight_rows_ln(const bf16* W, bf16* Wp, int N, int K, cudaStream_t stream);
+bool gemm_umma_ln_supported(int N, int K, const GemmLnEpilogue& ep);
+int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmLnEpilogue& ep, cudaStream_t stream);
+
 // Same contraction in fp32 on the CUDA cores (gemm_simt.cu) — the fp32 parity mode.
 int gemm_simt_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                   cudaStream_t stream);
@@ -60,6 +82,7 @@ int gather_features(const float* feat, const int* feat_index, int B, int R, int 
 int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int n, int H, float* dst_f32, bf16* dst_bf16,
                 cudaStream_t stream);
 int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream);
+int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStream_t stream);
 int gather_labels(const int64_t* labels, const int* rows, int n, int* out, cudaStream_t stream);
 int expand_key_mask(const float* mask, const int* index, int B, int R, float* out, cudaStream_t stream);
 

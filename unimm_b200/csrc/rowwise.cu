@@ -248,6 +248,34 @@ int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int
     return 0;
 }
 
+// 16-bit activation copy -> fp32 (refreshes the fp32 view of a residual stream that was kept in 16 bits)
+__global__ void widen_kernel(const uint2* __restrict__ src, float4* __restrict__ dst, size_t n4, int lp_kind) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint2 u = src[i];
+        float4 o;
+        if (lp_kind == LP_FP16) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            o = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)),
+                         b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            o = make_float4(a.x, a.y, b.x, b.y);
+        }
+        dst[i] = o;
+    }
+}
+
+int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStream_t stream) {
+    UNIMM_CHECK((n & 3) == 0, "cast: element count must be a multiple of 4");
+    const size_t n4 = n / 4;
+    int grid = static_cast<int>((n4 + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    widen_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint2*>(src), reinterpret_cast<float4*>(dst), n4, lp_kind);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
 int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream) {
     UNIMM_CHECK((n & 3) == 0, "cast: element count must be a multiple of 4");
     const size_t n4 = n / 4;
