@@ -199,6 +199,10 @@ int unimm_k_gemm_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, in
  * copy itself (may alias d_out_lp), which the kernel adds on the tensor core.  d_W_lp must be the row-permuted copy made by unimm_k_permute_w_ln (the engine
  * makes it once at weight-load time). */
 int unimm_k_permute_w_ln(const void* d_W_lp, void* d_Wp_lp, int N, int K, void* stream);
+/* mode 0 = the order above; mode 1 = the order of unimm_k_gemm_lp's 16-bit-output epilogue (pass lp_kind | 0x100 there to
+ * say that d_W_lp is such a copy: each thread's TMEM fragment is then 8 consecutive output columns, stored without a
+ * shared-memory transpose). */
+int unimm_k_permute_w(const void* d_W_lp, void* d_Wp_lp, int N, int K, int mode, void* stream);
 int unimm_k_gemm_ln_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias,
                        const float* d_residual, int ldr, const void* d_residual_lp, int ldr_lp, const float* d_gamma,
                        const float* d_beta, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp, int lp_kind, void* stream);

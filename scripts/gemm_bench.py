@@ -48,6 +48,13 @@ for name, N, K, act, res, lp_out in SHAPES:
     t_ref = timeit(lambda: torch.matmul(A, W.t()))
     fl = 2.0 * m * N * K
     extra = ""
+    if lp_out and not res:    # fragment-ordered weights: smem-free epilogue (+ the tanh-form GELU)
+        Wp = torch.empty_like(W)
+        check(lib.unimm_k_permute_w(ptr(W), ptr(Wp), N, K, 1, st()))
+        ff = lambda a=act: check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(Wp), K, m, N, K, ptr(bias), None, 0, a, None, 0, ptr(o16), N, 0, 0, 1 | 0x100, st()))
+        extra += f" | frag {fl/timeit(ff)/1e9:6.0f}"
+        if act == 1:
+            extra += f" | frag+tanh {fl/timeit(lambda: ff(3))/1e9:6.0f}"
     if MODES:
         for mode in (1, 2, 3, 4, 7):
             fm = lambda: check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(W), K, m, N, K, ptr(bias), ptr(R), N, act, ptr(o32), N, ptr(o16), N,

@@ -88,6 +88,33 @@ def test_gemm_umma(M, N, K, act, res, tile_n, lp):
     assert err16 < 0.05 * max(1.0, ref.abs().max().item() / 4)
 
 
+@pytest.mark.parametrize("lp", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,N,K,act,tile_n", [
+    (128, 256, 64, 0, 256), (300, 3072, 768, 1, 256), (300, 3072, 768, 3, 256), (512, 2304, 768, 0, 256), (37 * 5, 1024, 1024, 1, 128),
+    (130, 1600, 1024, 0, 128),          # N % 32 == 0 but not a multiple of the tile: ragged last tile
+    (40000, 768, 768, 0, 256),
+])
+def test_gemm_umma_fragment_epilogue(M, N, K, act, tile_n, lp):
+    """16-bit-output GEMM with fragment-ordered weights (no shared-memory transpose); act 3 = the 1-SFU tanh-form GELU."""
+    dt, kind = LP[lp]
+    A = rnd(M, K, seed=1).to(dt)
+    W = rnd(N, K, scale=0.05, seed=2).to(dt)
+    b = rnd(N, seed=3)
+    Wp = torch.empty_like(W)
+    check(lib.unimm_k_permute_w(ptr(W), ptr(Wp), N, K, 1, stream()))
+    o16 = torch.zeros(M, N, device=DEV, dtype=dt)
+    check(lib.unimm_k_gemm_lp(ptr(A), K, ptr(Wp), K, M, N, K, ptr(b), None, 0, act, None, 0, ptr(o16), N, tile_n, 0, kind | 0x100, stream()))
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    if act in (1, 3):
+        ref = gelu(ref)
+    err16 = (o16.double() - ref).abs().max().item()
+    print(f"gemm_umma_frag[{lp}] {M}x{N}x{K} act={act}: 16-bit-out err {err16:.3e}")
+    assert err16 < 0.05 * max(1.0, ref.abs().max().item() / 4)
+    if lp == "fp16":   # tighter: half an fp16 ulp of the largest value plus the GELU approximation
+        assert err16 < ref.abs().max().item() * (2 ** -11 + (3e-4 if act == 3 else 1e-5)) + 1e-5
+
+
 def test_gemm_umma_persistent_few_ctas():
     """Force 3 CTAs over 60 tiles so every CTA wraps the smem ring and both accumulators many times."""
     M, N, K = 128 * 10, 256 * 6, 320

@@ -91,6 +91,7 @@ SYMBOLS = {
     "unimm_reset_launch_count": (None, []),
     "unimm_k_gemm_lp": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "unimm_k_permute_w_ln": (C.c_int, [_P, _P, _I, _I, _P]),
+    "unimm_k_permute_w": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "unimm_k_gemm_ln_lp": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "unimm_k_gemm_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
     "unimm_k_lm_head_lp": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),

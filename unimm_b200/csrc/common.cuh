@@ -77,7 +77,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // exact (erf) GELU, reference models/vilbert_dialog.py:115-121
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_TANH = 3 /* fragment epilogue only: 1-SFU tanh form */ };
 
 // erf-GELU for the tensor-core epilogues, where the accurate erff (~30 issue slots per element) makes the
 // FFN-1 epilogue slower than its K=768 main loop.  GELU(x) = x * Phi(x) with Phi(x) = 1 / (1 + 2^(x * R(x^2))):
@@ -124,6 +124,40 @@ __device__ __forceinline__ void gelu_fast2(float& a, float& b) {
     float d0, d1;
     unpack(add(pack(fast_ex2(t0), fast_ex2(t1)), dup(1.0f)), d0, d1);
     unpack(mul(x, pack(fast_rcp(d0), fast_rcp(d1))), a, b);
+}
+// One-SFU-op variant: GELU(x) = h + h * tanh(x * T(x^2)), h = x / 2, T = the same fit rescaled (atanh(erf(x / sqrt 2)) / x).
+// tanh.approx.f32 has a relative error of up to 2^-11, i.e. |error| <= |x| * 2.4e-4 — up to half of the fp16 rounding
+// error of the stored result — in exchange for halving the SFU work of the FFN-1 epilogue (1 MUFU + 4 packed FP32 slots
+// per element).  Selected per GEMM with ACT_GELU_TANH (engine: UNIMM_GELU_TANH=1); the default keeps the 3.5e-6 ex2/rcp form.
+constexpr float kGeluT0 = 0.7978276471008666f, kGeluT1 = 0.03646983712264174f, kGeluT2 = -0.00012547381454677784f,
+                kGeluT3 = -3.0459227792119586e-05f, kGeluT4 = 1.1119725660024423e-06f;
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void gelu_tanh2(float& a, float& b) {
+    using namespace f32x2;
+    const uint64_t x = pack(a, b);
+    const uint64_t x2 = mul(x, x);
+    uint64_t r = fma(x2, dup(kGeluT4), dup(kGeluT3));
+    r = fma(r, x2, dup(kGeluT2));
+    r = fma(r, x2, dup(kGeluT1));
+    r = fma(r, x2, dup(kGeluT0));
+    float t0, t1;
+    unpack(mul(r, x), t0, t1);
+    const uint64_t h = mul(x, dup(0.5f));
+    unpack(fma(h, pack(fast_tanh(t0), fast_tanh(t1)), h), a, b);
+}
+#ifndef UNIMM_GELU_TANH
+#define UNIMM_GELU_TANH 0
+#endif
+__device__ __forceinline__ void gelu_epi2(float& a, float& b) {
+#if UNIMM_GELU_TANH
+    gelu_tanh2(a, b);
+#else
+    gelu_fast2(a, b);
+#endif
 }
 __device__ __forceinline__ float apply_act_fast(float x, int act) {
     if (act == ACT_GELU) return gelu_fast(x);

@@ -36,6 +36,7 @@ struct Linear {
     const float* w32 = nullptr;  // [N,K] fp32 (fp32 mode, and small heads)
     const bf16* wlp = nullptr;   // [N,K] bf16 (bf16 mode)
     const bf16* wlp_ln = nullptr;  // [N,K] rows permuted for the LayerNorm-fused cluster GEMM (gemm_umma_ln.cu)
+    const bf16* wlp_p16 = nullptr; // [N,K] rows permuted for the smem-free 16-bit-output epilogue (gemm_umma.cu)
     const float* b = nullptr;    // [N]
 };
 struct LayerNormP {
@@ -156,6 +157,8 @@ struct unimm_engine {
     int linear_ln(const ActBuf& x, int M, const Linear& L, const float* residual, int ldr, const LayerNormP& ln, float* pre,
                   ActBuf& out, cudaStream_t st);
     bool fuse_ln = true;
+    bool gelu_tanh = false;      // UNIMM_GELU_TANH=1: 1-SFU tanh-form GELU in the FFN-1 epilogue (|err| <= |x| * 2.4e-4)
+    bool frag_epilogue = true;   // QKV / FFN-1 GEMMs read fragment-ordered weight copies (UNIMM_FRAG_EPILOGUE=0 disables)
     // fp16 mode keeps the residual stream in 16 bits between sub-layers (the fused kernel adds it on the tensor core);
     // bf16's 8-bit mantissa cannot afford that, it keeps the fp32 master.  xt.f / xv.f are refreshed after the encoder.
     bool res16 = false;
@@ -222,6 +225,12 @@ int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each,
         UNIMM_TRY(dalloc(&h, static_cast<size_t>(L->N) * K));
         UNIMM_TRY(cast_f32_to_lp(w, h, static_cast<size_t>(L->N) * K, lp_kind(), 0));
         L->wlp = h;
+        if (frag_epilogue && L->N % 32 == 0 && K % 8 == 0) {
+            bf16* hp = nullptr;
+            UNIMM_TRY(dalloc(&hp, static_cast<size_t>(L->N) * K));
+            UNIMM_TRY(permute_weight_rows(h, hp, L->N, K, 1, 0));
+            L->wlp_p16 = hp;
+        }
     }
     return 0;
 }
@@ -386,6 +395,11 @@ int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const
         ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
         ep.out_bf16 = static_cast<bf16*>(out_lp); ep.ldo_bf16 = ldo_lp;
         UNIMM_CHECK(x.h != nullptr && L.wlp != nullptr, "bf16 operand missing");
+        if (L.wlp_p16 != nullptr && out_f32 == nullptr && residual == nullptr && out_lp != nullptr) {
+            ep.w_perm16 = true;
+            if (act == ACT_GELU && gelu_tanh) ep.act = ACT_GELU_TANH;
+            return gemm_umma_bf16(x.h, x.ld, L.wlp_p16, L.K, M, L.N, L.K, ep, 0, 0, st);
+        }
         return gemm_umma_bf16(x.h, x.ld, L.wlp, L.K, M, L.N, L.K, ep, 0, 0, st);
     }
     // fp32 mode: the "low precision" output slot is an fp32 tensor as well
@@ -770,6 +784,8 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     e->prec = precision;
     e->Bmax = max_sequences;
     if (const char* f = getenv("UNIMM_FUSE_LN")) e->fuse_ln = atoi(f) != 0;   // A/B switches for bench.py; defaults: on
+    if (const char* f = getenv("UNIMM_FRAG_EPILOGUE")) e->frag_epilogue = atoi(f) != 0;
+    if (const char* f = getenv("UNIMM_GELU_TANH")) e->gelu_tanh = atoi(f) != 0;
     e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;
@@ -995,6 +1011,8 @@ int unimm_k_gemm_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, i
                     const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp,
                     int tile_n, int max_ctas, int lp_kind, void* stream) {
     GemmEpilogue ep;
+    ep.w_perm16 = (lp_kind & 0x100) != 0;
+    lp_kind &= 0xff;
     ep.lp_kind = lp_kind;
     ep.debug_mode = tile_n / 1000;   // microbenchmark hook (scripts/gemm_bench.py): tile_n = 1000*mode + tile
     tile_n %= 1000;
@@ -1006,6 +1024,9 @@ int unimm_k_gemm_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, i
 
 int unimm_k_permute_w_ln(const void* d_W_lp, void* d_Wp_lp, int N, int K, void* stream) {
     return permute_weight_rows_ln(static_cast<const bf16*>(d_W_lp), static_cast<bf16*>(d_Wp_lp), N, K, static_cast<cudaStream_t>(stream));
+}
+int unimm_k_permute_w(const void* d_W_lp, void* d_Wp_lp, int N, int K, int mode, void* stream) {
+    return permute_weight_rows(static_cast<const bf16*>(d_W_lp), static_cast<bf16*>(d_Wp_lp), N, K, mode, static_cast<cudaStream_t>(stream));
 }
 
 int unimm_k_gemm_ln_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, int N, int K, const float* d_bias,

@@ -45,7 +45,7 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
-template <int BN, bool LSE, int ST = 0>
+template <int BN, bool LSE, int ST = 0, bool FRAG = false>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue ep) {
@@ -156,6 +156,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // 16-bit-only output with 128-byte aligned row segments: the paired-chunk path (needs N % 64 == 0 so pairs never split)
         const bool lp_only = fast_ok && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && (N % 64) == 0 &&
                              (ep.ldo_bf16 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0;
+        // FRAG instantiation: the host has checked lp_only && w_perm16 && N % 32 == 0 (launch()); the other paths are compiled out
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -172,6 +173,64 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int label = -1;
             if (LSE && row_ok) label = ep.labels[row];
 
+            if constexpr (FRAG) {
+                // ---- 16-bit-only outputs with fragment-ordered weights (QKV, FFN-1): tcgen05.ld.16x256b hands each thread
+                // 8 CONSECUTIVE output columns of 4 rows (see permute_weight_rows, mode 1), so bias + activation + pack + one
+                // 16-byte store per row happen straight out of the registers: no shared-memory transpose, no __syncwarp
+                const int a4 = lane & 3, r8 = lane >> 2;
+                uint32_t f[2][32];
+                auto ld_chunk = [&](int c, uint32_t* dst) {
+                    ptx::tmem_ld_16x256b_x4(taddr0 + c * 32, dst);
+                    ptx::tmem_ld_16x256b_x4(taddr0 + c * 32 + (16u << 16), dst + 16);
+                };
+                if (n0 < N) ld_chunk(0, f[0]);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= N) break;  // warp-uniform (N % 32 == 0)
+                    float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (ep.bias != nullptr) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * a4));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 8 * a4 + 4));
+                        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+                    }
+                    ptx::tmem_ld_wait();
+                    if (c + 1 < NCH && col0 + 32 < N) ld_chunk(c + 1, f[(c + 1) & 1]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {          // row 8 k + r8 of the warp's 32: slab k >> 1, half k & 1
+                        float y[8];
+#pragma unroll
+                        for (int m = 0; m < 8; m += 2) {
+                            const int reg = (k >> 1) * 16 + 4 * (m >> 1) + 2 * (k & 1);
+                            f32x2::unpack(f32x2::add(f32x2::pack(__uint_as_float(f[c & 1][reg]), __uint_as_float(f[c & 1][reg + 1])),
+                                                     f32x2::pack(bb[m], bb[m + 1])), y[m], y[m + 1]);
+                        }
+                        if (ep.act == ACT_GELU) {
+#pragma unroll
+                            for (int m = 0; m < 8; m += 2) gelu_fast2(y[m], y[m + 1]);
+                        } else if (ep.act == ACT_GELU_TANH) {
+#pragma unroll
+                            for (int m = 0; m < 8; m += 2) gelu_tanh2(y[m], y[m + 1]);
+                        } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                            for (int m = 0; m < 8; ++m) y[m] = fmaxf(y[m], 0.f);
+                        }
+                        uint4 pk;
+                        pk.x = pack_lp2(y[0], y[1], ep.lp_kind); pk.y = pack_lp2(y[2], y[3], ep.lp_kind);
+                        pk.z = pack_lp2(y[4], y[5], ep.lp_kind); pk.w = pack_lp2(y[6], y[7], ep.lp_kind);
+                        const int grow = m0 + ew * 32 + 8 * k + r8;
+                        if (grow < M) *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + col0 + 8 * a4) = pk;
+                    }
+                }
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
+            if constexpr (FRAG) continue;   // (unreachable; keeps the legacy paths out of this instantiation)
             uint32_t v[32];
             if (ep.debug_mode == 3) goto tile_done;
             if (n0 < N) ptx::tmem_ld_32x32b_x32(taddr0, v);      // chunk 0 in flight
@@ -224,7 +283,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // activation hoisted out of the element loop: a branch-free body lets the 32 independent chains interleave
                     if (ep.act == ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) gelu_fast2(x[j], x[j + 1]);
+                        for (int j = 0; j < 32; j += 2) gelu_epi2(x[j], x[j + 1]);
                     } else if (ep.act == ACT_RELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
@@ -288,7 +347,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (ep.act == ACT_GELU) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            gelu_fast2(y[i].x, y[i].y); gelu_fast2(y[i].z, y[i].w);
+                            gelu_epi2(y[i].x, y[i].y); gelu_epi2(y[i].z, y[i].w);
                         }
                     } else if (ep.act == ACT_RELU) {
 #pragma unroll
@@ -459,7 +518,7 @@ int num_sms() {
     return n;
 }
 
-template <int BN, bool LSE, int ST = 0>
+template <int BN, bool LSE, int ST = 0, bool FRAG = false>
 int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int max_ctas,
            cudaStream_t stream) {
     using Cfg = GemmCfg<BN, ST>;
@@ -468,13 +527,13 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN, &tmB));
     static bool attr_set = false;
     if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN, LSE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN, LSE, ST, FRAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int grid = tiles < num_sms() ? tiles : num_sms();
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    umma_gemm_kernel<BN, LSE, ST><<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+    umma_gemm_kernel<BN, LSE, ST, FRAG><<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -499,6 +558,14 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
         GemmEpilogue e2 = ep;
         e2.debug_mode -= 4;
         return launch<256, false, 3>(A, lda, W, ldw, M, N, K, e2, max_ctas, stream);
+    }
+    if (ep.w_perm16) {
+        auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        UNIMM_CHECK(ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && N % 32 == 0 && (ep.ldo_bf16 & 7) == 0 &&
+                        a16(ep.out_bf16) && (ep.bias == nullptr || a16(ep.bias)) && ep.debug_mode == 0,
+                    "fragment-ordered weights need a 16-bit-only, 16-byte aligned output with N % 32 == 0");
+        if (tile_n == 256) return launch<256, false, 0, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+        return launch<128, false, 0, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     }
     if (tile_n == 256) return launch<256, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     UNIMM_CHECK(tile_n == 128, "umma gemm: tile_n must be 128 or 256");

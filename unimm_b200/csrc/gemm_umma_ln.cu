@@ -398,9 +398,16 @@ __host__ __device__ inline int ln_weight_row(int p) {
     return (p & ~31) | (16 * (j >> 1) + 4 * a + 2 * (j & 1) + e);
 }
 
-__global__ void permute_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int row_vec) {
+// the 16-bit-output epilogue of gemm_umma.cu: accumulator column 8 j + 2 a + e holds output column 8 a + 2 j + e,
+// i.e. lane a owns the 8 consecutive output columns 8a..8a+7 of a 32-column chunk
+__host__ __device__ inline int p16_weight_row(int p) {
+    const int j = (p >> 3) & 3, a = (p >> 1) & 3, e = p & 1;
+    return (p & ~31) | (8 * a + 2 * j + e);
+}
+
+__global__ void permute_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int row_vec, int mode) {
     const int row = blockIdx.x;
-    const uint4* s = src + static_cast<size_t>(ln_weight_row(row)) * row_vec;
+    const uint4* s = src + static_cast<size_t>(mode == 0 ? ln_weight_row(row) : p16_weight_row(row)) * row_vec;
     uint4* d = dst + static_cast<size_t>(row) * row_vec;
     for (int i = threadIdx.x; i < row_vec; i += blockDim.x) d[i] = s[i];
 }
@@ -474,12 +481,13 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
 
 }  // namespace
 
-int permute_weight_rows_ln(const bf16* W, bf16* Wp, int N, int K, cudaStream_t stream) {
-    UNIMM_CHECK(N % 32 == 0 && K % 8 == 0 && W != Wp, "permute_weight_rows_ln: N must be a multiple of 32, K of 8, out of place");
-    permute_rows_kernel<<<N, 128, 0, stream>>>(reinterpret_cast<const uint4*>(W), reinterpret_cast<uint4*>(Wp), N, K / 8);
+int permute_weight_rows(const bf16* W, bf16* Wp, int N, int K, int mode, cudaStream_t stream) {
+    UNIMM_CHECK(N % 32 == 0 && K % 8 == 0 && W != Wp && (mode == 0 || mode == 1), "permute_weight_rows: N must be a multiple of 32, K of 8, out of place");
+    permute_rows_kernel<<<N, 128, 0, stream>>>(reinterpret_cast<const uint4*>(W), reinterpret_cast<uint4*>(Wp), N, K / 8, mode);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
+int permute_weight_rows_ln(const bf16* W, bf16* Wp, int N, int K, cudaStream_t stream) { return permute_weight_rows(W, Wp, N, K, 0, stream); }
 
 bool gemm_umma_ln_supported(int N, int K, const GemmLnEpilogue& ep) {
     auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

@@ -23,6 +23,7 @@ struct GemmEpilogue {
     int act = ACT_NONE;
     int debug_mode = 0;            // microbenchmark only: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue work
     int lp_kind = LP_BF16;         // encoding of the 16-bit operands and of out_bf16 (LP_BF16 / LP_FP16)
+    bool w_perm16 = false;         // W rows are in fragment order (permute_weight_rows mode 1): enables the smem-free 16-bit epilogue
     const int* labels = nullptr;   // LSE mode: [M]
     float2* partials = nullptr;    // LSE mode: [M, gemm_umma_lse_tiles(N)]
     float* label_logit = nullptr;  // LSE mode: [M]
@@ -53,6 +54,9 @@ struct GemmLnEpilogue {
 // W must be the row-permuted copy produced by permute_weight_rows_ln (see gemm_umma_ln.cu: the permutation makes each
 // thread's tcgen05.ld fragment 8 consecutive output columns).
 int permute_weight_rows_ln(const bf16* W, bf16* Wp, int N, int K, cudaStream_t stream);
+// mode 0: order for the LayerNorm-fused kernel (a thread's fragment = output columns 4a..4a+3 and 16+4a..16+4a+3);
+// mode 1: order for the 16-bit-output epilogue of gemm_umma_bf16 (fragment = output columns 8a..8a+7)
+int permute_weight_rows(const bf16* W, bf16* Wp, int N, int K, int mode, cudaStream_t stream);
 bool gemm_umma_ln_supported(int N, int K, const GemmLnEpilogue& ep);
 int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmLnEpilogue& ep, cudaStream_t stream);
 
