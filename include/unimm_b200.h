@@ -215,6 +215,14 @@ int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d
                       void* d_y_lp, int lp_kind, void* stream);
 int unimm_k_cast_lp(const float* d_src, void* d_dst_lp, int64_t n, int lp_kind, void* stream);
 /* elem_kind = 0: fp32 tensors, 1: bf16, 2: fp16.  impl: 0 = CUDA-core kernel, 1 = tensor-core kernel (16-bit only). */
+/* Attention over PACKED rows as a job list (csrc/attention_jobs.cu): every job = (q_start, q_len, kv_start, kv_len, win, mask_row, -, -);
+ * rows of win jobs additionally attend [lo, hi) U {self} from d_row_iv[row] = (lo, hi, self, -).  16-bit tensors only.
+ * impl 0 = generic job kernel, 1 = persistent mma.sync candidate kernel, 2 = tcgen05 / TMEM candidate kernel
+ * (csrc/attention_umma.cu; D = 64, halo <= 16; n_rows = rows of the q/k/v matrices).  Replaces models/vilbert_dialog.py:395-410
+ * for the rows a candidate owns under the generative mask of utils/data_utils.py:199-210. */
+int unimm_k_attention_jobs(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int n_rows,
+                           int heads, int D, const int32_t* d_jobs, int n_jobs, int max_q_len, int kv_cap, int win_cap,
+                           const int32_t* d_row_iv, int halo, int lp_kind, int impl, void* stream);
 int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,
                       int heads, int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc,
                       const float* d_key_mask, int elem_kind, int impl, void* stream);

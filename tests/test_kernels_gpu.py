@@ -291,6 +291,74 @@ def test_cross_and_image_attention(kind, impl):
     assert max(err1, err2, err3) < tol
 
 
+def packed_candidate_layout(units, seed=0):
+    """Synthetic prefix-shared layout: ``units`` = [(ctx_len, [last_len per candidate])].  Returns row count, candidate jobs,
+    row_iv and, per candidate row, the list of allowed key rows (context + own interval + self) for the reference."""
+    n_shared = sum(c for c, _ in units)
+    jobs, iv, allowed = [], {}, {}
+    s0, row = 0, n_shared
+    for ctx, lasts in units:
+        q_start = row
+        for last in lasts:
+            s_abs = row
+            for idx in range(1 + 2 * last):
+                r = s_abs + idx
+                if idx == 0:
+                    lo, hi, self_ = s_abs, s_abs + 1 + 2 * last, -1
+                elif idx <= last:
+                    lo, hi, self_ = s_abs + 1, s_abs + idx + 1, -1
+                else:
+                    lo, hi, self_ = s_abs + 1, s_abs + idx - last, r
+                iv[r] = (lo, hi, self_, 0)
+                allowed[r] = list(range(s0, s0 + ctx)) + list(range(lo, hi)) + ([self_] if self_ >= 0 else [])
+            row += 1 + 2 * last
+        jobs.append((q_start, row - q_start, s0, ctx, 1, -1, 0, 0))
+        s0 += ctx
+    M = row
+    row_iv = torch.zeros(M, 4, dtype=torch.int32)
+    row_iv[:, 2] = -1
+    for r, v in iv.items():
+        row_iv[r] = torch.tensor(v, dtype=torch.int32)
+    return M, torch.tensor(jobs, dtype=torch.int32), row_iv, allowed
+
+
+@pytest.mark.parametrize("lp", ["fp16", "bf16"])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_candidate_attention_kernels(impl, lp):
+    """Candidate rows over context U own rows: persistent mma.sync kernel (1) and tcgen05/TMEM kernel (2) against fp64."""
+    g = np.random.RandomState(5)
+    units = [(239, list(g.randint(1, 9, size=100))), (30, list(g.randint(1, 9, size=40))), (64, [8, 8, 1]), (129, list(g.randint(1, 9, size=57))),
+             (256, list(g.randint(1, 9, size=9))), (1, [3])]
+    M, jobs, row_iv, allowed = packed_candidate_layout(units)
+    heads, d = 12, 64
+    H = heads * d
+    dt = torch.float16 if lp == "fp16" else torch.bfloat16
+    qkv = rnd(M + 7, 3 * H, seed=31).to(dt)[:M]            # a few allocated rows behind the tensor extent
+    out = torch.full((M, H), float("nan"), device=DEV, dtype=dt)
+    e, base = qkv.element_size(), qkv.data_ptr()
+    max_q = int(jobs[:, 1].max())
+    dj, di = jobs.to(DEV), row_iv.to(DEV)
+    check(lib.unimm_k_attention_jobs(C.c_void_p(base), 3 * H, C.c_void_p(base + e * H), 3 * H, C.c_void_p(base + 2 * e * H), 3 * H,
+                                     ptr(out), H, M, heads, d, ptr(dj), jobs.shape[0], max_q, 256, 192, ptr(di), 16,
+                                     1 if lp == "fp16" else 0, impl, stream()))
+    torch.cuda.synchronize()
+    q = qkv[:, :H].double().view(M, heads, d)
+    k = qkv[:, H:2 * H].double().view(M, heads, d)
+    v = qkv[:, 2 * H:].double().view(M, heads, d)
+    rows = sorted(allowed)
+    err = 0.0
+    for r in rows[::7] + rows[-40:]:
+        keys = torch.tensor(allowed[r], device=DEV)
+        s = torch.einsum("hd,khd->hk", q[r], k[keys]) / math.sqrt(d)
+        ref = torch.einsum("hk,khd->hd", torch.softmax(s, -1), v[keys]).reshape(H)
+        err = max(err, (out[r].double() - ref).abs().max().item())
+    n_shared = sum(c for c, _ in units)
+    assert torch.isfinite(out[n_shared:].float()).all()
+    assert torch.isnan(out[:n_shared].float()).all()       # context rows are not this kernel's to write
+    print(f"candidate attention impl={impl} {lp}: max err {err:.3e}")
+    assert err < (4e-3 if lp == "fp16" else 3e-2)
+
+
 def test_verify_masks_kernel():
     desc = make_desc()
     B, S, R = desc.shape[0], 256, 37

@@ -1,0 +1,552 @@
+// tcgen05 / TMEM / TMA attention for the CANDIDATE rows of the prefix-shared layout (text self-attention, D = 64).
+//
+// Replaces, for the rows a candidate owns, the reference's matmul / +mask / softmax / matmul of BertSelfAttention
+// (models/vilbert_dialog.py:395-410) under the generative mask of utils/data_utils.py:199-210.  A candidate row r
+// attends   context rows [kv_start, kv_start + kv_len)  U  own-candidate rows [lo_r, hi_r) U {self_r}   (attention_jobs.cu).
+// 94 % of those (query, key) pairs are the context part, which is the same dense [q_len x kv_len] problem for every
+// row of a unit, so it runs on the 5th-generation tensor cores; the <= 17 own keys of a row lie within +-16 packed
+// rows of it and are handled by the softmax warps themselves with mma.sync on a TMA-staged window.  The two partial
+// softmaxes (each with its own running max) are merged in the epilogue.
+//
+// One persistent CTA per SM walks (unit, head) ITEMS; per item the context K / V (<= 256 keys) sit in shared memory and
+// the item's query rows stream through in 128-row tiles:
+//
+//   warp 0   TMA producer: Q tile (2 boxes of 64 rows x 128 B, SWIZZLE_128B) and the K / V window rows
+//            [tile - 16, tile + 176) into 2-deep rings
+//   warp 3   TMA producer of the per-item context K and V (single buffers, refilled as soon as the last QK / PV MMA of
+//            the previous item has read them: the K refill overlaps the previous item's last softmax)
+//   warp 1   one thread issues  S[b] = Q K_ctx^T   (tcgen05.mma M128 x N(64..256) x K16, both operands K-major in smem,
+//            fp32 accumulator = TMEM columns [256 b, 256 b + N))      one tile AHEAD of
+//                            O[b] = P[b] V_ctx    (A = P from TMEM, B = V as stored = MN-major in smem, N = 64)
+//   warp 2   TMEM allocator (512 columns: two S / P / O buffers)
+//   warps 4-7 / 8-11   two softmax warpgroups on alternating tiles (thread = one query row = one TMEM lane):
+//            pass 1 row max, pass 2 p = 2^(s*c - m*c) -> 16-bit pairs written back over S with tcgen05.st (P never
+//            touches shared memory), own-candidate part with mma.sync while the PV MMA runs, then O from TMEM in the
+//            mma fragment arrangement (tcgen05.ld.16x256b), merge, normalise, 16-bit stores.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "attn_common.cuh"
+#include "common.cuh"
+#include "gemm_common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace unimm {
+namespace {
+
+using namespace attn;
+
+constexpr int TQ = 128;                 // query rows per tile (= UMMA M)
+constexpr int BOXR = 64;                // rows per TMA box
+constexpr int BOXB = BOXR * 128;        // bytes per box: 64 rows x 64 16-bit elements
+constexpr int HALO = 16;                // own-candidate keys of row r lie in [r - HALO, r + HALO]
+constexpr int WBOXR = 32;               // rows per window TMA box
+constexpr int WBOXB = WBOXR * 128;
+constexpr int WBOX = 5;                 // window boxes: rows [tile - 16, tile + 144) = tile + 2 * HALO
+constexpr int WSTAGE = WBOX * WBOXB;    // 20 KB
+constexpr int KC_OFF = 0;               // context K: 4 boxes
+constexpr int VC_OFF = 4 * BOXB;        // context V: 4 boxes
+constexpr int Q_OFF = 8 * BOXB;         // 2 x 2 boxes
+constexpr int KW_OFF = 12 * BOXB;       // 2 stages
+constexpr int VW_OFF = KW_OFF + 2 * WSTAGE;
+constexpr int OST_OFF = VW_OFF + 2 * WSTAGE;   // output staging: 8 warps x 32 rows x 128 B
+constexpr int BAR_OFF = OST_OFF + 8 * 4096;
+constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024 /* alignment slack */;
+constexpr int O_COL = 192;              // O accumulator columns inside a 256-column TMEM buffer (P uses [0,128))
+
+enum Bar { KC_FULL = 0, KC_FREE, VC_FULL, VC_FREE, Q_FULL, Q_FREE = Q_FULL + 2, W_FULL = Q_FREE + 2, W_FREE = W_FULL + 2,
+           S_FULL = W_FREE + 2, S_FREE = S_FULL + 2, P_FULL = S_FREE + 2, O_FULL = P_FULL + 2, NBAR = O_FULL + 2 };
+
+// byte offset of 16-byte chunk `chunk` of row `row` inside a stack of SWIZZLE_128B boxes (rows of 128 bytes)
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) {
+    return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// polling wait of the single-thread roles (TMA producers, MMA issuer): back off between probes so that the spin does not
+// take issue slots from the softmax warps that share the scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        __nanosleep(40);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
+struct Item {
+    int q_start, q_len, kv_start, kv_len, head, n_tiles, nkb;
+};
+__device__ __forceinline__ Item load_item(const AttnJobsArgs& a, int item) {
+    Item it;
+    const int job = item / a.heads;
+    it.head = item - job * a.heads;
+    const int4 j = *reinterpret_cast<const int4*>(a.jobs + static_cast<size_t>(job) * 8);
+    it.q_start = j.x; it.q_len = j.y; it.kv_start = j.z; it.kv_len = j.w;
+    it.n_tiles = (it.q_len + TQ - 1) / TQ;
+    it.nkb = (it.kv_len + BOXR - 1) / BOXR;
+    return it;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(384, 1)
+attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKw,
+                      const __grid_constant__ CUtensorMap tmVw, AttnJobsArgs a, int n_items, int dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmK);
+        ptx::prefetch_tensormap(&tmV);
+        ptx::prefetch_tensormap(&tmKw);
+        ptx::prefetch_tensormap(&tmVw);
+    }
+    if (warp == 1 && ptx::elect_one()) {
+        ptx::mbar_init(&bars[KC_FULL], 1); ptx::mbar_init(&bars[KC_FREE], 1);
+        ptx::mbar_init(&bars[VC_FULL], 1); ptx::mbar_init(&bars[VC_FREE], 1);
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&bars[Q_FULL + b], 1); ptx::mbar_init(&bars[Q_FREE + b], 4);
+            ptx::mbar_init(&bars[W_FULL + b], 1); ptx::mbar_init(&bars[W_FREE + b], 4);
+            ptx::mbar_init(&bars[S_FULL + b], 1); ptx::mbar_init(&bars[S_FREE + b], 4);
+            ptx::mbar_init(&bars[P_FULL + b], 4); ptx::mbar_init(&bars[O_FULL + b], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- Q / window producer
+        if (ptx::elect_one()) {
+            int n = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const Item it = load_item(a, item);
+                const int col = it.head * 64;
+                for (int t = 0; t < it.n_tiles; ++t, ++n) {
+                    const int b = n & 1;
+                    const uint32_t ph = (n >> 1) & 1;
+                    const int r0 = it.q_start + t * TQ;
+                    mbar_wait_relaxed(&bars[Q_FREE + b], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&bars[Q_FULL + b], 2 * BOXB);
+                    ptx::tma_load_2d(smem + Q_OFF + b * 2 * BOXB, &tmQ, &bars[Q_FULL + b], col, r0);
+                    ptx::tma_load_2d(smem + Q_OFF + b * 2 * BOXB + BOXB, &tmQ, &bars[Q_FULL + b], col, r0 + BOXR);
+                    mbar_wait_relaxed(&bars[W_FREE + b], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&bars[W_FULL + b], 2 * WSTAGE);
+#pragma unroll
+                    for (int j = 0; j < WBOX; ++j) {
+                        ptx::tma_load_2d(smem + KW_OFF + b * WSTAGE + j * WBOXB, &tmKw, &bars[W_FULL + b], col, r0 - HALO + j * WBOXR);
+                        ptx::tma_load_2d(smem + VW_OFF + b * WSTAGE + j * WBOXB, &tmVw, &bars[W_FULL + b], col, r0 - HALO + j * WBOXR);
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ---------------------------------------------------------------- context K / V producer
+        if (ptx::elect_one()) {
+            uint32_t k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+                const Item it = load_item(a, item);
+                const int col = it.head * 64;
+                mbar_wait_relaxed(&bars[KC_FREE], (k & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&bars[KC_FULL], it.nkb * BOXB);
+                for (int j = 0; j < it.nkb; ++j)
+                    ptx::tma_load_2d(smem + KC_OFF + j * BOXB, &tmK, &bars[KC_FULL], col, it.kv_start + j * BOXR);
+                mbar_wait_relaxed(&bars[VC_FREE], (k & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&bars[VC_FULL], it.nkb * BOXB);
+                for (int j = 0; j < it.nkb; ++j)
+                    ptx::tma_load_2d(smem + VC_OFF + j * BOXB, &tmV, &bars[VC_FULL], col, it.kv_start + j * BOXR);
+            }
+            // the last item's "free" commits must have landed in this CTA's shared memory before it exits
+            if (k > 0) {
+                mbar_wait_relaxed(&bars[KC_FREE], (k - 1) & 1);
+                mbar_wait_relaxed(&bars[VC_FREE], (k - 1) & 1);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer: QK(n + 1) ahead of PV(n)
+        if (ptx::elect_one()) {
+            const uint32_t fmt = FP16 ? 0u : 1u;
+            struct Cursor { int item; uint32_t seq; int t; int n; Item it; bool valid; };
+            auto start = [&](Cursor& c) {
+                c.item = blockIdx.x; c.seq = 0; c.t = 0; c.n = 0;
+                c.valid = c.item < n_items;
+                if (c.valid) c.it = load_item(a, c.item);
+            };
+            auto advance = [&](Cursor& c) {
+                ++c.n;
+                if (++c.t == c.it.n_tiles) {
+                    c.t = 0; ++c.seq; c.item += gridDim.x;
+                    c.valid = c.item < n_items;
+                    if (c.valid) c.it = load_item(a, c.item);
+                }
+            };
+            auto issue_qk = [&](const Cursor& c) {
+                const int b = c.n & 1;
+                const uint32_t ph = (c.n >> 1) & 1;
+                if (c.t == 0) ptx::mbar_wait(&bars[KC_FULL], c.seq & 1);
+                ptx::mbar_wait(&bars[Q_FULL + b], ph);
+                ptx::mbar_wait(&bars[S_FREE + b], ph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t idesc = ptx::make_idesc_f16(TQ, c.it.nkb * BOXR, fmt);
+                const uint64_t da = ptx::make_sw128_kmajor_desc(smem_base + Q_OFF + b * 2 * BOXB);
+                const uint64_t db = ptx::make_sw128_kmajor_desc(smem_base + KC_OFF);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) ptx::umma_f16_ss(tmem_base + b * 256, da + 2 * ks, db + 2 * ks, idesc, ks != 0 ? 1u : 0u);
+                ptx::umma_commit(&bars[S_FULL + b]);
+                if (c.t == c.it.n_tiles - 1) ptx::umma_commit(&bars[KC_FREE]);
+            };
+            auto issue_pv = [&](const Cursor& c) {
+                const int b = c.n & 1;
+                const uint32_t ph = (c.n >> 1) & 1;
+                if (c.t == 0) ptx::mbar_wait(&bars[VC_FULL], c.seq & 1);
+                ptx::mbar_wait(&bars[P_FULL + b], ph);
+                ptx::tc_fence_after();
+                const uint32_t idesc = ptx::make_idesc_f16(TQ, 64, fmt) | (1u << 16);   // B (= V as stored) is MN-major
+                const uint64_t db = ptx::make_sw128_kmajor_desc(smem_base + VC_OFF);    // 8-key groups 1024 B apart
+                const int nks = c.it.nkb * 4;                                           // 16 keys per MMA
+                for (int ks = 0; ks < nks; ++ks)
+                    ptx::umma_f16_ts(tmem_base + b * 256 + O_COL, tmem_base + b * 256 + 8 * ks, db + 128 * ks, idesc, ks != 0 ? 1u : 0u);
+                ptx::umma_commit(&bars[O_FULL + b]);
+                if (c.t == c.it.n_tiles - 1) ptx::umma_commit(&bars[VC_FREE]);
+            };
+            Cursor cq, cp;
+            start(cq);
+            start(cp);
+            if (cq.valid) { issue_qk(cq); advance(cq); }
+            while (cp.valid) {
+                if (cq.valid) { issue_qk(cq); advance(cq); }
+                issue_pv(cp);
+                advance(cp);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- softmax / own-candidate / epilogue warpgroups
+        const int wg = (warp - 4) >> 2;
+        const int qd = warp & 3;                                   // TMEM lane quarter this warp may touch
+        const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+        const int g = lane >> 2, t4 = lane & 3;
+        const float sl = a.scale * 1.4426950408889634f;
+        int n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Item it = load_item(a, item);
+            const int n1p = it.nkb * BOXR;
+            const int q_end = it.q_start + it.q_len;
+            bf16* Og = static_cast<bf16*>(a.o) + it.head * 64;
+            for (int t = 0; t < it.n_tiles; ++t, ++n) {
+                if ((n & 1) != wg) continue;
+                const int b = wg;
+                const uint32_t ph = (n >> 1) & 1;
+                const int r0 = it.q_start + t * TQ;
+                const uint32_t tS = tmem_base + b * 256 + lane_off;
+                const uint32_t ost = smem_base + OST_OFF + (warp - 4) * 4096;   // this warp's 32 rows x 128 B stash / staging block
+
+                ptx::mbar_wait(&bars[S_FULL + b], ph);
+                ptx::tc_fence_after();
+
+                // ---- (1) pass 1: row max over the context keys (two 32-column loads in flight while two are folded)
+                float mx = -INFINITY;
+                {
+                    uint32_t a0[32], a1[32], b0[32], b1[32];
+                    auto fold = [&](const uint32_t* v, int c) {
+                        const int valid = it.kv_len - c;                      // warp-uniform
+                        if (valid >= 32) {
+                            float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+                            for (int j = 4; j < 32; j += 4) {
+                                m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                                m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                            }
+                            mx = fmaxf(mx, fmaxf(m0, m1));
+                        } else if (valid > 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < valid ? __uint_as_float(v[j]) : -INFINITY);
+                        }
+                    };
+                    if (dbg & 2) mx = 0.f;
+                    else {
+                        ptx::tmem_ld_32x32b_x32(tS, a0);
+                        ptx::tmem_ld_32x32b_x32(tS + 32, a1);
+                        for (int c = 0; c < n1p; c += 128) {
+                            ptx::tmem_ld_wait();
+                            const bool more = c + 64 < n1p;
+                            if (more) { ptx::tmem_ld_32x32b_x32(tS + c + 64, b0); ptx::tmem_ld_32x32b_x32(tS + c + 96, b1); }
+                            fold(a0, c);
+                            fold(a1, c + 32);
+                            if (more) {
+                                ptx::tmem_ld_wait();
+                                if (c + 128 < n1p) { ptx::tmem_ld_32x32b_x32(tS + c + 128, a0); ptx::tmem_ld_32x32b_x32(tS + c + 160, a1); }
+                                fold(b0, c + 64);
+                                fold(b1, c + 96);
+                            }
+                        }
+                    }
+                }
+                int4 iv[2][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int r = min(r0 + qd * 32 + mt * 16 + g + 8 * hh, q_end - 1);
+                        iv[mt][hh] = *reinterpret_cast<const int4*>(a.row_iv + static_cast<size_t>(r) * 4);
+                    }
+                const float m_ctx = mx;
+                const float msl = m_ctx * sl;
+
+                // ---- (2) pass 2: p = 2^(s*sl - m*sl), 16-bit pairs written back over S (columns [0, n1p / 2))
+                uint64_t lacc0 = f32x2::dup(0.f), lacc1 = f32x2::dup(0.f);
+                if (!(dbg & 4)) {
+                    uint32_t v0[32], v1[32];
+                    const uint64_t sl2 = f32x2::dup(sl), nm2 = f32x2::dup(-msl);
+                    auto emit_p = [&](const uint32_t* v, int c) {
+                        uint32_t pk[16];
+                        const int valid = it.kv_len - c;                      // warp-uniform
+                        if (valid >= 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float x0, x1, x2, x3;
+                                f32x2::unpack(f32x2::fma(f32x2::pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sl2, nm2), x0, x1);
+                                f32x2::unpack(f32x2::fma(f32x2::pack(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sl2, nm2), x2, x3);
+                                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+                                lacc0 = f32x2::add(lacc0, f32x2::pack(p0, p1));
+                                lacc1 = f32x2::add(lacc1, f32x2::pack(p2, p3));
+                                pk[j >> 1] = pack2<FP16>(p0, p1);
+                                pk[(j >> 1) + 1] = pack2<FP16>(p2, p3);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl, -msl));
+                                float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl, -msl));
+                                p0 = j < valid ? p0 : 0.f;
+                                p1 = j + 1 < valid ? p1 : 0.f;
+                                lacc0 = f32x2::add(lacc0, f32x2::pack(p0, p1));
+                                pk[j >> 1] = pack2<FP16>(p0, p1);
+                            }
+                        }
+                        tmem_st_32x32b_x16(tS + (c >> 1), pk);
+                    };
+                    ptx::tmem_ld_32x32b_x32(tS, v0);
+                    for (int c = 0; c < n1p; c += 64) {
+                        ptx::tmem_ld_wait();
+                        ptx::tmem_ld_32x32b_x32(tS + c + 32, v1);
+                        emit_p(v0, c);
+                        ptx::tmem_ld_wait();
+                        if (c + 64 < n1p) ptx::tmem_ld_32x32b_x32(tS + c + 64, v0);
+                        emit_p(v1, c + 32);
+                    }
+                }
+                float l0, l1, l2, l3;
+                f32x2::unpack(lacc0, l0, l1);
+                f32x2::unpack(lacc1, l2, l3);
+                const float l_ctx = (l0 + l1) + (l2 + l3);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars[P_FULL + b]);
+
+                // ---- (3) own-candidate part with mma.sync while the PV MMA runs: keys = window rows [rowbase, rowbase + 48)
+                ptx::mbar_wait(&bars[Q_FULL + b], ph);
+                ptx::mbar_wait(&bars[W_FULL + b], ph);
+                const uint32_t qs = smem_base + Q_OFF + b * 2 * BOXB;
+                const uint32_t kw = smem_base + KW_OFF + b * WSTAGE;
+                const uint32_t vw = smem_base + VW_OFF + b * WSTAGE;
+                float o_own[2][8][4];
+                float m_own[2][2], l_own[2][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    if (dbg & 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o_own[mt][i][0] = o_own[mt][i][1] = o_own[mt][i][2] = o_own[mt][i][3] = 0.f;
+                        m_own[mt][0] = m_own[mt][1] = -INFINITY; l_own[mt][0] = l_own[mt][1] = 0.f;
+                        continue;
+                    }
+                    const int rowbase = qd * 32 + mt * 16;              // keys = window rows [rowbase, rowbase + 48)
+                    float s[6][4];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        uint32_t qa[4];
+                        ldsm4(qa, qs + sw128(rowbase + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4)));
+#pragma unroll
+                        for (int nb2 = 0; nb2 < 3; ++nb2) {
+                            uint32_t kb[4];
+                            ldsm4(kb, kw + sw128(rowbase + nb2 * 16 + (lane & 7) + 8 * (lane >> 4), 2 * ks + ((lane >> 3) & 1)));
+                            mma_lp<FP16>(s[2 * nb2], qa, kb[0], kb[1]);
+                            mma_lp<FP16>(s[2 * nb2 + 1], qa, kb[2], kb[3]);
+                        }
+                    }
+                    const int key0 = r0 - HALO + rowbase + 2 * t4;          // packed row of this thread's first key column
+                    float tm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+                    for (int nb = 0; nb < 6; ++nb)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int hh = e >> 1, key = key0 + nb * 8 + (e & 1);
+                            const bool ok = (key >= iv[mt][hh].x && key < iv[mt][hh].y) || key == iv[mt][hh].z;
+                            s[nb][e] = ok ? s[nb][e] : -INFINITY;
+                            tm[hh] = fmaxf(tm[hh], s[nb][e]);
+                        }
+                    float ls[2] = {0.f, 0.f};
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        tm[hh] = fmaxf(tm[hh], __shfl_xor_sync(0xffffffffu, tm[hh], 1));
+                        tm[hh] = fmaxf(tm[hh], __shfl_xor_sync(0xffffffffu, tm[hh], 2));
+                        m_own[mt][hh] = tm[hh];
+                    }
+                    const float ms0 = tm[0] == -INFINITY ? 0.f : tm[0] * sl, ms1 = tm[1] == -INFINITY ? 0.f : tm[1] * sl;
+#pragma unroll
+                    for (int nb = 0; nb < 6; ++nb) {
+                        s[nb][0] = fast_exp2(fmaf(s[nb][0], sl, -ms0));
+                        s[nb][1] = fast_exp2(fmaf(s[nb][1], sl, -ms0));
+                        s[nb][2] = fast_exp2(fmaf(s[nb][2], sl, -ms1));
+                        s[nb][3] = fast_exp2(fmaf(s[nb][3], sl, -ms1));
+                        ls[0] += s[nb][0] + s[nb][1];
+                        ls[1] += s[nb][2] + s[nb][3];
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        ls[hh] += __shfl_xor_sync(0xffffffffu, ls[hh], 1);
+                        ls[hh] += __shfl_xor_sync(0xffffffffu, ls[hh], 2);
+                        l_own[mt][hh] = ls[hh];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o_own[mt][i][0] = o_own[mt][i][1] = o_own[mt][i][2] = o_own[mt][i][3] = 0.f;
+#pragma unroll
+                    for (int kc = 0; kc < 3; ++kc) {
+                        uint32_t pa[4];
+                        pa[0] = pack2<FP16>(s[2 * kc][0], s[2 * kc][1]);
+                        pa[1] = pack2<FP16>(s[2 * kc][2], s[2 * kc][3]);
+                        pa[2] = pack2<FP16>(s[2 * kc + 1][0], s[2 * kc + 1][1]);
+                        pa[3] = pack2<FP16>(s[2 * kc + 1][2], s[2 * kc + 1][3]);
+#pragma unroll
+                        for (int db2 = 0; db2 < 4; ++db2) {
+                            uint32_t vb[4];
+                            ldsm4_trans(vb, vw + sw128(rowbase + kc * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * db2 + (lane >> 4)));
+                            mma_lp<FP16>(o_own[mt][2 * db2], pa, vb[0], vb[1]);
+                            mma_lp<FP16>(o_own[mt][2 * db2 + 1], pa, vb[2], vb[3]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { ptx::mbar_arrive(&bars[Q_FREE + b]); ptx::mbar_arrive(&bars[W_FREE + b]); }
+
+                // ---- (4) O = P V from TMEM in the mma fragment arrangement, merge with the stashed own part, normalise
+                ptx::mbar_wait(&bars[O_FULL + b], ph);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    float ca[2], cb[2];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int src = mt * 16 + g + 8 * hh;
+                        const float mc = __shfl_sync(0xffffffffu, m_ctx, src), lc = __shfl_sync(0xffffffffu, l_ctx, src);
+                        const float mo = m_own[mt][hh];
+                        const float m = fmaxf(mc, mo);
+                        const float ea = fast_exp2((mc - m) * sl);
+                        const float eb = mo == -INFINITY ? 0.f : fast_exp2((mo - m) * sl);
+                        const float inv = 1.0f / (lc * ea + l_own[mt][hh] * eb);
+                        ca[hh] = ea * inv;
+                        cb[hh] = eb * inv;
+                    }
+                    uint32_t u[32];
+                    const uint32_t tO = tmem_base + b * 256 + O_COL + lane_off + (static_cast<uint32_t>(mt * 16) << 16);
+                    ptx::tmem_ld_16x256b_x4(tO, u);
+                    ptx::tmem_ld_16x256b_x4(tO + 32, u + 16);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int lr = mt * 16 + g + 8 * hh;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float x0 = __uint_as_float(u[4 * j + 2 * hh]) * ca[hh] + o_own[mt][j][2 * hh] * cb[hh];
+                            const float x1 = __uint_as_float(u[4 * j + 2 * hh + 1]) * ca[hh] + o_own[mt][j][2 * hh + 1] * cb[hh];
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ost + sw128(lr, j) + 4 * t4), "r"(pack2<FP16>(x0, x1)) : "memory");
+                        }
+                    }
+                }
+                // O has left TMEM: hand the S / P / O buffer back before the global stores
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars[S_FREE + b]);
+                // whole 128-byte rows to global: 8 lanes per row, 4 rows per instruction
+                if (!(dbg & 8)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int lr = i * 4 + (lane >> 3), ch = lane & 7;
+                        const int row = r0 + qd * 32 + lr;
+                        uint32_t x, y, z, w;
+                        ptx::lds_v4(ost + sw128(lr, ch), x, y, z, w);
+                        if (row < q_end) *reinterpret_cast<uint4*>(Og + static_cast<size_t>(row) * a.ldo + 8 * ch) = make_uint4(x, y, z, w);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+template <bool FP16>
+int launch_umma(const AttnJobsArgs& a, cudaStream_t stream) {
+    CUtensorMap tmQ, tmK, tmV, tmKw, tmVw;
+    const int W = a.heads * 64;
+    UNIMM_TRY(gemm_make_map(a.q, a.n_rows, W, a.ldq, BOXR, &tmQ));
+    UNIMM_TRY(gemm_make_map(a.k, a.n_rows, W, a.ldk, BOXR, &tmK));
+    UNIMM_TRY(gemm_make_map(a.v, a.n_rows, W, a.ldv, BOXR, &tmV));
+    UNIMM_TRY(gemm_make_map(a.k, a.n_rows, W, a.ldk, WBOXR, &tmKw));
+    UNIMM_TRY(gemm_make_map(a.v, a.n_rows, W, a.ldv, WBOXR, &tmVw));
+    static bool attr_set = false;
+    if (!attr_set) {
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cand_umma_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int n_items = a.n_jobs * a.heads;
+    const int grid = n_items < gemm_num_sms() ? n_items : gemm_num_sms();
+    static int dbg = getenv("UNIMM_ATTN_DBG") ? atoi(getenv("UNIMM_ATTN_DBG")) : 0;   // timing experiments only (results invalid)
+    attn_cand_umma_kernel<FP16><<<grid, 384, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmKw, tmVw, a, n_items, dbg);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+}  // namespace
+
+bool attention_candidates_umma_supported(const AttnJobsArgs& a, int halo) {
+    return a.D == 64 && halo <= HALO && a.kv_cap <= 256 && a.n_rows > 0 && (a.ldq % 8) == 0 && (a.ldk % 8) == 0 && (a.ldv % 8) == 0 &&
+           (a.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.k) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(a.v) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0 && (a.ldo % 8) == 0;
+}
+
+// candidate jobs (win = 1, D = 64, 16-bit, halo <= 16) on tcgen05: see the header of this file
+int attention_candidates_umma(const AttnJobsArgs& a, int halo, cudaStream_t stream) {
+    UNIMM_CHECK(a.n_jobs > 0 && attention_candidates_umma_supported(a, halo), "tcgen05 candidate attention: unsupported arguments");
+    return a.lp_kind == LP_FP16 ? launch_umma<true>(a, stream) : launch_umma<false>(a, stream);
+}
+
+}  // namespace unimm

@@ -158,6 +158,7 @@ struct unimm_engine {
                   ActBuf& out, cudaStream_t st);
     bool fuse_ln = true;
     bool gelu_tanh = false;      // UNIMM_GELU_TANH=1: 1-SFU tanh-form GELU in the FFN-1 epilogue (|err| <= |x| * 2.4e-4)
+    bool attn_umma = true;       // candidate-row attention on tcgen05 (attention_umma.cu); UNIMM_ATTN_UMMA=0 keeps the mma.sync kernel
     bool frag_epilogue = true;   // QKV / FFN-1 GEMMs read fragment-ordered weight copies (UNIMM_FRAG_EPILOGUE=0 disables)
     // fp16 mode keeps the residual stream in 16 bits between sub-layers (the fused kernel adds it on the tensor core);
     // bf16's 8-bit mantissa cannot afford that, it keeps the fp32 master.  xt.f / xv.f are refreshed after the encoder.
@@ -475,8 +476,10 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
             a.max_q_len = pk.max_q_text_self; a.kv_cap = pk.kv_cap_text; a.win_cap = pk.win_cap;
             a.row_iv = pk.d_row_iv; a.key_mask = nullptr; a.key_mask_ld = 0;
             a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind();
+            a.n_rows = M;
             Prof prof(this, CAT_ATTN, 4.0 * heads * D * pk.pairs_text_self, st);
-            UNIMM_TRY(attention_candidates(a, pk.cand_halo, st));
+            if (attn_umma && attention_candidates_umma_supported(a, pk.cand_halo)) UNIMM_TRY(attention_candidates_umma(a, pk.cand_halo, st));
+            else UNIMM_TRY(attention_candidates(a, pk.cand_halo, st));
         } else if (text) UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_text_self, pk.n_jobs_text_self,
                                                     pk.max_q_text_self, pk.kv_cap_text, pk.win_cap, pk.pairs_text_self, ac, st));
         else UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_img_self, pk.n_jobs_img_self,
@@ -786,6 +789,7 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     if (const char* f = getenv("UNIMM_FUSE_LN")) e->fuse_ln = atoi(f) != 0;   // A/B switches for bench.py; defaults: on
     if (const char* f = getenv("UNIMM_FRAG_EPILOGUE")) e->frag_epilogue = atoi(f) != 0;
     if (const char* f = getenv("UNIMM_GELU_TANH")) e->gelu_tanh = atoi(f) != 0;
+    if (const char* f = getenv("UNIMM_ATTN_UMMA")) e->attn_umma = atoi(f) != 0;
     e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;
@@ -1069,6 +1073,21 @@ int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d
 
 int unimm_k_cast_lp(const float* d_src, void* d_dst, int64_t n, int lp_kind, void* stream) {
     return cast_f32_to_lp(d_src, static_cast<bf16*>(d_dst), static_cast<size_t>(n), lp_kind, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_attention_jobs(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int n_rows,
+                           int heads, int D, const int32_t* d_jobs, int n_jobs, int max_q_len, int kv_cap, int win_cap,
+                           const int32_t* d_row_iv, int halo, int lp_kind, int impl, void* stream) {
+    AttnJobsArgs a;
+    a.q = d_q; a.ldq = ldq; a.k = d_k; a.ldk = ldk; a.v = d_v; a.ldv = ldv; a.o = d_o; a.ldo = ldo;
+    a.heads = heads; a.D = D; a.jobs = d_jobs; a.n_jobs = n_jobs; a.max_q_len = max_q_len; a.kv_cap = kv_cap; a.win_cap = win_cap;
+    a.row_iv = d_row_iv; a.key_mask = nullptr; a.key_mask_ld = 0;
+    a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind; a.n_rows = n_rows;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == 0) return attention_jobs(a, false, st);
+    if (impl == 1) return attention_candidates(a, halo, st);
+    UNIMM_CHECK(impl == 2, "impl: 0 = generic jobs, 1 = persistent mma.sync candidates, 2 = tcgen05 candidates");
+    return attention_candidates_umma(a, halo, st);
 }
 
 int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,

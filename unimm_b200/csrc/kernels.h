@@ -130,11 +130,16 @@ struct AttnJobsArgs {
     int key_mask_ld;
     float scale;
     int lp_kind;
+    int n_rows = 0;        // rows of the q / k / v matrices (TMA tensor extent; the tcgen05 candidate kernel only)
 };
 int attention_jobs(const AttnJobsArgs& a, bool fp32, cudaStream_t stream);
 // jobs that all have win = 1 (candidate rows over context + own rows), D = 64, 16-bit: persistent double-buffered kernel.
 // halo = (longest candidate's row count - 1): rows of a candidate lie within +-halo of any of its rows.
 int attention_candidates(const AttnJobsArgs& a, int halo, cudaStream_t stream);
+// the same jobs on tcgen05 (attention_umma.cu): context part on the 5th-gen tensor cores with S / P / O in TMEM, own-candidate
+// part with mma.sync on a TMA-staged window; needs halo <= 16 and a.n_rows
+bool attention_candidates_umma_supported(const AttnJobsArgs& a, int halo);
+int attention_candidates_umma(const AttnJobsArgs& a, int halo, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ heads.cu
 // packed layout: text pooled row = xt[cls_row[c]], image pooled row = xv[unit[c] * R]
