@@ -19,6 +19,7 @@
 //            [rows, 30522] logits never reach HBM.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -45,7 +46,10 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
-template <int BN, bool LSE, int ST = 0, bool FRAG = false>
+// CL = 2: two CTAs of a cluster work on vertically adjacent 128-row tiles of the same BN columns and each loads only half
+// of the shared W box, multicast into both CTAs' shared memory (operand traffic from L2 per CTA: 32 KB instead of 48 KB per
+// k-block at BN = 256); a ring slot is reusable once BOTH CTAs' MMAs have read it (empty barriers count 2, multicast commit).
+template <int BN, bool LSE, int ST = 0, bool FRAG = false, int CL = 1>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue ep) {
@@ -65,10 +69,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_m = (M + BM - 1) / BM;
+    const int num_m = ((M + BM - 1) / BM + CL - 1) / CL;     // row blocks of CL x 128 rows (a padding tile is all out of bounds)
     const int num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_k = K / BK;
+    const uint32_t crank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+    const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;
+    constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
     if (warp == 0 && ptx::elect_one()) {
         ptx::prefetch_tensormap(&tmA);
@@ -77,7 +84,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1 && ptx::elect_one()) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], CL);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
@@ -87,7 +94,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all();   // the peer's barriers exist before anything arrives on them remotely
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -96,14 +104,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * BM;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                const int m0 = ((tile / num_n) * CL + static_cast<int>(crank)) * BM;
                 const int n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_k; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
-                    ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
+                    if (CL == 1) ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
+                    else ptx::tma_load_2d_mc(sB + stage * Cfg::kBBytes + crank * (Cfg::kBBytes / CL), &tmB, &full_bar[stage], kb * BK,
+                                             n0 + static_cast<int>(crank) * (BN / CL), kMask);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -116,7 +126,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
@@ -130,7 +140,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
                         ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    if (CL == 1) ptx::umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    else ptx::umma_commit_mc(&empty_bar[stage], kMask);  // ... in both CTAs (the peer multicasts into this slot too)
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
@@ -159,9 +170,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // FRAG instantiation: the host has checked lp_only && w_perm16 && N % 32 == 0 (launch()); the other paths are compiled out
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int tn = tile % num_n;
-            const int m0 = (tile / num_n) * BM;
+            const int m0 = ((tile / num_n) * CL + static_cast<int>(crank)) * BM;
             const int n0 = tn * BN + half * HALF_N;
             const int row = m0 + ew * 32 + lane;
             const bool row_ok = row < M;
@@ -440,7 +451,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all();   // no CTA leaves while its peer may still multicast into its shared memory / barriers
+    else __syncthreads();
     if (warp == 2) ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
@@ -518,22 +530,50 @@ int num_sms() {
     return n;
 }
 
-template <int BN, bool LSE, int ST = 0, bool FRAG = false>
+template <int BN, bool LSE, int ST = 0, bool FRAG = false, int CL = 1>
 int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int max_ctas,
            cudaStream_t stream) {
     using Cfg = GemmCfg<BN, ST>;
     CUtensorMap tmA, tmB;
     UNIMM_TRY(make_map_bf16(A, M, K, lda, BM, &tmA));
-    UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN, &tmB));
+    UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN / CL, &tmB));
     static bool attr_set = false;
+    static int max_clusters = 0;
+    auto kernel = umma_gemm_kernel<BN, LSE, ST, FRAG, CL>;
     if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN, LSE, ST, FRAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    int grid = tiles < num_sms() ? tiles : num_sms();
-    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    umma_gemm_kernel<BN, LSE, ST, FRAG><<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+    const int tiles = (((M + BM - 1) / BM + CL - 1) / CL) * ((N + BN - 1) / BN);
+    if (CL == 1) {
+        int grid = tiles < num_sms() ? tiles : num_sms();
+        if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+        kernel<<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+        UNIMM_LAUNCH_CHECK(1);
+        return 0;
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters == 0) {
+        cfg.gridDim = dim3(num_sms() / CL * CL, 1, 1);
+        int n = 0;
+        UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+        UNIMM_CHECK(n > 0, "no co-resident cluster fits the multicast GEMM");
+        max_clusters = n < num_sms() / CL ? n : num_sms() / CL;
+    }
+    int clusters = tiles < max_clusters ? tiles : max_clusters;
+    if (max_ctas > 0 && clusters > max_ctas / CL) clusters = max_ctas / CL > 0 ? max_ctas / CL : 1;
+    cfg.gridDim = dim3(clusters * CL, 1, 1);
+    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, M, N, K, ep));
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -550,8 +590,12 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     UNIMM_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "umma gemm: K must be a positive multiple of 64");
     const bool lse = ep.partials != nullptr;
     if (tile_n == 0) tile_n = (N % 256 == 0 || N > 2048) ? 256 : 128;
+    // tall problems (every SM gets several row blocks): CTA pairs sharing the W tile by TMA multicast
+    static const bool mc_enabled = getenv("UNIMM_GEMM_MULTICAST") == nullptr || atoi(getenv("UNIMM_GEMM_MULTICAST")) != 0;
+    const bool mc = mc_enabled && M >= 8192 && ep.debug_mode == 0;
     if (lse) {
         UNIMM_CHECK(tile_n == 256, "LSE epilogue uses 256-wide vocabulary tiles");
+        if (mc) return launch<256, true, 0, false, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         return launch<256, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     }
     if (tile_n == 256 && ep.debug_mode >= 4) {   // microbenchmark: 3-stage ring, epilogue mode = debug_mode - 4
@@ -564,9 +608,11 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
         UNIMM_CHECK(ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && N % 32 == 0 && (ep.ldo_bf16 & 7) == 0 &&
                         a16(ep.out_bf16) && (ep.bias == nullptr || a16(ep.bias)) && ep.debug_mode == 0,
                     "fragment-ordered weights need a 16-bit-only, 16-byte aligned output with N % 32 == 0");
+        if (tile_n == 256 && mc) return launch<256, false, 0, true, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         if (tile_n == 256) return launch<256, false, 0, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         return launch<128, false, 0, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     }
+    if (tile_n == 256 && mc) return launch<256, false, 0, false, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     if (tile_n == 256) return launch<256, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     UNIMM_CHECK(tile_n == 128, "umma gemm: tile_n must be 128 or 256");
     return launch<128, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
