@@ -223,6 +223,12 @@ int unimm_k_cast_lp(const float* d_src, void* d_dst_lp, int64_t n, int lp_kind, 
 int unimm_k_attention_jobs(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int n_rows,
                            int heads, int D, const int32_t* d_jobs, int n_jobs, int max_q_len, int kv_cap, int win_cap,
                            const int32_t* d_row_iv, int halo, int lp_kind, int impl, void* stream);
+/* Window-free jobs over <= 64 keys whose K / V live in another matrix (text -> image co-attention, models/vilbert_dialog.py:681-698):
+ * d_key_mask[mask_row] (job[5]) marks valid keys; no valid key = all keys, as the reference's additive mask.
+ * impl 0 = generic job kernel, 2 = tcgen05 / TMEM kernel (D = 128). */
+int unimm_k_attention_cross_jobs(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo,
+                                 int n_q_rows, int n_kv_rows, int heads, int D, const int32_t* d_jobs, int n_jobs, int max_q_len,
+                                 const float* d_key_mask, int key_mask_ld, int lp_kind, int impl, void* stream);
 int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,
                       int heads, int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc,
                       const float* d_key_mask, int elem_kind, int impl, void* stream);

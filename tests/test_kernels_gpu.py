@@ -360,6 +360,47 @@ def test_candidate_attention_kernels(impl, lp):
     assert err < (4e-3 if lp == "fp16" else 3e-2)
 
 
+@pytest.mark.parametrize("lp", ["fp16", "bf16"])
+@pytest.mark.parametrize("impl", [0, 2])
+def test_text_to_image_jobs(impl, lp):
+    """Packed text rows over their unit's 37 image regions (D = 128, image padding mask): generic job kernel and tcgen05 kernel."""
+    R, heads, d = 37, 8, 128
+    H = heads * d
+    q_lens = [239, 1100, 30, 700, 1, 129, 256, 64]            # two jobs per unit (context rows, candidate rows)
+    U = len(q_lens) // 2
+    jobs, row = [], 0
+    for i, n in enumerate(q_lens):
+        jobs.append((row, n, (i // 2) * R, R, 0, i // 2, 0, 0))
+        row += n
+    Mt, Mv = row, U * R
+    dt = torch.float16 if lp == "fp16" else torch.bfloat16
+    qkv_t, qkv_v = rnd(Mt, 3 * H, seed=41).to(dt), rnd(Mv, 3 * H, seed=42).to(dt)
+    mask = torch.ones(U, R, device=DEV)
+    mask[1, 30:] = 0
+    mask[2, 1:] = 0
+    mask[3, :] = 0                                            # nothing valid: every key allowed (the reference's additive mask)
+    out = torch.full((Mt, H), float("nan"), device=DEV, dtype=dt)
+    dj = torch.tensor(jobs, dtype=torch.int32, device=DEV)
+    e = qkv_v.element_size()
+    check(lib.unimm_k_attention_cross_jobs(ptr(qkv_t), 3 * H, C.c_void_p(qkv_v.data_ptr() + e * H), 3 * H,
+                                           C.c_void_p(qkv_v.data_ptr() + 2 * e * H), 3 * H, ptr(out), H, Mt, Mv, heads, d, ptr(dj),
+                                           len(jobs), max(q_lens), ptr(mask), R, 1 if lp == "fp16" else 0, impl, stream()))
+    torch.cuda.synchronize()
+    err = 0.0
+    for (q0, n, k0, _, _, u, _, _) in jobs:
+        q = qkv_t[q0:q0 + n, :H].double().view(n, heads, d)
+        k = qkv_v[k0:k0 + R, H:2 * H].double().view(R, heads, d)
+        v = qkv_v[k0:k0 + R, 2 * H:].double().view(R, heads, d)
+        sc = torch.einsum("qhd,khd->hqk", q, k) / math.sqrt(d)
+        m = mask[u].bool() if mask[u].any() else torch.ones(R, dtype=torch.bool, device=DEV)
+        sc = sc.masked_fill(~m[None, None, :], float("-inf"))
+        ref = torch.einsum("hqk,khd->qhd", torch.softmax(sc, -1), v).reshape(n, H)
+        err = max(err, (out[q0:q0 + n].double() - ref).abs().max().item())
+    assert torch.isfinite(out.float()).all()
+    print(f"text->image jobs impl={impl} {lp}: max err {err:.3e}")
+    assert err < (4e-3 if lp == "fp16" else 3e-2)
+
+
 def test_verify_masks_kernel():
     desc = make_desc()
     B, S, R = desc.shape[0], 256, 37

@@ -98,6 +98,7 @@ SYMBOLS = {
     "unimm_k_layernorm": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "unimm_k_cast_lp": (C.c_int, [_P, _P, C.c_int64, _I, _P]),
     "unimm_k_attention_jobs": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "unimm_k_attention_cross_jobs": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P]),
     "unimm_k_attention": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
 }
 

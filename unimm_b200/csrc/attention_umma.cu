@@ -535,6 +535,289 @@ int launch_umma(const AttnJobsArgs& a, cudaStream_t stream) {
     return 0;
 }
 
+
+// =================================================================================================================
+// Text -> image co-attention of the packed layout (BertBiAttention, models/vilbert_dialog.py:681-698): every text row
+// of a unit (context rows and candidate rows are separate jobs) attends the unit's <= 64 image regions, D = 128, keys
+// masked by the unit's image mask.  Tiny arithmetic (37 keys) over a large row stream: the kernel is a Q-in / O-out
+// stream at HBM speed — Q tiles by TMA, S = Q K^T and O = P V on tcgen05 with S / P / O in TMEM, thread-per-row
+// softmax, output rows staged in shared memory and written as whole 256-byte rows.  Same roles as the kernel above.
+// =================================================================================================================
+namespace x {
+constexpr int XD = 128;
+constexpr int XKATOM = 64 * 128;          // one 64-column atom of the 64 staged key rows: 8 KB
+constexpr int XQATOM = TQ * 128;          // one 64-column atom of a 128-row Q tile: 16 KB
+constexpr int XKI_OFF = 0;                // 2 buffers x 2 atoms
+constexpr int XVI_OFF = 4 * XKATOM;
+constexpr int XQ_OFF = 8 * XKATOM;         // 2 buffers x 2 atoms
+constexpr int XOST_OFF = XQ_OFF + 4 * XQATOM;      // 8 warps x 32 rows x 256 B
+constexpr int XBAR_OFF = XOST_OFF + 8 * 8192;
+constexpr int XSMEM_BYTES = XBAR_OFF + 256 + 1024;
+constexpr int XO_COL = 64;                // S / P at [0,64), O at [64,192) of a 256-column buffer
+enum Bar { XKV_FULL = 0, XKV_FREE = 2, XQ_FULL = 4, XQ_FREE = 6, XS_FULL = 8, XS_FREE = 10, XP_FULL = 12, XO_FULL = 14, XNBAR = 16 };
+}  // namespace x
+
+// SWIZZLE_128B descriptor with an explicit leading-dimension byte offset (distance between 64-element MN atoms of an
+// MN-major operand); 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_sw128_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(384, 1)
+attn_cross_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, AttnJobsArgs a, int n_items) {
+    using namespace x;   // X-prefixed constants
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XBAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XNBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmK);
+        ptx::prefetch_tensormap(&tmV);
+    }
+    if (warp == 1 && ptx::elect_one()) {
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&bars[XKV_FULL + b], 1); ptx::mbar_init(&bars[XKV_FREE + b], 1);
+            ptx::mbar_init(&bars[XQ_FULL + b], 1); ptx::mbar_init(&bars[XQ_FREE + b], 1);
+            ptx::mbar_init(&bars[XS_FULL + b], 1); ptx::mbar_init(&bars[XS_FREE + b], 4);
+            ptx::mbar_init(&bars[XP_FULL + b], 4); ptx::mbar_init(&bars[XO_FULL + b], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = ptx::smem_u32(smem);
+
+    auto item_of = [&](int item, int& q_start, int& q_len, int& kv_start, int& kv_len, int& mask_row, int& head) {
+        const int job = item / a.heads;
+        head = item - job * a.heads;
+        const int* j = a.jobs + static_cast<size_t>(job) * 8;
+        q_start = j[0]; q_len = j[1]; kv_start = j[2]; kv_len = j[3]; mask_row = j[5];
+    };
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- Q producer
+        if (ptx::elect_one()) {
+            int n = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int q_start, q_len, kv_start, kv_len, mask_row, head;
+                item_of(item, q_start, q_len, kv_start, kv_len, mask_row, head);
+                const int n_tiles = (q_len + TQ - 1) / TQ;
+                for (int t = 0; t < n_tiles; ++t, ++n) {
+                    const int b = n & 1;
+                    mbar_wait_relaxed(&bars[XQ_FREE + b], ((n >> 1) & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(&bars[XQ_FULL + b], 2 * XQATOM);
+                    ptx::tma_load_2d(smem + XQ_OFF + (2 * b) * XQATOM, &tmQ, &bars[XQ_FULL + b], head * XD, q_start + t * TQ);
+                    ptx::tma_load_2d(smem + XQ_OFF + (2 * b + 1) * XQATOM, &tmQ, &bars[XQ_FULL + b], head * XD + 64, q_start + t * TQ);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ---------------------------------------------------------------- image K / V producer (double buffered per item)
+        if (ptx::elect_one()) {
+            uint32_t k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+                int q_start, q_len, kv_start, kv_len, mask_row, head;
+                item_of(item, q_start, q_len, kv_start, kv_len, mask_row, head);
+                const int kb = k & 1;
+                mbar_wait_relaxed(&bars[XKV_FREE + kb], ((k >> 1) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&bars[XKV_FULL + kb], 4 * XKATOM);
+                ptx::tma_load_2d(smem + XKI_OFF + (2 * kb) * XKATOM, &tmK, &bars[XKV_FULL + kb], head * XD, kv_start);
+                ptx::tma_load_2d(smem + XKI_OFF + (2 * kb + 1) * XKATOM, &tmK, &bars[XKV_FULL + kb], head * XD + 64, kv_start);
+                ptx::tma_load_2d(smem + XVI_OFF + (2 * kb) * XKATOM, &tmV, &bars[XKV_FULL + kb], head * XD, kv_start);
+                ptx::tma_load_2d(smem + XVI_OFF + (2 * kb + 1) * XKATOM, &tmV, &bars[XKV_FULL + kb], head * XD + 64, kv_start);
+            }
+            for (uint32_t j = (k > 2 ? k - 2 : 0); j < k; ++j)     // the last commits must have landed before this CTA exits
+                mbar_wait_relaxed(&bars[XKV_FREE + (j & 1)], (j >> 1) & 1);
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer: QK(n + 1) ahead of PV(n)
+        if (ptx::elect_one()) {
+            const uint32_t fmt = FP16 ? 0u : 1u;
+            struct Cursor { int item; uint32_t seq; int t, n, n_tiles, kv_len; bool valid; };
+            auto load = [&](Cursor& c) {
+                c.valid = c.item < n_items;
+                if (c.valid) {
+                    int q_start, q_len, kv_start, mask_row, head;
+                    item_of(c.item, q_start, q_len, kv_start, c.kv_len, mask_row, head);
+                    c.n_tiles = (q_len + TQ - 1) / TQ;
+                }
+            };
+            auto start = [&](Cursor& c) { c.item = blockIdx.x; c.seq = 0; c.t = 0; c.n = 0; load(c); };
+            auto advance = [&](Cursor& c) {
+                ++c.n;
+                if (++c.t == c.n_tiles) { c.t = 0; ++c.seq; c.item += gridDim.x; load(c); }
+            };
+            auto issue_qk = [&](const Cursor& c) {
+                const int b = c.n & 1, kb = c.seq & 1;
+                const uint32_t ph = (c.n >> 1) & 1;
+                if (c.t == 0) ptx::mbar_wait(&bars[XKV_FULL + kb], (c.seq >> 1) & 1);
+                ptx::mbar_wait(&bars[XQ_FULL + b], ph);
+                ptx::mbar_wait(&bars[XS_FREE + b], ph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t idesc = ptx::make_idesc_f16(TQ, 64, fmt);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(smem_base + XQ_OFF + (2 * b + (ks >> 2)) * XQATOM) + 2 * (ks & 3);
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(smem_base + XKI_OFF + (2 * kb + (ks >> 2)) * XKATOM) + 2 * (ks & 3);
+                    ptx::umma_f16_ss(tmem_base + b * 256, da, db, idesc, ks != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&bars[XS_FULL + b]);
+                ptx::umma_commit(&bars[XQ_FREE + b]);      // Q is read by these MMAs only
+            };
+            auto issue_pv = [&](const Cursor& c) {
+                const int b = c.n & 1, kb = c.seq & 1;
+                const uint32_t ph = (c.n >> 1) & 1;
+                ptx::mbar_wait(&bars[XP_FULL + b], ph);
+                ptx::tc_fence_after();
+                const uint32_t idesc = ptx::make_idesc_f16(TQ, XD, fmt) | (1u << 16);      // B = V as stored: MN-major, two 64-dim atoms
+                const uint64_t db = make_sw128_desc_lbo(smem_base + XVI_OFF + (2 * kb) * XKATOM, XKATOM);
+                const int nks = (c.kv_len + 15) >> 4;                                      // 16 keys per MMA
+                for (int ks = 0; ks < nks; ++ks)
+                    ptx::umma_f16_ts(tmem_base + b * 256 + XO_COL, tmem_base + b * 256 + 8 * ks, db + 128 * ks, idesc, ks != 0 ? 1u : 0u);
+                ptx::umma_commit(&bars[XO_FULL + b]);
+                if (c.t == c.n_tiles - 1) ptx::umma_commit(&bars[XKV_FREE + kb]);
+            };
+            Cursor cq, cp;
+            start(cq);
+            start(cp);
+            if (cq.valid) { issue_qk(cq); advance(cq); }
+            while (cp.valid) {
+                if (cq.valid) { issue_qk(cq); advance(cq); }
+                issue_pv(cp);
+                advance(cp);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- softmax / epilogue warpgroups (thread = query row)
+        const int wg = (warp - 4) >> 2;
+        const int qd = warp & 3;
+        const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+        const float sl = a.scale * 1.4426950408889634f;
+        const uint32_t ost = smem_base + XOST_OFF + (warp - 4) * 8192;
+        int n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int q_start, q_len, kv_start, kv_len, mask_row, head;
+            item_of(item, q_start, q_len, kv_start, kv_len, mask_row, head);
+            const int n_tiles = (q_len + TQ - 1) / TQ;
+            const int q_end = q_start + q_len;
+            // key validity bits (image padding mask of the unit); no valid key = every key allowed, as the reference's additive mask
+            unsigned long long kbits = kv_len >= 64 ? ~0ull : ((1ull << kv_len) - 1ull);
+            if (mask_row >= 0) {
+                const float* km = a.key_mask + static_cast<size_t>(mask_row) * a.key_mask_ld;
+                const unsigned lo = __ballot_sync(0xffffffffu, lane < kv_len && km[lane] > 0.5f);
+                const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < kv_len && km[min(lane + 32, kv_len - 1)] > 0.5f);
+                const unsigned long long m = (static_cast<unsigned long long>(hi) << 32) | lo;
+                if (m != 0ull) kbits = m;
+            }
+            bf16* Og = static_cast<bf16*>(a.o) + head * XD;
+            for (int t = 0; t < n_tiles; ++t, ++n) {
+                if ((n & 1) != wg) continue;
+                const int b = wg;
+                const uint32_t ph = (n >> 1) & 1;
+                const int r0 = q_start + t * TQ;
+                const uint32_t tS = tmem_base + b * 256 + lane_off;
+                ptx::mbar_wait(&bars[XS_FULL + b], ph);
+                ptx::tc_fence_after();
+                uint32_t v[64];
+                ptx::tmem_ld_32x32b_x32(tS, v);
+                ptx::tmem_ld_32x32b_x32(tS + 32, v + 32);
+                ptx::tmem_ld_wait();
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const float sv = ((kbits >> j) & 1ull) ? __uint_as_float(v[j]) : -INFINITY;
+                    v[j] = __float_as_uint(sv);
+                    mx = fmaxf(mx, sv);
+                }
+                const float msl = mx * sl;
+                float l0 = 0.f, l1 = 0.f;
+                uint32_t pk[32];
+#pragma unroll
+                for (int j = 0; j < 64; j += 2) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl, -msl));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl, -msl));
+                    l0 += p0; l1 += p1;
+                    pk[j >> 1] = pack2<FP16>(p0, p1);
+                }
+                ptx::tmem_st_32x32b_x32(tS, pk);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars[XP_FULL + b]);
+                const float inv = 1.0f / (l0 + l1);
+
+                ptx::mbar_wait(&bars[XO_FULL + b], ph);
+                ptx::tc_fence_after();
+                // normalised row -> this warp's staging block: 32 rows x 256 B, 16-byte chunks XOR-swizzled by (row & 7)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t u[32];
+                    ptx::tmem_ld_32x32b_x32(tS + XO_COL + c * 32, u);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int chunk = c * 4 + q;
+                        ptx::sts_v4(ost + lane * 256 + ((chunk ^ (lane & 7)) << 4),
+                                    pack2<FP16>(__uint_as_float(u[8 * q]) * inv, __uint_as_float(u[8 * q + 1]) * inv),
+                                    pack2<FP16>(__uint_as_float(u[8 * q + 2]) * inv, __uint_as_float(u[8 * q + 3]) * inv),
+                                    pack2<FP16>(__uint_as_float(u[8 * q + 4]) * inv, __uint_as_float(u[8 * q + 5]) * inv),
+                                    pack2<FP16>(__uint_as_float(u[8 * q + 6]) * inv, __uint_as_float(u[8 * q + 7]) * inv));
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars[XS_FREE + b]);
+                // whole 256-byte rows to global: 16 lanes per row, 2 rows per instruction
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int lr = i * 2 + (lane >> 4), ch = lane & 15;
+                    const int row = r0 + qd * 32 + lr;
+                    uint32_t x0, x1, x2, x3;
+                    ptx::lds_v4(ost + lr * 256 + ((ch ^ (lr & 7)) << 4), x0, x1, x2, x3);
+                    if (row < q_end) *reinterpret_cast<uint4*>(Og + static_cast<size_t>(row) * a.ldo + 8 * ch) = make_uint4(x0, x1, x2, x3);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+template <bool FP16>
+int launch_cross(const AttnJobsArgs& a, cudaStream_t stream) {
+    CUtensorMap tmQ, tmK, tmV;
+    const int W = a.heads * x::XD;
+    UNIMM_TRY(gemm_make_map(a.q, a.n_rows, W, a.ldq, TQ, &tmQ));
+    UNIMM_TRY(gemm_make_map(a.k, a.n_kv_rows, W, a.ldk, 64, &tmK));
+    UNIMM_TRY(gemm_make_map(a.v, a.n_kv_rows, W, a.ldv, 64, &tmV));
+    static bool attr_set = false;
+    if (!attr_set) {
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cross_umma_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, x::XSMEM_BYTES));
+        attr_set = true;
+    }
+    const int n_items = a.n_jobs * a.heads;
+    const int grid = n_items < gemm_num_sms() ? n_items : gemm_num_sms();
+    attn_cross_umma_kernel<FP16><<<grid, 384, x::XSMEM_BYTES, stream>>>(tmQ, tmK, tmV, a, n_items);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
 }  // namespace
 
 bool attention_candidates_umma_supported(const AttnJobsArgs& a, int halo) {
@@ -549,4 +832,17 @@ int attention_candidates_umma(const AttnJobsArgs& a, int halo, cudaStream_t stre
     return a.lp_kind == LP_FP16 ? launch_umma<true>(a, stream) : launch_umma<false>(a, stream);
 }
 
+}  // namespace unimm
+
+namespace unimm {
+bool attention_cross_umma_supported(const AttnJobsArgs& a) {
+    auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return a.D == 128 && a.kv_cap <= 64 && a.win_cap == 0 && a.n_rows > 0 && a.n_kv_rows > 0 && (a.ldq % 8) == 0 && (a.ldk % 8) == 0 &&
+           (a.ldv % 8) == 0 && (a.ldo % 8) == 0 && a16(a.q) && a16(a.k) && a16(a.v) && a16(a.o);
+}
+// jobs without windows over <= 64 keys, D = 128, 16-bit (text -> image co-attention) on tcgen05
+int attention_cross_umma(const AttnJobsArgs& a, cudaStream_t stream) {
+    UNIMM_CHECK(a.n_jobs > 0 && attention_cross_umma_supported(a), "tcgen05 cross attention: unsupported arguments");
+    return a.lp_kind == LP_FP16 ? launch_cross<true>(a, stream) : launch_cross<false>(a, stream);
+}
 }  // namespace unimm

@@ -171,6 +171,7 @@ struct unimm_engine {
         int B = 0;
         const SeqDesc* desc = nullptr;
         const float* key_mask = nullptr;
+        int n_q_rows = 0, n_kv_rows = 0;            // set (per call) to allow the tcgen05 cross-attention kernel
     };
     int attention_packed(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int heads, int D,
                          const int* jobs, int n_jobs, int max_q, int kv_cap, int win_cap, double qk_pairs, const AttnCtx& ac,
@@ -452,7 +453,9 @@ int unimm_engine::attention_packed(const void* q, int ldq, const void* k, int ld
     a.heads = heads; a.D = D; a.jobs = jobs; a.n_jobs = n_jobs; a.max_q_len = max_q; a.kv_cap = kv_cap; a.win_cap = win_cap;
     a.row_iv = ac.pk->d_row_iv; a.key_mask = ac.pk->d_image_mask; a.key_mask_ld = cfg.num_regions;
     a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind();
+    a.n_rows = ac.n_q_rows; a.n_kv_rows = ac.n_kv_rows;
     Prof prof(this, CAT_ATTN, 4.0 * heads * D * qk_pairs, st);
+    if (lp() && attn_umma && ac.n_q_rows > 0 && max_q > 64 && attention_cross_umma_supported(a)) return attention_cross_umma(a, st);
     return attention_jobs(a, !lp(), st);
 }
 
@@ -511,8 +514,10 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
     if (ac.pk != nullptr) {
         const unimm_packed_batch_t& pk = *ac.pk;
         // text queries (shared + candidate rows of a unit) over the unit's image keys/values (:681-698)
+        AttnCtx ax = ac;
+        ax.n_q_rows = Mt; ax.n_kv_rows = Mv;
         UNIMM_TRY(attention_packed(qkv_t, 3 * Hb, byte_ptr(qkv_v) + e * Hb, 3 * Hb, byte_ptr(qkv_v) + e * 2 * Hb, 3 * Hb, ctx_t, Hb, heads, D,
-                                   pk.d_jobs_t2i, pk.n_jobs_t2i, pk.max_q_t2i, 64, 0, static_cast<double>(Mt) * R, ac, st));
+                                   pk.d_jobs_t2i, pk.n_jobs_t2i, pk.max_q_t2i, 64, 0, static_cast<double>(Mt) * R, ax, st));
         // image queries over the unit's context rows = the co-attention interval [1,ctx) (:701-721)
         UNIMM_TRY(attention_packed(qkv_v, 3 * Hb, byte_ptr(qkv_t) + e * Hb, 3 * Hb, byte_ptr(qkv_t) + e * 2 * Hb, 3 * Hb, ctx_v, Hb, heads, D,
                                    pk.d_jobs_i2t, pk.n_jobs_i2t, R, pk.kv_cap_text, 0, pk.pairs_i2t, ac, st));
@@ -1088,6 +1093,20 @@ int unimm_k_attention_jobs(const void* d_q, int ldq, const void* d_k, int ldk, c
     if (impl == 1) return attention_candidates(a, halo, st);
     UNIMM_CHECK(impl == 2, "impl: 0 = generic jobs, 1 = persistent mma.sync candidates, 2 = tcgen05 candidates");
     return attention_candidates_umma(a, halo, st);
+}
+
+int unimm_k_attention_cross_jobs(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo,
+                                 int n_q_rows, int n_kv_rows, int heads, int D, const int32_t* d_jobs, int n_jobs, int max_q_len,
+                                 const float* d_key_mask, int key_mask_ld, int lp_kind, int impl, void* stream) {
+    AttnJobsArgs a;
+    a.q = d_q; a.ldq = ldq; a.k = d_k; a.ldk = ldk; a.v = d_v; a.ldv = ldv; a.o = d_o; a.ldo = ldo;
+    a.heads = heads; a.D = D; a.jobs = d_jobs; a.n_jobs = n_jobs; a.max_q_len = max_q_len; a.kv_cap = 64; a.win_cap = 0;
+    a.row_iv = nullptr; a.key_mask = d_key_mask; a.key_mask_ld = key_mask_ld;
+    a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind; a.n_rows = n_q_rows; a.n_kv_rows = n_kv_rows;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == 0) return attention_jobs(a, false, st);
+    UNIMM_CHECK(impl == 2, "impl: 0 = generic jobs, 2 = tcgen05 cross attention");
+    return attention_cross_umma(a, st);
 }
 
 int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,

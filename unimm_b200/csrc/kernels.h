@@ -130,7 +130,8 @@ struct AttnJobsArgs {
     int key_mask_ld;
     float scale;
     int lp_kind;
-    int n_rows = 0;        // rows of the q / k / v matrices (TMA tensor extent; the tcgen05 candidate kernel only)
+    int n_rows = 0;        // rows of the q (and, for self-attention, k / v) matrices: TMA tensor extent of the tcgen05 kernels
+    int n_kv_rows = 0;     // rows of the k / v matrices when they differ from q's (cross attention)
 };
 int attention_jobs(const AttnJobsArgs& a, bool fp32, cudaStream_t stream);
 // jobs that all have win = 1 (candidate rows over context + own rows), D = 64, 16-bit: persistent double-buffered kernel.
@@ -140,6 +141,9 @@ int attention_candidates(const AttnJobsArgs& a, int halo, cudaStream_t stream);
 // part with mma.sync on a TMA-staged window; needs halo <= 16 and a.n_rows
 bool attention_candidates_umma_supported(const AttnJobsArgs& a, int halo);
 int attention_candidates_umma(const AttnJobsArgs& a, int halo, cudaStream_t stream);
+// window-free jobs over <= 64 keys with D = 128 (text -> image co-attention) on tcgen05; needs n_rows and n_kv_rows
+bool attention_cross_umma_supported(const AttnJobsArgs& a);
+int attention_cross_umma(const AttnJobsArgs& a, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ heads.cu
 // packed layout: text pooled row = xt[cls_row[c]], image pooled row = xv[unit[c] * R]
