@@ -46,6 +46,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 pairs = sum(sum((1 + 2 * l) * c for l in ls) for c, ls in units)
 print(f"rows {M}, units {len(units)}, ctx pairs {pairs/1e6:.1f} M, ctx FLOPs {4*heads*d*pairs/1e9:.1f} G, Q+O+K+V own bytes {4*(M-sum(c for c,_ in units))*H*2/1e6:.0f} MB")
 ref = None
+FLUSH = os.environ.get("ATTN_BENCH_FLUSH", "1") != "0"
 for impl in [int(x) for x in (sys.argv[1:] or ["1", "2"])]:
     def run():
         check(lib.unimm_k_attention_jobs(C.c_void_p(base), 3 * H, C.c_void_p(base + e * H), 3 * H, C.c_void_p(base + 2 * e * H), 3 * H,
@@ -53,7 +54,7 @@ for impl in [int(x) for x in (sys.argv[1:] or ["1", "2"])]:
     for _ in range(3): run()
     ts = []
     for _ in range(10):
-        flush.zero_()
+        if FLUSH: flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); run(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)

@@ -295,6 +295,40 @@ def main():
              nsp_weight=np.array([[5.0, 1.0]], dtype=np.float32),
              lm_loss=lm_loss.numpy(), img_loss=img_loss.numpy(), nsp_loss=nsp_loss.numpy(), nsp_scores=nsp.numpy())
 
+    # ---------------------------------------------------------------- config 5: dense-annotation fine-tuning forward + loss
+    # (dense_annotation_finetuning.py:253 -> train.forward; dataloader_dense_annotations.py:148-172: ONE mode per image,
+    # relevance as the token weight -> the LongTensor truncates 0.2..0.8 to 0, relevance 0 makes the option a negative;
+    # nsp_weight = None, dense_annotation_finetuning.py:145)
+    for name, fn_name in (("ft8gen_perturbed", "encode_input_gen"), ("ft8dis_perturbed", "encode_input_dis")):
+        if not want(name):
+            continue
+        np.random.seed(31)
+        random.seed(31)
+        relevance = [1.0, 0.0, 0.4, 0.8, 0.0, 1.0, 0.6, 1.0]
+        kw = dict(mask_prob=0.1, vocab_size=30522, is_negtive=[int(r == 0) for r in relevance],
+                  weight=[(r if r > 0 else 1) for r in relevance])
+        b = ref_batch(du, context, answers[:8], feats, loc, image_mask, getattr(du, fn_name), seed=31, **kw)
+        ofn = enc.encode_gen if fn_name.endswith("gen") else enc.encode_dis
+        assert_encoders_match(b, oracle_batch(context, answers[:8], feats, loc, image_mask, ofn, seed=31, **kw))
+        np.random.seed(32)
+        target = torch.from_numpy(np.random.dirichlet(np.ones(1601), size=37).astype(np.float32))
+        f2, l2, im2, tgt2, img_label = du.encode_image_input(feats.numpy(), 37, loc.numpy(), target.numpy(),
+                                                             max_regions=37, mask_prob=0.1)
+        b["image_feat"] = f2.unsqueeze(0).expand(8, -1, -1).contiguous()
+        b["image_loc"] = l2.unsqueeze(0).expand(8, -1, -1).contiguous()
+        b["image_mask"] = im2.unsqueeze(0).expand(8, -1).contiguous()
+        nsl = torch.LongTensor([int(r == 0) for r in relevance])
+        extras = dict(next_sentence_label=nsl, image_label=img_label.unsqueeze(0).expand(8, -1).contiguous(),
+                      image_target=tgt2.unsqueeze(0).expand(8, -1, -1).contiguous(), nsp_weight=None)
+        model = get_model(1, True)
+        lm_loss, img_loss, nsp_loss, nsp, lm = call_reference(model, b, extras)
+        print(name, "weights used:", sorted(set(b["weights"].view(-1).tolist())), "losses", lm_loss.item(), img_loss.item(), nsp_loss.item())
+        save(name, weight_seed=np.array(1), perturbed=np.array(True), **pack_inputs(b),
+             image_feat=f2.numpy(), image_loc=l2.numpy(), image_mask=im2.numpy(),
+             next_sentence_label=nsl.numpy(), image_label=img_label.numpy(), image_target=tgt2.numpy(),
+             relevance=np.array(relevance, dtype=np.float32),
+             lm_loss=lm_loss.numpy(), img_loss=img_loss.numpy(), nsp_loss=nsp_loss.numpy(), nsp_scores=nsp.numpy())
+
     # ---------------------------------------------------------------- config 1: 100 candidates, ranking metrics
     for name, seed, perturbed in (("gen100_default", 0, False),):
         if not want(name):

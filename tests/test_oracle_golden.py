@@ -73,6 +73,22 @@ def test_training_losses_match_reference(full_cfg):
     np.testing.assert_allclose(out["img_loss"].item(), g["img_loss"].item(), atol=TOL, rtol=0)
 
 
+@pytest.mark.parametrize("name", ["ft8gen_perturbed", "ft8dis_perturbed"])
+def test_dense_annotation_losses_match_reference(full_cfg, name):
+    """BASELINE config 5: one mask mode for all options, relevance as (integer-truncated) token weight, nsp_weight None."""
+    g, batch = load_golden(name)
+    n = batch["tokens"].shape[0]
+    out = _run(full_cfg, g, batch,
+               next_sentence_label=torch.from_numpy(g["next_sentence_label"]),
+               image_label=torch.from_numpy(g["image_label"]).unsqueeze(0).expand(n, -1),
+               image_target=torch.from_numpy(g["image_target"]).unsqueeze(0).expand(n, -1, -1),
+               nsp_weight=None)
+    np.testing.assert_allclose(out["lm_loss"].item(), g["lm_loss"].item(), atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["nsp_loss"].item(), g["nsp_loss"].item(), atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["img_loss"].item(), g["img_loss"].item(), atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["nsp_scores"].numpy(), g["nsp_scores"], atol=TOL, rtol=0)
+
+
 def test_encoders_reproduce_reference_tensors():
     """oracle.encode_inputs regenerates the committed reference-made inputs from the same RNG stream."""
     g, batch = load_golden("gen8_default")

@@ -104,6 +104,28 @@ def test_training_losses(full_cfg, precision):
     assert abs(nsp - g["nsp_loss"].item()) < tol
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["ft8gen_perturbed", "ft8dis_perturbed"])
+def test_dense_annotation_losses(full_cfg, name, precision):
+    """BASELINE config 5 (dense_annotation_finetuning.py forward + loss): relevance-weighted L/UL loss, unweighted NSP CE."""
+    g, batch = load_golden(name)
+    eng = get_engine(full_cfg, g, precision)
+    n = batch["tokens"].shape[0]
+    o = run_engine(eng, batch, ("losses", "nsp_scores"), lm_weight=batch["weights"],
+                   next_sentence_label=torch.from_numpy(g["next_sentence_label"]),
+                   image_label=torch.from_numpy(g["image_label"]).unsqueeze(0).expand(n, -1).contiguous(),
+                   image_target=torch.from_numpy(g["image_target"]).unsqueeze(0).expand(n, -1, -1).contiguous(),
+                   nsp_weight=None)
+    lm, img, nsp = o["losses"][:3].cpu().numpy()
+    print(f"[{precision}] {name} losses lm {lm:.6f}/{g['lm_loss'].item():.6f} img {img:.6f}/{g['img_loss'].item():.6f} "
+          f"nsp {nsp:.6f}/{g['nsp_loss'].item():.6f}")
+    tol = TOL[precision]
+    assert abs(lm - g["lm_loss"].item()) < tol
+    assert abs(img - g["img_loss"].item()) < tol
+    assert abs(nsp - g["nsp_loss"].item()) < tol
+    np.testing.assert_allclose(o["nsp_scores"].cpu().numpy(), g["nsp_scores"], atol=tol, rtol=0)
+
+
 def test_config1_ranking_fp32(full_cfg):
     """100 candidates of one round: scores within 1e-4 and ranks / MRR / R@k / NDCG identical in fp32 mode."""
     from oracle import visdial_metrics as om

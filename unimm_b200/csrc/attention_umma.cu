@@ -150,11 +150,11 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     const int b = n & 1;
                     const uint32_t ph = (n >> 1) & 1;
                     const int r0 = it.q_start + t * TQ;
-                    mbar_wait_relaxed(&bars[Q_FREE + b], ph ^ 1);
+                    ptx::mbar_wait(&bars[Q_FREE + b], ph ^ 1);
                     ptx::mbar_arrive_expect_tx(&bars[Q_FULL + b], 2 * BOXB);
                     ptx::tma_load_2d(smem + Q_OFF + b * 2 * BOXB, &tmQ, &bars[Q_FULL + b], col, r0);
                     ptx::tma_load_2d(smem + Q_OFF + b * 2 * BOXB + BOXB, &tmQ, &bars[Q_FULL + b], col, r0 + BOXR);
-                    mbar_wait_relaxed(&bars[W_FREE + b], ph ^ 1);
+                    ptx::mbar_wait(&bars[W_FREE + b], ph ^ 1);
                     ptx::mbar_arrive_expect_tx(&bars[W_FULL + b], 2 * WSTAGE);
 #pragma unroll
                     for (int j = 0; j < WBOX; ++j) {
@@ -171,19 +171,19 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
                 const Item it = load_item(a, item);
                 const int col = it.head * 64;
-                mbar_wait_relaxed(&bars[KC_FREE], (k & 1) ^ 1);
+                ptx::mbar_wait(&bars[KC_FREE], (k & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&bars[KC_FULL], it.nkb * BOXB);
                 for (int j = 0; j < it.nkb; ++j)
                     ptx::tma_load_2d(smem + KC_OFF + j * BOXB, &tmK, &bars[KC_FULL], col, it.kv_start + j * BOXR);
-                mbar_wait_relaxed(&bars[VC_FREE], (k & 1) ^ 1);
+                ptx::mbar_wait(&bars[VC_FREE], (k & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&bars[VC_FULL], it.nkb * BOXB);
                 for (int j = 0; j < it.nkb; ++j)
                     ptx::tma_load_2d(smem + VC_OFF + j * BOXB, &tmV, &bars[VC_FULL], col, it.kv_start + j * BOXR);
             }
             // the last item's "free" commits must have landed in this CTA's shared memory before it exits
             if (k > 0) {
-                mbar_wait_relaxed(&bars[KC_FREE], (k - 1) & 1);
-                mbar_wait_relaxed(&bars[VC_FREE], (k - 1) & 1);
+                ptx::mbar_wait(&bars[KC_FREE], (k - 1) & 1);
+                ptx::mbar_wait(&bars[VC_FREE], (k - 1) & 1);
             }
         }
     } else if (warp == 1) {
@@ -267,44 +267,37 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 ptx::mbar_wait(&bars[S_FULL + b], ph);
                 ptx::tc_fence_after();
 
-                // ---- (1) pass 1: row max over the context keys (two 32-column loads in flight while two are folded)
+                // ---- (1) pass 1: row max over the context keys (the next 32 columns are in flight while 32 are folded)
                 float mx = -INFINITY;
-                {
-                    uint32_t a0[32], a1[32], b0[32], b1[32];
-                    auto fold = [&](const uint32_t* v, int c) {
-                        const int valid = it.kv_len - c;                      // warp-uniform
-                        if (valid >= 32) {
-                            float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                uint32_t v0[32], v1[32];
+                auto fold_max = [&](const uint32_t* v, int c) {
+                    if (c + 32 <= it.kv_len) {
+                        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                            for (int j = 4; j < 32; j += 4) {
-                                m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-                                m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-                            }
-                            mx = fmaxf(mx, fmaxf(m0, m1));
-                        } else if (valid > 0) {
+                        for (int j = 0; j < 32; j += 4) {
+                            m0 = fmaxf(m0, __uint_as_float(v[j])); m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(v[j + 2])); m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+                        }
+                        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < valid ? __uint_as_float(v[j]) : -INFINITY);
-                        }
-                    };
-                    if (dbg & 2) mx = 0.f;
-                    else {
-                        ptx::tmem_ld_32x32b_x32(tS, a0);
-                        ptx::tmem_ld_32x32b_x32(tS + 32, a1);
-                        for (int c = 0; c < n1p; c += 128) {
-                            ptx::tmem_ld_wait();
-                            const bool more = c + 64 < n1p;
-                            if (more) { ptx::tmem_ld_32x32b_x32(tS + c + 64, b0); ptx::tmem_ld_32x32b_x32(tS + c + 96, b1); }
-                            fold(a0, c);
-                            fold(a1, c + 32);
-                            if (more) {
-                                ptx::tmem_ld_wait();
-                                if (c + 128 < n1p) { ptx::tmem_ld_32x32b_x32(tS + c + 128, a0); ptx::tmem_ld_32x32b_x32(tS + c + 160, a1); }
-                                fold(b0, c + 64);
-                                fold(b1, c + 96);
-                            }
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            if (c + j < it.kv_len) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                };
+                if (dbg & 2) mx = 0.f;
+                else {
+                    ptx::tmem_ld_32x32b_x32(tS, v0);
+                    for (int c = 0; c < n1p; c += 64) {
+                        ptx::tmem_ld_wait();
+                        ptx::tmem_ld_32x32b_x32(tS + c + 32, v1);
+                        fold_max(v0, c);
+                        ptx::tmem_ld_wait();
+                        if (c + 64 < n1p) ptx::tmem_ld_32x32b_x32(tS + c + 64, v0);
+                        fold_max(v1, c + 32);
                     }
                 }
+                // own-candidate intervals of this thread's 4 fragment rows (global loads fly during pass 2)
                 int4 iv[2][2];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
@@ -317,38 +310,29 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 const float msl = m_ctx * sl;
 
                 // ---- (2) pass 2: p = 2^(s*sl - m*sl), 16-bit pairs written back over S (columns [0, n1p / 2))
-                uint64_t lacc0 = f32x2::dup(0.f), lacc1 = f32x2::dup(0.f);
-                if (!(dbg & 4)) {
-                    uint32_t v0[32], v1[32];
-                    const uint64_t sl2 = f32x2::dup(sl), nm2 = f32x2::dup(-msl);
-                    auto emit_p = [&](const uint32_t* v, int c) {
-                        uint32_t pk[16];
-                        const int valid = it.kv_len - c;                      // warp-uniform
-                        if (valid >= 32) {
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                auto emit_p = [&](const uint32_t* v, int c) {
+                    uint32_t pk[16];
+                    const bool full = c + 32 <= it.kv_len;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float x0, x1, x2, x3;
-                                f32x2::unpack(f32x2::fma(f32x2::pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sl2, nm2), x0, x1);
-                                f32x2::unpack(f32x2::fma(f32x2::pack(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sl2, nm2), x2, x3);
-                                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
-                                lacc0 = f32x2::add(lacc0, f32x2::pack(p0, p1));
-                                lacc1 = f32x2::add(lacc1, f32x2::pack(p2, p3));
-                                pk[j >> 1] = pack2<FP16>(p0, p1);
-                                pk[(j >> 1) + 1] = pack2<FP16>(p2, p3);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl, -msl));
-                                float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl, -msl));
-                                p0 = j < valid ? p0 : 0.f;
-                                p1 = j + 1 < valid ? p1 : 0.f;
-                                lacc0 = f32x2::add(lacc0, f32x2::pack(p0, p1));
-                                pk[j >> 1] = pack2<FP16>(p0, p1);
-                            }
+                    for (int j = 0; j < 32; j += 4) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl, -msl));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl, -msl));
+                        float p2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), sl, -msl));
+                        float p3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), sl, -msl));
+                        if (!full) {
+                            if (c + j >= it.kv_len) p0 = 0.f;
+                            if (c + j + 1 >= it.kv_len) p1 = 0.f;
+                            if (c + j + 2 >= it.kv_len) p2 = 0.f;
+                            if (c + j + 3 >= it.kv_len) p3 = 0.f;
                         }
-                        tmem_st_32x32b_x16(tS + (c >> 1), pk);
-                    };
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        pk[j >> 1] = pack2<FP16>(p0, p1);
+                        pk[(j >> 1) + 1] = pack2<FP16>(p2, p3);
+                    }
+                    tmem_st_32x32b_x16(tS + (c >> 1), pk);
+                };
+                if (!(dbg & 4)) {
                     ptx::tmem_ld_32x32b_x32(tS, v0);
                     for (int c = 0; c < n1p; c += 64) {
                         ptx::tmem_ld_wait();
@@ -359,9 +343,6 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         emit_p(v1, c + 32);
                     }
                 }
-                float l0, l1, l2, l3;
-                f32x2::unpack(lacc0, l0, l1);
-                f32x2::unpack(lacc1, l2, l3);
                 const float l_ctx = (l0 + l1) + (l2 + l3);
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
