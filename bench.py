@@ -370,7 +370,7 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", type=int, default=250)
     ap.add_argument("--mode", default="packed", choices=["packed", "dense"], help="packed = prefix-shared rows (default); dense = one 256-row sequence per candidate, as the reference computes it")
     ap.add_argument("--images-per-step", type=int, default=8)
-    ap.add_argument("--cpu-sample", type=int, default=50)
+    ap.add_argument("--cpu-sample", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
