@@ -106,7 +106,7 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1 && ptx::elect_one()) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], ep.a_multicast ? CS : 1);   // multicast A: a slot is reusable once EVERY CTA of the cluster has read it
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
@@ -138,7 +138,11 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     if (!RES16 || kb < num_k) {
-                        ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
+                        // the CS CTAs of the cluster multiply the SAME 128 x 64 activation box: CTA kb % CS fetches it once and
+                        // multicasts it into every CTA's slot (data and mbarrier bytes land at the same CTA-relative offsets)
+                        if (!ep.a_multicast) ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
+                        else if (kb % CS == static_cast<int>(rank))
+                            ptx::tma_load_2d_mc(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0, static_cast<uint16_t>((1u << CS) - 1u));
                         ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
                     } else {      // residual columns n0 + 64 j .. against identity columns 64 j ..
                         const int j = kb - num_k;
@@ -170,7 +174,8 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
-                    ptx::umma_commit(&empty_bar[stage]);
+                    if (ep.a_multicast) ptx::umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CS) - 1u));
+                    else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(&tfull_bar[acc]);
@@ -498,8 +503,13 @@ bool gemm_umma_ln_supported(int N, int K, const GemmLnEpilogue& ep) {
            (ep.out_lp == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_lp) & 7) == 0 && (ep.ldo_lp & 3) == 0));
 }
 
-int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmLnEpilogue& ep, cudaStream_t stream) {
-    UNIMM_CHECK(M > 0 && gemm_umma_ln_supported(N, K, ep), "LayerNorm-fused GEMM: N must be 768 or 1024, K a multiple of 64, pointers 16-byte aligned");
+int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmLnEpilogue& ep_in, cudaStream_t stream) {
+    UNIMM_CHECK(M > 0 && gemm_umma_ln_supported(N, K, ep_in), "LayerNorm-fused GEMM: N must be 768 or 1024, K a multiple of 64, pointers 16-byte aligned");
+    // measured on B200 (profiles/r01_v8): sharing the activation box across the 3 CTAs by multicast couples their pipelines and
+    // costs 2-4 % on FFN-2 + LN, more than the saved L2 traffic returns; kept as an opt-in (UNIMM_LN_MULTICAST=1)
+    static const bool mc_enabled = getenv("UNIMM_LN_MULTICAST") != nullptr && atoi(getenv("UNIMM_LN_MULTICAST")) != 0;
+    GemmLnEpilogue ep = ep_in;
+    ep.a_multicast = ep.a_multicast && mc_enabled;
     if (ep.residual_lp != nullptr) {
         if (N == 768) return launch_ln<3, true>(A, lda, W, ldw, M, K, ep, stream);
         return launch_ln<4, true>(A, lda, W, ldw, M, K, ep, stream);

@@ -50,6 +50,7 @@ struct GemmLnEpilogue {
     bf16* out_lp = nullptr;           // [M, ldo_lp] 16-bit GEMM-operand copy (optional)
     int ldo_lp = 0;
     int lp_kind = LP_BF16;
+    bool a_multicast = true;          // the cluster's CTAs share the activation box by TMA multicast (UNIMM_LN_MULTICAST=0 disables)
 };
 // W must be the row-permuted copy produced by permute_weight_rows_ln (see gemm_umma_ln.cu: the permutation makes each
 // thread's tcgen05.ld fragment 8 consecutive output columns).
