@@ -214,7 +214,8 @@ int unimm_k_lm_head_lp(const void* d_H_lp, int ldh, const void* d_E_lp, int lde,
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
                       void* d_y_lp, int lp_kind, void* stream);
 int unimm_k_cast_lp(const float* d_src, void* d_dst_lp, int64_t n, int lp_kind, void* stream);
-/* elem_kind = 0: fp32 tensors, 1: bf16, 2: fp16.  impl: 0 = CUDA-core kernel, 1 = tensor-core kernel (16-bit only). */
+/* unimm_k_attention (dense [B, S] layout): elem_kind = 0: fp32 tensors, 1: bf16, 2: fp16.  impl: 0 = CUDA-core kernel, 1 = mma.sync kernel (16-bit),
+ * 2 = tcgen05 / TMEM kernel (16-bit, text self-attention with descriptor masks, D = 64, S <= 256). */
 /* Attention over PACKED rows as a job list (csrc/attention_jobs.cu): every job = (q_start, q_len, kv_start, kv_len, win, mask_row, -, -);
  * rows of win jobs additionally attend [lo, hi) U {self} from d_row_iv[row] = (lo, hi, self, -).  16-bit tensors only.
  * impl 0 = generic job kernel, 1 = persistent mma.sync candidate kernel, 2 = tcgen05 / TMEM candidate kernel

@@ -232,7 +232,7 @@ ELEM = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}
 ATOL = {0: 2e-5, 1: 3e-2, 2: 4e-3}
 
 
-@pytest.mark.parametrize("kind,impl", [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1)])
+@pytest.mark.parametrize("kind,impl", [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1), (1, 2), (2, 2)])     # impl 2 = tcgen05 / TMEM
 def test_text_self_attention(kind, impl):
     desc = make_desc()
     B, S, heads, d = desc.shape[0], 256, 12, 64

@@ -90,20 +90,29 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 }
 
 struct Item {
-    int q_start, q_len, kv_start, kv_len, head, n_tiles, nkb;
+    int q_start, q_len, kv_start, kv_len, head, n_tiles, nkb, job;
 };
 __device__ __forceinline__ Item load_item(const AttnJobsArgs& a, int item) {
     Item it;
     const int job = item / a.heads;
     it.head = item - job * a.heads;
-    const int4 j = *reinterpret_cast<const int4*>(a.jobs + static_cast<size_t>(job) * 8);
-    it.q_start = j.x; it.q_len = j.y; it.kv_start = j.z; it.kv_len = j.w;
+    it.job = job;
+    if (a.jobs == nullptr) {      // dense layout: job = sequence, its seq_len rows are queries and keys
+        it.q_start = job * a.seq_len; it.q_len = a.seq_len; it.kv_start = it.q_start; it.kv_len = a.seq_len;
+    } else {
+        const int4 j = *reinterpret_cast<const int4*>(a.jobs + static_cast<size_t>(job) * 8);
+        it.q_start = j.x; it.q_len = j.y; it.kv_start = j.z; it.kv_len = j.w;
+    }
     it.n_tiles = (it.q_len + TQ - 1) / TQ;
     it.nkb = (it.kv_len + BOXR - 1) / BOXR;
     return it;
 }
 
-template <bool FP16>
+// DENSE = true: the dense [B, S <= 256] layout (discriminative scoring, training forward): item = (sequence, head), the
+// sequence's own S rows are the "context" keys, the allowed columns of a row come from its descriptor (text_row_interval:
+// generative / discriminative masks of utils/data_utils.py:149-210, :300-354; padding rows attend everything, exactly like the
+// reference's additive -10000), and there is no own-candidate part and no window ring.
+template <bool FP16, bool DENSE>
 __global__ void __launch_bounds__(384, 1)
 attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKw,
@@ -154,12 +163,14 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     ptx::mbar_arrive_expect_tx(&bars[Q_FULL + b], 2 * BOXB);
                     ptx::tma_load_2d(smem + Q_OFF + b * 2 * BOXB, &tmQ, &bars[Q_FULL + b], col, r0);
                     ptx::tma_load_2d(smem + Q_OFF + b * 2 * BOXB + BOXB, &tmQ, &bars[Q_FULL + b], col, r0 + BOXR);
-                    ptx::mbar_wait(&bars[W_FREE + b], ph ^ 1);
-                    ptx::mbar_arrive_expect_tx(&bars[W_FULL + b], 2 * WSTAGE);
+                    if (!DENSE) {
+                        ptx::mbar_wait(&bars[W_FREE + b], ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&bars[W_FULL + b], 2 * WSTAGE);
 #pragma unroll
-                    for (int j = 0; j < WBOX; ++j) {
-                        ptx::tma_load_2d(smem + KW_OFF + b * WSTAGE + j * WBOXB, &tmKw, &bars[W_FULL + b], col, r0 - HALO + j * WBOXR);
-                        ptx::tma_load_2d(smem + VW_OFF + b * WSTAGE + j * WBOXB, &tmVw, &bars[W_FULL + b], col, r0 - HALO + j * WBOXR);
+                        for (int j = 0; j < WBOX; ++j) {
+                            ptx::tma_load_2d(smem + KW_OFF + b * WSTAGE + j * WBOXB, &tmKw, &bars[W_FULL + b], col, r0 - HALO + j * WBOXR);
+                            ptx::tma_load_2d(smem + VW_OFF + b * WSTAGE + j * WBOXB, &tmVw, &bars[W_FULL + b], col, r0 - HALO + j * WBOXR);
+                        }
                     }
                 }
             }
@@ -264,6 +275,13 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 const uint32_t tS = tmem_base + b * 256 + lane_off;
                 const uint32_t ost = smem_base + OST_OFF + (warp - 4) * 4096;   // this warp's 32 rows x 128 B stash / staging block
 
+                // allowed context columns of this thread's row: [c_lo, c_hi) U {c_self}
+                int c_lo = 0, c_hi = it.kv_len, c_self = -1;
+                if (DENSE) {
+                    const int r = t * TQ + qd * 32 + lane;
+                    text_row_interval(a.desc[it.job], r, a.seq_len, c_lo, c_hi, c_self);
+                    if (c_hi <= c_lo && c_self < 0) { c_lo = 0; c_hi = a.seq_len; }      // padding row: softmax over the raw scores
+                }
                 ptx::mbar_wait(&bars[S_FULL + b], ph);
                 ptx::tc_fence_after();
 
@@ -271,7 +289,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 float mx = -INFINITY;
                 uint32_t v0[32], v1[32];
                 auto fold_max = [&](const uint32_t* v, int c) {
-                    if (c + 32 <= it.kv_len) {
+                    if (c >= c_lo && c + 32 <= c_hi) {
                         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -282,7 +300,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (c + j < it.kv_len) mx = fmaxf(mx, __uint_as_float(v[j]));
+                            if ((c + j >= c_lo && c + j < c_hi) || c + j == c_self) mx = fmaxf(mx, __uint_as_float(v[j]));
                     }
                 };
                 if (dbg & 2) mx = 0.f;
@@ -304,7 +322,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const int r = min(r0 + qd * 32 + mt * 16 + g + 8 * hh, q_end - 1);
-                        iv[mt][hh] = *reinterpret_cast<const int4*>(a.row_iv + static_cast<size_t>(r) * 4);
+                        iv[mt][hh] = DENSE ? make_int4(0, 0, -1, 0) : *reinterpret_cast<const int4*>(a.row_iv + static_cast<size_t>(r) * 4);
                     }
                 const float m_ctx = mx;
                 const float msl = m_ctx * sl;
@@ -313,7 +331,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 auto emit_p = [&](const uint32_t* v, int c) {
                     uint32_t pk[16];
-                    const bool full = c + 32 <= it.kv_len;
+                    const bool full = c >= c_lo && c + 32 <= c_hi;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl, -msl));
@@ -321,10 +339,11 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         float p2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), sl, -msl));
                         float p3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), sl, -msl));
                         if (!full) {
-                            if (c + j >= it.kv_len) p0 = 0.f;
-                            if (c + j + 1 >= it.kv_len) p1 = 0.f;
-                            if (c + j + 2 >= it.kv_len) p2 = 0.f;
-                            if (c + j + 3 >= it.kv_len) p3 = 0.f;
+                            const int cj = c + j;
+                            if (!((cj >= c_lo && cj < c_hi) || cj == c_self)) p0 = 0.f;
+                            if (!((cj + 1 >= c_lo && cj + 1 < c_hi) || cj + 1 == c_self)) p1 = 0.f;
+                            if (!((cj + 2 >= c_lo && cj + 2 < c_hi) || cj + 2 == c_self)) p2 = 0.f;
+                            if (!((cj + 3 >= c_lo && cj + 3 < c_hi) || cj + 3 == c_self)) p3 = 0.f;
                         }
                         l0 += p0; l1 += p1; l2 += p2; l3 += p3;
                         pk[j >> 1] = pack2<FP16>(p0, p1);
@@ -350,8 +369,18 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 if (lane == 0) ptx::mbar_arrive(&bars[P_FULL + b]);
 
                 // ---- (3) own-candidate part with mma.sync while the PV MMA runs: keys = window rows [rowbase, rowbase + 48)
-                ptx::mbar_wait(&bars[Q_FULL + b], ph);
-                ptx::mbar_wait(&bars[W_FULL + b], ph);
+                // rows without own keys (context rows scored in the same launch, the dense layout): nothing to do for the warp
+                bool any_own = false;
+                if (!DENSE) {
+                    bool mine = false;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) mine |= iv[mt][hh].y > iv[mt][hh].x || iv[mt][hh].z >= 0;
+                    any_own = __any_sync(0xffffffffu, mine) && !(dbg & 1);
+                    ptx::mbar_wait(&bars[Q_FULL + b], ph);
+                    ptx::mbar_wait(&bars[W_FULL + b], ph);
+                }
                 const uint32_t qs = smem_base + Q_OFF + b * 2 * BOXB;
                 const uint32_t kw = smem_base + KW_OFF + b * WSTAGE;
                 const uint32_t vw = smem_base + VW_OFF + b * WSTAGE;
@@ -359,7 +388,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 float m_own[2][2], l_own[2][2];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
-                    if (dbg & 1) {
+                    if (!any_own) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o_own[mt][i][0] = o_own[mt][i][1] = o_own[mt][i][2] = o_own[mt][i][3] = 0.f;
                         m_own[mt][0] = m_own[mt][1] = -INFINITY; l_own[mt][0] = l_own[mt][1] = 0.f;
@@ -434,7 +463,10 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     }
                 }
                 __syncwarp();
-                if (lane == 0) { ptx::mbar_arrive(&bars[Q_FREE + b]); ptx::mbar_arrive(&bars[W_FREE + b]); }
+                if (lane == 0) {
+                    ptx::mbar_arrive(&bars[Q_FREE + b]);            // (S_FULL was awaited above: the QK MMA has read Q)
+                    if (!DENSE) ptx::mbar_arrive(&bars[W_FREE + b]);
+                }
 
                 // ---- (4) O = P V from TMEM in the mma fragment arrangement, merge with the stashed own part, normalise
                 ptx::mbar_wait(&bars[O_FULL + b], ph);
@@ -494,7 +526,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
-template <bool FP16>
+template <bool FP16, bool DENSE>
 int launch_umma(const AttnJobsArgs& a, cudaStream_t stream) {
     CUtensorMap tmQ, tmK, tmV, tmKw, tmVw;
     const int W = a.heads * 64;
@@ -505,13 +537,13 @@ int launch_umma(const AttnJobsArgs& a, cudaStream_t stream) {
     UNIMM_TRY(gemm_make_map(a.v, a.n_rows, W, a.ldv, WBOXR, &tmVw));
     static bool attr_set = false;
     if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cand_umma_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cand_umma_kernel<FP16, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     const int n_items = a.n_jobs * a.heads;
     const int grid = n_items < gemm_num_sms() ? n_items : gemm_num_sms();
     static int dbg = getenv("UNIMM_ATTN_DBG") ? atoi(getenv("UNIMM_ATTN_DBG")) : 0;   // timing experiments only (results invalid)
-    attn_cand_umma_kernel<FP16><<<grid, 384, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmKw, tmVw, a, n_items, dbg);
+    attn_cand_umma_kernel<FP16, DENSE><<<grid, 384, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmKw, tmVw, a, n_items, dbg);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -810,7 +842,20 @@ bool attention_candidates_umma_supported(const AttnJobsArgs& a, int halo) {
 // candidate jobs (win = 1, D = 64, 16-bit, halo <= 16) on tcgen05: see the header of this file
 int attention_candidates_umma(const AttnJobsArgs& a, int halo, cudaStream_t stream) {
     UNIMM_CHECK(a.n_jobs > 0 && attention_candidates_umma_supported(a, halo), "tcgen05 candidate attention: unsupported arguments");
-    return a.lp_kind == LP_FP16 ? launch_umma<true>(a, stream) : launch_umma<false>(a, stream);
+    return a.lp_kind == LP_FP16 ? launch_umma<true, false>(a, stream) : launch_umma<false, false>(a, stream);
+}
+
+bool attention_dense_umma_supported(const AttnJobsArgs& a) {
+    auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return a.D == 64 && a.seq_len > 0 && a.seq_len <= 256 && a.desc != nullptr && a.n_rows == a.n_jobs * a.seq_len && (a.ldq % 8) == 0 &&
+           (a.ldk % 8) == 0 && (a.ldv % 8) == 0 && (a.ldo % 8) == 0 && a16(a.q) && a16(a.k) && a16(a.v) && a16(a.o);
+}
+// text self-attention of the dense [B, S] layout under the descriptor masks on tcgen05 (n_jobs = B sequences, jobs = nullptr)
+int attention_dense_umma(const AttnJobsArgs& a_in, cudaStream_t stream) {
+    AttnJobsArgs a = a_in;
+    a.jobs = nullptr;
+    UNIMM_CHECK(a.n_jobs > 0 && attention_dense_umma_supported(a), "tcgen05 dense attention: unsupported arguments");
+    return a.lp_kind == LP_FP16 ? launch_umma<true, true>(a, stream) : launch_umma<false, true>(a, stream);
 }
 
 }  // namespace unimm

@@ -98,6 +98,7 @@ struct unimm_engine {
     ActBuf vhead_h;
     float* v_logits = nullptr;
     int* err_flag = nullptr;
+    int* dense_jobs = nullptr;     // [Bmax, 8] text -> image jobs of the dense layout: (b*S, S, b*R, R, 0, b, 0, 0)
     // host staging for unimm_score_host
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -381,6 +382,15 @@ int unimm_engine::alloc_workspace() {
     if (lp()) UNIMM_TRY(dalloc(&vhead_h.h, Mv * Hv));
     UNIMM_TRY(dalloc(&v_logits, Mv * c.v_target_size));
     UNIMM_TRY(dalloc(&err_flag, 4));
+    {
+        std::vector<int> jobs(static_cast<size_t>(Bmax) * 8, 0);
+        for (int b = 0; b < Bmax; ++b) {
+            int* j = &jobs[static_cast<size_t>(b) * 8];
+            j[0] = b * c.seq_len; j[1] = c.seq_len; j[2] = b * c.num_regions; j[3] = c.num_regions; j[4] = 0; j[5] = b;
+        }
+        UNIMM_TRY(dalloc(&dense_jobs, jobs.size()));
+        UNIMM_CUDA_CHECK(cudaMemcpy(dense_jobs, jobs.data(), jobs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -442,6 +452,20 @@ int unimm_engine::attention(const void* q, int ldq, const void* k, int ldk, cons
     a.scale = 1.0f / sqrtf(static_cast<float>(D));
     a.lp_kind = lp_kind();
     Prof prof(this, CAT_ATTN, 4.0 * B * heads * static_cast<double>(Sq) * Skv * D, st);
+    if (lp() && attn_umma) {
+        AttnJobsArgs j;
+        j.q = q; j.ldq = ldq; j.k = k; j.ldk = ldk; j.v = v; j.ldv = ldv; j.o = o; j.ldo = ldo;
+        j.heads = heads; j.D = D; j.jobs = nullptr; j.n_jobs = B; j.max_q_len = Sq; j.kv_cap = Skv <= 64 ? 64 : 256; j.win_cap = 0;
+        j.row_iv = nullptr; j.key_mask = nullptr; j.key_mask_ld = 0; j.scale = a.scale; j.lp_kind = lp_kind();
+        if (mask_kind == MASK_TEXT_SELF && Sq == Skv) {          // text self-attention of the dense layout: tcgen05, masks from descriptors
+            j.n_rows = B * Sq; j.desc = desc; j.seq_len = Sq;
+            if (attention_dense_umma_supported(j)) return attention_dense_umma(j, st);
+        } else if (mask_kind == MASK_KEY_VECTOR && Sq == cfg.seq_len && Skv == cfg.num_regions && Sq > 64 && key_mask != nullptr) {
+            // text -> image: one job per sequence (rows b*S.., keys b*R.., mask row b)
+            j.jobs = dense_jobs; j.n_rows = B * Sq; j.n_kv_rows = B * Skv; j.key_mask = key_mask; j.key_mask_ld = Skv;
+            if (attention_cross_umma_supported(j)) return attention_cross_umma(j, st);
+        }
+    }
     return lp() ? attention_mma_lp(a, st) : attention_simt_f32(a, st);
 }
 
@@ -469,8 +493,23 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
     if (ac.pk != nullptr) {
         const unimm_packed_batch_t& pk = *ac.pk;
         if (text && lp() && D == 64) {
-            // context rows attend their context (plain jobs); candidate rows run the persistent double-buffered kernel
+            // tcgen05 path: context jobs and candidate jobs in ONE launch (context rows simply have no own-candidate keys)
             const int n_ctx = pk.n_jobs_text_ctx, n_cand = pk.n_jobs_text_self - pk.n_jobs_text_ctx;
+            {
+                AttnJobsArgs a;
+                a.q = qp; a.ldq = 3 * H; a.k = kp; a.ldk = 3 * H; a.v = vp; a.ldv = 3 * H; a.o = ctx; a.ldo = H;
+                a.heads = heads; a.D = D; a.jobs = pk.d_jobs_text_self; a.n_jobs = pk.n_jobs_text_self;
+                a.max_q_len = pk.max_q_text_self; a.kv_cap = pk.kv_cap_text; a.win_cap = pk.win_cap;
+                a.row_iv = pk.d_row_iv; a.key_mask = nullptr; a.key_mask_ld = 0;
+                a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind();
+                a.n_rows = M;
+                if (attn_umma && attention_candidates_umma_supported(a, pk.cand_halo)) {
+                    Prof prof(this, CAT_ATTN, 4.0 * heads * D * pk.pairs_text_self, st);
+                    UNIMM_TRY(attention_candidates_umma(a, pk.cand_halo, st));
+                    goto attention_done;
+                }
+            }
+            // mma.sync path: context rows attend their context (plain jobs); candidate rows run the persistent double-buffered kernel
             UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_text_self, n_ctx, pk.kv_cap_text,
                                        pk.kv_cap_text, 0, 0.0, ac, st));
             AttnJobsArgs a;
@@ -481,8 +520,7 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
             a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind();
             a.n_rows = M;
             Prof prof(this, CAT_ATTN, 4.0 * heads * D * pk.pairs_text_self, st);
-            if (attn_umma && attention_candidates_umma_supported(a, pk.cand_halo)) UNIMM_TRY(attention_candidates_umma(a, pk.cand_halo, st));
-            else UNIMM_TRY(attention_candidates(a, pk.cand_halo, st));
+            UNIMM_TRY(attention_candidates(a, pk.cand_halo, st));
         } else if (text) UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_text_self, pk.n_jobs_text_self,
                                                     pk.max_q_text_self, pk.kv_cap_text, pk.win_cap, pk.pairs_text_self, ac, st));
         else UNIMM_TRY(attention_packed(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, heads, D, pk.d_jobs_img_self, pk.n_jobs_img_self,
@@ -492,6 +530,7 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
         UNIMM_TRY(attention(qp, 3 * H, kp, 3 * H, vp, 3 * H, ctx, H, ac.B, heads, D, Sx, Sx, text ? MASK_TEXT_SELF : MASK_KEY_VECTOR,
                             text ? ac.desc : nullptr, text ? nullptr : ac.key_mask, st));
     }
+attention_done:
     ActBuf c;
     c.f = lp() ? nullptr : static_cast<float*>(ctx); c.h = lp() ? static_cast<bf16*>(ctx) : nullptr; c.ld = H;
     UNIMM_TRY(linear_ln(c, M, L.out, x.f, H, L.ln1, pre, x, st));
@@ -1123,6 +1162,15 @@ int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const 
         return attention_simt_f32(a, st);
     }
     a.lp_kind = elem_kind == 2 ? LP_FP16 : LP_BF16;
+    if (impl == 2) {          // tcgen05 kernel of the dense layout (text self-attention only)
+        UNIMM_CHECK(mask_kind == MASK_TEXT_SELF && Sq == Skv, "impl 2 is the dense text self-attention");
+        AttnJobsArgs j;
+        j.q = d_q; j.ldq = ldq; j.k = d_k; j.ldk = ldk; j.v = d_v; j.ldv = ldv; j.o = d_o; j.ldo = ldo;
+        j.heads = heads; j.D = D; j.jobs = nullptr; j.n_jobs = B; j.max_q_len = Sq; j.kv_cap = 256; j.win_cap = 0;
+        j.row_iv = nullptr; j.key_mask = nullptr; j.key_mask_ld = 0; j.scale = a.scale; j.lp_kind = a.lp_kind;
+        j.n_rows = B * Sq; j.desc = a.desc; j.seq_len = Sq;
+        return attention_dense_umma(j, st);
+    }
     return impl == 0 ? attention_simt_lp(a, st) : attention_mma_lp(a, st);
 }
 

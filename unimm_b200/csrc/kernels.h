@@ -133,6 +133,8 @@ struct AttnJobsArgs {
     int lp_kind;
     int n_rows = 0;        // rows of the q (and, for self-attention, k / v) matrices: TMA tensor extent of the tcgen05 kernels
     int n_kv_rows = 0;     // rows of the k / v matrices when they differ from q's (cross attention)
+    const SeqDesc* desc = nullptr;   // dense layout (attention_dense_umma): one descriptor per sequence
+    int seq_len = 0;                 //   rows per sequence (<= 256)
 };
 int attention_jobs(const AttnJobsArgs& a, bool fp32, cudaStream_t stream);
 // jobs that all have win = 1 (candidate rows over context + own rows), D = 64, 16-bit: persistent double-buffered kernel.
@@ -142,6 +144,9 @@ int attention_candidates(const AttnJobsArgs& a, int halo, cudaStream_t stream);
 // part with mma.sync on a TMA-staged window; needs halo <= 16 and a.n_rows
 bool attention_candidates_umma_supported(const AttnJobsArgs& a, int halo);
 int attention_candidates_umma(const AttnJobsArgs& a, int halo, cudaStream_t stream);
+// dense [B, seq_len] text self-attention under the descriptor masks on tcgen05 (a.desc, a.seq_len, a.n_jobs = B, a.n_rows = B * seq_len)
+bool attention_dense_umma_supported(const AttnJobsArgs& a);
+int attention_dense_umma(const AttnJobsArgs& a, cudaStream_t stream);
 // window-free jobs over <= 64 keys with D = 128 (text -> image co-attention) on tcgen05; needs n_rows and n_kv_rows
 bool attention_cross_umma_supported(const AttnJobsArgs& a);
 int attention_cross_umma(const AttnJobsArgs& a, cudaStream_t stream);
