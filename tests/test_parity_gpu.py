@@ -259,3 +259,28 @@ def test_prefix_shared_host_path(full_cfg):
     eng.score_packed_host(pb, score, nsp)
     np.testing.assert_allclose(score.numpy(), g["seq_score"], atol=1e-4, rtol=0)
     np.testing.assert_allclose(nsp.numpy(), g["nsp_scores"], atol=1e-4, rtol=0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_engines_on_two_devices_in_one_process():
+    """One handle per device inside ONE process (the reference's DataParallel threading model): per-device
+    kernel attributes, tensor maps and workspaces must not leak between devices."""
+    from unimm_b200 import synthetic as syn
+    from unimm_b200.config import tiny_config
+    from unimm_b200.weights import random_state_dict
+    cfg = tiny_config()
+    sd = random_state_dict(cfg, seed=3, perturbed=True)
+    rng = np.random.RandomState(0)
+    feat, loc, mask = (torch.from_numpy(a) for a in syn.synth_image(rng))
+    rnd = syn.encode_round_gen(syn.synth_context(rng, round_id=3), syn.synth_answers(rng, 6))
+    tokens, segments, positions, labels, desc, index = syn.stack_rounds([rnd])
+    outs = []
+    for dev in (1, 0):                                   # the SECOND device first: nothing may depend on device 0 having run
+        eng = Engine(cfg, sd, precision="fp16", max_sequences=8, device=dev)
+        o = eng.forward(tokens, segments, positions, desc, feat[None], loc[None], mask[None], feat_index=index,
+                        masked_lm_labels=labels, want=("seq_score",))
+        torch.cuda.synchronize(dev)
+        outs.append(o["seq_score"].cpu())
+        eng.close()
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])                # same kernels, same inputs: bit-identical across devices

@@ -199,11 +199,7 @@ attn_simt_kernel(AttnArgs a) {
 template <typename T, int D>
 int launch_simt(const AttnArgs& a, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (QT * D + KT * (D + 1) + KT * D + NW * RPW * KT);
-    static bool attr_set = false;
-    if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_simt_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_simt_kernel<T, D>), smem));
     dim3 grid((a.Sq + QT - 1) / QT, a.heads, a.B);
     UNIMM_CHECK(a.B <= 65535, "attention: batch too large for one launch");
     attn_simt_kernel<T, D><<<grid, NW * 32, smem, stream>>>(a);

@@ -465,11 +465,7 @@ template <bool FP16>
 int launch_cand(const AttnJobsArgs& a, int halo, cudaStream_t stream) {
     const size_t smem = sizeof(bf16) * (2 * static_cast<size_t>(a.kv_cap) + 2 * (128 + 2 * static_cast<size_t>(a.win_cap))) * (64 + PADE);
     UNIMM_CHECK(smem <= 227 * 1024, "candidate attention: staging does not fit shared memory");
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cand_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_cand_kernel<FP16>), smem));
     const int max_tiles = (a.max_q_len + 127) / 128;
     dim3 grid(max_tiles < 2 ? max_tiles : 2, a.heads, a.n_jobs);     // two CTAs share a unit's tiles: ~2 x heads x units CTAs
     attn_cand_kernel<FP16><<<grid, 256, smem, stream>>>(a, halo);
@@ -545,11 +541,7 @@ int launch_jobs(const AttnJobsArgs& a, cudaStream_t stream) {
     constexpr int MQT = 16 * NW;
     const size_t smem = sizeof(bf16) * (MQT + 2 * static_cast<size_t>(a.kv_cap + a.win_cap)) * (D + PADE);
     UNIMM_CHECK(smem <= 227 * 1024, "attention jobs: staged key range does not fit shared memory");
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_jobs_kernel<D, FP16, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_jobs_kernel<D, FP16, NW>), smem));
     dim3 grid((a.max_q_len + MQT - 1) / MQT, a.heads, a.n_jobs);
     attn_jobs_kernel<D, FP16, NW><<<grid, NW * 32, smem, stream>>>(a);
     UNIMM_LAUNCH_CHECK(1);

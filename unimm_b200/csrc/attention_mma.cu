@@ -240,11 +240,7 @@ int launch_mma(const AttnArgs& a, cudaStream_t stream) {
     constexpr int MQT = 16 * NW;
     const int kv_rows_max = ((a.Skv + MKT - 1) / MKT) * MKT;
     const size_t smem = sizeof(bf16) * (MQT + 2 * static_cast<size_t>(kv_rows_max)) * (D + PADE);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel<D, FP16, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_mma_kernel<D, FP16, NW>), smem));
     dim3 grid((a.Sq + MQT - 1) / MQT, a.heads, a.B);
     attn_mma_kernel<D, FP16, NW><<<grid, NW * 32, smem, stream>>>(a, kv_rows_max);
     UNIMM_LAUNCH_CHECK(1);

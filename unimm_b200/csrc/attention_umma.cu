@@ -535,11 +535,7 @@ int launch_umma(const AttnJobsArgs& a, cudaStream_t stream) {
     UNIMM_TRY(gemm_make_map(a.v, a.n_rows, W, a.ldv, BOXR, &tmV));
     UNIMM_TRY(gemm_make_map(a.k, a.n_rows, W, a.ldk, WBOXR, &tmKw));
     UNIMM_TRY(gemm_make_map(a.v, a.n_rows, W, a.ldv, WBOXR, &tmVw));
-    static bool attr_set = false;
-    if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cand_umma_kernel<FP16, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_cand_umma_kernel<FP16, DENSE>), SMEM_BYTES));
     const int n_items = a.n_jobs * a.heads;
     const int grid = n_items < gemm_num_sms() ? n_items : gemm_num_sms();
     static int dbg = getenv("UNIMM_ATTN_DBG") ? atoi(getenv("UNIMM_ATTN_DBG")) : 0;   // timing experiments only (results invalid)
@@ -819,11 +815,7 @@ int launch_cross(const AttnJobsArgs& a, cudaStream_t stream) {
     UNIMM_TRY(gemm_make_map(a.q, a.n_rows, W, a.ldq, TQ, &tmQ));
     UNIMM_TRY(gemm_make_map(a.k, a.n_kv_rows, W, a.ldk, 64, &tmK));
     UNIMM_TRY(gemm_make_map(a.v, a.n_kv_rows, W, a.ldv, 64, &tmV));
-    static bool attr_set = false;
-    if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(attn_cross_umma_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, x::XSMEM_BYTES));
-        attr_set = true;
-    }
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_cross_umma_kernel<FP16>), x::XSMEM_BYTES));
     const int n_items = a.n_jobs * a.heads;
     const int grid = n_items < gemm_num_sms() ? n_items : gemm_num_sms();
     attn_cross_umma_kernel<FP16><<<grid, 384, x::XSMEM_BYTES, stream>>>(tmQ, tmK, tmV, a, n_items);

@@ -49,6 +49,10 @@ void count_launches(int n);
         if (_rc != 0) return _rc;  \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: raise it once per (device, kernel) — a process may
+// hold engines on several devices (one handle per device) — and only upwards.  Thread-safe.
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 typedef __nv_bfloat16 bf16;
 
 constexpr int kWarp = 32;

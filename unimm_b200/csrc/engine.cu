@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,20 @@ void set_error(const std::string& msg) { g_error = msg; }
 const char* get_error() { return g_error.c_str(); }
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    int dev = 0;
+    UNIMM_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(mu);
+    size_t& have = done[{dev, kernel}];
+    if (bytes > have) {
+        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+        have = bytes;
+    }
+    return 0;
+}
 
 namespace {
 

@@ -537,13 +537,9 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     CUtensorMap tmA, tmB;
     UNIMM_TRY(make_map_bf16(A, M, K, lda, BM, &tmA));
     UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN / CL, &tmB));
-    static bool attr_set = false;
     static int max_clusters = 0;
     auto kernel = umma_gemm_kernel<BN, LSE, ST, FRAG, CL>;
-    if (!attr_set) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), Cfg::kSmemBytes));
     const int tiles = (((M + BM - 1) / BM + CL - 1) / CL) * ((N + BN - 1) / BN);
     if (CL == 1) {
         int grid = tiles < num_sms() ? tiles : num_sms();

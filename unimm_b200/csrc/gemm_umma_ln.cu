@@ -467,8 +467,8 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     cfg.blockDim = dim3(384, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&umma_gemm_ln_kernel<CS, RES16>), Cfg::kSmemBytes));
     if (max_clusters == 0) {
-        UNIMM_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_ln_kernel<CS, RES16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         cfg.gridDim = dim3((gemm_num_sms() / CS) * CS, 1, 1);
         int n = 0;
         UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, umma_gemm_ln_kernel<CS, RES16>, &cfg));
