@@ -36,11 +36,11 @@ constexpr int BM = 128;
 constexpr int BK = 64;      // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;  // fixed for 16-bit inputs
 
-template <int BN, int ST = 0>
+template <int BN, int ST = 0, bool SM2 = false>
 struct GemmCfg {
-    static constexpr int kStages = ST > 0 ? ST : ((BN == 256) ? 4 : 6);
+    static constexpr int kStages = ST > 0 ? ST : ((BN == 256 && !SM2) ? 4 : 6);
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (SM2 ? BN / 2 : BN) * BK * 2;     // a CTA pair keeps half of the W box in each CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
@@ -49,11 +49,16 @@ struct GemmCfg {
 // CL = 2: two CTAs of a cluster work on vertically adjacent 128-row tiles of the same BN columns and each loads only half
 // of the shared W box, multicast into both CTAs' shared memory (operand traffic from L2 per CTA: 32 KB instead of 48 KB per
 // k-block at BN = 256); a ring slot is reusable once BOTH CTAs' MMAs have read it (empty barriers count 2, multicast commit).
+// CL = 3: the same two CTAs as ONE cta_group::2 MMA (M = 256 across the two SMs): each CTA holds only its half of the W box
+// (no duplicate in shared memory, half the operand reads per SM), the leader CTA issues tcgen05.mma.cta_group::2 for both,
+// both CTAs' TMA loads complete on the leader's full barrier, commits are multicast to both CTAs.
 template <int BN, bool LSE, int ST = 0, bool FRAG = false, int CL = 1>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue ep) {
-    using Cfg = GemmCfg<BN, ST>;
+    constexpr bool SM2 = CL == 3;
+    constexpr int CS = CL == 1 ? 1 : 2;                      // CTAs per cluster
+    using Cfg = GemmCfg<BN, ST, SM2>;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte aligned bases
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,13 +74,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_m = ((M + BM - 1) / BM + CL - 1) / CL;     // row blocks of CL x 128 rows (a padding tile is all out of bounds)
+    const int num_m = ((M + BM - 1) / BM + CS - 1) / CS;     // row blocks of CS x 128 rows (a padding tile is all out of bounds)
     const int num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_k = K / BK;
-    const uint32_t crank = CL > 1 ? ptx::cluster_ctarank() : 0u;
-    const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;
-    constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
+    const uint32_t crank = CS > 1 ? ptx::cluster_ctarank() : 0u;
+    const int first_tile = blockIdx.x / CS, tile_step = gridDim.x / CS;
+    constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1u);
 
     if (warp == 0 && ptx::elect_one()) {
         ptx::prefetch_tensormap(&tmA);
@@ -84,17 +89,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1 && ptx::elect_one()) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], CL);
+            ptx::mbar_init(&empty_bar[s], CL == 2 ? 2 : 1);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], 8);  // one arrival per epilogue warp
+            ptx::mbar_init(&tempty_bar[a], SM2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs for a CTA pair)
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (warp == 2) {
+        if (SM2) ptx::tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+        else ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
     ptx::tc_fence_before();
-    if (CL > 1) ptx::cluster_sync_all();   // the peer's barriers exist before anything arrives on them remotely
+    if (CS > 1) ptx::cluster_sync_all();   // the peer's barriers exist before anything arrives on them remotely
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -105,10 +113,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-                const int m0 = ((tile / num_n) * CL + static_cast<int>(crank)) * BM;
+                const int m0 = ((tile / num_n) * CS + static_cast<int>(crank)) * BM;
                 const int n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_k; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (SM2) {
+                        // both CTAs' boxes are counted on the leader's barrier, which the leader arms for the pair
+                        if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0 + static_cast<int>(crank) * (BN / 2));
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
                     if (CL == 1) ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
@@ -120,8 +136,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (ptx::elect_one()) {
-            const uint32_t idesc = ptx::make_idesc_f16(BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u);
+        if (ptx::elect_one() && (!SM2 || crank == 0)) {
+            const uint32_t idesc = ptx::make_idesc_f16(SM2 ? 2 * BM : BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -138,13 +154,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-                        ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (SM2) ptx::umma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     if (CL == 1) ptx::umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
-                    else ptx::umma_commit_mc(&empty_bar[stage], kMask);  // ... in both CTAs (the peer multicasts into this slot too)
+                    else if (CL == 2) ptx::umma_commit_mc(&empty_bar[stage], kMask);  // ... in both CTAs (the peer multicasts into this slot too)
+                    else ptx::umma_commit_2sm_mc(&empty_bar[stage], kMask);   // both CTAs' producers may refill their halves
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+                if (SM2) ptx::umma_commit_2sm_mc(&tfull_bar[acc], kMask);   // both CTAs' epilogues own half of the 256 rows
+                else ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -168,11 +187,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool lp_only = fast_ok && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && (N % 64) == 0 &&
                              (ep.ldo_bf16 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0;
         // FRAG instantiation: the host has checked lp_only && w_perm16 && N % 32 == 0 (launch()); the other paths are compiled out
+        // the accumulator pair is handed back to the MMA warp of the LEADER CTA
+        auto arrive_tempty = [&](uint64_t* bar) {
+            if (SM2 && crank != 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(bar), 0));
+            else ptx::mbar_arrive(bar);
+        };
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int tn = tile % num_n;
-            const int m0 = ((tile / num_n) * CL + static_cast<int>(crank)) * BM;
+            const int m0 = ((tile / num_n) * CS + static_cast<int>(crank)) * BM;
             const int n0 = tn * BN + half * HALF_N;
             const int row = m0 + ew * 32 + lane;
             const bool row_ok = row < M;
@@ -236,7 +260,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) arrive_tempty(&tempty_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
                 continue;
@@ -445,15 +469,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // hand the accumulator back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) arrive_tempty(&tempty_bar[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
     ptx::tc_fence_before();
-    if (CL > 1) ptx::cluster_sync_all();   // no CTA leaves while its peer may still multicast into its shared memory / barriers
+    if (CS > 1) ptx::cluster_sync_all();   // no CTA leaves while its peer may still multicast into its shared memory / barriers
     else __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (warp == 2) {
+        if (SM2) ptx::tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+        else ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -533,14 +560,15 @@ int num_sms() {
 template <int BN, bool LSE, int ST = 0, bool FRAG = false, int CL = 1>
 int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int max_ctas,
            cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, ST>;
+    constexpr int CS = CL == 1 ? 1 : 2;
+    using Cfg = GemmCfg<BN, ST, CL == 3>;
     CUtensorMap tmA, tmB;
     UNIMM_TRY(make_map_bf16(A, M, K, lda, BM, &tmA));
-    UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN / CL, &tmB));
+    UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN / CS, &tmB));
     static int max_clusters = 0;
     auto kernel = umma_gemm_kernel<BN, LSE, ST, FRAG, CL>;
     UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), Cfg::kSmemBytes));
-    const int tiles = (((M + BM - 1) / BM + CL - 1) / CL) * ((N + BN - 1) / BN);
+    const int tiles = (((M + BM - 1) / BM + CS - 1) / CS) * ((N + BN - 1) / BN);
     if (CL == 1) {
         int grid = tiles < num_sms() ? tiles : num_sms();
         if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
@@ -550,7 +578,7 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     }
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cudaLaunchConfig_t cfg = {};
@@ -560,15 +588,15 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (max_clusters == 0) {
-        cfg.gridDim = dim3(num_sms() / CL * CL, 1, 1);
+        cfg.gridDim = dim3(num_sms() / CS * CS, 1, 1);
         int n = 0;
         UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
         UNIMM_CHECK(n > 0, "no co-resident cluster fits the multicast GEMM");
-        max_clusters = n < num_sms() / CL ? n : num_sms() / CL;
+        max_clusters = n < num_sms() / CS ? n : num_sms() / CS;
     }
     int clusters = tiles < max_clusters ? tiles : max_clusters;
-    if (max_ctas > 0 && clusters > max_ctas / CL) clusters = max_ctas / CL > 0 ? max_ctas / CL : 1;
-    cfg.gridDim = dim3(clusters * CL, 1, 1);
+    if (max_ctas > 0 && clusters > max_ctas / CS) clusters = max_ctas / CS > 0 ? max_ctas / CS : 1;
+    cfg.gridDim = dim3(clusters * CS, 1, 1);
     UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, M, N, K, ep));
     UNIMM_LAUNCH_CHECK(1);
     return 0;
@@ -587,11 +615,16 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     const bool lse = ep.partials != nullptr;
     if (tile_n == 0) tile_n = (N % 256 == 0 || N > 2048) ? 256 : 128;
     // tall problems (every SM gets several row blocks): CTA pairs sharing the W tile by TMA multicast
-    static const bool mc_enabled = getenv("UNIMM_GEMM_MULTICAST") == nullptr || atoi(getenv("UNIMM_GEMM_MULTICAST")) != 0;
-    const bool mc = mc_enabled && M >= 8192 && ep.debug_mode == 0;
+    // UNIMM_GEMM_MULTICAST: 0 = independent CTAs, 1 = CTA pairs sharing W by multicast, 2 = CTA pairs as one cta_group::2 MMA
+    // (measured, profiles/r01_v8: mode 2 is +3..9 % per projection GEMM over mode 1 and on par with / above cuBLAS; the LM head's
+    // log-sum-exp epilogue is the slower side there and prefers mode 1)
+    static const int pair_mode = getenv("UNIMM_GEMM_MULTICAST") == nullptr ? 2 : atoi(getenv("UNIMM_GEMM_MULTICAST"));
+    const bool tall = M >= 8192 && ep.debug_mode == 0;
+    const bool mc = pair_mode == 1 && tall;
+    const bool sm2 = pair_mode == 2 && tall;
     if (lse) {
         UNIMM_CHECK(tile_n == 256, "LSE epilogue uses 256-wide vocabulary tiles");
-        if (mc) return launch<256, true, 0, false, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+        if (mc || sm2) return launch<256, true, 0, false, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         return launch<256, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     }
     if (tile_n == 256 && ep.debug_mode >= 4) {   // microbenchmark: 3-stage ring, epilogue mode = debug_mode - 4
@@ -605,10 +638,12 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
                         a16(ep.out_bf16) && (ep.bias == nullptr || a16(ep.bias)) && ep.debug_mode == 0,
                     "fragment-ordered weights need a 16-bit-only, 16-byte aligned output with N % 32 == 0");
         if (tile_n == 256 && mc) return launch<256, false, 0, true, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+        if (tile_n == 256 && sm2) return launch<256, false, 0, true, 3>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         if (tile_n == 256) return launch<256, false, 0, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         return launch<128, false, 0, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     }
     if (tile_n == 256 && mc) return launch<256, false, 0, false, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
+    if (tile_n == 256 && sm2) return launch<256, false, 0, false, 3>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     if (tile_n == 256) return launch<256, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     UNIMM_CHECK(tile_n == 128, "umma gemm: tile_n must be 128 or 256");
     return launch<128, false>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
