@@ -46,14 +46,14 @@ namespace unimm {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int IDN = 256;           // the identity operand (largest column block per CTA)
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr float kLnEps = 1e-12f;   // BertLayerNorm eps (reference models/vilbert_dialog.py:322)
 
-template <int CS>
+template <int CS, int BN>
 struct LnCfg {
-    static constexpr int kStages = 4;
+    static constexpr int kStages = BN == 256 ? 4 : 5;
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -69,11 +69,13 @@ struct LnCfg {
 //                the residual tile R[128 x 256] (TMA box from tmR) by a (row-permuted) 256 x 256 identity (tmI) and
 //                accumulate in fp32 — no register traffic, no latency-exposed loads, the epilogue never touches global
 //                memory except for its stores.  Costs 256 extra K per tile (+33 % MMA work at K = 768, +8 % at 3072).
-template <int CS, bool RES16>
+// BN = columns per CTA: 256 (N = 768 as 3 CTAs, N = 1024 as 4) or 192 (N = 768 as 4 CTAs: clusters of 4 tile all 148 SMs, clusters
+// of 3 only 135 of them).
+template <int CS, bool RES16, int BN>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmI, int M, int K, GemmLnEpilogue ep) {
-    using Cfg = LnCfg<CS>;
+    using Cfg = LnCfg<CS, BN>;
     constexpr int N = CS * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -421,7 +423,7 @@ __global__ void permute_rows_kernel(const uint4* __restrict__ src, uint4* __rest
 // residual column ln_weight_row(p)); built once per device and encoding
 __global__ void identity_kernel(uint16_t* I, uint16_t one) {
     const int p = blockIdx.x;
-    for (int k = threadIdx.x; k < BN; k += blockDim.x) I[p * BN + k] = (k == ln_weight_row(p)) ? one : uint16_t(0);
+    for (int k = threadIdx.x; k < IDN; k += blockDim.x) I[p * IDN + k] = (k == ln_weight_row(p)) ? one : uint16_t(0);
 }
 int identity_for(int lp_kind, const bf16** out) {
     static const bf16* cache[16][2] = {};
@@ -431,8 +433,8 @@ int identity_for(int lp_kind, const bf16** out) {
     const int kind = lp_kind == LP_FP16 ? 1 : 0;
     if (cache[dev][kind] == nullptr) {
         void* p = nullptr;
-        UNIMM_CUDA_CHECK(cudaMalloc(&p, BN * BN * 2));
-        identity_kernel<<<BN, 128>>>(static_cast<uint16_t*>(p), kind ? uint16_t(0x3C00) : uint16_t(0x3F80));
+        UNIMM_CUDA_CHECK(cudaMalloc(&p, IDN * IDN * 2));
+        identity_kernel<<<IDN, 128>>>(static_cast<uint16_t*>(p), kind ? uint16_t(0x3C00) : uint16_t(0x3F80));
         UNIMM_CUDA_CHECK(cudaDeviceSynchronize());
         cache[dev][kind] = static_cast<const bf16*>(p);
     }
@@ -440,9 +442,9 @@ int identity_for(int lp_kind, const bf16** out) {
     return 0;
 }
 
-template <int CS, bool RES16>
+template <int CS, bool RES16, int BN>
 int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const GemmLnEpilogue& ep, cudaStream_t stream) {
-    using Cfg = LnCfg<CS>;
+    using Cfg = LnCfg<CS, BN>;
     CUtensorMap tmA, tmB, tmR, tmI;
     UNIMM_TRY(gemm_make_map(A, M, K, lda, BM, &tmA));
     UNIMM_TRY(gemm_make_map(W, CS * BN, K, ldw, BN, &tmB));
@@ -450,7 +452,7 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
         const bf16* ident = nullptr;
         UNIMM_TRY(identity_for(ep.lp_kind, &ident));
         UNIMM_TRY(gemm_make_map(ep.residual_lp, M, CS * BN, ep.ldr_lp, BM, &tmR));
-        UNIMM_TRY(gemm_make_map(ident, BN, BN, BN, BN, &tmI));
+        UNIMM_TRY(gemm_make_map(ident, IDN, IDN, IDN, BN, &tmI));      // top-left BN x BN block: the row order is 32-periodic
     } else {
         tmR = tmA;
         tmI = tmB;
@@ -467,11 +469,11 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     cfg.blockDim = dim3(384, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&umma_gemm_ln_kernel<CS, RES16>), Cfg::kSmemBytes));
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&umma_gemm_ln_kernel<CS, RES16, BN>), Cfg::kSmemBytes));
     if (max_clusters == 0) {
         cfg.gridDim = dim3((gemm_num_sms() / CS) * CS, 1, 1);
         int n = 0;
-        UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, umma_gemm_ln_kernel<CS, RES16>, &cfg));
+        UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, umma_gemm_ln_kernel<CS, RES16, BN>, &cfg));
         UNIMM_CHECK(n > 0, "no co-resident cluster fits the LayerNorm-fused GEMM");
         max_clusters = n < gemm_num_sms() / CS ? n : gemm_num_sms() / CS;
         if (getenv("UNIMM_DEBUG")) fprintf(stderr, "[unimm] LayerNorm-fused GEMM: cluster size %d, %d co-resident clusters (occupancy query %d)\n", CS, max_clusters, n);
@@ -479,7 +481,7 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     const int num_m = (M + BM - 1) / BM;
     const int clusters = num_m < max_clusters ? num_m : max_clusters;
     cfg.gridDim = dim3(clusters * CS, 1, 1);
-    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm_ln_kernel<CS, RES16>, tmA, tmB, tmR, tmI, M, K, ep));
+    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm_ln_kernel<CS, RES16, BN>, tmA, tmB, tmR, tmI, M, K, ep));
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -510,12 +512,16 @@ int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     static const bool mc_enabled = getenv("UNIMM_LN_MULTICAST") != nullptr && atoi(getenv("UNIMM_LN_MULTICAST")) != 0;
     GemmLnEpilogue ep = ep_in;
     ep.a_multicast = ep.a_multicast && mc_enabled;
+    // N = 768 as 4 CTAs x 192 columns keeps every SM busy (37 clusters of 4 = 148 SMs; 3 x 256 leaves 13 SMs idle) at the price of 11 %
+    // more operand bytes per FLOP.  Measured (profiles/r01_v8): 6-10 % faster per launch in isolation, but 0.7 % SLOWER inside the
+    // power-capped step (the step is limited by energy per FLOP, not by idle SMs) -> 3 x 256 stays the default, UNIMM_LN_SPLIT=4 opts in
+    static const int split = getenv("UNIMM_LN_SPLIT") ? atoi(getenv("UNIMM_LN_SPLIT")) : 3;
     if (ep.residual_lp != nullptr) {
-        if (N == 768) return launch_ln<3, true>(A, lda, W, ldw, M, K, ep, stream);
-        return launch_ln<4, true>(A, lda, W, ldw, M, K, ep, stream);
+        if (N == 768) return split == 3 ? launch_ln<3, true, 256>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, true, 192>(A, lda, W, ldw, M, K, ep, stream);
+        return launch_ln<4, true, 256>(A, lda, W, ldw, M, K, ep, stream);
     }
-    if (N == 768) return launch_ln<3, false>(A, lda, W, ldw, M, K, ep, stream);
-    return launch_ln<4, false>(A, lda, W, ldw, M, K, ep, stream);
+    if (N == 768) return split == 3 ? launch_ln<3, false, 256>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, false, 192>(A, lda, W, ldw, M, K, ep, stream);
+    return launch_ln<4, false, 256>(A, lda, W, ldw, M, K, ep, stream);
 }
 
 }  // namespace unimm
