@@ -71,7 +71,9 @@ struct LnCfg {
 //                memory except for its stores.  Costs 256 extra K per tile (+33 % MMA work at K = 768, +8 % at 3072).
 // BN = columns per CTA: 256 (N = 768 as 3 CTAs, N = 1024 as 4) or 192 (N = 768 as 4 CTAs: clusters of 4 tile all 148 SMs, clusters
 // of 3 only 135 of them).
-template <int CS, bool RES16, int BN>
+// RLP (with RES16 = false): the precharged residual is the 16-bit activation copy (converted by the epilogue warps) — the
+// residual costs no tensor-core work at all, only its 2 bytes per element of HBM read.
+template <int CS, bool RES16, int BN, bool RLP = false>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmI, int M, int K, GemmLnEpilogue ep) {
@@ -205,11 +207,27 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // accumulator <- residual + bias for row block mb (tcgen05.st), then hand the buffer to the MMA warp
         auto precharge = [&](int mb) {
             const int row0 = mb * BM + q * 32 + r8;
-            const float* res_base = ep.residual + static_cast<size_t>(row0) * ep.ldr + n0 + a * 4;
+            const float* res_base = RLP ? nullptr : ep.residual + static_cast<size_t>(row0) * ep.ldr + n0 + a * 4;
+            const bf16* res_lp = RLP ? ep.residual_lp + static_cast<size_t>(row0) * ep.ldr_lp + n0 + a * 4 : nullptr;
+            auto cvt4 = [&](uint2 w) {
+                float2 lo, hi;
+                if (ep.lp_kind == LP_FP16) {
+                    lo = __half22float2(*reinterpret_cast<const __half2*>(&w.x)); hi = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+                } else {
+                    lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x)); hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+                }
+                return make_float4(lo.x, lo.y, hi.x, hi.y);
+            };
             auto ld_res = [&](int c, float4* r) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (row0 + 8 * k < M) {
+                        if (RLP) {
+                            const bf16* p = res_lp + static_cast<size_t>(8 * k) * ep.ldr_lp + c * 32;
+                            r[2 * k] = cvt4(*reinterpret_cast<const uint2*>(p));
+                            r[2 * k + 1] = cvt4(*reinterpret_cast<const uint2*>(p + 16));
+                            continue;
+                        }
                         const float* p = res_base + static_cast<size_t>(8 * k) * ep.ldr + c * 32;
                         r[2 * k] = *reinterpret_cast<const float4*>(p);
                         r[2 * k + 1] = *reinterpret_cast<const float4*>(p + 16);
@@ -223,9 +241,10 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int mb2 = mb + 2 * num_clusters;
                 const int prow = mb2 * BM + q * 32 + lane;
                 if (mb2 < num_m && prow < M) {
-                    const char* p = reinterpret_cast<const char*>(ep.residual + static_cast<size_t>(prow) * ep.ldr + n0);
+                    const char* p = RLP ? reinterpret_cast<const char*>(ep.residual_lp + static_cast<size_t>(prow) * ep.ldr_lp + n0)
+                                        : reinterpret_cast<const char*>(ep.residual + static_cast<size_t>(prow) * ep.ldr + n0);
 #pragma unroll
-                    for (int i = 0; i < BN * 4 / 128; ++i) ptx::prefetch_l2(p + i * 128);
+                    for (int i = 0; i < BN * (RLP ? 2 : 4) / 128; ++i) ptx::prefetch_l2(p + i * 128);
                 }
             }
             float4 r[3][8];
@@ -442,7 +461,7 @@ int identity_for(int lp_kind, const bf16** out) {
     return 0;
 }
 
-template <int CS, bool RES16, int BN>
+template <int CS, bool RES16, int BN, bool RLP = false>
 int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const GemmLnEpilogue& ep, cudaStream_t stream) {
     using Cfg = LnCfg<CS, BN>;
     CUtensorMap tmA, tmB, tmR, tmI;
@@ -469,11 +488,11 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     cfg.blockDim = dim3(384, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&umma_gemm_ln_kernel<CS, RES16, BN>), Cfg::kSmemBytes));
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&umma_gemm_ln_kernel<CS, RES16, BN, RLP>), Cfg::kSmemBytes));
     if (max_clusters == 0) {
         cfg.gridDim = dim3((gemm_num_sms() / CS) * CS, 1, 1);
         int n = 0;
-        UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, umma_gemm_ln_kernel<CS, RES16, BN>, &cfg));
+        UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, umma_gemm_ln_kernel<CS, RES16, BN, RLP>, &cfg));
         UNIMM_CHECK(n > 0, "no co-resident cluster fits the LayerNorm-fused GEMM");
         max_clusters = n < gemm_num_sms() / CS ? n : gemm_num_sms() / CS;
         if (getenv("UNIMM_DEBUG")) fprintf(stderr, "[unimm] LayerNorm-fused GEMM: cluster size %d, %d co-resident clusters (occupancy query %d)\n", CS, max_clusters, n);
@@ -481,7 +500,7 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     const int num_m = (M + BM - 1) / BM;
     const int clusters = num_m < max_clusters ? num_m : max_clusters;
     cfg.gridDim = dim3(clusters * CS, 1, 1);
-    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm_ln_kernel<CS, RES16, BN>, tmA, tmB, tmR, tmI, M, K, ep));
+    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm_ln_kernel<CS, RES16, BN, RLP>, tmA, tmB, tmR, tmI, M, K, ep));
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -516,6 +535,13 @@ int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     // more operand bytes per FLOP.  Measured (profiles/r01_v8): 6-10 % faster per launch in isolation, but 0.7 % SLOWER inside the
     // power-capped step (the step is limited by energy per FLOP, not by idle SMs) -> 3 x 256 stays the default, UNIMM_LN_SPLIT=4 opts in
     static const int split = getenv("UNIMM_LN_SPLIT") ? atoi(getenv("UNIMM_LN_SPLIT")) : 3;
+    // 16-bit residual: added on the tensor core (identity k-blocks; UNIMM_LN_RES=mma) or precharged into the accumulator by the
+    // epilogue warps (UNIMM_LN_RES=precharge: no extra MMA work, +25 % K otherwise at K = 768)
+    static const bool res_precharge = getenv("UNIMM_LN_RES") != nullptr && std::string(getenv("UNIMM_LN_RES")) == "precharge";
+    if (ep.residual_lp != nullptr && res_precharge) {
+        if (N == 768) return split == 3 ? launch_ln<3, false, 256, true>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, false, 192, true>(A, lda, W, ldw, M, K, ep, stream);
+        return launch_ln<4, false, 256, true>(A, lda, W, ldw, M, K, ep, stream);
+    }
     if (ep.residual_lp != nullptr) {
         if (N == 768) return split == 3 ? launch_ln<3, true, 256>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, true, 192>(A, lda, W, ldw, M, K, ep, stream);
         return launch_ln<4, true, 256>(A, lda, W, ldw, M, K, ep, stream);
