@@ -177,6 +177,16 @@ int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_s
 int unimm_profile_begin(unimm_engine_t* e);
 int unimm_profile_end(unimm_engine_t* e, double* ms, double* work, int64_t* launches, int ncat);
 
+/* Dense-annotation objective on the NSP probabilities, forward values:
+ * unimm_neural_ndcg: utils/rank_loss.py:518-581 (neuralNDCG_transposed: deterministic NeuralSort :79-112 + Sinkhorn scaling :55-78,
+ *   powered relevancies, no padded entries, k = n_opt <= 128) as called at dense_annotation_finetuning.py:288.  d_y_pred / d_y_true
+ *   [rows, n_opt]; out: d_ndcg [rows] (0 where the ideal DCG is 0), d_idcg [rows].  loss = -sum(ndcg) / #(idcg != 0).
+ * unimm_ensemble_normalise: val.py:152-161 / evaluate.py:107-117: per model min-max over the options, sum-normalise, sum over
+ *   models.  d_probs [models, rows, n_opt] -> d_out [rows, n_opt]. */
+int unimm_neural_ndcg(const float* d_y_pred, const float* d_y_true, int rows, int n_opt, float temperature, int max_iter, float tol,
+                      float* d_ndcg, float* d_idcg, void* stream);
+int unimm_ensemble_normalise(const float* d_probs, int n_models, int rows, int n_opt, float* d_out, void* stream);
+
 /* Ranking metrics of the reference's utils/visdial_metrics.py on the device: d_scores [rows, n_opt]; optional d_gt_index
  * [rows] (sparse metrics), d_relevance [rows, n_opt] (NDCG), d_ranks [rows, n_opt] out (1-based, stable on ties).
  * d_sums: 9 doubles, zeroed by the caller, accumulated: rows, #rank<=1, #rank<=5, #rank<=10, sum rank, sum 1/rank,

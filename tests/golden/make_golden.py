@@ -329,6 +329,42 @@ def main():
              relevance=np.array(relevance, dtype=np.float32),
              lm_loss=lm_loss.numpy(), img_loss=img_loss.numpy(), nsp_loss=nsp_loss.numpy(), nsp_scores=nsp.numpy())
 
+    # ---------------------------------------------------------------- dense-annotation objective on NSP probabilities
+    if want("rankloss"):
+        import importlib
+        from oracle import rank_loss as orl
+        rl = importlib.import_module("utils.rank_loss")
+        g = np.random.RandomState(77)
+        cases = []
+        for kind in range(5):
+            b = 3
+            p = g.rand(b, 100).astype(np.float32)
+            if kind == 1:
+                p = (g.rand(b, 100) ** 4).astype(np.float32)            # peaked, NSP-like
+            if kind == 3:
+                p = np.sort(p, -1)[:, ::-1].copy()                       # already sorted
+            y = g.choice([0, 0, 0, 0.2, 0.4, 0.6, 0.8, 1.0], size=(b, 100)).astype(np.float32)
+            if kind == 2:
+                y[1] = 0                                                 # a slate without any relevant option
+            if kind == 4:
+                y[:] = 0                                                 # none at all: the loss is 0
+            loss = rl.neuralNDCG_transposed(torch.from_numpy(p.copy()), torch.from_numpy(y.copy()))
+            mine = orl.neural_ndcg_transposed(p, y)[0]
+            assert abs(float(loss) - float(mine)) < 1e-6, (kind, float(loss), float(mine))
+            cases.append((p, y, np.float32(loss)))
+        # val.py:152-161 (inline code in the reference; the same torch expressions)
+        probs = torch.from_numpy(g.rand(5, 4, 10, 100).astype(np.float32))
+        res = None
+        for tmp in probs:
+            a_ = tmp.min(dim=-1)[0].unsqueeze(-1)
+            b_ = tmp.max(dim=-1)[0].unsqueeze(-1)
+            e_x = (tmp - a_) / (b_ - a_)
+            res_tmp = e_x / (e_x.sum(dim=-1).unsqueeze(-1))
+            res = res_tmp if res is None else res + res_tmp
+        assert np.abs(orl.ensemble_normalise(probs.numpy().reshape(5, 40, 100)).reshape(4, 10, 100) - res.numpy()).max() < 1e-6
+        save("rankloss", y_pred=np.stack([c[0] for c in cases]), y_true=np.stack([c[1] for c in cases]),
+             loss=np.array([c[2] for c in cases], dtype=np.float32), ens_probs=probs.numpy(), ens_out=res.numpy())
+
     # ---------------------------------------------------------------- config 1: 100 candidates, ranking metrics
     for name, seed, perturbed in (("gen100_default", 0, False),):
         if not want(name):

@@ -43,3 +43,16 @@ def test_ties_are_reported_and_ranked_stably():
     s = torch.tensor([[0.5, 0.7, 0.5, 0.1]]).cuda()
     out = rank_metrics(s, torch.tensor([2]).cuda())
     assert out["ties"] == 1 and out["ranks"].view(-1).tolist() == [2, 1, 3, 4]
+
+
+def test_neural_ndcg_and_ensemble_match_reference_values():
+    """Dense-annotation objective pieces (utils/rank_loss.py:518-581, val.py:152-161) against golden values from the reference."""
+    import os
+    from unimm_b200.rank_loss import ensemble_normalise, neural_ndcg_loss
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rankloss.npz"))
+    for p, y, want in zip(z["y_pred"], z["y_true"], z["loss"]):
+        got = neural_ndcg_loss(torch.from_numpy(p).cuda(), torch.from_numpy(y).cuda()).item()
+        print(f"neuralNDCG: {got:.7f} vs reference {float(want):.7f}")
+        assert abs(got - float(want)) < 2e-5
+    ens = ensemble_normalise(torch.from_numpy(z["ens_probs"]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(ens, z["ens_out"], atol=1e-6, rtol=0)

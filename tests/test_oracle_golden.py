@@ -1,4 +1,6 @@
 """CPU: the oracle restatement against fixtures produced by the unmodified reference (tests/golden/)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -114,3 +116,14 @@ def test_rank_metrics_on_golden_scores():
             "ndcg": om.ndcg(score.view(1, 100), torch.from_numpy(g["relevance"]))}
     for k, v in zip(g["metric_names"], g["metric_values"]):
         assert abs(mine[str(k)] - v) < 1e-6, k
+
+
+def test_rank_loss_oracle_matches_reference():
+    """NeuralNDCG-transposed and the NSP ensemble normalisation against values from the unmodified reference."""
+    from oracle import rank_loss as orl
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rankloss.npz"))
+    for p, y, want in zip(z["y_pred"], z["y_true"], z["loss"]):
+        got = orl.neural_ndcg_transposed(p, y)[0]
+        assert abs(float(got) - float(want)) < 1e-6
+    ens = orl.ensemble_normalise(z["ens_probs"].reshape(5, 40, 100)).reshape(4, 10, 100)
+    np.testing.assert_allclose(ens, z["ens_out"], atol=1e-6, rtol=0)

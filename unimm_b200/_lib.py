@@ -85,6 +85,8 @@ SYMBOLS = {
     "unimm_verify_masks": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "unimm_score_host": (C.c_int, [_P, C.POINTER(HostBatch), _P, _P, _P]),
     "unimm_rank_metrics": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "unimm_neural_ndcg": (C.c_int, [_P, _P, _I, _I, C.c_float, _I, C.c_float, _P, _P, _P]),
+    "unimm_ensemble_normalise": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "unimm_profile_begin": (C.c_int, [_P]),
     "unimm_profile_end": (C.c_int, [_P, _P, _P, _P, _I]),
     "unimm_launch_count": (C.c_int64, []),

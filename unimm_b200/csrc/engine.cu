@@ -1049,6 +1049,17 @@ int unimm_rank_metrics(const float* d_scores, int rows, int n_opt, const int32_t
     return rank_metrics(d_scores, rows, n_opt, d_gt_index, d_relevance, d_ranks, d_sums, static_cast<cudaStream_t>(stream));
 }
 
+int unimm_neural_ndcg(const float* d_y_pred, const float* d_y_true, int rows, int n_opt, float temperature, int max_iter, float tol,
+                      float* d_ndcg, float* d_idcg, void* stream) {
+    UNIMM_CHECK(d_y_pred && d_y_true && d_ndcg && d_idcg, "null argument");
+    return neural_ndcg(d_y_pred, d_y_true, rows, n_opt, temperature, max_iter, tol, d_ndcg, d_idcg, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_ensemble_normalise(const float* d_probs, int n_models, int rows, int n_opt, float* d_out, void* stream) {
+    UNIMM_CHECK(d_probs && d_out, "null argument");
+    return ensemble_normalise(d_probs, n_models, rows, n_opt, d_out, static_cast<cudaStream_t>(stream));
+}
+
 int unimm_profile_begin(unimm_engine_t* e) {
     UNIMM_CHECK(e != nullptr, "null engine");
     e->profiling = true;

@@ -185,6 +185,11 @@ int image_kl_loss(const float* v_logits, int ld, const float* target, const int6
 // GPU ranking metrics (metrics.cu); sums is a zero-initialised double[9]
 int rank_metrics(const float* scores, int rows, int n_opt, const int* gt_index, const float* relevance, int* ranks, double* sums,
                  cudaStream_t stream);
+// NeuralNDCG-transposed forward value per slate (utils/rank_loss.py:518-581 as used by dense_annotation_finetuning.py:288); n <= 128
+int neural_ndcg(const float* y_pred, const float* y_true, int rows, int n, float temperature, int max_iter, float tol, float* ndcg,
+                float* idcg, cudaStream_t stream);
+// ensemble of per-model option probabilities (val.py:152-161): probs [models, rows, n_opt] -> out [rows, n_opt]
+int ensemble_normalise(const float* probs, int n_models, int rows, int n_opt, float* out, cudaStream_t stream);
 // regenerate the dense masks from descriptors and compare with the caller's dense tensors (boundary check)
 int verify_masks(const SeqDesc* desc, int B, int S, int R, const void* txt_mask, int txt_elem_bytes, int txt_is_2d,
                  const int64_t* co_mask, int* mismatch_flag, cudaStream_t stream);

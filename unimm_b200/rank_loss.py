@@ -1,0 +1,43 @@
+"""Dense-annotation objective pieces on the GPU (reference utils/rank_loss.py:518-581, val.py:152-161) — forward values.
+
+``neural_ndcg_loss(y_pred, y_true)`` is ``neuralNDCG_transposed(y_pred, y_true)`` with the defaults
+dense_annotation_finetuning.py:288 uses; ``ensemble_normalise(probs)`` is the 5-model NSP ensemble of val.py / evaluate.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib, ptr
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def neural_ndcg_loss(y_pred: torch.Tensor, y_true: torch.Tensor, temperature: float = 1.0, max_iter: int = 50, tol: float = 1e-6,
+                     return_parts: bool = False):
+    if not y_pred.is_cuda:
+        raise ValueError("neural_ndcg_loss runs on the device the scores live on (CUDA)")
+    if (y_true == -1).any():
+        raise NotImplementedError("padded slates (y_true == -1) are not part of the dense-annotation path")
+    n = y_pred.shape[-1]
+    p = y_pred.detach().reshape(-1, n).float().contiguous()
+    t = y_true.detach().reshape(-1, n).to(p.device, torch.float32).contiguous()
+    ndcg, idcg = torch.empty(p.shape[0], device=p.device), torch.empty(p.shape[0], device=p.device)
+    check(lib.unimm_neural_ndcg(ptr(p), ptr(t), p.shape[0], n, temperature, max_iter, tol, ptr(ndcg), ptr(idcg), _stream(p.device)))
+    valid = idcg != 0
+    loss = -(ndcg.sum() / valid.sum()) if bool(valid.any()) else torch.zeros((), device=p.device)
+    return (loss, ndcg, idcg) if return_parts else loss
+
+
+def ensemble_normalise(probs: torch.Tensor) -> torch.Tensor:
+    """probs [models, ..., options] -> [..., options]."""
+    if not probs.is_cuda:
+        raise ValueError("ensemble_normalise runs on the device the probabilities live on (CUDA)")
+    m, n = probs.shape[0], probs.shape[-1]
+    p = probs.detach().reshape(m, -1, n).float().contiguous()
+    out = torch.empty(p.shape[1], n, device=p.device)
+    check(lib.unimm_ensemble_normalise(ptr(p), m, p.shape[1], n, ptr(out), _stream(p.device)))
+    return out.view(*probs.shape[1:])
