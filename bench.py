@@ -86,6 +86,20 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def gemm_traffic(launches_per_step, packed):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/*_gemm_traffic.json, written by scripts/gemm_traffic.py): per-shape dram__bytes_read.sum + dram__bytes_write.sum,
+    averaged over this bench's launch mix.  None when no capture of this layout is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    if not files or not packed:
+        return None, None
+    t = json.load(open(files[-1]))
+    if abs(t.get("launches_per_step", 0) - launches_per_step) > 2:
+        return None, None
+    return t["bytes_per_launch"], os.path.relpath(files[-1], ROOT)
+
+
 # ------------------------------------------------------------------------------------------------ workload
 def image_batch(image_id):
     """One step's inputs: 10 rounds x 100 candidates of one synthetic image, as pinned host tensors."""
@@ -315,9 +329,11 @@ def main_ours(args):
         g = prof["gemm"]
         dense_flops_per_cand = F_ENC + F_POOL + F_HEAD_PER_ROW * rows_per_cand
         # FLOPs actually issued in the timed region (this rank): every GEMM (2MNK of its real M), attention, LM head
-        executed = prof["gemm"]["work"] + prof["attention"]["work"] + prof["lm_head"]["work"]
+        executed = prof["gemm"]["work"] + prof["gemm_ln"]["work"] + prof["attention"]["work"] + prof["lm_head"]["work"]
         executed_per_cand = executed / (args.steps * cands_per_step)
         achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        tf = lambda c: (prof[c]["work"] / (prof[c]["ms"] * 1e-3) / 1e12) if prof[c]["ms"] > 0 else 0.0
+        traffic, traffic_src = gemm_traffic(g["launches"] // max(1, args.steps), packed)
         share = {k: round(v["ms"] / (ms_total * 1.0), 4) for k, v in prof.items()}
         step_tflops = executed / (ms_total * 1e-3) / 1e12
         workload = ("configs[1]: synthetic VisDial v1.0 val sweep, generative scoring; 1 step = %d image(s) = %d rounds x 100 candidates "
@@ -342,11 +358,13 @@ def main_ours(args):
                                  "peaks": pk["source"], "dense_equivalent_speedup": dense_flops_per_cand / executed_per_cand},
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"kernel": "umma_gemm_kernel (tcgen05 projections / FFN)" if args.precision != "fp32" else "sgemm_nt_kernel (fp32 CUDA cores)",
+            "roofline": {"kernel": "umma_gemm_kernel (tcgen05 QKV / FFN-1 / co-attention projections, cta_group::2 pairs)" if args.precision != "fp32" else "sgemm_nt_kernel (fp32 CUDA cores)",
                          "bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["sustained"], "frac_of_burst_peak": achieved / pk["burst"], "peak_source": pk["source"],
-                         "traffic": None, "launches": g["launches"], "avg_launch_ms": g["ms"] / max(1, g["launches"]),
-                         "share_of_step": share},
+                         "traffic": traffic, "traffic_source": traffic_src, "launches": g["launches"],
+                         "avg_launch_ms": g["ms"] / max(1, g["launches"]), "share_of_step": share,
+                         "other_tensor_kernels_tflops": {"umma_gemm_ln_kernel (LayerNorm-fused cluster GEMM)": tf("gemm_ln"),
+                                                         "umma_gemm_kernel<LSE> (LM head)": tf("lm_head")}},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

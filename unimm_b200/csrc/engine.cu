@@ -123,7 +123,7 @@ struct unimm_engine {
     static constexpr int kLogitRows = 2048;
 
     // optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline numbers)
-    enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ROWWISE = 2, CAT_LMHEAD = 3, CAT_OTHER = 4, NCAT = 5 };
+    enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ROWWISE = 2, CAT_LMHEAD = 3, CAT_GEMM_LN = 4, NCAT = 5 };   // GEMM = umma_gemm_kernel, GEMM_LN = umma_gemm_ln_kernel
     struct ProfRec { cudaEvent_t a, b; int cat; double work; };
     bool profiling = false;
     std::vector<ProfRec> prof_recs;
@@ -447,7 +447,7 @@ int unimm_engine::linear_ln(const ActBuf& x, int M, const Linear& L, const float
         }
         if (L.wlp_ln != nullptr && gemm_umma_ln_supported(L.N, L.K, ep)) {
             UNIMM_CHECK(x.h != nullptr, "16-bit operand missing");
-            Prof prof(this, CAT_GEMM, 2.0 * M * L.N * L.K, st);
+            Prof prof(this, CAT_GEMM_LN, 2.0 * M * L.N * L.K, st);
             return gemm_umma_ln(x.h, x.ld, L.wlp_ln, L.K, M, L.N, L.K, ep, st);
         }
     }

@@ -184,7 +184,7 @@ class Engine:
         check(lib.unimm_score_packed_host(self._h, C.byref(s), ptr(seq_score), ptr(nsp_scores), C.c_void_p(stream)))
 
     # ------------------------------------------------------------------------------------------ profiling
-    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "lm_head", "other")
+    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "lm_head", "gemm_ln")     # gemm = umma_gemm_kernel, gemm_ln = umma_gemm_ln_kernel
 
     def profile_begin(self) -> None:
         check(lib.unimm_profile_begin(self._h))
