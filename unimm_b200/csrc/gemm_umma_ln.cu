@@ -51,11 +51,11 @@ constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr float kLnEps = 1e-12f;   // BertLayerNorm eps (reference models/vilbert_dialog.py:322)
 
-template <int CS, int BN>
+template <int CS, int BN, bool PAIR = false>
 struct LnCfg {
-    static constexpr int kStages = BN == 256 ? 4 : 5;
+    static constexpr int kStages = PAIR ? 6 : (BN == 256 ? 4 : 5);
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;           // a cta_group::2 pair keeps half of the W box per CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStatsBytes = 2 * 2 * 4 * (CS - 1) * 32 * 8;       // [use parity][group][warp][source][row] float2
     static constexpr int kParamBytes = 3 * BN * 4;                          // bias, gamma, beta of this CTA's 256 columns
@@ -73,12 +73,17 @@ struct LnCfg {
 // of 3 only 135 of them).
 // RLP (with RES16 = false): the precharged residual is the 16-bit activation copy (converted by the epilogue warps) — the
 // residual costs no tensor-core work at all, only its 2 bytes per element of HBM read.
-template <int CS, bool RES16, int BN, bool RLP = false>
+// PAIR: clusters of 2 * CS CTAs — two vertically adjacent row blocks per cluster, the two CTAs that own the same 256 columns of
+// them form a cta_group::2 pair (ranks 2 n and 2 n + 1): ONE M = 256 MMA issued by the even rank, half of the W box (and of the
+// identity) in each CTA, TMA completions on the leader's barrier, multicast commits (see gemm_umma.cu, CL = 3).  The row
+// statistics are exchanged among the CS CTAs of the same row block (ranks of equal parity).
+template <int CS, bool RES16, int BN, bool RLP = false, bool PAIR = false>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmI, int M, int K, GemmLnEpilogue ep) {
-    using Cfg = LnCfg<CS, BN>;
+    using Cfg = LnCfg<CS, BN, PAIR>;
     constexpr int N = CS * BN;
+    constexpr int CL = PAIR ? 2 * CS : CS;                   // CTAs per cluster
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -95,10 +100,15 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const int cluster_id = blockIdx.x / CS;
-    const int num_clusters = gridDim.x / CS;
-    const int num_m = (M + BM - 1) / BM;
+    const uint32_t crank = ptx::cluster_ctarank();
+    const uint32_t rank = PAIR ? crank >> 1 : crank;         // column block of this CTA
+    const int m_r = PAIR ? static_cast<int>(crank & 1) : 0;  // which row block of the pair
+    const uint32_t leader = crank & ~1u;                     // PAIR: the rank that issues the MMAs for this CTA
+    const uint16_t pair_mask = static_cast<uint16_t>(3u << leader);
+    const int cluster_id = blockIdx.x / CL;
+    const int num_clusters = gridDim.x / CL;
+    const int num_m = PAIR ? ((M + BM - 1) / BM + 1) / 2 : (M + BM - 1) / BM;      // row blocks (pairs of them) = work items of a cluster
+    auto row_of = [&](int mb) { return (PAIR ? 2 * mb + m_r : mb) * BM; };          // first row of this CTA's block in work item mb
     const int num_k = K / BK;
     const int num_kr = RES16 ? num_k + BN / BK : num_k;       // + the residual x identity k-blocks
     const int n0 = static_cast<int>(rank) * BN;
@@ -110,16 +120,19 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1 && ptx::elect_one()) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], ep.a_multicast ? CS : 1);   // multicast A: a slot is reusable once EVERY CTA of the cluster has read it
+            ptx::mbar_init(&empty_bar[s], (ep.a_multicast && !PAIR) ? CS : 1);   // multicast A: a slot is reusable once EVERY CTA of the cluster has read it
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp of the group
+            ptx::mbar_init(&tempty_bar[a], PAIR ? 8 : 4);   // one arrival per epilogue warp of the group (of both CTAs of a pair)
         }
         for (int b = 0; b < 16; ++b) ptx::mbar_init(&stats_bar[b], 1);   // the owner's arrive.expect_tx; peers complete bytes
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
+    if (warp == 2) {
+        if (PAIR) ptx::tmem_alloc_2sm<512>(tmem_slot);
+        else ptx::tmem_alloc<512>(tmem_slot);
+    }
     for (int i = threadIdx.x; i < BN; i += blockDim.x) {
         sparam[i] = ep.bias[n0 + i];
         sparam[BN + i] = ep.gamma[n0 + i];
@@ -137,15 +150,28 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int mb = cluster_id; mb < num_m; mb += num_clusters) {
-                const int m0 = mb * BM;
+                const int m0 = row_of(mb);
                 for (int kb = 0; kb < num_kr; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (PAIR) {
+                        if (m_r == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);     // both CTAs' boxes
+                        if (!RES16 || kb < num_k) {
+                            ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
+                            ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0 + m_r * (BN / 2));
+                        } else {
+                            const int j = kb - num_k;
+                            ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmR, &full_bar[stage], n0 + j * BK, m0);
+                            ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmI, &full_bar[stage], j * BK, m_r * (BN / 2));
+                        }
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     if (!RES16 || kb < num_k) {
                         // the CS CTAs of the cluster multiply the SAME 128 x 64 activation box: CTA kb % CS fetches it once and
                         // multicasts it into every CTA's slot (data and mbarrier bytes land at the same CTA-relative offsets)
                         if (!ep.a_multicast) ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
-                        else if (kb % CS == static_cast<int>(rank))
+                        else if (kb % CS == static_cast<int>(rank))   /* (a_multicast is never set with PAIR) */
                             ptx::tma_load_2d_mc(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0, static_cast<uint16_t>((1u << CS) - 1u));
                         ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
                     } else {      // residual columns n0 + 64 j .. against identity columns 64 j ..
@@ -159,8 +185,8 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (ptx::elect_one()) {
-            const uint32_t idesc = ptx::make_idesc_f16(BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u);
+        if (ptx::elect_one() && m_r == 0) {
+            const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -177,12 +203,17 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * Cfg::kABytes));
                     const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
-                    if (ep.a_multicast) ptx::umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CS) - 1u));
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (PAIR) ptx::umma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
+                        else ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
+                    }
+                    if (PAIR) ptx::umma_commit_2sm_mc(&empty_bar[stage], pair_mask);
+                    else if (ep.a_multicast) ptx::umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CS) - 1u));
                     else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);
+                if (PAIR) ptx::umma_commit_2sm_mc(&tfull_bar[acc], pair_mask);
+                else ptx::umma_commit(&tfull_bar[acc]);
             }
         }
     } else if (warp >= 4) {
@@ -195,6 +226,11 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         constexpr int NCH = BN / 32;
         // one 32-row x 32-column chunk = two 16-lane slabs of 16 registers; register of (row 8 k + r8, value m):
         // m < 4 -> output column 4 a + m, m >= 4 -> 16 + 4 a + (m - 4) of the chunk
+        // the accumulator goes back to the MMA warp of the pair's LEADER
+        auto arrive_tempty = [&](uint64_t* bar) {
+            if (PAIR && m_r != 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(bar), leader));
+            else ptx::mbar_arrive(bar);
+        };
         auto frag = [](int k, int m) { return (k >> 1) * 16 + 4 * (m >> 1) + 2 * (k & 1) + (m & 1); };
         auto ld_chunk = [&](int c, uint32_t* v) {
             ptx::tmem_ld_16x256b_x4(taddr0 + c * 32, v);
@@ -206,7 +242,7 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
         // accumulator <- residual + bias for row block mb (tcgen05.st), then hand the buffer to the MMA warp
         auto precharge = [&](int mb) {
-            const int row0 = mb * BM + q * 32 + r8;
+            const int row0 = row_of(mb) + q * 32 + r8;
             const float* res_base = RLP ? nullptr : ep.residual + static_cast<size_t>(row0) * ep.ldr + n0 + a * 4;
             const bf16* res_lp = RLP ? ep.residual_lp + static_cast<size_t>(row0) * ep.ldr_lp + n0 + a * 4 : nullptr;
             auto cvt4 = [&](uint2 w) {
@@ -239,7 +275,7 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             };
             {   // pull the rows of this group's tile AFTER this one towards L2
                 const int mb2 = mb + 2 * num_clusters;
-                const int prow = mb2 * BM + q * 32 + lane;
+                const int prow = row_of(mb2) + q * 32 + lane;
                 if (mb2 < num_m && prow < M) {
                     const char* p = RLP ? reinterpret_cast<const char*>(ep.residual_lp + static_cast<size_t>(prow) * ep.ldr_lp + n0)
                                         : reinterpret_cast<const char*>(ep.residual + static_cast<size_t>(prow) * ep.ldr + n0);
@@ -274,14 +310,14 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+            if (lane == 0) arrive_tempty(&tempty_bar[g]);
         };
 
         int mb = cluster_id + g * num_clusters;
         if (!RES16 && mb < num_m) precharge(mb);
         for (int use = 0; mb < num_m; mb += 2 * num_clusters, ++use) {
             const uint32_t par = use & 1;
-            const int row0 = mb * BM + q * 32 + r8;               // this lane's rows: row0 + 8 k
+            const int row0 = row_of(mb) + q * 32 + r8;            // this lane's rows: row0 + 8 k
             float2* slots = stats + ((par * 2 + g) * 4 + q) * (CS - 1) * 32;
             uint64_t* sbar = &stats_bar[(par * 2 + g) * 4 + q];
             if (lane == 0) ptx::mbar_arrive_expect_tx(sbar, (CS - 1) * 32 * 8);   // the peers' partials of this tile
@@ -334,7 +370,8 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int p = 0; p < CS; ++p) {
                 if (p == static_cast<int>(rank)) continue;
                 const int src = static_cast<int>(rank) < p ? static_cast<int>(rank) : static_cast<int>(rank) - 1;
-                ptx::st_async_v2(ptx::mapa(ptx::smem_u32(slots + src * 32 + my_row), p), my_s, my_m2, ptx::mapa(ptx::smem_u32(sbar), p));
+                const uint32_t pr = PAIR ? static_cast<uint32_t>(2 * p + m_r) : static_cast<uint32_t>(p);   // same row block, column block p
+                ptx::st_async_v2(ptx::mapa(ptx::smem_u32(slots + src * 32 + my_row), pr), my_s, my_m2, ptx::mapa(ptx::smem_u32(sbar), pr));
             }
             ptx::mbar_wait(sbar, (use >> 1) & 1);
             float tot = my_s, m2 = my_m2;
@@ -404,7 +441,7 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (RES16) {      // hand the drained accumulator back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+                if (lane == 0) arrive_tempty(&tempty_bar[g]);
             } else if (mb + 2 * num_clusters < num_m) {
                 precharge(mb + 2 * num_clusters);   // the buffer's next tile (which also hands it back to the MMA warp)
             }
@@ -413,7 +450,10 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();    // no CTA leaves while a peer may still push statistics into its shared memory
-    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+    if (warp == 2) {
+        if (PAIR) ptx::tmem_dealloc_2sm<512>(tmem_base);
+        else ptx::tmem_dealloc<512>(tmem_base);
+    }
 }
 
 // weight row that must sit at position `p` of the B operand so that accumulator column p holds output column
@@ -461,17 +501,18 @@ int identity_for(int lp_kind, const bf16** out) {
     return 0;
 }
 
-template <int CS, bool RES16, int BN, bool RLP = false>
+template <int CS, bool RES16, int BN, bool RLP = false, bool PAIR = false>
 int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, const GemmLnEpilogue& ep, cudaStream_t stream) {
-    using Cfg = LnCfg<CS, BN>;
+    using Cfg = LnCfg<CS, BN, PAIR>;
+    constexpr int CL = PAIR ? 2 * CS : CS;
     CUtensorMap tmA, tmB, tmR, tmI;
     UNIMM_TRY(gemm_make_map(A, M, K, lda, BM, &tmA));
-    UNIMM_TRY(gemm_make_map(W, CS * BN, K, ldw, BN, &tmB));
+    UNIMM_TRY(gemm_make_map(W, CS * BN, K, ldw, PAIR ? BN / 2 : BN, &tmB));
     if (RES16) {
         const bf16* ident = nullptr;
         UNIMM_TRY(identity_for(ep.lp_kind, &ident));
         UNIMM_TRY(gemm_make_map(ep.residual_lp, M, CS * BN, ep.ldr_lp, BM, &tmR));
-        UNIMM_TRY(gemm_make_map(ident, IDN, IDN, IDN, BN, &tmI));      // top-left BN x BN block: the row order is 32-periodic
+        UNIMM_TRY(gemm_make_map(ident, IDN, IDN, IDN, PAIR ? BN / 2 : BN, &tmI));      // top-left BN x BN block: the row order is 32-periodic
     } else {
         tmR = tmA;
         tmI = tmB;
@@ -480,7 +521,7 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -488,19 +529,19 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     cfg.blockDim = dim3(384, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&umma_gemm_ln_kernel<CS, RES16, BN, RLP>), Cfg::kSmemBytes));
+    UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&umma_gemm_ln_kernel<CS, RES16, BN, RLP, PAIR>), Cfg::kSmemBytes));
     if (max_clusters == 0) {
-        cfg.gridDim = dim3((gemm_num_sms() / CS) * CS, 1, 1);
+        cfg.gridDim = dim3((gemm_num_sms() / CL) * CL, 1, 1);
         int n = 0;
-        UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, umma_gemm_ln_kernel<CS, RES16, BN, RLP>, &cfg));
+        UNIMM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, umma_gemm_ln_kernel<CS, RES16, BN, RLP, PAIR>, &cfg));
         UNIMM_CHECK(n > 0, "no co-resident cluster fits the LayerNorm-fused GEMM");
-        max_clusters = n < gemm_num_sms() / CS ? n : gemm_num_sms() / CS;
+        max_clusters = n < gemm_num_sms() / CL ? n : gemm_num_sms() / CL;
         if (getenv("UNIMM_DEBUG")) fprintf(stderr, "[unimm] LayerNorm-fused GEMM: cluster size %d, %d co-resident clusters (occupancy query %d)\n", CS, max_clusters, n);
     }
-    const int num_m = (M + BM - 1) / BM;
+    const int num_m = PAIR ? ((M + BM - 1) / BM + 1) / 2 : (M + BM - 1) / BM;
     const int clusters = num_m < max_clusters ? num_m : max_clusters;
-    cfg.gridDim = dim3(clusters * CS, 1, 1);
-    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm_ln_kernel<CS, RES16, BN, RLP>, tmA, tmB, tmR, tmI, M, K, ep));
+    cfg.gridDim = dim3(clusters * CL, 1, 1);
+    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm_ln_kernel<CS, RES16, BN, RLP, PAIR>, tmA, tmB, tmR, tmI, M, K, ep));
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -541,6 +582,12 @@ int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     if (ep.residual_lp != nullptr && res_precharge) {
         if (N == 768) return split == 3 ? launch_ln<3, false, 256, true>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, false, 192, true>(A, lda, W, ldw, M, K, ep, stream);
         return launch_ln<4, false, 256, true>(A, lda, W, ldw, M, K, ep, stream);
+    }
+    // tall problems with the 16-bit residual: cta_group::2 pairs inside clusters of 6 (N = 768) — UNIMM_LN_PAIR=0 keeps clusters of 3
+    static const bool pair_enabled = getenv("UNIMM_LN_PAIR") == nullptr || atoi(getenv("UNIMM_LN_PAIR")) != 0;
+    if (ep.residual_lp != nullptr && pair_enabled && N == 768 && M >= 8192 && split == 3) {
+        ep.a_multicast = false;
+        return launch_ln<3, true, 256, false, true>(A, lda, W, ldw, M, K, ep, stream);
     }
     if (ep.residual_lp != nullptr) {
         if (N == 768) return split == 3 ? launch_ln<3, true, 256>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, true, 192>(A, lda, W, ldw, M, K, ep, stream);
