@@ -280,6 +280,39 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
                 if (c + 1 < NCH && col0 + 32 < N) ptx::tmem_ld_32x32b_x32(taddr0 + (c + 1) * 32, v);   // next chunk in flight
                 if (LSE) {
+                    constexpr float kLog2e = 1.4426950408889634f;
+                    if (ncols == 32 && fast_ok) {
+                        // full chunk (all but the last vocabulary tile): 128-bit uniform bias loads, no per-column predicates
+                        if (ep.bias != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                                x[j] += b4.x; x[j + 1] += b4.y; x[j + 2] += b4.z; x[j + 3] += b4.w;
+                            }
+                        }
+                        float c0 = fmaxf(x[0], x[1]), c1 = fmaxf(x[2], x[3]);
+#pragma unroll
+                        for (int j = 4; j < 32; j += 4) { c0 = fmaxf(c0, fmaxf(x[j], x[j + 1])); c1 = fmaxf(c1, fmaxf(x[j + 2], x[j + 3])); }
+                        const float nmax = fmaxf(run_max, fmaxf(c0, c1));
+                        const float nm2 = nmax * kLog2e;
+                        float s0 = run_sum * fast_ex2((run_max - nmax) * kLog2e), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            s0 += fast_ex2(fmaf(x[j], kLog2e, -nm2));
+                            s1 += fast_ex2(fmaf(x[j + 1], kLog2e, -nm2));
+                            s2 += fast_ex2(fmaf(x[j + 2], kLog2e, -nm2));
+                            s3 += fast_ex2(fmaf(x[j + 3], kLog2e, -nm2));
+                        }
+                        const int lj = label - col0;
+                        if (lj >= 0 && lj < 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j == lj) lab_logit = x[j];
+                        }
+                        run_max = nmax;
+                        run_sum = (s0 + s1) + (s2 + s3);
+                        continue;
+                    }
                     if (ep.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -290,7 +323,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) cmax = fmaxf(cmax, x[j]);
                     const float nmax = fmaxf(run_max, cmax);
-                    constexpr float kLog2e = 1.4426950408889634f;
                     const float nm2 = nmax * kLog2e;
                     float s = run_sum * fast_ex2((run_max - nmax) * kLog2e);  // 2^-inf = 0 on the first chunk
 #pragma unroll
