@@ -656,6 +656,8 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     const bool sm2 = pair_mode == 2 && tall;
     if (lse) {
         UNIMM_CHECK(tile_n == 256, "LSE epilogue uses 256-wide vocabulary tiles");
+        static const bool lse_sm2 = getenv("UNIMM_LSE_SM2") != nullptr && atoi(getenv("UNIMM_LSE_SM2")) != 0;
+        if (sm2 && lse_sm2) return launch<256, true, 0, false, 3>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         if (mc || sm2) return launch<256, true, 0, false, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
         return launch<256, true>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);
     }
