@@ -139,6 +139,8 @@ typedef struct {
     const int32_t* d_cand_cls_row;               /* [C]   packed row of each candidate's [CLS]                  */
     const int32_t* d_cand_img_row;               /* [C]   unit * R                                              */
     double pairs_text_self, pairs_i2t;           /* sum over jobs of q_len * keys (profiling only)             */
+    int32_t n_shared_rows;                       /* rows [0, n_shared_rows) are the units' context rows: the only text rows whose
+                                                  * co-attention keys / values anything reads (0 = unknown: project all rows) */
 } unimm_packed_batch_t;
 /* outputs (each optional): seq_score [C], nsp_scores [C,2], token_logp [n_lm] */
 int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, float* d_seq_score, float* d_nsp_scores,

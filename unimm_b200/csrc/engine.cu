@@ -174,6 +174,7 @@ struct unimm_engine {
                   ActBuf& out, cudaStream_t st);
     bool fuse_ln = true;
     bool gelu_tanh = false;      // 1-SFU tanh-form GELU in the FFN-1 epilogue (|err| <= |x| * 2.4e-4): default in fp16 mode, UNIMM_GELU_TANH overrides
+    bool kv2_ctx_only = true;    // packed layout: co-attention K2 | V2 for the context rows only (UNIMM_KV2_ALL=1 projects every row)
     bool attn_umma = true;       // candidate-row attention on tcgen05 (attention_umma.cu); UNIMM_ATTN_UMMA=0 keeps the mma.sync kernel
     bool frag_epilogue = true;   // QKV / FFN-1 GEMMs read fragment-ordered weight copies (UNIMM_FRAG_EPILOGUE=0 disables)
     // fp16 mode keeps the residual stream in 16 bits between sub-layers (the fused kernel adds it on the tensor core);
@@ -564,7 +565,23 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
     const int heads = c.bi_num_attention_heads, D = Hb / heads;
     const size_t e = esz();
     UNIMM_TRY(linear(xv, Mv, L.qkv_v, ACT_NONE, nullptr, 0, nullptr, 0, qkv_v, 3 * Hb, st));
-    UNIMM_TRY(linear(xt, Mt, L.qkv_t, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
+    const int n_sh = (ac.pk != nullptr && kv2_ctx_only) ? ac.pk->n_shared_rows : 0;
+    if (n_sh > 0 && n_sh < Mt && L.qkv_t.w32 != nullptr) {
+        // prefix-shared layout: the image rows attend ONLY the context rows (co-mask [1,ctx), utils/data_utils.py:199-210), so the
+        // text-side keys / values K2 | V2 (:670-672) of the candidate rows — 86 % of the text rows — are never read: project the
+        // queries Q2 for all rows, K2 | V2 for the context rows [0, n_shared) only (the packer puts them first)
+        Linear q2 = L.qkv_t, kv2 = L.qkv_t;
+        q2.N = Hb;
+        kv2.N = 2 * Hb;
+        const size_t off = static_cast<size_t>(Hb) * L.qkv_t.K;
+        kv2.w32 = L.qkv_t.w32 + off; kv2.b = L.qkv_t.b + Hb;
+        if (L.qkv_t.wlp) kv2.wlp = L.qkv_t.wlp + off;
+        if (L.qkv_t.wlp_p16) kv2.wlp_p16 = L.qkv_t.wlp_p16 + off;
+        UNIMM_TRY(linear(xt, Mt, q2, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
+        UNIMM_TRY(linear(xt, n_sh, kv2, ACT_NONE, nullptr, 0, nullptr, 0, byte_ptr(qkv_t) + e * Hb, 3 * Hb, st));
+    } else {
+        UNIMM_TRY(linear(xt, Mt, L.qkv_t, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
+    }
     if (ac.pk != nullptr) {
         const unimm_packed_batch_t& pk = *ac.pk;
         // text queries (shared + candidate rows of a unit) over the unit's image keys/values (:681-698)
@@ -852,6 +869,7 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     e->gelu_tanh = precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_GELU_TANH")) e->gelu_tanh = atoi(f) != 0;
     if (const char* f = getenv("UNIMM_ATTN_UMMA")) e->attn_umma = atoi(f) != 0;
+    if (const char* f = getenv("UNIMM_KV2_ALL")) e->kv2_ctx_only = atoi(f) == 0;
     e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;

@@ -85,6 +85,7 @@ class PackedBatch:
         s.kv_cap_text, s.win_cap = self.kv_cap_text, self.win_cap
         s.n_lm_rows = self.lm_rows.shape[0]
         s.pairs_text_self, s.pairs_i2t = float(self.pairs_text_self), float(self.pairs_i2t)
+        s.n_shared_rows = int(getattr(self, "n_shared_rows", 0))
         return s
 
 
@@ -181,7 +182,7 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt))
     max_rows_per_cand = int(all_rows.max())
     return PackedBatch(
-        n_units=U, n_cands=C_tot, n_text_rows=M,
+        n_units=U, n_cands=C_tot, n_text_rows=M, n_shared_rows=n_shared,
         input_ids=t(ids, np.int32), token_type_ids=t(segs, np.int32), position_ids=t(pos, np.int32), row_iv=t(row_iv, np.int32),
         jobs_text_self=t(np.asarray(jobs_ctx + jobs_cand), np.int32), n_jobs_text_ctx=len(jobs_ctx), cand_halo=max_rows_per_cand - 1, jobs_t2i=t(np.asarray(jobs_t2i), np.int32),
         jobs_i2t=t(np.asarray(jobs_i2t), np.int32), jobs_img_self=t(np.asarray(jobs_img), np.int32),
