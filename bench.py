@@ -143,7 +143,7 @@ def run_step_host(eng, b, chunk, score_host, HostArrays):
     return h2d, d2h
 
 
-def packed_step_batch(first_image, n_images, stride):
+def packed_step_batch(first_image, n_images, stride, scores_only=True):
     """One prefix-shared step: n_images synthetic images x 10 rounds x 100 candidates, packed (pinned host tensors)."""
     from unimm_b200 import synthetic as syn
     from unimm_b200.packing import pack_units, units_from_rounds
@@ -153,7 +153,7 @@ def packed_step_batch(first_image, n_images, stride):
         rounds += rs
         slots += [i] * len(rs)
         feats.append(feat), locs.append(loc), masks.append(mask)
-    pb = pack_units(units_from_rounds(rounds, slots), np.stack(feats), np.stack(locs), np.stack(masks))
+    pb = pack_units(units_from_rounds(rounds, slots), np.stack(feats), np.stack(locs), np.stack(masks), scores_only=scores_only)
     return pb.pin()
 
 
@@ -228,7 +228,7 @@ def main_ours(args):
     stream = torch.cuda.current_stream(dev)
     if packed:
         cands_per_step = args.images_per_step * SEQ_PER_IMAGE
-        host = [packed_step_batch((rank + world * i) * args.images_per_step, args.images_per_step, 1) for i in range(n_batches)]
+        host = [packed_step_batch((rank + world * i) * args.images_per_step, args.images_per_step, 1, not args.nsp_rows) for i in range(n_batches)]
         cap = max(max(-(-pb.n_text_rows // 256) for pb in host), max(pb.n_units for pb in host)) + 1    # workspace in 256-row units
     else:
         cap = chunk
@@ -346,6 +346,9 @@ def main_ours(args):
         if packed:
             cfg_d["packed_text_rows_per_step"] = packed_rows
             cfg_d["dense_text_rows_per_step"] = cands_per_step * 256
+            cfg_d["candidate_rows"] = ("CLS + A + B (NSP logits available)" if args.nsp_rows else
+                                       "scores only: the [CLS] and A_last rows, which no labelled position attends and only the NSP logit "
+                                       "(fetched but unused by val_lm.py:124-139) reads, are not packed")
             cfg_d["note"] = ("prefix-shared layout: context + image rows once per round (SURVEY.md F5); roofline and % of peak count "
                              "EXECUTED FLOPs only; dense_equivalent_speedup = dense FLOPs / executed FLOPs")
         else:
@@ -388,6 +391,7 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", type=int, default=250)
     ap.add_argument("--mode", default="packed", choices=["packed", "dense"], help="packed = prefix-shared rows (default); dense = one 256-row sequence per candidate, as the reference computes it")
     ap.add_argument("--images-per-step", type=int, default=8)
+    ap.add_argument("--nsp-rows", action="store_true", help="packed mode: keep the [CLS] and A_last rows that only the (unused) NSP logit reads")
     ap.add_argument("--cpu-sample", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

@@ -141,6 +141,8 @@ typedef struct {
     double pairs_text_self, pairs_i2t;           /* sum over jobs of q_len * keys (profiling only)             */
     int32_t n_shared_rows;                       /* rows [0, n_shared_rows) are the units' context rows: the only text rows whose
                                                   * co-attention keys / values anything reads (0 = unknown: project all rows) */
+    int32_t no_cls_rows;                         /* 1: packed for the sequence scores only — the candidates carry no [CLS] row (and no
+                                                  * A_{last-1} row), d_cand_cls_row is unused and NSP scores cannot be requested   */
 } unimm_packed_batch_t;
 /* outputs (each optional): seq_score [C], nsp_scores [C,2], token_logp [n_lm] */
 int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, float* d_seq_score, float* d_nsp_scores,

@@ -48,8 +48,8 @@ def engine(full_cfg, step):
     eng.close()
 
 
-def packed_scores(eng, rounds, slots, feat, loc, mask):
-    pb = pack_units(units_from_rounds(rounds, slots), feat, loc, mask)
+def packed_scores(eng, rounds, slots, feat, loc, mask, scores_only=False):
+    pb = pack_units(units_from_rounds(rounds, slots), feat, loc, mask, scores_only=scores_only)
     out = eng.forward_packed(pb.to(eng.device), want=("seq_score",))["seq_score"]
     torch.cuda.synchronize()
     return out.cpu().numpy(), pb
@@ -77,6 +77,12 @@ def test_packed_equals_dense_at_bench_size(engine, step):
           f"top-1 agreement {(p.argmax(1) == d.argmax(1)).mean():.3f}")
     assert diff.max() < TOL
     assert (top_gap < TOL).all()
+    # scores-only packing (what bench.py and the sweep driver run): 2 rows fewer per candidate, same scores
+    lean, pl = packed_scores(engine, rounds, slots, feat, loc, mask, scores_only=True)
+    assert pl.n_text_rows == pb.n_text_rows - 2 * pb.n_cands
+    d_lean = np.abs(lean - dense)
+    print(f"scores-only packing ({pl.n_text_rows} rows) vs dense: max |diff| {d_lean.max():.3e}; vs full packing {np.abs(lean - packed).max():.3e}")
+    assert d_lean.max() < TOL and np.abs(lean - packed).max() < 5e-3
 
 
 def test_candidate_permutation_and_duplicates(engine, step):

@@ -8,7 +8,7 @@ from unimm_b200.descriptors import dense_text_mask, descriptors_from_masks
 from unimm_b200.packing import pack_units, units_from_flat, units_from_rounds
 
 
-def _check(pb, rounds):
+def _check(pb, rounds, scores_only=False):
     iv, jobs = pb.row_iv.numpy(), pb.jobs_text_self.numpy()
     lab, off = pb.lm_labels.numpy(), pb.cand_lm_off.numpy()
     c = 0
@@ -22,20 +22,23 @@ def _check(pb, rounds):
         row = int(cj[0])
         for j in range(len(r.desc)):
             L, last = int(r.desc[j, 2]), int(r.desc[j, 3])
-            assert pb.cand_cls_row[c] == row
-            for idx in range(1 + 2 * last):
-                col = 0 if idx == 0 else ctx + idx - 1
+            # dense columns of the candidate's packed rows, in packed order
+            cols = ([] if scores_only else [0]) + [ctx + k for k in range(last - (1 if scores_only else 0))] + [L + k for k in range(last)]
+            assert pb.cand_cls_row[c] == (-1 if scores_only else row)
+            first = row
+            for idx, col in enumerate(cols):
                 allowed = set(range(1, ctx))
                 lo, hi, sf = iv[row, :3]
                 for a in list(range(lo, hi)) + ([sf] if sf >= 0 else []):
-                    k = a - (row - idx)
-                    assert 0 <= k <= 2 * last, "a row may only see rows of its own candidate"
-                    allowed.add(0 if k == 0 else ctx + k - 1)
+                    assert 0 <= a - first < len(cols), "a row may only see rows of its own candidate"
+                    allowed.add(cols[a - first])
+                # the packed row sees exactly what the dense mask lets this position see (so every key it needs is a kept row)
                 assert allowed == set(np.nonzero(dm[j, col])[0].tolist()), (ui, j, idx)
                 assert pb.input_ids[row] == r.tokens[j, col] and pb.position_ids[row] == r.positions[j, col]
                 assert pb.token_type_ids[row] == r.segments[j, col]
                 row += 1
             assert (lab[off[c]:off[c + 1]] == r.labels[j, L:L + last]).all()
+            assert (pb.lm_rows[off[c]:off[c + 1]].numpy() == np.arange(row - last, row)).all()       # the labelled rows are the B rows
             c += 1
     assert c == pb.n_cands and pb.win_cap % 64 == 0 and pb.kv_cap_text % 64 == 0 and pb.kv_cap_text <= 256
 
@@ -47,6 +50,22 @@ def test_packed_rows_reproduce_dense_masks_and_tokens():
     pb = pack_units(units_from_rounds(rounds, [0, 0, 0]), img[0][None], img[1][None], img[2][None])
     _check(pb, rounds)
     assert pb.n_text_rows == sum(int(r.desc[0, 1]) - 1 + int((1 + 2 * r.desc[:, 3]).sum()) for r in rounds)
+
+
+def test_scores_only_packing_drops_only_rows_nothing_labelled_can_see():
+    """scores_only: no [CLS], no A_{last-1}.  _check proves that every kept row's packed key set equals its dense-mask key set,
+    i.e. the kept rows are closed under "is attended by" — the dropped rows can only change the pooled NSP logit."""
+    rng = np.random.RandomState(5)
+    img = syn.synth_image(rng)
+    rounds = [syn.encode_round_gen(syn.synth_context(rng, r), syn.synth_answers(rng, n)) for r, n in ((1, 7), (3, 12), (10, 9))]
+    pb = pack_units(units_from_rounds(rounds, [0, 0, 0]), img[0][None], img[1][None], img[2][None], scores_only=True)
+    _check(pb, rounds, scores_only=True)
+    full = pack_units(units_from_rounds(rounds, [0, 0, 0]), img[0][None], img[1][None], img[2][None])
+    assert pb.n_text_rows == full.n_text_rows - 2 * pb.n_cands and pb.c_struct().no_cls_rows == 1 and full.c_struct().no_cls_rows == 0
+    assert (pb.lm_labels == full.lm_labels).all() and (pb.cand_lm_off == full.cand_lm_off).all()
+    # the image rows never look at candidate rows at all (co-attention interval = the context rows)
+    for j in pb.jobs_i2t.numpy():
+        assert j[2] + j[3] <= pb.n_shared_rows
 
 
 def test_packing_the_reference_made_inputs():

@@ -223,6 +223,38 @@ def test_prefix_shared_scores_match_reference(full_cfg, precision):
         assert flips == 0
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+def test_scores_only_packing_matches_reference(full_cfg, precision):
+    """scores_only packing (no [CLS] / A_{last-1} rows: nothing labelled sees them) reproduces the reference's 100 sequence
+    log-likelihoods and ranks; NSP logits cannot be asked of such a batch."""
+    from oracle import visdial_metrics as om
+    from unimm_b200.packing import pack_units, units_from_flat
+    g, batch = load_golden("gen100_default")
+    eng = get_engine(full_cfg, g, precision)
+    desc = descriptors_from_masks(batch["txt_attention_mask"], batch["co_attention_mask"])
+    units = units_from_flat(batch["tokens"], batch["segments"], batch["positions"], batch["mask"], desc, np.zeros(100, np.int64))
+    full = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None])
+    pb = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None], scores_only=True)
+    assert pb.n_text_rows == full.n_text_rows - 200
+    out = eng.forward_packed(pb.to(eng.device), want=("seq_score", "token_logp"))
+    ref = eng.forward_packed(full.to(eng.device), want=("seq_score", "token_logp"))
+    score = out["seq_score"].cpu()
+    err = np.abs(score.numpy() - g["seq_score"]).max()
+    d_full = (out["token_logp"] - ref["token_logp"]).abs().max().item()
+    flips = int((om.scores_to_ranks(score.view(1, 1, 100)).view(100).numpy() != g["ranks"]).sum())
+    print(f"[{precision}] scores-only packing, config 1: seq_score err {err:.3e}  token log p vs full packing {d_full:.3e}  "
+          f"rank changes {flips}/100  ({pb.n_text_rows} packed text rows)")
+    assert err < TIGHT[precision]
+    assert d_full < (2e-5 if precision == "fp32" else TIGHT[precision])
+    if precision == "fp32":
+        assert flips == 0
+        with pytest.raises(RuntimeError, match="CLS"):
+            eng.forward_packed(pb.to(eng.device), want=("seq_score", "nsp_scores"))
+        score_h = torch.zeros(100).pin_memory()
+        eng.score_packed_host(pb.pin(), score_h)
+        np.testing.assert_allclose(score_h.numpy(), score.numpy(), atol=1e-6, rtol=0)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_prefix_shared_equals_dense_path_multi_unit(full_cfg, precision):
     """Several rounds of different context lengths in one packed forward vs the dense per-sequence forward."""

@@ -770,6 +770,7 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
     UNIMM_CHECK(static_cast<long long>(M) <= static_cast<long long>(Bmax) * c.seq_len && U <= Bmax, "packed batch exceeds the engine workspace");
     UNIMM_CHECK(in.kv_cap_text > 0 && in.kv_cap_text <= 256 && in.kv_cap_text % 64 == 0 && in.win_cap % 64 == 0, "bad staging capacities");
     UNIMM_CHECK(in.n_lm_rows >= 0 && in.n_lm_rows <= M, "n_lm_rows out of range");
+    UNIMM_CHECK(!(d_nsp_scores && in.no_cls_rows), "NSP scores requested from a batch packed without [CLS] rows (scores_only)");
     const int Mv = U * R;
     UNIMM_TRY(embed_text_ln_i32(in.d_input_ids, in.d_token_type_ids, in.d_position_ids, M, H, c.vocab_size, c.max_position_embeddings,
                                 c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h, lp_kind(),

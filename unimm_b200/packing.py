@@ -20,6 +20,12 @@ Which keys a packed row attends (equals the dense mask restricted to real rows):
     B_k                 shared rows + A_0..A_{k-1} + itself                     (dense: [1, j-last) U {j})
     image region        the unit's image rows (self) / the unit's shared rows (co-attention)
     any text row        the unit's image rows in the text->image co-attention
+
+``scores_only=True`` additionally drops the candidate rows that no labelled position can see: [CLS] (position 0 is outside
+every other row's interval) and A_{last-1} (the visible copy's closing [SEP]: B_k sees A_0..A_{k-1} with k <= last-1, A_k sees
+A_0..A_k).  They only feed the pooled NSP logit, which val_lm.py:124 fetches but never uses for the ranking, so a candidate
+then costs 2*last_len - 1 rows instead of 2*last_len + 1 and the sequence log-likelihoods are unchanged
+(tests/test_packing_cpu.py proves the closure on the dense masks; tests/test_parity_gpu.py compares the scores).
 """
 from __future__ import annotations
 
@@ -86,6 +92,7 @@ class PackedBatch:
         s.n_lm_rows = self.lm_rows.shape[0]
         s.pairs_text_self, s.pairs_i2t = float(self.pairs_text_self), float(self.pairs_i2t)
         s.n_shared_rows = int(getattr(self, "n_shared_rows", 0))
+        s.no_cls_rows = int(bool(getattr(self, "scores_only", False)))
         return s
 
 
@@ -94,10 +101,12 @@ def _roundup(x: int, m: int) -> int:
 
 
 def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: np.ndarray, image_mask: np.ndarray,
-               R: int = R_DEFAULT, verify_shared: bool = True) -> PackedBatch:
+               R: int = R_DEFAULT, verify_shared: bool = True, scores_only: bool = False) -> PackedBatch:
     """Pack generative-mode units.  ``image_*`` hold one block per *slot* ([n_slots,R,...]); a unit's image rows are
     gathered from ``unit.image_slot`` (so the 10 rounds of an image can share one host copy)."""
     U = len(units)
+    n_cls = 0 if scores_only else 1           # [CLS] rows per candidate
+    a_drop = 1 if scores_only else 0          # visible-copy rows dropped from the end (A_{last-1})
     sh_len, n_cand, cand_rows = [], [], []
     for u in units:
         d = u.desc
@@ -113,7 +122,7 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
                 raise ValueError("candidates of a unit differ in their context rows: cannot share the prefix")
         sh_len.append(ctx - 1)
         n_cand.append(len(d))
-        cand_rows.append(1 + 2 * d[:, 3].astype(np.int64))
+        cand_rows.append(n_cls - a_drop + 2 * d[:, 3].astype(np.int64))
     sh_start = np.concatenate([[0], np.cumsum(sh_len)])
     n_shared = int(sh_start[-1])
     all_rows = np.concatenate(cand_rows)
@@ -143,29 +152,33 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
         L = u.desc[:, 2].astype(np.int64)
         cs = c_start[ci:ci + n]                                   # absolute first row of each candidate
         rows_u = int(c_start[ci + n] - c_start[ci])
-        # per-candidate row index inside the candidate: 0 = CLS, 1..last = A, last+1..2last = B
-        rep = 1 + 2 * last
+        # per-candidate row index inside the candidate: [CLS] (n_cls rows), A_0..A_{na-1}, B_0..B_{last-1}
+        rep = n_cls - a_drop + 2 * last
         owner = np.repeat(np.arange(n), rep)
         idx = np.arange(rows_u) - np.repeat(cs - cs[0], rep)
-        src_col = np.where(idx == 0, 0, ctx + idx - 1)            # dense column this packed row comes from
+        s_abs = np.repeat(cs, rep)
+        last_r = np.repeat(last, rep)
+        na_r = last_r - a_drop
+        is_cls, is_b = idx < n_cls, idx >= n_cls + na_r
+        is_a = ~is_cls & ~is_b
+        k = np.where(is_b, idx - n_cls - na_r, idx - n_cls)       # index inside the A / B copy
+        src_col = np.where(is_cls, 0, np.where(is_a, ctx + k, ctx + last_r + k))   # dense column this packed row comes from
         dst = int(cs[0]) + np.arange(rows_u)
         ids[dst] = u.tokens[owner, src_col]
         segs[dst] = u.segments[owner, src_col]
         pos[dst] = u.positions[owner, src_col]
-        s_abs = np.repeat(cs, rep)
-        last_r = np.repeat(last, rep)
-        is_cls, is_a, is_b = idx == 0, (idx >= 1) & (idx <= last_r), idx > last_r
-        lo = np.where(is_cls, s_abs, s_abs + 1)
-        hi = np.where(is_cls, s_abs + 1 + 2 * last_r, np.where(is_a, s_abs + idx + 1, s_abs + idx - last_r))
+        a0 = s_abs + n_cls                                        # first A row of the candidate
+        lo = np.where(is_cls, s_abs, a0)
+        hi = np.where(is_cls, s_abs + rep[owner], np.where(is_a, a0 + k + 1, a0 + k))
         row_iv[dst, 0], row_iv[dst, 1] = lo, hi
         row_iv[dst, 2] = np.where(is_b, dst, -1)
-        own_keys = np.where(is_cls, 1 + 2 * last_r, np.where(is_a, idx, idx - last_r))   # own-candidate keys incl. self
+        own_keys = np.where(is_cls, rep[owner], k + 1)            # own-candidate keys incl. self
         pairs_ts += (ctx - 1) ** 2 + int(((ctx - 1) + own_keys).sum())
         pairs_i2t += R * (ctx - 1)
         lm_rows.append(dst[is_b])
-        lm_labels.append(u.labels[owner[is_b], (L[owner] + idx - last_r - 1)[is_b]])
+        lm_labels.append(u.labels[owner[is_b], (L[owner] + k)[is_b]])
         cand_lm_off.extend((cand_lm_off[-1] + np.cumsum(last)).tolist())
-        cls_row[ci:ci + n] = cs
+        cls_row[ci:ci + n] = cs if n_cls else -1
         img_row[ci:ci + n] = ui * R
         jobs_ctx.append((s0, ctx - 1, s0, ctx - 1, 0, -1, 0, 0))
         jobs_cand.append((int(cs[0]), rows_u, s0, ctx - 1, 1, -1, 0, 0))
@@ -182,7 +195,7 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt))
     max_rows_per_cand = int(all_rows.max())
     return PackedBatch(
-        n_units=U, n_cands=C_tot, n_text_rows=M, n_shared_rows=n_shared,
+        n_units=U, n_cands=C_tot, n_text_rows=M, n_shared_rows=n_shared, scores_only=bool(scores_only),
         input_ids=t(ids, np.int32), token_type_ids=t(segs, np.int32), position_ids=t(pos, np.int32), row_iv=t(row_iv, np.int32),
         jobs_text_self=t(np.asarray(jobs_ctx + jobs_cand), np.int32), n_jobs_text_ctx=len(jobs_ctx), cand_halo=max_rows_per_cand - 1, jobs_t2i=t(np.asarray(jobs_t2i), np.int32),
         jobs_i2t=t(np.asarray(jobs_i2t), np.int32), jobs_img_self=t(np.asarray(jobs_img), np.int32),

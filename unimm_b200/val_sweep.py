@@ -65,7 +65,7 @@ def packed_scorer(engine) -> Callable[[List[DialogItem]], torch.Tensor]:
             rounds += list(it.rounds)
             slots += [s] * len(it.rounds)
         pb = pack_units(units_from_rounds(rounds, slots), np.stack([it.feat for it in items]), np.stack([it.loc for it in items]),
-                        np.stack([it.mask for it in items])).pin()
+                        np.stack([it.mask for it in items]), scores_only=True).pin()   # the ranking reads the LM scores only (val_lm.py:124-139)
         out = torch.empty(pb.n_cands, dtype=torch.float32).pin_memory()
         engine.score_packed_host(pb, out)
         n_rounds = len(items[0].rounds)
