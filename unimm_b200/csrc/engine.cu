@@ -100,6 +100,8 @@ struct unimm_engine {
 
     // workspace (sized for Bmax sequences)
     ActBuf xt, xv;            // hidden states: fp32 master (+ bf16 shadow in bf16 mode)
+    ActBuf xk;                // scores-only packed batches: the labelled rows' stream through the tail of the LAST text layer
+    bool xk_live = false;     // the last forward left its final text rows in xk (row i = labelled row i) instead of xt
     float *pre_t = nullptr, *pre_v = nullptr;   // pre-LayerNorm fp32
     void *qkv_t = nullptr, *qkv_v = nullptr, *ctx_t = nullptr, *ctx_v = nullptr, *ffn_t = nullptr, *ffn_v = nullptr;
     void* feat_a = nullptr;        // gathered image features (GEMM operand)
@@ -174,6 +176,8 @@ struct unimm_engine {
                   ActBuf& out, cudaStream_t st);
     bool fuse_ln = true;
     bool gelu_tanh = false;      // 1-SFU tanh-form GELU in the FFN-1 epilogue (|err| <= |x| * 2.4e-4): default in fp16 mode, UNIMM_GELU_TANH overrides
+    bool prune_tail = true;      // scores-only packed batches: skip everything after the last connection that only the pooled NSP
+                                 // logit reads, and run the last text layer's out-proj / FFN on the labelled rows only (UNIMM_PRUNE_TAIL=0 disables)
     bool kv2_ctx_only = true;    // packed layout: co-attention K2 | V2 for the context rows only (UNIMM_KV2_ALL=1 projects every row)
     bool attn_umma = true;       // candidate-row attention on tcgen05 (attention_umma.cu); UNIMM_ATTN_UMMA=0 keeps the mma.sync kernel
     bool frag_epilogue = true;   // QKV / FFN-1 GEMMs read fragment-ordered weight copies (UNIMM_FRAG_EPILOGUE=0 disables)
@@ -193,11 +197,15 @@ struct unimm_engine {
     int attention_packed(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int heads, int D,
                          const int* jobs, int n_jobs, int max_q, int kv_cap, int win_cap, double qk_pairs, const AttnCtx& ac,
                          cudaStream_t st);
+    // keep_rows != nullptr: after the attention only these n_keep rows continue (gathered into x_keep, which the layer's output then is)
     int self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int M, int heads, bool text,
-                   const AttnCtx& ac, cudaStream_t st);
-    int conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& ac, cudaStream_t st);
+                   const AttnCtx& ac, cudaStream_t st, const int* keep_rows = nullptr, int n_keep = 0, ActBuf* x_keep = nullptr);
+    // image_out = false: the image stream's own update (image->text attention, dense1, image FFN) is skipped — nothing reads it
+    int self_layer_tail(const SelfLayer& L, const ActBuf& c, ActBuf& x, float* pre, void* ffn, int M, cudaStream_t st);
+    int conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& ac, cudaStream_t st, bool image_out = true);
     int run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st);
-    int lm_head_rows(const int* d_rows, const int* d_labels, int n, cudaStream_t st);
+    // d_rows == nullptr: src's rows [0, n) are the labelled rows already
+    int lm_head_rows(const ActBuf& src, const int* d_rows, const int* d_labels, int n, cudaStream_t st);
     int forward(const unimm_batch_t& in, const unimm_outputs_t& out, cudaStream_t st);
     int forward_packed(const unimm_packed_batch_t& in, float* d_seq_score, float* d_nsp_scores, float* d_token_logp, cudaStream_t st);
 };
@@ -371,6 +379,8 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&xt.f, Mt * H)); xt.ld = H;
     UNIMM_TRY(dalloc(&xv.f, Mv * Hv)); xv.ld = Hv;
     if (lp()) { UNIMM_TRY(dalloc(&xt.h, Mt * H)); UNIMM_TRY(dalloc(&xv.h, Mv * Hv)); }
+    UNIMM_TRY(dalloc(&xk.f, Mt * H)); xk.ld = H;
+    if (lp()) UNIMM_TRY(dalloc(&xk.h, Mt * H));
     UNIMM_TRY(dalloc(&pre_t, Mt * H));
     UNIMM_TRY(dalloc(&pre_v, Mv * Hv));
     char* p;
@@ -500,8 +510,10 @@ int unimm_engine::attention_packed(const void* q, int ldq, const void* k, int ld
 }
 
 // BertLayer / BertImageLayer: QKV -> attention -> out-proj + residual -> LN -> FFN1+GELU -> FFN2 + residual -> LN
-int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qkv, void* ctx, void* ffn, int M, int heads, bool text,
-                             const AttnCtx& ac, cudaStream_t st) {
+int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x_in, float* pre, void* qkv, void* ctx, void* ffn, int M_in, int heads, bool text,
+                             const AttnCtx& ac, cudaStream_t st, const int* keep_rows, int n_keep, ActBuf* x_keep) {
+    ActBuf& x = x_in;
+    const int M = M_in;
     const int H = x.ld, D = H / heads;
     const size_t e = esz();
     UNIMM_TRY(linear(x, M, L.qkv, ACT_NONE, nullptr, 0, nullptr, 0, qkv, 3 * H, st));
@@ -549,6 +561,26 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x, float* pre, void* qk
 attention_done:
     ActBuf c;
     c.f = lp() ? nullptr : static_cast<float*>(ctx); c.h = lp() ? static_cast<bf16*>(ctx) : nullptr; c.ld = H;
+    if (keep_rows != nullptr) {
+        // only n_keep rows are read downstream: gather their attention context (into the FFN buffer, free until FFN-1 writes it)
+        // and their residual stream (into x_keep), and run the row-wise rest of the layer on those rows alone
+        UNIMM_CHECK(x_keep != nullptr && n_keep > 0 && n_keep <= M, "self_layer: bad row subset");
+        ActBuf cc;
+        cc.f = lp() ? nullptr : static_cast<float*>(ffn); cc.h = lp() ? static_cast<bf16*>(ffn) : nullptr; cc.ld = H;
+        const bool f32_live = !(lp() && fuse_ln && res16);     // the 16-bit residual mode keeps only x.h current
+        {
+            Prof prof(this, CAT_ROWWISE, (2.0 * esz() + (f32_live ? 8.0 : 0.0) + (lp() ? 4.0 : 0.0)) * n_keep * H, st);
+            UNIMM_TRY(gather_rows(c.f, c.h, keep_rows, n_keep, H, cc.f, cc.h, st));
+            UNIMM_TRY(gather_rows(f32_live ? x.f : nullptr, x.h, keep_rows, n_keep, H, f32_live ? x_keep->f : nullptr, lp() ? x_keep->h : nullptr, st));
+        }
+        return self_layer_tail(L, cc, *x_keep, pre, ffn, n_keep, st);
+    }
+    return self_layer_tail(L, c, x, pre, ffn, M, st);
+}
+
+// out-proj + residual -> LN -> FFN1+GELU -> FFN2 + residual -> LN on rows [0, M) of (attention context c, stream x)
+int unimm_engine::self_layer_tail(const SelfLayer& L, const ActBuf& c, ActBuf& x, float* pre, void* ffn, int M, cudaStream_t st) {
+    const int H = x.ld;
     UNIMM_TRY(linear_ln(c, M, L.out, x.f, H, L.ln1, pre, x, st));
     const int I = L.ffn1.N;
     UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st));
@@ -559,14 +591,20 @@ attention_done:
 }
 
 // BertConnectionLayer (reference :770-783): stream 1 = image, stream 2 = text
-int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& ac, cudaStream_t st) {
+int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& ac, cudaStream_t st, bool image_out) {
     const unimm_config_t& c = cfg;
     const int S = c.seq_len, R = c.num_regions, H = c.hidden_size, Hv = c.v_hidden_size, Hb = c.bi_hidden_size;
     const int heads = c.bi_num_attention_heads, D = Hb / heads;
     const size_t e = esz();
     UNIMM_TRY(linear(xv, Mv, L.qkv_v, ACT_NONE, nullptr, 0, nullptr, 0, qkv_v, 3 * Hb, st));
     const int n_sh = (ac.pk != nullptr && kv2_ctx_only) ? ac.pk->n_shared_rows : 0;
-    if (n_sh > 0 && n_sh < Mt && L.qkv_t.w32 != nullptr) {
+    UNIMM_CHECK(image_out || ac.pk != nullptr, "conn_layer: the image update can only be skipped in the packed layout");
+    if (!image_out) {
+        // nothing reads this layer's image output (scores-only batch, last connection): no image queries, hence no K2 | V2 at all
+        Linear q2 = L.qkv_t;
+        q2.N = Hb;
+        UNIMM_TRY(linear(xt, Mt, q2, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
+    } else if (n_sh > 0 && n_sh < Mt && L.qkv_t.w32 != nullptr) {
         // prefix-shared layout: the image rows attend ONLY the context rows (co-mask [1,ctx), utils/data_utils.py:199-210), so the
         // text-side keys / values K2 | V2 (:670-672) of the candidate rows — 86 % of the text rows — are never read: project the
         // queries Q2 for all rows, K2 | V2 for the context rows [0, n_shared) only (the packer puts them first)
@@ -590,7 +628,7 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
         UNIMM_TRY(attention_packed(qkv_t, 3 * Hb, byte_ptr(qkv_v) + e * Hb, 3 * Hb, byte_ptr(qkv_v) + e * 2 * Hb, 3 * Hb, ctx_t, Hb, heads, D,
                                    pk.d_jobs_t2i, pk.n_jobs_t2i, pk.max_q_t2i, 64, 0, static_cast<double>(Mt) * R, ax, st));
         // image queries over the unit's context rows = the co-attention interval [1,ctx) (:701-721)
-        UNIMM_TRY(attention_packed(qkv_v, 3 * Hb, byte_ptr(qkv_t) + e * Hb, 3 * Hb, byte_ptr(qkv_t) + e * 2 * Hb, 3 * Hb, ctx_v, Hb, heads, D,
+        if (image_out) UNIMM_TRY(attention_packed(qkv_v, 3 * Hb, byte_ptr(qkv_t) + e * Hb, 3 * Hb, byte_ptr(qkv_t) + e * 2 * Hb, 3 * Hb, ctx_v, Hb, heads, D,
                                    pk.d_jobs_i2t, pk.n_jobs_i2t, R, pk.kv_cap_text, 0, pk.pairs_i2t, ac, st));
     } else {
         // text queries over image keys/values, image padding mask only (:681-698)
@@ -604,14 +642,16 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
     cv.f = lp() ? nullptr : static_cast<float*>(ctx_v); cv.h = lp() ? static_cast<bf16*>(ctx_v) : nullptr; cv.ld = Hb;
     ct.f = lp() ? nullptr : static_cast<float*>(ctx_t); ct.h = lp() ? static_cast<bf16*>(ctx_t) : nullptr; ct.ld = Hb;
     // BertBiOutput (:744-754): image rows take the image-query context through dense1, text rows the other through dense2
-    UNIMM_TRY(linear_ln(cv, Mv, L.dense1, xv.f, Hv, L.ln1, pre_v, xv, st));
+    if (image_out) UNIMM_TRY(linear_ln(cv, Mv, L.dense1, xv.f, Hv, L.ln1, pre_v, xv, st));
     UNIMM_TRY(linear_ln(ct, Mt, L.dense2, xt.f, H, L.ln2, pre_t, xt, st));
     // image FFN, text FFN (:777-781)
     const int Iv = L.v_ffn1.N, I = L.t_ffn1.N;
-    UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st));
-    ActBuf fv;
-    fv.f = lp() ? nullptr : static_cast<float*>(ffn_v); fv.h = lp() ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
-    UNIMM_TRY(linear_ln(fv, Mv, L.v_ffn2, xv.f, Hv, L.v_ln, pre_v, xv, st));
+    if (image_out) {
+        UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st));
+        ActBuf fv;
+        fv.f = lp() ? nullptr : static_cast<float*>(ffn_v); fv.h = lp() ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
+        UNIMM_TRY(linear_ln(fv, Mv, L.v_ffn2, xv.f, Hv, L.v_ln, pre_v, xv, st));
+    }
     UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st));
     ActBuf ft;
     ft.f = lp() ? nullptr : static_cast<float*>(ffn_t); ft.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; ft.ld = I;
@@ -675,7 +715,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     if (n > 0) {
         UNIMM_CHECK(in.d_lm_rows && in.d_masked_lm_labels, "lm rows given without labels");
         UNIMM_TRY(gather_labels(in.d_masked_lm_labels, in.d_lm_rows, n, g_labels, st));
-        UNIMM_TRY(lm_head_rows(in.d_lm_rows, g_labels, n, st));
+        UNIMM_TRY(lm_head_rows(xt, in.d_lm_rows, g_labels, n, st));
     }
     if (out.d_seq_score || out.d_token_logp || out.d_token_ul)
         UNIMM_TRY(scatter_scores(row_logp, row_ul, in.d_lm_rows, n, B, S, out.d_token_logp, out.d_token_ul, out.d_seq_score, st));
@@ -712,15 +752,30 @@ int unimm_engine::run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st
     int v_start = 0, t_start = 0;
     auto run_v = [&](int i) { return self_layer(v_layers[i], xv, pre_v, qkv_v, ctx_v, ffn_v, Mv, c.v_num_attention_heads, false, ac, st); };
     auto run_t = [&](int i) { return self_layer(t_layers[i], xt, pre_t, qkv_t, ctx_t, ffn_t, Mt, c.num_attention_heads, true, ac, st); };
+    // Scores-only packed batch (no [CLS] rows, only the labelled rows' log-likelihoods are asked for): after the last connection
+    // the image stream feeds nothing but the pooled NSP logit (:946-967), and of the last text layer's output only the labelled
+    // rows reach the LM head — the other rows matter to that layer as keys / values alone.
+    const bool lean = prune_tail && ac.pk != nullptr && ac.pk->no_cls_rows && ac.pk->n_lm_rows > 0 && c.num_connections > 0;
+    xk_live = false;
     for (int k = 0; k < c.num_connections; ++k) {
         for (int i = v_start; i < c.v_biattention_id[k]; ++i) UNIMM_TRY(run_v(i));
         for (int i = t_start; i < c.t_biattention_id[k]; ++i) UNIMM_TRY(run_t(i));
-        UNIMM_TRY(conn_layer(c_layers[k], Mt, Mv, ac, st));
+        UNIMM_TRY(conn_layer(c_layers[k], Mt, Mv, ac, st, !(lean && k == c.num_connections - 1)));
         v_start = c.v_biattention_id[k];
         t_start = c.t_biattention_id[k];
     }
-    for (int i = v_start; i < c.v_num_hidden_layers; ++i) UNIMM_TRY(run_v(i));
-    for (int i = t_start; i < c.num_hidden_layers; ++i) UNIMM_TRY(run_t(i));
+    if (!lean) {
+        for (int i = v_start; i < c.v_num_hidden_layers; ++i) UNIMM_TRY(run_v(i));
+        for (int i = t_start; i < c.num_hidden_layers; ++i) UNIMM_TRY(run_t(i));
+    } else {
+        for (int i = t_start; i < c.num_hidden_layers - 1; ++i) UNIMM_TRY(run_t(i));
+        if (t_start < c.num_hidden_layers) {
+            UNIMM_TRY(self_layer(t_layers[c.num_hidden_layers - 1], xt, pre_t, qkv_t, ctx_t, ffn_t, Mt, c.num_attention_heads, true, ac, st,
+                                 ac.pk->d_lm_rows, ac.pk->n_lm_rows, &xk));
+            xk_live = true;
+        }
+        return 0;     // nobody reads the fp32 views of a scores-only batch
+    }
     if (lp() && fuse_ln && res16) {   // the poolers and the optional sequence outputs read the fp32 view
         Prof prof(this, CAT_ROWWISE, 6.0 * (static_cast<double>(Mt) * xt.ld + static_cast<double>(Mv) * xv.ld), st);
         UNIMM_TRY(cast_lp_to_f32(xt.h, xt.f, static_cast<size_t>(Mt) * xt.ld, lp_kind(), st));
@@ -730,11 +785,12 @@ int unimm_engine::run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st
 }
 
 // gathered LM head (reference :982-986, :1023-1026 on the labelled rows only): fills row_logp / row_ul [n]
-int unimm_engine::lm_head_rows(const int* d_rows, const int* d_labels, int n, cudaStream_t st) {
+int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* d_labels, int n, cudaStream_t st) {
     const unimm_config_t& c = cfg;
     const int H = c.hidden_size;
-    UNIMM_TRY(gather_rows(lp() ? nullptr : xt.f, lp() ? xt.h : nullptr, d_rows, n, H, lp() ? nullptr : g_in.f, lp() ? g_in.h : nullptr, st));
-    UNIMM_TRY(linear(g_in, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
+    if (d_rows != nullptr)
+        UNIMM_TRY(gather_rows(lp() ? nullptr : src.f, lp() ? src.h : nullptr, d_rows, n, H, lp() ? nullptr : g_in.f, lp() ? g_in.h : nullptr, st));
+    UNIMM_TRY(linear(d_rows != nullptr ? g_in : src, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
     { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, lp_kind(), st)); }
     if (lp()) {
         GemmEpilogue ep;
@@ -790,7 +846,10 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
         UNIMM_TRY(pooler_nsp_indexed(xt.f, H, in.d_cand_cls_row, xv.f, Hv, in.d_cand_img_row, C, H, Hv, c.bi_hidden_size, tp_w, tp_b, vp_w, vp_b,
                                      nsp_w, nsp_b, d_nsp_scores, st));
     const int n = in.n_lm_rows;
-    if (n > 0) UNIMM_TRY(lm_head_rows(in.d_lm_rows, in.d_lm_labels, n, st));
+    if (n > 0) {
+        if (xk_live) UNIMM_TRY(lm_head_rows(xk, nullptr, in.d_lm_labels, n, st));       // the last text layer already gathered them
+        else UNIMM_TRY(lm_head_rows(xt, in.d_lm_rows, in.d_lm_labels, n, st));
+    }
     if (d_seq_score) UNIMM_TRY(segment_sum(row_logp, in.d_cand_lm_off, C, d_seq_score, st));
     if (d_token_logp && n > 0) UNIMM_CUDA_CHECK(cudaMemcpyAsync(d_token_logp, row_logp, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -871,6 +930,7 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     if (const char* f = getenv("UNIMM_GELU_TANH")) e->gelu_tanh = atoi(f) != 0;
     if (const char* f = getenv("UNIMM_ATTN_UMMA")) e->attn_umma = atoi(f) != 0;
     if (const char* f = getenv("UNIMM_KV2_ALL")) e->kv2_ctx_only = atoi(f) == 0;
+    if (const char* f = getenv("UNIMM_PRUNE_TAIL")) e->prune_tail = atoi(f) != 0;
     e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;
