@@ -147,6 +147,8 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t smem_base = ptx::smem_u32(smem);
+    ptx::grid_dep_launch_dependents();
+    ptx::grid_dep_wait();                  // the prologue above overlapped the previous kernel's tail; Q / K / V are its outputs
 
     if (warp == 0) {
         // ---------------------------------------------------------------- Q / window producer
@@ -539,7 +541,15 @@ int launch_umma(const AttnJobsArgs& a, cudaStream_t stream) {
     const int n_items = a.n_jobs * a.heads;
     const int grid = n_items < gemm_num_sms() ? n_items : gemm_num_sms();
     static int dbg = getenv("UNIMM_ATTN_DBG") ? atoi(getenv("UNIMM_ATTN_DBG")) : 0;   // timing experiments only (results invalid)
-    attn_cand_umma_kernel<FP16, DENSE><<<grid, 384, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmKw, tmVw, a, n_items, dbg);
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    add_pdl_attr(attr, &cfg.numAttrs);
+    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_cand_umma_kernel<FP16, DENSE>, tmQ, tmK, tmV, tmKw, tmVw, a, n_items, dbg));
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
@@ -609,6 +619,8 @@ attn_cross_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t smem_base = ptx::smem_u32(smem);
+    ptx::grid_dep_launch_dependents();
+    ptx::grid_dep_wait();                  // the prologue above overlapped the previous kernel's tail; Q / K / V are its outputs
 
     auto item_of = [&](int item, int& q_start, int& q_len, int& kv_start, int& kv_len, int& mask_row, int& head) {
         const int job = item / a.heads;
@@ -818,7 +830,15 @@ int launch_cross(const AttnJobsArgs& a, cudaStream_t stream) {
     UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_cross_umma_kernel<FP16>), x::XSMEM_BYTES));
     const int n_items = a.n_jobs * a.heads;
     const int grid = n_items < gemm_num_sms() ? n_items : gemm_num_sms();
-    attn_cross_umma_kernel<FP16><<<grid, 384, x::XSMEM_BYTES, stream>>>(tmQ, tmK, tmV, a, n_items);
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = x::XSMEM_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    add_pdl_attr(attr, &cfg.numAttrs);
+    UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_cross_umma_kernel<FP16>, tmQ, tmK, tmV, a, n_items));
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -43,6 +43,22 @@ void count_launches(int n);
         UNIMM_CUDA_CHECK(cudaGetLastError());   \
     } while (0)
 
+// Programmatic dependent launch (opt-in: UNIMM_PDL=1): kernels that execute griddepcontrol.wait before their first global access
+// are launched with this attribute, so that their prologue (CTA launch, barrier init, TMEM allocation, tensor-map prefetch) overlaps
+// the tail of the kernel before them.  Parity-green, but measured +-0.5 % on the bench step (the step is power-bound: idle gaps
+// between kernels are not lost time, they buy clock), so it stays off by default.
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("UNIMM_PDL"); v = e ? (atoi(e) != 0) : 0; }
+    return v != 0;
+}
+inline void add_pdl_attr(cudaLaunchAttribute* attr, unsigned* n) {
+    if (!pdl_enabled()) return;
+    attr[*n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[*n].val.programmaticStreamSerializationAllowed = 1;
+    ++*n;
+}
+
 #define UNIMM_TRY(expr)            \
     do {                           \
         int _rc = (expr);          \

@@ -106,6 +106,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch_dependents();
+    ptx::grid_dep_wait();                  // everything above overlapped the previous kernel's tail; A (and the residual) are its outputs
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -604,11 +606,21 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     if (CL == 1) {
         int grid = tiles < num_sms() ? tiles : num_sms();
         if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-        kernel<<<grid, 384, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+        cudaLaunchAttribute attr1[1];
+        unsigned n1 = 0;
+        add_pdl_attr(attr1, &n1);
+        cudaLaunchConfig_t cfg1 = {};
+        cfg1.gridDim = dim3(grid, 1, 1);
+        cfg1.blockDim = dim3(384, 1, 1);
+        cfg1.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg1.stream = stream;
+        cfg1.attrs = attr1;
+        cfg1.numAttrs = n1;
+        UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg1, kernel, tmA, tmB, M, N, K, ep));
         UNIMM_LAUNCH_CHECK(1);
         return 0;
     }
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
@@ -629,6 +641,7 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     int clusters = tiles < max_clusters ? tiles : max_clusters;
     if (max_ctas > 0 && clusters > max_ctas / CS) clusters = max_ctas / CS > 0 ? max_ctas / CS : 1;
     cfg.gridDim = dim3(clusters * CS, 1, 1);
+    add_pdl_attr(attr, &cfg.numAttrs);
     UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, M, N, K, ep));
     UNIMM_LAUNCH_CHECK(1);
     return 0;

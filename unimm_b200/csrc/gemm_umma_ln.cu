@@ -143,6 +143,8 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::cluster_sync_all();    // every peer's barriers are initialised before anyone arrives on them remotely
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_dep_launch_dependents();
+    ptx::grid_dep_wait();                  // everything above (weights-only reads included) overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -519,7 +521,7 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     }
     static int max_clusters = 0;
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
@@ -541,6 +543,7 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     const int num_m = PAIR ? ((M + BM - 1) / BM + 1) / 2 : (M + BM - 1) / BM;
     const int clusters = num_m < max_clusters ? num_m : max_clusters;
     cfg.gridDim = dim3(clusters * CL, 1, 1);
+    add_pdl_attr(attr, &cfg.numAttrs);
     UNIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_gemm_ln_kernel<CS, RES16, BN, RLP, PAIR>, tmA, tmB, tmR, tmI, M, K, ep));
     UNIMM_LAUNCH_CHECK(1);
     return 0;

@@ -61,6 +61,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel in the stream (if launched with programmaticStreamSerializationAllowed) may start placing
+// its CTAs once EVERY CTA of this grid has executed this (or exited); wait: blocks until all prerequisite grids have completed and
+// their memory is visible (a no-op for a normal launch).  Order inside our kernels: barrier init + TMEM allocation -> launch_dependents
+// -> wait -> first global access, so a dependent CTA can never hold TMEM / barriers a predecessor CTA still needs to acquire.
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
