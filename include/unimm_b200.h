@@ -110,7 +110,10 @@ int unimm_forward(unimm_engine_t* e, const unimm_batch_t* batch, const unimm_out
  * Text rows are packed: all units' context rows, then all candidates' rows.  Attention is described by job
  * lists over packed rows (8 int32 per job: q_start, q_len, kv_start, kv_len, win, mask_row, 0, 0) and, for
  * candidate rows, by row_iv[r] = (lo, hi, self, 0): the packed rows of its own candidate it may attend
- * besides the whole context.  unimm_b200/packing.py builds all of this. */
+ * besides the whole context.  unimm_b200/packing.py builds all of this.
+ * Scores-only batches (no_cls_rows = 1) leave out the two candidate rows no labelled position attends ([CLS] and
+ * A_{last-1}); the engine then also skips what only the pooled NSP logit reads (the image stream after the last
+ * connection) and runs the row-wise half of the last text layer on the labelled rows alone. */
 typedef struct {
     int32_t n_units, n_cands, n_text_rows;       /* U, C, M                                                   */
     const int32_t* d_input_ids;                  /* [M]                                                        */
