@@ -91,7 +91,9 @@ def gemm_traffic(launches_per_step, packed):
     (profiles/*_gemm_traffic.json, written by scripts/gemm_traffic.py): per-shape dram__bytes_read.sum + dram__bytes_write.sum,
     averaged over this bench's launch mix.  None when no capture of this layout is committed."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")),
+                   key=lambda f: [int(x) for x in re.findall(r"\d+", os.path.basename(f))])      # r01_v10 after r01_v9
     if not files or not packed:
         return None, None
     t = json.load(open(files[-1]))
