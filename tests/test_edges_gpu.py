@@ -63,6 +63,36 @@ def test_ragged_and_extreme_units(tiny, precision):
     print(f"[{precision}] extreme units: seq_score diff {d1:.3e}  nsp diff {d2:.3e}")
     tol = 5e-5 if precision == "fp32" else 2e-2
     assert torch.isfinite(packed["seq_score"]).all() and d1 < tol and d2 < tol
+    # the same units packed for the scores only (no [CLS] / A_last rows; tail pruning inside the engine)
+    lean = pack_units(units_from_rounds(rounds, slots), feat, loc, mask, scores_only=True)
+    assert lean.n_text_rows == pb.n_text_rows - 2 * pb.n_cands
+    d3 = (eng.forward_packed(lean.to(eng.device), want=("seq_score",))["seq_score"] - dense["seq_score"]).abs().max().item()
+    print(f"[{precision}] extreme units, scores-only packing: seq_score diff {d3:.3e}")
+    assert d3 < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_empty_answers_pack_to_a_single_row(tiny, precision):
+    """Candidates whose answer is empty (last_len = 1: only the closing [SEP] is predicted) keep ONE row each in the scores-only
+    layout (cand_halo = 0, no own-candidate keys besides the row itself); mixed with ordinary candidates in a second unit."""
+    _, _, engines = tiny
+    eng = engines[precision]
+    rng = np.random.RandomState(33)
+    feat, loc, mask = (a[None] for a in syn.synth_image(rng))
+    empty = syn.encode_round_gen(syn.synth_context(rng, 2), [[] for _ in range(5)])
+    mixed = syn.encode_round_gen(syn.synth_context(rng, 4), [[], [2000], [], [3000, 3001, 3002]])
+    tol = 5e-5 if precision == "fp32" else 2e-2
+    for rounds in ([empty], [empty, mixed]):
+        slots = [0] * len(rounds)
+        dense = _dense(eng, rounds, slots, feat, loc, mask, want=("seq_score",))["seq_score"]
+        for scores_only in (False, True):
+            pb = pack_units(units_from_rounds(rounds, slots), feat, loc, mask, scores_only=scores_only)
+            if scores_only and len(rounds) == 1:
+                assert pb.cand_halo == 0 and pb.n_text_rows == pb.n_shared_rows + 5
+            got = eng.forward_packed(pb.to(eng.device), want=("seq_score",))["seq_score"]
+            d = (got - dense).abs().max().item()
+            print(f"[{precision}] empty answers, {len(rounds)} unit(s), scores_only={scores_only}: seq_score diff {d:.3e}")
+            assert torch.isfinite(got).all() and d < tol
 
 
 def test_capacity_limits_fail_loudly(tiny):
