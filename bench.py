@@ -189,9 +189,59 @@ def cpu_reference_rate(n_candidates, steps=1, warmup=0):
     return n_candidates * len(times) / total, total / len(times), torch.get_num_threads()
 
 
+def eager_gpu_rate(mode, steps, warmup, chunk=250):
+    """SURVEY.md §8(d) / BASELINE.md §4 "second on-box bar": the reference's forward as eager PyTorch on ONE B200 (the oracle's
+    functional restatement on cuda tensors: cuBLAS / ATen kernels, dense masks, full-vocabulary logits as val_lm.py:121-137),
+    fp32 with TF32 matmuls or bf16 autocast, chunks of 250.  One step = one image = 10 rounds x 100 candidates."""
+    from oracle import vilbert_oracle as vo
+    from unimm_b200 import synthetic as syn
+    from unimm_b200.config import DEFAULT_CONFIG_PATH, ViLBertConfig
+    from unimm_b200.descriptors import dense_co_mask, dense_text_mask
+    from unimm_b200.weights import random_state_dict
+    dev = torch.device("cuda", 0)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
+    sd = {k: v.to(dev) for k, v in random_state_dict(cfg, 0).items()}
+    batches = []
+    for i in range(2):
+        (feat, loc, mask), rounds = syn.synth_dialog_rounds(i)
+        tokens, segments, positions, labels, desc, _ = syn.stack_rounds(rounds)
+        n = tokens.shape[0]
+        f, l, m = (torch.from_numpy(a).to(dev) for a in (feat, loc, mask))
+        batches.append({k: v.to(dev) for k, v in {
+            "tokens": tokens, "segments": segments, "positions": positions, "mask": labels,
+            "txt_attention_mask": dense_text_mask(desc, 256), "co_attention_mask": dense_co_mask(desc, 256)}.items()})
+        batches[-1]["co_attention_mask"] = batches[-1]["co_attention_mask"].unsqueeze(1).repeat(1, 37, 1)
+        batches[-1].update(image_feat=f.expand(n, -1, -1), image_loc=l.expand(n, -1, -1), image_mask=m.expand(n, -1))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = None
+    for it in range(warmup + steps):
+        if it == warmup:
+            torch.cuda.synchronize(dev)
+            ev0.record()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            out = vo.score_candidates(sd, cfg, batches[it % 2], chunk=chunk, full_logits=True)[0]
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    assert torch.isfinite(out).all()
+    sec = ev0.elapsed_time(ev1) * 1e-3 / steps
+    return SEQ_PER_IMAGE / sec, sec
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.ref_device == "cuda":
+        rate, sec = eager_gpu_rate(args.ref_mode, args.steps, args.warmup)
+        print(json.dumps({"impl": "reference", "metric": "candidates_scored_per_sec", "value": rate, "unit": "candidates/s", "n_gpus": 1,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                          "dtype": "fp32 (TF32 matmuls)" if args.ref_mode == "tf32" else "bf16 autocast", "data": "synthetic",
+                          "config": {"workload": "configs[1]: 1 step = 1 synthetic image = 10 rounds x 100 candidates, dense 256-row sequences, "
+                                                 "chunks of 250, full-vocabulary logits", "device": torch.cuda.get_device_name(0)},
+                          "gpu_eager": {"what": "the oracle's restatement of the reference forward as eager PyTorch on cuda:0 (vendor-library "
+                                                "kernels; not the product path, not the driver's reference arm)", "mode": args.ref_mode}}), flush=True)
         return
     per_step = 10
     rate, sec, cores = cpu_reference_rate(per_step, steps=args.steps, warmup=args.warmup)
@@ -368,7 +418,8 @@ def main_ours(args):
             "roofline": {"kernel": "umma_gemm_kernel (tcgen05 QKV / FFN-1 / co-attention projections, cta_group::2 pairs)" if args.precision != "fp32" else "sgemm_nt_kernel (fp32 CUDA cores)",
                          "bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["sustained"], "frac_of_burst_peak": achieved / pk["burst"], "peak_source": pk["source"],
-                         "traffic": traffic, "traffic_source": traffic_src, "launches": g["launches"],
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": (g["bytes"] / g["launches"]) if g["launches"] else None, "launches": g["launches"],
                          "avg_launch_ms": g["ms"] / max(1, g["launches"]), "share_of_step": share,
                          "other_tensor_kernels_tflops": {"umma_gemm_ln_kernel (LayerNorm-fused cluster GEMM)": tf("gemm_ln"),
                                                          "umma_gemm_kernel<LSE> (LM head)": tf("lm_head")}},
@@ -397,6 +448,8 @@ if __name__ == "__main__":
     ap.add_argument("--images-per-step", type=int, default=8)
     ap.add_argument("--nsp-rows", action="store_true", help="packed mode: keep the [CLS] and A_last rows that only the (unused) NSP logit reads")
     ap.add_argument("--cpu-sample", type=int, default=250)
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: cuda = the eager-PyTorch-on-B200 bar (extra; the driver's arm is cpu)")
+    ap.add_argument("--ref-mode", default="tf32", choices=["tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

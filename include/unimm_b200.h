@@ -183,6 +183,9 @@ int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_s
  * ncat must be >= 5. */
 int unimm_profile_begin(unimm_engine_t* e);
 int unimm_profile_end(unimm_engine_t* e, double* ms, double* work, int64_t* launches, int ncat);
+/* Algorithmic HBM bytes per class of the region the last unimm_profile_end closed (class 0 only: operands and weights once,
+ * every output and residual once; 0 for the classes that do not state them).  bench.py puts them next to the ncu DRAM traffic. */
+int unimm_profile_bytes(unimm_engine_t* e, double* bytes, int ncat);
 
 /* Dense-annotation objective on the NSP probabilities, forward values:
  * unimm_neural_ndcg: utils/rank_loss.py:518-581 (neuralNDCG_transposed: deterministic NeuralSort :79-112 + Sinkhorn scaling :55-78,

@@ -234,7 +234,7 @@ def forward(sd: Dict[str, torch.Tensor], cfg, input_ids, image_feat, image_loc, 
         logp = logp_all.gather(1, labels[:, None])[:, 0]
         p_all = torch.softmax(row_logits, dim=-1)
         ul = torch.log(torch.clamp(1.0 - p_all, min=1e-6)).gather(1, labels[:, None])[:, 0]   # :1587
-        seq = torch.zeros(B, dtype=dtype).index_add_(0, rows[:, 0], logp)      # val_lm.py:131-136
+        seq = torch.zeros(B, dtype=logp.dtype, device=logp.device).index_add_(0, rows[:, 0], logp)      # val_lm.py:131-136
         out.update(token_rows=rows, token_logp=logp, token_ul=ul, seq_score=seq)
 
     if masked_lm_labels is not None and next_sentence_label is not None and image_target is not None:

@@ -89,6 +89,7 @@ SYMBOLS = {
     "unimm_ensemble_normalise": (C.c_int, [_P, _I, _I, _I, _P, _P]),
     "unimm_profile_begin": (C.c_int, [_P]),
     "unimm_profile_end": (C.c_int, [_P, _P, _P, _P, _I]),
+    "unimm_profile_bytes": (C.c_int, [_P, _P, _I]),
     "unimm_launch_count": (C.c_int64, []),
     "unimm_reset_launch_count": (None, []),
     "unimm_k_gemm_lp": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P]),

@@ -126,7 +126,8 @@ struct unimm_engine {
 
     // optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline numbers)
     enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ROWWISE = 2, CAT_LMHEAD = 3, CAT_GEMM_LN = 4, NCAT = 5 };   // GEMM = umma_gemm_kernel, GEMM_LN = umma_gemm_ln_kernel
-    struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+    struct ProfRec { cudaEvent_t a, b; int cat; double work; double bytes; };   // bytes = algorithmic HBM bytes of the launch (0: not stated)
+    double prof_bytes[5] = {0, 0, 0, 0, 0};    // per class, summed by the last unimm_profile_end
     bool profiling = false;
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
@@ -136,8 +137,8 @@ struct unimm_engine {
     }
     struct Prof {   // RAII: event before / after whatever is launched in its scope
         unimm_engine* e; cudaStream_t st; ProfRec r; bool on;
-        Prof(unimm_engine* e_, int cat, double work, cudaStream_t st_) : e(e_), st(st_), on(e_->profiling) {
-            if (on) { r.a = e->prof_event(); r.b = e->prof_event(); r.cat = cat; r.work = work; cudaEventRecord(r.a, st); }
+        Prof(unimm_engine* e_, int cat, double work, cudaStream_t st_, double bytes = 0.0) : e(e_), st(st_), on(e_->profiling) {
+            if (on) { r.a = e->prof_event(); r.b = e->prof_event(); r.cat = cat; r.work = work; r.bytes = bytes; cudaEventRecord(r.a, st); }
         }
         ~Prof() { if (on) { cudaEventRecord(r.b, st); e->prof_recs.push_back(r); } }
     };
@@ -428,7 +429,11 @@ int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const
     ep.ldr = ldr;
     ep.act = act;
     ep.lp_kind = lp_kind();
-    Prof prof(this, CAT_GEMM, 2.0 * M * L.N * L.K, st);
+    // algorithmic bytes: A + W once, every output (and the residual) once
+    const double mn = static_cast<double>(M) * L.N;
+    Prof prof(this, CAT_GEMM, 2.0 * M * L.N * L.K, st,
+              esz() * (static_cast<double>(M) * L.K + static_cast<double>(L.N) * L.K) + (out_lp ? esz() * mn : 0.0) +
+                  (out_f32 ? 4.0 * mn : 0.0) + (residual ? 4.0 * mn : 0.0));
     if (lp()) {
         ep.out_f32 = out_f32; ep.ldo_f32 = ldo_f32;
         ep.out_bf16 = static_cast<bf16*>(out_lp); ep.ldo_bf16 = ldo_lp;
@@ -1152,13 +1157,21 @@ int unimm_profile_end(unimm_engine_t* e, double* ms, double* work, int64_t* laun
     e->profiling = false;
     UNIMM_CUDA_CHECK(cudaDeviceSynchronize());
     for (int i = 0; i < ncat; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+    for (double& b : e->prof_bytes) b = 0;
     for (auto& r : e->prof_recs) {
         float t = 0.f;
         UNIMM_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
         ms[r.cat] += t; work[r.cat] += r.work; launches[r.cat] += 1;
+        e->prof_bytes[r.cat] += r.bytes;
         e->prof_pool.push_back(r.a); e->prof_pool.push_back(r.b);
     }
     e->prof_recs.clear();
+    return 0;
+}
+
+int unimm_profile_bytes(unimm_engine_t* e, double* bytes, int ncat) {
+    UNIMM_CHECK(e && bytes && ncat >= unimm_engine::NCAT, "bad argument");
+    for (int i = 0; i < ncat; ++i) bytes[i] = i < unimm_engine::NCAT ? e->prof_bytes[i] : 0.0;
     return 0;
 }
 

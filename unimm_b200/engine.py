@@ -190,11 +190,13 @@ class Engine:
         check(lib.unimm_profile_begin(self._h))
 
     def profile_end(self) -> Dict[str, Dict[str, float]]:
-        """{class: {ms, work, launches}}; work = FLOPs (bytes for layernorm); synchronises the device."""
+        """{class: {ms, work, launches, bytes}}; work = FLOPs (bytes for layernorm), bytes = algorithmic HBM bytes (gemm class); synchronises."""
         n = len(self.PROFILE_CLASSES)
         ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
         check(lib.unimm_profile_end(self._h, ms, work, cnt, n))
-        return {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
+        nbytes = (C.c_double * n)()
+        check(lib.unimm_profile_bytes(self._h, nbytes, n))
+        return {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i]), "bytes": nbytes[i]} for i, k in enumerate(self.PROFILE_CLASSES)}
 
     # ------------------------------------------------------------------------------------------ host path
     def score_host(self, hb: "HostArrays", seq_score: torch.Tensor, nsp_scores: Optional[torch.Tensor] = None) -> None:
