@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libunimm_b200.so")
+LIB_PATH = os.environ.get("UNIMM_LIB_PATH") or os.path.join(_HERE, "lib", "libunimm_b200.so")   # override: A/B runs of two builds
 
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 LP_BF16, LP_FP16 = 0, 1

@@ -57,10 +57,11 @@ struct LnCfg {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;           // a cta_group::2 pair keeps half of the W box per CTA
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kIdentBytes = (PAIR ? 32 : 64) * BK * 2;           // resident 64 x 64 identity block (a pair keeps half of its rows per CTA)
     static constexpr int kStatsBytes = 2 * 2 * 4 * (CS - 1) * 32 * 8;       // [use parity][group][warp][source][row] float2
     static constexpr int kParamBytes = 3 * BN * 4;                          // bias, gamma, beta of this CTA's 256 columns
     static constexpr int kBarBytes = 512;
-    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStatsBytes + kParamBytes + kBarBytes;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kIdentBytes + kStatsBytes + kParamBytes + kBarBytes;
 };
 
 // RES16 = false: fp32 residual, precharged into the accumulator by the epilogue warps (see above).
@@ -68,7 +69,10 @@ struct LnCfg {
 //                exact tensor-core operand, so it is added by the tensor core: four extra k-blocks per tile multiply
 //                the residual tile R[128 x 256] (TMA box from tmR) by a (row-permuted) 256 x 256 identity (tmI) and
 //                accumulate in fp32 — no register traffic, no latency-exposed loads, the epilogue never touches global
-//                memory except for its stores.  Costs 256 extra K per tile (+33 % MMA work at K = 768, +8 % at 3072).
+//                memory except for its stores.  Only the 64 x 64 diagonal block of each identity k-block is non-zero (the row
+//                permutation is 32-periodic), so residual k-block j is issued as N = 64 MMAs into accumulator columns
+//                [64 j, 64 j + 64) against ONE 64 x 64 identity block that stays resident in shared memory (loaded once per CTA):
+//                +8 % MMA work at K = 768 (+2 % at 3072) instead of +33 % (+8 %), and no identity operand traffic at all.
 // BN = columns per CTA: 256 (N = 768 as 3 CTAs, N = 1024 as 4) or 192 (N = 768 as 4 CTAs: clusters of 4 tile all 148 SMs, clusters
 // of 3 only 135 of them).
 // RLP (with RES16 = false): the precharged residual is the 16-bit activation copy (converted by the epilogue warps) — the
@@ -88,15 +92,17 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
-    float2* stats = reinterpret_cast<float2*>(smem + Cfg::kStages * Cfg::kStageBytes);
-    float* sparam = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStatsBytes);   // [3][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStatsBytes + Cfg::kParamBytes);
+    uint8_t* sI = smem + Cfg::kStages * Cfg::kStageBytes;    // 1024-byte aligned: the stage sizes are multiples of 1024
+    float2* stats = reinterpret_cast<float2*>(sI + Cfg::kIdentBytes);
+    float* sparam = reinterpret_cast<float*>(sI + Cfg::kIdentBytes + Cfg::kStatsBytes);   // [3][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sI + Cfg::kIdentBytes + Cfg::kStatsBytes + Cfg::kParamBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::kStages;
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* stats_bar = tempty_bar + 2;                  // [use parity][group][warp] = 16 barriers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stats_bar + 16);
+    uint64_t* ident_bar = stats_bar + 16;                  // the resident identity block has landed (once per kernel)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -127,6 +133,7 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_init(&tempty_bar[a], PAIR ? 8 : 4);   // one arrival per epilogue warp of the group (of both CTAs of a pair)
         }
         for (int b = 0; b < 16; ++b) ptx::mbar_init(&stats_bar[b], 1);   // the owner's arrive.expect_tx; peers complete bytes
+        ptx::mbar_init(ident_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -151,35 +158,43 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            if (RES16) {      // the 64 x 64 identity block (rows [32 m_r, 32 m_r + 32) of it in a pair): once, stays resident
+                if (PAIR) {
+                    if (m_r == 0) ptx::mbar_arrive_expect_tx(ident_bar, 2 * Cfg::kIdentBytes);
+                    ptx::tma_load_2d_2sm(sI, &tmI, ident_bar, 0, m_r * 32);
+                } else {
+                    ptx::mbar_arrive_expect_tx(ident_bar, Cfg::kIdentBytes);
+                    ptx::tma_load_2d(sI, &tmI, ident_bar, 0, 0);
+                }
+            }
             for (int mb = cluster_id; mb < num_m; mb += num_clusters) {
                 const int m0 = row_of(mb);
                 for (int kb = 0; kb < num_kr; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const bool resid = RES16 && kb >= num_k;      // residual k-block: only the A box (the residual tile) is loaded
                     if (PAIR) {
-                        if (m_r == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);     // both CTAs' boxes
-                        if (!RES16 || kb < num_k) {
+                        if (m_r == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], resid ? 2 * Cfg::kABytes : 2 * Cfg::kStageBytes);     // both CTAs' boxes
+                        if (!resid) {
                             ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
                             ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0 + m_r * (BN / 2));
                         } else {
                             const int j = kb - num_k;
                             ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmR, &full_bar[stage], n0 + j * BK, m0);
-                            ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmI, &full_bar[stage], j * BK, m_r * (BN / 2));
                         }
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    if (!RES16 || kb < num_k) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], resid ? Cfg::kABytes : Cfg::kStageBytes);
+                    if (!resid) {
                         // the CS CTAs of the cluster multiply the SAME 128 x 64 activation box: CTA kb % CS fetches it once and
                         // multicasts it into every CTA's slot (data and mbarrier bytes land at the same CTA-relative offsets)
                         if (!ep.a_multicast) ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
                         else if (kb % CS == static_cast<int>(rank))   /* (a_multicast is never set with PAIR) */
                             ptx::tma_load_2d_mc(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0, static_cast<uint16_t>((1u << CS) - 1u));
                         ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
-                    } else {      // residual columns n0 + 64 j .. against identity columns 64 j ..
+                    } else {      // residual columns n0 + 64 j .. (against the resident identity block)
                         const int j = kb - num_k;
                         ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmR, &full_bar[stage], n0 + j * BK, m0);
-                        ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmI, &full_bar[stage], j * BK, 0);
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -189,6 +204,12 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one() && m_r == 0) {
             const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u);
+            const uint32_t idesc_r = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BK, ep.lp_kind == LP_FP16 ? 0u : 1u);   // N = 64: one diagonal block
+            const uint64_t di = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sI));
+            if (RES16) {
+                ptx::mbar_wait(ident_bar, 0);
+                ptx::tc_fence_after();
+            }
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -203,11 +224,21 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * Cfg::kABytes));
-                    const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * Cfg::kBBytes));
+                    if (RES16 && kb >= num_k) {
+                        // accumulator columns [64 j, 64 j + 64) += residual columns [64 j, 64 j + 64) x the (row-permuted) identity block
+                        const uint32_t tmem_r = tmem_d + static_cast<uint32_t>(kb - num_k) * BK;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        if (PAIR) ptx::umma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
-                        else ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            if (PAIR) ptx::umma_f16_ss_2sm(tmem_r, da + 2 * k, di + 2 * k, idesc_r, 1u);
+                            else ptx::umma_f16_ss(tmem_r, da + 2 * k, di + 2 * k, idesc_r, 1u);
+                        }
+                    } else {
+                        const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            if (PAIR) ptx::umma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
+                            else ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (RES16 && (kb | k) == 0) ? 0u : 1u);
+                        }
                     }
                     if (PAIR) ptx::umma_commit_2sm_mc(&empty_bar[stage], pair_mask);
                     else if (ep.a_multicast) ptx::umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>((1u << CS) - 1u));
@@ -514,7 +545,7 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
         const bf16* ident = nullptr;
         UNIMM_TRY(identity_for(ep.lp_kind, &ident));
         UNIMM_TRY(gemm_make_map(ep.residual_lp, M, CS * BN, ep.ldr_lp, BM, &tmR));
-        UNIMM_TRY(gemm_make_map(ident, IDN, IDN, IDN, PAIR ? BN / 2 : BN, &tmI));      // top-left BN x BN block: the row order is 32-periodic
+        UNIMM_TRY(gemm_make_map(ident, IDN, IDN, IDN, PAIR ? 32 : 64, &tmI));          // top-left 64 x 64 block: the row order is 32-periodic
     } else {
         tmR = tmA;
         tmI = tmB;
