@@ -145,7 +145,7 @@ def run_step_host(eng, b, chunk, score_host, HostArrays):
     return h2d, d2h
 
 
-def packed_step_batch(first_image, n_images, stride, scores_only=True):
+def packed_step_batch(first_image, n_images, stride, scores_only=True, share_first_mask=True):
     """One prefix-shared step: n_images synthetic images x 10 rounds x 100 candidates, packed (pinned host tensors)."""
     from unimm_b200 import synthetic as syn
     from unimm_b200.packing import pack_units, units_from_rounds
@@ -155,7 +155,8 @@ def packed_step_batch(first_image, n_images, stride, scores_only=True):
         rounds += rs
         slots += [i] * len(rs)
         feats.append(feat), locs.append(loc), masks.append(mask)
-    pb = pack_units(units_from_rounds(rounds, slots), np.stack(feats), np.stack(locs), np.stack(masks), scores_only=scores_only)
+    pb = pack_units(units_from_rounds(rounds, slots), np.stack(feats), np.stack(locs), np.stack(masks), scores_only=scores_only,
+                    share_first_mask=share_first_mask)
     return pb.pin()
 
 
@@ -280,7 +281,7 @@ def main_ours(args):
     stream = torch.cuda.current_stream(dev)
     if packed:
         cands_per_step = args.images_per_step * SEQ_PER_IMAGE
-        host = [packed_step_batch((rank + world * i) * args.images_per_step, args.images_per_step, 1, not args.nsp_rows) for i in range(n_batches)]
+        host = [packed_step_batch((rank + world * i) * args.images_per_step, args.images_per_step, 1, not args.nsp_rows, not args.own_b0) for i in range(n_batches)]
         cap = max(max(-(-pb.n_text_rows // 256) for pb in host), max(pb.n_units for pb in host)) + 1    # workspace in 256-row units
     else:
         cap = chunk
@@ -402,7 +403,8 @@ def main_ours(args):
             cfg_d["dense_text_rows_per_step"] = cands_per_step * 256
             cfg_d["candidate_rows"] = ("CLS + A + B (NSP logits available)" if args.nsp_rows else
                                        "scores only: the [CLS] and A_last rows, which no labelled position attends and only the NSP logit "
-                                       "(fetched but unused by val_lm.py:124-139) reads, are not packed")
+                                       "(fetched but unused by val_lm.py:124-139) reads, are not packed" +
+                                       ("" if args.own_b0 else "; the first masked position B_0 (identical for the candidates of a round) once per round"))
             cfg_d["note"] = ("prefix-shared layout: context + image rows once per round (SURVEY.md F5); roofline and % of peak count "
                              "EXECUTED FLOPs only; dense_equivalent_speedup = dense FLOPs / executed FLOPs")
         else:
@@ -446,6 +448,7 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", type=int, default=250)
     ap.add_argument("--mode", default="packed", choices=["packed", "dense"], help="packed = prefix-shared rows (default); dense = one 256-row sequence per candidate, as the reference computes it")
     ap.add_argument("--images-per-step", type=int, default=8)
+    ap.add_argument("--own-b0", action="store_true", help="packed mode: one B_0 row per candidate instead of one per unit")
     ap.add_argument("--nsp-rows", action="store_true", help="packed mode: keep the [CLS] and A_last rows that only the (unused) NSP logit reads")
     ap.add_argument("--cpu-sample", type=int, default=250)
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: cuda = the eager-PyTorch-on-B200 bar (extra; the driver's arm is cpu)")

@@ -65,7 +65,7 @@ def test_ragged_and_extreme_units(tiny, precision):
     assert torch.isfinite(packed["seq_score"]).all() and d1 < tol and d2 < tol
     # the same units packed for the scores only (no [CLS] / A_last rows; tail pruning inside the engine)
     lean = pack_units(units_from_rounds(rounds, slots), feat, loc, mask, scores_only=True)
-    assert lean.n_text_rows == pb.n_text_rows - 2 * pb.n_cands
+    assert lean.n_text_rows == pb.n_text_rows - 3 * pb.n_cands + pb.n_units         # no [CLS] / A_last rows, one B_0 row per unit
     d3 = (eng.forward_packed(lean.to(eng.device), want=("seq_score",))["seq_score"] - dense["seq_score"]).abs().max().item()
     print(f"[{precision}] extreme units, scores-only packing: seq_score diff {d3:.3e}")
     assert d3 < tol
@@ -88,7 +88,7 @@ def test_empty_answers_pack_to_a_single_row(tiny, precision):
         for scores_only in (False, True):
             pb = pack_units(units_from_rounds(rounds, slots), feat, loc, mask, scores_only=scores_only)
             if scores_only and len(rounds) == 1:
-                assert pb.cand_halo == 0 and pb.n_text_rows == pb.n_shared_rows + 5
+                assert pb.cand_halo == 0 and pb.n_text_rows == pb.n_shared_rows + 1      # five empty answers: the unit's B_0 row is all there is
             got = eng.forward_packed(pb.to(eng.device), want=("seq_score",))["seq_score"]
             d = (got - dense).abs().max().item()
             print(f"[{precision}] empty answers, {len(rounds)} unit(s), scores_only={scores_only}: seq_score diff {d:.3e}")

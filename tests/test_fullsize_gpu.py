@@ -79,7 +79,7 @@ def test_packed_equals_dense_at_bench_size(engine, step):
     assert (top_gap < TOL).all()
     # scores-only packing (what bench.py and the sweep driver run): 2 rows fewer per candidate, same scores
     lean, pl = packed_scores(engine, rounds, slots, feat, loc, mask, scores_only=True)
-    assert pl.n_text_rows == pb.n_text_rows - 2 * pb.n_cands
+    assert pl.n_text_rows == pb.n_text_rows - 3 * pb.n_cands + pb.n_units      # no [CLS] / A_last rows, one B_0 row per unit
     d_lean = np.abs(lean - dense)
     print(f"scores-only packing ({pl.n_text_rows} rows) vs dense: max |diff| {d_lean.max():.3e}; vs full packing {np.abs(lean - packed).max():.3e}")
     assert d_lean.max() < TOL and np.abs(lean - packed).max() < 5e-3

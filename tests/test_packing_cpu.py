@@ -8,9 +8,12 @@ from unimm_b200.descriptors import dense_text_mask, descriptors_from_masks
 from unimm_b200.packing import pack_units, units_from_flat, units_from_rounds
 
 
-def _check(pb, rounds, scores_only=False):
+def _check(pb, rounds, scores_only=False, shared_b0=False):
+    """Every packed row carries the token / segment / position of the dense position it stands for and sees exactly the keys the
+    dense mask gives that position (so every key a kept row needs is itself a kept row)."""
     iv, jobs = pb.row_iv.numpy(), pb.jobs_text_self.numpy()
     lab, off = pb.lm_labels.numpy(), pb.cand_lm_off.numpy()
+    lm_rows = pb.lm_rows.numpy()
     c = 0
     for ui, r in enumerate(rounds):
         ctx = int(r.desc[0, 1])
@@ -20,10 +23,15 @@ def _check(pb, rounds, scores_only=False):
         assert (pb.input_ids[sh[0]:sh[0] + ctx - 1].numpy() == r.tokens[0, 1:ctx]).all()
         dm = dense_text_mask(torch.from_numpy(r.desc), 256).numpy()
         row = int(cj[0])
+        b0_row = -1
+        if shared_b0:                                        # one B_0 row at the head of the unit's candidate block
+            b0_row, row = row, row + 1
+            assert tuple(iv[b0_row, :3]) == (b0_row, b0_row, b0_row)
         for j in range(len(r.desc)):
             L, last = int(r.desc[j, 2]), int(r.desc[j, 3])
-            # dense columns of the candidate's packed rows, in packed order
-            cols = ([] if scores_only else [0]) + [ctx + k for k in range(last - (1 if scores_only else 0))] + [L + k for k in range(last)]
+            # dense columns of the candidate's own packed rows, in packed order
+            cols = ([] if scores_only else [0]) + [ctx + k for k in range(last - (1 if scores_only else 0))] + \
+                [L + k for k in range(1 if shared_b0 else 0, last)]
             assert pb.cand_cls_row[c] == (-1 if scores_only else row)
             first = row
             for idx, col in enumerate(cols):
@@ -32,14 +40,21 @@ def _check(pb, rounds, scores_only=False):
                 for a in list(range(lo, hi)) + ([sf] if sf >= 0 else []):
                     assert 0 <= a - first < len(cols), "a row may only see rows of its own candidate"
                     allowed.add(cols[a - first])
-                # the packed row sees exactly what the dense mask lets this position see (so every key it needs is a kept row)
                 assert allowed == set(np.nonzero(dm[j, col])[0].tolist()), (ui, j, idx)
                 assert pb.input_ids[row] == r.tokens[j, col] and pb.position_ids[row] == r.positions[j, col]
                 assert pb.token_type_ids[row] == r.segments[j, col]
                 row += 1
+            if shared_b0:
+                # the unit's B_0 row stands for dense position L of THIS candidate too: same inputs, keys = context + itself
+                assert set(np.nonzero(dm[j, L])[0].tolist()) == set(range(1, ctx)) | {L}
+                assert pb.input_ids[b0_row] == r.tokens[j, L] and pb.position_ids[b0_row] == r.positions[j, L]
+                assert pb.token_type_ids[b0_row] == r.segments[j, L]
+                assert lm_rows[off[c]] == b0_row and (lm_rows[off[c] + 1:off[c + 1]] == np.arange(row - (last - 1), row)).all()
+            else:
+                assert (lm_rows[off[c]:off[c + 1]] == np.arange(row - last, row)).all()     # the labelled rows are the B rows
             assert (lab[off[c]:off[c + 1]] == r.labels[j, L:L + last]).all()
-            assert (pb.lm_rows[off[c]:off[c + 1]].numpy() == np.arange(row - last, row)).all()       # the labelled rows are the B rows
             c += 1
+        assert row == cj[0] + cj[1]
     assert c == pb.n_cands and pb.win_cap % 64 == 0 and pb.kv_cap_text % 64 == 0 and pb.kv_cap_text <= 256
 
 
@@ -53,19 +68,32 @@ def test_packed_rows_reproduce_dense_masks_and_tokens():
 
 
 def test_scores_only_packing_drops_only_rows_nothing_labelled_can_see():
-    """scores_only: no [CLS], no A_{last-1}.  _check proves that every kept row's packed key set equals its dense-mask key set,
-    i.e. the kept rows are closed under "is attended by" — the dropped rows can only change the pooled NSP logit."""
+    """scores_only: no [CLS], no A_{last-1}; B_0 once per unit.  _check proves that every kept row's packed key set equals its
+    dense-mask key set, i.e. the kept rows are closed under "is attended by" — the dropped rows can only change the pooled NSP
+    logit — and that the shared B_0 row is, for every candidate, the row the dense layout has at its position L."""
     rng = np.random.RandomState(5)
     img = syn.synth_image(rng)
     rounds = [syn.encode_round_gen(syn.synth_context(rng, r), syn.synth_answers(rng, n)) for r, n in ((1, 7), (3, 12), (10, 9))]
-    pb = pack_units(units_from_rounds(rounds, [0, 0, 0]), img[0][None], img[1][None], img[2][None], scores_only=True)
-    _check(pb, rounds, scores_only=True)
-    full = pack_units(units_from_rounds(rounds, [0, 0, 0]), img[0][None], img[1][None], img[2][None])
-    assert pb.n_text_rows == full.n_text_rows - 2 * pb.n_cands and pb.c_struct().no_cls_rows == 1 and full.c_struct().no_cls_rows == 0
-    assert (pb.lm_labels == full.lm_labels).all() and (pb.cand_lm_off == full.cand_lm_off).all()
+    rounds.append(syn.encode_round_gen(syn.synth_context(rng, 2), [[], [5000], []]))             # empty answers: no own rows at all
+    slots = [0] * len(rounds)
+    full = pack_units(units_from_rounds(rounds, slots), img[0][None], img[1][None], img[2][None])
+    lean = pack_units(units_from_rounds(rounds, slots), img[0][None], img[1][None], img[2][None], scores_only=True, share_first_mask=False)
+    pb = pack_units(units_from_rounds(rounds, slots), img[0][None], img[1][None], img[2][None], scores_only=True)
+    _check(lean, rounds, scores_only=True)
+    _check(pb, rounds, scores_only=True, shared_b0=True)
+    assert lean.n_text_rows == full.n_text_rows - 2 * pb.n_cands and lean.c_struct().no_cls_rows == 1 and full.c_struct().no_cls_rows == 0
+    assert pb.n_text_rows == lean.n_text_rows - pb.n_cands + len(rounds) and pb.n_b0_shared == len(rounds)
+    for other in (lean, pb):
+        assert (other.lm_labels == full.lm_labels).all() and (other.cand_lm_off == full.cand_lm_off).all()
     # the image rows never look at candidate rows at all (co-attention interval = the context rows)
     for j in pb.jobs_i2t.numpy():
         assert j[2] + j[3] <= pb.n_shared_rows
+    # a unit whose masked copies differ in their first position keeps one B_0 per candidate
+    odd = syn.encode_round_gen(syn.synth_context(rng, 2), syn.synth_answers(rng, 4))
+    odd.positions[1, int(odd.desc[1, 2])] += 1
+    pb2 = pack_units(units_from_rounds([odd], [0]), img[0][None], img[1][None], img[2][None], scores_only=True)
+    assert pb2.n_b0_shared == 0
+    _check(pb2, [odd], scores_only=True)
 
 
 def test_packing_the_reference_made_inputs():

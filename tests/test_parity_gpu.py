@@ -235,7 +235,11 @@ def test_scores_only_packing_matches_reference(full_cfg, precision):
     units = units_from_flat(batch["tokens"], batch["segments"], batch["positions"], batch["mask"], desc, np.zeros(100, np.int64))
     full = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None])
     pb = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None], scores_only=True)
-    assert pb.n_text_rows == full.n_text_rows - 200
+    assert pb.n_text_rows == full.n_text_rows - 200 - 99      # no [CLS] / A_last rows, one B_0 row for the 100 candidates
+    mid = pack_units(units, g["image_feat"][None], g["image_loc"][None], g["image_mask"][None], scores_only=True, share_first_mask=False)
+    assert mid.n_text_rows == full.n_text_rows - 200
+    d_mid = (eng.forward_packed(mid.to(eng.device), want=("seq_score",))["seq_score"].cpu().numpy() - g["seq_score"])
+    assert np.abs(d_mid).max() < TIGHT[precision]
     out = eng.forward_packed(pb.to(eng.device), want=("seq_score", "token_logp"))
     ref = eng.forward_packed(full.to(eng.device), want=("seq_score", "token_logp"))
     score = out["seq_score"].cpu()
