@@ -146,6 +146,12 @@ typedef struct {
                                                   * co-attention keys / values anything reads (0 = unknown: project all rows) */
     int32_t no_cls_rows;                         /* 1: packed for the sequence scores only — the candidates carry no [CLS] row (and no
                                                   * A_{last-1} row), d_cand_cls_row is unused and NSP scores cannot be requested   */
+    /* optional: d_lm_rows lists some row more than once (the unit-wide B_0 row of a scores-only batch, once per candidate with that
+     * candidate's label).  d_lm_urows [n_lm_unique] = the distinct labelled rows, d_lm_uidx [n_lm] = index of entry i's row in it;
+     * the 16-bit modes then run the LM head once per distinct row.  n_lm_unique = 0: not given. */
+    const int32_t* d_lm_urows;
+    const int32_t* d_lm_uidx;
+    int32_t n_lm_unique;
 } unimm_packed_batch_t;
 /* outputs (each optional): seq_score [C], nsp_scores [C,2], token_logp [n_lm] */
 int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, float* d_seq_score, float* d_nsp_scores,

@@ -254,9 +254,11 @@ def test_scores_only_packing_matches_reference(full_cfg, precision):
         assert flips == 0
         with pytest.raises(RuntimeError, match="CLS"):
             eng.forward_packed(pb.to(eng.device), want=("seq_score", "nsp_scores"))
-        score_h = torch.zeros(100).pin_memory()
-        eng.score_packed_host(pb.pin(), score_h)
-        np.testing.assert_allclose(score_h.numpy(), score.numpy(), atol=1e-6, rtol=0)
+    # the host-buffer entry point stages the same arrays (incl. the distinct-row lists of the shared B_0 rows)
+    assert pb.lm_urows.shape[0] == pb.lm_rows.shape[0] - 99
+    score_h = torch.zeros(100).pin_memory()
+    eng.score_packed_host(pb.pin(), score_h)
+    np.testing.assert_allclose(score_h.numpy(), score.numpy(), atol=1e-6, rtol=0)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])

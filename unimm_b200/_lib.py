@@ -67,7 +67,8 @@ class PackedBatchStruct(C.Structure):
         ("kv_cap_text", C.c_int32), ("win_cap", C.c_int32),
         ("d_lm_rows", C.c_void_p), ("d_lm_labels", C.c_void_p), ("n_lm_rows", C.c_int32),
         ("d_cand_lm_off", C.c_void_p), ("d_cand_cls_row", C.c_void_p), ("d_cand_img_row", C.c_void_p),
-        ("pairs_text_self", C.c_double), ("pairs_i2t", C.c_double), ("n_shared_rows", C.c_int32), ("no_cls_rows", C.c_int32)]
+        ("pairs_text_self", C.c_double), ("pairs_i2t", C.c_double), ("n_shared_rows", C.c_int32), ("no_cls_rows", C.c_int32),
+        ("d_lm_urows", C.c_void_p), ("d_lm_uidx", C.c_void_p), ("n_lm_unique", C.c_int32)]
 
 
 # every symbol include/unimm_b200.h declares: name -> (restype, argtypes)

@@ -110,6 +110,10 @@ struct unimm_engine {
     int* g_labels = nullptr;
     float2* partials = nullptr;
     float *label_logit = nullptr, *row_logp = nullptr, *row_ul = nullptr;
+    float* lse_u = nullptr;         // log-sum-exp per UNIQUE labelled row (packed batches that share labelled rows)
+    bool lm_dedup = true;           // run the LM head once per unique labelled row (UNIMM_LM_DEDUP=0: once per (row, label) entry)
+    const int* keep_rows_ = nullptr;   // rows the lean tail of run_encoder keeps (set by forward_packed)
+    int n_keep_ = 0;
     float* logits_chunk = nullptr;  // fp32 mode: [kLogitRows, V]
     float* vhead = nullptr;         // image head scratch [Mv, Hv]
     ActBuf vhead_h;
@@ -207,6 +211,8 @@ struct unimm_engine {
     int run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st);
     // d_rows == nullptr: src's rows [0, n) are the labelled rows already
     int lm_head_rows(const ActBuf& src, const int* d_rows, const int* d_labels, int n, cudaStream_t st);
+    // n_u unique rows (of src, or src[d_urows]) serve n (row, label) entries: entry i reads unique row d_uidx[i]
+    int lm_head_shared(const ActBuf& src, const int* d_urows, int n_u, const int* d_uidx, const int* d_labels, int n, cudaStream_t st);
     int forward(const unimm_batch_t& in, const unimm_outputs_t& out, cudaStream_t st);
     int forward_packed(const unimm_packed_batch_t& in, float* d_seq_score, float* d_nsp_scores, float* d_token_logp, cudaStream_t st);
 };
@@ -401,6 +407,7 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&label_logit, Mt));
     UNIMM_TRY(dalloc(&row_logp, Mt));
     UNIMM_TRY(dalloc(&row_ul, Mt));
+    UNIMM_TRY(dalloc(&lse_u, Mt));
     if (lp()) UNIMM_TRY(dalloc(&partials, Mt * gemm_umma_lse_tiles(c.vocab_size)));
     else UNIMM_TRY(dalloc(&logits_chunk, static_cast<size_t>(kLogitRows) * c.vocab_size));
     UNIMM_TRY(dalloc(&vhead, Mv * Hv));
@@ -776,7 +783,7 @@ int unimm_engine::run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st
         for (int i = t_start; i < c.num_hidden_layers - 1; ++i) UNIMM_TRY(run_t(i));
         if (t_start < c.num_hidden_layers) {
             UNIMM_TRY(self_layer(t_layers[c.num_hidden_layers - 1], xt, pre_t, qkv_t, ctx_t, ffn_t, Mt, c.num_attention_heads, true, ac, st,
-                                 ac.pk->d_lm_rows, ac.pk->n_lm_rows, &xk));
+                                 keep_rows_, n_keep_, &xk));
             xk_live = true;
         }
         return 0;     // nobody reads the fp32 views of a scores-only batch
@@ -821,6 +828,32 @@ int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* 
     return 0;
 }
 
+// LM head with shared labelled rows (16-bit modes): transform + LayerNorm + vocabulary log-sum-exp once per unique row, then the
+// label logits of the n entries as gathered dot products
+int unimm_engine::lm_head_shared(const ActBuf& src, const int* d_urows, int n_u, const int* d_uidx, const int* d_labels, int n,
+                                 cudaStream_t st) {
+    const unimm_config_t& c = cfg;
+    const int H = c.hidden_size;
+    UNIMM_CHECK(lp(), "shared labelled rows need a 16-bit mode");
+    if (d_urows != nullptr) UNIMM_TRY(gather_rows(nullptr, src.h, d_urows, n_u, H, nullptr, g_in.h, st));
+    UNIMM_TRY(linear(d_urows != nullptr ? g_in : src, n_u, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n_u) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n_u, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, lp_kind(), st)); }
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(g_labels, 0, sizeof(int) * n_u, st));      // the fused epilogue's label pick is unused here
+    {
+        GemmEpilogue ep;
+        ep.bias = lm_decoder.b;
+        ep.labels = g_labels;
+        ep.partials = partials;
+        ep.label_logit = label_logit;
+        ep.lp_kind = lp_kind();
+        Prof prof(this, CAT_LMHEAD, 2.0 * n_u * c.vocab_size * H, st);
+        UNIMM_TRY(gemm_umma_bf16(g_h.h, H, lm_decoder.wlp, H, n_u, c.vocab_size, H, ep, 256, 0, st));
+    }
+    UNIMM_TRY(lse_merge(partials, gemm_umma_lse_tiles(c.vocab_size), n_u, lse_u, st));
+    UNIMM_TRY(label_scores(g_h.h, H, lm_decoder.wlp, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, lp_kind(), row_logp, row_ul, st));
+    return 0;
+}
+
 // Prefix-shared generative scoring over packed rows (see attention_jobs.cu and unimm_b200/packing.py)
 int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_score, float* d_nsp_scores, float* d_token_logp,
                                  cudaStream_t st) {
@@ -846,13 +879,18 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
     }
     AttnCtx ac;
     ac.pk = &in;
+    const int n = in.n_lm_rows;
+    // labelled rows shared by several candidates (the unit-wide B_0 row of a scores-only batch): LM head once per unique row
+    const bool dedup = lp() && lm_dedup && n > 0 && in.n_lm_unique > 0 && in.n_lm_unique < n && in.d_lm_urows && in.d_lm_uidx;
+    keep_rows_ = dedup ? in.d_lm_urows : in.d_lm_rows;
+    n_keep_ = dedup ? in.n_lm_unique : n;
     UNIMM_TRY(run_encoder(M, Mv, ac, st));
     if (d_nsp_scores)
         UNIMM_TRY(pooler_nsp_indexed(xt.f, H, in.d_cand_cls_row, xv.f, Hv, in.d_cand_img_row, C, H, Hv, c.bi_hidden_size, tp_w, tp_b, vp_w, vp_b,
                                      nsp_w, nsp_b, d_nsp_scores, st));
-    const int n = in.n_lm_rows;
     if (n > 0) {
-        if (xk_live) UNIMM_TRY(lm_head_rows(xk, nullptr, in.d_lm_labels, n, st));       // the last text layer already gathered them
+        if (dedup) UNIMM_TRY(lm_head_shared(xk_live ? xk : xt, xk_live ? nullptr : in.d_lm_urows, in.n_lm_unique, in.d_lm_uidx, in.d_lm_labels, n, st));
+        else if (xk_live) UNIMM_TRY(lm_head_rows(xk, nullptr, in.d_lm_labels, n, st));       // the last text layer already gathered them
         else UNIMM_TRY(lm_head_rows(xt, in.d_lm_rows, in.d_lm_labels, n, st));
     }
     if (d_seq_score) UNIMM_TRY(segment_sum(row_logp, in.d_cand_lm_off, C, d_seq_score, st));
@@ -936,6 +974,7 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     if (const char* f = getenv("UNIMM_ATTN_UMMA")) e->attn_umma = atoi(f) != 0;
     if (const char* f = getenv("UNIMM_KV2_ALL")) e->kv2_ctx_only = atoi(f) == 0;
     if (const char* f = getenv("UNIMM_PRUNE_TAIL")) e->prune_tail = atoi(f) != 0;
+    if (const char* f = getenv("UNIMM_LM_DEDUP")) e->lm_dedup = atoi(f) != 0;
     e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;
@@ -1009,8 +1048,8 @@ int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, f
     PackedStage& ps = g_packed_stage[e];
     if (ps.i32 == nullptr) {
         const size_t rows = static_cast<size_t>(e->Bmax) * c.seq_len;
-        // ids, types, pos (3M) + row_iv (4M) + lm rows/labels (2M) + cand arrays (3C+1 <= 3M+1) + jobs (6U*8)
-        ps.i32_cap = rows * 12 + static_cast<size_t>(e->Bmax) * 48 + 64;
+        // ids, types, pos (3M) + row_iv (4M) + lm rows/labels/unique rows/indices (4M) + cand arrays (3C+1 <= 3M+1) + jobs (6U*8)
+        ps.i32_cap = rows * 14 + static_cast<size_t>(e->Bmax) * 48 + 64;
         UNIMM_TRY(e->dalloc(&ps.i32, ps.i32_cap));
         ps.f32_cap = static_cast<size_t>(e->Bmax) * R * (F + 6) + rows * 3 + 64;
         UNIMM_TRY(e->dalloc(&ps.f32, ps.f32_cap));
@@ -1047,6 +1086,8 @@ int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, f
     UNIMM_TRY(put_i(hb->d_cand_lm_off, static_cast<size_t>(C) + 1, &d.d_cand_lm_off));
     UNIMM_TRY(put_i(hb->d_cand_cls_row, C, &d.d_cand_cls_row));
     UNIMM_TRY(put_i(hb->d_cand_img_row, C, &d.d_cand_img_row));
+    UNIMM_TRY(put_i(hb->d_lm_urows, hb->n_lm_unique, &d.d_lm_urows));
+    UNIMM_TRY(put_i(hb->d_lm_uidx, hb->d_lm_urows != nullptr && hb->n_lm_unique > 0 ? hb->n_lm_rows : 0, &d.d_lm_uidx));
     UNIMM_TRY(put_f(hb->d_image_feat, static_cast<size_t>(U) * R * F, &d.d_image_feat));
     UNIMM_TRY(put_f(hb->d_image_loc, static_cast<size_t>(U) * R * 5, &d.d_image_loc));
     UNIMM_TRY(put_f(hb->d_image_mask, static_cast<size_t>(U) * R, &d.d_image_mask));

@@ -151,6 +151,57 @@ __global__ void lse_partials_kernel(const float2* __restrict__ partials, int til
     }
 }
 
+// Shared labelled rows (several (row, label) entries per LM-head row): log-sum-exp per unique row, then per entry the label's
+// logit as a gathered dot product  h[urow] . E[label] + b[label]  (same 16-bit operands and fp32 accumulation as the fused GEMM
+// epilogue, only the summation order differs) -> log p and log(max(1 - p, 1e-6)) (models/vilbert_dialog.py:1586-1591).
+__global__ void lse_merge_kernel(const float2* __restrict__ partials, int tiles, int rows, float* __restrict__ lse) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float2* p = partials + static_cast<size_t>(row) * tiles;
+    float mx = -INFINITY;
+    for (int i = lane; i < tiles; i += 32) mx = fmaxf(mx, p[i].x);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < tiles; i += 32) s += p[i].y * expf(p[i].x - mx);
+    s = warp_sum(s);
+    if (lane == 0) lse[row] = mx + logf(s);
+}
+
+template <bool FP16>
+__global__ void label_score_kernel(const bf16* __restrict__ h, int ldh, const bf16* __restrict__ E, int lde, const float* __restrict__ bias,
+                                   const int* __restrict__ uidx, const int* __restrict__ labels, const float* __restrict__ lse, int n, int K,
+                                   float* __restrict__ logp, float* __restrict__ ul) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int u = uidx[i], lab = labels[i];
+    const uint4* a = reinterpret_cast<const uint4*>(h + static_cast<size_t>(u) * ldh);
+    const uint4* b = reinterpret_cast<const uint4*>(E + static_cast<size_t>(lab) * lde);
+    float acc = 0.f;
+    for (int c = lane; c < K / 8; c += 32) {
+        const uint4 x = a[c], y = __ldg(b + c);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 fx, fy;
+            if (FP16) {
+                fx = __half22float2(*reinterpret_cast<const __half2*>(&xs[j])); fy = __half22float2(*reinterpret_cast<const __half2*>(&ys[j]));
+            } else {
+                fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[j])); fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[j]));
+            }
+            acc = fmaf(fx.x, fy.x, acc);
+            acc = fmaf(fx.y, fy.y, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float lp = (acc + bias[lab]) - lse[u];
+        logp[i] = lp;
+        ul[i] = logf(fmaxf(1.0f - expf(lp), 1e-6f));
+    }
+}
+
 __global__ void scatter_scores_kernel(const float* __restrict__ logp, const float* __restrict__ ul,
                                       const int* __restrict__ flat_rows, int n, float* token_logp, float* token_ul) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,6 +371,23 @@ int lse_from_partials(const float2* partials, int tiles, const float* label_logi
                       cudaStream_t stream) {
     if (rows == 0) return 0;
     lse_partials_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(partials, tiles, label_logit, rows, logp, ul);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int lse_merge(const float2* partials, int tiles, int rows, float* lse, cudaStream_t stream) {
+    if (rows == 0) return 0;
+    lse_merge_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(partials, tiles, rows, lse);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int label_scores(const bf16* h, int ldh, const bf16* E, int lde, const float* bias, const int* uidx, const int* labels, const float* lse,
+                 int n, int K, int lp_kind, float* logp, float* ul, cudaStream_t stream) {
+    if (n == 0) return 0;
+    UNIMM_CHECK(K % 8 == 0 && ldh % 8 == 0 && lde % 8 == 0, "label_scores: rows must be 16-byte aligned");
+    if (lp_kind == LP_FP16) label_score_kernel<true><<<(n + 3) / 4, 128, 0, stream>>>(h, ldh, E, lde, bias, uidx, labels, lse, n, K, logp, ul);
+    else label_score_kernel<false><<<(n + 3) / 4, 128, 0, stream>>>(h, ldh, E, lde, bias, uidx, labels, lse, n, K, logp, ul);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

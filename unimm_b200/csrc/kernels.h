@@ -166,6 +166,9 @@ int pooler_nsp(const float* xt, int ldt_seq, const float* xv, int ldv_seq, int B
 int lse_from_logits(const float* logits, int ld, int rows, int V, const int* labels, float* logp, float* ul,
                     cudaStream_t stream);
 // tcgen05 LM head tail: merge the per-tile (max, sum) partials
+int lse_merge(const float2* partials, int tiles, int rows, float* lse, cudaStream_t stream);
+int label_scores(const bf16* h, int ldh, const bf16* E, int lde, const float* bias, const int* uidx, const int* labels, const float* lse,
+                 int n, int K, int lp_kind, float* logp, float* ul, cudaStream_t stream);
 int lse_from_partials(const float2* partials, int tiles, const float* label_logit, int rows, float* logp, float* ul,
                       cudaStream_t stream);
 // scatter the compact per-row results to dense [B,S] (zero elsewhere) and sum per sequence (val_lm.py:131-136)

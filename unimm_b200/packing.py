@@ -59,7 +59,7 @@ class PackedBatch:
     """Host-side packed batch (torch CPU tensors, optionally pinned) + counts."""
 
     INT_FIELDS = ("input_ids", "token_type_ids", "position_ids", "row_iv", "jobs_text_self", "jobs_t2i", "jobs_i2t",
-                  "jobs_img_self", "lm_rows", "lm_labels", "cand_lm_off", "cand_cls_row", "cand_img_row")
+                  "jobs_img_self", "lm_rows", "lm_labels", "cand_lm_off", "cand_cls_row", "cand_img_row", "lm_urows", "lm_uidx")
     FLOAT_FIELDS = ("image_feat", "image_loc", "image_mask")
 
     def __init__(self, **kw):
@@ -97,6 +97,7 @@ class PackedBatch:
         s.pairs_text_self, s.pairs_i2t = float(self.pairs_text_self), float(self.pairs_i2t)
         s.n_shared_rows = int(getattr(self, "n_shared_rows", 0))
         s.no_cls_rows = int(bool(getattr(self, "scores_only", False)))
+        s.n_lm_unique = self.lm_urows.shape[0] if self.lm_urows.shape[0] < self.lm_rows.shape[0] else 0
         return s
 
 
@@ -216,6 +217,8 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
         jobs_img.append((ui * R, R, ui * R, R, 0, ui, 0, 0))
         max_cand_q = max(max_cand_q, rows_u)
         ci += n
+    lm_rows_all = np.concatenate(lm_rows)
+    lm_urows, lm_uidx = np.unique(lm_rows_all, return_inverse=True)     # distinct labelled rows (the shared B_0 rows appear once)
     lm_labels = np.concatenate(lm_labels).astype(np.int32)
     if (lm_labels < 0).any():
         raise ValueError("a masked-copy position carries no label")
@@ -227,7 +230,7 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
         input_ids=t(ids, np.int32), token_type_ids=t(segs, np.int32), position_ids=t(pos, np.int32), row_iv=t(row_iv, np.int32),
         jobs_text_self=t(np.asarray(jobs_ctx + jobs_cand), np.int32), n_jobs_text_ctx=len(jobs_ctx), cand_halo=max_rows_per_cand - 1, jobs_t2i=t(np.asarray(jobs_t2i), np.int32),
         jobs_i2t=t(np.asarray(jobs_i2t), np.int32), jobs_img_self=t(np.asarray(jobs_img), np.int32),
-        lm_rows=t(np.concatenate(lm_rows), np.int32), lm_labels=t(lm_labels, np.int32),
+        lm_rows=t(lm_rows_all, np.int32), lm_labels=t(lm_labels, np.int32), lm_urows=t(lm_urows, np.int32), lm_uidx=t(lm_uidx, np.int32),
         cand_lm_off=t(np.asarray(cand_lm_off), np.int32), cand_cls_row=t(cls_row, np.int32), cand_img_row=t(img_row, np.int32),
         image_feat=t(image_feat[slots], np.float32), image_loc=t(image_loc[slots], np.float32), image_mask=t(image_mask[slots], np.float32),
         max_q_text_self=max(max_cand_q, max(sh_len)), max_q_t2i=max(max_cand_q, max(sh_len)),
