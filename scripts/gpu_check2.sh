@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-P="python -m pytest -q -s -p no:cacheprovider"
-timeout 600 $P tests/test_edges_gpu.py 2>&1 | grep -E "^\.?\[|passed|failed|FAIL|Error" | cut -c1-200
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | cut -c1-300
+timeout 600 python bench.py --steps 10 --warmup 3 --precision bf16 --no-cpu-baseline > gpurun_out/bench_bf16.log 2>&1; tail -1 gpurun_out/bench_bf16.log | cut -c1-200
