@@ -91,3 +91,56 @@ def test_prediction_records_are_evalai_shaped():
     s = res["scores"]
     assert recs[4]["ranks"][int(s[1, 1].argmax())] == 1
     assert set(res["metrics"]) >= {"r@1", "r@5", "r@10", "mean", "mrr", "ndcg"}
+
+
+class _TwoPhase:
+    """Stand-in for PackedScorer: prepare() is slow host work, score() the 'device' call; both log when they start and end."""
+    def __init__(self):
+        import threading
+        self.log, self.lock, self.threads = [], threading.Lock(), set()
+
+    def _mark(self, what, step):
+        import threading
+        import time
+        with self.lock:
+            self.log.append((what, step[0].image_id, time.perf_counter()))
+            if what.startswith("prepare"):
+                self.threads.add(threading.get_ident())
+
+    def prepare(self, step):
+        import time
+        self._mark("prepare_begin", step)
+        time.sleep(0.05)
+        self._mark("prepare_end", step)
+        return [it.image_id for it in step]
+
+    def score(self, prepared, step):
+        import time
+        assert prepared == [it.image_id for it in step]            # every step is scored with ITS preparation
+        self._mark("score_begin", step)
+        time.sleep(0.05)
+        out = _scorer(step)
+        self._mark("score_end", step)
+        return out
+
+    def __call__(self, step):
+        return self.score(self.prepare(step), step)
+
+
+def test_two_phase_scorer_is_pipelined_and_gives_the_same_result():
+    import threading
+    items = _items(7)
+    serial = run_sweep(items, _scorer, 0, 1, images_per_step=2, metrics_fn=_metrics)
+    tp = _TwoPhase()
+    piped = run_sweep(items, tp, 0, 1, images_per_step=2, metrics_fn=_metrics)
+    np.testing.assert_array_equal(piped["scores"].numpy(), serial["scores"].numpy())
+    assert piped["predictions"] == serial["predictions"]
+    assert tp.threads and threading.get_ident() not in tp.threads                      # preparation ran on the worker thread
+    t = {(w, i): ts for w, i, ts in tp.log}
+    firsts = sorted({i for _, i, _ in tp.log})
+    for a, b in zip(firsts, firsts[1:]):                                               # step b is prepared while step a is scored
+        assert t[("prepare_begin", b)] < t[("score_end", a)]
+    off = _TwoPhase()
+    plain = run_sweep(items, off, 0, 1, images_per_step=2, metrics_fn=_metrics, prefetch=0)
+    np.testing.assert_array_equal(plain["scores"].numpy(), serial["scores"].numpy())
+    assert off.threads == {threading.get_ident()}

@@ -15,7 +15,9 @@ What differs from the reference loop — by design, not in results:
     (csrc/metrics.cu) or, without one, through any ``metrics_fn`` the caller passes.
 
 ``scorer(step_items) -> float32 [len(step_items), rounds, options]`` is the only device-touching piece, so the
-sharding / gathering / bookkeeping is tested on CPU with a stand-in scorer (tests/test_val_sweep_cpu.py).
+sharding / gathering / bookkeeping is tested on CPU with a stand-in scorer (tests/test_val_sweep_cpu.py).  A scorer that also
+has ``prepare(step_items)`` / ``score(prepared, step_items)`` (``PackedScorer``) is pipelined: the next step is packed and
+pinned on a worker thread while the device scores the current one.
 """
 from __future__ import annotations
 
@@ -55,22 +57,45 @@ def synthetic_items(image_ids: Sequence[int], n_candidates: int = 100) -> List[D
     return out
 
 
-def packed_scorer(engine) -> Callable[[List[DialogItem]], torch.Tensor]:
-    """Score a step with ONE prefix-shared forward through the host-buffer C ABI (unimm_score_packed_host)."""
-    from .packing import pack_units, units_from_rounds
+class PackedScorer:
+    """Scores a step with ONE prefix-shared forward through the host-buffer C ABI (unimm_score_packed_host), in two phases so
+    that ``run_sweep`` can overlap them: ``prepare`` (host only: pack + pin, ~20-30 ms for 8 images) runs on a worker thread for
+    step i + 1 while ``score`` (H2D + forward + D2H, one blocking C call that releases the GIL) runs step i.
 
-    def score(items: List[DialogItem]) -> torch.Tensor:
+    The packer's context-equality check is made on the first ``verify_steps`` steps of a scorer's life only: it catches a loader
+    whose candidates do not share their context, and costs a third of the packing time."""
+
+    def __init__(self, engine, verify_steps: int = 1):
+        self.engine = engine
+        self.verify_steps = verify_steps
+        self._prepared = 0
+
+    def prepare(self, items: List[DialogItem]):
+        from .packing import pack_units, units_from_rounds
+        if self.engine is not None and self.engine.device.type == "cuda":
+            torch.cuda.set_device(self.engine.device)           # worker threads start on device 0: pin under this rank's context
         rounds, slots = [], []
         for s, it in enumerate(items):
             rounds += list(it.rounds)
             slots += [s] * len(it.rounds)
+        verify = self._prepared < self.verify_steps
+        self._prepared += 1
+        # the ranking reads the LM scores only (val_lm.py:124-139): scores-only layout
         pb = pack_units(units_from_rounds(rounds, slots), np.stack([it.feat for it in items]), np.stack([it.loc for it in items]),
-                        np.stack([it.mask for it in items]), scores_only=True).pin()   # the ranking reads the LM scores only (val_lm.py:124-139)
+                        np.stack([it.mask for it in items]), scores_only=True, verify_shared=verify)
+        return pb.pin() if torch.cuda.is_available() else pb
+
+    def score(self, pb, items: List[DialogItem]) -> torch.Tensor:
         out = torch.empty(pb.n_cands, dtype=torch.float32).pin_memory()
-        engine.score_packed_host(pb, out)
-        n_rounds = len(items[0].rounds)
-        return out.view(len(items), n_rounds, -1).clone()
-    return score
+        self.engine.score_packed_host(pb, out)
+        return out.view(len(items), len(items[0].rounds), -1).clone()
+
+    def __call__(self, items: List[DialogItem]) -> torch.Tensor:
+        return self.score(self.prepare(items), items)
+
+
+def packed_scorer(engine) -> PackedScorer:
+    return PackedScorer(engine)
 
 
 def gpu_metrics(scores: torch.Tensor, gt_index: torch.Tensor, ndcg_scores: Optional[torch.Tensor], relevance: Optional[torch.Tensor],
@@ -85,7 +110,7 @@ def gpu_metrics(scores: torch.Tensor, gt_index: torch.Tensor, ndcg_scores: Optio
 
 
 def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1, images_per_step: int = 8,
-              metrics_fn: Optional[Callable] = None, group=None) -> Dict[str, object]:
+              metrics_fn: Optional[Callable] = None, group=None, prefetch: int = 1) -> Dict[str, object]:
     """Score this rank's images, all-gather the scores, rank them and assemble metrics + EvalAI records (on every rank).
 
     ``items`` is the GLOBAL list (every rank passes the same one; only its own shard is scored).
@@ -96,12 +121,26 @@ def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1
     mine = shard_units(n, rank, world)
     n_rounds = len(items[0].rounds)
     local = []
-    for s in range(0, len(mine), images_per_step):
-        step = [items[i] for i in mine[s:s + images_per_step]]
-        out = scorer(step)
+    steps = [[items[i] for i in mine[s:s + images_per_step]] for s in range(0, len(mine), images_per_step)]
+
+    def keep(out, step):
         if tuple(out.shape[:2]) != (len(step), n_rounds):
             raise ValueError("scorer must return [images, rounds, options]")
         local.append(out.float().cpu())
+
+    if prefetch > 0 and hasattr(scorer, "prepare") and hasattr(scorer, "score") and steps:
+        # two-phase scorer: the host-side preparation of step i + 1 overlaps the device work of step i
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(scorer.prepare, steps[0])
+            for i, step in enumerate(steps):
+                prepared = fut.result()
+                if i + 1 < len(steps):
+                    fut = pool.submit(scorer.prepare, steps[i + 1])
+                keep(scorer.score(prepared, step), step)
+    else:
+        for step in steps:
+            keep(scorer(step), step)
     n_opt = local[0].shape[-1] if local else len(items[0].rounds[0].tokens)
     local_t = torch.cat(local).reshape(len(mine), n_rounds * n_opt) if local else torch.zeros(0, n_rounds * n_opt)
     scores = gather_scores(local_t, n, rank, world, group).view(n, n_rounds, n_opt)       # the path's only exchange
@@ -136,6 +175,7 @@ def main() -> None:
     ap.add_argument("--images-per-step", type=int, default=8)
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--out", default="")
+    ap.add_argument("--prefetch", type=int, default=1, help="0: pack and score serially; 1: pack step i+1 on a worker thread while step i is scored")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -148,9 +188,19 @@ def main() -> None:
     scorer = packed_scorer(eng)
     # the score tensor is exchanged as a host tensor: 8 MB for the full val sweep, a gloo group next to NCCL is plenty
     group = dist.new_group(backend="gloo") if world > 1 else None
-    res = run_sweep(items, scorer, rank, world, a.images_per_step, metrics_fn=lambda s, g, ns, r: gpu_metrics(s, g, ns, r, dev), group=group)
+    import time
+    metrics_fn = lambda s, g, ns, r: gpu_metrics(s, g, ns, r, dev)
+    run_sweep(items[:world * a.images_per_step], scorer, rank, world, a.images_per_step, metrics_fn=metrics_fn, group=group)     # warm-up step
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    res = run_sweep(items, scorer, rank, world, a.images_per_step, metrics_fn=metrics_fn, group=group, prefetch=a.prefetch)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
     if rank == 0:
-        print(json.dumps({k: v for k, v in res["metrics"].items()}))
+        n_cand = sum(len(r.tokens) for it in items for r in it.rounds)
+        print(json.dumps(dict({k: v for k, v in res["metrics"].items()}, sweep_candidates=n_cand, sweep_seconds=dt,
+                              sweep_candidates_per_sec=n_cand / dt, prefetch=a.prefetch,
+                              note="whole driver incl. host-side packing, pinning, score gather, ranks and metrics; wall clock")))
         if a.out:
             write_predictions(res["predictions"], a.out)
     eng.close()
