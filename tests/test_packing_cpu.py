@@ -15,7 +15,9 @@ def _check(pb, rounds, scores_only=False, shared_b0=False):
     lab, off = pb.lm_labels.numpy(), pb.cand_lm_off.numpy()
     lm_rows = pb.lm_rows.numpy()
     c = 0
+    shared_list = shared_b0 if isinstance(shared_b0, (list, tuple)) else [shared_b0] * len(rounds)
     for ui, r in enumerate(rounds):
+        shared_b0 = shared_list[ui]
         ctx = int(r.desc[0, 1])
         sh, cj = jobs[ui], jobs[pb.n_jobs_text_ctx + ui]
         assert sh[1] == ctx - 1 and tuple(sh[:2]) == tuple(sh[2:4]) and sh[4] == 0          # context attends itself
@@ -116,3 +118,33 @@ def test_packer_rejects_units_that_do_not_share_a_context():
     except ValueError:
         return
     raise AssertionError("differing contexts must be rejected")
+
+
+def test_random_batches_in_every_layout():
+    """Seeded random batches (1-5 units, 1-25 candidates, answers of 0-7 tokens, rounds 1-10) through the three layouts: every
+    packed row reproduces its dense position and its dense-mask key set; the layouts agree on labels and candidate offsets."""
+    rng = np.random.RandomState(1234)
+    img = syn.synth_image(rng)
+    for trial in range(25):
+        rounds = []
+        for _ in range(int(rng.randint(1, 6))):
+            n = int(rng.randint(1, 26))
+            answers = [list(rng.randint(1000, 30522, size=int(rng.randint(0, 8)))) for _ in range(n)]
+            rounds.append(syn.encode_round_gen(syn.synth_context(rng, int(rng.randint(1, 11))), answers))
+        slots = [0] * len(rounds)
+        args = (units_from_rounds(rounds, slots), img[0][None], img[1][None], img[2][None])
+        full = pack_units(*args)
+        lean = pack_units(*args, scores_only=True, share_first_mask=False)
+        b0 = pack_units(*args, scores_only=True)
+        _check(full, rounds)
+        _check(lean, rounds, scores_only=True)
+        shared = [len(r.desc) > 1 for r in rounds]          # a unit of one candidate keeps its own B_0 row
+        _check(b0, rounds, scores_only=True, shared_b0=shared)
+        assert b0.n_b0_shared == sum(shared)
+        assert lean.n_text_rows == full.n_text_rows - 2 * full.n_cands
+        assert b0.n_text_rows == lean.n_text_rows - sum(len(r.desc) - 1 for r, sh in zip(rounds, shared) if sh)
+        for other in (lean, b0):
+            assert (other.lm_labels == full.lm_labels).all() and (other.cand_lm_off == full.cand_lm_off).all()
+        # the distinct-row lists reconstruct lm_rows
+        assert (b0.lm_urows[b0.lm_uidx.long()] == b0.lm_rows).all() and len(torch.unique(b0.lm_urows)) == len(b0.lm_urows)
+        assert int(b0.row_iv[:, 1].max()) <= b0.n_text_rows and int(b0.lm_rows.max()) < b0.n_text_rows
