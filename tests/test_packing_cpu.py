@@ -5,7 +5,8 @@ import torch
 from conftest import load_golden
 from unimm_b200 import synthetic as syn
 from unimm_b200.descriptors import dense_text_mask, descriptors_from_masks
-from unimm_b200.packing import pack_units, units_from_flat, units_from_rounds
+from packing_reference import pack_units_loop
+from unimm_b200.packing import PackedBatch, pack_units, units_from_flat, units_from_rounds
 
 
 def _check(pb, rounds, scores_only=False, shared_b0=False):
@@ -136,6 +137,14 @@ def test_random_batches_in_every_layout():
         full = pack_units(*args)
         lean = pack_units(*args, scores_only=True, share_first_mask=False)
         b0 = pack_units(*args, scores_only=True)
+        # the vectorised packer and the per-unit loop build the same batch, tensor for tensor
+        for got, kw in ((full, {}), (lean, dict(scores_only=True, share_first_mask=False)), (b0, dict(scores_only=True))):
+            want = pack_units_loop(*args, **kw)
+            for k in PackedBatch.INT_FIELDS + PackedBatch.FLOAT_FIELDS:
+                assert torch.equal(getattr(got, k), getattr(want, k)), (trial, kw, k)
+            for k in ("n_text_rows", "n_shared_rows", "cand_halo", "win_cap", "kv_cap_text", "max_q_text_self", "n_jobs_text_ctx",
+                      "pairs_text_self", "pairs_i2t", "n_b0_shared"):
+                assert getattr(got, k) == getattr(want, k), (trial, kw, k)
         _check(full, rounds)
         _check(lean, rounds, scores_only=True)
         shared = [len(r.desc) > 1 for r in rounds]          # a unit of one candidate keeps its own B_0 row

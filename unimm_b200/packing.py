@@ -208,7 +208,11 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
         lm_labels[l0_:l1_] = np.take(u.labels.reshape(-1), flat_lab[l0_:l1_])
     if (lm_labels < 0).any():
         raise ValueError("a masked-copy position carries no label")
-    lm_urows, lm_uidx = np.unique(lm_rows_all, return_inverse=True)     # distinct labelled rows (the shared B_0 rows appear once)
+    # distinct labelled rows in ascending order (the shared B_0 rows appear once) and every entry's index among them
+    is_lm = np.zeros(M, bool)
+    is_lm[lm_rows_all] = True
+    lm_urows = np.flatnonzero(is_lm)
+    lm_uidx = (np.cumsum(is_lm) - 1)[lm_rows_all]
     # ---- attention jobs (8 int32 each: q_start, q_len, kv_start, kv_len, win, mask_row, 0, 0)
     zu, uu = np.zeros(U, np.int64), np.arange(U)
     s0_u, q0_u = sh_start[:-1], unit_base[:-1]
