@@ -137,6 +137,16 @@ def test_random_batches_in_every_layout():
         full = pack_units(*args)
         lean = pack_units(*args, scores_only=True, share_first_mask=False)
         b0 = pack_units(*args, scores_only=True)
+        # units given as row ranges of ONE stacked array per field (the reference loader's layout) take the grouped gather path
+        tok, seg, pos, lab, dsc, index = syn.stack_rounds(rounds)
+        stacked = units_from_flat(tok, seg, pos, lab, dsc, index)
+        for u in stacked:
+            u.image_slot = 0
+        assert len(stacked) == len(rounds) and all(u.tokens.base is stacked[0].tokens.base for u in stacked)
+        for got, kw in ((full, {}), (b0, dict(scores_only=True))):
+            again = pack_units(stacked, *args[1:], **kw)
+            for k in PackedBatch.INT_FIELDS + PackedBatch.FLOAT_FIELDS:
+                assert torch.equal(getattr(got, k), getattr(again, k)), (trial, kw, k)
         # the vectorised packer and the per-unit loop build the same batch, tensor for tensor
         for got, kw in ((full, {}), (lean, dict(scores_only=True, share_first_mask=False)), (b0, dict(scores_only=True))):
             want = pack_units_loop(*args, **kw)

@@ -101,6 +101,18 @@ class PackedBatch:
         return s
 
 
+def _row_range_of(a: np.ndarray):
+    """(base, first_row) when ``a`` is a row range of a C-contiguous 2-D array with the same row length, else (a itself, 0)."""
+    b = a.base
+    if isinstance(b, np.ndarray) and b.ndim == 2 and a.ndim == 2 and b.shape[1] == a.shape[1] and b.dtype == a.dtype \
+            and b.flags.c_contiguous and a.flags.c_contiguous:
+        off = a.__array_interface__["data"][0] - b.__array_interface__["data"][0]
+        row_bytes = b.shape[1] * b.itemsize
+        if off >= 0 and off % row_bytes == 0 and off // row_bytes + a.shape[0] <= b.shape[0]:
+            return b, off // row_bytes
+    return np.ascontiguousarray(a), 0
+
+
 def _roundup(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -124,27 +136,44 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
     if (desc[:, 1] != ctx_u[unit_of]).any() or (ctx_u < 2).any():
         raise ValueError("all candidates of a unit must share one context of at least one token")
     last, L = desc[:, 3], desc[:, 2]
+    if verify_shared:
+        for ui, u in enumerate(units):
+            ctx = int(ctx_u[ui])
+            if n_u[ui] > 1:
+                same = (u.tokens[:, 1:ctx] == u.tokens[0, 1:ctx]).all() and (u.segments[:, 1:ctx] == u.segments[0, 1:ctx]).all() \
+                    and (u.positions[:, 1:ctx] == u.positions[0, 1:ctx]).all()
+                if not same:
+                    raise ValueError("candidates of a unit differ in their context rows: cannot share the prefix")
+    # ---- source arrays: consecutive units that are row ranges of the same arrays (the rounds of an image, as the reference's
+    # loader stores them) are gathered from with ONE numpy call per field; a stand-alone unit is a group of its own
+    S = units[0].tokens.shape[1]
+    first_c = np.concatenate([[0], np.cumsum(n_u)])[:-1]          # first candidate of every unit
+    src = [[_row_range_of(a) for a in (u.tokens, u.segments, u.positions, u.labels)] for u in units]
+    row0_u = np.asarray([[r0 for _, r0 in fields] for fields in src], np.int64)            # [U,4] first row inside the base
+    groups, g0 = [], 0                                                                    # (first unit, end unit)
+    for ui in range(1, U + 1):
+        if ui == U or any(src[ui][f][0] is not src[g0][f][0] for f in range(4)):
+            groups.append((g0, ui))
+            g0 = ui
+    c_end = np.concatenate([first_c, [C_tot]])
+    local_c = np.arange(C_tot) - first_c[unit_of]                 # candidate index inside its unit
+    # B_0 (the first masked position) sees the context and itself only; if its token / segment / position agree across the
+    # candidates its whole row is the same for all of them: one row per unit (scores-only layout: nothing but [CLS] attends it)
     b0_shared = np.zeros(U, np.int64)
-    for ui, u in enumerate(units):
-        ctx = int(ctx_u[ui])
-        if verify_shared and n_u[ui] > 1:
-            same = (u.tokens[:, 1:ctx] == u.tokens[0, 1:ctx]).all() and (u.segments[:, 1:ctx] == u.segments[0, 1:ctx]).all() \
-                and (u.positions[:, 1:ctx] == u.positions[0, 1:ctx]).all()
-            if not same:
-                raise ValueError("candidates of a unit differ in their context rows: cannot share the prefix")
-        # B_0 (the first masked position) sees the context and itself only; if its token / segment / position agree across the
-        # candidates its whole row is the same for all of them: one row per unit (scores-only layout: nothing but [CLS] attends it)
-        if scores_only and share_first_mask and n_u[ui] > 1:
-            fl = np.arange(len(u.desc)) * u.tokens.shape[1] + np.asarray(u.desc[:, 2], np.int64)      # flat index of (c, L_c)
-            tk, sg, ps = (np.take(a.reshape(-1), fl) for a in (u.tokens, u.segments, u.positions))
-            b0_shared[ui] = int((tk == tk[0]).all() and (sg == sg[0]).all() and (ps == ps[0]).all())
+    if scores_only and share_first_mask:
+        ok = np.ones(C_tot, bool)
+        for g_lo, g_hi in groups:
+            c0, c1 = int(c_end[g_lo]), int(c_end[g_hi])
+            for f in range(3):
+                v = np.take(src[g_lo][f][0].reshape(-1), (row0_u[unit_of[c0:c1], f] + local_c[c0:c1]) * S + L[c0:c1])
+                ok[c0:c1] &= v == v[first_c[unit_of[c0:c1]] - c0]
+        b0_shared = (np.logical_and.reduceat(ok, first_c) & (n_u > 1)).astype(np.int64)
     # ---- row layout: [all units' context rows | per unit: its shared B_0 row (if any), candidate 0's rows, candidate 1's rows, ...]
     sh_len = ctx_u - 1
     sh_start = np.concatenate([[0], np.cumsum(sh_len)])
     n_shared = int(sh_start[-1])
     b_drop = b0_shared[unit_of]                                   # [C] 1: this candidate's B_0 lives in the unit's shared row
     rep = n_cls - a_drop - b_drop + 2 * last                      # [C] own rows: [CLS] (n_cls), A_0..A_{na-1}, B_{b_drop}..B_{last-1}
-    first_c = np.concatenate([[0], np.cumsum(n_u)])[:-1]          # first candidate of every unit
     rep_excl = np.cumsum(rep) - rep                               # own rows before candidate c (whole batch)
     unit_own = np.add.reduceat(rep, first_c)                      # own rows of every unit (n_u >= 1)
     unit_rows = b0_shared + unit_own
@@ -186,26 +215,22 @@ def pack_units(units: Sequence[UnitArrays], image_feat: np.ndarray, image_loc: n
     pos = np.zeros(M, np.int32)
     lm_labels = np.empty(int(lm_off[-1]), np.int32)
     own_off = np.concatenate([[0], np.cumsum(unit_own)])
-    lm_unit_off = lm_off[np.concatenate([first_c, [C_tot]])]
-    S = units[0].tokens.shape[1]
-    flat_src = (owner - first_c[unit_of][owner]) * S + src_col           # index into the unit's flattened [n, S] arrays
-    flat_lab = (owner_l - first_c[unit_of][owner_l]) * S + lab_col
-    for ui, u in enumerate(units):
-        ctx, s0, q0 = int(ctx_u[ui]), int(sh_start[ui]), int(unit_base[ui])
-        ids[s0:s0 + ctx - 1] = u.tokens[0, 1:ctx]
-        segs[s0:s0 + ctx - 1] = u.segments[0, 1:ctx]
-        pos[s0:s0 + ctx - 1] = u.positions[0, 1:ctx]
-        o0, o1 = int(own_off[ui]), int(own_off[ui + 1])
-        d0 = q0 + int(b0_shared[ui])                              # the unit's own rows are the contiguous range [d0, d0 + o1 - o0)
-        fi = flat_src[o0:o1]
-        ids[d0:d0 + o1 - o0] = np.take(u.tokens.reshape(-1), fi)
-        segs[d0:d0 + o1 - o0] = np.take(u.segments.reshape(-1), fi)
-        pos[d0:d0 + o1 - o0] = np.take(u.positions.reshape(-1), fi)
-        if b0_shared[ui]:
-            l0 = int(u.desc[0, 2])
-            ids[q0], segs[q0], pos[q0] = u.tokens[0, l0], u.segments[0, l0], u.positions[0, l0]
-        l0_, l1_ = int(lm_unit_off[ui]), int(lm_unit_off[ui + 1])
-        lm_labels[l0_:l1_] = np.take(u.labels.reshape(-1), flat_lab[l0_:l1_])
+    lm_unit_off = lm_off[c_end]
+    u_own, u_lm = unit_of[owner], unit_of[owner_l]
+    ctx_unit = np.repeat(np.arange(U), sh_len)                    # unit of every context row
+    ctx_col = 1 + np.arange(n_shared) - sh_start[:-1][ctx_unit]   # its dense column (candidate 0 of the unit)
+    own_dst = unit_base[:-1] + b0_shared                          # the unit's own rows are the contiguous range [own_dst, + unit_own)
+    for g_lo, g_hi in groups:
+        o0, o1 = int(own_off[g_lo]), int(own_off[g_hi])
+        s0, s1 = int(sh_start[g_lo]), int(sh_start[g_hi])
+        l0_, l1_ = int(lm_unit_off[g_lo]), int(lm_unit_off[g_hi])
+        b0u = np.flatnonzero(b0_shared[g_lo:g_hi]) + g_lo
+        for f, dst_arr in enumerate((ids, segs, pos)):
+            base = src[g_lo][f][0].reshape(-1)
+            dst_arr[s0:s1] = np.take(base, row0_u[ctx_unit[s0:s1], f] * S + ctx_col[s0:s1])
+            dst_arr[dst[o0:o1]] = np.take(base, (row0_u[u_own[o0:o1], f] + local_c[owner[o0:o1]]) * S + src_col[o0:o1])
+            dst_arr[unit_base[b0u]] = np.take(base, row0_u[b0u, f] * S + L[first_c[b0u]])
+        lm_labels[l0_:l1_] = np.take(src[g_lo][3][0].reshape(-1), (row0_u[u_lm[l0_:l1_], 3] + local_c[owner_l[l0_:l1_]]) * S + lab_col[l0_:l1_])
     if (lm_labels < 0).any():
         raise ValueError("a masked-copy position carries no label")
     # distinct labelled rows in ascending order (the shared B_0 rows appear once) and every entry's index among them
@@ -249,8 +274,8 @@ def units_from_rounds(rounds, image_slots: Optional[List[int]] = None) -> List[U
 def units_from_flat(tokens, segments, positions, labels, desc, unit_index) -> List[UnitArrays]:
     """Reference-format flat batch ([B,S] tensors + descriptors) grouped by ``unit_index`` [B] (non-decreasing)."""
     tok, seg, pos, lab, d, ui = (np.asarray(x) for x in (tokens, segments, positions, labels, desc, unit_index))
-    out = []
-    for u in np.unique(ui):
-        m = ui == u
-        out.append(UnitArrays(tok[m], seg[m], pos[m], lab[m], d[m], int(u)))
-    return out
+    if ui.size and (np.diff(ui) < 0).any():
+        raise ValueError("unit_index must be non-decreasing")
+    cuts = np.concatenate([[0], np.flatnonzero(np.diff(ui)) + 1, [ui.size]])
+    # row ranges (views) of the flat arrays: the packer gathers from the flat arrays directly
+    return [UnitArrays(tok[a:b], seg[a:b], pos[a:b], lab[a:b], d[a:b], int(ui[a])) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]

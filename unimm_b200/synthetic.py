@@ -122,7 +122,15 @@ def synth_dialog_rounds(image_id: int, rounds: Sequence[int] = tuple(range(1, 11
     out = []
     for r in rounds:
         out.append(encode_round_gen(synth_context(rng, r), synth_answers(rng, n_candidates)))
-    return img, out
+    # like the reference's loader (dataloader_visdial.py:437-457: one [rounds * options, 256] tensor per field and image), keep
+    # the rounds of an image as row ranges of ONE array per field: the packer then gathers per image instead of per round
+    cat = {f: np.concatenate([getattr(r, f) for r in out], 0) for f in ("tokens", "segments", "positions", "labels", "desc")}
+    views, s = [], 0
+    for r in out:
+        e = s + len(r.tokens)
+        views.append(Round(cat["tokens"][s:e], cat["segments"][s:e], cat["positions"][s:e], cat["labels"][s:e], cat["desc"][s:e]))
+        s = e
+    return img, views
 
 
 def stack_rounds(rounds: Sequence[Round]):

@@ -22,6 +22,7 @@ pinned on a worker thread while the device scores the current one.
 from __future__ import annotations
 
 import json
+import threading
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -69,6 +70,7 @@ class PackedScorer:
         self.engine = engine
         self.verify_steps = verify_steps
         self._prepared = 0
+        self._lock = threading.Lock()
 
     def prepare(self, items: List[DialogItem]):
         from .packing import pack_units, units_from_rounds
@@ -78,8 +80,9 @@ class PackedScorer:
         for s, it in enumerate(items):
             rounds += list(it.rounds)
             slots += [s] * len(it.rounds)
-        verify = self._prepared < self.verify_steps
-        self._prepared += 1
+        with self._lock:
+            verify = self._prepared < self.verify_steps
+            self._prepared += 1
         # the ranking reads the LM scores only (val_lm.py:124-139): scores-only layout
         pb = pack_units(units_from_rounds(rounds, slots), np.stack([it.feat for it in items]), np.stack([it.loc for it in items]),
                         np.stack([it.mask for it in items]), scores_only=True, verify_shared=verify)
@@ -130,13 +133,15 @@ def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1
 
     if prefetch > 0 and hasattr(scorer, "prepare") and hasattr(scorer, "score") and steps:
         # two-phase scorer: the host-side preparation of step i + 1 overlaps the device work of step i
+        # (``prefetch`` steps in flight on as many worker threads: the packer spends most of its time inside numpy, GIL released)
+        from collections import deque
         from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            fut = pool.submit(scorer.prepare, steps[0])
+        with ThreadPoolExecutor(max_workers=prefetch) as pool:
+            futs = deque(pool.submit(scorer.prepare, st) for st in steps[:prefetch])
             for i, step in enumerate(steps):
-                prepared = fut.result()
-                if i + 1 < len(steps):
-                    fut = pool.submit(scorer.prepare, steps[i + 1])
+                prepared = futs.popleft().result()
+                if i + prefetch < len(steps):
+                    futs.append(pool.submit(scorer.prepare, steps[i + prefetch]))
                 keep(scorer.score(prepared, step), step)
     else:
         for step in steps:
@@ -175,7 +180,7 @@ def main() -> None:
     ap.add_argument("--images-per-step", type=int, default=8)
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--out", default="")
-    ap.add_argument("--prefetch", type=int, default=1, help="0: pack and score serially; 1: pack step i+1 on a worker thread while step i is scored")
+    ap.add_argument("--prefetch", type=int, default=1, help="0: pack and score serially; n: pack steps i+1..i+n on n worker threads while step i is scored")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
