@@ -167,3 +167,20 @@ def test_random_batches_in_every_layout():
         # the distinct-row lists reconstruct lm_rows
         assert (b0.lm_urows[b0.lm_uidx.long()] == b0.lm_rows).all() and len(torch.unique(b0.lm_urows)) == len(b0.lm_urows)
         assert int(b0.row_iv[:, 1].max()) <= b0.n_text_rows and int(b0.lm_rows.max()) < b0.n_text_rows
+
+
+def test_units_backed_by_odd_arrays_pack_the_same():
+    """Units whose arrays are not row ranges of a contiguous array (column-strided views, different bases per field) go through
+    the stand-alone path and give the same batch."""
+    rng = np.random.RandomState(9)
+    img = syn.synth_image(rng)
+    rounds = [syn.encode_round_gen(syn.synth_context(rng, r), syn.synth_answers(rng, n)) for r, n in ((2, 5), (6, 8))]
+    want = pack_units(units_from_rounds(rounds, [0, 0]), img[0][None], img[1][None], img[2][None], scores_only=True)
+    odd = []
+    for r in rounds:
+        wide = np.zeros((len(r.tokens), 512), np.int64)
+        wide[:, ::2] = r.tokens                                    # every second column: a non-contiguous view
+        odd.append(syn.Round(wide[:, ::2], np.asfortranarray(r.segments), r.positions.copy(), r.labels, r.desc))
+    got = pack_units(units_from_rounds(odd, [0, 0]), img[0][None], img[1][None], img[2][None], scores_only=True)
+    for k in PackedBatch.INT_FIELDS + PackedBatch.FLOAT_FIELDS:
+        assert torch.equal(getattr(got, k), getattr(want, k)), k
