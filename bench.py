@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the generative-scoring hot path: candidates scored per second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|bf16|fp32] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|bf16|fp32] [--impl ours|reference] [--workload steps|sweep]
 
-Workload (BASELINE.json configs[1]): the synthetic VisDial v1.0 val sweep — images x 10 rounds x 100
-candidate answers, generative (autoregressive-MLM) masks, text padded to 256, 36 regions + global,
-random-init bert_base_6layer_6conect.  One STEP = one image = 10 rounds x 100 candidates = 1000 sequences
-per rank, run as forward chunks of --chunk sequences.  Ranks own images rank, rank+N, ... (weak scaling, no
-collective on the data path; one all-gather of the scores at the end).
+Workload (BASELINE.json configs[1]): the synthetic VisDial v1.0 val sweep — images x 10 rounds x 100 candidate answers,
+generative (autoregressive-MLM) masks, text padded to 256, 36 regions + global, random-init bert_base_6layer_6conect.
 
-Numbers on the JSON line
-  value     candidates/s, inputs already resident in HBM, CUDA-event timed, max over ranks
-  e2e       the same through the C ABI with pinned HOST buffers (unimm_score_host: H2D + forward + D2H + sync)
-  roofline  the tcgen05 GEMM class: algorithmic FLOPs / CUDA-event time of those launches inside the timed region
+--workload steps (default; what the driver times): one STEP = --images-per-step images = that many x 10 rounds x 100 candidates per
+rank as ONE prefix-shared forward; ranks own different images (weak scaling, no collective on the data path; one NCCL all-gather of
+the scores at the end).
+  value     candidates/s, packed inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e       the same measured from the REFERENCE'S OWN HOST LAYOUT (per image one int64 [1000, 256] tensor per field + one feature
+            block, dataloader_visdial.py:437-457): every step packs on the host (C++ packer, csrc/packer.cu, into pinned staging;
+            step i + 1 on a worker thread while the device runs step i), copies H2D, runs the forward, copies the scores D2H and
+            synchronises — all inside the timed region (CUDA events on the launch stream around the K steps)
+  roofline  the dominant tcgen05 GEMM class: algorithmic FLOPs / CUDA-event time of those launches inside the timed region
   cpu_baseline  the oracle (CPU port of the reference path, val_lm-style full logits) on the host cores (rank 0, N=1)
+  bf16_mode  (fp16 runs only) value / e2e / % of peak of the SAME step in bf16 mode, measured in the same process
 
---impl reference times that CPU port alone (the reference has no compiled code to build; oracle/ is its
-restatement, pinned by tests/golden).  Nothing here reads /root/reference.
+--workload sweep: the WHOLE sweep (--images, default 2064) strong-scaled over the ranks through unimm_b200.val_sweep (packing,
+scoring, NCCL all-gather, GPU ranks / metrics, EvalAI records), wall clock, max over ranks.
+
+--impl reference times the CPU port alone (the reference is pure Python: nothing to compile into oracle/_ref; oracle/ is its
+restatement, pinned by tests/golden) on 100-candidate rounds in chunks of 25.  Nothing here reads /root/reference.
 """
 from __future__ import annotations
 
@@ -153,19 +159,11 @@ def run_step_host(eng, b, chunk, score_host, HostArrays):
     return h2d, d2h
 
 
-def packed_step_batch(first_image, n_images, stride, scores_only=True, share_first_mask=True):
-    """One prefix-shared step: n_images synthetic images x 10 rounds x 100 candidates, packed (pinned host tensors)."""
-    from unimm_b200 import synthetic as syn
-    from unimm_b200.packing import pack_units, units_from_rounds
-    rounds, slots, feats, locs, masks = [], [], [], [], []
-    for i in range(n_images):
-        (feat, loc, mask), rs = syn.synth_dialog_rounds(first_image + i * stride)
-        rounds += rs
-        slots += [i] * len(rs)
-        feats.append(feat), locs.append(loc), masks.append(mask)
-    pb = pack_units(units_from_rounds(rounds, slots), np.stack(feats), np.stack(locs), np.stack(masks), scores_only=scores_only,
-                    share_first_mask=share_first_mask)
-    return pb.pin()
+def step_items(first_image, n_images, stride=1):
+    """One step's inputs in the reference's host layout: ``n_images`` DialogItems (val_sweep), each holding one int64
+    [1000, 256] array per field (10 rounds x 100 candidates) and its [37, 2048] feature block."""
+    from unimm_b200.val_sweep import synthetic_items
+    return synthetic_items([first_image + i * stride for i in range(n_images)])
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -252,15 +250,17 @@ def main_reference(args):
                           "gpu_eager": {"what": "the oracle's restatement of the reference forward as eager PyTorch on cuda:0 (vendor-library "
                                                 "kernels; not the product path, not the driver's reference arm)", "mode": args.ref_mode}}), flush=True)
         return
-    per_step = 10
-    rate, sec, cores = cpu_reference_rate(per_step, steps=args.steps, warmup=args.warmup)
+    per_step = args.ref_candidates          # one 100-candidate round per step, chunks of 25
+    rate, sec, cores = cpu_reference_rate(per_step, steps=args.steps, warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": "candidates_scored_per_sec", "value": rate, "unit": "candidates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "configs[1] synthetic VisDial val sweep, generative scoring (bounded CPU sample)",
-                       "candidates_per_step": per_step, "seq_len": 256, "regions": 37, "model": "bert_base_6layer_6conect random init"},
+            "config": {"workload": "configs[1] synthetic VisDial val sweep, generative scoring (bounded CPU sample: one round-10 dialog "
+                                   "round of %d candidates per step; the CPU port of the reference path, not the unmodified module)" % per_step,
+                       "candidates_per_step": per_step, "seq_len": 256, "regions": 37, "model": "bert_base_6layer_6conect random init",
+                       "cpu_warmup_steps": min(args.warmup, 1)},
             "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {per_step} candidates of a round-10 dialog, chunks of <=25, full-vocab logits "
+                             "sample": f"{args.steps} steps x {per_step} candidates of a round-10 dialog, chunks of 25, full-vocab logits "
                                        "+ cross_entropy as val_lm.py:121-137"},
             "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -268,11 +268,127 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def measure_packed(args, eng, scorer, step_list, dev, world, rank, stream, sampler=None, gathered=None):
+    """Device-resident and end-to-end throughput of one engine over ``step_list`` (lists of DialogItems, cycled)."""
+    import torch.distributed as dist
+    from unimm_b200._lib import lib
+    from unimm_b200.flat_packer import view_to_batch
+    n_batches = len(step_list)
+    cands_per_step = sum(len(r.tokens) for it in step_list[0] for r in it.rounds)
+    R, F = eng.num_regions, eng.cfg.v_feature_size
+    devb, h2d_bytes = [], 0
+    for st in step_list:                                    # device-resident copies of the SAME packed batches the e2e loop builds
+        v = scorer.prepare(st)
+        devb.append(view_to_batch(v, R, F).to(dev))
+        h2d_bytes = v.bytes()
+    lm_rows = float(sum(b.lm_rows.shape[0] for b in devb)) / n_batches
+    packed_rows = float(sum(b.n_text_rows for b in devb)) / n_batches
+    scores = torch.zeros(args.steps, cands_per_step, device=dev)
+    scratch = torch.zeros(cands_per_step, device=dev)
+
+    def step_device(i, out):
+        out.copy_(eng.forward_packed(devb[i % n_batches], want=("seq_score",))["seq_score"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step_device(i, scratch)
+    if world > 1:                                            # warm the exchange up as well (NCCL connects its all-gather channels lazily)
+        if gathered is None:
+            gathered = [torch.empty_like(scores) for _ in range(world)]
+        dist.all_gather(gathered, scores)
+    barrier()
+    lib.unimm_reset_launch_count()
+    eng.profile_begin()                                      # per-class events are recorded inside the timed region: they only deflate `value`
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.mark_start()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_device(i, scores[i])
+    if world > 1:                                            # the path's only exchange: gather the scores for the metrics
+        dist.all_gather(gathered, scores)
+    ev1.record(stream)
+    barrier()
+    launches = int(lib.unimm_launch_count())
+    prof = eng.profile_end()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+
+    # ---- end to end from the reference's host layout: pack (worker thread, one step ahead) + H2D + forward + D2H + sync per step
+    from concurrent.futures import ThreadPoolExecutor
+    last = [None]
+
+    def run_e2e(n_steps):
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(scorer.prepare, step_list[0])
+            for i in range(n_steps):
+                view = fut.result()
+                if i + 1 < n_steps:
+                    fut = pool.submit(scorer.prepare, step_list[(i + 1) % n_batches])
+                last[0] = scorer.score(view, step_list[i % n_batches])
+
+    run_e2e(min(args.warmup, 3))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    run_e2e(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    # the two paths must agree (same kernels, same inputs as the last timed step)
+    ref_scores = torch.zeros(cands_per_step, device=dev)
+    step_device(args.steps - 1, ref_scores)
+    torch.cuda.synchronize(dev)
+    assert torch.allclose(ref_scores.cpu(), last[0].reshape(-1), atol=1e-5), "host and device paths disagree"
+    total = world * args.steps * cands_per_step
+    return {"value": total / (ms_total * 1e-3), "ms_total": ms_total, "e2e": total / (float(ms2[0]) * 1e-3), "e2e_wall": total / (float(ms2[1]) * 1e-3),
+            "h2d": h2d_bytes, "d2h": 4 * cands_per_step, "launches": launches, "prof": prof, "lm_rows": lm_rows, "packed_rows": packed_rows,
+            "cands_per_step": cands_per_step, "gathered": gathered}
+
+
+def main_sweep(args):
+    import torch.distributed as dist
+    from unimm_b200.val_sweep import synthetic_sweep
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local) if rank == 0 else None
+    rep = synthetic_sweep(args.images, args.images_per_step, args.precision, 1, not args.no_verify, "", rank, world, local)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        steps = -(-len(range(0, args.images, world)) // args.images_per_step)
+        line = {"metric": "candidates_scored_per_sec", "value": rep["sweep_candidates_per_sec"], "unit": "candidates/s", "n_gpus": world,
+                "steps": steps, "warmup": 1, "ms_per_step": rep["sweep_seconds"] * 1e3 / steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "configs[1] WHOLE sweep: %d synthetic images x 10 rounds x 100 candidates, strong-scaled over %d rank(s) "
+                                       "(image i -> rank i mod N), %d images per step" % (args.images, world, args.images_per_step),
+                           "model": "bert_base_6layer_6conect, random init (seed 0)", "mode": "packed (prefix-shared, scores only)",
+                           "timing": "wall clock from the first pack to the last EvalAI record, max over ranks (clocks line covers generation + warm-up too)"},
+                "e2e": {"value": rep["sweep_candidates_per_sec"], "unit": "candidates/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": 4000 * args.images_per_step},
+                "sweep": rep, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main_ours(args):
     import torch.distributed as dist
     from unimm_b200.config import DEFAULT_CONFIG_PATH, ViLBertConfig
     from unimm_b200.engine import Engine, HostArrays
     from unimm_b200._lib import lib
+    from unimm_b200.val_sweep import packed_scorer
     from unimm_b200.weights import random_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,29 +403,41 @@ def main_ours(args):
     n_batches = max(2, min(4, args.steps))                   # distinct inputs cycled through the timed steps
     packed = args.mode == "packed"
     stream = torch.cuda.current_stream(dev)
+    sd = random_state_dict(cfg, 0)
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi needs ~100 ms to spin up
+    extra = {}
     if packed:
-        cands_per_step = args.images_per_step * SEQ_PER_IMAGE
-        host = [packed_step_batch((rank + world * i) * args.images_per_step, args.images_per_step, 1, not args.nsp_rows, not args.own_b0) for i in range(n_batches)]
-        cap = max(max(-(-pb.n_text_rows // 256) for pb in host), max(pb.n_units for pb in host)) + 1    # workspace in 256-row units
+        ips = args.images_per_step
+        step_list = [step_items((rank + world * i) * ips, ips) for i in range(n_batches)]
+        cap = ips * 52                                       # workspace in 256-row units (a step of 8 images is ~75 k packed rows)
+        eng = Engine(cfg, sd, precision=args.precision, max_sequences=cap, device=local)
+        scorer = packed_scorer(eng, verify_shared=not args.no_verify)
+        if args.nsp_rows or args.own_b0:
+            raise SystemExit("--nsp-rows / --own-b0 were round-1 layout A/B switches; the bench packs scores-only with one B_0 row per round")
+        r = measure_packed(args, eng, scorer, step_list, dev, world, rank, stream, sampler)
+        clocks = sampler.stop() if sampler else None
+        value, ms_total, e2e_value, h2d, d2h, launches, prof = r["value"], r["ms_total"], r["e2e"], r["h2d"], r["d2h"], r["launches"], r["prof"]
+        cands_per_step, packed_rows = r["cands_per_step"], r["packed_rows"]
+        rows_per_cand = r["lm_rows"] / cands_per_step
+        extra["e2e_wall_clock"] = r["e2e_wall"]
+        if args.precision == "fp16" and not args.no_bf16:
+            # the metric is quoted against the bf16 tensor peak and the north star names a bf16 mode: the same steps in bf16 mode,
+            # same process, right after the fp16 measurement
+            eng.close()
+            eng = Engine(cfg, sd, precision="bf16", max_sequences=cap, device=local)
+            scorer = packed_scorer(eng, verify_shared=not args.no_verify)
+            rb = measure_packed(args, eng, scorer, step_list, dev, world, rank, stream, None, r["gathered"])
+            ex_b = sum(rb["prof"][k]["work"] for k in ("gemm", "gemm_ln", "attention", "lm_head"))
+            tf_b = ex_b / (rb["ms_total"] * 1e-3) / 1e12
+            pk = peaks()
+            gb = rb["prof"]["gemm"]
+            extra["bf16_mode"] = {"value": rb["value"], "e2e": rb["e2e"], "ms_per_step": rb["ms_total"] / args.steps, "executed_tflops": tf_b,
+                                  "pct_of_bf16_peak_burst": tf_b / pk["burst"], "pct_of_bf16_peak_sustained": tf_b / pk["sustained"],
+                                  "gemm_tflops": gb["work"] / (gb["ms"] * 1e-3) / 1e12 if gb["ms"] > 0 else None,
+                                  "share_of_step": {k: round(v["ms"] / rb["ms_total"], 4) for k, v in rb["prof"].items()},
+                                  "note": "bf16 operands, fp32 residual stream, exact-form GELU; parity bound 2e-2 (tests/test_parity_gpu.py)"}
     else:
-        cap = chunk
-    eng = Engine(cfg, random_state_dict(cfg, 0), precision=args.precision, max_sequences=cap, device=local)
-    if packed:
-        devb = [pb.to(dev) for pb in host]
-        rows_per_cand = float(sum(pb.lm_rows.shape[0] for pb in host)) / (n_batches * cands_per_step)
-        packed_rows = float(sum(pb.n_text_rows for pb in host)) / n_batches
-        scores = torch.zeros(args.steps, cands_per_step, device=dev)
-
-        def step_device(i, out):
-            out.copy_(eng.forward_packed(devb[i % n_batches], want=("seq_score",))["seq_score"])
-
-        score_host = torch.zeros(cands_per_step).pin_memory()
-
-        def step_host(i):
-            pb = host[i % n_batches]
-            eng.score_packed_host(pb, score_host)
-            return pb.bytes(), 4 * cands_per_step
-    else:
+        eng = Engine(cfg, sd, precision=args.precision, max_sequences=chunk, device=local)
         cands_per_step = SEQ_PER_IMAGE
         host = [image_batch(rank + world * i) for i in range(n_batches)]
         devb = [to_device(b, dev) for b in host]
@@ -331,63 +459,57 @@ def main_ours(args):
 
         def step_host(i):
             return run_step_host(eng, host[i % n_batches], chunk, score_host, HostArrays)
-    scratch = torch.zeros(cands_per_step, device=dev)
+        scratch = torch.zeros(cands_per_step, device=dev)
 
-    def barrier():
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        for i in range(args.warmup):
+            step_device(i, scratch)
         if world > 1:
-            dist.barrier()
+            gathered = [torch.empty_like(scores) for _ in range(world)]
+            dist.all_gather(gathered, scores)
+        barrier()
+        lib.unimm_reset_launch_count()
+        eng.profile_begin()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.mark_start()
+        ev0.record(stream)
+        for i in range(args.steps):
+            step_device(i, scores[i])
+        if world > 1:
+            dist.all_gather(gathered, scores)
+        ev1.record(stream)
+        barrier()
+        launches = int(lib.unimm_launch_count())
+        prof = eng.profile_end()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        total_cands = world * args.steps * cands_per_step
+        value = total_cands / (ms_total * 1e-3)
+        for i in range(min(args.warmup, 2)):
+            step_host(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            h2d, d2h = step_host(i)
+        e1.record(stream)
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e_value = total_cands / (float(ms2.item()) * 1e-3)
+        ref_scores = torch.zeros(cands_per_step, device=dev)
+        step_device(args.steps - 1, ref_scores)
         torch.cuda.synchronize(dev)
-
-    # ---- device-resident throughput (the clock sampler starts before the warm-up: nvidia-smi needs ~100 ms to spin up
-    # and the warm-up runs the same kernels as the timed steps)
-    sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(args.warmup):
-        step_device(i, scratch)
-    if world > 1:                                            # warm the exchange up as well (NCCL connects its all-gather channels lazily)
-        gathered = [torch.empty_like(scores) for _ in range(world)]
-        dist.all_gather(gathered, scores)
-    barrier()
-    lib.unimm_reset_launch_count()
-    eng.profile_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if sampler:
-        sampler.mark_start()
-    ev0.record(stream)
-    for i in range(args.steps):
-        step_device(i, scores[i])
-    if world > 1:                                            # the path's only exchange: gather the scores for the metrics
-        dist.all_gather(gathered, scores)
-    ev1.record(stream)
-    barrier()
-    launches = int(lib.unimm_launch_count())
-    prof = eng.profile_end()
-    clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    total_cands = world * args.steps * cands_per_step
-    value = total_cands / (ms_total * 1e-3)
-
-    # ---- end to end through the host-buffer C ABI
-    for i in range(min(args.warmup, 2)):
-        step_host(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        h2d, d2h = step_host(i)
-    e1.record(stream)
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = total_cands / (float(ms2.item()) * 1e-3)
-    # the two paths must agree (same kernels, same inputs as the last timed device step)
-    ref_scores = torch.zeros(cands_per_step, device=dev)
-    step_device(args.steps - 1, ref_scores)
-    torch.cuda.synchronize(dev)
-    assert torch.allclose(ref_scores.cpu(), score_host, atol=1e-5), "host and device paths disagree"
+        assert torch.allclose(ref_scores.cpu(), score_host, atol=1e-5), "host and device paths disagree"
 
     if rank == 0:
         pk = peaks()
@@ -411,10 +533,13 @@ def main_ours(args):
         if packed:
             cfg_d["packed_text_rows_per_step"] = packed_rows
             cfg_d["dense_text_rows_per_step"] = cands_per_step * 256
-            cfg_d["candidate_rows"] = ("CLS + A + B (NSP logits available)" if args.nsp_rows else
-                                       "scores only: the [CLS] and A_last rows, which no labelled position attends and only the NSP logit "
-                                       "(fetched but unused by val_lm.py:124-139) reads, are not packed" +
-                                       ("" if args.own_b0 else "; the first masked position B_0 (identical for the candidates of a round) once per round"))
+            cfg_d["candidate_rows"] = ("scores only: the [CLS] and A_last rows, which no labelled position attends and only the NSP logit "
+                                       "(fetched but unused by val_lm.py:124-139) reads, are not packed; the first masked position B_0 "
+                                       "(identical for the candidates of a round) once per round")
+            cfg_d["e2e_input"] = ("the reference's host layout: per image int64 [1000,256] input_ids / token_type_ids / position_ids / "
+                                  "masked_lm_labels + descriptors + one [37,2048] feature block; packed by the C++ packer inside the timed "
+                                  "region (step i+1 on a worker thread while the device runs step i); context equality verified every step: "
+                                  + str(not args.no_verify))
             cfg_d["note"] = ("prefix-shared layout: context + image rows once per round (SURVEY.md F5); roofline and % of peak count "
                              "EXECUTED FLOPs only; dense_equivalent_speedup = dense FLOPs / executed FLOPs")
         else:
@@ -437,6 +562,7 @@ def main_ours(args):
                                                          "umma_gemm_kernel<LSE> (LM head)": tf("lm_head")}},
             "clocks": clocks,
         }
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             rate, sec, cores = cpu_reference_rate(args.cpu_sample)
             line["cpu_baseline"] = {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port",
@@ -464,8 +590,15 @@ if __name__ == "__main__":
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: cuda = the eager-PyTorch-on-B200 bar (extra; the driver's arm is cpu)")
     ap.add_argument("--ref-mode", default="tf32", choices=["tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="steps", choices=["steps", "sweep"], help="sweep = the whole configs[1] sweep, strong-scaled (see the docstring)")
+    ap.add_argument("--images", type=int, default=2064, help="--workload sweep: images of the sweep")
+    ap.add_argument("--no-verify", action="store_true", help="skip the per-step context-equality check of the packer")
+    ap.add_argument("--no-bf16", action="store_true", help="fp16 runs: skip the nested bf16_mode measurement")
+    ap.add_argument("--ref-candidates", type=int, default=100, help="--impl reference: candidates per CPU step")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)
+    elif a.workload == "sweep":
+        main_sweep(a)
     else:
         main_ours(a)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UNIMM_ABI_VERSION 1
+#define UNIMM_ABI_VERSION 2
 
 typedef struct unimm_engine unimm_engine_t;
 
@@ -102,6 +102,10 @@ int unimm_load_weight(unimm_engine_t* e, const char* name, const float* h_data, 
 /* Packs (QKV concatenation, bf16 casts) and verifies that every key the forward needs was loaded. */
 int unimm_finalize_weights(unimm_engine_t* e);
 int unimm_forward(unimm_engine_t* e, const unimm_batch_t* batch, const unimm_outputs_t* out, void* stream);
+/* The reference's nn.Embedding raises on a token / position / token-type id outside its table (models/vilbert_dialog.py:334-350).
+ * The asynchronous forwards clamp such an id and set a device flag; this call synchronises `stream`, returns non-zero if any
+ * forward on it since the previous check saw one, and clears the flag.  The host-buffer entry points (unimm_score_host, unimm_score_packed_host) do this themselves. */
+int unimm_check_ids(unimm_engine_t* e, void* stream);
 
 /* ---- prefix-shared generative scoring --------------------------------------------------------------------
  * In generative mode the context rows [1,ctx) and the image rows are identical for the 100 candidates of a
@@ -152,12 +156,58 @@ typedef struct {
     const int32_t* d_lm_urows;
     const int32_t* d_lm_uidx;
     int32_t n_lm_unique;
+    /* optional: one feature / box / mask block per IMAGE instead of per unit (the 10 rounds of an image share it, val_lm.py:84-93
+     * copies it x1000): d_image_feat / d_image_loc / d_image_mask then hold n_images blocks, d_unit_image [U] names each unit's
+     * block and the mask_row field of the t2i / img_self jobs is an image index.  NULL: one block per unit (n_images ignored). */
+    const int32_t* d_unit_image;
+    int32_t n_images;
 } unimm_packed_batch_t;
 /* outputs (each optional): seq_score [C], nsp_scores [C,2], token_logp [n_lm] */
 int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, float* d_seq_score, float* d_nsp_scores,
                          float* d_token_logp, void* stream);
 /* Same with every pointer of `hb` (and the outputs) in HOST memory: H2D + forward + D2H + sync inside the call. */
 int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream);
+
+/* ---- packing on the host, from the reference's own layout -------------------------------------------------
+ * What val_lm.py:55-121 holds for one step BEFORE the dense masks exist: per image one int64 [rows, S] tensor per field
+ * (dataloader_visdial.py:437-457; rows = rounds x options) and one feature block.  A unit = (image, round) is a row
+ * range of its image's block.  unimm_packer_pack turns a step of such blocks into the prefix-shared layout above (row
+ * gathers, per-row intervals, job lists, labelled-row lists) inside the packer's own (pinned, when a CUDA device is
+ * present) host buffers; unimm_packer_batch returns the unimm_packed_batch_t whose pointers name those buffers — pass it
+ * to unimm_score_packed_host.  Host code only: threads = worker threads over units (0 = 4).  A packer is not
+ * re-entrant; two packers double-buffer a sweep (pack step i + 1 while the device scores step i).
+ * Sequences truncated at S (utils/data_utils.py:205-209, :237-244: L + last_len > S) keep the rows that exist.
+ * desc == NULL: (ctx, L, last_len) are derived from position_ids (the masked copy restarts at position ctx, :227). */
+typedef struct unimm_packer unimm_packer_t;
+typedef struct {
+    int32_t rows;                        /* sequences in this block                                     */
+    const int64_t* input_ids;            /* [rows,S]                                                     */
+    const int64_t* token_type_ids;       /* [rows,S]                                                     */
+    const int64_t* position_ids;         /* [rows,S]                                                     */
+    const int64_t* masked_lm_labels;     /* [rows,S]  -1 = ignore                                        */
+    const unimm_seq_desc_t* desc;        /* [rows] or NULL                                               */
+    const float* image_feat;             /* [R,F]                                                        */
+    const float* image_loc;              /* [R,5]                                                        */
+    const float* image_mask;             /* [R]                                                          */
+} unimm_image_block_t;
+typedef struct {
+    int32_t n_blocks;
+    const unimm_image_block_t* blocks;
+    int32_t n_units;
+    const int32_t* unit_block;           /* [U] block (image) of every unit, non-decreasing              */
+    const int32_t* unit_row0;            /* [U] first sequence of the unit inside its block              */
+    const int32_t* unit_rows;            /* [U] candidates of the unit                                   */
+    int32_t scores_only;                 /* 1: no [CLS] / trailing A rows (see no_cls_rows above)        */
+    int32_t share_first_mask;            /* 1: one B_0 row per unit when the candidates' agree           */
+    int32_t verify_shared;               /* 1: compare every candidate's context with candidate 0's      */
+} unimm_flat_batch_t;
+int unimm_packer_create(int seq_len, int num_regions, int feature_size, int pinned, unimm_packer_t** out);
+int unimm_packer_destroy(unimm_packer_t* p);
+int unimm_packer_pack(unimm_packer_t* p, const unimm_flat_batch_t* fb, int threads);
+/* the batch of the last successful unimm_packer_pack (HOST pointers, valid until the next pack / destroy) */
+int unimm_packer_batch(const unimm_packer_t* p, unimm_packed_batch_t* out);
+/* descriptors the last pack used (given or derived), in unit order: [n_cands] */
+int unimm_packer_desc(const unimm_packer_t* p, const unimm_seq_desc_t** out, int32_t* n);
 
 /* Boundary helper: check that the caller's dense masks equal what the descriptors regenerate.
  * d_txt_mask: [B,S,S] elements of txt_elem_bytes (1 = bool/uint8, 8 = int64); d_co_mask: [B,R,S] int64 or NULL.

@@ -365,6 +365,80 @@ def main():
         save("rankloss", y_pred=np.stack([c[0] for c in cases]), y_true=np.stack([c[1] for c in cases]),
              loss=np.array([c[2] for c in cases], dtype=np.float32), ens_probs=probs.numpy(), ens_out=res.numpy())
 
+
+    # ---------------------------------------------------------------- bench-shape sweep slice: 3 rounds x 100 candidates of ONE image
+    # (val_lm.py:104-137 over several rounds of an image: contexts of different lengths share one feature block).  Inputs are the
+    # bench's own synthetic generator (unimm_b200.synthetic.synth_dialog_rounds), rebuilt here with the REFERENCE encoders and
+    # required to be identical, so that the fixture pins exactly what bench.py / val_sweep.py feed the packed path.
+    for name, seed, perturbed in (("sweep3x100_default", 0, False), ("sweep3x100_perturbed", 1, True)):
+        if not want(name):
+            continue
+        from unimm_b200 import synthetic as syn
+        image_id, round_ids = 7, (1, 5, 10)
+        srng = np.random.RandomState(100003 + image_id)                      # same draw order as syn.synth_dialog_rounds
+        s_feat, s_loc, s_mask = (torch.from_numpy(a) for a in syn.synth_image(srng))
+        batches = []
+        for r in round_ids:
+            ctx_utts, ans = syn.synth_context(srng, r), syn.synth_answers(srng, 100)
+            batches.append(ref_batch(du, ctx_utts, ans, s_feat, s_loc, s_mask, du.encode_input_gen, seed=7))
+        (feat2, loc2, mask2), views = syn.synth_dialog_rounds(image_id, rounds=round_ids)
+        assert np.array_equal(feat2, s_feat.numpy()) and np.array_equal(loc2, s_loc.numpy())
+        for b, v in zip(batches, views):
+            assert np.array_equal(b["tokens"].numpy(), v.tokens) and np.array_equal(b["segments"].numpy(), v.segments)
+            assert np.array_equal(b["positions"].numpy(), v.positions) and np.array_equal(b["mask"].numpy(), v.labels)
+            from unimm_b200.descriptors import dense_co_mask, dense_text_mask
+            d = torch.from_numpy(v.desc)
+            assert torch.equal(dense_text_mask(d, 256), b["txt_attention_mask"].bool())
+            assert torch.equal(dense_co_mask(d, 256), b["co_attention_mask"][:, 0, :])
+        model = get_model(seed, perturbed)
+        scores = []
+        for b in batches:
+            for s in range(0, 100, 25):
+                bb = {k: v[s:s + 25] for k, v in b.items()}
+                _, _, _, nsp, lm = call_reference(model, bb)
+                scores.append(val_lm_scores(lm, bb["mask"])[0])
+        score = torch.cat(scores).view(len(round_ids), 100)
+        ranks = vm.scores_to_ranks(score.view(1, len(round_ids), 100).clone()).view(len(round_ids), 100)
+        save(name, weight_seed=np.array(seed), perturbed=np.array(perturbed), image_id=np.array(image_id), round_ids=np.array(round_ids),
+             tokens=np.concatenate([v.tokens for v in views]).astype(np.int32), labels=np.concatenate([v.labels for v in views]).astype(np.int32),
+             desc=np.concatenate([v.desc for v in views]), seq_score=score.numpy(), ranks=ranks.numpy())
+
+    # ---------------------------------------------------------------- sequences truncated at max_seq_len (data_utils.py:205-209, :237-244)
+    # context of 247 positions: answers of 1..3 tokens fit (T <= 256), 4..7 lose part of the masked copy, 8 loses all of it (L = 256),
+    # 10 loses part of the visible copy too (L > 256)
+    if want("gen10_truncated"):
+        trng = np.random.RandomState(4321)
+        draw = lambda n: trng.randint(1000, 30522, size=n).tolist()
+        t_context = [draw(20)] + [draw(10) for _ in range(19)] + [draw(15)]          # 1 + 21 + 20 + 190 + 15 = 247 positions
+        t_answers = [draw(n) for n in (1, 3, 4, 5, 7, 8, 10, 2, 6, 3)]
+        b = ref_batch(du, t_context, t_answers, feats, loc, image_mask, du.encode_input_gen, seed=7)
+        assert_encoders_match(b, oracle_batch(t_context, t_answers, feats, loc, image_mask, enc.encode_gen, seed=7))
+        assert int(b["txt_attention_mask"][0, 0].sum()) == 251 and int(b["txt_attention_mask"][2, 0].sum()) == 256
+        model = get_model(1, True)
+        _, _, _, nsp, lm = call_reference(model, b)
+        score, nll = val_lm_scores(lm, b["mask"])
+        rows = (b["mask"] != -1).nonzero()
+        save("gen10_truncated", weight_seed=np.array(1), perturbed=np.array(True), **pack_inputs(b), **image_np,
+             answer_lens=np.array([len(a) for a in t_answers]), seq_score=score.numpy(), nsp_scores=nsp.numpy(),
+             token_rows=rows.numpy(), token_logp=(-nll[rows[:, 0], rows[:, 1]]).numpy())
+
+    # ---------------------------------------------------------------- config 4: 100 candidates, discriminative NSP ranking (val.py:125-161)
+    if want("dis100_default"):
+        b = ref_batch(du, context, answers, feats, loc, image_mask, du.encode_input_dis, seed=13)
+        model = get_model(0, False)
+        nsps = []
+        for s in range(0, 100, 25):
+            bb = {k: v[s:s + 25] for k, v in b.items()}
+            _, _, _, nsp, lm = call_reference(model, bb)
+            nsps.append(nsp)
+        nsp = torch.cat(nsps)
+        prob0 = F.softmax(nsp, 1)[:, 0]                                   # val.py:127-131: the "is the right answer" probability
+        ranks = vm.scores_to_ranks(prob0.view(1, 1, 100).clone())
+        srt = prob0.sort(descending=True)[0]
+        print("dis100_default min adjacent gap", float((srt[:-1] - srt[1:]).min()))
+        save("dis100_default", weight_seed=np.array(0), perturbed=np.array(False), **pack_inputs(b), **image_np,
+             nsp_scores=nsp.numpy(), nsp_prob0=prob0.numpy(), ranks=ranks.view(100).numpy())
+
     # ---------------------------------------------------------------- config 1: 100 candidates, ranking metrics
     for name, seed, perturbed in (("gen100_default", 0, False),):
         if not want(name):

@@ -90,6 +90,17 @@ def test_config1_context_has_239_positions():
     assert ((r.desc[:, 2] + r.desc[:, 3]) <= 255).all()
 
 
+def test_vectorised_round_encoder_equals_the_per_candidate_statement():
+    rng = np.random.RandomState(3)
+    for r, n in ((1, 7), (10, 100), (5, 33), (2, 1)):
+        c, a = syn.synth_context(rng, r), syn.synth_answers(rng, n)
+        if n == 7:
+            a[2] = []                                        # an empty answer: only [SEP] / one [MASK]
+        x, y = syn.encode_round_gen(c, a), syn._encode_round_gen_loop(c, a)
+        for f in ("tokens", "segments", "positions", "labels", "desc"):
+            assert np.array_equal(getattr(x, f), getattr(y, f)) and getattr(x, f).dtype == getattr(y, f).dtype, (f, r, n)
+
+
 def test_library_loads_and_exports_every_declared_symbol():
     """No compute without a GPU: only that the in-tree .so loads and matches include/unimm_b200.h."""
     from unimm_b200 import _lib
@@ -99,7 +110,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.unimm_abi_version() == 1
+    assert _lib.lib.unimm_abi_version() == 2
     assert _lib.LIB_PATH.startswith(ROOT)          # in-tree, so the driver sees it loaded
 
 

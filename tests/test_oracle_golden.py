@@ -127,3 +127,45 @@ def test_rank_loss_oracle_matches_reference():
         assert abs(float(got) - float(want)) < 1e-6
     ens = orl.ensemble_normalise(z["ens_probs"].reshape(5, 40, 100)).reshape(4, 10, 100)
     np.testing.assert_allclose(ens, z["ens_out"], atol=1e-6, rtol=0)
+
+
+def test_truncated_sequences_match_reference(full_cfg):
+    """Sequences cut at max_seq_len (utils/data_utils.py:205-209, :237-244): the oracle on the reference's own truncated inputs."""
+    g, batch = load_golden("gen10_truncated")
+    out = _run(full_cfg, g, batch)
+    assert np.array_equal(out["token_rows"].numpy(), g["token_rows"])
+    np.testing.assert_allclose(out["token_logp"].numpy(), g["token_logp"], atol=TOL, rtol=0)
+    np.testing.assert_allclose(out["seq_score"].numpy(), g["seq_score"], atol=5 * TOL, rtol=0)
+    np.testing.assert_allclose(out["nsp_scores"].numpy(), g["nsp_scores"], atol=TOL, rtol=0)
+    assert g["seq_score"][5] == 0 and g["seq_score"][6] == 0          # no masked-copy position left inside 256
+
+
+def test_config4_nsp_ranking_sample_matches_reference(full_cfg):
+    """BASELINE config 4 (val.py:125-131): discriminative masks, NSP probability of 'is the answer' — a 10-candidate sample of the
+    100-candidate fixture (the whole round is the GPU test's)."""
+    g, batch = load_golden("dis100_default")
+    b = {k: v[40:50] for k, v in batch.items()}
+    out = _run(full_cfg, g, b)
+    np.testing.assert_allclose(out["nsp_scores"].numpy(), g["nsp_scores"][40:50], atol=TOL, rtol=0)
+    np.testing.assert_allclose(torch.softmax(out["nsp_scores"], 1)[:, 0].numpy(), g["nsp_prob0"][40:50], atol=TOL, rtol=0)
+
+
+def test_sweep_fixture_sample_matches_reference(full_cfg):
+    """tests/golden/sweep3x100_perturbed.npz (3 rounds x 100 candidates of the bench's own generator, scored by the reference):
+    the oracle on 4 candidates of each round, inputs regenerated by unimm_b200.synthetic."""
+    from unimm_b200 import synthetic as syn
+    from unimm_b200.descriptors import dense_co_mask, dense_text_mask
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "sweep3x100_perturbed.npz")))
+    (feat, loc, mask), rounds = syn.synth_dialog_rounds(int(g["image_id"]), rounds=tuple(int(r) for r in g["round_ids"]))
+    assert np.array_equal(np.concatenate([r.tokens for r in rounds]), g["tokens"])
+    sd = golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+    pick = [0, 33, 66, 99]
+    for ri, r in enumerate(rounds):
+        desc = torch.from_numpy(r.desc[pick])
+        n = len(pick)
+        with torch.no_grad():
+            out = vo.forward(sd, full_cfg, torch.from_numpy(r.tokens[pick]), torch.from_numpy(feat).expand(n, -1, -1),
+                             torch.from_numpy(loc).expand(n, -1, -1), torch.from_numpy(r.segments[pick]), torch.from_numpy(r.positions[pick]),
+                             dense_text_mask(desc, 256), torch.from_numpy(mask).expand(n, -1), dense_co_mask(desc, 256).unsqueeze(1).repeat(1, 37, 1),
+                             masked_lm_labels=torch.from_numpy(r.labels[pick]))
+        np.testing.assert_allclose(out["seq_score"].numpy(), g["seq_score"][ri, pick], atol=5 * TOL, rtol=0)

@@ -68,7 +68,20 @@ class PackedBatchStruct(C.Structure):
         ("d_lm_rows", C.c_void_p), ("d_lm_labels", C.c_void_p), ("n_lm_rows", C.c_int32),
         ("d_cand_lm_off", C.c_void_p), ("d_cand_cls_row", C.c_void_p), ("d_cand_img_row", C.c_void_p),
         ("pairs_text_self", C.c_double), ("pairs_i2t", C.c_double), ("n_shared_rows", C.c_int32), ("no_cls_rows", C.c_int32),
-        ("d_lm_urows", C.c_void_p), ("d_lm_uidx", C.c_void_p), ("n_lm_unique", C.c_int32)]
+        ("d_lm_urows", C.c_void_p), ("d_lm_uidx", C.c_void_p), ("n_lm_unique", C.c_int32),
+        ("d_unit_image", C.c_void_p), ("n_images", C.c_int32)]
+
+
+class ImageBlock(C.Structure):
+    """unimm_image_block_t: one image's [rows,S] int64 tensors (reference dataloader layout) and its feature block."""
+    _fields_ = [("rows", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "input_ids", "token_type_ids", "position_ids", "masked_lm_labels", "desc", "image_feat", "image_loc", "image_mask")]
+
+
+class FlatBatch(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("blocks", C.POINTER(ImageBlock)), ("n_units", C.c_int32),
+                ("unit_block", C.c_void_p), ("unit_row0", C.c_void_p), ("unit_rows", C.c_void_p),
+                ("scores_only", C.c_int32), ("share_first_mask", C.c_int32), ("verify_shared", C.c_int32)]
 
 
 # every symbol include/unimm_b200.h declares: name -> (restype, argtypes)
@@ -83,6 +96,12 @@ SYMBOLS = {
     "unimm_forward": (C.c_int, [_P, C.POINTER(Batch), C.POINTER(Outputs), _P]),
     "unimm_forward_packed": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _P, _P, _P, _P]),
     "unimm_score_packed_host": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _P, _P, _P]),
+    "unimm_check_ids": (C.c_int, [_P, _P]),
+    "unimm_packer_create": (C.c_int, [_I, _I, _I, _I, C.POINTER(C.c_void_p)]),
+    "unimm_packer_destroy": (C.c_int, [_P]),
+    "unimm_packer_pack": (C.c_int, [_P, C.POINTER(FlatBatch), _I]),
+    "unimm_packer_batch": (C.c_int, [_P, C.POINTER(PackedBatchStruct)]),
+    "unimm_packer_desc": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "unimm_verify_masks": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "unimm_score_host": (C.c_int, [_P, C.POINTER(HostBatch), _P, _P, _P]),
     "unimm_rank_metrics": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),

@@ -68,6 +68,23 @@ struct ConnLayer {  // BertConnectionLayer
     LayerNormP ln1, ln2, v_ln, t_ln;
 };
 
+// device-side staging of unimm_score_host (allocated on first use, sized for Bmax)
+struct HostPath {
+    int64_t *ids = nullptr, *types = nullptr, *pos = nullptr, *labels = nullptr;
+    unimm_seq_desc_t* desc = nullptr;
+    float *feat = nullptr, *loc = nullptr, *mask = nullptr, *score = nullptr, *nsp = nullptr;
+    int32_t *index = nullptr, *rows = nullptr;
+    int32_t* h_rows = nullptr;  // pinned
+};
+
+// device staging of unimm_score_packed_host: one int32 and one fp32 arena per engine
+struct PackedStage {
+    int32_t* i32 = nullptr;
+    size_t i32_cap = 0;
+    float* f32 = nullptr;
+    size_t f32_cap = 0;
+};
+
 // activation matrix that exists as fp32 and/or bf16
 struct ActBuf {
     float* f = nullptr;
@@ -118,7 +135,10 @@ struct unimm_engine {
     float* vhead = nullptr;         // image head scratch [Mv, Hv]
     ActBuf vhead_h;
     float* v_logits = nullptr;
-    int* err_flag = nullptr;
+    int* err_flag = nullptr;       // device: set by the embedding kernel on an out-of-range token / position / type id
+    int* h_err = nullptr;          // pinned copy, read after a stream synchronisation (check_ids)
+    HostPath host_path;            // staging of unimm_score_host / unimm_score_packed_host: per engine, so engines on different
+    PackedStage packed_stage;      // devices can be driven from different threads
     int* dense_jobs = nullptr;     // [Bmax, 8] text -> image jobs of the dense layout: (b*S, S, b*R, R, 0, b, 0, 0)
     // host staging for unimm_score_host
     void* h_stage = nullptr;
@@ -214,6 +234,17 @@ struct unimm_engine {
     // n_u unique rows (of src, or src[d_urows]) serve n (row, label) entries: entry i reads unique row d_uidx[i]
     int lm_head_shared(const ActBuf& src, const int* d_urows, int n_u, const int* d_uidx, const int* d_labels, int n, cudaStream_t st);
     int forward(const unimm_batch_t& in, const unimm_outputs_t& out, cudaStream_t st);
+    // the reference's nn.Embedding raises on an id outside its table (models/vilbert_dialog.py:334-350); the embedding kernel clamps
+    // and raises err_flag instead: queue its copy behind the forward, and after the caller's synchronisation turn it into an error
+    int queue_id_check(cudaStream_t st) {
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_err, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        UNIMM_CUDA_CHECK(cudaMemsetAsync(err_flag, 0, sizeof(int), st));      // sticky between checks, cleared by each one
+        return 0;
+    }
+    int id_check_result() {
+        UNIMM_CHECK(h_err[0] == 0, "token, position or token-type id outside its embedding table (the reference raises an IndexError here)");
+        return 0;
+    }
     int forward_packed(const unimm_packed_batch_t& in, float* d_seq_score, float* d_nsp_scores, float* d_token_logp, cudaStream_t st);
 };
 
@@ -342,7 +373,7 @@ int unimm_engine::finalize() {
 
     UNIMM_TRY(make_linear({"cls.predictions.transform.dense"}, H, H, &lm_transform));
     UNIMM_TRY(make_ln("cls.predictions.transform.LayerNorm", H, &lm_ln));
-    // tied decoder (reference :1020): accept either key, insist they agree when both are present
+    // tied decoder (reference :1020): accept either key, insist they agree when both are present (compared below)
     {
         lm_decoder.N = c.vocab_size;
         lm_decoder.K = H;
@@ -350,7 +381,13 @@ int unimm_engine::finalize() {
         auto it = raw.find("cls.predictions.decoder.weight");
         if (it != raw.end()) {
             UNIMM_CHECK(it->second.numel == static_cast<size_t>(c.vocab_size) * H, "bad decoder weight shape");
-            lm_decoder.w32 = it->second.p;  // identical to word_emb in every reference checkpoint
+            // the reference ties the two (one Parameter, :1020): a checkpoint in which they differ is not a reference checkpoint
+            int* d_diff = nullptr;
+            UNIMM_TRY(dalloc(&d_diff, 4));
+            UNIMM_TRY(buffers_differ(it->second.p, word_emb, it->second.numel, d_diff, 0));
+            int h_diff = 0;
+            UNIMM_CUDA_CHECK(cudaMemcpy(&h_diff, d_diff, sizeof(int), cudaMemcpyDeviceToHost));
+            UNIMM_CHECK(h_diff == 0, "cls.predictions.decoder.weight differs from bert.embeddings.word_embeddings.weight (the reference ties them)");
         }
         UNIMM_TRY(get("cls.predictions.bias", &t, {c.vocab_size}));
         lm_decoder.b = t->p;
@@ -416,6 +453,8 @@ int unimm_engine::alloc_workspace() {
     if (lp()) UNIMM_TRY(dalloc(&vhead_h.h, Mv * Hv));
     UNIMM_TRY(dalloc(&v_logits, Mv * c.v_target_size));
     UNIMM_TRY(dalloc(&err_flag, 4));
+    UNIMM_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_err), 4 * sizeof(int)));
+    h_err[0] = 0;
     {
         std::vector<int> jobs(static_cast<size_t>(Bmax) * 8, 0);
         for (int b = 0; b < Bmax; ++b) {
@@ -866,12 +905,16 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
     UNIMM_CHECK(in.n_lm_rows >= 0 && in.n_lm_rows <= M, "n_lm_rows out of range");
     UNIMM_CHECK(!(d_nsp_scores && in.no_cls_rows), "NSP scores requested from a batch packed without [CLS] rows (scores_only)");
     const int Mv = U * R;
+    // the job kernels stage the image keys of a unit in a 64-row buffer
+    UNIMM_CHECK(R <= 64, "the prefix-shared layout supports at most 64 image regions per unit");
+    UNIMM_CHECK(in.win_cap >= 128 + 2 * in.cand_halo, "win_cap too small for the longest candidate (needs 128 + 2 * cand_halo)");
     UNIMM_TRY(embed_text_ln_i32(in.d_input_ids, in.d_token_type_ids, in.d_position_ids, M, H, c.vocab_size, c.max_position_embeddings,
                                 c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h, lp_kind(),
                                 err_flag, st));
-    UNIMM_TRY(gather_features(in.d_image_feat, nullptr, U, R, c.v_feature_size, lp() ? nullptr : static_cast<float*>(feat_a),
+    UNIMM_CHECK(in.d_unit_image == nullptr || in.n_images > 0, "d_unit_image given without n_images");
+    UNIMM_TRY(gather_features(in.d_image_feat, in.d_unit_image, U, R, c.v_feature_size, lp() ? nullptr : static_cast<float*>(feat_a),
                               lp() ? static_cast<bf16*>(feat_a) : nullptr, lp_kind(), st));
-    UNIMM_TRY(image_loc_embed(in.d_image_loc, nullptr, U, R, Hv, loc_w, loc_b, pre_v, st));
+    UNIMM_TRY(image_loc_embed(in.d_image_loc, in.d_unit_image, U, R, Hv, loc_w, loc_b, pre_v, st));
     {
         ActBuf fa;
         fa.f = lp() ? nullptr : static_cast<float*>(feat_a); fa.h = lp() ? static_cast<bf16*>(feat_a) : nullptr; fa.ld = c.v_feature_size;
@@ -914,24 +957,6 @@ struct DeviceGuard {
     }
 };
 
-// device-side staging of unimm_score_host (allocated on first use, sized for Bmax)
-struct HostPath {
-    int64_t *ids = nullptr, *types = nullptr, *pos = nullptr, *labels = nullptr;
-    unimm_seq_desc_t* desc = nullptr;
-    float *feat = nullptr, *loc = nullptr, *mask = nullptr, *score = nullptr, *nsp = nullptr;
-    int32_t *index = nullptr, *rows = nullptr;
-    int32_t* h_rows = nullptr;  // pinned
-};
-std::map<unimm_engine*, HostPath> g_host_paths;
-
-// device staging of unimm_score_packed_host: one int32 and one fp32 arena per engine
-struct PackedStage {
-    int32_t* i32 = nullptr;
-    size_t i32_cap = 0;
-    float* f32 = nullptr;
-    size_t f32_cap = 0;
-};
-std::map<unimm_engine*, PackedStage> g_packed_stage;
 }  // namespace
 
 extern "C" {
@@ -985,12 +1010,8 @@ int unimm_destroy(unimm_engine_t* e) {
     if (e == nullptr) return 0;
     DeviceGuard g(e->device);
     cudaDeviceSynchronize();
-    g_packed_stage.erase(e);
-    auto it = g_host_paths.find(e);
-    if (it != g_host_paths.end()) {
-        if (it->second.h_rows) cudaFreeHost(it->second.h_rows);
-        g_host_paths.erase(it);
-    }
+    if (e->host_path.h_rows) cudaFreeHost(e->host_path.h_rows);
+    if (e->h_err) cudaFreeHost(e->h_err);
     for (void* p : e->owned) cudaFree(p);
     delete e;
     return 0;
@@ -1045,15 +1066,21 @@ int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, f
                     C <= e->Bmax * c.seq_len, "packed batch exceeds the engine workspace");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PackedStage& ps = g_packed_stage[e];
+    PackedStage& ps = e->packed_stage;
     if (ps.i32 == nullptr) {
         const size_t rows = static_cast<size_t>(e->Bmax) * c.seq_len;
         // ids, types, pos (3M) + row_iv (4M) + lm rows/labels/unique rows/indices (4M) + cand arrays (3C+1 <= 3M+1) + jobs (6U*8)
-        ps.i32_cap = rows * 14 + static_cast<size_t>(e->Bmax) * 48 + 64;
+        ps.i32_cap = rows * 14 + static_cast<size_t>(e->Bmax) * 52 + 64;
         UNIMM_TRY(e->dalloc(&ps.i32, ps.i32_cap));
         ps.f32_cap = static_cast<size_t>(e->Bmax) * R * (F + 6) + rows * 3 + 64;
         UNIMM_TRY(e->dalloc(&ps.f32, ps.f32_cap));
     }
+    // the staged key ranges must fit the capacities the kernels were sized with (the arrays are host memory here: check them)
+    for (int j = 0; j < hb->n_jobs_text_self; ++j)
+        UNIMM_CHECK(hb->d_jobs_text_self[8 * j + 3] <= hb->kv_cap_text, "a text job's key range exceeds kv_cap_text");
+    for (int j = 0; j < hb->n_jobs_i2t; ++j)
+        UNIMM_CHECK(hb->d_jobs_i2t[8 * j + 3] <= hb->kv_cap_text, "an image->text job's key range exceeds kv_cap_text");
+    for (int j = 0; j < hb->n_jobs_t2i; ++j) UNIMM_CHECK(hb->d_jobs_t2i[8 * j + 3] <= 64, "a text->image job has more than 64 keys");
     // carve the device staging buffers and copy each host array behind the previous one
     unimm_packed_batch_t d = *hb;
     size_t io = 0, fo = 0;
@@ -1088,17 +1115,21 @@ int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, f
     UNIMM_TRY(put_i(hb->d_cand_img_row, C, &d.d_cand_img_row));
     UNIMM_TRY(put_i(hb->d_lm_urows, hb->n_lm_unique, &d.d_lm_urows));
     UNIMM_TRY(put_i(hb->d_lm_uidx, hb->d_lm_urows != nullptr && hb->n_lm_unique > 0 ? hb->n_lm_rows : 0, &d.d_lm_uidx));
-    UNIMM_TRY(put_f(hb->d_image_feat, static_cast<size_t>(U) * R * F, &d.d_image_feat));
-    UNIMM_TRY(put_f(hb->d_image_loc, static_cast<size_t>(U) * R * 5, &d.d_image_loc));
-    UNIMM_TRY(put_f(hb->d_image_mask, static_cast<size_t>(U) * R, &d.d_image_mask));
+    const int NI = hb->d_unit_image != nullptr ? hb->n_images : U;      // feature blocks: one per image, or one per unit
+    UNIMM_CHECK(NI > 0 && NI <= U, "n_images out of range");
+    UNIMM_TRY(put_i(hb->d_unit_image, hb->d_unit_image != nullptr ? U : 0, &d.d_unit_image));
+    UNIMM_TRY(put_f(hb->d_image_feat, static_cast<size_t>(NI) * R * F, &d.d_image_feat));
+    UNIMM_TRY(put_f(hb->d_image_loc, static_cast<size_t>(NI) * R * 5, &d.d_image_loc));
+    UNIMM_TRY(put_f(hb->d_image_mask, static_cast<size_t>(NI) * R, &d.d_image_mask));
     float* d_score = ps.f32 + fo;
     float* d_nsp = d_score + ((C + 3) & ~3);
     UNIMM_CHECK(fo + static_cast<size_t>(C) * 3 + 8 <= ps.f32_cap, "packed host batch larger than the staging buffer");
     UNIMM_TRY(e->forward_packed(d, d_score, h_nsp_scores ? d_nsp : nullptr, nullptr, st));
     UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_seq_score, d_score, sizeof(float) * C, cudaMemcpyDeviceToHost, st));
     if (h_nsp_scores) UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_nsp_scores, d_nsp, sizeof(float) * 2 * C, cudaMemcpyDeviceToHost, st));
+    UNIMM_TRY(e->queue_id_check(st));
     UNIMM_CUDA_CHECK(cudaStreamSynchronize(st));
-    return 0;
+    return e->id_check_result();
 }
 
 int unimm_verify_masks(const unimm_seq_desc_t* d_desc, int B, int S, int R, const void* d_txt_mask, int txt_elem_bytes,
@@ -1117,7 +1148,7 @@ int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_s
     UNIMM_CHECK(hb->h_feat_index != nullptr || U == B, "feat_index required when U != B");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    HostPath& hp = g_host_paths[e];
+    HostPath& hp = e->host_path;
     if (hp.ids == nullptr) {
         const size_t n = static_cast<size_t>(e->Bmax);
         UNIMM_TRY(e->dalloc(&hp.ids, n * S)); UNIMM_TRY(e->dalloc(&hp.types, n * S)); UNIMM_TRY(e->dalloc(&hp.pos, n * S));
@@ -1164,8 +1195,18 @@ int unimm_score_host(unimm_engine_t* e, const unimm_host_batch_t* hb, float* h_s
     UNIMM_TRY(e->forward(in, out, st));
     UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_seq_score, hp.score, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
     if (h_nsp_scores) UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_nsp_scores, hp.nsp, sizeof(float) * 2 * B, cudaMemcpyDeviceToHost, st));
+    UNIMM_TRY(e->queue_id_check(st));
     UNIMM_CUDA_CHECK(cudaStreamSynchronize(st));
-    return 0;
+    return e->id_check_result();
+}
+
+int unimm_check_ids(unimm_engine_t* e, void* stream) {
+    UNIMM_CHECK(e != nullptr && e->finalized, "null or unfinalized engine");
+    DeviceGuard g(e->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    UNIMM_TRY(e->queue_id_check(st));
+    UNIMM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return e->id_check_result();
 }
 
 int unimm_rank_metrics(const float* d_scores, int rows, int n_opt, const int32_t* d_gt_index, const float* d_relevance,

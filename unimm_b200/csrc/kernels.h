@@ -87,6 +87,8 @@ int gather_features(const float* feat, const int* feat_index, int B, int R, int 
 int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int n, int H, float* dst_f32, bf16* dst_bf16,
                 cudaStream_t stream);
 int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream);
+// *d_flag = 1 iff the two fp32 buffers differ in any bit
+int buffers_differ(const float* a, const float* b, size_t n, int* d_flag, cudaStream_t stream);
 int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStream_t stream);
 int gather_labels(const int64_t* labels, const int* rows, int n, int* out, cudaStream_t stream);
 int expand_key_mask(const float* mask, const int* index, int B, int R, float* out, cudaStream_t stream);

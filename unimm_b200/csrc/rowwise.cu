@@ -276,6 +276,19 @@ int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStrea
     return 0;
 }
 
+__global__ void differ_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, int* flag) {
+    bool d = false;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        d |= __float_as_uint(a[i]) != __float_as_uint(b[i]);
+    if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+int buffers_differ(const float* a, const float* b, size_t n, int* d_flag, cudaStream_t stream) {
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+    differ_kernel<<<148 * 8, 256, 0, stream>>>(a, b, n, d_flag);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
 int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream) {
     UNIMM_CHECK((n & 3) == 0, "cast: element count must be a multiple of 4");
     const size_t n4 = n / 4;

@@ -46,13 +46,20 @@ def descriptors_from_masks(attention_mask: torch.Tensor, co_attention_mask: torc
         raise ValueError("expected attention_mask [B,S,S] and co_attention_mask [B,R,S]")
     B, S, _ = attention_mask.shape
     co = co_attention_mask[:, 0, :].long()
-    row0 = attention_mask[:, 0, :].long().sum(-1)
     is_dis = co[:, 0] == 1
     ctx = co.sum(-1) + 1
-    L_gen = (row0 + ctx) // 2
-    last_gen = (row0 - ctx) // 2
-    zero = torch.zeros_like(row0)
-    desc = torch.stack([is_dis.long(), torch.where(is_dis, zero, ctx), torch.where(is_dis, row0, L_gen),
+    # generative rows (utils/data_utils.py:199-209): a visible-copy row i in [ctx, L) allows columns [1, i] — i of them — and the
+    # first masked-copy row L allows [1, ctx) and itself — ctx of them.  So L is the first row >= ctx whose allowed-column count
+    # is not its own index; this also holds for sequences truncated at S (L + last_len > S, :205-209), where row 0 no longer
+    # tells T.  No such row: the visible copy itself runs into S (L >= S): L = S describes the same mask.
+    rs = attention_mask.long().sum(-1)                                   # [B,S] allowed columns per row
+    r = torch.arange(S, device=rs.device).view(1, S)
+    brk = (r >= ctx.view(-1, 1)) & (rs != r)
+    L_gen = torch.where(brk.any(-1), brk.float().argmax(-1), torch.full_like(ctx, S))
+    last_gen = L_gen - ctx
+    L_dis = rs[:, 0]
+    zero = torch.zeros_like(ctx)
+    desc = torch.stack([is_dis.long(), torch.where(is_dis, zero, ctx), torch.where(is_dis, L_dis, L_gen),
                         torch.where(is_dis, zero, last_gen)], dim=1).to(torch.int32)
     if verify:
         ok = torch.equal(dense_text_mask(desc, S), attention_mask.bool()) and \
@@ -60,6 +67,6 @@ def descriptors_from_masks(attention_mask: torch.Tensor, co_attention_mask: torc
         if not ok:
             raise NotImplementedError(
                 "attention_mask / co_attention_mask are not of the form produced by the reference's "
-                "encode_input_gen / encode_input_dis (possibly a sequence truncated at max_seq_len); "
+                "encode_input_gen / encode_input_dis (truncation at max_seq_len included); "
                 "the descriptor-driven kernels do not implement arbitrary dense masks")
     return desc

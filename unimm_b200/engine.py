@@ -154,6 +154,12 @@ class Engine:
         out["_keepalive"] = keep
         return out
 
+    def check_ids(self) -> None:
+        """Synchronise the current stream and raise if the last forward met a token / position / token-type id outside its
+        embedding table (the reference's nn.Embedding raises an IndexError there; the kernels clamp and flag)."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib.unimm_check_ids(self._h, C.c_void_p(stream)))
+
     # ------------------------------------------------------------------------------------------ prefix-shared path
     def forward_packed(self, pb, want=("seq_score", "nsp_scores")) -> Dict[str, torch.Tensor]:
         """Prefix-shared generative scoring of a ``packing.PackedBatch`` whose tensors are on this device."""

@@ -8,8 +8,10 @@ answers of one dialog round they are bit-identical.  A *unit* = (
     candidate rows   [CLS] (position 0), the visible answer copy A (positions ctx .. L-1) and the masked copy B
                      (positions L .. T-1)                      (once per candidate: 1 + 2*last_len rows)
 
-Text rows of a forward are packed as ``[all units' shared rows | all candidates' rows]``.  This module turns the
-reference-format per-sequence arrays (tokens / segments / positions / labels ``[n,256]`` + descriptors, i.e. what
+Text rows of a forward are packed as ``[all units' shared rows | all candidates' rows]``.  This module is the readable
+SPECIFICATION of that layout (vectorised numpy); the sweep and the bench pack through ``unimm_b200.flat_packer`` (threaded C++ in
+``csrc/packer.cu``, same arrays row for row — ``tests/test_packer_cpu.py`` — plus truncated sequences and one feature block per
+image).  It turns the reference-format per-sequence arrays (tokens / segments / positions / labels ``[n,256]`` + descriptors, i.e. what
 ``encode_input_gen`` produces and ``unimm_b200.synthetic`` generates) into that layout plus the attention job
 lists and per-row intervals ``libunimm_b200`` consumes (include/unimm_b200.h: ``unimm_packed_batch_t``).
 
@@ -66,7 +68,10 @@ class PackedBatch:
         self.__dict__.update(kw)
 
     def tensors(self):
-        return {k: getattr(self, k) for k in self.INT_FIELDS + self.FLOAT_FIELDS}
+        d = {k: getattr(self, k) for k in self.INT_FIELDS + self.FLOAT_FIELDS}
+        if getattr(self, "unit_image", None) is not None:       # one feature block per IMAGE (flat_packer): unit -> block
+            d["unit_image"] = self.unit_image
+        return d
 
     def pin(self) -> "PackedBatch":
         for k, t in self.tensors().items():
@@ -86,8 +91,8 @@ class PackedBatch:
         from ._lib import PackedBatchStruct
         s = PackedBatchStruct()
         s.n_units, s.n_cands, s.n_text_rows = self.n_units, self.n_cands, self.n_text_rows
-        for k in self.INT_FIELDS + self.FLOAT_FIELDS:
-            setattr(s, "d_" + k, C.c_void_p(getattr(self, k).data_ptr()))
+        for k, t in self.tensors().items():
+            setattr(s, "d_" + k, C.c_void_p(t.data_ptr()))
         s.n_jobs_text_self, s.max_q_text_self = self.jobs_text_self.shape[0], self.max_q_text_self
         s.n_jobs_text_ctx, s.cand_halo = self.n_jobs_text_ctx, self.cand_halo
         s.n_jobs_t2i, s.max_q_t2i = self.jobs_t2i.shape[0], self.max_q_t2i
@@ -98,6 +103,10 @@ class PackedBatch:
         s.n_shared_rows = int(getattr(self, "n_shared_rows", 0))
         s.no_cls_rows = int(bool(getattr(self, "scores_only", False)))
         s.n_lm_unique = self.lm_urows.shape[0] if self.lm_urows.shape[0] < self.lm_rows.shape[0] else 0
+        if getattr(self, "unit_image", None) is None:
+            s.d_unit_image, s.n_images = None, 0      # this (specification) packer stores one feature block per unit
+        else:
+            s.n_images = int(self.image_feat.shape[0])
         return s
 
 

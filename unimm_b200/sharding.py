@@ -20,11 +20,13 @@ def shard_units(n_units: int, rank: int, world: int) -> List[int]:
 
 
 def gather_scores(local_scores: torch.Tensor, n_units: int, rank: Optional[int] = None, world: Optional[int] = None,
-                  group=None) -> torch.Tensor:
+                  group=None, device=None) -> torch.Tensor:
     """All-gather per-unit score rows into the global ``[n_units, n_options]`` tensor (every rank gets it).
 
     ``local_scores[i]`` belongs to unit ``shard_units(n_units, rank, world)[i]``.  Ranks may own different numbers of
-    units; rows are padded to the maximum count for the collective and dropped afterwards.
+    units; rows are padded to the maximum count for the collective and dropped afterwards.  ``device``: run the collective on
+    that device (NCCL over NVLink: one ncclAllGather of ``[ceil(n/world), n_options]`` per rank) and return a tensor there;
+    None: on the tensor's own device (gloo for the CPU tests).
     """
     if world is None:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -34,15 +36,15 @@ def gather_scores(local_scores: torch.Tensor, n_units: int, rank: Optional[int] 
     if local_scores.shape[0] != len(mine):
         raise ValueError(f"rank {rank} owns {len(mine)} units but passed {local_scores.shape[0]} score rows")
     n_opt = local_scores.shape[1]
+    if device is not None:
+        local_scores = local_scores.to(device, non_blocking=True)
     if world == 1:
         return local_scores.clone()
     per_rank = (n_units + world - 1) // world
     padded = local_scores.new_zeros(per_rank, n_opt)
     padded[: len(mine)] = local_scores
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
-    full = local_scores.new_zeros(n_units, n_opt)
-    for r, part in enumerate(parts):
-        ids = shard_units(n_units, r, world)
-        full[ids] = part[: len(ids)]
-    return full
+    out = local_scores.new_empty(world * per_rank, n_opt)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    # unit u lives at row (u mod world) * per_rank + u // world of the gathered tensor
+    u = torch.arange(n_units, device=out.device)
+    return out[(u % world) * per_rank + u // world]

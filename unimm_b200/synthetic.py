@@ -35,6 +35,44 @@ class Round:
 
 def encode_round_gen(context: Sequence[Sequence[int]], answers: Sequence[Sequence[int]], start_segment: int = 1,
                      S: int = S_MAX) -> Round:
+    """All candidates of a round at once (index arithmetic over [n, S]); ``_encode_round_gen_loop`` is the per-candidate
+    statement of the same layout and tests/test_host_cpu.py requires the two to agree."""
+    n = len(answers)
+    ctx_tok, ctx_seg = [CLS], [start_segment]
+    seg = start_segment
+    for u in context:
+        ctx_tok += list(u) + [SEP]
+        ctx_seg += [seg] * (len(u) + 1)
+        seg ^= 1
+    ctx = len(ctx_tok)
+    last = np.asarray([len(a) + 1 for a in answers], np.int64)
+    if n and ctx + 2 * int(last.max()) > S:
+        raise ValueError("synthetic sequence exceeds max_seq_len; shorten the dialog")
+    mx = int(last.max()) if n else 1
+    ans = np.full((n, mx), SEP, np.int64)                 # answer tokens followed by [SEP]
+    for j, a in enumerate(answers):
+        ans[j, :len(a)] = a
+    col = np.arange(S)[None, :]
+    L, T = (ctx + last)[:, None], (ctx + 2 * last)[:, None]
+    in_a, in_b = (col >= ctx) & (col < L), (col >= L) & (col < T)
+    k_a = np.clip(col - ctx, 0, mx - 1)
+    k_b = np.clip(col - L, 0, mx - 1)
+    rows = np.arange(n)[:, None]
+    tokens = np.zeros((n, S), np.int64)
+    tokens[:, :ctx] = ctx_tok
+    tokens = np.where(in_a, ans[rows, k_a], np.where(in_b, MASK, tokens))
+    segments = np.zeros((n, S), np.int64)
+    segments[:, :ctx] = ctx_seg
+    segments = np.where(in_a | in_b, seg, segments)
+    positions = np.where(col < L, col, np.where(in_b, col - last[:, None], 0)) + np.zeros((n, 1), np.int64)
+    labels = np.where(in_b, ans[rows, k_b], -1)
+    desc = np.stack([np.zeros(n, np.int64), np.full(n, ctx), ctx + last, last], 1).astype(np.int32)
+    return Round(np.ascontiguousarray(tokens), np.ascontiguousarray(segments), np.ascontiguousarray(positions.astype(np.int64)),
+                 np.ascontiguousarray(labels.astype(np.int64)), desc)
+
+
+def _encode_round_gen_loop(context: Sequence[Sequence[int]], answers: Sequence[Sequence[int]], start_segment: int = 1,
+                           S: int = S_MAX) -> Round:
     n = len(answers)
     tokens = np.zeros((n, S), np.int64)
     segments = np.zeros((n, S), np.int64)

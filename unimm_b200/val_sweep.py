@@ -16,8 +16,9 @@ What differs from the reference loop — by design, not in results:
 
 ``scorer(step_items) -> float32 [len(step_items), rounds, options]`` is the only device-touching piece, so the
 sharding / gathering / bookkeeping is tested on CPU with a stand-in scorer (tests/test_val_sweep_cpu.py).  A scorer that also
-has ``prepare(step_items)`` / ``score(prepared, step_items)`` (``PackedScorer``) is pipelined: the next step is packed and
-pinned on a worker thread while the device scores the current one.
+has ``prepare(step_items)`` / ``score(prepared, step_items)`` (``PackedScorer``) is pipelined: the next step is packed into
+pinned staging (C++ packer, ``csrc/packer.cu``, straight from the per-image int64 tensors the reference's loader yields) on a
+worker thread while the device scores the current one.
 """
 from __future__ import annotations
 
@@ -43,53 +44,75 @@ class DialogItem:
     gt_index: np.ndarray        # [n_rounds] ground-truth option of every round (dataloader_visdial.py:337-342)
     relevance_round: int = -1   # 0-based round that carries dense annotations (-1: none)
     relevance: Optional[np.ndarray] = None   # [n_options]
+    arrays: object = None       # flat_packer.ImageArrays over the rounds' arrays (the loader's per-image tensors); built on demand
+
+    def image_arrays(self):
+        if self.arrays is None:
+            from .flat_packer import ImageArrays
+            self.arrays = ImageArrays.from_rounds(self.rounds, self.feat, self.loc, self.mask)
+        return self.arrays
 
 
-def synthetic_items(image_ids: Sequence[int], n_candidates: int = 100) -> List[DialogItem]:
-    """The synthetic VisDial-shaped sweep of BASELINE.json configs[1] (seed = image id; gt option 0 as the reference's loader)."""
+def synthetic_items(image_ids: Sequence[int], n_candidates: int = 100, only: Optional[Sequence[int]] = None, n_rounds: int = 10) -> List[DialogItem]:
+    """The synthetic VisDial-shaped sweep of BASELINE.json configs[1] (seed = image id; gt option 0 as the reference's loader).
+
+    ``only``: positions (into ``image_ids``) whose dialogs are actually generated — a rank passes its own shard; the other items
+    carry just the ids / ground truth / relevance that the metrics need on every rank (``rounds`` is None there)."""
     from . import synthetic as syn
     out = []
-    for i in image_ids:
-        (feat, loc, mask), rounds = syn.synth_dialog_rounds(int(i), n_candidates=n_candidates)
+    only = None if only is None else set(int(x) for x in only)
+    for k, i in enumerate(image_ids):
         rng = np.random.RandomState(900001 + int(i))
         rel = rng.choice([0, 0, 0, 0.2, 0.4, 0.6, 0.8, 1.0], size=n_candidates).astype(np.float32)
         rel[0] = 1.0
-        out.append(DialogItem(int(i), feat, loc, mask, rounds, np.zeros(len(rounds), np.int64), int(rng.randint(len(rounds))), rel))
+        rel_round = int(rng.randint(n_rounds))
+        if only is not None and k not in only:
+            out.append(DialogItem(int(i), None, None, None, None, np.zeros(n_rounds, np.int64), rel_round, rel))
+            continue
+        (feat, loc, mask), rounds = syn.synth_dialog_rounds(int(i), rounds=tuple(range(1, n_rounds + 1)), n_candidates=n_candidates)
+        it = DialogItem(int(i), feat, loc, mask, rounds, np.zeros(len(rounds), np.int64), rel_round, rel)
+        it.image_arrays()
+        out.append(it)
     return out
 
 
 class PackedScorer:
     """Scores a step with ONE prefix-shared forward through the host-buffer C ABI (unimm_score_packed_host), in two phases so
-    that ``run_sweep`` can overlap them: ``prepare`` (host only: pack + pin, ~20-30 ms for 8 images) runs on a worker thread for
-    step i + 1 while ``score`` (H2D + forward + D2H, one blocking C call that releases the GIL) runs step i.
+    that ``run_sweep`` can overlap them: ``prepare`` (host only: the C++ packer fills a pinned staging buffer from the items'
+    per-image int64 arrays, a few ms for 8 images) runs on a worker thread for step i + 1 while ``score`` (H2D + forward + D2H, one
+    blocking C call that releases the GIL) runs step i.  ``depth`` + 1 packers rotate, so a prepared batch stays intact until it
+    has been scored.
 
-    The packer's context-equality check is made on the first ``verify_steps`` steps of a scorer's life only: it catches a loader
-    whose candidates do not share their context, and costs a third of the packing time."""
+    Every step is checked for the precondition of the layout — the candidates of a round share their context token for token —
+    unless ``verify_shared=False`` (the check is a threaded memcmp inside the packer, ~2 ms per step)."""
 
-    def __init__(self, engine, verify_steps: int = 1):
+    def __init__(self, engine, verify_shared: bool = True, depth: int = 1, seq_len: int = 256, num_regions: int = 37,
+                 feature_size: int = 2048, threads: int = 2):
+        from .flat_packer import FlatPacker
         self.engine = engine
-        self.verify_steps = verify_steps
-        self._prepared = 0
+        self.verify_shared = verify_shared
+        pinned = engine is not None
+        if engine is not None:
+            seq_len, num_regions, feature_size = engine.seq_len, engine.num_regions, engine.cfg.v_feature_size
+            torch.cuda.set_device(engine.device)                 # pinned allocations belong to this rank's context
+        self._packers = [FlatPacker(seq_len, num_regions, feature_size, pinned=pinned, threads=threads) for _ in range(depth + 1)]
+        self._next = 0
         self._lock = threading.Lock()
+        self._out = None
 
     def prepare(self, items: List[DialogItem]):
-        from .packing import pack_units, units_from_rounds
         if self.engine is not None and self.engine.device.type == "cuda":
             torch.cuda.set_device(self.engine.device)           # worker threads start on device 0: pin under this rank's context
-        rounds, slots = [], []
-        for s, it in enumerate(items):
-            rounds += list(it.rounds)
-            slots += [s] * len(it.rounds)
         with self._lock:
-            verify = self._prepared < self.verify_steps
-            self._prepared += 1
+            pk = self._packers[self._next % len(self._packers)]
+            self._next += 1
         # the ranking reads the LM scores only (val_lm.py:124-139): scores-only layout
-        pb = pack_units(units_from_rounds(rounds, slots), np.stack([it.feat for it in items]), np.stack([it.loc for it in items]),
-                        np.stack([it.mask for it in items]), scores_only=True, verify_shared=verify)
-        return pb.pin() if torch.cuda.is_available() else pb
+        return pk.pack([it.image_arrays() for it in items], scores_only=True, share_first_mask=True, verify_shared=self.verify_shared)
 
     def score(self, pb, items: List[DialogItem]) -> torch.Tensor:
-        out = torch.empty(pb.n_cands, dtype=torch.float32).pin_memory()
+        if self._out is None or self._out.numel() < pb.n_cands:
+            self._out = torch.empty(pb.n_cands, dtype=torch.float32).pin_memory()
+        out = self._out[:pb.n_cands]
         self.engine.score_packed_host(pb, out)
         return out.view(len(items), len(items[0].rounds), -1).clone()
 
@@ -97,8 +120,8 @@ class PackedScorer:
         return self.score(self.prepare(items), items)
 
 
-def packed_scorer(engine) -> PackedScorer:
-    return PackedScorer(engine)
+def packed_scorer(engine, **kw) -> PackedScorer:
+    return PackedScorer(engine, **kw)
 
 
 def gpu_metrics(scores: torch.Tensor, gt_index: torch.Tensor, ndcg_scores: Optional[torch.Tensor], relevance: Optional[torch.Tensor],
@@ -113,7 +136,8 @@ def gpu_metrics(scores: torch.Tensor, gt_index: torch.Tensor, ndcg_scores: Optio
 
 
 def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1, images_per_step: int = 8,
-              metrics_fn: Optional[Callable] = None, group=None, prefetch: int = 1) -> Dict[str, object]:
+              metrics_fn: Optional[Callable] = None, group=None, prefetch: int = 1, gather_device=None,
+              timing: Optional[dict] = None) -> Dict[str, object]:
     """Score this rank's images, all-gather the scores, rank them and assemble metrics + EvalAI records (on every rank).
 
     ``items`` is the GLOBAL list (every rank passes the same one; only its own shard is scored).
@@ -122,8 +146,10 @@ def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1
     """
     n = len(items)
     mine = shard_units(n, rank, world)
-    n_rounds = len(items[0].rounds)
+    n_rounds = len(items[0].gt_index)
     local = []
+    import time
+    t_start = time.perf_counter()
     steps = [[items[i] for i in mine[s:s + images_per_step]] for s in range(0, len(mine), images_per_step)]
 
     def keep(out, step):
@@ -146,18 +172,25 @@ def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1
     else:
         for step in steps:
             keep(scorer(step), step)
-    n_opt = local[0].shape[-1] if local else len(items[0].rounds[0].tokens)
+    n_opt = local[0].shape[-1] if local else len(items[0].relevance)
     local_t = torch.cat(local).reshape(len(mine), n_rounds * n_opt) if local else torch.zeros(0, n_rounds * n_opt)
-    scores = gather_scores(local_t, n, rank, world, group).view(n, n_rounds, n_opt)       # the path's only exchange
+    t_scored = time.perf_counter()
+    # the path's only exchange: with ``gather_device`` the local scores go up once and travel over NCCL / NVLink
+    scores = gather_scores(local_t, n, rank, world, group, device=gather_device).view(n, n_rounds, n_opt)
+    t_gathered = time.perf_counter()
     gt = torch.from_numpy(np.stack([it.gt_index for it in items])).long()
     ann = [i for i, it in enumerate(items) if it.relevance is not None and it.relevance_round >= 0]
-    ndcg_scores = torch.stack([scores[i, items[i].relevance_round] for i in ann]) if ann else None
+    ndcg_scores = scores[torch.tensor(ann), torch.tensor([items[i].relevance_round for i in ann])] if ann else None
     rel = torch.from_numpy(np.stack([items[i].relevance for i in ann])).float() if ann else None
     m = dict(metrics_fn(scores, gt, ndcg_scores, rel))
     ranks = m.pop("ranks")
-    records = [{"image_id": int(items[i].image_id), "round_id": j + 1, "ranks": [int(r) for r in ranks[i, j].tolist()]}
-               for i in range(n) for j in range(n_rounds)]
-    return {"scores": scores, "metrics": m, "predictions": records}
+    t_metrics = time.perf_counter()
+    ranks_l = ranks.tolist()
+    records = [{"image_id": int(items[i].image_id), "round_id": j + 1, "ranks": ranks_l[i][j]} for i in range(n) for j in range(n_rounds)]
+    if timing is not None:
+        timing.update(score_s=t_scored - t_start, gather_s=t_gathered - t_scored, metrics_s=t_metrics - t_gathered,
+                      records_s=time.perf_counter() - t_metrics, steps=len(steps))
+    return {"scores": scores.cpu(), "metrics": m, "predictions": records}
 
 
 def write_predictions(records: List[dict], path: str) -> None:
@@ -166,49 +199,78 @@ def write_predictions(records: List[dict], path: str) -> None:
         json.dump(records, f)
 
 
-def main() -> None:
-    import argparse
-    import os
+def synthetic_sweep(n_images: int, images_per_step: int = 8, precision: str = "fp16", prefetch: int = 1, verify_shared: bool = True,
+                    out_path: str = "", rank: int = 0, world: int = 1, local_rank: int = 0) -> Dict[str, object]:
+    """BASELINE.json configs[1]: ``n_images`` synthetic images x 10 rounds x 100 candidates, STRONG-scaled over ``world`` ranks
+    (image i -> rank i mod world), scores all-gathered over NCCL, ranks / metrics on the GPU, EvalAI records on every rank.
+    ``torch.distributed`` must already be initialised with the NCCL backend when ``world`` > 1.  Returns rank 0's report:
+    wall clock of the whole sweep (first pack to last record; max over ranks) and its phases."""
+    import time
 
     import torch.distributed as dist
 
     from .config import DEFAULT_CONFIG_PATH, ViLBertConfig
     from .engine import Engine
+    from .sharding import shard_units
     from .weights import random_state_dict
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
+    mine = shard_units(n_images, rank, world)
+    t0 = time.perf_counter()
+    items = synthetic_items(range(n_images), only=mine)                     # generation is not part of the sweep's clock
+    gen_s = time.perf_counter() - t0
+    eng = Engine(cfg, random_state_dict(cfg, 0), precision=precision, max_sequences=images_per_step * 52, device=local_rank)
+    scorer = packed_scorer(eng, verify_shared=verify_shared, depth=max(1, prefetch))
+    metrics_fn = lambda s, g, ns, r: gpu_metrics(s, g, ns, r, dev)
+    # warm-up: one step per rank through the whole driver (kernels, pinned staging, NCCL channels, metric kernels)
+    warm = synthetic_items(range(world * images_per_step))
+    run_sweep(warm, scorer, rank, world, images_per_step, metrics_fn=metrics_fn, gather_device=dev, prefetch=prefetch)
+    del warm
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    timing: Dict[str, float] = {}
+    t0 = time.perf_counter()
+    res = run_sweep(items, scorer, rank, world, images_per_step, metrics_fn=metrics_fn, gather_device=dev, prefetch=prefetch, timing=timing)
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0, timing["score_s"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    n_cand = n_images * len(items[0].gt_index) * len(items[0].relevance)
+    report = dict({k: (float(v) if not isinstance(v, (int, float)) else v) for k, v in res["metrics"].items()},
+                  sweep_images=n_images, sweep_candidates=n_cand, sweep_seconds=float(dt[0]), sweep_candidates_per_sec=n_cand / float(dt[0]),
+                  score_phase_seconds=float(dt[1]), score_phase_candidates_per_sec=n_cand / float(dt[1]),
+                  phases_rank0={k: v for k, v in timing.items()}, prefetch=prefetch, images_per_step=images_per_step, world=world,
+                  precision=precision, generation_seconds_rank0=gen_s, verify_shared=verify_shared,
+                  note="wall clock of the whole driver on every rank (max over ranks): C++ packing from the per-image int64 arrays, "
+                       "H2D, forward, D2H, NCCL all-gather of the scores, GPU ranks / metrics, EvalAI records; synthetic generation excluded")
+    if rank == 0 and out_path:
+        write_predictions(res["predictions"], out_path)
+    eng.close()
+    return report
+
+
+def main() -> None:
+    import argparse
+    import os
+
+    import torch.distributed as dist
     ap = argparse.ArgumentParser(description="synthetic generative ranking sweep (one process per GPU under torchrun)")
     ap.add_argument("--images", type=int, default=16)
     ap.add_argument("--images-per-step", type=int, default=8)
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--out", default="")
+    ap.add_argument("--no-verify", action="store_true", help="skip the per-step check that the candidates of a round share their context")
     ap.add_argument("--prefetch", type=int, default=1, help="0: pack and score serially; n: pack steps i+1..i+n on n worker threads while step i is scored")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
-    items = synthetic_items(range(a.images))
-    eng = Engine(cfg, random_state_dict(cfg, 0), precision=a.precision, max_sequences=a.images_per_step * 52, device=local)
-    scorer = packed_scorer(eng)
-    # the score tensor is exchanged as a host tensor: 8 MB for the full val sweep, a gloo group next to NCCL is plenty
-    group = dist.new_group(backend="gloo") if world > 1 else None
-    import time
-    metrics_fn = lambda s, g, ns, r: gpu_metrics(s, g, ns, r, dev)
-    run_sweep(items[:world * a.images_per_step], scorer, rank, world, a.images_per_step, metrics_fn=metrics_fn, group=group)     # warm-up step
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    res = run_sweep(items, scorer, rank, world, a.images_per_step, metrics_fn=metrics_fn, group=group, prefetch=a.prefetch)
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rep = synthetic_sweep(a.images, a.images_per_step, a.precision, a.prefetch, not a.no_verify, a.out, rank, world, local)
     if rank == 0:
-        n_cand = sum(len(r.tokens) for it in items for r in it.rounds)
-        print(json.dumps(dict({k: v for k, v in res["metrics"].items()}, sweep_candidates=n_cand, sweep_seconds=dt,
-                              sweep_candidates_per_sec=n_cand / dt, prefetch=a.prefetch,
-                              note="whole driver incl. host-side packing, pinning, score gather, ranks and metrics; wall clock")))
-        if a.out:
-            write_predictions(res["predictions"], a.out)
-    eng.close()
+        print(json.dumps(rep))
     if world > 1:
         dist.destroy_process_group()
 

@@ -7,7 +7,8 @@ and a reference checkpoint work unchanged — but the body runs in ``libunimm_b2
 Differences that are deliberate and visible:
   * inference only (forward + losses); no autograd graph is built (SURVEY.md §8f lists backward as next);
   * dropout is the identity (the reference's ``.eval()`` behaviour);
-  * dense masks are converted to 4-integer descriptors and verified; other mask patterns raise;
+  * dense masks are converted to 4-integer descriptors and verified (sequences truncated at max_seq_len included); any other
+    mask pattern raises;
   * ``score()`` is the fast entry: per-sequence log-likelihoods without the [B,S,30522] logits that
     ``output_lm_scores=True`` has to materialise for compatibility.
 """
@@ -91,6 +92,7 @@ class VisualDialogEncoder(nn.Module):
                             masked_lm_labels=masked_lm_labels[sl], want=want)
             for k in want:
                 outs[k].append(o[k])
+        eng.check_ids()
         return {k: torch.cat(v, 0) for k, v in outs.items()}
 
     # ------------------------------------------------------------------ reference signature
@@ -136,6 +138,7 @@ class VisualDialogEncoder(nn.Module):
                                           image_loc[sl], image_attention_mask[sl],
                                           masked_lm_labels=None if masked_lm_labels is None else masked_lm_labels[sl],
                                           want=tuple(want)))
+        eng.check_ids()          # an out-of-range id is an error here exactly as in the reference's nn.Embedding
         if output_nsp_scores:
             out = out + (torch.cat([c["nsp_scores"] for c in chunks], 0),)
         if output_lm_scores:
