@@ -439,6 +439,101 @@ def main():
         save("dis100_default", weight_seed=np.array(0), perturbed=np.array(False), **pack_inputs(b), **image_np,
              nsp_scores=nsp.numpy(), nsp_prob0=prob0.numpy(), ranks=ranks.view(100).numpy())
 
+
+    # ---------------------------------------------------------------- config 3 at its stated size: train.py step forward + loss,
+    # batch 240 = 40 images x 6 sequences (1 positive + 5 negatives of one round, dataloader_visdial.py:199-262), mode drawn per
+    # sequence (train_dis_rate 0.5), mask_prob 0.15, unlikelihood weight -1 on the negatives, nsp_weight [5, 1] (train.py:402).
+    # Image blocks are regenerated from seeds at test time (oracle.encode_inputs.synth_image / a seeded Dirichlet); only the
+    # random masking decisions of encode_image_input are stored.
+    if want("train240_perturbed"):
+        np.random.seed(101)
+        random.seed(101)
+        n_img, per_img = 40, 6
+        cols = [[] for _ in range(8)]
+        nsl, seq_image, img_seeds = [], [], []
+        feats_all, loc_all, mask_all, tgt_all, lab_all, zeroed = [], [], [], [], [], []
+        for i in range(n_img):
+            irng = np.random.RandomState(7000 + i)
+            img_seeds.append(7000 + i)
+            f_i, l_i, m_i = enc.synth_image(irng)
+            tgt = torch.from_numpy(np.random.RandomState(8000 + i).dirichlet(np.ones(1601), size=37).astype(np.float32))
+            f2, l2, im2, tgt2, img_label = du.encode_image_input(f_i.numpy(), 37, l_i.numpy(), tgt.numpy(), max_regions=37, mask_prob=0.15)
+            feats_all.append(f2), loc_all.append(l2), mask_all.append(im2), tgt_all.append(tgt2), lab_all.append(img_label)
+            zeroed.append((f2.abs().sum(-1) == 0).numpy())
+            rnd = int(irng.randint(1, 11))
+            ctx_i = [irng.randint(1000, 30522, size=int(irng.randint(5, 20))).tolist()]
+            for _ in range(2 * (rnd - 1)):
+                ctx_i.append(irng.randint(1000, 30522, size=int(irng.randint(2, 12))).tolist())
+            ctx_i.append(irng.randint(1000, 30522, size=int(irng.randint(3, 10))).tolist())          # the round's question
+            for j in range(per_img):
+                neg = int(j > 0)
+                ans = irng.randint(1000, 30522, size=int(irng.randint(1, 8))).tolist()
+                out = du.encode_input(0.5, ctx_i + [ans], 1, enc.CLS, enc.SEP, enc.MASK, max_seq_len=256, mask_prob=0.15, is_negtive=neg,
+                                      weight=1, vocab_size=30522)
+                for c, o in zip(cols, out):
+                    c.append(o.long() if o.dim() == 3 else o)
+                nsl.append(neg), seq_image.append(i)
+        tokens, segments, positions, sep_indices, labels, weights, att, co = (torch.cat(c, 0) for c in cols)
+        seq_image = torch.LongTensor(seq_image)
+        B = tokens.shape[0]
+        stack = lambda xs: torch.stack(xs)[seq_image]
+        b = {"tokens": tokens, "segments": segments, "positions": positions, "sep_indices": sep_indices, "mask": labels, "weights": weights,
+             "txt_attention_mask": att, "co_attention_mask": co.unsqueeze(1).repeat(1, 37, 1),
+             "image_feat": stack(feats_all), "image_loc": stack(loc_all), "image_mask": stack(mask_all)}
+        extras = dict(next_sentence_label=torch.LongTensor(nsl), image_label=stack(lab_all), image_target=stack(tgt_all),
+                      nsp_weight=torch.FloatTensor([[5.0, 1.0]]))
+        model = get_model(1, True)
+        lm_loss, img_loss, nsp_loss, nsp, lm = call_reference(model, b, extras)
+        del lm
+        print("train240: modes dis/gen", int((co[:, 0] == 1).sum()), int((co[:, 0] == 0).sum()), "losses", lm_loss.item(), img_loss.item(), nsp_loss.item())
+        inp = pack_inputs(b)
+        save("train240_perturbed", weight_seed=np.array(1), perturbed=np.array(True), **inp, seq_image=seq_image.numpy(),
+             image_seeds=np.array(img_seeds), image_zeroed=np.stack(zeroed), image_label=torch.stack(lab_all).numpy(),
+             image_loc=torch.stack(loc_all).numpy(), image_mask=torch.stack(mask_all).numpy(),
+             next_sentence_label=np.array(nsl), nsp_weight=np.array([[5.0, 1.0]], dtype=np.float32),
+             lm_loss=lm_loss.numpy(), img_loss=img_loss.numpy(), nsp_loss=nsp_loss.numpy(), nsp_scores=nsp.numpy())
+
+    # ---------------------------------------------------------------- config 5 at its stated size: dense-annotation fine-tuning step,
+    # the 100 options of one annotated round, ONE mode for all of them, relevance as token weight (integer-truncated),
+    # nsp_weight None, + the objectives dense_annotation_finetuning.py:263-296 builds on the NSP scores
+    for name, fn_name in (("ft100gen_perturbed", "encode_input_gen"), ("ft100dis_perturbed", "encode_input_dis")):
+        if not want(name):
+            continue
+        import importlib
+        rl = importlib.import_module("utils.rank_loss")
+        np.random.seed(41)
+        random.seed(41)
+        relevance = np.random.RandomState(42).choice([0, 0, 0, 0.2, 0.4, 0.6, 0.8, 1.0], size=100).astype(np.float32)
+        relevance[0] = 1.0
+        rel_l = relevance.tolist()
+        kw = dict(mask_prob=0.1, vocab_size=30522, is_negtive=[int(r == 0) for r in rel_l], weight=[(r if r > 0 else 1) for r in rel_l])
+        b = ref_batch(du, context, answers, feats, loc, image_mask, getattr(du, fn_name), seed=41, **kw)
+        np.random.seed(43)
+        target = torch.from_numpy(np.random.RandomState(44).dirichlet(np.ones(1601), size=37).astype(np.float32))
+        f2, l2, im2, tgt2, img_label = du.encode_image_input(feats.numpy(), 37, loc.numpy(), target.numpy(), max_regions=37, mask_prob=0.1)
+        b["image_feat"] = f2.unsqueeze(0).expand(100, -1, -1).contiguous()
+        b["image_loc"] = l2.unsqueeze(0).expand(100, -1, -1).contiguous()
+        b["image_mask"] = im2.unsqueeze(0).expand(100, -1).contiguous()
+        nsl = torch.LongTensor([int(r == 0) for r in rel_l])
+        extras = dict(next_sentence_label=nsl, image_label=img_label.unsqueeze(0).expand(100, -1).contiguous(),
+                      image_target=tgt2.unsqueeze(0).expand(100, -1, -1).contiguous(), nsp_weight=None)
+        model = get_model(1, True)
+        lm_loss, img_loss, nsp_loss, nsp, lm = call_reference(model, b, extras)
+        del lm
+        # dense_annotation_finetuning.py:263-296
+        nsp_scores = nsp.view(-1, 100, 2)
+        ce_nsp = F.cross_entropy(nsp_scores.view(-1, 2), nsl.view(-1))
+        gt_rel = torch.from_numpy(relevance).view(1, 100)
+        nsp_probs = F.softmax(nsp_scores, dim=-1)
+        target_loss = rl.neuralNDCG_transposed(nsp_probs[:, :, 0], gt_rel)
+        total = target_loss + lm_loss.mean() + 1.0 * ce_nsp
+        print(name, "losses", lm_loss.item(), img_loss.item(), nsp_loss.item(), "neuralNDCG", float(target_loss), "total", float(total))
+        save(name, weight_seed=np.array(1), perturbed=np.array(True), **pack_inputs(b),
+             image_feat=f2.numpy(), image_loc=l2.numpy(), image_mask=im2.numpy(),
+             next_sentence_label=nsl.numpy(), image_label=img_label.numpy(), image_target=tgt2.numpy(), relevance=relevance,
+             lm_loss=lm_loss.numpy(), img_loss=img_loss.numpy(), nsp_loss=nsp_loss.numpy(), nsp_scores=nsp.numpy(),
+             nsp_ce_unweighted=ce_nsp.numpy(), neural_ndcg_loss=np.float32(target_loss), total_loss=np.float32(total))
+
     # ---------------------------------------------------------------- config 1: 100 candidates, ranking metrics
     for name, seed, perturbed in (("gen100_default", 0, False),):
         if not want(name):

@@ -144,3 +144,55 @@ def test_config4_nsp_ranking_of_100_candidates(full_cfg, precision):
     e1, e2 = np.abs(nsp.numpy() - g["nsp_scores"]).max(), np.abs(p0 - g["nsp_prob0"]).max()
     print(f"[{precision}] config 4, 100 options: nsp logit err {e1:.3e}, P(answer) err {e2:.3e}")
     assert e1 < TOL[precision] and e2 < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+def test_config3_train_step_forward_at_size(full_cfg, precision):
+    """BASELINE config 3 at its stated size (train.py:53-92, :445): 240 sequences = 40 images x (1 positive + 5 negatives), mixed
+    generative / discriminative masks, 15 % masking, unlikelihood on the negatives: the three losses of the reference."""
+    from conftest import load_golden_multi_image
+    g, b, im = load_golden_multi_image("train240_perturbed")
+    desc = descriptors_from_masks(b["txt_attention_mask"], b["co_attention_mask"])
+    assert 60 < int((desc[:, 0] == 1).sum()) < 180                  # both mask families in one batch
+    eng = engine(full_cfg, g["weight_seed"], g["perturbed"], precision, 240)
+    idx = b["seq_image"]
+    o = eng.forward(b["tokens"], b["segments"], b["positions"], desc, im["image_feat"], im["image_loc"], im["image_mask"],
+                    feat_index=idx.to(torch.int32), masked_lm_labels=b["mask"], lm_weight=b["weights"],
+                    next_sentence_label=torch.from_numpy(g["next_sentence_label"]), image_label=im["image_label"][idx].contiguous(),
+                    image_target=im["image_target"][idx].contiguous(), nsp_weight=torch.from_numpy(g["nsp_weight"]), want=("losses", "nsp_scores"))
+    eng.check_ids()
+    lm, img, nsp = o["losses"][:3].cpu().numpy()
+    print(f"[{precision}] config 3, B = 240: lm {lm:.6f}/{g['lm_loss'].item():.6f} img {img:.6f}/{g['img_loss'].item():.6f} "
+          f"nsp {nsp:.6f}/{g['nsp_loss'].item():.6f}; nsp logits err {np.abs(o['nsp_scores'].cpu().numpy() - g['nsp_scores']).max():.3e}")
+    tol = TOL[precision]
+    assert abs(lm - g["lm_loss"].item()) < tol and abs(img - g["img_loss"].item()) < tol and abs(nsp - g["nsp_loss"].item()) < tol
+    np.testing.assert_allclose(o["nsp_scores"].cpu().numpy(), g["nsp_scores"], atol=tol, rtol=0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["ft100gen_perturbed", "ft100dis_perturbed"])
+def test_config5_dense_annotation_step_at_size(full_cfg, name, precision):
+    """BASELINE config 5 at its stated size (dense_annotation_finetuning.py:253-296): the 100 options of one annotated round,
+    relevance-weighted L / UL loss, unweighted NSP CE, and the NeuralNDCG objective on the NSP probabilities."""
+    from unimm_b200.rank_loss import neural_ndcg_loss
+    g, b = load_golden(name)
+    desc = descriptors_from_masks(b["txt_attention_mask"], b["co_attention_mask"])
+    eng = engine(full_cfg, g["weight_seed"], g["perturbed"], precision, 128)
+    n = 100
+    o = eng.forward(b["tokens"], b["segments"], b["positions"], desc, torch.from_numpy(g["image_feat"])[None], torch.from_numpy(g["image_loc"])[None],
+                    torch.from_numpy(g["image_mask"])[None], feat_index=torch.zeros(n, dtype=torch.int32), masked_lm_labels=b["mask"],
+                    lm_weight=b["weights"], next_sentence_label=torch.from_numpy(g["next_sentence_label"]),
+                    image_label=torch.from_numpy(g["image_label"]).unsqueeze(0).expand(n, -1).contiguous(),
+                    image_target=torch.from_numpy(g["image_target"]).unsqueeze(0).expand(n, -1, -1).contiguous(), nsp_weight=None,
+                    want=("losses", "nsp_scores"))
+    lm, img, nsp = o["losses"][:3].cpu().numpy()
+    probs = torch.softmax(o["nsp_scores"], -1)[:, 0].view(1, n)
+    ndcg = float(neural_ndcg_loss(probs, torch.from_numpy(g["relevance"]).view(1, n).to(probs.device)))
+    total = ndcg + lm + nsp
+    print(f"[{precision}] {name}: lm {lm:.6f}/{g['lm_loss'].item():.6f} nsp {nsp:.6f}/{g['nsp_ce_unweighted'].item():.6f} "
+          f"neuralNDCG {ndcg:.6f}/{float(g['neural_ndcg_loss']):.6f} total {total:.6f}/{float(g['total_loss']):.6f}")
+    tol = TOL[precision]
+    assert abs(lm - g["lm_loss"].item()) < tol and abs(img - g["img_loss"].item()) < tol
+    assert abs(nsp - g["nsp_ce_unweighted"].item()) < tol            # nsp_weight None: the engine's NSP loss IS the unweighted CE
+    assert abs(ndcg - float(g["neural_ndcg_loss"])) < (2e-4 if precision == "fp32" else 2e-2)
+    assert abs(total - float(g["total_loss"])) < 3 * tol

@@ -97,7 +97,8 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // exact (erf) GELU, reference models/vilbert_dialog.py:115-121
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_TANH = 3 /* fragment epilogue only: 1-SFU tanh form */ };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_TANH = 3 /* fragment epilogue only: 1-SFU tanh form */,
+                 ACT_GELU_ERF = 4 /* erff form of the fp32-class mode */ };
 
 // erf-GELU for the tensor-core epilogues, where the accurate erff (~30 issue slots per element) makes the
 // FFN-1 epilogue slower than its K=768 main loop.  GELU(x) = x * Phi(x) with Phi(x) = 1 / (1 + 2^(x * R(x^2))):
@@ -216,7 +217,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 //   LP_FP16  5-bit exponent, 10-bit mantissa (8x finer rounding; values saturate at +-65504 instead of
 //            overflowing — every tensor stored this way is LayerNorm-bounded, a GELU output, a QKV
 //            projection or an attention context, far inside that range)
-enum LpKind : int { LP_BF16 = 0, LP_FP16 = 1 };
+//   LP_HILO  (fp32-class mode) TWO fp16 planes per row: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) — 22 mantissa bits;
+//            a row of K values is stored as [hi_0 .. hi_{K-1} | lo_0 .. lo_{K-1}] (leading dimension >= 2K).  The tcgen05 GEMM
+//            then accumulates a_lo*w_hi + a_hi*w_lo + a_hi*w_hi in its fp32 TMEM accumulator (gemm_umma.cu, split3)
+enum LpKind : int { LP_BF16 = 0, LP_FP16 = 1, LP_HILO = 2 };
 typedef __half fp16;
 
 template <>
@@ -228,6 +232,12 @@ __device__ __forceinline__ uint32_t pack_fp16x2(float lo, float hi) {
     uint32_t r;   // one F2FP.SATFINITE: round to nearest, clamp to +-65504 (first source operand -> upper half)
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+// two values -> their fp16 hi parts and the fp16 residuals
+__device__ __forceinline__ void split_hilo2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_fp16x2(a, b);
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_fp16x2(a - h.x, b - h.y);
 }
 __device__ __forceinline__ uint32_t pack_lp2(float lo, float hi, int kind) {
     return kind == LP_FP16 ? pack_fp16x2(lo, hi) : pack_bf16x2(lo, hi);

@@ -147,6 +147,7 @@ struct unimm_engine {
     size_t d_stage_bytes = 0;
 
     static constexpr int kLogitRows = 2048;
+    int logits_ld() const { return (cfg.vocab_size + 31) / 32 * 32; }     // 128-byte aligned rows: the coalesced epilogue path
 
     // optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline numbers)
     enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_ROWWISE = 2, CAT_LMHEAD = 3, CAT_GEMM_LN = 4, NCAT = 5 };   // GEMM = umma_gemm_kernel, GEMM_LN = umma_gemm_ln_kernel
@@ -179,6 +180,13 @@ struct unimm_engine {
     bool lp() const { return prec == UNIMM_PREC_BF16 || prec == UNIMM_PREC_FP16; }
     int lp_kind() const { return prec == UNIMM_PREC_FP16 ? LP_FP16 : LP_BF16; }
     size_t esz() const { return lp() ? 2 : 4; }
+    // fp32-class mode on the tensor cores: activations and weights as fp16 hi | lo planes (LP_HILO), every projection as three
+    // tcgen05 passes into one fp32 accumulator (gemm_umma.cu split3); UNIMM_FP32_SIMT=1 keeps the CUDA-core sgemm instead
+    bool tc32_ = false;
+    bool tc32() const { return tc32_; }
+    int act_kind() const { return tc32() ? LP_HILO : lp_kind(); }      // what the LayerNorm / embedding kernels write next to fp32
+    bf16* split_scratch = nullptr;     // [rows, 2K] planes of an fp32 operand that no producer wrote as planes
+    size_t split_cap = 0;
 
     int get(const std::string& name, const DevTensor** out, std::vector<int64_t> shape) {
         auto it = raw.find(name);
@@ -195,7 +203,7 @@ struct unimm_engine {
 
     // y = act(x W^T + b) (+ residual); x/y selected by mode
     int linear(const ActBuf& x, int M, const Linear& L, int act, const float* residual, int ldr, float* out_f32, int ldo_f32,
-               void* out_lp, int ldo_lp, cudaStream_t st);
+               void* out_lp, int ldo_lp, cudaStream_t st, bool out_hilo = false);
     // out = LayerNorm(x W^T + b + residual): one cluster-fused kernel in the 16-bit modes, GEMM + LayerNorm kernel otherwise
     int linear_ln(const ActBuf& x, int M, const Linear& L, const float* residual, int ldr, const LayerNormP& ln, float* pre,
                   ActBuf& out, cudaStream_t st);
@@ -285,6 +293,12 @@ int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each,
     }
     L->w32 = w;
     L->b = b;
+    if (tc32() && !keep_f32_only && K % 64 == 0) {
+        bf16* h = nullptr;
+        UNIMM_TRY(dalloc(&h, static_cast<size_t>(L->N) * 2 * K));
+        UNIMM_TRY(split_f32_to_hilo(w, K, L->N, K, h, 0));
+        L->wlp = h;
+    }
     if (lp() && !keep_f32_only) {
         bf16* h = nullptr;
         UNIMM_TRY(dalloc(&h, static_cast<size_t>(L->N) * K));
@@ -396,6 +410,11 @@ int unimm_engine::finalize() {
             UNIMM_TRY(dalloc(&h, static_cast<size_t>(c.vocab_size) * H));
             UNIMM_TRY(cast_f32_to_lp(lm_decoder.w32, h, static_cast<size_t>(c.vocab_size) * H, lp_kind(), 0));
             lm_decoder.wlp = h;
+        } else if (tc32()) {
+            bf16* h = nullptr;
+            UNIMM_TRY(dalloc(&h, static_cast<size_t>(c.vocab_size) * 2 * H));
+            UNIMM_TRY(split_f32_to_hilo(lm_decoder.w32, H, c.vocab_size, H, h, 0));
+            lm_decoder.wlp = h;
         }
     }
     UNIMM_TRY(make_linear({"cls.imagePredictions.transform.dense"}, Hv, Hv, &img_transform));
@@ -422,9 +441,14 @@ int unimm_engine::alloc_workspace() {
     const size_t wv = std::max(std::max(3 * Hv, 3 * Hb), c.v_intermediate_size);
     UNIMM_TRY(dalloc(&xt.f, Mt * H)); xt.ld = H;
     UNIMM_TRY(dalloc(&xv.f, Mv * Hv)); xv.ld = Hv;
-    if (lp()) { UNIMM_TRY(dalloc(&xt.h, Mt * H)); UNIMM_TRY(dalloc(&xv.h, Mv * Hv)); }
+    const size_t planes = tc32() ? 2 : 1;           // LP_HILO rows are two fp16 planes wide
+    if (lp() || tc32()) { UNIMM_TRY(dalloc(&xt.h, Mt * H * planes)); UNIMM_TRY(dalloc(&xv.h, Mv * Hv * planes)); }
     UNIMM_TRY(dalloc(&xk.f, Mt * H)); xk.ld = H;
-    if (lp()) UNIMM_TRY(dalloc(&xk.h, Mt * H));
+    if (lp() || tc32()) UNIMM_TRY(dalloc(&xk.h, Mt * H * planes));
+    if (tc32()) {
+        split_cap = std::max(Mt * 2 * static_cast<size_t>(std::max(std::max(H, Hb), Hv)), Mv * 2 * static_cast<size_t>(std::max(c.v_feature_size, std::max(Hv, Hb))));
+        UNIMM_TRY(dalloc(&split_scratch, split_cap));
+    }
     UNIMM_TRY(dalloc(&pre_t, Mt * H));
     UNIMM_TRY(dalloc(&pre_v, Mv * Hv));
     char* p;
@@ -439,6 +463,7 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&g_in.f, lp() ? 4 : Mt * H)); g_in.ld = H;
     UNIMM_TRY(dalloc(&g_h.f, Mt * H)); g_h.ld = H;
     if (lp()) { UNIMM_TRY(dalloc(&g_in.h, Mt * H)); UNIMM_TRY(dalloc(&g_h.h, Mt * H)); }
+    if (tc32()) UNIMM_TRY(dalloc(&g_h.h, Mt * H * 2));
     UNIMM_TRY(dalloc(&g_t1, Mt * H));
     UNIMM_TRY(dalloc(&g_labels, Mt));
     UNIMM_TRY(dalloc(&label_logit, Mt));
@@ -446,11 +471,11 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&row_ul, Mt));
     UNIMM_TRY(dalloc(&lse_u, Mt));
     if (lp()) UNIMM_TRY(dalloc(&partials, Mt * gemm_umma_lse_tiles(c.vocab_size)));
-    else UNIMM_TRY(dalloc(&logits_chunk, static_cast<size_t>(kLogitRows) * c.vocab_size));
+    else UNIMM_TRY(dalloc(&logits_chunk, static_cast<size_t>(kLogitRows) * logits_ld()));
     UNIMM_TRY(dalloc(&vhead, Mv * Hv));
     vhead_h.ld = Hv;
     UNIMM_TRY(dalloc(&vhead_h.f, Mv * Hv));
-    if (lp()) UNIMM_TRY(dalloc(&vhead_h.h, Mv * Hv));
+    if (lp() || tc32()) UNIMM_TRY(dalloc(&vhead_h.h, Mv * Hv * planes));
     UNIMM_TRY(dalloc(&v_logits, Mv * c.v_target_size));
     UNIMM_TRY(dalloc(&err_flag, 4));
     UNIMM_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_err), 4 * sizeof(int)));
@@ -468,7 +493,7 @@ int unimm_engine::alloc_workspace() {
 }
 
 int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const float* residual, int ldr, float* out_f32,
-                         int ldo_f32, void* out_lp, int ldo_lp, cudaStream_t st) {
+                         int ldo_f32, void* out_lp, int ldo_lp, cudaStream_t st, bool out_hilo) {
     GemmEpilogue ep;
     ep.bias = L.b;
     ep.residual = residual;
@@ -491,10 +516,31 @@ int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const
         }
         return gemm_umma_bf16(x.h, x.ld, L.wlp, L.K, M, L.N, L.K, ep, 0, 0, st);
     }
-    // fp32 mode: the "low precision" output slot is an fp32 tensor as well
+    // fp32 mode: the "low precision" output slot is an fp32 tensor as well (or, out_hilo, its fp16 hi | lo planes)
     UNIMM_CHECK(!(out_f32 && out_lp), "fp32 mode writes one output");
-    ep.out_f32 = out_f32 ? out_f32 : static_cast<float*>(out_lp);
-    ep.ldo_f32 = out_f32 ? ldo_f32 : ldo_lp;
+    if (out_hilo) {
+        UNIMM_CHECK(tc32() && out_lp != nullptr, "hi | lo output is the fp32-class tensor-core mode's");
+        ep.out_bf16 = static_cast<bf16*>(out_lp); ep.ldo_bf16 = 2 * ldo_lp; ep.out_hilo = true;
+    } else {
+        ep.out_f32 = out_f32 ? out_f32 : static_cast<float*>(out_lp);
+        ep.ldo_f32 = out_f32 ? ldo_f32 : ldo_lp;
+    }
+    if (tc32() && L.wlp != nullptr && L.K % 64 == 0) {
+        const bf16* a = x.h;
+        if (a == nullptr) {            // an fp32 operand nobody wrote as planes (attention context, gathered rows, image features)
+            UNIMM_CHECK(x.f != nullptr && static_cast<size_t>(M) * 2 * L.K <= split_cap, "fp32-class GEMM: operand larger than the split scratch");
+            Prof prof2(this, CAT_ROWWISE, 8.0 * M * L.K, st);
+            UNIMM_TRY(split_f32_to_hilo(x.f, x.ld, M, L.K, split_scratch, st));
+            a = split_scratch;
+        } else {
+            UNIMM_CHECK(x.ld == L.K, "fp32-class GEMM: plane operand with a leading dimension other than K");
+        }
+        ep.lp_kind = LP_FP16;
+        ep.split3 = 1;
+        if (act == ACT_GELU) ep.act = ACT_GELU_ERF;
+        return gemm_umma_bf16(a, 2 * L.K, L.wlp, 2 * L.K, M, L.N, L.K, ep, 0, 0, st);
+    }
+    UNIMM_CHECK(!out_hilo, "hi | lo output needs the tensor-core path (K % 64 == 0)");
     return gemm_simt_f32(x.f, x.ld, L.w32, L.K, M, L.N, L.K, ep, st);
 }
 
@@ -516,7 +562,7 @@ int unimm_engine::linear_ln(const ActBuf& x, int M, const Linear& L, const float
     UNIMM_CHECK(!(lp() && fuse_ln && res16), "16-bit residual stream needs the LayerNorm-fused GEMM (N = 768 or 1024, K % 64 == 0)");
     UNIMM_TRY(linear(x, M, L, ACT_NONE, residual, ldr, pre, L.N, nullptr, 0, st));
     Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * M * L.N, st);
-    return layernorm_rows(pre, L.N, M, L.N, ln.g, ln.b, out.f, out.h, lp_kind(), st);
+    return layernorm_rows(pre, L.N, M, L.N, ln.g, ln.b, out.f, out.h, act_kind(), st);
 }
 
 int unimm_engine::attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
@@ -634,9 +680,10 @@ int unimm_engine::self_layer_tail(const SelfLayer& L, const ActBuf& c, ActBuf& x
     const int H = x.ld;
     UNIMM_TRY(linear_ln(c, M, L.out, x.f, H, L.ln1, pre, x, st));
     const int I = L.ffn1.N;
-    UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st));
+    UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st, tc32()));
     ActBuf f;
-    f.f = lp() ? nullptr : static_cast<float*>(ffn); f.h = lp() ? static_cast<bf16*>(ffn) : nullptr; f.ld = I;
+    const bool f16 = lp() || tc32();            // tc32: the GELU output exists as hi | lo planes only
+    f.f = f16 ? nullptr : static_cast<float*>(ffn); f.h = f16 ? static_cast<bf16*>(ffn) : nullptr; f.ld = I;
     UNIMM_TRY(linear_ln(f, M, L.ffn2, x.f, H, L.ln2, pre, x, st));
     return 0;
 }
@@ -664,7 +711,7 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
         kv2.N = 2 * Hb;
         const size_t off = static_cast<size_t>(Hb) * L.qkv_t.K;
         kv2.w32 = L.qkv_t.w32 + off; kv2.b = L.qkv_t.b + Hb;
-        if (L.qkv_t.wlp) kv2.wlp = L.qkv_t.wlp + off;
+        if (L.qkv_t.wlp) kv2.wlp = L.qkv_t.wlp + (tc32() ? 2 * off : off);
         if (L.qkv_t.wlp_p16) kv2.wlp_p16 = L.qkv_t.wlp_p16 + off;
         UNIMM_TRY(linear(xt, Mt, q2, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
         UNIMM_TRY(linear(xt, n_sh, kv2, ACT_NONE, nullptr, 0, nullptr, 0, byte_ptr(qkv_t) + e * Hb, 3 * Hb, st));
@@ -698,14 +745,14 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
     // image FFN, text FFN (:777-781)
     const int Iv = L.v_ffn1.N, I = L.t_ffn1.N;
     if (image_out) {
-        UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st));
+        UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st, tc32()));
         ActBuf fv;
-        fv.f = lp() ? nullptr : static_cast<float*>(ffn_v); fv.h = lp() ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
+        fv.f = (lp() || tc32()) ? nullptr : static_cast<float*>(ffn_v); fv.h = (lp() || tc32()) ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
         UNIMM_TRY(linear_ln(fv, Mv, L.v_ffn2, xv.f, Hv, L.v_ln, pre_v, xv, st));
     }
-    UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st));
+    UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st, tc32()));
     ActBuf ft;
-    ft.f = lp() ? nullptr : static_cast<float*>(ffn_t); ft.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; ft.ld = I;
+    ft.f = (lp() || tc32()) ? nullptr : static_cast<float*>(ffn_t); ft.h = (lp() || tc32()) ? static_cast<bf16*>(ffn_t) : nullptr; ft.ld = I;
     UNIMM_TRY(linear_ln(ft, Mt, L.t_ffn2, xt.f, H, L.t_ln, pre_t, xt, st));
     return 0;
 }
@@ -723,7 +770,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     // ---- embeddings (reference :326-356, :1487-1493)
     UNIMM_TRY(embed_text_ln(in.d_input_ids, in.d_token_type_ids, in.d_position_ids, Mt, H, c.vocab_size, c.max_position_embeddings,
                             c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h,
-                            lp_kind(), err_flag, st));
+                            act_kind(), err_flag, st));
     UNIMM_TRY(gather_features(in.d_image_feat, in.d_feat_index, B, R, c.v_feature_size, lp() ? nullptr : static_cast<float*>(feat_a),
                               lp() ? static_cast<bf16*>(feat_a) : nullptr, lp_kind(), st));
     UNIMM_TRY(image_loc_embed(in.d_image_loc, in.d_feat_index, B, R, Hv, loc_w, loc_b, pre_v, st));
@@ -778,7 +825,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
         // image head (:1085-1088) + masked KL (:1569-1574)
         UNIMM_CHECK(in.d_image_label != nullptr, "image_label required with image_target");
         UNIMM_TRY(linear(xv, Mv, img_transform, ACT_GELU, nullptr, 0, vhead, Hv, nullptr, 0, st));
-        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(vhead, Hv, Mv, Hv, img_ln.g, img_ln.b, vhead_h.f, vhead_h.h, lp_kind(), st)); }
+        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mv) * (Hv), st); UNIMM_TRY(layernorm_rows(vhead, Hv, Mv, Hv, img_ln.g, img_ln.b, vhead_h.f, vhead_h.h, act_kind(), st)); }
         UNIMM_TRY(linear(vhead_h, Mv, img_decoder, ACT_NONE, nullptr, 0, v_logits, c.v_target_size, nullptr, 0, st));
         // d_losses[1] = loss, [3..4] scratch
         float* kl = out.d_losses + 3;
@@ -842,7 +889,7 @@ int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* 
     if (d_rows != nullptr)
         UNIMM_TRY(gather_rows(lp() ? nullptr : src.f, lp() ? src.h : nullptr, d_rows, n, H, lp() ? nullptr : g_in.f, lp() ? g_in.h : nullptr, st));
     UNIMM_TRY(linear(d_rows != nullptr ? g_in : src, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, lp_kind(), st)); }
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, act_kind(), st)); }
     if (lp()) {
         GemmEpilogue ep;
         ep.bias = lm_decoder.b;
@@ -859,9 +906,16 @@ int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* 
             GemmEpilogue ep;
             ep.bias = lm_decoder.b;
             ep.out_f32 = logits_chunk;
-            ep.ldo_f32 = c.vocab_size;
-            UNIMM_TRY(gemm_simt_f32(g_h.f + static_cast<size_t>(r0) * H, H, lm_decoder.w32, H, nr, c.vocab_size, H, ep, st));
-            UNIMM_TRY(lse_from_logits(logits_chunk, c.vocab_size, nr, c.vocab_size, d_labels + r0, row_logp + r0, row_ul + r0, st));
+            ep.ldo_f32 = logits_ld();
+            Prof prof(this, CAT_LMHEAD, 2.0 * nr * c.vocab_size * H, st);
+            if (tc32()) {
+                ep.lp_kind = LP_FP16;
+                ep.split3 = 1;
+                UNIMM_TRY(gemm_umma_bf16(g_h.h + static_cast<size_t>(r0) * 2 * H, 2 * H, lm_decoder.wlp, 2 * H, nr, c.vocab_size, H, ep, 256, 0, st));
+            } else {
+                UNIMM_TRY(gemm_simt_f32(g_h.f + static_cast<size_t>(r0) * H, H, lm_decoder.w32, H, nr, c.vocab_size, H, ep, st));
+            }
+            UNIMM_TRY(lse_from_logits(logits_chunk, logits_ld(), nr, c.vocab_size, d_labels + r0, row_logp + r0, row_ul + r0, st));
         }
     }
     return 0;
@@ -909,7 +963,7 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
     UNIMM_CHECK(R <= 64, "the prefix-shared layout supports at most 64 image regions per unit");
     UNIMM_CHECK(in.win_cap >= 128 + 2 * in.cand_halo, "win_cap too small for the longest candidate (needs 128 + 2 * cand_halo)");
     UNIMM_TRY(embed_text_ln_i32(in.d_input_ids, in.d_token_type_ids, in.d_position_ids, M, H, c.vocab_size, c.max_position_embeddings,
-                                c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h, lp_kind(),
+                                c.type_vocab_size, 10, word_emb, pos_emb, type_emb, type_ext_emb, emb_ln.g, emb_ln.b, xt.f, xt.h, act_kind(),
                                 err_flag, st));
     UNIMM_CHECK(in.d_unit_image == nullptr || in.n_images > 0, "d_unit_image given without n_images");
     UNIMM_TRY(gather_features(in.d_image_feat, in.d_unit_image, U, R, c.v_feature_size, lp() ? nullptr : static_cast<float*>(feat_a),
@@ -1000,6 +1054,8 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     if (const char* f = getenv("UNIMM_KV2_ALL")) e->kv2_ctx_only = atoi(f) == 0;
     if (const char* f = getenv("UNIMM_PRUNE_TAIL")) e->prune_tail = atoi(f) != 0;
     if (const char* f = getenv("UNIMM_LM_DEDUP")) e->lm_dedup = atoi(f) != 0;
+    e->tc32_ = precision == UNIMM_PREC_FP32;
+    if (const char* f = getenv("UNIMM_FP32_SIMT")) e->tc32_ = e->tc32_ && atoi(f) == 0;
     e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;

@@ -77,7 +77,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_m = ((M + BM - 1) / BM + CS - 1) / CS;     // row blocks of CS x 128 rows (a padding tile is all out of bounds)
     const int num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int num_k = K / BK;
+    const int num_k1 = K / BK;
+    // fp32-class mode: every k-block three times — (a_lo, w_hi), (a_hi, w_lo), (a_hi, w_hi), small terms first — into one accumulator
+    const int num_k = ep.split3 ? 3 * num_k1 : num_k1;
     const uint32_t crank = CS > 1 ? ptx::cluster_ctarank() : 0u;
     const int first_tile = blockIdx.x / CS, tile_step = gridDim.x / CS;
     constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1u);
@@ -118,19 +120,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int m0 = ((tile / num_n) * CS + static_cast<int>(crank)) * BM;
                 const int n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_k; ++kb) {
+                    int ka = kb * BK, kw = kb * BK;          // column of the A box / of the W box
+                    if (ep.split3) {
+                        const int pass = kb / num_k1, kk = (kb - pass * num_k1) * BK;
+                        ka = kk + (pass == 0 ? K : 0);       // pass 0 reads the lo plane of A, pass 1 the lo plane of W
+                        kw = kk + (pass == 1 ? K : 0);
+                    }
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (SM2) {
                         // both CTAs' boxes are counted on the leader's barrier, which the leader arms for the pair
                         if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                        ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
-                        ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0 + static_cast<int>(crank) * (BN / 2));
+                        ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, m0);
+                        ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kw, n0 + static_cast<int>(crank) * (BN / 2));
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m0);
-                    if (CL == 1) ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0);
-                    else ptx::tma_load_2d_mc(sB + stage * Cfg::kBBytes + crank * (Cfg::kBBytes / CL), &tmB, &full_bar[stage], kb * BK,
+                    ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, m0);
+                    if (CL == 1) ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kw, n0);
+                    else ptx::tma_load_2d_mc(sB + stage * Cfg::kBBytes + crank * (Cfg::kBBytes / CL), &tmB, &full_bar[stage], kw,
                                              n0 + static_cast<int>(crank) * (BN / CL), kMask);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -186,7 +194,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              (ep.residual == nullptr || ((ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0)) &&
                              (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
         // 16-bit-only output with 128-byte aligned row segments: the paired-chunk path (needs N % 64 == 0 so pairs never split)
-        const bool lp_only = fast_ok && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && (N % 64) == 0 &&
+        const bool lp_only = fast_ok && !ep.out_hilo && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && (N % 64) == 0 &&
                              (ep.ldo_bf16 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0;
         // FRAG instantiation: the host has checked lp_only && w_perm16 && N % 32 == 0 (launch()); the other paths are compiled out
         // the accumulator pair is handed back to the MMA warp of the LEADER CTA
@@ -418,6 +426,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int i = 0; i < 8; ++i) {
                             gelu_epi2(y[i].x, y[i].y); gelu_epi2(y[i].z, y[i].w);
                         }
+                    } else if (ep.act == ACT_GELU_ERF) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            y[i].x = gelu_erf(y[i].x); y[i].y = gelu_erf(y[i].y); y[i].z = gelu_erf(y[i].z); y[i].w = gelu_erf(y[i].w);
+                        }
                     } else if (ep.act == ACT_RELU) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -434,7 +447,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (grow < M) {
                             if (ep.out_f32 != nullptr)
                                 *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc) = y[i];
-                            if (ep.out_bf16 != nullptr) {
+                            if (ep.out_bf16 != nullptr && ep.out_hilo) {
+                                uint2 hi, lo;
+                                split_hilo2(y[i].x, y[i].y, hi.x, lo.x);
+                                split_hilo2(y[i].z, y[i].w, hi.y, lo.y);
+                                *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + cc) = hi;
+                                *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + N + cc) = lo;
+                            } else if (ep.out_bf16 != nullptr) {
                                 uint2 pk;
                                 pk.x = pack_lp2(y[i].x, y[i].y, ep.lp_kind);
                                 pk.y = pack_lp2(y[i].z, y[i].w, ep.lp_kind);
@@ -453,6 +472,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (ep.act == ACT_GELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
+                } else if (ep.act == ACT_GELU_ERF) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
                 } else if (ep.act == ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
@@ -597,8 +619,9 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     constexpr int CS = CL == 1 ? 1 : 2;
     using Cfg = GemmCfg<BN, ST, CL == 3>;
     CUtensorMap tmA, tmB;
-    UNIMM_TRY(make_map_bf16(A, M, K, lda, BM, &tmA));
-    UNIMM_TRY(make_map_bf16(W, N, K, ldw, BN / CS, &tmB));
+    const int kcols = ep.split3 ? 2 * K : K;                 // fp32-class mode: hi | lo planes side by side
+    UNIMM_TRY(make_map_bf16(A, M, kcols, lda, BM, &tmA));
+    UNIMM_TRY(make_map_bf16(W, N, kcols, ldw, BN / CS, &tmB));
     static int max_clusters = 0;
     auto kernel = umma_gemm_kernel<BN, LSE, ST, FRAG, CL>;
     UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), Cfg::kSmemBytes));
@@ -658,6 +681,9 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
                    int max_ctas, cudaStream_t stream) {
     UNIMM_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "umma gemm: K must be a positive multiple of 64");
     const bool lse = ep.partials != nullptr;
+    UNIMM_CHECK(!ep.split3 || (!lse && !ep.w_perm16 && ep.lp_kind == LP_FP16), "split3 takes fp16 hi | lo planes and the plain epilogue");
+    UNIMM_CHECK(!ep.out_hilo || (ep.out_bf16 != nullptr && N % 32 == 0 && (ep.ldo_bf16 & 3) == 0 && ep.ldo_bf16 >= 2 * N),
+                "hi | lo output needs N % 32 == 0 and a [M, 2N] 16-bit matrix");
     if (tile_n == 0) tile_n = (N % 256 == 0 || N > 2048) ? 256 : 128;
     // tall problems (every SM gets several row blocks): CTA pairs sharing the W tile by TMA multicast
     // UNIMM_GEMM_MULTICAST: 0 = independent CTAs, 1 = CTA pairs sharing W by multicast, 2 = CTA pairs as one cta_group::2 MMA

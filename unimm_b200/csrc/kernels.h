@@ -23,6 +23,8 @@ struct GemmEpilogue {
     int act = ACT_NONE;
     int debug_mode = 0;            // microbenchmark only: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue work
     int lp_kind = LP_BF16;         // encoding of the 16-bit operands and of out_bf16 (LP_BF16 / LP_FP16)
+    int split3 = 0;                // fp32-class mode: A [M, 2K] and W [N, 2K] are fp16 hi | lo planes (LP_HILO); three passes per k-block
+    bool out_hilo = false;         // write out_bf16 as hi | lo planes of an [M, 2N] fp16 matrix (ldo_bf16 >= 2N) instead of one 16-bit value
     bool w_perm16 = false;         // W rows are in fragment order (permute_weight_rows mode 1): enables the smem-free 16-bit epilogue
     const int* labels = nullptr;   // LSE mode: [M]
     float2* partials = nullptr;    // LSE mode: [M, gemm_umma_lse_tiles(N)]
@@ -87,6 +89,8 @@ int gather_features(const float* feat, const int* feat_index, int B, int R, int 
 int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int n, int H, float* dst_f32, bf16* dst_bf16,
                 cudaStream_t stream);
 int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream);
+// fp32 [rows, K] -> fp16 hi | lo planes [rows, 2K] (LP_HILO, the operand layout of the fp32-class tcgen05 GEMM)
+int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaStream_t stream);
 // *d_flag = 1 iff the two fp32 buffers differ in any bit
 int buffers_differ(const float* a, const float* b, size_t n, int* d_flag, cudaStream_t stream);
 int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStream_t stream);

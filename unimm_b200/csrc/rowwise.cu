@@ -34,7 +34,13 @@ __device__ __forceinline__ void ln_normalise_store(float4 (&x)[NV], int lane, co
         y.z = (x[i].z - mean) * rstd * g.z + b.z;
         y.w = (x[i].w - mean) * rstd * g.w + b.w;
         if (y_f32 != nullptr) *reinterpret_cast<float4*>(y_f32 + c) = y;
-        if (y_bf16 != nullptr) {
+        if (y_bf16 != nullptr && lp_kind == LP_HILO) {      // fp32-class mode: hi plane at [0, H), lo plane at [H, 2H) of the row
+            uint2 hi, lo;
+            split_hilo2(y.x, y.y, hi.x, lo.x);
+            split_hilo2(y.z, y.w, hi.y, lo.y);
+            *reinterpret_cast<uint2*>(y_bf16 + c) = hi;
+            *reinterpret_cast<uint2*>(y_bf16 + H + c) = lo;
+        } else if (y_bf16 != nullptr) {
             uint2 p;
             p.x = pack_lp2(y.x, y.y, lp_kind);
             p.y = pack_lp2(y.z, y.w, lp_kind);
@@ -56,7 +62,7 @@ layernorm_kernel(const float* __restrict__ x, int ldx, int rows, const float* __
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
     ln_normalise_store<NV>(v, lane, gamma, beta, y_f32 ? y_f32 + static_cast<size_t>(row) * H : nullptr,
-                           y_bf16 ? y_bf16 + static_cast<size_t>(row) * H : nullptr, lp_kind);
+                           y_bf16 ? y_bf16 + static_cast<size_t>(row) * (lp_kind == LP_HILO ? 2 * H : H) : nullptr, lp_kind);
 }
 
 template <int NV, typename IdT>
@@ -93,7 +99,7 @@ embed_text_ln_kernel(const IdT* __restrict__ ids, const IdT* __restrict__ type_i
         v[i] = make_float4((a.x + b.x) + d.x, (a.y + b.y) + d.y, (a.z + b.z) + d.z, (a.w + b.w) + d.w);
     }
     ln_normalise_store<NV>(v, lane, gamma, beta, out_f32 ? out_f32 + static_cast<size_t>(row) * H : nullptr,
-                           out_bf16 ? out_bf16 + static_cast<size_t>(row) * H : nullptr, lp_kind);
+                           out_bf16 ? out_bf16 + static_cast<size_t>(row) * (lp_kind == LP_HILO ? 2 * H : H) : nullptr, lp_kind);
 }
 
 __global__ void image_loc_kernel(const float* __restrict__ loc, const int* __restrict__ feat_index, int R, int H,
@@ -272,6 +278,31 @@ int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStrea
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
     widen_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint2*>(src), reinterpret_cast<float4*>(dst), n4, lp_kind);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+// fp32 [rows, K] (leading dimension ldx) -> the two fp16 planes [rows, 2K] of the fp32-class mode (LP_HILO)
+__global__ void split_hilo_kernel(const float* __restrict__ x, int ldx, int rows, int K, bf16* __restrict__ out) {
+    const int kv = K / 4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < static_cast<size_t>(rows) * kv;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / kv;
+        const int c = static_cast<int>(i % kv) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        uint2 hi, lo;
+        split_hilo2(v.x, v.y, hi.x, lo.x);
+        split_hilo2(v.z, v.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(out + r * 2 * K + c) = hi;
+        *reinterpret_cast<uint2*>(out + r * 2 * K + K + c) = lo;
+    }
+}
+int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaStream_t stream) {
+    UNIMM_CHECK(rows > 0 && K % 4 == 0 && ldx % 4 == 0, "split: K and ldx must be multiples of 4");
+    const size_t n = static_cast<size_t>(rows) * (K / 4);
+    int grid = static_cast<int>((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    split_hilo_kernel<<<grid, 256, 0, stream>>>(x, ldx, rows, K, out);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
