@@ -18,6 +18,8 @@ the scores at the end).
   cpu_baseline  the oracle (CPU port of the reference path, val_lm-style full logits) on the host cores (rank 0, N=1)
   bf16_mode  (fp16 runs only) value / e2e / % of peak of the SAME step in bf16 mode, measured in the same process
 
+--workload train_fwd | dis_nsp | dense_ft: BASELINE configs 3 / 4 / 5 at their stated sizes on one GPU (see main_dense_workload).
+
 --workload sweep: the WHOLE sweep (--images, default 2064) strong-scaled over the ranks through unimm_b200.val_sweep (packing,
 scoring, NCCL all-gather, GPU ranks / metrics, EvalAI records), wall clock, max over ranks.
 
@@ -383,6 +385,145 @@ def main_sweep(args):
         dist.destroy_process_group()
 
 
+def main_dense_workload(args):
+    """BASELINE configs 3 / 4 / 5 at their stated sizes on ONE GPU, dense layout (rows differ per sequence: no prefix to share):
+      train_fwd  config 3: 240 sequences = 40 images x (1 positive + 5 negatives), mixed gen / dis masks, 15 % masking, UL on negatives;
+                 forward + the three losses (train.py:53-92, :445)
+      dis_nsp    config 4: one image = 10 rounds x 100 options under the discriminative masks, NSP probability per option
+                 (val.py:125-161), chunks of 250
+      dense_ft   config 5: the 100 options of one annotated round, one mask mode, relevance-weighted L / UL loss + NSP CE +
+                 NeuralNDCG on the NSP probabilities (dense_annotation_finetuning.py:253-296)
+    value = sequences / s with inputs resident in HBM; e2e = the same from pinned host tensors (ids, descriptors, per-image feature
+    blocks, targets) through Engine.forward, losses / scores read back every step."""
+    from unimm_b200 import synthetic as syn
+    from unimm_b200.config import DEFAULT_CONFIG_PATH, ViLBertConfig
+    from unimm_b200.engine import Engine
+    from unimm_b200._lib import lib
+    from unimm_b200.rank_loss import neural_ndcg_loss
+    from unimm_b200.weights import random_state_dict
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
+    wl = args.workload
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    batches = []
+    for i in range(3):
+        if wl == "train_fwd":
+            b = syn.train_batch(1000 + i)
+            b = {k: T(v) for k, v in b.items()}
+            idx = b["seq_image"].long()
+            b["image_label_seq"], b["image_target_seq"] = b["image_label"][idx].contiguous(), b["image_target"][idx].contiguous()
+            b["nsp_weight"] = torch.tensor([5.0, 1.0])
+        else:
+            rng = np.random.RandomState(2000 + i)
+            f, l, m = syn.synth_image(rng)
+            rounds = []
+            if wl == "dis_nsp":
+                for r in range(1, 11):
+                    rounds.append(syn.encode_round_dis(syn.synth_context(rng, r), syn.synth_answers(rng, 100)))
+                tokens, segments, positions, labels, desc, _ = syn.stack_rounds(rounds)
+                b = {"tokens": tokens, "segments": segments, "positions": positions, "labels": labels, "desc": desc}
+            else:
+                ctx = syn.synth_context(rng, int(rng.randint(1, 11)))
+                rel = rng.choice([0, 0, 0, 0.2, 0.4, 0.6, 0.8, 1.0], size=100).astype(np.float32)
+                cols = [[] for _ in range(6)]
+                dis = bool(i % 2)
+                for j in range(100):
+                    out = syn.encode_train_sequence(rng, ctx, syn._draw(rng, int(rng.randint(1, 8))), dis=dis, negative=rel[j] == 0, mask_prob=0.1,
+                                                    weight=1)
+                    for c, o in zip(cols, out):
+                        c.append(o)
+                tokens, segments, positions, labels, weights, desc = (T(np.stack(c)) for c in cols)
+                il = np.where(rng.rand(37) < 0.1, 1, -1); il[0] = 0
+                tgt = rng.rand(37, 1601).astype(np.float32) ** 8
+                tgt /= tgt.sum(-1, keepdims=True)
+                b = {"tokens": tokens, "segments": segments, "positions": positions, "labels": labels, "weights": weights, "desc": desc,
+                     "next_sentence_label": T((rel == 0).astype(np.int64)), "relevance": T(rel).view(1, 100),
+                     "image_label_seq": T(il.astype(np.int64)).unsqueeze(0).expand(100, -1).contiguous(),
+                     "image_target_seq": T(tgt).unsqueeze(0).expand(100, -1, -1).contiguous()}
+            n = b["tokens"].shape[0]
+            b.update(image_feat=T(f)[None], image_loc=T(l)[None], image_mask=T(m)[None], seq_image=torch.zeros(n, dtype=torch.int32))
+        batches.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()})
+    B = batches[0]["tokens"].shape[0]
+    chunk = 250 if wl == "dis_nsp" else B
+    eng = Engine(cfg, random_state_dict(cfg, 0), precision=args.precision, max_sequences=chunk, device=0)
+
+    def step(b):
+        """-> small result tensor on the device (losses / probabilities)"""
+        if wl == "dis_nsp":
+            outs = []
+            for s0 in range(0, B, chunk):
+                sl = slice(s0, s0 + chunk)
+                o = eng.forward(b["tokens"][sl], b["segments"][sl], b["positions"][sl], b["desc"][sl], b["image_feat"], b["image_loc"], b["image_mask"],
+                                feat_index=b["seq_image"][sl], want=("nsp_scores",))
+                outs.append(o["nsp_scores"])
+            return torch.softmax(torch.cat(outs), 1)[:, 0]
+        o = eng.forward(b["tokens"], b["segments"], b["positions"], b["desc"], b["image_feat"], b["image_loc"], b["image_mask"],
+                        feat_index=b["seq_image"], masked_lm_labels=b["labels"], lm_weight=b["weights"], next_sentence_label=b["next_sentence_label"],
+                        image_label=b["image_label_seq"], image_target=b["image_target_seq"], nsp_weight=b.get("nsp_weight"),
+                        want=("losses", "nsp_scores"))
+        if wl == "dense_ft":
+            probs = torch.softmax(o["nsp_scores"], 1)[:, 0].view(1, -1)
+            nd = neural_ndcg_loss(probs, b["relevance"].to(probs.device, non_blocking=True))
+            return torch.cat([o["losses"][:3], nd.view(1)])
+        return o["losses"][:3].clone()
+
+    devb = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in batches]
+    stream = torch.cuda.current_stream(dev)
+    sampler = ClockSampler(0)
+    for i in range(args.warmup):
+        step(devb[i % 3])
+    torch.cuda.synchronize(dev)
+    lib.unimm_reset_launch_count()
+    eng.profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_start()
+    ev0.record(stream)
+    for i in range(args.steps):
+        res = step(devb[i % 3])
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    launches = int(lib.unimm_launch_count())
+    prof = eng.profile_end()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    for i in range(min(args.warmup, 2)):
+        step(batches[i % 3]).cpu()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        host_res = step(batches[i % 3]).cpu()                # H2D of every input + forward + D2H of the result, every step
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms2 = e0.elapsed_time(e1)
+    h2d = sum(v.numel() * v.element_size() for v in batches[0].values() if torch.is_tensor(v))
+    pk = peaks()
+    g = prof["gemm"]
+    executed = sum(prof[k]["work"] for k in ("gemm", "gemm_ln", "attention", "lm_head"))
+    tfl = executed / (ms_total * 1e-3) / 1e12
+    achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    names = {"train_fwd": "configs[2]: train.py UniMM-UL step forward + loss, batch 240 = 40 images x 6 sequences (1 positive + 5 negatives), "
+                          "mixed generative / discriminative masks, mask_prob 0.15, unlikelihood on the negatives",
+             "dis_nsp": "configs[3]: discriminative NSP scoring of one image = 10 rounds x 100 options (val.py path), chunks of 250",
+             "dense_ft": "configs[4]: dense_annotation_finetuning.py forward + loss, the 100 options of one annotated round (batch 100), "
+                         "relevance-weighted L / UL + NSP CE + NeuralNDCG"}
+    line = {"metric": "sequences_per_sec", "value": args.steps * B / (ms_total * 1e-3), "unit": "sequences/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": names[wl], "sequences_per_step": B, "layout": "dense (256 rows per sequence)", "seq_len": 256, "regions": 37,
+                       "model": "bert_base_6layer_6conect, random init (seed 0)", "result_of_last_step": [float(x) for x in res.flatten()[:4].tolist()]},
+            "pct_of_bf16_peak": {"executed_tflops": tfl, "burst": tfl / pk["burst"], "sustained": tfl / pk["sustained"], "peaks": pk["source"]},
+            "e2e": {"value": args.steps * B / (ms2 * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(host_res.numel() * 4)},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "umma_gemm_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["sustained"], "traffic": None,
+                         "share_of_step": {k: round(v["ms"] / ms_total, 4) for k, v in prof.items()}},
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main_ours(args):
     import torch.distributed as dist
     from unimm_b200.config import DEFAULT_CONFIG_PATH, ViLBertConfig
@@ -590,7 +731,8 @@ if __name__ == "__main__":
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: cuda = the eager-PyTorch-on-B200 bar (extra; the driver's arm is cpu)")
     ap.add_argument("--ref-mode", default="tf32", choices=["tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="steps", choices=["steps", "sweep"], help="sweep = the whole configs[1] sweep, strong-scaled (see the docstring)")
+    ap.add_argument("--workload", default="steps", choices=["steps", "sweep", "train_fwd", "dis_nsp", "dense_ft"],
+                    help="sweep = the whole configs[1] sweep, strong-scaled; train_fwd / dis_nsp / dense_ft = configs 3 / 4 / 5 at their stated sizes (1 GPU)")
     ap.add_argument("--images", type=int, default=2064, help="--workload sweep: images of the sweep")
     ap.add_argument("--no-verify", action="store_true", help="skip the per-step context-equality check of the packer")
     ap.add_argument("--no-bf16", action="store_true", help="fp16 runs: skip the nested bf16_mode measurement")
@@ -600,5 +742,7 @@ if __name__ == "__main__":
         main_reference(a)
     elif a.workload == "sweep":
         main_sweep(a)
+    elif a.workload in ("train_fwd", "dis_nsp", "dense_ft"):
+        main_dense_workload(a)
     else:
         main_ours(a)

@@ -111,7 +111,19 @@ struct unimm_engine {
     LayerNormP emb_ln, vemb_ln, lm_ln, img_ln;
     Linear img_emb, lm_transform, lm_decoder, img_transform, img_decoder;
     const float *loc_w = nullptr, *loc_b = nullptr;
-    const float *tp_w = nullptr, *tp_b = nullptr, *vp_w = nullptr, *vp_b = nullptr, *nsp_w = nullptr, *nsp_b = nullptr;
+    const float *nsp_w = nullptr, *nsp_b = nullptr;
+    // poolers (ref :946-967): Linear + ReLU on the [CLS] / global-image rows, as fp32-class tcgen05 GEMMs in EVERY precision mode
+    // (fp16 hi | lo planes of the fp32 stream and of the weights, three passes: the pooled NSP logit keeps its fp32-level accuracy)
+    Linear t_pool, v_pool;
+    bf16* pool_split = nullptr;        // [pool_cap, 2 * max(H, Hv)] planes of the pooled rows
+    float *pool_t = nullptr, *pool_v = nullptr;   // [pool_cap, Hb]
+    int pool_cap = 0;
+    int make_pool_linear(const std::string& name, int N, int K, Linear* L);
+    // text row of sequence i: t_rows ? t_rows[i] : i * t_stride (same for the image rows)
+    int pooler_head(const float* xt_f, int ldt, const int* t_rows, int t_stride, const float* xv_f, int ldv, const int* v_rows, int v_stride,
+                    int n, float* nsp, cudaStream_t st);
+    int* seq_rows_t = nullptr;         // [Bmax] b * S
+    int* seq_rows_v = nullptr;         // [Bmax] b * R
     std::vector<SelfLayer> t_layers, v_layers;
     std::vector<ConnLayer> c_layers;
 
@@ -185,6 +197,13 @@ struct unimm_engine {
     bool tc32_ = false;
     bool tc32() const { return tc32_; }
     int act_kind() const { return tc32() ? LP_HILO : lp_kind(); }      // what the LayerNorm / embedding kernels write next to fp32
+    // dense layout in the fp32-class mode: job lists / per-row intervals built from the descriptors (attention_split.cu)
+    int *dj_text = nullptr, *dj_i2t = nullptr, *dj_img = nullptr, *dj_row_iv = nullptr;
+    // attention over fp16 hi | lo planes: q / k / v point at hi planes of rows `ld` wide whose lo plane lies lo_in columns further;
+    // the context goes to o (rows ldo wide, lo plane lo_out further)
+    int attention_split(const bf16* q, const bf16* k, const bf16* v, int ld_q, int lo_q, int ld_kv, int lo_kv, bf16* o, int ldo, int lo_out,
+                        int heads, int D, const int* jobs, int n_jobs, int max_q, const int* row_iv, const float* key_mask, int key_mask_ld,
+                        double qk_pairs, cudaStream_t st);
     bf16* split_scratch = nullptr;     // [rows, 2K] planes of an fp32 operand that no producer wrote as planes
     size_t split_cap = 0;
 
@@ -203,7 +222,7 @@ struct unimm_engine {
 
     // y = act(x W^T + b) (+ residual); x/y selected by mode
     int linear(const ActBuf& x, int M, const Linear& L, int act, const float* residual, int ldr, float* out_f32, int ldo_f32,
-               void* out_lp, int ldo_lp, cudaStream_t st, bool out_hilo = false);
+               void* out_lp, int ldo_lp, cudaStream_t st, int hilo_off = 0);     // hilo_off > 0: fp16 hi | lo planes, lo plane hilo_off columns further
     // out = LayerNorm(x W^T + b + residual): one cluster-fused kernel in the 16-bit modes, GEMM + LayerNorm kernel otherwise
     int linear_ln(const ActBuf& x, int M, const Linear& L, const float* residual, int ldr, const LayerNormP& ln, float* pre,
                   ActBuf& out, cudaStream_t st);
@@ -314,6 +333,44 @@ int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each,
     return 0;
 }
 
+int unimm_engine::make_pool_linear(const std::string& name, int N, int K, Linear* L) {
+    const DevTensor *tw, *tb;
+    UNIMM_TRY(get(name + ".weight", &tw, {N, K}));
+    UNIMM_TRY(get(name + ".bias", &tb, {N}));
+    UNIMM_CHECK(K % 64 == 0, "pooler input width must be a multiple of 64");
+    L->N = N; L->K = K; L->w32 = tw->p; L->b = tb->p;
+    bf16* h = nullptr;
+    UNIMM_TRY(dalloc(&h, static_cast<size_t>(N) * 2 * K));
+    UNIMM_TRY(split_f32_to_hilo(tw->p, K, N, K, h, 0));
+    L->wlp = h;
+    return 0;
+}
+
+// poolers + NSP head: pooled = relu(W x_row + b) for the text and the image row of each sequence as two split3 GEMMs (M = n),
+// then nsp = Wn (pooled_t * pooled_v) + bn
+int unimm_engine::pooler_head(const float* xt_f, int ldt, const int* t_rows, int t_stride, const float* xv_f, int ldv, const int* v_rows,
+                              int v_stride, int n, float* nsp, cudaStream_t st) {
+    const int Hb = cfg.bi_hidden_size;
+    UNIMM_CHECK(t_rows != nullptr || t_stride == cfg.seq_len, "pooler: dense rows are b * S");
+    for (int s0 = 0; s0 < n; s0 += pool_cap) {
+        const int m = std::min(pool_cap, n - s0);
+        for (int side = 0; side < 2; ++side) {
+            const Linear& L = side == 0 ? t_pool : v_pool;
+            const float* x = side == 0 ? xt_f : xv_f;
+            const int ld = side == 0 ? ldt : ldv;
+            const int* rows = side == 0 ? t_rows : v_rows;
+            const int* rows_dense = side == 0 ? seq_rows_t : seq_rows_v;
+            UNIMM_TRY(split_f32_to_hilo(x, ld, m, L.K, pool_split, st, rows != nullptr ? rows + s0 : rows_dense + s0));
+            GemmEpilogue ep;
+            ep.bias = L.b; ep.act = ACT_RELU; ep.lp_kind = LP_FP16; ep.split3 = 1;
+            ep.out_f32 = side == 0 ? pool_t : pool_v; ep.ldo_f32 = Hb;
+            UNIMM_TRY(gemm_umma_bf16(pool_split, 2 * L.K, L.wlp, 2 * L.K, m, Hb, L.K, ep, 0, 0, st));
+        }
+        UNIMM_TRY(nsp_from_pooled(pool_t, pool_v, m, Hb, nsp_w, nsp_b, nsp + static_cast<size_t>(s0) * 2, st));
+    }
+    return 0;
+}
+
 // second 16-bit copy of a weight whose output feeds a residual + LayerNorm, in the row order the fused kernel wants
 int unimm_engine::make_ln_weight(Linear* L) {
     if (!lp() || !fuse_ln || L->wlp == nullptr || (L->N != 768 && L->N != 1024) || L->K % 64 != 0) return 0;
@@ -378,10 +435,8 @@ int unimm_engine::finalize() {
         UNIMM_TRY(make_linear({p + "t_output.dense"}, H, I, &L.t_ffn2));
         UNIMM_TRY(make_ln(p + "t_output.LayerNorm", H, &L.t_ln));
     }
-    UNIMM_TRY(get("bert.t_pooler.dense.weight", &t, {Hb, H})); tp_w = t->p;
-    UNIMM_TRY(get("bert.t_pooler.dense.bias", &t, {Hb})); tp_b = t->p;
-    UNIMM_TRY(get("bert.v_pooler.dense.weight", &t, {Hb, Hv})); vp_w = t->p;
-    UNIMM_TRY(get("bert.v_pooler.dense.bias", &t, {Hb})); vp_b = t->p;
+    UNIMM_TRY(make_pool_linear("bert.t_pooler.dense", Hb, H, &t_pool));
+    UNIMM_TRY(make_pool_linear("bert.v_pooler.dense", Hb, Hv, &v_pool));
     UNIMM_TRY(get("cls.bi_seq_relationship.weight", &t, {2, Hb})); nsp_w = t->p;
     UNIMM_TRY(get("cls.bi_seq_relationship.bias", &t, {2})); nsp_b = t->p;
 
@@ -446,6 +501,10 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&xk.f, Mt * H)); xk.ld = H;
     if (lp() || tc32()) UNIMM_TRY(dalloc(&xk.h, Mt * H * planes));
     if (tc32()) {
+        UNIMM_TRY(dalloc(&dj_text, static_cast<size_t>(Bmax) * 8));
+        UNIMM_TRY(dalloc(&dj_i2t, static_cast<size_t>(Bmax) * 8));
+        UNIMM_TRY(dalloc(&dj_img, static_cast<size_t>(Bmax) * 8));
+        UNIMM_TRY(dalloc(&dj_row_iv, Mt * 4));
         split_cap = std::max(Mt * 2 * static_cast<size_t>(std::max(std::max(H, Hb), Hv)), Mv * 2 * static_cast<size_t>(std::max(c.v_feature_size, std::max(Hv, Hb))));
         UNIMM_TRY(dalloc(&split_scratch, split_cap));
     }
@@ -477,6 +536,18 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&vhead_h.f, Mv * Hv));
     if (lp() || tc32()) UNIMM_TRY(dalloc(&vhead_h.h, Mv * Hv * planes));
     UNIMM_TRY(dalloc(&v_logits, Mv * c.v_target_size));
+    {
+        pool_cap = std::max(Bmax, 2048);
+        UNIMM_TRY(dalloc(&pool_split, static_cast<size_t>(pool_cap) * 2 * std::max(H, Hv)));
+        UNIMM_TRY(dalloc(&pool_t, static_cast<size_t>(pool_cap) * Hb));
+        UNIMM_TRY(dalloc(&pool_v, static_cast<size_t>(pool_cap) * Hb));
+        std::vector<int> rt(pool_cap), rv(pool_cap);
+        for (int b = 0; b < pool_cap; ++b) { rt[b] = b * c.seq_len; rv[b] = b * c.num_regions; }
+        UNIMM_TRY(dalloc(&seq_rows_t, pool_cap));
+        UNIMM_TRY(dalloc(&seq_rows_v, pool_cap));
+        UNIMM_CUDA_CHECK(cudaMemcpy(seq_rows_t, rt.data(), sizeof(int) * pool_cap, cudaMemcpyHostToDevice));
+        UNIMM_CUDA_CHECK(cudaMemcpy(seq_rows_v, rv.data(), sizeof(int) * pool_cap, cudaMemcpyHostToDevice));
+    }
     UNIMM_TRY(dalloc(&err_flag, 4));
     UNIMM_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_err), 4 * sizeof(int)));
     h_err[0] = 0;
@@ -493,7 +564,8 @@ int unimm_engine::alloc_workspace() {
 }
 
 int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const float* residual, int ldr, float* out_f32,
-                         int ldo_f32, void* out_lp, int ldo_lp, cudaStream_t st, bool out_hilo) {
+                         int ldo_f32, void* out_lp, int ldo_lp, cudaStream_t st, int hilo_off) {
+    const bool out_hilo = hilo_off > 0;
     GemmEpilogue ep;
     ep.bias = L.b;
     ep.residual = residual;
@@ -520,7 +592,7 @@ int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const
     UNIMM_CHECK(!(out_f32 && out_lp), "fp32 mode writes one output");
     if (out_hilo) {
         UNIMM_CHECK(tc32() && out_lp != nullptr, "hi | lo output is the fp32-class tensor-core mode's");
-        ep.out_bf16 = static_cast<bf16*>(out_lp); ep.ldo_bf16 = 2 * ldo_lp; ep.out_hilo = true;
+        ep.out_bf16 = static_cast<bf16*>(out_lp); ep.ldo_bf16 = 2 * ldo_lp; ep.out_hilo = true; ep.hilo_off = hilo_off;
     } else {
         ep.out_f32 = out_f32 ? out_f32 : static_cast<float*>(out_lp);
         ep.ldo_f32 = out_f32 ? ldo_f32 : ldo_lp;
@@ -592,6 +664,19 @@ int unimm_engine::attention(const void* q, int ldq, const void* k, int ldk, cons
     return lp() ? attention_mma_lp(a, st) : attention_simt_f32(a, st);
 }
 
+int unimm_engine::attention_split(const bf16* q, const bf16* k, const bf16* v, int ld_q, int lo_q, int ld_kv, int lo_kv, bf16* o, int ldo,
+                                  int lo_out, int heads, int D, const int* jobs, int n_jobs, int max_q, const int* row_iv,
+                                  const float* key_mask, int key_mask_ld, double qk_pairs, cudaStream_t st) {
+    AttnJobsArgs a;
+    a.q = q; a.ldq = ld_q; a.k = k; a.ldk = ld_kv; a.v = v; a.ldv = ld_kv; a.o = o; a.ldo = ldo;
+    a.lo_off_q = lo_q; a.lo_off_k = lo_kv; a.lo_off_v = lo_kv; a.lo_off_o = lo_out;
+    a.heads = heads; a.D = D; a.jobs = jobs; a.n_jobs = n_jobs; a.max_q_len = max_q; a.kv_cap = 256; a.win_cap = 256;
+    a.row_iv = row_iv; a.key_mask = key_mask; a.key_mask_ld = key_mask_ld;
+    a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = LP_FP16;
+    Prof prof(this, CAT_ATTN, 4.0 * heads * D * qk_pairs, st);
+    return attention_jobs_split(a, st);
+}
+
 int unimm_engine::attention_packed(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int heads,
                                    int D, const int* jobs, int n_jobs, int max_q, int kv_cap, int win_cap, double qk_pairs,
                                    const AttnCtx& ac, cudaStream_t st) {
@@ -613,6 +698,43 @@ int unimm_engine::self_layer(const SelfLayer& L, ActBuf& x_in, float* pre, void*
     const int M = M_in;
     const int H = x.ld, D = H / heads;
     const size_t e = esz();
+    if (tc32()) {
+        // fp32-class mode: Q | K | V as fp16 hi | lo planes ([M, 6H]: hi planes in columns [0, 3H), lo planes 3H further) straight
+        // from the split3 GEMM, attention as three mma.sync passes per product, context out as planes [M, 2H]
+        UNIMM_TRY(linear(x, M, L.qkv, ACT_NONE, nullptr, 0, nullptr, 0, qkv, 3 * H, st, 3 * H));
+        const bf16* q16 = static_cast<const bf16*>(qkv);
+        bf16* c16 = static_cast<bf16*>(ctx);
+        const int S = cfg.seq_len, R = cfg.num_regions;
+        if (ac.pk != nullptr) {
+            const unimm_packed_batch_t& pk = *ac.pk;
+            if (text) UNIMM_TRY(attention_split(q16, q16 + H, q16 + 2 * H, 6 * H, 3 * H, 6 * H, 3 * H, c16, 2 * H, H, heads, D, pk.d_jobs_text_self,
+                                                pk.n_jobs_text_self, pk.max_q_text_self, pk.d_row_iv, nullptr, 0, pk.pairs_text_self, st));
+            else UNIMM_TRY(attention_split(q16, q16 + H, q16 + 2 * H, 6 * H, 3 * H, 6 * H, 3 * H, c16, 2 * H, H, heads, D, pk.d_jobs_img_self,
+                                           pk.n_jobs_img_self, R, nullptr, pk.d_image_mask, R, static_cast<double>(pk.n_units) * R * R, st));
+        } else {
+            if (text) UNIMM_TRY(attention_split(q16, q16 + H, q16 + 2 * H, 6 * H, 3 * H, 6 * H, 3 * H, c16, 2 * H, H, heads, D, dj_text, ac.B, S,
+                                                dj_row_iv, nullptr, 0, static_cast<double>(ac.B) * S * S, st));
+            else UNIMM_TRY(attention_split(q16, q16 + H, q16 + 2 * H, 6 * H, 3 * H, 6 * H, 3 * H, c16, 2 * H, H, heads, D, dj_img, ac.B, R, nullptr,
+                                           ac.key_mask, R, static_cast<double>(ac.B) * R * R, st));
+        }
+        ActBuf c;
+        c.f = nullptr; c.h = c16; c.ld = H;
+        if (keep_rows != nullptr) {
+            UNIMM_CHECK(x_keep != nullptr && n_keep > 0 && n_keep <= M, "self_layer: bad row subset");
+            ActBuf cc;
+            cc.f = nullptr; cc.h = static_cast<bf16*>(ffn); cc.ld = H;
+            {
+                Prof prof(this, CAT_ROWWISE, 16.0 * n_keep * H, st);
+                UNIMM_TRY(gather_rows(nullptr, c.h, keep_rows, n_keep, 2 * H, nullptr, cc.h, st));      // both planes of a row
+                UNIMM_TRY(gather_rows(x.f, nullptr, keep_rows, n_keep, H, x_keep->f, nullptr, st));
+            }
+            // the FFN-1 planes of the kept rows go behind their context planes (n_keep <= M / 2 is not guaranteed: use pre's tail? no —
+            // ffn holds [M, 2I] planes; the kept context occupies its first n_keep * 2H elements, which FFN-1 overwrites only
+            // after the output projection has consumed them)
+            return self_layer_tail(L, cc, *x_keep, pre, ffn, n_keep, st);
+        }
+        return self_layer_tail(L, c, x, pre, ffn, M, st);
+    }
     UNIMM_TRY(linear(x, M, L.qkv, ACT_NONE, nullptr, 0, nullptr, 0, qkv, 3 * H, st));
     const void *qp = qkv, *kp = byte_ptr(qkv) + e * H, *vp = byte_ptr(qkv) + e * 2 * H;
     if (ac.pk != nullptr) {
@@ -680,7 +802,7 @@ int unimm_engine::self_layer_tail(const SelfLayer& L, const ActBuf& c, ActBuf& x
     const int H = x.ld;
     UNIMM_TRY(linear_ln(c, M, L.out, x.f, H, L.ln1, pre, x, st));
     const int I = L.ffn1.N;
-    UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st, tc32()));
+    UNIMM_TRY(linear(x, M, L.ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn, I, st, tc32() ? I : 0));
     ActBuf f;
     const bool f16 = lp() || tc32();            // tc32: the GELU output exists as hi | lo planes only
     f.f = f16 ? nullptr : static_cast<float*>(ffn); f.h = f16 ? static_cast<bf16*>(ffn) : nullptr; f.ld = I;
@@ -693,15 +815,16 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
     const unimm_config_t& c = cfg;
     const int S = c.seq_len, R = c.num_regions, H = c.hidden_size, Hv = c.v_hidden_size, Hb = c.bi_hidden_size;
     const int heads = c.bi_num_attention_heads, D = Hb / heads;
-    const size_t e = esz();
-    UNIMM_TRY(linear(xv, Mv, L.qkv_v, ACT_NONE, nullptr, 0, nullptr, 0, qkv_v, 3 * Hb, st));
+    const size_t e = tc32() ? 2 : esz();             // fp32-class mode: Q | K | V live as fp16 planes, hi in [0, 3Hb), lo 3Hb further
+    const int pl = tc32() ? 3 * Hb : 0;             // lo-plane offset handed to the projections
+    UNIMM_TRY(linear(xv, Mv, L.qkv_v, ACT_NONE, nullptr, 0, nullptr, 0, qkv_v, 3 * Hb, st, pl));
     const int n_sh = (ac.pk != nullptr && kv2_ctx_only) ? ac.pk->n_shared_rows : 0;
     UNIMM_CHECK(image_out || ac.pk != nullptr, "conn_layer: the image update can only be skipped in the packed layout");
     if (!image_out) {
         // nothing reads this layer's image output (scores-only batch, last connection): no image queries, hence no K2 | V2 at all
         Linear q2 = L.qkv_t;
         q2.N = Hb;
-        UNIMM_TRY(linear(xt, Mt, q2, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
+        UNIMM_TRY(linear(xt, Mt, q2, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st, pl));
     } else if (n_sh > 0 && n_sh < Mt && L.qkv_t.w32 != nullptr) {
         // prefix-shared layout: the image rows attend ONLY the context rows (co-mask [1,ctx), utils/data_utils.py:199-210), so the
         // text-side keys / values K2 | V2 (:670-672) of the candidate rows — 86 % of the text rows — are never read: project the
@@ -713,11 +836,27 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
         kv2.w32 = L.qkv_t.w32 + off; kv2.b = L.qkv_t.b + Hb;
         if (L.qkv_t.wlp) kv2.wlp = L.qkv_t.wlp + (tc32() ? 2 * off : off);
         if (L.qkv_t.wlp_p16) kv2.wlp_p16 = L.qkv_t.wlp_p16 + off;
-        UNIMM_TRY(linear(xt, Mt, q2, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
-        UNIMM_TRY(linear(xt, n_sh, kv2, ACT_NONE, nullptr, 0, nullptr, 0, byte_ptr(qkv_t) + e * Hb, 3 * Hb, st));
+        UNIMM_TRY(linear(xt, Mt, q2, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st, pl));
+        UNIMM_TRY(linear(xt, n_sh, kv2, ACT_NONE, nullptr, 0, nullptr, 0, byte_ptr(qkv_t) + e * Hb, 3 * Hb, st, pl));
     } else {
-        UNIMM_TRY(linear(xt, Mt, L.qkv_t, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st));
+        UNIMM_TRY(linear(xt, Mt, L.qkv_t, ACT_NONE, nullptr, 0, nullptr, 0, qkv_t, 3 * Hb, st, pl));
     }
+    if (tc32()) {
+        const bf16 *qt = static_cast<const bf16*>(qkv_t), *qv = static_cast<const bf16*>(qkv_v);
+        bf16 *ct16 = static_cast<bf16*>(ctx_t), *cv16 = static_cast<bf16*>(ctx_v);
+        if (ac.pk != nullptr) {
+            const unimm_packed_batch_t& pk = *ac.pk;
+            UNIMM_TRY(attention_split(qt, qv + Hb, qv + 2 * Hb, 6 * Hb, 3 * Hb, 6 * Hb, 3 * Hb, ct16, 2 * Hb, Hb, heads, D, pk.d_jobs_t2i, pk.n_jobs_t2i,
+                                      pk.max_q_t2i, nullptr, pk.d_image_mask, R, static_cast<double>(Mt) * R, st));
+            if (image_out) UNIMM_TRY(attention_split(qv, qt + Hb, qt + 2 * Hb, 6 * Hb, 3 * Hb, 6 * Hb, 3 * Hb, cv16, 2 * Hb, Hb, heads, D, pk.d_jobs_i2t,
+                                                     pk.n_jobs_i2t, R, nullptr, nullptr, 0, pk.pairs_i2t, st));
+        } else {
+            UNIMM_TRY(attention_split(qt, qv + Hb, qv + 2 * Hb, 6 * Hb, 3 * Hb, 6 * Hb, 3 * Hb, ct16, 2 * Hb, Hb, heads, D, dense_jobs, ac.B, S, nullptr,
+                                      ac.key_mask, R, static_cast<double>(Mt) * R, st));
+            UNIMM_TRY(attention_split(qv, qt + Hb, qt + 2 * Hb, 6 * Hb, 3 * Hb, 6 * Hb, 3 * Hb, cv16, 2 * Hb, Hb, heads, D, dj_i2t, ac.B, R, nullptr,
+                                      nullptr, 0, static_cast<double>(Mv) * S, st));
+        }
+    } else
     if (ac.pk != nullptr) {
         const unimm_packed_batch_t& pk = *ac.pk;
         // text queries (shared + candidate rows of a unit) over the unit's image keys/values (:681-698)
@@ -737,20 +876,21 @@ int unimm_engine::conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& 
                             D, R, S, MASK_CO_INTERVAL, ac.desc, nullptr, st));
     }
     ActBuf cv, ct;
-    cv.f = lp() ? nullptr : static_cast<float*>(ctx_v); cv.h = lp() ? static_cast<bf16*>(ctx_v) : nullptr; cv.ld = Hb;
-    ct.f = lp() ? nullptr : static_cast<float*>(ctx_t); ct.h = lp() ? static_cast<bf16*>(ctx_t) : nullptr; ct.ld = Hb;
+    const bool c16 = lp() || tc32();                // tc32: the contexts are fp16 hi | lo planes
+    cv.f = c16 ? nullptr : static_cast<float*>(ctx_v); cv.h = c16 ? static_cast<bf16*>(ctx_v) : nullptr; cv.ld = Hb;
+    ct.f = c16 ? nullptr : static_cast<float*>(ctx_t); ct.h = c16 ? static_cast<bf16*>(ctx_t) : nullptr; ct.ld = Hb;
     // BertBiOutput (:744-754): image rows take the image-query context through dense1, text rows the other through dense2
     if (image_out) UNIMM_TRY(linear_ln(cv, Mv, L.dense1, xv.f, Hv, L.ln1, pre_v, xv, st));
     UNIMM_TRY(linear_ln(ct, Mt, L.dense2, xt.f, H, L.ln2, pre_t, xt, st));
     // image FFN, text FFN (:777-781)
     const int Iv = L.v_ffn1.N, I = L.t_ffn1.N;
     if (image_out) {
-        UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st, tc32()));
+        UNIMM_TRY(linear(xv, Mv, L.v_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_v, Iv, st, tc32() ? Iv : 0));
         ActBuf fv;
         fv.f = (lp() || tc32()) ? nullptr : static_cast<float*>(ffn_v); fv.h = (lp() || tc32()) ? static_cast<bf16*>(ffn_v) : nullptr; fv.ld = Iv;
         UNIMM_TRY(linear_ln(fv, Mv, L.v_ffn2, xv.f, Hv, L.v_ln, pre_v, xv, st));
     }
-    UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st, tc32()));
+    UNIMM_TRY(linear(xt, Mt, L.t_ffn1, ACT_GELU, nullptr, 0, nullptr, 0, ffn_t, I, st, tc32() ? I : 0));
     ActBuf ft;
     ft.f = (lp() || tc32()) ? nullptr : static_cast<float*>(ffn_t); ft.h = (lp() || tc32()) ? static_cast<bf16*>(ffn_t) : nullptr; ft.ld = I;
     UNIMM_TRY(linear_ln(ft, Mt, L.t_ffn2, xt.f, H, L.t_ln, pre_t, xt, st));
@@ -788,6 +928,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
         key_mask = km;
     }
 
+    if (tc32()) UNIMM_TRY(build_dense_jobs(desc, B, S, R, dj_text, dj_i2t, dj_img, dj_row_iv, st));
     // ---- encoder schedule (reference :842-929)
     AttnCtx ac;
     ac.B = B; ac.desc = desc; ac.key_mask = key_mask;
@@ -803,7 +944,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
     float* nsp = out.d_nsp_scores;
     if (nsp == nullptr && training) nsp = label_logit;  // scratch (B*2 <= Mt)
     if (nsp != nullptr)
-        UNIMM_TRY(pooler_nsp(xt.f, S * H, xv.f, R * Hv, B, H, Hv, c.bi_hidden_size, tp_w, tp_b, vp_w, vp_b, nsp_w, nsp_b, nsp, st));
+        UNIMM_TRY(pooler_head(xt.f, H, nullptr, S, xv.f, Hv, nullptr, R, B, nsp, st));
     if (training && out.d_losses)
         UNIMM_TRY(nsp_ce_loss(nsp, in.d_next_sentence_label, B, in.d_nsp_weight, out.d_losses + 2, st));
 
@@ -983,8 +1124,7 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
     n_keep_ = dedup ? in.n_lm_unique : n;
     UNIMM_TRY(run_encoder(M, Mv, ac, st));
     if (d_nsp_scores)
-        UNIMM_TRY(pooler_nsp_indexed(xt.f, H, in.d_cand_cls_row, xv.f, Hv, in.d_cand_img_row, C, H, Hv, c.bi_hidden_size, tp_w, tp_b, vp_w, vp_b,
-                                     nsp_w, nsp_b, d_nsp_scores, st));
+        UNIMM_TRY(pooler_head(xt.f, H, in.d_cand_cls_row, 0, xv.f, Hv, in.d_cand_img_row, 0, C, d_nsp_scores, st));
     if (n > 0) {
         if (dedup) UNIMM_TRY(lm_head_shared(xk_live ? xk : xt, xk_live ? nullptr : in.d_lm_urows, in.n_lm_unique, in.d_lm_uidx, in.d_lm_labels, n, st));
         else if (xk_live) UNIMM_TRY(lm_head_rows(xk, nullptr, in.d_lm_labels, n, st));       // the last text layer already gathered them

@@ -452,7 +452,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 split_hilo2(y[i].x, y[i].y, hi.x, lo.x);
                                 split_hilo2(y[i].z, y[i].w, hi.y, lo.y);
                                 *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + cc) = hi;
-                                *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + N + cc) = lo;
+                                *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + (ep.hilo_off > 0 ? ep.hilo_off : N) + cc) = lo;
                             } else if (ep.out_bf16 != nullptr) {
                                 uint2 pk;
                                 pk.x = pack_lp2(y[i].x, y[i].y, ep.lp_kind);
@@ -682,8 +682,9 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     UNIMM_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "umma gemm: K must be a positive multiple of 64");
     const bool lse = ep.partials != nullptr;
     UNIMM_CHECK(!ep.split3 || (!lse && !ep.w_perm16 && ep.lp_kind == LP_FP16), "split3 takes fp16 hi | lo planes and the plain epilogue");
-    UNIMM_CHECK(!ep.out_hilo || (ep.out_bf16 != nullptr && N % 32 == 0 && (ep.ldo_bf16 & 3) == 0 && ep.ldo_bf16 >= 2 * N),
-                "hi | lo output needs N % 32 == 0 and a [M, 2N] 16-bit matrix");
+    UNIMM_CHECK(!ep.out_hilo || (ep.out_bf16 != nullptr && N % 32 == 0 && (ep.ldo_bf16 & 3) == 0 && (ep.hilo_off & 3) == 0 &&
+                                 ep.ldo_bf16 >= (ep.hilo_off > 0 ? ep.hilo_off : N) + N && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0),
+                "hi | lo output needs N % 32 == 0 and 8-byte aligned planes inside the row");
     if (tile_n == 0) tile_n = (N % 256 == 0 || N > 2048) ? 256 : 128;
     // tall problems (every SM gets several row blocks): CTA pairs sharing the W tile by TMA multicast
     // UNIMM_GEMM_MULTICAST: 0 = independent CTAs, 1 = CTA pairs sharing W by multicast, 2 = CTA pairs as one cta_group::2 MMA

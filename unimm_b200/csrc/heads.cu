@@ -32,75 +32,27 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
     return scratch[0];
 }
 
-// one CTA per sequence: pooled_t = relu(Wt x_t[b,0] + bt), pooled_v = relu(Wv x_v[b,0] + bv),
-// nsp = Wn (pooled_t * pooled_v) + bn   (reference models/vilbert_dialog.py:946-967, :1065-1070)
-__global__ void __launch_bounds__(256)
-pooler_nsp_kernel(const float* __restrict__ xt, int ldt_seq, const float* __restrict__ xv, int ldv_seq, int Ht, int Hv, int Hb,
-                  const float* __restrict__ Wt, const float* __restrict__ bt, const float* __restrict__ Wv,
-                  const float* __restrict__ bv, const float* __restrict__ Wn, const float* __restrict__ bn,
-                  float* __restrict__ nsp) {
-    extern __shared__ float sm[];
-    float* st = sm;            // [Ht]
-    float* sv = st + Ht;       // [Hv]
-    float* sz = sv + Hv;       // [Hb]
-    __shared__ float scratch[32];
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-    for (int i = tid; i < Ht; i += blockDim.x) st[i] = xt[static_cast<size_t>(b) * ldt_seq + i];
-    for (int i = tid; i < Hv; i += blockDim.x) sv[i] = xv[static_cast<size_t>(b) * ldv_seq + i];
-    __syncthreads();
-    for (int j = warp; j < Hb; j += nw) {
-        float a = 0.f, c = 0.f;
-        const float* wt = Wt + static_cast<size_t>(j) * Ht;
-        const float* wv = Wv + static_cast<size_t>(j) * Hv;
-        for (int i = lane; i < Ht; i += 32) a = fmaf(__ldg(wt + i), st[i], a);
-        for (int i = lane; i < Hv; i += 32) c = fmaf(__ldg(wv + i), sv[i], c);
-        a = warp_sum(a);
-        c = warp_sum(c);
-        if (lane == 0) sz[j] = fmaxf(a + bt[j], 0.f) * fmaxf(c + bv[j], 0.f);
+// NSP head (reference models/vilbert_dialog.py:1062-1070, fusion 'mul'): one warp per sequence over the pooled vectors the two
+// pooler GEMMs produced (engine.cu: pooler_head)
+__global__ void __launch_bounds__(128)
+nsp_from_pooled_kernel(const float* __restrict__ pt, const float* __restrict__ pv, int n, int Hb, const float* __restrict__ Wn,
+                       const float* __restrict__ bn, float* __restrict__ nsp) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= n) return;
+    const float4* t = reinterpret_cast<const float4*>(pt + static_cast<size_t>(b) * Hb);
+    const float4* v = reinterpret_cast<const float4*>(pv + static_cast<size_t>(b) * Hb);
+    const float4* w0 = reinterpret_cast<const float4*>(Wn);
+    const float4* w1 = reinterpret_cast<const float4*>(Wn + Hb);
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = lane; i < Hb / 4; i += 32) {
+        const float4 x = t[i], y = v[i], p = __ldg(w0 + i), q = __ldg(w1 + i);
+        const float zx = x.x * y.x, zy = x.y * y.y, zz = x.z * y.z, zw = x.w * y.w;
+        a0 = fmaf(zx, p.x, a0); a0 = fmaf(zy, p.y, a0); a0 = fmaf(zz, p.z, a0); a0 = fmaf(zw, p.w, a0);
+        a1 = fmaf(zx, q.x, a1); a1 = fmaf(zy, q.y, a1); a1 = fmaf(zz, q.z, a1); a1 = fmaf(zw, q.w, a1);
     }
-    __syncthreads();
-    for (int o = 0; o < 2; ++o) {
-        float a = 0.f;
-        for (int i = tid; i < Hb; i += blockDim.x) a = fmaf(__ldg(Wn + o * Hb + i), sz[i], a);
-        a = block_sum(a, scratch);
-        if (tid == 0) nsp[b * 2 + o] = a + bn[o];
-    }
-}
-
-// packed-layout variant: explicit row indices for the pooled text / image rows
-__global__ void __launch_bounds__(256)
-pooler_nsp_indexed_kernel(const float* __restrict__ xt, int ldt, const int* __restrict__ cls_row, const float* __restrict__ xv,
-                          int ldv, const int* __restrict__ img_row, int Ht, int Hv, int Hb, const float* __restrict__ Wt,
-                          const float* __restrict__ bt, const float* __restrict__ Wv, const float* __restrict__ bv,
-                          const float* __restrict__ Wn, const float* __restrict__ bn, float* __restrict__ nsp) {
-    extern __shared__ float sm[];
-    float* st = sm;
-    float* sv = st + Ht;
-    float* sz = sv + Hv;
-    __shared__ float scratch[32];
-    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-    const float* rt = xt + static_cast<size_t>(cls_row[c]) * ldt;
-    const float* rv = xv + static_cast<size_t>(img_row[c]) * ldv;
-    for (int i = tid; i < Ht; i += blockDim.x) st[i] = rt[i];
-    for (int i = tid; i < Hv; i += blockDim.x) sv[i] = rv[i];
-    __syncthreads();
-    for (int j = warp; j < Hb; j += nw) {
-        float a = 0.f, d = 0.f;
-        const float* wt = Wt + static_cast<size_t>(j) * Ht;
-        const float* wv = Wv + static_cast<size_t>(j) * Hv;
-        for (int i = lane; i < Ht; i += 32) a = fmaf(__ldg(wt + i), st[i], a);
-        for (int i = lane; i < Hv; i += 32) d = fmaf(__ldg(wv + i), sv[i], d);
-        a = warp_sum(a);
-        d = warp_sum(d);
-        if (lane == 0) sz[j] = fmaxf(a + bt[j], 0.f) * fmaxf(d + bv[j], 0.f);
-    }
-    __syncthreads();
-    for (int o = 0; o < 2; ++o) {
-        float a = 0.f;
-        for (int i = tid; i < Hb; i += blockDim.x) a = fmaf(__ldg(Wn + o * Hb + i), sz[i], a);
-        a = block_sum(a, scratch);
-        if (tid == 0) nsp[c * 2 + o] = a + bn[o];
-    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) { nsp[b * 2] = a0 + bn[0]; nsp[b * 2 + 1] = a1 + bn[1]; }
 }
 
 __global__ void segment_sum_kernel(const float* __restrict__ vals, const int* __restrict__ off, int C, float* __restrict__ out) {
@@ -333,21 +285,11 @@ verify_masks_kernel(const SeqDesc* __restrict__ desc, int S, int R, const void* 
 
 }  // namespace
 
-int pooler_nsp(const float* xt, int ldt_seq, const float* xv, int ldv_seq, int B, int Ht, int Hv, int Hb, const float* Wt,
-               const float* bt, const float* Wv, const float* bv, const float* Wn, const float* bn, float* nsp_logits,
-               cudaStream_t stream) {
-    const size_t smem = sizeof(float) * (Ht + Hv + Hb);
-    pooler_nsp_kernel<<<B, 256, smem, stream>>>(xt, ldt_seq, xv, ldv_seq, Ht, Hv, Hb, Wt, bt, Wv, bv, Wn, bn, nsp_logits);
-    UNIMM_LAUNCH_CHECK(1);
-    return 0;
-}
-
-int pooler_nsp_indexed(const float* xt, int ldt, const int* cls_row, const float* xv, int ldv, const int* img_row, int C, int Ht,
-                       int Hv, int Hb, const float* Wt, const float* bt, const float* Wv, const float* bv, const float* Wn,
-                       const float* bn, float* nsp_logits, cudaStream_t stream) {
-    if (C == 0) return 0;
-    const size_t smem = sizeof(float) * (Ht + Hv + Hb);
-    pooler_nsp_indexed_kernel<<<C, 256, smem, stream>>>(xt, ldt, cls_row, xv, ldv, img_row, Ht, Hv, Hb, Wt, bt, Wv, bv, Wn, bn, nsp_logits);
+int nsp_from_pooled(const float* pooled_t, const float* pooled_v, int n, int Hb, const float* Wn, const float* bn, float* nsp_logits,
+                    cudaStream_t stream) {
+    if (n == 0) return 0;
+    UNIMM_CHECK(Hb % 4 == 0, "nsp head: bi_hidden_size must be a multiple of 4");
+    nsp_from_pooled_kernel<<<(n + 3) / 4, 128, 0, stream>>>(pooled_t, pooled_v, n, Hb, Wn, bn, nsp_logits);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

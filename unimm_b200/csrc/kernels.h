@@ -24,7 +24,8 @@ struct GemmEpilogue {
     int debug_mode = 0;            // microbenchmark only: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue work
     int lp_kind = LP_BF16;         // encoding of the 16-bit operands and of out_bf16 (LP_BF16 / LP_FP16)
     int split3 = 0;                // fp32-class mode: A [M, 2K] and W [N, 2K] are fp16 hi | lo planes (LP_HILO); three passes per k-block
-    bool out_hilo = false;         // write out_bf16 as hi | lo planes of an [M, 2N] fp16 matrix (ldo_bf16 >= 2N) instead of one 16-bit value
+    bool out_hilo = false;         // write out_bf16 as fp16 hi | lo planes instead of one 16-bit value: hi at column c, lo at column
+    int hilo_off = 0;              //   hilo_off + c of the same row (0 = N: an [M, 2N] matrix)
     bool w_perm16 = false;         // W rows are in fragment order (permute_weight_rows mode 1): enables the smem-free 16-bit epilogue
     const int* labels = nullptr;   // LSE mode: [M]
     float2* partials = nullptr;    // LSE mode: [M, gemm_umma_lse_tiles(N)]
@@ -90,7 +91,8 @@ int gather_rows(const float* src_f32, const bf16* src_bf16, const int* rows, int
                 cudaStream_t stream);
 int cast_f32_to_lp(const float* src, bf16* dst, size_t n, int lp_kind, cudaStream_t stream);
 // fp32 [rows, K] -> fp16 hi | lo planes [rows, 2K] (LP_HILO, the operand layout of the fp32-class tcgen05 GEMM)
-int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaStream_t stream);
+// (row_idx: optional gather — output row r reads source row row_idx[r])
+int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaStream_t stream, const int* row_idx = nullptr);
 // *d_flag = 1 iff the two fp32 buffers differ in any bit
 int buffers_differ(const float* a, const float* b, size_t n, int* d_flag, cudaStream_t stream);
 int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStream_t stream);
@@ -141,7 +143,15 @@ struct AttnJobsArgs {
     int n_kv_rows = 0;     // rows of the k / v matrices when they differ from q's (cross attention)
     const SeqDesc* desc = nullptr;   // dense layout (attention_dense_umma): one descriptor per sequence
     int seq_len = 0;                 //   rows per sequence (<= 256)
+    // fp32-class mode (attention_jobs_split): q / k / v / o are fp16 hi planes, the lo plane of the same row lies lo_off_*
+    // elements further
+    int lo_off_q = 0, lo_off_k = 0, lo_off_v = 0, lo_off_o = 0;
 };
+// attention_split.cu: the same job semantics with hi | lo fp16 planes and three mma.sync passes per product (fp32-class mode)
+int attention_jobs_split(const AttnJobsArgs& a, cudaStream_t stream);
+// job lists / per-row intervals of the DENSE [B, S] layout from the descriptors: jobs_text / jobs_i2t / jobs_img [B, 8], row_iv [B*S, 4]
+int build_dense_jobs(const SeqDesc* desc, int B, int S, int R, int* jobs_text, int* jobs_i2t, int* jobs_img, int* row_iv,
+                     cudaStream_t stream);
 int attention_jobs(const AttnJobsArgs& a, bool fp32, cudaStream_t stream);
 // jobs that all have win = 1 (candidate rows over context + own rows), D = 64, 16-bit: persistent double-buffered kernel.
 // halo = (longest candidate's row count - 1): rows of a candidate lie within +-halo of any of its rows.
@@ -158,16 +168,11 @@ bool attention_cross_umma_supported(const AttnJobsArgs& a);
 int attention_cross_umma(const AttnJobsArgs& a, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ heads.cu
-// packed layout: text pooled row = xt[cls_row[c]], image pooled row = xv[unit[c] * R]
-int pooler_nsp_indexed(const float* xt, int ldt, const int* cls_row, const float* xv, int ldv, const int* img_row, int C, int Ht,
-                       int Hv, int Hb, const float* Wt, const float* bt, const float* Wv, const float* bv, const float* Wn,
-                       const float* bn, float* nsp_logits, cudaStream_t stream);
+// NSP head on the pooled vectors (ref :1062-1070 with fusion 'mul'): nsp[b, c] = sum_j pooled_t[b, j] * pooled_v[b, j] * Wn[c, j] + bn[c]
+int nsp_from_pooled(const float* pooled_t, const float* pooled_v, int n, int Hb, const float* Wn, const float* bn, float* nsp_logits,
+                    cudaStream_t stream);
 // per-candidate sum of the compact per-row log-probs: rows [off[c], off[c+1])
 int segment_sum(const float* vals, const int* off, int C, float* out, cudaStream_t stream);
-// poolers + 'mul' fusion + NSP linear (ref :946-967, :1062-1070), all fp32
-int pooler_nsp(const float* xt, int ldt_seq, const float* xv, int ldv_seq, int B, int Ht, int Hv, int Hb, const float* Wt,
-               const float* bt, const float* Wv, const float* bv, const float* Wn, const float* bn, float* nsp_logits,
-               cudaStream_t stream);
 // fp32 LM head tail: per row log-softmax pick from materialised logits (fp32 mode only)
 int lse_from_logits(const float* logits, int ld, int rows, int V, const int* labels, float* logp, float* ul,
                     cudaStream_t stream);

@@ -282,14 +282,16 @@ int cast_lp_to_f32(const bf16* src, float* dst, size_t n, int lp_kind, cudaStrea
     return 0;
 }
 
-// fp32 [rows, K] (leading dimension ldx) -> the two fp16 planes [rows, 2K] of the fp32-class mode (LP_HILO)
-__global__ void split_hilo_kernel(const float* __restrict__ x, int ldx, int rows, int K, bf16* __restrict__ out) {
+// fp32 [rows, K] (leading dimension ldx) -> the two fp16 planes [rows, 2K] of the fp32-class mode (LP_HILO).
+// Source row of output row r: row_idx ? row_idx[r] : r.
+__global__ void split_hilo_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ row_idx, int rows, int K, bf16* __restrict__ out) {
     const int kv = K / 4;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < static_cast<size_t>(rows) * kv;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const size_t r = i / kv;
         const int c = static_cast<int>(i % kv) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        const size_t sr = row_idx ? static_cast<size_t>(row_idx[r]) : r;
+        const float4 v = *reinterpret_cast<const float4*>(x + sr * ldx + c);
         uint2 hi, lo;
         split_hilo2(v.x, v.y, hi.x, lo.x);
         split_hilo2(v.z, v.w, hi.y, lo.y);
@@ -297,12 +299,12 @@ __global__ void split_hilo_kernel(const float* __restrict__ x, int ldx, int rows
         *reinterpret_cast<uint2*>(out + r * 2 * K + K + c) = lo;
     }
 }
-int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaStream_t stream) {
+int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaStream_t stream, const int* row_idx) {
     UNIMM_CHECK(rows > 0 && K % 4 == 0 && ldx % 4 == 0, "split: K and ldx must be multiples of 4");
     const size_t n = static_cast<size_t>(rows) * (K / 4);
     int grid = static_cast<int>((n + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    split_hilo_kernel<<<grid, 256, 0, stream>>>(x, ldx, rows, K, out);
+    split_hilo_kernel<<<grid, 256, 0, stream>>>(x, ldx, row_idx, rows, K, out);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -176,3 +176,86 @@ def stack_rounds(rounds: Sequence[Round]):
     cat = lambda f: torch.from_numpy(np.concatenate([getattr(r, f) for r in rounds], 0))
     index = np.concatenate([np.full(len(r.tokens), u, np.int32) for u, r in enumerate(rounds)])
     return cat("tokens"), cat("segments"), cat("positions"), cat("labels"), cat("desc"), torch.from_numpy(index)
+
+
+# ------------------------------------------------------------------------------------------------ configs 3 / 4 / 5 (bench inputs)
+def _context_arrays(context, start_segment=1):
+    tok, seg, s = [CLS], [start_segment], start_segment
+    for u in context:
+        tok += list(u) + [SEP]
+        seg += [s] * (len(u) + 1)
+        s ^= 1
+    return tok, seg, s
+
+
+def encode_train_sequence(rng, context, answer, dis: bool, negative: bool, mask_prob: float = 0.15, weight: int = 1, S: int = S_MAX,
+                          vocab: int = 30522):
+    """One training sequence the way ``encode_input`` shapes it (utils/data_utils.py:139-436): random 15 % masking with the
+    80/10/10 rule on the visible tokens, the masked answer copy in generative mode, token weights +w (likelihood), -w on a
+    negative's masked copy (unlikelihood) and 0 on a negative's visible answer.  Shape-faithful synthetic data for the bench (the
+    parity fixtures use the reference's own encoder)."""
+    tok, seg, cur = _context_arrays(context)
+    ctx = len(tok)
+    a = list(answer) + [SEP]
+    last = len(a)
+    tokens = np.zeros(S, np.int64); segments = np.zeros(S, np.int64); positions = np.zeros(S, np.int64)
+    labels = np.full(S, -1, np.int64); weights = np.zeros(S, np.int64)
+    L = ctx + last
+    tokens[:ctx], tokens[ctx:L] = tok, a
+    segments[:ctx], segments[ctx:L] = seg, cur
+    positions[:L] = np.arange(L)
+    # random masking of the visible (non-special) tokens
+    special = np.zeros(S, bool)
+    special[0] = True
+    special[:L] |= tokens[:L] == SEP
+    draw = (rng.rand(L) < mask_prob) & ~special[:L]
+    if last <= 2:
+        draw[ctx:L] = False                                   # one-token answers are never masked in place (:173-175)
+    for p in np.flatnonzero(draw):
+        labels[p] = tokens[p]
+        weights[p] = 0 if (negative and p >= ctx) else 1
+        r = rng.rand()
+        tokens[p] = MASK if r < 0.8 else (rng.randint(0, vocab) if r < 0.9 else tokens[p])
+    if dis:
+        desc = (1, 0, L, 0)
+    else:
+        T = L + last
+        if T > S:
+            raise ValueError("synthetic training sequence exceeds max_seq_len")
+        tokens[L:T] = MASK
+        segments[L:T] = cur
+        positions[L:T] = np.arange(ctx, L)
+        labels[L:T] = a
+        weights[L:T] = -weight if negative else weight
+        desc = (0, ctx, L, last)
+    return tokens, segments, positions, labels, weights, np.asarray(desc, np.int32)
+
+
+def train_batch(seed: int, n_images: int = 40, per_image: int = 6, dis_rate: float = 0.5, mask_prob: float = 0.15):
+    """BASELINE config 3's batch: ``n_images`` x (1 positive + ``per_image``-1 negatives of one round), mode drawn per sequence.
+    Returns a dict of numpy arrays: ids [B,256] x3, labels, weights, desc [B,4], next_sentence_label [B], seq_image [B] and the
+    per-image blocks image_feat / image_loc / image_mask / image_label [n,37] / image_target [n,37,1601]."""
+    rng = np.random.RandomState(seed)
+    cols = [[] for _ in range(6)]
+    nsl, seq_image, feats, locs, masks, ilabels, targets = [], [], [], [], [], [], []
+    for i in range(n_images):
+        f, l, m = synth_image(rng)
+        il = np.where(rng.rand(37) < 0.15, 1, -1)
+        il[0] = 0
+        f = f.copy()
+        f[(il == 1) & (rng.rand(37) < 0.9)] = 0
+        t = rng.rand(37, 1601).astype(np.float32) ** 8
+        t /= t.sum(-1, keepdims=True)
+        feats.append(f), locs.append(l), masks.append(m), ilabels.append(il), targets.append(t)
+        context = synth_context(rng, int(rng.randint(1, 11)))
+        for j in range(per_image):
+            out = encode_train_sequence(rng, context, _draw(rng, int(rng.randint(1, 8))), dis=rng.rand() < dis_rate, negative=j > 0,
+                                        mask_prob=mask_prob)
+            for c, o in zip(cols, out):
+                c.append(o)
+            nsl.append(int(j > 0)), seq_image.append(i)
+    tokens, segments, positions, labels, weights, desc = (np.stack(c) for c in cols)
+    return {"tokens": tokens, "segments": segments, "positions": positions, "labels": labels, "weights": weights, "desc": desc,
+            "next_sentence_label": np.asarray(nsl, np.int64), "seq_image": np.asarray(seq_image, np.int32),
+            "image_feat": np.stack(feats), "image_loc": np.stack(locs), "image_mask": np.stack(masks),
+            "image_label": np.stack(ilabels).astype(np.int64), "image_target": np.stack(targets)}
