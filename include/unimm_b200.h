@@ -18,6 +18,7 @@
 #ifndef UNIMM_B200_H
 #define UNIMM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -287,6 +288,18 @@ int unimm_k_gemm_f32(const float* d_A, int lda, const float* d_W, int ldw, int M
 int unimm_k_lm_head_lp(const void* d_H_lp, int ldh, const void* d_E_lp, int lde, int rows, int V, int K,
                        const float* d_bias, const int32_t* d_labels, float* d_partials_scratch, float* d_label_logit_scratch,
                        float* d_logp, float* d_ul, int lp_kind, void* stream);
+/* Backward of the fused LM head + likelihood / unlikelihood loss (first piece; reference
+ * models/vilbert_dialog.py:1577-1595 under train.py:453-463's backward): for rows with hidden states H [rows, K] (16-bit), tied
+ * decoder E [V, K] (16-bit), bias [V], labels and token weights w (w > 0: likelihood row, loss -w log p; w == -1: unlikelihood row,
+ * loss -log(max(1 - p, 1e-6))), the gradients of  grad_scale * sum_i loss_i :
+ *   dH [rows, K], dE [V, K] (decoder / word-embedding weight), dbias [V]   (fp32; d_dbias and d_logp optional).
+ * No [rows, V] fp32 logits: the vocabulary GEMM is recomputed twice on tcgen05 (online log-sum-exp, then dz = coef (softmax - onehot)
+ * written as 16-bit operands in both orientations) and dH = dz E, dE = dz^T H are two more tcgen05 GEMMs.
+ * d_scratch: unimm_k_lm_head_backward_scratch(rows, V, K) bytes. */
+size_t unimm_k_lm_head_backward_scratch(int rows, int V, int K);
+int unimm_k_lm_head_backward(const void* d_H_lp, int ldh, const void* d_E_lp, int lde, int rows, int V, int K, const float* d_bias,
+                             const int32_t* d_labels, const float* d_weight, float grad_scale, float* d_dH, float* d_dE, float* d_dbias,
+                             float* d_logp, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream);
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
                       void* d_y_lp, int lp_kind, void* stream);
 int unimm_k_cast_lp(const float* d_src, void* d_dst_lp, int64_t n, int lp_kind, void* stream);

@@ -1,7 +1,7 @@
 # ncu evidence for profiles/: (1) every launch with its device time, (2) full captures of the top kernels.
 mkdir -p gpurun_out
 rm -f gpurun_out/prof_*.ncu-rep gpurun_out/launches.csv
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --precision ${PREC:-fp16} --mode ${MODE:-packed} --images-per-step ${IPS:-8}"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --precision ${PREC:-fp16} --mode ${MODE:-packed} --images-per-step ${IPS:-8} --no-bf16 ${EXTRA:-}"
 $CMD > gpurun_out/prof_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-400} -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 tail -1 gpurun_out/ncu_launches.log | cut -c1-200

@@ -1,0 +1,54 @@
+"""GPU: backward of the fused LM head + L / UL loss (unimm_k_lm_head_backward) against torch.autograd in fp64 on the SAME 16-bit
+operands (the rounding of h and E to the operand format is the forward's, not the backward's)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from unimm_b200.lm_head_grad import lm_head_backward  # noqa: E402
+
+
+def reference(h, E, b, labels, w, scale):
+    """The reference's loss (models/vilbert_dialog.py:1577-1595) in fp64 with autograd."""
+    h = h.double().requires_grad_(True)
+    E = E.double().requires_grad_(True)
+    b = b.double().requires_grad_(True)
+    z = h @ E.t() + b
+    logp_all = torch.log_softmax(z, -1)
+    lp = logp_all.gather(1, labels.view(-1, 1).long())[:, 0]
+    l_rows, ul_rows = w > 0, w == -1
+    loss = -(w[l_rows].double() * lp[l_rows]).sum() - torch.log(torch.clamp(1.0 - lp[ul_rows].exp(), min=1e-6)).sum()
+    (loss * scale).backward()
+    return h.grad, E.grad, b.grad, lp.detach()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 4e-3), ("bf16", 3e-2)])
+@pytest.mark.parametrize("n", [300, 64])
+def test_lm_head_backward_matches_autograd(precision, tol, n):
+    g = torch.Generator().manual_seed(5 + n)
+    V, K = 30522, 768
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    h = torch.randn(n, K, generator=g).to(dt).float()                   # values exactly representable in the operand format
+    E = (0.02 * torch.randn(V, K, generator=g)).to(dt).float()
+    E[:50] *= 30.0                                                      # a few confident tokens: p(label) far from 1 / V, UL rows with real weight
+    b = 0.1 * torch.randn(V, generator=g)
+    labels = torch.randint(0, V, (n,), generator=g)
+    labels[: n // 3] = torch.randint(0, 50, (n // 3,), generator=g)
+    w = torch.ones(n)
+    w[1::3] = -1.0                                                      # unlikelihood rows
+    w[2::7] = 0.0                                                       # rows that carry no loss at all
+    w[5::11] = 2.0
+    scale = 1.0 / float((w != 0).sum())
+    out = lm_head_backward(h.cuda(), E.cuda(), b, labels, w, grad_scale=scale, precision=precision)
+    dH, dE, db, lp = reference(h, E, b, labels, w, scale)
+    for name, mine, ref in (("dH", out["dH"], dH), ("dE", out["dE"], dE), ("dbias", out["dbias"], db)):
+        err = (mine.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"[{precision}] n={n} {name}: max |err| / max |ref| = {err:.3e}")
+        assert err < tol, name
+    assert (out["logp"].cpu().double() - lp).abs().max().item() < 2e-3
+    # rows without a loss get no gradient
+    assert out["dH"][2::7].abs().max().item() == 0.0

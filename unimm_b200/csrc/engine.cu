@@ -529,8 +529,8 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&row_logp, Mt));
     UNIMM_TRY(dalloc(&row_ul, Mt));
     UNIMM_TRY(dalloc(&lse_u, Mt));
-    if (lp()) UNIMM_TRY(dalloc(&partials, Mt * gemm_umma_lse_tiles(c.vocab_size)));
-    else UNIMM_TRY(dalloc(&logits_chunk, static_cast<size_t>(kLogitRows) * logits_ld()));
+    if (lp() || tc32()) UNIMM_TRY(dalloc(&partials, Mt * gemm_umma_lse_tiles(c.vocab_size)));
+    if (!lp() && !tc32()) UNIMM_TRY(dalloc(&logits_chunk, static_cast<size_t>(kLogitRows) * logits_ld()));
     UNIMM_TRY(dalloc(&vhead, Mv * Hv));
     vhead_h.ld = Hv;
     UNIMM_TRY(dalloc(&vhead_h.f, Mv * Hv));
@@ -1031,15 +1031,19 @@ int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* 
         UNIMM_TRY(gather_rows(lp() ? nullptr : src.f, lp() ? src.h : nullptr, d_rows, n, H, lp() ? nullptr : g_in.f, lp() ? g_in.h : nullptr, st));
     UNIMM_TRY(linear(d_rows != nullptr ? g_in : src, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
     { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, act_kind(), st)); }
-    if (lp()) {
+    if (lp() || tc32()) {
+        // the vocabulary GEMM with the online log-sum-exp epilogue: logits never leave TMEM / registers (fp32-class mode: the same
+        // epilogue over the three-pass accumulator)
         GemmEpilogue ep;
         ep.bias = lm_decoder.b;
         ep.labels = d_labels;
         ep.partials = partials;
         ep.label_logit = label_logit;
-        ep.lp_kind = lp_kind();
+        ep.lp_kind = tc32() ? LP_FP16 : lp_kind();
+        ep.split3 = tc32() ? 1 : 0;
+        const int ld = tc32() ? 2 * H : H;
         Prof prof(this, CAT_LMHEAD, 2.0 * n * c.vocab_size * H, st);
-        UNIMM_TRY(gemm_umma_bf16(g_h.h, H, lm_decoder.wlp, H, n, c.vocab_size, H, ep, 256, 0, st));
+        UNIMM_TRY(gemm_umma_bf16(g_h.h, ld, lm_decoder.wlp, ld, n, c.vocab_size, H, ep, 256, 0, st));
         UNIMM_TRY(lse_from_partials(partials, gemm_umma_lse_tiles(c.vocab_size), label_logit, n, row_logp, row_ul, st));
     } else {
         for (int r0 = 0; r0 < n; r0 += kLogitRows) {
@@ -1049,13 +1053,7 @@ int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* 
             ep.out_f32 = logits_chunk;
             ep.ldo_f32 = logits_ld();
             Prof prof(this, CAT_LMHEAD, 2.0 * nr * c.vocab_size * H, st);
-            if (tc32()) {
-                ep.lp_kind = LP_FP16;
-                ep.split3 = 1;
-                UNIMM_TRY(gemm_umma_bf16(g_h.h + static_cast<size_t>(r0) * 2 * H, 2 * H, lm_decoder.wlp, 2 * H, nr, c.vocab_size, H, ep, 256, 0, st));
-            } else {
-                UNIMM_TRY(gemm_simt_f32(g_h.f + static_cast<size_t>(r0) * H, H, lm_decoder.w32, H, nr, c.vocab_size, H, ep, st));
-            }
+            UNIMM_TRY(gemm_simt_f32(g_h.f + static_cast<size_t>(r0) * H, H, lm_decoder.w32, H, nr, c.vocab_size, H, ep, st));
             UNIMM_TRY(lse_from_logits(logits_chunk, logits_ld(), nr, c.vocab_size, d_labels + r0, row_logp + r0, row_ul + r0, st));
         }
     }
@@ -1507,6 +1505,74 @@ int unimm_k_lm_head_lp(const void* d_H, int ldh, const void* d_E, int lde, int r
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     UNIMM_TRY(gemm_umma_bf16(static_cast<const bf16*>(d_H), ldh, static_cast<const bf16*>(d_E), lde, rows, V, K, ep, 256, 0, st));
     return lse_from_partials(ep.partials, gemm_umma_lse_tiles(V), d_label_logit_scratch, rows, d_logp, d_ul, st);
+}
+
+size_t unimm_k_lm_head_backward_scratch(int rows, int V, int K) {
+    const size_t Vp = (static_cast<size_t>(V) + 63) / 64 * 64, np = (static_cast<size_t>(rows) + 63) / 64 * 64;
+    // dz [rows, Vp] + dzT [V, np] + Et [K, Vp] + hT [K, np] 16-bit, partials float2 [rows, tiles], lse / coef / label logit / logp / ul fp32 [rows]
+    return 2 * (rows * Vp + V * np + K * Vp + K * np) + 8 * static_cast<size_t>(rows) * gemm_umma_lse_tiles(V) + 4 * 5 * static_cast<size_t>(rows) + 4096;
+}
+
+int unimm_k_lm_head_backward(const void* d_H, int ldh, const void* d_E, int lde, int rows, int V, int K, const float* d_bias,
+                             const int32_t* d_labels, const float* d_weight, float grad_scale, float* d_dH, float* d_dE, float* d_dbias,
+                             float* d_logp, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
+    UNIMM_CHECK(d_H && d_E && d_bias && d_labels && d_weight && d_dH && d_dE && d_scratch && rows > 0 && V > 0 && K % 64 == 0, "bad argument");
+    UNIMM_CHECK(scratch_bytes >= unimm_k_lm_head_backward_scratch(rows, V, K), "scratch smaller than unimm_k_lm_head_backward_scratch()");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Vp = (V + 63) / 64 * 64, np = (rows + 63) / 64 * 64, tiles = gemm_umma_lse_tiles(V);
+    char* p = static_cast<char*>(d_scratch);
+    auto carve = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~size_t(255); return q; };
+    bf16* dz = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(rows) * Vp));
+    bf16* dzT = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(V) * np));
+    bf16* Et = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(K) * Vp));
+    bf16* hT = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(K) * np));
+    float2* partials = reinterpret_cast<float2*>(carve(8 * static_cast<size_t>(rows) * tiles));
+    float* lse = reinterpret_cast<float*>(carve(4 * static_cast<size_t>(rows)));
+    float* coef = reinterpret_cast<float*>(carve(4 * static_cast<size_t>(rows)));
+    float* lab_logit = reinterpret_cast<float*>(carve(4 * static_cast<size_t>(rows)));
+    float* logp = reinterpret_cast<float*>(carve(4 * static_cast<size_t>(rows)));
+    float* ul = reinterpret_cast<float*>(carve(4 * static_cast<size_t>(rows)));
+    UNIMM_CHECK(static_cast<size_t>(p - static_cast<char*>(d_scratch)) <= scratch_bytes, "scratch carve overflow");
+    // 1. forward recompute: log-sum-exp per row (and log p of the label) without materialising logits
+    {
+        GemmEpilogue ep;
+        ep.lp_kind = lp_kind; ep.bias = d_bias; ep.labels = d_labels; ep.partials = partials; ep.label_logit = lab_logit;
+        UNIMM_TRY(gemm_umma_bf16(static_cast<const bf16*>(d_H), ldh, static_cast<const bf16*>(d_E), lde, rows, V, K, ep, 256, 0, st));
+        UNIMM_TRY(lse_merge(partials, tiles, rows, lse, st));
+        UNIMM_TRY(lse_from_partials(partials, tiles, lab_logit, rows, logp, ul, st));
+        if (d_logp) UNIMM_CUDA_CHECK(cudaMemcpyAsync(d_logp, logp, sizeof(float) * rows, cudaMemcpyDeviceToDevice, st));
+    }
+    // 2. dz = coef (softmax - onehot), both orientations, 16-bit.  The factor kScale keeps the ~1/V-sized probabilities out of the
+    // fp16 subnormal range; the two gradient GEMMs multiply it back out (alpha)
+    const float kScale = lp_kind == LP_FP16 ? 1024.f : 1.f;
+    UNIMM_TRY(lm_loss_coef(logp, d_weight, rows, grad_scale * kScale, coef, st));
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(dz, 0, 2 * static_cast<size_t>(rows) * Vp, st));
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(dzT, 0, 2 * static_cast<size_t>(V) * np, st));
+    {
+        GemmEpilogue ep;
+        ep.lp_kind = lp_kind; ep.bias = d_bias; ep.labels = d_labels; ep.lse = lse; ep.coef = coef;
+        ep.dz = dz; ep.ldz = Vp; ep.dz_cols = Vp; ep.dzT = dzT; ep.ldzt = np;
+        UNIMM_TRY(gemm_umma_bf16(static_cast<const bf16*>(d_H), ldh, static_cast<const bf16*>(d_E), lde, rows, V, K, ep, 256, 0, st));
+    }
+    // 3. dH = dz E  (contraction over the vocabulary: W operand = E^T, K-major)
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(Et, 0, 2 * static_cast<size_t>(K) * Vp, st));
+    UNIMM_TRY(transpose_16(static_cast<const bf16*>(d_E), lde, V, K, Et, Vp, st));
+    {
+        GemmEpilogue ep;
+        ep.lp_kind = lp_kind; ep.out_f32 = d_dH; ep.ldo_f32 = K; ep.alpha = 1.f / kScale;
+        UNIMM_TRY(gemm_umma_bf16(dz, Vp, Et, Vp, rows, K, Vp, ep, 0, 0, st));
+    }
+    // 4. dE = dz^T h  (contraction over the rows: A = dz^T, W = h^T)
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(hT, 0, 2 * static_cast<size_t>(K) * np, st));
+    UNIMM_TRY(transpose_16(static_cast<const bf16*>(d_H), ldh, rows, K, hT, np, st));
+    {
+        GemmEpilogue ep;
+        ep.lp_kind = lp_kind; ep.out_f32 = d_dE; ep.ldo_f32 = K; ep.alpha = 1.f / kScale;
+        UNIMM_TRY(gemm_umma_bf16(dzT, np, hT, np, V, K, np, ep, 0, 0, st));
+    }
+    // 5. dbias = column sums of dz = row sums of dz^T
+    if (d_dbias) UNIMM_TRY(row_sums_16(dzT, np, V, rows, lp_kind, 1.f / kScale, d_dbias, st));
+    return 0;
 }
 
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,

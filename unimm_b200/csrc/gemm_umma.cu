@@ -291,6 +291,45 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (c + 1 < NCH && col0 + 32 < N) ptx::tmem_ld_32x32b_x32(taddr0 + (c + 1) * 32, v);   // next chunk in flight
                 if (LSE) {
                     constexpr float kLog2e = 1.4426950408889634f;
+                    if (ep.dz != nullptr) {
+                        // ---- LM-head backward: dz = coef * (softmax - onehot) recomputed from the saved log-sum-exp, written in both
+                        // orientations as 16-bit GEMM operands (row-major for dH = dz E, transposed for dE = dz^T h)
+                        const float l2 = row_ok ? ep.lse[row] * kLog2e : 0.f;
+                        const float cf = row_ok ? ep.coef[row] : 0.f;
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float d0 = 0.f, d1 = 0.f;
+                            if (j < ncols) {
+                                const float v = x[j] + __ldg(ep.bias + col0 + j);
+                                d0 = cf * (fast_ex2(fmaf(v, kLog2e, -l2)) - (col0 + j == label ? 1.f : 0.f));
+                            }
+                            if (j + 1 < ncols) {
+                                const float v = x[j + 1] + __ldg(ep.bias + col0 + j + 1);
+                                d1 = cf * (fast_ex2(fmaf(v, kLog2e, -l2)) - (col0 + j + 1 == label ? 1.f : 0.f));
+                            }
+                            pk[j >> 1] = pack_lp2(d0, d1, ep.lp_kind);
+                        }
+                        if (row_ok) {
+                            bf16* drow = ep.dz + static_cast<size_t>(row) * ep.ldz + col0;
+                            if (col0 + 32 <= ep.dz_cols) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    *reinterpret_cast<uint4*>(drow + 8 * q) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 2)
+                                    if (col0 + j + 2 <= ep.dz_cols) *reinterpret_cast<uint32_t*>(drow + j) = pk[j >> 1];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncols) {
+                                    const uint16_t h16 = static_cast<uint16_t>((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xffffu));
+                                    reinterpret_cast<uint16_t*>(ep.dzT)[static_cast<size_t>(col0 + j) * ep.ldzt + row] = h16;
+                                }
+                        }
+                        continue;
+                    }
                     if (ncols == 32 && fast_ok) {
                         // full chunk (all but the last vocabulary tile): 128-bit uniform bias loads, no per-column predicates
                         if (ep.bias != nullptr) {
@@ -419,6 +458,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         y[i] = stage[r * 8 + (ch ^ (r & 7))];
                     }
                     __syncwarp();   // the staging block is rewritten by the next chunk
+                    if (ep.alpha != 1.f) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { y[i].x *= ep.alpha; y[i].y *= ep.alpha; y[i].z *= ep.alpha; y[i].w *= ep.alpha; }
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { y[i].x += b4.x; y[i].y += b4.y; y[i].z += b4.z; y[i].w += b4.w; }
                     if (ep.act == ACT_GELU) {
@@ -464,6 +507,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     continue;
                 }
                 // ---- generic path (ragged last columns, unaligned leading dimensions): one row per thread
+                if (ep.alpha != 1.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] *= ep.alpha;
+                }
                 if (ep.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -516,7 +563,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         tile_done:
             ptx::tmem_ld_wait();   // no TMEM load may be outstanding when the accumulator is handed back
-            if (LSE && row_ok && n0 < N) {
+            if (LSE && ep.dz != nullptr) {
+                // nothing per tile: dz went out chunk by chunk
+            } else if (LSE && row_ok && n0 < N) {
                 ep.partials[static_cast<size_t>(row) * (2 * num_n) + 2 * tn + half] = make_float2(run_max, run_sum);
                 if (label >= n0 && label < min(n0 + HALF_N, N)) ep.label_logit[row] = lab_logit;
             } else if (LSE && row_ok) {
@@ -680,8 +729,12 @@ int gemm_num_sms() { return num_sms(); }
 int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int tile_n,
                    int max_ctas, cudaStream_t stream) {
     UNIMM_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "umma gemm: K must be a positive multiple of 64");
-    const bool lse = ep.partials != nullptr;
-    UNIMM_CHECK(!ep.split3 || (!lse && !ep.w_perm16 && ep.lp_kind == LP_FP16), "split3 takes fp16 hi | lo planes and the plain epilogue");
+    const bool lse = ep.partials != nullptr || ep.dz != nullptr;
+    UNIMM_CHECK(ep.dz == nullptr || (ep.dzT != nullptr && ep.lse != nullptr && ep.coef != nullptr && ep.labels != nullptr && ep.bias != nullptr &&
+                                     (ep.ldz & 7) == 0 && (ep.dz_cols & 1) == 0 && ep.dz_cols <= ep.ldz && ep.ldzt >= M),
+                "dz epilogue: incomplete arguments");
+    UNIMM_CHECK(ep.alpha == 1.f || (!lse && ep.out_bf16 == nullptr), "alpha applies to the fp32-output epilogue only");
+    UNIMM_CHECK(!ep.split3 || (!ep.w_perm16 && ep.lp_kind == LP_FP16), "split3 takes fp16 hi | lo planes (plain or log-sum-exp epilogue)");
     UNIMM_CHECK(!ep.out_hilo || (ep.out_bf16 != nullptr && N % 32 == 0 && (ep.ldo_bf16 & 3) == 0 && (ep.hilo_off & 3) == 0 &&
                                  ep.ldo_bf16 >= (ep.hilo_off > 0 ? ep.hilo_off : N) + N && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0),
                 "hi | lo output needs N % 32 == 0 and 8-byte aligned planes inside the row");

@@ -55,6 +55,52 @@ nsp_from_pooled_kernel(const float* __restrict__ pt, const float* __restrict__ p
     if (lane == 0) { nsp[b * 2] = a0 + bn[0]; nsp[b * 2 + 1] = a1 + bn[1]; }
 }
 
+// ---- LM-head backward helpers -----------------------------------------------------------------------------------------
+// 32 x 32 tiles through shared memory: coalesced 16-bit reads along src rows, coalesced writes along dst rows
+__global__ void __launch_bounds__(256)
+transpose16_kernel(const uint16_t* __restrict__ src, int lds, int rows, int cols, uint16_t* __restrict__ dst, int ldt) {
+    __shared__ uint16_t tile[32][34];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? src[static_cast<size_t>(r) * lds + c] : uint16_t(0);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < cols && r < rows) dst[static_cast<size_t>(c) * ldt + r] = tile[tx][i];
+    }
+}
+
+// d loss_i / d z_ij = coef_i * (p_ij - [j == y_i])  (reference models/vilbert_dialog.py:1577-1595):
+//   likelihood row (w > 0):      loss_i = -w log p_y                         coef = w
+//   unlikelihood row (w == -1):  loss_i = -log(max(1 - p_y, 1e-6))           coef = -p_y / (1 - p_y), 0 where the clamp is active
+__global__ void lm_loss_coef_kernel(const float* __restrict__ logp, const float* __restrict__ weight, int n, float scale, float* __restrict__ coef) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float w = weight[i];
+    float c = 0.f;
+    if (w > 0.f) c = w;
+    else if (w == -1.f) {
+        const float p = expf(logp[i]);
+        c = (1.0f - p > 1e-6f) ? -p / (1.0f - p) : 0.f;
+    }
+    coef[i] = c * scale;
+}
+
+template <bool FP16>
+__global__ void row_sums16_kernel(const uint16_t* __restrict__ x, int ld, int rows, int cols, float alpha, float* __restrict__ out) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+        const uint16_t v = x[static_cast<size_t>(r) * ld + c];
+        s += FP16 ? __half2float(*reinterpret_cast<const __half*>(&v)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&v));
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s * alpha;
+}
+
 __global__ void segment_sum_kernel(const float* __restrict__ vals, const int* __restrict__ off, int C, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -290,6 +336,29 @@ int nsp_from_pooled(const float* pooled_t, const float* pooled_v, int n, int Hb,
     if (n == 0) return 0;
     UNIMM_CHECK(Hb % 4 == 0, "nsp head: bi_hidden_size must be a multiple of 4");
     nsp_from_pooled_kernel<<<(n + 3) / 4, 128, 0, stream>>>(pooled_t, pooled_v, n, Hb, Wn, bn, nsp_logits);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int transpose_16(const bf16* src, int lds, int rows, int cols, bf16* dst, int ldt, cudaStream_t stream) {
+    if (rows == 0 || cols == 0) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(src), lds, rows, cols, reinterpret_cast<uint16_t*>(dst), ldt);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int lm_loss_coef(const float* logp, const float* weight, int n, float scale, float* coef, cudaStream_t stream) {
+    if (n == 0) return 0;
+    lm_loss_coef_kernel<<<(n + 255) / 256, 256, 0, stream>>>(logp, weight, n, scale, coef);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float alpha, float* out, cudaStream_t stream) {
+    if (rows == 0) return 0;
+    if (lp_kind == LP_FP16) row_sums16_kernel<true><<<(rows + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), ld, rows, cols, alpha, out);
+    else row_sums16_kernel<false><<<(rows + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), ld, rows, cols, alpha, out);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -27,6 +27,16 @@ struct GemmEpilogue {
     bool out_hilo = false;         // write out_bf16 as fp16 hi | lo planes instead of one 16-bit value: hi at column c, lo at column
     int hilo_off = 0;              //   hilo_off + c of the same row (0 = N: an [M, 2N] matrix)
     bool w_perm16 = false;         // W rows are in fragment order (permute_weight_rows mode 1): enables the smem-free 16-bit epilogue
+    float alpha = 1.f;             // plain fp32-output paths: out = act(alpha * acc + bias) (+ residual)
+    // LSE-mode variant "dz" (LM-head backward, heads.cu: lm_head_backward): instead of the partials, write
+    //   dz[row, col] = coef[row] * (exp(x - lse[row]) - [col == labels[row]])     x = acc + bias
+    // as 16-bit values to dz [M, ldz] (columns < dz_cols) and, transposed, to dzT [N, ldzt]
+    bf16* dz = nullptr;
+    int ldz = 0, dz_cols = 0;
+    bf16* dzT = nullptr;
+    int ldzt = 0;
+    const float* lse = nullptr;    // [M]
+    const float* coef = nullptr;   // [M]
     const int* labels = nullptr;   // LSE mode: [M]
     float2* partials = nullptr;    // LSE mode: [M, gemm_umma_lse_tiles(N)]
     float* label_logit = nullptr;  // LSE mode: [M]
@@ -176,6 +186,13 @@ int segment_sum(const float* vals, const int* off, int C, float* out, cudaStream
 // fp32 LM head tail: per row log-softmax pick from materialised logits (fp32 mode only)
 int lse_from_logits(const float* logits, int ld, int rows, int V, const int* labels, float* logp, float* ul,
                     cudaStream_t stream);
+// LM-head backward building blocks (heads.cu)
+// 16-bit transpose: dst[c, r] = src[r, c] for r < rows, c < cols (dst rows ldt wide; the caller zeroes any padding)
+int transpose_16(const bf16* src, int lds, int rows, int cols, bf16* dst, int ldt, cudaStream_t stream);
+// per labelled row: coef = scale * w (likelihood row, w > 0) or -scale * p / (1 - p) (unlikelihood row, w == -1; 0 where 1 - p was
+// clamped at 1e-6), p = exp(logp)
+int lm_loss_coef(const float* logp, const float* weight, int n, float scale, float* coef, cudaStream_t stream);
+int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float alpha, float* out, cudaStream_t stream);
 // tcgen05 LM head tail: merge the per-tile (max, sum) partials
 int lse_merge(const float2* partials, int tiles, int rows, float* lse, cudaStream_t stream);
 int label_scores(const bf16* h, int ldh, const bf16* E, int lde, const float* bias, const int* uidx, const int* labels, const float* lse,
