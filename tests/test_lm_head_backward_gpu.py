@@ -33,8 +33,9 @@ def test_lm_head_backward_matches_autograd(precision, tol, n):
     V, K = 30522, 768
     dt = torch.float16 if precision == "fp16" else torch.bfloat16
     h = torch.randn(n, K, generator=g).to(dt).float()                   # values exactly representable in the operand format
-    E = (0.02 * torch.randn(V, K, generator=g)).to(dt).float()
+    E = 0.02 * torch.randn(V, K, generator=g)
     E[:50] *= 30.0                                                      # a few confident tokens: p(label) far from 1 / V, UL rows with real weight
+    E = E.to(dt).float()
     b = 0.1 * torch.randn(V, generator=g)
     labels = torch.randint(0, V, (n,), generator=g)
     labels[: n // 3] = torch.randint(0, 50, (n // 3,), generator=g)

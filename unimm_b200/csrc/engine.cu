@@ -1066,10 +1066,11 @@ int unimm_engine::lm_head_shared(const ActBuf& src, const int* d_urows, int n_u,
                                  cudaStream_t st) {
     const unimm_config_t& c = cfg;
     const int H = c.hidden_size;
-    UNIMM_CHECK(lp(), "shared labelled rows need a 16-bit mode");
-    if (d_urows != nullptr) UNIMM_TRY(gather_rows(nullptr, src.h, d_urows, n_u, H, nullptr, g_in.h, st));
+    UNIMM_CHECK(lp() || tc32(), "shared labelled rows need a tensor-core mode");
+    if (d_urows != nullptr) UNIMM_TRY(gather_rows(lp() ? nullptr : src.f, lp() ? src.h : nullptr, d_urows, n_u, H, lp() ? nullptr : g_in.f,
+                                                  lp() ? g_in.h : nullptr, st));
     UNIMM_TRY(linear(d_urows != nullptr ? g_in : src, n_u, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n_u) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n_u, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, lp_kind(), st)); }
+    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n_u) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n_u, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, act_kind(), st)); }
     UNIMM_CUDA_CHECK(cudaMemsetAsync(g_labels, 0, sizeof(int) * n_u, st));      // the fused epilogue's label pick is unused here
     {
         GemmEpilogue ep;
@@ -1077,12 +1078,15 @@ int unimm_engine::lm_head_shared(const ActBuf& src, const int* d_urows, int n_u,
         ep.labels = g_labels;
         ep.partials = partials;
         ep.label_logit = label_logit;
-        ep.lp_kind = lp_kind();
+        ep.lp_kind = tc32() ? LP_FP16 : lp_kind();
+        ep.split3 = tc32() ? 1 : 0;
+        const int ld = tc32() ? 2 * H : H;
         Prof prof(this, CAT_LMHEAD, 2.0 * n_u * c.vocab_size * H, st);
-        UNIMM_TRY(gemm_umma_bf16(g_h.h, H, lm_decoder.wlp, H, n_u, c.vocab_size, H, ep, 256, 0, st));
+        UNIMM_TRY(gemm_umma_bf16(g_h.h, ld, lm_decoder.wlp, ld, n_u, c.vocab_size, H, ep, 256, 0, st));
     }
     UNIMM_TRY(lse_merge(partials, gemm_umma_lse_tiles(c.vocab_size), n_u, lse_u, st));
-    UNIMM_TRY(label_scores(g_h.h, H, lm_decoder.wlp, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, lp_kind(), row_logp, row_ul, st));
+    if (tc32()) UNIMM_TRY(label_scores_f32(g_h.f, H, lm_decoder.w32, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, row_logp, row_ul, st));
+    else UNIMM_TRY(label_scores(g_h.h, H, lm_decoder.wlp, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, lp_kind(), row_logp, row_ul, st));
     return 0;
 }
 
@@ -1117,7 +1121,7 @@ int unimm_engine::forward_packed(const unimm_packed_batch_t& in, float* d_seq_sc
     ac.pk = &in;
     const int n = in.n_lm_rows;
     // labelled rows shared by several candidates (the unit-wide B_0 row of a scores-only batch): LM head once per unique row
-    const bool dedup = lp() && lm_dedup && n > 0 && in.n_lm_unique > 0 && in.n_lm_unique < n && in.d_lm_urows && in.d_lm_uidx;
+    const bool dedup = (lp() || tc32()) && lm_dedup && n > 0 && in.n_lm_unique > 0 && in.n_lm_unique < n && in.d_lm_urows && in.d_lm_uidx;
     keep_rows_ = dedup ? in.d_lm_urows : in.d_lm_rows;
     n_keep_ = dedup ? in.n_lm_unique : n;
     UNIMM_TRY(run_encoder(M, Mv, ac, st));

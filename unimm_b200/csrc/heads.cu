@@ -200,6 +200,29 @@ __global__ void label_score_kernel(const bf16* __restrict__ h, int ldh, const bf
     }
 }
 
+// fp32 operands (fp32-class mode): the label logit as an fp32 dot product of the hidden row and the fp32 embedding row
+__global__ void label_score_f32_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ E, int lde, const float* __restrict__ bias,
+                                       const int* __restrict__ uidx, const int* __restrict__ labels, const float* __restrict__ lse, int n, int K,
+                                       float* __restrict__ logp, float* __restrict__ ul) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int u = uidx[i], lab = labels[i];
+    const float4* a = reinterpret_cast<const float4*>(h + static_cast<size_t>(u) * ldh);
+    const float4* b = reinterpret_cast<const float4*>(E + static_cast<size_t>(lab) * lde);
+    float acc = 0.f;
+    for (int c = lane; c < K / 4; c += 32) {
+        const float4 x = a[c], y = __ldg(b + c);
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float lp = (acc + bias[lab]) - lse[u];
+        logp[i] = lp;
+        ul[i] = logf(fmaxf(1.0f - expf(lp), 1e-6f));
+    }
+}
+
 __global__ void scatter_scores_kernel(const float* __restrict__ logp, const float* __restrict__ ul,
                                       const int* __restrict__ flat_rows, int n, float* token_logp, float* token_ul) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,6 +422,15 @@ int label_scores(const bf16* h, int ldh, const bf16* E, int lde, const float* bi
     UNIMM_CHECK(K % 8 == 0 && ldh % 8 == 0 && lde % 8 == 0, "label_scores: rows must be 16-byte aligned");
     if (lp_kind == LP_FP16) label_score_kernel<true><<<(n + 3) / 4, 128, 0, stream>>>(h, ldh, E, lde, bias, uidx, labels, lse, n, K, logp, ul);
     else label_score_kernel<false><<<(n + 3) / 4, 128, 0, stream>>>(h, ldh, E, lde, bias, uidx, labels, lse, n, K, logp, ul);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int label_scores_f32(const float* h, int ldh, const float* E, int lde, const float* bias, const int* uidx, const int* labels, const float* lse,
+                     int n, int K, float* logp, float* ul, cudaStream_t stream) {
+    if (n == 0) return 0;
+    UNIMM_CHECK(K % 4 == 0 && ldh % 4 == 0 && lde % 4 == 0, "label_scores: rows must be 16-byte aligned");
+    label_score_f32_kernel<<<(n + 3) / 4, 128, 0, stream>>>(h, ldh, E, lde, bias, uidx, labels, lse, n, K, logp, ul);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -197,6 +197,8 @@ int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float al
 int lse_merge(const float2* partials, int tiles, int rows, float* lse, cudaStream_t stream);
 int label_scores(const bf16* h, int ldh, const bf16* E, int lde, const float* bias, const int* uidx, const int* labels, const float* lse,
                  int n, int K, int lp_kind, float* logp, float* ul, cudaStream_t stream);
+int label_scores_f32(const float* h, int ldh, const float* E, int lde, const float* bias, const int* uidx, const int* labels, const float* lse,
+                     int n, int K, float* logp, float* ul, cudaStream_t stream);
 int lse_from_partials(const float2* partials, int tiles, const float* label_logit, int rows, float* logp, float* ul,
                       cudaStream_t stream);
 // scatter the compact per-row results to dense [B,S] (zero elsewhere) and sum per sequence (val_lm.py:131-136)

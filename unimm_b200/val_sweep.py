@@ -137,7 +137,7 @@ def gpu_metrics(scores: torch.Tensor, gt_index: torch.Tensor, ndcg_scores: Optio
 
 def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1, images_per_step: int = 8,
               metrics_fn: Optional[Callable] = None, group=None, prefetch: int = 1, gather_device=None,
-              timing: Optional[dict] = None) -> Dict[str, object]:
+              timing: Optional[dict] = None, records_rank: Optional[int] = None) -> Dict[str, object]:
     """Score this rank's images, all-gather the scores, rank them and assemble metrics + EvalAI records (on every rank).
 
     ``items`` is the GLOBAL list (every rank passes the same one; only its own shard is scored).
@@ -185,12 +185,20 @@ def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1
     m = dict(metrics_fn(scores, gt, ndcg_scores, rel))
     ranks = m.pop("ranks")
     t_metrics = time.perf_counter()
-    ranks_l = ranks.tolist()
-    records = [{"image_id": int(items[i].image_id), "round_id": j + 1, "ranks": ranks_l[i][j]} for i in range(n) for j in range(n_rounds)]
+    # EvalAI records (val_lm.py:152-167) are written by ONE process: build them on ``records_rank`` only (None: every rank)
+    records = None
+    if records_rank is None or records_rank == rank:
+        records = evalai_records(items, ranks)
     if timing is not None:
         timing.update(score_s=t_scored - t_start, gather_s=t_gathered - t_scored, metrics_s=t_metrics - t_gathered,
                       records_s=time.perf_counter() - t_metrics, steps=len(steps))
-    return {"scores": scores.cpu(), "metrics": m, "predictions": records}
+    return {"scores": scores.cpu(), "metrics": m, "predictions": records, "ranks": ranks}
+
+
+def evalai_records(items: Sequence[DialogItem], ranks: torch.Tensor) -> List[dict]:
+    """``{"image_id", "round_id" (1-based), "ranks"}`` per (image, round) — the reference's ranks_json (val_lm.py:152-167)."""
+    ranks_l = ranks.tolist()
+    return [{"image_id": int(it.image_id), "round_id": j + 1, "ranks": ranks_l[i][j]} for i, it in enumerate(items) for j in range(len(ranks_l[i]))]
 
 
 def write_predictions(records: List[dict], path: str) -> None:
@@ -227,12 +235,15 @@ def synthetic_sweep(n_images: int, images_per_step: int = 8, precision: str = "f
     warm = synthetic_items(range(world * images_per_step))
     run_sweep(warm, scorer, rank, world, images_per_step, metrics_fn=metrics_fn, gather_device=dev, prefetch=prefetch)
     del warm
+    from .sharding import gather_scores
+    gather_scores(torch.zeros(len(mine), len(items[0].gt_index) * len(items[0].relevance)), n_images, rank, world, device=dev)        # the exchange once at its real size
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     timing: Dict[str, float] = {}
     t0 = time.perf_counter()
-    res = run_sweep(items, scorer, rank, world, images_per_step, metrics_fn=metrics_fn, gather_device=dev, prefetch=prefetch, timing=timing)
+    res = run_sweep(items, scorer, rank, world, images_per_step, metrics_fn=metrics_fn, gather_device=dev, prefetch=prefetch, timing=timing,
+                    records_rank=0)
     torch.cuda.synchronize(dev)
     dt = torch.tensor([time.perf_counter() - t0, timing["score_s"]], device=dev, dtype=torch.float64)
     if world > 1:
@@ -243,8 +254,8 @@ def synthetic_sweep(n_images: int, images_per_step: int = 8, precision: str = "f
                   score_phase_seconds=float(dt[1]), score_phase_candidates_per_sec=n_cand / float(dt[1]),
                   phases_rank0={k: v for k, v in timing.items()}, prefetch=prefetch, images_per_step=images_per_step, world=world,
                   precision=precision, generation_seconds_rank0=gen_s, verify_shared=verify_shared,
-                  note="wall clock of the whole driver on every rank (max over ranks): C++ packing from the per-image int64 arrays, "
-                       "H2D, forward, D2H, NCCL all-gather of the scores, GPU ranks / metrics, EvalAI records; synthetic generation excluded")
+                  note="wall clock of the whole driver (max over ranks): C++ packing from the per-image int64 arrays, H2D, forward, D2H, "
+                       "NCCL all-gather of the scores, GPU ranks / metrics on every rank, EvalAI records on rank 0; synthetic generation excluded")
     if rank == 0 and out_path:
         write_predictions(res["predictions"], out_path)
     eng.close()
