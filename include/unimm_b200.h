@@ -168,6 +168,12 @@ int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, f
                          float* d_token_logp, void* stream);
 /* Same with every pointer of `hb` (and the outputs) in HOST memory: H2D + forward + D2H + sync inside the call. */
 int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream);
+/* The same in two halves, so that a sweep keeps the device busy across steps: submit enqueues H2D + forward + D2H of the batch on
+ * `stream` using staging slot 0 or 1 and returns at once (the host arrays of `hb` and the result buffers must stay untouched until
+ * the matching wait); wait blocks until that slot's scores have landed and reports an out-of-range id like unimm_check_ids.
+ * Submit step i + 1 into the other slot before waiting for step i. */
+int unimm_submit_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, int slot, float* h_seq_score, float* h_nsp_scores, void* stream);
+int unimm_wait_packed(unimm_engine_t* e, int slot);
 
 /* ---- packing on the host, from the reference's own layout -------------------------------------------------
  * What val_lm.py:55-121 holds for one step BEFORE the dense masks exist: per image one int64 [rows, S] tensor per field

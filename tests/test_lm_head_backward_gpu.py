@@ -52,4 +52,4 @@ def test_lm_head_backward_matches_autograd(precision, tol, n):
         assert err < tol, name
     assert (out["logp"].cpu().double() - lp).abs().max().item() < 2e-3
     # rows without a loss get no gradient
-    assert out["dH"][2::7].abs().max().item() == 0.0
+    assert out["dH"][(w == 0).nonzero().view(-1).cuda()].abs().max().item() == 0.0

@@ -203,3 +203,38 @@ def test_config5_dense_annotation_step_at_size(full_cfg, name, precision):
     assert abs(nsp - g["nsp_ce_unweighted"].item()) < tol            # nsp_weight None: the engine's NSP loss IS the unweighted CE
     assert abs(ndcg - float(g["neural_ndcg_loss"])) < (2e-4 if precision == "fp32" else 2e-2)
     assert abs(total - float(g["total_loss"])) < 3 * tol
+
+
+def test_two_steps_in_flight_equal_blocking_calls(full_cfg):
+    """unimm_submit_packed_host / unimm_wait_packed (step i + 1 queued in the second staging slot behind step i) return exactly
+    what the blocking unimm_score_packed_host returns for each step, in either slot, across repeated use."""
+    g, _ = load_golden("gen8_default")
+    eng = engine(full_cfg, g["weight_seed"], g["perturbed"], "fp16", 64)
+    steps = []
+    for i in (1, 2, 3):
+        (f, l, m), rs = syn.synth_dialog_rounds(60 + i, rounds=(1 + i, 9), n_candidates=20 + 5 * i)
+        steps.append([ImageArrays.from_rounds(rs, f, l, m)])
+    packers = [FlatPacker() for _ in range(3)]
+    want = []
+    for k, st in enumerate(steps):
+        v = packers[0].pack(st)
+        out = torch.zeros(v.n_cands).pin_memory()
+        eng.score_packed_host(v, out)
+        want.append(out.clone())
+    outs = [torch.zeros(4096).pin_memory() for _ in range(2)]
+    got, pending = [], None
+    for rep in range(2):
+        for k, st in enumerate(steps):
+            i = rep * len(steps) + k
+            v = packers[i % 3].pack(st)
+            eng.submit_packed_host(v, i & 1, outs[i & 1])
+            if pending is not None:
+                eng.wait_packed(pending[0])
+                got.append(outs[pending[0]][:pending[1]].clone())
+            pending = (i & 1, v.n_cands)
+    eng.wait_packed(pending[0])
+    got.append(outs[pending[0]][:pending[1]].clone())
+    for i, o in enumerate(got):
+        assert torch.equal(o, want[i % len(steps)]), i
+    for p in packers:
+        p.close()

@@ -96,6 +96,8 @@ SYMBOLS = {
     "unimm_forward": (C.c_int, [_P, C.POINTER(Batch), C.POINTER(Outputs), _P]),
     "unimm_forward_packed": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _P, _P, _P, _P]),
     "unimm_score_packed_host": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _P, _P, _P]),
+    "unimm_submit_packed_host": (C.c_int, [_P, C.POINTER(PackedBatchStruct), _I, _P, _P, _P]),
+    "unimm_wait_packed": (C.c_int, [_P, _I]),
     "unimm_check_ids": (C.c_int, [_P, _P]),
     "unimm_packer_create": (C.c_int, [_I, _I, _I, _I, C.POINTER(C.c_void_p)]),
     "unimm_packer_destroy": (C.c_int, [_P]),

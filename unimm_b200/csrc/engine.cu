@@ -150,7 +150,8 @@ struct unimm_engine {
     int* err_flag = nullptr;       // device: set by the embedding kernel on an out-of-range token / position / type id
     int* h_err = nullptr;          // pinned copy, read after a stream synchronisation (check_ids)
     HostPath host_path;            // staging of unimm_score_host / unimm_score_packed_host: per engine, so engines on different
-    PackedStage packed_stage;      // devices can be driven from different threads
+    PackedStage packed_stage[2];   // devices can be driven from different threads; two slots: step i + 1 is uploaded and queued
+    cudaEvent_t slot_done[2] = {nullptr, nullptr};   // behind step i (unimm_submit_packed_host / unimm_wait_packed)
     int* dense_jobs = nullptr;     // [Bmax, 8] text -> image jobs of the dense layout: (b*S, S, b*R, R, 0, b, 0, 0)
     // host staging for unimm_score_host
     void* h_stage = nullptr;
@@ -263,13 +264,15 @@ struct unimm_engine {
     int forward(const unimm_batch_t& in, const unimm_outputs_t& out, cudaStream_t st);
     // the reference's nn.Embedding raises on an id outside its table (models/vilbert_dialog.py:334-350); the embedding kernel clamps
     // and raises err_flag instead: queue its copy behind the forward, and after the caller's synchronisation turn it into an error
-    int queue_id_check(cudaStream_t st) {
-        UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_err, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int queue_id_check(cudaStream_t st, int slot = 0) {
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_err + slot, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         UNIMM_CUDA_CHECK(cudaMemsetAsync(err_flag, 0, sizeof(int), st));      // sticky between checks, cleared by each one
         return 0;
     }
-    int id_check_result() {
-        UNIMM_CHECK(h_err[0] == 0, "token, position or token-type id outside its embedding table (the reference raises an IndexError here)");
+    int id_check_result(int slot = 0) {
+        const int bad = h_err[slot];
+        h_err[slot] = 0;
+        UNIMM_CHECK(bad == 0, "token, position or token-type id outside its embedding table (the reference raises an IndexError here)");
         return 0;
     }
     int forward_packed(const unimm_packed_batch_t& in, float* d_seq_score, float* d_nsp_scores, float* d_token_logp, cudaStream_t st);
@@ -550,7 +553,7 @@ int unimm_engine::alloc_workspace() {
     }
     UNIMM_TRY(dalloc(&err_flag, 4));
     UNIMM_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_err), 4 * sizeof(int)));
-    h_err[0] = 0;
+    h_err[0] = h_err[1] = h_err[2] = h_err[3] = 0;
     {
         std::vector<int> jobs(static_cast<size_t>(Bmax) * 8, 0);
         for (int b = 0; b < Bmax; ++b) {
@@ -1210,6 +1213,8 @@ int unimm_destroy(unimm_engine_t* e) {
     cudaDeviceSynchronize();
     if (e->host_path.h_rows) cudaFreeHost(e->host_path.h_rows);
     if (e->h_err) cudaFreeHost(e->h_err);
+    for (cudaEvent_t ev : e->slot_done)
+        if (ev) cudaEventDestroy(ev);
     for (void* p : e->owned) cudaFree(p);
     delete e;
     return 0;
@@ -1255,8 +1260,9 @@ int unimm_forward_packed(unimm_engine_t* e, const unimm_packed_batch_t* batch, f
     return e->forward_packed(*batch, d_seq_score, d_nsp_scores, d_token_logp, static_cast<cudaStream_t>(stream));
 }
 
-int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream) {
+int unimm_submit_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, int slot, float* h_seq_score, float* h_nsp_scores, void* stream) {
     UNIMM_CHECK(e && hb && h_seq_score, "null argument");
+    UNIMM_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
     UNIMM_CHECK(e->finalized, "weights not finalized");
     const unimm_config_t& c = e->cfg;
     const int U = hb->n_units, C = hb->n_cands, M = hb->n_text_rows, R = c.num_regions, F = c.v_feature_size;
@@ -1264,7 +1270,8 @@ int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, f
                     C <= e->Bmax * c.seq_len, "packed batch exceeds the engine workspace");
     DeviceGuard g(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PackedStage& ps = e->packed_stage;
+    PackedStage& ps = e->packed_stage[slot];
+    if (e->slot_done[slot] == nullptr) UNIMM_CUDA_CHECK(cudaEventCreateWithFlags(&e->slot_done[slot], cudaEventDisableTiming));
     if (ps.i32 == nullptr) {
         const size_t rows = static_cast<size_t>(e->Bmax) * c.seq_len;
         // ids, types, pos (3M) + row_iv (4M) + lm rows/labels/unique rows/indices (4M) + cand arrays (3C+1 <= 3M+1) + jobs (6U*8)
@@ -1325,9 +1332,22 @@ int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, f
     UNIMM_TRY(e->forward_packed(d, d_score, h_nsp_scores ? d_nsp : nullptr, nullptr, st));
     UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_seq_score, d_score, sizeof(float) * C, cudaMemcpyDeviceToHost, st));
     if (h_nsp_scores) UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_nsp_scores, d_nsp, sizeof(float) * 2 * C, cudaMemcpyDeviceToHost, st));
-    UNIMM_TRY(e->queue_id_check(st));
-    UNIMM_CUDA_CHECK(cudaStreamSynchronize(st));
-    return e->id_check_result();
+    UNIMM_TRY(e->queue_id_check(st, slot));
+    UNIMM_CUDA_CHECK(cudaEventRecord(e->slot_done[slot], st));
+    return 0;
+}
+
+int unimm_wait_packed(unimm_engine_t* e, int slot) {
+    UNIMM_CHECK(e != nullptr && (slot == 0 || slot == 1), "bad argument");
+    UNIMM_CHECK(e->slot_done[slot] != nullptr, "nothing was submitted to this slot");
+    DeviceGuard g(e->device);
+    UNIMM_CUDA_CHECK(cudaEventSynchronize(e->slot_done[slot]));
+    return e->id_check_result(slot);
+}
+
+int unimm_score_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, float* h_seq_score, float* h_nsp_scores, void* stream) {
+    UNIMM_TRY(unimm_submit_packed_host(e, hb, 0, h_seq_score, h_nsp_scores, stream));
+    return unimm_wait_packed(e, 0);
 }
 
 int unimm_verify_masks(const unimm_seq_desc_t* d_desc, int B, int S, int R, const void* d_txt_mask, int txt_elem_bytes,

@@ -189,6 +189,16 @@ class Engine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(lib.unimm_score_packed_host(self._h, C.byref(s), ptr(seq_score), ptr(nsp_scores), C.c_void_p(stream)))
 
+    def submit_packed_host(self, pb, slot: int, seq_score: torch.Tensor, nsp_scores: Optional[torch.Tensor] = None) -> None:
+        """Asynchronous half of ``score_packed_host``: enqueue H2D + forward + D2H into staging slot 0 / 1 and return; ``pb`` and the
+        (pinned) result tensors must stay untouched until ``wait_packed(slot)``."""
+        s = pb.c_struct()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib.unimm_submit_packed_host(self._h, C.byref(s), int(slot), ptr(seq_score), ptr(nsp_scores), C.c_void_p(stream)))
+
+    def wait_packed(self, slot: int) -> None:
+        check(lib.unimm_wait_packed(self._h, int(slot)))
+
     # ------------------------------------------------------------------------------------------ profiling
     PROFILE_CLASSES = ("gemm", "attention", "layernorm", "lm_head", "gemm_ln")     # gemm = umma_gemm_kernel, gemm_ln = umma_gemm_ln_kernel
 

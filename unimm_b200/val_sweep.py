@@ -86,7 +86,7 @@ class PackedScorer:
     Every step is checked for the precondition of the layout — the candidates of a round share their context token for token —
     unless ``verify_shared=False`` (the check is a threaded memcmp inside the packer, ~2 ms per step)."""
 
-    def __init__(self, engine, verify_shared: bool = True, depth: int = 1, seq_len: int = 256, num_regions: int = 37,
+    def __init__(self, engine, verify_shared: bool = True, depth: int = 2, seq_len: int = 256, num_regions: int = 37,
                  feature_size: int = 2048, threads: int = 2):
         from .flat_packer import FlatPacker
         self.engine = engine
@@ -115,6 +115,21 @@ class PackedScorer:
         out = self._out[:pb.n_cands]
         self.engine.score_packed_host(pb, out)
         return out.view(len(items), len(items[0].rounds), -1).clone()
+
+    # ---- asynchronous halves (unimm_submit_packed_host / unimm_wait_packed): the device gets step i + 1 queued behind step i
+    def submit(self, pb, items: List[DialogItem], slot: int) -> None:
+        if not hasattr(self, "_outs"):
+            self._outs = [None, None]
+        if self._outs[slot] is None or self._outs[slot].numel() < pb.n_cands:
+            self._outs[slot] = torch.empty(max(pb.n_cands, 1024), dtype=torch.float32).pin_memory()
+        self.engine.submit_packed_host(pb, slot, self._outs[slot])
+        self._shape = getattr(self, "_shape", {})
+        self._shape[slot] = (len(items), len(items[0].rounds), pb.n_cands)
+
+    def collect(self, slot: int) -> torch.Tensor:
+        self.engine.wait_packed(slot)
+        n_img, n_rounds, n_cands = self._shape[slot]
+        return self._outs[slot][:n_cands].view(n_img, n_rounds, -1).clone()
 
     def __call__(self, items: List[DialogItem]) -> torch.Tensor:
         return self.score(self.prepare(items), items)
@@ -157,7 +172,17 @@ def run_sweep(items: Sequence[DialogItem], scorer, rank: int = 0, world: int = 1
             raise ValueError("scorer must return [images, rounds, options]")
         local.append(out.float().cpu())
 
-    if prefetch > 0 and hasattr(scorer, "prepare") and hasattr(scorer, "score") and steps:
+    if prefetch > 0 and hasattr(scorer, "submit") and hasattr(scorer, "collect") and steps:
+        # asynchronous scorer: step i is packed (a few ms of host work) and queued on the device while step i - 1 still runs there;
+        # its scores are collected only after step i + 1... has been queued, so the device never waits for the host
+        pending = None
+        for i, step in enumerate(steps):
+            scorer.submit(scorer.prepare(step), step, i & 1)
+            if pending is not None:
+                keep(scorer.collect(pending[0]), pending[1])
+            pending = (i & 1, step)
+        keep(scorer.collect(pending[0]), pending[1])
+    elif prefetch > 0 and hasattr(scorer, "prepare") and hasattr(scorer, "score") and steps:
         # two-phase scorer: the host-side preparation of step i + 1 overlaps the device work of step i
         # (``prefetch`` steps in flight on as many worker threads: the packer spends most of its time inside numpy, GIL released)
         from collections import deque
@@ -229,7 +254,7 @@ def synthetic_sweep(n_images: int, images_per_step: int = 8, precision: str = "f
     items = synthetic_items(range(n_images), only=mine)                     # generation is not part of the sweep's clock
     gen_s = time.perf_counter() - t0
     eng = Engine(cfg, random_state_dict(cfg, 0), precision=precision, max_sequences=images_per_step * 52, device=local_rank)
-    scorer = packed_scorer(eng, verify_shared=verify_shared, depth=max(1, prefetch))
+    scorer = packed_scorer(eng, verify_shared=verify_shared, depth=max(2, prefetch))
     metrics_fn = lambda s, g, ns, r: gpu_metrics(s, g, ns, r, dev)
     # warm-up: one step per rank through the whole driver (kernels, pinned staging, NCCL channels, metric kernels)
     warm = synthetic_items(range(world * images_per_step))
