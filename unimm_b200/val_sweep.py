@@ -233,7 +233,7 @@ def write_predictions(records: List[dict], path: str) -> None:
 
 
 def synthetic_sweep(n_images: int, images_per_step: int = 8, precision: str = "fp16", prefetch: int = 1, verify_shared: bool = True,
-                    out_path: str = "", rank: int = 0, world: int = 1, local_rank: int = 0) -> Dict[str, object]:
+                    out_path: str = "", rank: int = 0, world: int = 1, local_rank: int = 0, on_timed_start=None) -> Dict[str, object]:
     """BASELINE.json configs[1]: ``n_images`` synthetic images x 10 rounds x 100 candidates, STRONG-scaled over ``world`` ranks
     (image i -> rank i mod world), scores all-gathered over NCCL, ranks / metrics on the GPU, EvalAI records on every rank.
     ``torch.distributed`` must already be initialised with the NCCL backend when ``world`` > 1.  Returns rank 0's report:
@@ -266,6 +266,8 @@ def synthetic_sweep(n_images: int, images_per_step: int = 8, precision: str = "f
     if world > 1:
         dist.barrier()
     timing: Dict[str, float] = {}
+    if on_timed_start is not None:
+        on_timed_start()
     t0 = time.perf_counter()
     res = run_sweep(items, scorer, rank, world, images_per_step, metrics_fn=metrics_fn, gather_device=dev, prefetch=prefetch, timing=timing,
                     records_rank=0)
