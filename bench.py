@@ -9,13 +9,15 @@ generative (autoregressive-MLM) masks, text padded to 256, 36 regions + global, 
 --workload steps (default; what the driver times): one STEP = --images-per-step images = that many x 10 rounds x 100 candidates per
 rank as ONE prefix-shared forward; ranks own different images (weak scaling, no collective on the data path; one NCCL all-gather of
 the scores at the end).
-  value     candidates/s, packed inputs already resident in HBM, CUDA-event timed, max over ranks
+  value     candidates/s, packed inputs already resident in HBM, CUDA-event timed over K steps, max over ranks
   e2e       the same measured from the REFERENCE'S OWN HOST LAYOUT (per image one int64 [1000, 256] tensor per field + one feature
             block, dataloader_visdial.py:437-457): every step packs on the host (C++ packer, csrc/packer.cu, into pinned staging),
             copies H2D, runs the forward and copies the scores D2H; step i + 1 is packed and queued (second staging slot) while the
             device runs step i, every step's scores are waited for and read on the host — all inside the timed region (CUDA events
             on the launch stream around the K steps; the wall clock of the same region is reported beside it)
-  roofline  the dominant tcgen05 GEMM class: algorithmic FLOPs / CUDA-event time of those launches inside the timed region
+  roofline  the dominant tcgen05 GEMM class: algorithmic FLOPs / CUDA-event time of those launches, from a second pass over the same
+            K steps with an event pair around every launch (`profiled_pass`; the events cost 2-3 %, so `value` comes from the pass
+            without them)
   cpu_baseline  the oracle (CPU port of the reference path, val_lm-style full logits) on the host cores (rank 0, N=1)
   bf16_mode  (fp16 runs only) value / e2e / % of peak of the SAME step in bf16 mode, measured in the same process
 
@@ -304,8 +306,8 @@ def measure_packed(args, eng, scorer, step_list, dev, world, rank, stream, sampl
             gathered = [torch.empty_like(scores) for _ in range(world)]
         dist.all_gather(gathered, scores)
     barrier()
+    # ---- pass 1: the K timed steps, nothing but the path's own launches on the stream -> `value`
     lib.unimm_reset_launch_count()
-    eng.profile_begin()                                      # per-class events are recorded inside the timed region: they only deflate `value`
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.mark_start()
@@ -317,11 +319,20 @@ def measure_packed(args, eng, scorer, step_list, dev, world, rank, stream, sampl
     ev1.record(stream)
     barrier()
     launches = int(lib.unimm_launch_count())
+    # ---- pass 2: the same K steps again with a CUDA-event pair around every launch of the engine (unimm_profile_begin/end) ->
+    # `roofline` and the per-class shares; the ~320 extra event records per step cost 2-3 %, which is why `value` is not taken here
+    eng.profile_begin()
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record(stream)
+    for i in range(args.steps):
+        step_device(i, scores[i])
+    pv1.record(stream)
+    barrier()
     prof = eng.profile_end()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    ms = torch.tensor([ev0.elapsed_time(ev1), pv0.elapsed_time(pv1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total, ms_prof = float(ms[0]), float(ms[1])
 
     # ---- end to end from the reference's host layout: per step pack (host C++) + H2D + forward + D2H, with step i + 1 packed and
     # queued on the device (unimm_submit_packed_host, second staging slot) before step i's scores are waited for
@@ -357,7 +368,7 @@ def measure_packed(args, eng, scorer, step_list, dev, world, rank, stream, sampl
     assert torch.allclose(ref_scores.cpu(), last[0].reshape(-1), atol=1e-5), "host and device paths disagree"
     total = world * args.steps * cands_per_step
     return {"value": total / (ms_total * 1e-3), "ms_total": ms_total, "e2e": total / (float(ms2[0]) * 1e-3), "e2e_wall": total / (float(ms2[1]) * 1e-3),
-            "h2d": h2d_bytes, "d2h": 4 * cands_per_step, "launches": launches, "prof": prof, "lm_rows": lm_rows, "packed_rows": packed_rows,
+            "h2d": h2d_bytes, "d2h": 4 * cands_per_step, "launches": launches, "prof": prof, "ms_prof": ms_prof, "lm_rows": lm_rows, "packed_rows": packed_rows,
             "cands_per_step": cands_per_step, "gathered": gathered}
 
 
@@ -561,6 +572,10 @@ def main_ours(args):
         r = measure_packed(args, eng, scorer, step_list, dev, world, rank, stream, sampler)
         clocks = sampler.stop() if sampler else None
         value, ms_total, e2e_value, h2d, d2h, launches, prof = r["value"], r["ms_total"], r["e2e"], r["h2d"], r["d2h"], r["launches"], r["prof"]
+        ms_prof = r["ms_prof"]
+        extra["profiled_pass"] = {"ms_per_step": ms_prof / args.steps,
+                                  "what": "the K steps repeated with a CUDA-event pair around every engine launch: source of `roofline` and of the "
+                                          "per-class shares (shares are fractions of THIS pass); `value` / `ms_per_step` come from the pass without them"}
         cands_per_step, packed_rows = r["cands_per_step"], r["packed_rows"]
         rows_per_cand = r["lm_rows"] / cands_per_step
         extra["e2e_wall_clock"] = r["e2e_wall"]
@@ -578,7 +593,7 @@ def main_ours(args):
             extra["bf16_mode"] = {"value": rb["value"], "e2e": rb["e2e"], "ms_per_step": rb["ms_total"] / args.steps, "executed_tflops": tf_b,
                                   "pct_of_bf16_peak_burst": tf_b / pk["burst"], "pct_of_bf16_peak_sustained": tf_b / pk["sustained"],
                                   "gemm_tflops": gb["work"] / (gb["ms"] * 1e-3) / 1e12 if gb["ms"] > 0 else None,
-                                  "share_of_step": {k: round(v["ms"] / rb["ms_total"], 4) for k, v in rb["prof"].items()},
+                                  "share_of_step": {k: round(v["ms"] / rb["ms_prof"], 4) for k, v in rb["prof"].items()},
                                   "note": "bf16 operands, fp32 residual stream, exact-form GELU; parity bound 2e-2 (tests/test_parity_gpu.py)"}
     else:
         eng = Engine(cfg, sd, precision=args.precision, max_sequences=chunk, device=local)
@@ -635,6 +650,7 @@ def main_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms_total = float(ms.item())
+        ms_prof = ms_total                                   # dense layout: one pass, profiled
         total_cands = world * args.steps * cands_per_step
         value = total_cands / (ms_total * 1e-3)
         for i in range(min(args.warmup, 2)):
@@ -665,7 +681,7 @@ def main_ours(args):
         achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         tf = lambda c: (prof[c]["work"] / (prof[c]["ms"] * 1e-3) / 1e12) if prof[c]["ms"] > 0 else 0.0
         traffic, traffic_src = gemm_traffic(g["launches"] // max(1, args.steps), packed)
-        share = {k: round(v["ms"] / (ms_total * 1.0), 4) for k, v in prof.items()}
+        share = {k: round(v["ms"] / (ms_prof * 1.0), 4) for k, v in prof.items()}
         step_tflops = executed / (ms_total * 1e-3) / 1e12
         workload = ("configs[1]: synthetic VisDial v1.0 val sweep, generative scoring; 1 step = %d image(s) = %d rounds x 100 candidates "
                     "per rank" % (cands_per_step // SEQ_PER_IMAGE, cands_per_step // 100))
