@@ -52,7 +52,7 @@ def descriptors_from_masks(attention_mask: torch.Tensor, co_attention_mask: torc
     # first masked-copy row L allows [1, ctx) and itself — ctx of them.  So L is the first row >= ctx whose allowed-column count
     # is not its own index; this also holds for sequences truncated at S (L + last_len > S, :205-209), where row 0 no longer
     # tells T.  No such row: the visible copy itself runs into S (L >= S): L = S describes the same mask.
-    rs = attention_mask.long().sum(-1)                                   # [B,S] allowed columns per row
+    rs = attention_mask.sum(-1, dtype=torch.int64)                       # [B,S] allowed columns per row
     r = torch.arange(S, device=rs.device).view(1, S)
     brk = (r >= ctx.view(-1, 1)) & (rs != r)
     L_gen = torch.where(brk.any(-1), brk.float().argmax(-1), torch.full_like(ctx, S))

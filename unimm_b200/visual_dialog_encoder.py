@@ -70,6 +70,19 @@ class VisualDialogEncoder(nn.Module):
             self._dirty = False
         return self._engine
 
+    def _masks_on_device(self, attention_mask, co_attention_mask):
+        """The dense masks are only read to derive (and verify) the 4-integer descriptors: do that on the engine's device instead of
+        with CPU reductions over [B,S,S] (the reference's callers hand over CPU tensors, train.py:113-129).  int64 masks are narrowed
+        to bool on the host first (8x fewer bytes over PCIe)."""
+        dev = self.engine().device
+        if attention_mask.device != dev:
+            if attention_mask.dtype not in (torch.bool, torch.uint8):
+                attention_mask = attention_mask != 0
+            attention_mask = attention_mask.to(dev, non_blocking=True)
+        if co_attention_mask.device != dev:
+            co_attention_mask = co_attention_mask.to(dev, non_blocking=True)
+        return attention_mask, co_attention_mask
+
     # ------------------------------------------------------------------ fast entry
     @torch.no_grad()
     def score(self, input_ids, image_feat, image_loc, token_type_ids, token_position_ids, masked_lm_labels,
@@ -78,7 +91,7 @@ class VisualDialogEncoder(nn.Module):
         """Per-sequence generative scores (val_lm.py:131-136) and NSP logits; chunks internally."""
         eng = self.engine()
         if desc is None:
-            desc = descriptors_from_masks(attention_mask, co_attention_mask, verify=self.verify_masks)
+            desc = descriptors_from_masks(*self._masks_on_device(attention_mask, co_attention_mask), verify=self.verify_masks)
         B = input_ids.shape[0]
         outs = {k: [] for k in want}
         for s in range(0, B, eng.max_sequences):
@@ -112,7 +125,7 @@ class VisualDialogEncoder(nn.Module):
             image_attention_mask = torch.ones(image_feat.shape[:2])
         if attention_mask is None or co_attention_mask is None:
             raise ValueError("attention_mask and co_attention_mask are required (the reference callers always pass them)")
-        desc = descriptors_from_masks(attention_mask, co_attention_mask, verify=self.verify_masks)
+        desc = descriptors_from_masks(*self._masks_on_device(attention_mask, co_attention_mask), verify=self.verify_masks)
         training = next_sentence_label is not None and masked_lm_labels is not None and image_target is not None
         want = []
         if output_nsp_scores:
