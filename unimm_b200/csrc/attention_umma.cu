@@ -331,6 +331,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
                 // ---- (2) pass 2: p = 2^(s*sl - m*sl), 16-bit pairs written back over S (columns [0, n1p / 2))
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                const bool poly = !(dbg & 8);           // UNIMM_ATTN_DBG=8: every exponential on the SFU (A/B timing)
                 auto emit_p = [&](const uint32_t* v, int c) {
                     uint32_t pk[16];
                     const bool full = c >= c_lo && c + 32 <= c_hi;
@@ -338,8 +339,13 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     for (int j = 0; j < 32; j += 4) {
                         float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl, -msl));
                         float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl, -msl));
-                        float p2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), sl, -msl));
-                        float p3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), sl, -msl));
+                        float p2, p3;
+                        if (poly) {                     // half of the exponentials off the SFU (exp2_poly2, attn_common.cuh)
+                            exp2_poly2(fmaf(__uint_as_float(v[j + 2]), sl, -msl), fmaf(__uint_as_float(v[j + 3]), sl, -msl), p2, p3);
+                        } else {
+                            p2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), sl, -msl));
+                            p3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), sl, -msl));
+                        }
                         if (!full) {
                             const int cj = c + j;
                             if (!((cj >= c_lo && cj < c_hi) || cj == c_self)) p0 = 0.f;

@@ -43,6 +43,26 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x for x <= 0 on the FMA / integer pipes (no SFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-4 minimax
+// polynomial (max relative error 7.6e-6 — far below the 16-bit rounding of the stored probability), 2^n by an exponent-field add.
+// Two lanes at once on the packed-fp32 pipe.  Used for HALF of the probabilities of the tcgen05 attention's pass 2, whose two
+// softmax warpgroups otherwise queue on the 16-per-clock ex2 unit; anything below 2^-125 comes out as ~0.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+    using namespace f32x2;
+    constexpr float kMagic = 12582912.f;          // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+    x0 = fmaxf(x0, -125.f);
+    x1 = fmaxf(x1, -125.f);
+    const float t0 = x0 + kMagic, t1 = x1 + kMagic;
+    const uint64_t f = pack(x0 - (t0 - kMagic), x1 - (t1 - kMagic));
+    uint64_t r = fma(dup(0.009278289042413235f), f, dup(0.05586502328515053f));
+    r = fma(r, f, dup(0.2403089553117752f));
+    r = fma(r, f, dup(0.6931295394897461f));
+    r = fma(r, f, dup(0.9999978542327881f));
+    float q0, q1;
+    unpack(r, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 __device__ __forceinline__ unsigned long long low_bits(int n) {   // n in [0,64]
     return n >= 64 ? ~0ull : ((1ull << n) - 1ull);
 }
