@@ -331,7 +331,7 @@ attn_cand_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
                 // ---- (2) pass 2: p = 2^(s*sl - m*sl), 16-bit pairs written back over S (columns [0, n1p / 2))
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                const bool poly = !(dbg & 8);           // UNIMM_ATTN_DBG=8: every exponential on the SFU (A/B timing)
+                const bool poly = (dbg & 16) != 0;      // UNIMM_ATTN_DBG=16: half of the exponentials on the FMA pipe (measured SLOWER: DESIGN.md 5c)
                 auto emit_p = [&](const uint32_t* v, int c) {
                     uint32_t pk[16];
                     const bool full = c >= c_lo && c + 32 <= c_hi;

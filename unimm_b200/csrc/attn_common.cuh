@@ -45,8 +45,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 // 2^x for x <= 0 on the FMA / integer pipes (no SFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-4 minimax
 // polynomial (max relative error 7.6e-6 — far below the 16-bit rounding of the stored probability), 2^n by an exponent-field add.
-// Two lanes at once on the packed-fp32 pipe.  Used for HALF of the probabilities of the tcgen05 attention's pass 2, whose two
-// softmax warpgroups otherwise queue on the 16-per-clock ex2 unit; anything below 2^-125 comes out as ~0.
+// Two lanes at once on the packed-fp32 pipe.  An EXPERIMENT (UNIMM_ATTN_DBG=16): half of the probabilities of the tcgen05 attention's
+// pass 2 computed this way instead of on the 16-per-clock ex2 unit.  Parity-green, but measured 1 % slower on the bench step (the
+// softmax warps are issue- / latency-bound, the ~9 extra issue slots per element pair cost more than the SFU queue they relieve),
+// so it is off by default; anything below 2^-125 comes out as ~0.
 __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
     using namespace f32x2;
     constexpr float kMagic = 12582912.f;          // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits

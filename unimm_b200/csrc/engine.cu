@@ -152,6 +152,9 @@ struct unimm_engine {
     HostPath host_path;            // staging of unimm_score_host / unimm_score_packed_host: per engine, so engines on different
     PackedStage packed_stage[2];   // devices can be driven from different threads; two slots: step i + 1 is uploaded and queued
     cudaEvent_t slot_done[2] = {nullptr, nullptr};   // behind step i (unimm_submit_packed_host / unimm_wait_packed)
+    cudaStream_t copy_stream = nullptr;              // the upload of step i + 1 runs here, beside step i's kernels
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
     int* dense_jobs = nullptr;     // [Bmax, 8] text -> image jobs of the dense layout: (b*S, S, b*R, R, 0, b, 0, 0)
     // host staging for unimm_score_host
     void* h_stage = nullptr;
@@ -1215,6 +1218,9 @@ int unimm_destroy(unimm_engine_t* e) {
     if (e->h_err) cudaFreeHost(e->h_err);
     for (cudaEvent_t ev : e->slot_done)
         if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->h2d_done)
+        if (ev) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (void* p : e->owned) cudaFree(p);
     delete e;
     return 0;
@@ -1272,6 +1278,14 @@ int unimm_submit_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     PackedStage& ps = e->packed_stage[slot];
     if (e->slot_done[slot] == nullptr) UNIMM_CUDA_CHECK(cudaEventCreateWithFlags(&e->slot_done[slot], cudaEventDisableTiming));
+    if (e->h2d_done[slot] == nullptr) UNIMM_CUDA_CHECK(cudaEventCreateWithFlags(&e->h2d_done[slot], cudaEventDisableTiming));
+    if (e->copy_stream == nullptr) UNIMM_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    // The slot's previous occupant has been waited for (unimm_wait_packed) before it is reused, so its staging arena is free NOW:
+    // upload on the copy stream, concurrently with whatever the other slot's step is still computing on `st`.
+    cudaStream_t cs = e->copy_stream;
+    // (a caller that reuses a slot WITHOUT having waited still gets ordered behind the previous occupant: no-op once it is done)
+    if (e->slot_used[slot]) UNIMM_CUDA_CHECK(cudaStreamWaitEvent(cs, e->slot_done[slot], 0));
+    e->slot_used[slot] = true;
     if (ps.i32 == nullptr) {
         const size_t rows = static_cast<size_t>(e->Bmax) * c.seq_len;
         // ids, types, pos (3M) + row_iv (4M) + lm rows/labels/unique rows/indices (4M) + cand arrays (3C+1 <= 3M+1) + jobs (6U*8)
@@ -1279,6 +1293,7 @@ int unimm_submit_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, 
         UNIMM_TRY(e->dalloc(&ps.i32, ps.i32_cap));
         ps.f32_cap = static_cast<size_t>(e->Bmax) * R * (F + 6) + rows * 3 + 64;
         UNIMM_TRY(e->dalloc(&ps.f32, ps.f32_cap));
+        UNIMM_CUDA_CHECK(cudaDeviceSynchronize());      // dalloc clears on the legacy stream, which the non-blocking copy stream does not follow
     }
     // the staged key ranges must fit the capacities the kernels were sized with (the arrays are host memory here: check them)
     for (int j = 0; j < hb->n_jobs_text_self; ++j)
@@ -1293,14 +1308,14 @@ int unimm_submit_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, 
         *out = nullptr;
         if (h == nullptr || n == 0) return 0;
         UNIMM_CHECK(io + n <= ps.i32_cap, "packed host batch larger than the staging buffer");
-        UNIMM_CUDA_CHECK(cudaMemcpyAsync(ps.i32 + io, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(ps.i32 + io, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
         *out = ps.i32 + io;
         io += (n + 3) & ~size_t(3);
         return 0;
     };
     auto put_f = [&](const float* h, size_t n, const float** out) -> int {
         UNIMM_CHECK(h != nullptr && fo + n <= ps.f32_cap, "packed host batch larger than the staging buffer");
-        UNIMM_CUDA_CHECK(cudaMemcpyAsync(ps.f32 + fo, h, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        UNIMM_CUDA_CHECK(cudaMemcpyAsync(ps.f32 + fo, h, n * sizeof(float), cudaMemcpyHostToDevice, cs));
         *out = ps.f32 + fo;
         fo += (n + 3) & ~size_t(3);
         return 0;
@@ -1329,6 +1344,8 @@ int unimm_submit_packed_host(unimm_engine_t* e, const unimm_packed_batch_t* hb, 
     float* d_score = ps.f32 + fo;
     float* d_nsp = d_score + ((C + 3) & ~3);
     UNIMM_CHECK(fo + static_cast<size_t>(C) * 3 + 8 <= ps.f32_cap, "packed host batch larger than the staging buffer");
+    UNIMM_CUDA_CHECK(cudaEventRecord(e->h2d_done[slot], cs));
+    UNIMM_CUDA_CHECK(cudaStreamWaitEvent(st, e->h2d_done[slot], 0));
     UNIMM_TRY(e->forward_packed(d, d_score, h_nsp_scores ? d_nsp : nullptr, nullptr, st));
     UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_seq_score, d_score, sizeof(float) * C, cudaMemcpyDeviceToHost, st));
     if (h_nsp_scores) UNIMM_CUDA_CHECK(cudaMemcpyAsync(h_nsp_scores, d_nsp, sizeof(float) * 2 * C, cudaMemcpyDeviceToHost, st));
