@@ -306,6 +306,12 @@ size_t unimm_k_lm_head_backward_scratch(int rows, int V, int K);
 int unimm_k_lm_head_backward(const void* d_H_lp, int ldh, const void* d_E_lp, int lde, int rows, int V, int K, const float* d_bias,
                              const int32_t* d_labels, const float* d_weight, float grad_scale, float* d_dH, float* d_dE, float* d_dbias,
                              float* d_logp, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream);
+/* dgrad / wgrad of one nn.Linear  y = x W^T + b  on tcgen05 (SURVEY.md 8f item 1 building block; every projection of the path is one):
+ * dY fp32 [M, N] (leading dimension ldy), X 16-bit [M, K], W 16-bit [N, K]  ->  dX = dY W fp32 [M, K], dW = dY^T X fp32 [N, K],
+ * db = column sums of dY fp32 [N]  (each output optional).  N % 64 == 0.  d_scratch: unimm_k_linear_backward_scratch(M, N, K) bytes. */
+size_t unimm_k_linear_backward_scratch(int M, int N, int K);
+int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X_lp, int ldx, const void* d_W_lp, int ldw, int M, int N, int K,
+                            float* d_dX, float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream);
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
                       void* d_y_lp, int lp_kind, void* stream);
 int unimm_k_cast_lp(const float* d_src, void* d_dst_lp, int64_t n, int lp_kind, void* stream);

@@ -53,3 +53,25 @@ def test_lm_head_backward_matches_autograd(precision, tol, n):
     assert (out["logp"].cpu().double() - lp).abs().max().item() < 2e-3
     # rows without a loss get no gradient
     assert out["dH"][(w == 0).nonzero().view(-1).cuda()].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 3e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("shape", [(300, 3072, 768), (1000, 768, 3072), (77, 2304, 768)])
+def test_linear_backward_matches_autograd(precision, tol, shape):
+    """dgrad / wgrad / db of one projection (unimm_k_linear_backward) against fp64 autograd; the incoming gradient is tiny (1e-6:
+    below fp16's normal range) to exercise the power-of-two scaling."""
+    from unimm_b200.lm_head_grad import linear_backward
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    X = torch.randn(M, K, generator=g).to(dt).float()
+    W = (0.02 * torch.randn(N, K, generator=g)).to(dt).float()
+    dY = 1e-6 * torch.randn(M, N, generator=g)
+    out = linear_backward(dY.cuda(), X, W, precision=precision)
+    dX = dY.double() @ W.double()
+    dW = dY.double().t() @ X.double()
+    db = dY.double().sum(0)
+    for name, mine, ref in (("dX", out["dX"], dX), ("dW", out["dW"], dW), ("db", out["db"], db)):
+        err = (mine.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"[{precision}] {shape} {name}: max |err| / max |ref| = {err:.3e}")
+        assert err < (1e-5 if name == "db" else tol), name

@@ -1616,6 +1616,50 @@ int unimm_k_lm_head_backward(const void* d_H, int ldh, const void* d_E, int lde,
     return 0;
 }
 
+size_t unimm_k_linear_backward_scratch(int M, int N, int K) {
+    const size_t Mp = (static_cast<size_t>(M) + 63) / 64 * 64;
+    // dY16 [M, N] + dY16^T [N, Mp] + X^T [K, Mp] + W^T [K, N] (16-bit) + the scale pair
+    return 2 * (static_cast<size_t>(M) * N + N * Mp + K * Mp + static_cast<size_t>(K) * N) + 4096;
+}
+
+int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
+                            float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
+    UNIMM_CHECK(d_dY && d_X && d_W && d_scratch && M > 0 && N > 0 && K > 0, "bad argument");
+    UNIMM_CHECK(N % 64 == 0 && K % 8 == 0 && ldy % 2 == 0, "linear backward: N must be a multiple of 64 (the dgrad contraction), K of 8");
+    UNIMM_CHECK(scratch_bytes >= unimm_k_linear_backward_scratch(M, N, K), "scratch smaller than unimm_k_linear_backward_scratch()");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Mp = (M + 63) / 64 * 64;
+    char* p = static_cast<char*>(d_scratch);
+    auto carve = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~size_t(255); return q; };
+    float* scale = reinterpret_cast<float*>(carve(16));
+    bf16* dY16 = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(M) * N));
+    bf16* dYT = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(N) * Mp));
+    bf16* XT = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(K) * Mp));
+    bf16* WT = reinterpret_cast<bf16*>(carve(2 * static_cast<size_t>(K) * N));
+    UNIMM_CHECK(static_cast<size_t>(p - static_cast<char*>(d_scratch)) <= scratch_bytes, "scratch carve overflow");
+    // the incoming gradient as a 16-bit operand: fp16 gets a power-of-two scale from its own maximum (gradients are routinely below
+    // fp16's normal range), multiplied back out by the GEMM epilogues straight from device memory
+    UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st));
+    UNIMM_TRY(cast_scaled_lp(d_dY, ldy, M, N, scale, dY16, N, lp_kind, st));
+    if (d_dX != nullptr) {        // dX [M, K] = dY [M, N] · W [N, K]: contraction over N, W operand = W^T (K-major in N)
+        UNIMM_TRY(transpose_16(static_cast<const bf16*>(d_W), ldw, N, K, WT, N, st));
+        GemmEpilogue ep;
+        ep.lp_kind = lp_kind; ep.out_f32 = d_dX; ep.ldo_f32 = K; ep.alpha_ptr = scale + 1;
+        UNIMM_TRY(gemm_umma_bf16(dY16, N, WT, N, M, K, N, ep, 0, 0, st));
+    }
+    if (d_dW != nullptr) {        // dW [N, K] = dY^T [N, M] · X [M, K]: contraction over the rows (zero-padded to a multiple of 64)
+        UNIMM_CUDA_CHECK(cudaMemsetAsync(dYT, 0, 2 * static_cast<size_t>(N) * Mp, st));
+        UNIMM_CUDA_CHECK(cudaMemsetAsync(XT, 0, 2 * static_cast<size_t>(K) * Mp, st));
+        UNIMM_TRY(transpose_16(dY16, N, M, N, dYT, Mp, st));
+        UNIMM_TRY(transpose_16(static_cast<const bf16*>(d_X), ldx, M, K, XT, Mp, st));
+        GemmEpilogue ep;
+        ep.lp_kind = lp_kind; ep.out_f32 = d_dW; ep.ldo_f32 = K; ep.alpha_ptr = scale + 1;
+        UNIMM_TRY(gemm_umma_bf16(dYT, Mp, XT, Mp, N, K, Mp, ep, 0, 0, st));
+    }
+    if (d_db != nullptr) UNIMM_TRY(column_sums_f32(d_dY, ldy, M, N, d_db, st));
+    return 0;
+}
+
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
                       void* d_y_lp, int lp_kind, void* stream) {
     return layernorm_rows(d_x, ldx, rows, H, d_gamma, d_beta, d_y_f32, static_cast<bf16*>(d_y_lp), lp_kind, static_cast<cudaStream_t>(stream));

@@ -458,9 +458,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         y[i] = stage[r * 8 + (ch ^ (r & 7))];
                     }
                     __syncwarp();   // the staging block is rewritten by the next chunk
-                    if (ep.alpha != 1.f) {
+                    const float alpha = ep.alpha_ptr != nullptr ? __ldg(ep.alpha_ptr) : ep.alpha;
+                    if (alpha != 1.f) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { y[i].x *= ep.alpha; y[i].y *= ep.alpha; y[i].z *= ep.alpha; y[i].w *= ep.alpha; }
+                        for (int i = 0; i < 8; ++i) { y[i].x *= alpha; y[i].y *= alpha; y[i].z *= alpha; y[i].w *= alpha; }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { y[i].x += b4.x; y[i].y += b4.y; y[i].z += b4.z; y[i].w += b4.w; }
@@ -507,9 +508,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     continue;
                 }
                 // ---- generic path (ragged last columns, unaligned leading dimensions): one row per thread
-                if (ep.alpha != 1.f) {
+                {
+                    const float alpha = ep.alpha_ptr != nullptr ? __ldg(ep.alpha_ptr) : ep.alpha;
+                    if (alpha != 1.f) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] *= ep.alpha;
+                        for (int j = 0; j < 32; ++j) x[j] *= alpha;
+                    }
                 }
                 if (ep.bias != nullptr) {
 #pragma unroll
@@ -733,7 +737,7 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     UNIMM_CHECK(ep.dz == nullptr || (ep.dzT != nullptr && ep.lse != nullptr && ep.coef != nullptr && ep.labels != nullptr && ep.bias != nullptr &&
                                      (ep.ldz & 7) == 0 && (ep.dz_cols & 1) == 0 && ep.dz_cols <= ep.ldz && ep.ldzt >= M),
                 "dz epilogue: incomplete arguments");
-    UNIMM_CHECK(ep.alpha == 1.f || (!lse && ep.out_bf16 == nullptr), "alpha applies to the fp32-output epilogue only");
+    UNIMM_CHECK((ep.alpha == 1.f && ep.alpha_ptr == nullptr) || (!lse && ep.out_bf16 == nullptr), "alpha applies to the fp32-output epilogue only");
     UNIMM_CHECK(!ep.split3 || (!ep.w_perm16 && ep.lp_kind == LP_FP16), "split3 takes fp16 hi | lo planes (plain or log-sum-exp epilogue)");
     UNIMM_CHECK(!ep.out_hilo || (ep.out_bf16 != nullptr && N % 32 == 0 && (ep.ldo_bf16 & 3) == 0 && (ep.hilo_off & 3) == 0 &&
                                  ep.ldo_bf16 >= (ep.hilo_off > 0 ? ep.hilo_off : N) + N && (reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0),

@@ -101,6 +101,52 @@ __global__ void row_sums16_kernel(const uint16_t* __restrict__ x, int ld, int ro
     if (lane == 0) out[r] = s * alpha;
 }
 
+// ---- dgrad / wgrad helpers ------------------------------------------------------------------------------------------------
+__global__ void amax_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ bits) {
+    unsigned mx = 0u;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const unsigned u = __float_as_uint(fabsf(x[i]));
+        mx = u > mx ? u : mx;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(bits, mx);
+}
+__global__ void scale_from_amax_kernel(const unsigned* __restrict__ bits, int want_scale, float* __restrict__ out2) {
+    const float amax = __uint_as_float(*bits);
+    float s = 1.f;
+    if (want_scale && amax > 0.f && isfinite(amax)) {
+        int e;
+        frexpf(amax, &e);                    // amax = m * 2^e, m in [0.5, 1)
+        s = ldexpf(1.f, 10 - e);             // amax * s in [2^9, 2^10): far from fp16's 65504 and from its subnormals
+    }
+    out2[0] = s;
+    out2[1] = 1.f / s;
+}
+__global__ void cast_scaled_kernel(const float* __restrict__ x, int ldx, int rows, int cols, const float* __restrict__ scale,
+                                   bf16* __restrict__ y, int ldy, int lp_kind) {
+    const float s = scale[0];
+    const int cv = cols / 2;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < static_cast<size_t>(rows) * cv;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / cv;
+        const int c = static_cast<int>(i % cv) * 2;
+        const float2 v = *reinterpret_cast<const float2*>(x + r * ldx + c);
+        *reinterpret_cast<uint32_t*>(y + r * ldy + c) = pack_lp2(v.x * s, v.y * s, lp_kind);
+    }
+}
+__global__ void column_sums_kernel(const float* __restrict__ x, int ldx, int rows, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f, comp = 0.f;               // Kahan: rows can be in the tens of thousands
+    for (int r = 0; r < rows; ++r) {
+        const float v = x[static_cast<size_t>(r) * ldx + c] - comp;
+        const float t = s + v;
+        comp = (t - s) - v;
+        s = t;
+    }
+    out[c] = s;
+}
+
 __global__ void segment_sum_kernel(const float* __restrict__ vals, const int* __restrict__ off, int C, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -382,6 +428,33 @@ int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float al
     if (rows == 0) return 0;
     if (lp_kind == LP_FP16) row_sums16_kernel<true><<<(rows + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), ld, rows, cols, alpha, out);
     else row_sums16_kernel<false><<<(rows + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), ld, rows, cols, alpha, out);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream) {
+    // out2[0] doubles as the atomicMax cell before it receives the scale
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), stream));
+    int grid = static_cast<int>((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    amax_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(x, n, reinterpret_cast<unsigned*>(out2 + 1));
+    scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const unsigned*>(out2 + 1), want_scale, out2);
+    UNIMM_LAUNCH_CHECK(2);
+    return 0;
+}
+
+int cast_scaled_lp(const float* x, int ldx, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind, cudaStream_t stream) {
+    UNIMM_CHECK(rows > 0 && cols % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0, "cast_scaled: even columns and leading dimensions");
+    const size_t n = static_cast<size_t>(rows) * (cols / 2);
+    int grid = static_cast<int>((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    cast_scaled_kernel<<<grid, 256, 0, stream>>>(x, ldx, rows, cols, scale, y, ldy, lp_kind);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int column_sums_f32(const float* x, int ldx, int rows, int cols, float* out, cudaStream_t stream) {
+    column_sums_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(x, ldx, rows, cols, out);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -28,6 +28,7 @@ struct GemmEpilogue {
     int hilo_off = 0;              //   hilo_off + c of the same row (0 = N: an [M, 2N] matrix)
     bool w_perm16 = false;         // W rows are in fragment order (permute_weight_rows mode 1): enables the smem-free 16-bit epilogue
     float alpha = 1.f;             // plain fp32-output paths: out = act(alpha * acc + bias) (+ residual)
+    const float* alpha_ptr = nullptr;   // the same factor read from device memory (wins; lets a scale computed on the device stay there)
     // LSE-mode variant "dz" (LM-head backward, heads.cu: lm_head_backward): instead of the partials, write
     //   dz[row, col] = coef[row] * (exp(x - lse[row]) - [col == labels[row]])     x = acc + bias
     // as 16-bit values to dz [M, ldz] (columns < dz_cols) and, transposed, to dzT [N, ldzt]
@@ -193,6 +194,11 @@ int transpose_16(const bf16* src, int lds, int rows, int cols, bf16* dst, int ld
 // clamped at 1e-6), p = exp(logp)
 int lm_loss_coef(const float* logp, const float* weight, int n, float scale, float* coef, cudaStream_t stream);
 int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float alpha, float* out, cudaStream_t stream);
+// dgrad / wgrad helpers (unimm_k_linear_backward): out2[0] = 2^k with max|x| * 2^k in [2^9, 2^10) (1 when want_scale == 0 or x == 0),
+// out2[1] = 1 / out2[0];  y16 = lp(x * out2[0]);  colsum[j] = sum_i x[i, j]
+int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream);
+int cast_scaled_lp(const float* x, int ldx, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind, cudaStream_t stream);
+int column_sums_f32(const float* x, int ldx, int rows, int cols, float* out, cudaStream_t stream);
 // tcgen05 LM head tail: merge the per-tile (max, sum) partials
 int lse_merge(const float2* partials, int tiles, int rows, float* lse, cudaStream_t stream);
 int label_scores(const bf16* h, int ldh, const bf16* E, int lde, const float* bias, const int* uidx, const int* labels, const float* lse,

@@ -38,3 +38,30 @@ def lm_head_backward(h: torch.Tensor, E: torch.Tensor, bias: torch.Tensor, label
     check(lib.unimm_k_lm_head_backward(ptr(h16), K, ptr(E16), K, n, V, K, ptr(b), ptr(lab), ptr(w), float(grad_scale), ptr(dH), ptr(dE),
                                        ptr(dbias), ptr(logp), ptr(scratch), nbytes, kind, stream))
     return {"dH": dH, "dE": dE, "dbias": dbias, "logp": logp}
+
+
+def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor, precision: str = "fp16", want=("dX", "dW", "db")):
+    """dgrad / wgrad / bias gradient of ``y = x W^T + b`` on tcgen05 (``unimm_k_linear_backward``): dY fp32 [M,N], X [M,K], W [N,K]
+    (cast here to the 16-bit operand format) -> dict of fp32 tensors."""
+    if not dY.is_cuda:
+        raise ValueError("linear_backward runs on a CUDA device (B200); there is no CPU path")
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    kind = LP_FP16 if precision == "fp16" else LP_BF16
+    dev = dY.device
+    dY = dY.float().contiguous()
+    X16, W16 = X.to(dev, dt).contiguous(), W.to(dev, dt).contiguous()
+    M, N = dY.shape
+    K = X16.shape[1]
+    nbytes = lib.unimm_k_linear_backward_scratch(M, N, K)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {}
+    if "dX" in want:
+        out["dX"] = torch.empty(M, K, device=dev)
+    if "dW" in want:
+        out["dW"] = torch.empty(N, K, device=dev)
+    if "db" in want:
+        out["db"] = torch.empty(N, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.unimm_k_linear_backward(ptr(dY), N, ptr(X16), K, ptr(W16), K, M, N, K, ptr(out.get("dX")), ptr(out.get("dW")), ptr(out.get("db")),
+                                      ptr(scratch), nbytes, kind, stream))
+    return out
