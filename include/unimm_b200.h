@@ -314,6 +314,11 @@ int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X_lp, int 
                             float* d_dX, float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream);
 int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d_gamma, const float* d_beta, float* d_y_f32,
                       void* d_y_lp, int lp_kind, void* stream);
+/* Backward of BertLayerNorm (models/vilbert_dialog.py:270-279; eps inside the sqrt, biased variance) and of the erf GELU (:115-121),
+ * fp32: dx [rows, H], dgamma / dbeta [H] from dy and the layer's INPUT x; dx = dy * gelu'(x) (in place allowed). */
+int unimm_k_layernorm_backward(const float* d_dy, const float* d_x, int rows, int H, const float* d_gamma, float* d_dx, float* d_dgamma,
+                               float* d_dbeta, void* stream);
+int unimm_k_gelu_backward(const float* d_dy, const float* d_x, int64_t n, float* d_dx, void* stream);
 int unimm_k_cast_lp(const float* d_src, void* d_dst_lp, int64_t n, int lp_kind, void* stream);
 /* unimm_k_attention (dense [B, S] layout): elem_kind = 0: fp32 tensors, 1: bf16, 2: fp16.  impl: 0 = CUDA-core kernel, 1 = mma.sync kernel (16-bit),
  * 2 = tcgen05 / TMEM kernel (16-bit, text self-attention with descriptor masks, D = 64, S <= 256). */

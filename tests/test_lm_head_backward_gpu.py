@@ -75,3 +75,41 @@ def test_linear_backward_matches_autograd(precision, tol, shape):
         err = (mine.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
         print(f"[{precision}] {shape} {name}: max |err| / max |ref| = {err:.3e}")
         assert err < (1e-5 if name == "db" else tol), name
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-2), ("bf16", 6e-2)])
+def test_whole_lm_head_backward_matches_autograd(precision, tol):
+    """cls.predictions (transform dense -> erf-GELU -> LayerNorm -> tied decoder + bias) under the L / UL loss: the chained device
+    kernels against fp64 autograd of the same module — gradient w.r.t. the head's input rows and every parameter of the head."""
+    from unimm_b200.lm_head_grad import lm_head_block_backward
+    g = torch.Generator().manual_seed(21)
+    n, V, K = 200, 30522, 768
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    x = torch.randn(n, K, generator=g).to(dt).float()
+    P = {"transform.dense.weight": (0.03 * torch.randn(K, K, generator=g)).to(dt).float(), "transform.dense.bias": 0.05 * torch.randn(K, generator=g),
+         "transform.LayerNorm.weight": 1.0 + 0.1 * torch.randn(K, generator=g), "transform.LayerNorm.bias": 0.1 * torch.randn(K, generator=g),
+         "decoder.weight": 0.02 * torch.randn(V, K, generator=g), "bias": 0.1 * torch.randn(V, generator=g)}
+    P["decoder.weight"][:40] *= 25.0
+    P["decoder.weight"] = P["decoder.weight"].to(dt).float()
+    labels = torch.randint(0, V, (n,), generator=g)
+    labels[: n // 3] = torch.randint(0, 40, (n // 3,), generator=g)
+    w = torch.ones(n)
+    w[1::3] = -1.0
+    scale = 1.0 / float((w != 0).sum())
+    out = lm_head_block_backward(x.cuda(), P, labels, w, grad_scale=scale, precision=precision)
+    # fp64 reference of the same module
+    xr = x.double().requires_grad_(True)
+    R = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    t = xr @ R["transform.dense.weight"].t() + R["transform.dense.bias"]
+    gl = t * 0.5 * (1.0 + torch.erf(t / 2.0 ** 0.5))
+    mu, var = gl.mean(-1, keepdim=True), gl.var(-1, unbiased=False, keepdim=True)
+    h = (gl - mu) / torch.sqrt(var + 1e-12) * R["transform.LayerNorm.weight"] + R["transform.LayerNorm.bias"]
+    z = h @ R["decoder.weight"].t() + R["bias"]
+    lp = torch.log_softmax(z, -1).gather(1, labels.view(-1, 1))[:, 0]
+    loss = -(w[w > 0].double() * lp[w > 0]).sum() - torch.log(torch.clamp(1.0 - lp[w == -1].exp(), min=1e-6)).sum()
+    (loss * scale).backward()
+    refs = {"dx": xr.grad, **{k: v.grad for k, v in R.items()}}
+    for name, ref in refs.items():
+        err = (out[name].cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"[{precision}] whole LM head, {name}: max |err| / max |ref| = {err:.3e}")
+        assert err < tol, name

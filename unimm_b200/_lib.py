@@ -125,6 +125,8 @@ SYMBOLS = {
     "unimm_k_linear_backward_scratch": (C.c_size_t, [_I, _I, _I]),
     "unimm_k_linear_backward": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, C.c_size_t, _I, _P]),
     "unimm_k_layernorm": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "unimm_k_layernorm_backward": (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "unimm_k_gelu_backward": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "unimm_k_cast_lp": (C.c_int, [_P, _P, C.c_int64, _I, _P]),
     "unimm_k_attention_jobs": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "unimm_k_attention_cross_jobs": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P]),

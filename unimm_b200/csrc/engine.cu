@@ -1665,6 +1665,17 @@ int unimm_k_layernorm(const float* d_x, int ldx, int rows, int H, const float* d
     return layernorm_rows(d_x, ldx, rows, H, d_gamma, d_beta, d_y_f32, static_cast<bf16*>(d_y_lp), lp_kind, static_cast<cudaStream_t>(stream));
 }
 
+int unimm_k_layernorm_backward(const float* d_dy, const float* d_x, int rows, int H, const float* d_gamma, float* d_dx, float* d_dgamma,
+                               float* d_dbeta, void* stream) {
+    UNIMM_CHECK(d_dy && d_x && d_gamma && d_dx && d_dgamma && d_dbeta, "null argument");
+    return layernorm_backward(d_dy, d_x, rows, H, d_gamma, d_dx, d_dgamma, d_dbeta, static_cast<cudaStream_t>(stream));
+}
+
+int unimm_k_gelu_backward(const float* d_dy, const float* d_x, int64_t n, float* d_dx, void* stream) {
+    UNIMM_CHECK(d_dy && d_x && d_dx && n > 0, "bad argument");
+    return gelu_backward(d_dy, d_x, static_cast<size_t>(n), d_dx, static_cast<cudaStream_t>(stream));
+}
+
 int unimm_k_cast_lp(const float* d_src, void* d_dst, int64_t n, int lp_kind, void* stream) {
     return cast_f32_to_lp(d_src, static_cast<bf16*>(d_dst), static_cast<size_t>(n), lp_kind, static_cast<cudaStream_t>(stream));
 }

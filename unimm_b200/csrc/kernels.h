@@ -92,6 +92,10 @@ int embed_text_ln_i32(const int32_t* ids, const int32_t* type_ids, const int32_t
 // y = LayerNorm(x) * gamma + beta, eps 1e-12 inside the sqrt, biased variance; x may alias y_f32.
 int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma, const float* beta, float* y_f32,
                    bf16* y_bf16, int lp_kind, cudaStream_t stream);
+// backward of layernorm_rows (dx may not alias dy; dgamma / dbeta [H] are zeroed here) and of the erf GELU
+int layernorm_backward(const float* dy, const float* x, int rows, int H, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                       cudaStream_t stream);
+int gelu_backward(const float* dy, const float* x, size_t n, float* dx, cudaStream_t stream);
 // image location term: out[r, :] = loc[idx(r), 0:5] · Wloc[H,5]^T + bloc  (fp32, K = 5)
 int image_loc_embed(const float* loc, const int* feat_index, int B, int R, int H, const float* Wloc, const float* bloc,
                     float* out, cudaStream_t stream);

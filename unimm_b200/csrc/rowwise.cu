@@ -309,6 +309,92 @@ int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaS
     return 0;
 }
 
+// ---- backward of y = LayerNorm(x) * gamma + beta (eps inside the sqrt, biased variance — BertLayerNorm, reference :270-279) ----
+//   xhat = (x - mean) * rstd;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma = sum_rows dy * xhat;  dbeta = sum_rows dy
+// One warp per row; the column sums go through per-block shared accumulators and one atomicAdd per column and block.
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int rows, const float* __restrict__ gamma,
+                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    constexpr int H = NV * 128;
+    __shared__ float s_dg[H], s_db[H];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
+        float4 xv[NV], gv[NV], dv[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            xv[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * H + (lane + 32 * i) * 4);
+            s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / H);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+            q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + kLnEps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            dv[i] = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * H + c);
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;            // xhat
+            gv[i] = make_float4(dv[i].x * gm.x, dv[i].y * gm.y, dv[i].z * gm.z, dv[i].w * gm.w);
+            sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+            sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+        }
+        const float mg = warp_sum(sg) * (1.0f / H), mgx = warp_sum(sgx) * (1.0f / H);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            float4 o;
+            o.x = rstd * (gv[i].x - mg - xv[i].x * mgx); o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
+            o.z = rstd * (gv[i].z - mg - xv[i].z * mgx); o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
+            *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * H + c) = o;
+            atomicAdd(&s_dg[c], dv[i].x * xv[i].x); atomicAdd(&s_dg[c + 1], dv[i].y * xv[i].y);
+            atomicAdd(&s_dg[c + 2], dv[i].z * xv[i].z); atomicAdd(&s_dg[c + 3], dv[i].w * xv[i].w);
+            atomicAdd(&s_db[c], dv[i].x); atomicAdd(&s_db[c + 1], dv[i].y); atomicAdd(&s_db[c + 2], dv[i].z); atomicAdd(&s_db[c + 3], dv[i].w);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { atomicAdd(dgamma + i, s_dg[i]); atomicAdd(dbeta + i, s_db[i]); }
+}
+int layernorm_backward(const float* dy, const float* x, int rows, int H, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                       cudaStream_t stream) {
+    UNIMM_CHECK(rows > 0, "layernorm backward: no rows");
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * H, stream));
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * H, stream));
+    int grid = (rows + 3) / 4;
+    if (grid > 148 * 4) grid = 148 * 4;
+    if (H == 768) layernorm_bwd_kernel<6><<<grid, 128, 0, stream>>>(dy, x, rows, gamma, dx, dgamma, dbeta);
+    else if (H == 1024) layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(dy, x, rows, gamma, dx, dgamma, dbeta);
+    else UNIMM_CHECK(false, "layernorm backward: hidden size must be 768 or 1024");
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+// backward of the exact (erf) GELU (reference :115-121): dx = dy * (Phi(x) + x * phi(x)); in place allowed (dx == dy)
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, size_t n, float* __restrict__ dx) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+        dx[i] = dy[i] * (cdf + v * pdf);
+    }
+}
+int gelu_backward(const float* dy, const float* x, size_t n, float* dx, cudaStream_t stream) {
+    int grid = static_cast<int>((n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    gelu_bwd_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(dy, x, n, dx);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
 __global__ void differ_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, int* flag) {
     bool d = false;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)

@@ -65,3 +65,39 @@ def linear_backward(dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor, precisio
     check(lib.unimm_k_linear_backward(ptr(dY), N, ptr(X16), K, ptr(W16), K, M, N, K, ptr(out.get("dX")), ptr(out.get("dW")), ptr(out.get("db")),
                                       ptr(scratch), nbytes, kind, stream))
     return out
+
+
+def lm_head_block_backward(x: torch.Tensor, params: dict, labels: torch.Tensor, weight: torch.Tensor, grad_scale: float = 1.0,
+                           precision: str = "fp16"):
+    """Backward of the WHOLE masked-LM head of the reference (``cls.predictions``: transform dense -> erf-GELU -> LayerNorm -> tied
+    decoder + bias, models/vilbert_dialog.py:982-986, :1023-1026) under the likelihood / unlikelihood loss (:1577-1595), on the rows
+    ``x [n, 768]`` that carry a label: chains ``unimm_k_lm_head_backward`` (decoder + loss), ``unimm_k_layernorm_backward``,
+    ``unimm_k_gelu_backward`` and ``unimm_k_linear_backward`` (transform).  ``params``: ``transform.dense.weight/bias``,
+    ``transform.LayerNorm.weight/bias``, ``decoder.weight`` (= word embeddings), ``bias``.  Returns the gradient with respect to ``x``
+    (what the encoder's backward starts from) and to every parameter of the head, fp32."""
+    if not x.is_cuda:
+        raise ValueError("lm_head_block_backward runs on a CUDA device (B200); there is no CPU path")
+    dev = x.device
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    kind = LP_FP16 if precision == "fp16" else LP_BF16
+    P = {k: v.to(dev, torch.float32).contiguous() for k, v in params.items()}
+    n, K = x.shape
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    x16 = x.to(dt).contiguous()
+    Wt16 = P["transform.dense.weight"].to(dt).contiguous()
+    # forward recompute of the head's activations (the engine's forward keeps none of them): t = x Wt^T + bt, g = gelu(t), h = LN(g)
+    t = torch.empty(n, K, device=dev)
+    check(lib.unimm_k_gemm_lp(ptr(x16), K, ptr(Wt16), K, n, K, K, ptr(P["transform.dense.bias"]), None, 0, 0, ptr(t), K, None, 0, 0, 0, kind, stream))
+    g = torch.empty(n, K, device=dev)
+    check(lib.unimm_k_gemm_lp(ptr(x16), K, ptr(Wt16), K, n, K, K, ptr(P["transform.dense.bias"]), None, 0, 1, ptr(g), K, None, 0, 0, 0, kind, stream))
+    h16 = torch.empty(n, K, device=dev, dtype=dt)
+    check(lib.unimm_k_layernorm(ptr(g), K, n, K, ptr(P["transform.LayerNorm.weight"]), ptr(P["transform.LayerNorm.bias"]), None, ptr(h16), kind, stream))
+    # decoder + loss
+    head = lm_head_backward(h16, P["decoder.weight"], P["bias"], labels, weight, grad_scale=grad_scale, precision=precision)
+    # LayerNorm, GELU, transform
+    dg, dgamma, dbeta = torch.empty(n, K, device=dev), torch.empty(K, device=dev), torch.empty(K, device=dev)
+    check(lib.unimm_k_layernorm_backward(ptr(head["dH"]), ptr(g), n, K, ptr(P["transform.LayerNorm.weight"]), ptr(dg), ptr(dgamma), ptr(dbeta), stream))
+    check(lib.unimm_k_gelu_backward(ptr(dg), ptr(t), n * K, ptr(dg), stream))
+    lin = linear_backward(dg, x16, Wt16, precision=precision)
+    return {"dx": lin["dX"], "transform.dense.weight": lin["dW"], "transform.dense.bias": lin["db"], "transform.LayerNorm.weight": dgamma,
+            "transform.LayerNorm.bias": dbeta, "decoder.weight": head["dE"], "bias": head["dbias"], "logp": head["logp"]}
