@@ -38,3 +38,31 @@ def test_sweep_metrics_and_ranks_match_the_oracle(full_cfg):
         i, j = rec["image_id"], rec["round_id"] - 1
         assert rec["ranks"] == ranks[i, j].tolist()
     print("sweep metrics:", {k: round(float(v), 4) for k, v in res["metrics"].items()})
+
+
+def test_nsp_sweep_matches_reference_ranking_rule(full_cfg):
+    """val.py's discriminative ranking (NSP probability, per-round min-max normalisation, ensemble sum) through run_sweep: the scores
+    equal the rule applied by hand to the engine's own NSP logits, and a two-member 'ensemble' of the same model changes nothing
+    but the scale."""
+    import numpy as np
+
+    from conftest import golden_state_dict
+    from unimm_b200.engine import Engine
+    from unimm_b200.val_sweep import NspScorer, gpu_metrics, run_sweep, synthetic_items
+    items = synthetic_items(range(2), n_candidates=12, n_rounds=3, mode="dis")
+    eng = Engine(full_cfg, golden_state_dict(full_cfg, 0, False), precision="fp16", max_sequences=64)
+    dev = eng.device
+    res = run_sweep(items, NspScorer([eng]), images_per_step=1, metrics_fn=lambda s, g, ns, r: gpu_metrics(s, g, ns, r, dev))
+    res2 = run_sweep(items, NspScorer([eng, eng]), images_per_step=2, metrics_fn=lambda s, g, ns, r: gpu_metrics(s, g, ns, r, dev))
+    assert res["scores"].shape == (2, 3, 12)
+    np.testing.assert_allclose(res2["scores"].numpy(), 2 * res["scores"].numpy(), rtol=1e-5, atol=1e-7)
+    assert torch.equal(res["ranks"].cpu(), res2["ranks"].cpu())
+    # by hand for image 0, round 1
+    it, r = items[0], items[0].rounds[1]
+    o = eng.forward(torch.from_numpy(r.tokens), torch.from_numpy(r.segments), torch.from_numpy(r.positions), torch.from_numpy(r.desc),
+                    torch.from_numpy(it.feat)[None], torch.from_numpy(it.loc)[None], torch.from_numpy(it.mask)[None],
+                    feat_index=torch.zeros(12, dtype=torch.int32), want=("nsp_scores",))
+    p = torch.softmax(o["nsp_scores"], 1)[:, 0].cpu()
+    e = (p - p.min()) / (p.max() - p.min())
+    np.testing.assert_allclose(res["scores"][0, 1].numpy(), (e / e.sum()).numpy(), rtol=1e-4, atol=1e-6)
+    eng.close()

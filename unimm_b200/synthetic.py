@@ -153,13 +153,15 @@ def synth_image(rng: np.random.RandomState, n_boxes: int = 36, feat_dim: int = 2
     return f, loc, np.ones(n_boxes + 1, np.float32)
 
 
-def synth_dialog_rounds(image_id: int, rounds: Sequence[int] = tuple(range(1, 11)), n_candidates: int = 100):
-    """All requested rounds of one synthetic image (seed = image id): (image arrays, [Round, ...])."""
+def synth_dialog_rounds(image_id: int, rounds: Sequence[int] = tuple(range(1, 11)), n_candidates: int = 100, mode: str = "gen"):
+    """All requested rounds of one synthetic image (seed = image id): (image arrays, [Round, ...]).  ``mode="dis"``: the same
+    dialogs under the discriminative layout (val.py's NSP ranking)."""
     rng = np.random.RandomState(100003 + image_id)
     img = synth_image(rng)
     out = []
+    enc = encode_round_gen if mode == "gen" else encode_round_dis
     for r in rounds:
-        out.append(encode_round_gen(synth_context(rng, r), synth_answers(rng, n_candidates)))
+        out.append(enc(synth_context(rng, r), synth_answers(rng, n_candidates)))
     # like the reference's loader (dataloader_visdial.py:437-457: one [rounds * options, 256] tensor per field and image), keep
     # the rounds of an image as row ranges of ONE array per field: the packer then gathers per image instead of per round
     cat = {f: np.concatenate([getattr(r, f) for r in out], 0) for f in ("tokens", "segments", "positions", "labels", "desc")}

@@ -53,7 +53,8 @@ class DialogItem:
         return self.arrays
 
 
-def synthetic_items(image_ids: Sequence[int], n_candidates: int = 100, only: Optional[Sequence[int]] = None, n_rounds: int = 10) -> List[DialogItem]:
+def synthetic_items(image_ids: Sequence[int], n_candidates: int = 100, only: Optional[Sequence[int]] = None, n_rounds: int = 10,
+                    mode: str = "gen") -> List[DialogItem]:
     """The synthetic VisDial-shaped sweep of BASELINE.json configs[1] (seed = image id; gt option 0 as the reference's loader).
 
     ``only``: positions (into ``image_ids``) whose dialogs are actually generated — a rank passes its own shard; the other items
@@ -69,9 +70,10 @@ def synthetic_items(image_ids: Sequence[int], n_candidates: int = 100, only: Opt
         if only is not None and k not in only:
             out.append(DialogItem(int(i), None, None, None, None, np.zeros(n_rounds, np.int64), rel_round, rel))
             continue
-        (feat, loc, mask), rounds = syn.synth_dialog_rounds(int(i), rounds=tuple(range(1, n_rounds + 1)), n_candidates=n_candidates)
+        (feat, loc, mask), rounds = syn.synth_dialog_rounds(int(i), rounds=tuple(range(1, n_rounds + 1)), n_candidates=n_candidates, mode=mode)
         it = DialogItem(int(i), feat, loc, mask, rounds, np.zeros(len(rounds), np.int64), rel_round, rel)
-        it.image_arrays()
+        if mode == "gen":
+            it.image_arrays()
         out.append(it)
     return out
 
@@ -133,6 +135,37 @@ class PackedScorer:
 
     def __call__(self, items: List[DialogItem]) -> torch.Tensor:
         return self.score(self.prepare(items), items)
+
+
+class NspScorer:
+    """The discriminative ranking of the reference's val.py (:100-161): every option of every round is one dense sequence under the
+    discriminative masks, its score is the NSP probability ``softmax(seq_relationship_score)[:, 0]``; with several models the
+    per-round min-max-normalised probabilities are summed (``unimm_ensemble_normalise``, val.py:152-161).  ``engines``: one Engine per
+    ensemble member on this rank's device.  Items must carry discriminative rounds (``synthetic_items(mode="dis")``)."""
+
+    def __init__(self, engines, chunk: int = 250):
+        self.engines = list(engines)
+        self.chunk = min(chunk, min(e.max_sequences for e in self.engines))
+
+    def __call__(self, items: List[DialogItem]) -> torch.Tensor:
+        from .rank_loss import ensemble_normalise
+        out = []
+        for it in items:
+            tok, seg, pos, desc = (torch.from_numpy(np.concatenate([getattr(r, f) for r in it.rounds])) for f in ("tokens", "segments", "positions", "desc"))
+            n, n_rounds = tok.shape[0], len(it.rounds)
+            feat, loc, mask = (torch.from_numpy(np.ascontiguousarray(a))[None] for a in (it.feat, it.loc, it.mask))
+            index = torch.zeros(n, dtype=torch.int32)
+            probs = []
+            for eng in self.engines:
+                p0 = []
+                for s0 in range(0, n, self.chunk):
+                    sl = slice(s0, s0 + self.chunk)
+                    o = eng.forward(tok[sl], seg[sl], pos[sl], desc[sl], feat, loc, mask, feat_index=index[sl], want=("nsp_scores",))
+                    p0.append(torch.softmax(o["nsp_scores"], 1)[:, 0])
+                eng.check_ids()
+                probs.append(torch.cat(p0).view(n_rounds, -1))
+            out.append(ensemble_normalise(torch.stack(probs)).cpu())           # [rounds, options]
+        return torch.stack(out)
 
 
 def packed_scorer(engine, **kw) -> PackedScorer:
