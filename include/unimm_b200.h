@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UNIMM_ABI_VERSION 2
+#define UNIMM_ABI_VERSION 3
 
 typedef struct unimm_engine unimm_engine_t;
 
@@ -339,6 +339,57 @@ int unimm_k_attention_cross_jobs(const void* d_q, int ldq, const void* d_k, int 
 int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B,
                       int heads, int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc,
                       const float* d_key_mask, int elem_kind, int impl, void* stream);
+
+/* ---- training step (reference train.py:445-463: forward + loss.backward() + optimizer.step()) ----
+ * Kernel-level entry points; the layer schedule in reverse and the saved activations are host logic (unimm_b200/train_step.py), as
+ * autograd is in the reference.  All gradients are fp32; every tensor-core operand is 16-bit (lp_kind 0 = bf16, 1 = fp16). */
+/* same as unimm_k_linear_backward; accumulate_dx != 0: dX += dY W (the residual branch's gradient is already in d_dX) */
+int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X_lp, int ldx, const void* d_W_lp, int ldw, int M, int N, int K,
+                                float* d_dX, int accumulate_dx, float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind,
+                                void* stream);
+/* mma.sync attention of the dense [B, S] layout (unimm_k_attention impl 1) that also saves the row log-sum-exp d_lse [B, heads, Sq]
+ * (natural log, softmax scale included) for the backward. */
+int unimm_k_attention_lse(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B, int heads,
+                          int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind,
+                          float* d_lse, void* stream);
+/* Backward of softmax(Q K^T / sqrt(D) + mask) V (models/vilbert_dialog.py:395-410, :681-721) from the saved 16-bit q / k / v / o and
+ * d_lse: d_dO fp32 contiguous [B*Sq, heads*D] -> d_dq [B*Sq, lddq], d_dk / d_dv [B*Skv, lddk / lddv] fp32 (head h at column h*D, so the
+ * three can be the column blocks of one [rows, 3H] matrix).  P is recomputed tile by tile; no [B, heads, Sq, Skv] tensor, no atomics.
+ * The masks are the forward's, regenerated from d_desc / d_key_mask. */
+size_t unimm_k_attention_backward_scratch(int B, int heads, int D, int Sq);
+int unimm_k_attention_backward(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, const void* d_o, int ldo,
+                               const float* d_dO, const float* d_lse, int B, int heads, int D, int Sq, int Skv, int mask_kind,
+                               const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind, float* d_dq, int lddq, float* d_dk,
+                               int lddk, float* d_dv, int lddv, void* d_scratch, size_t scratch_bytes, void* stream);
+/* text embeddings without the LayerNorm (its input is what the backward needs): word + position + (type | type-extension)
+ * (models/vilbert_dialog.py:334-352) -> d_out fp32 [rows, H]; and the scatter-add of that sum's gradient into the four tables
+ * (accumulating: the word table's gradient also receives the tied decoder's). */
+int unimm_t_embed_text_sum(const int64_t* d_ids, const int64_t* d_type_ids, const int64_t* d_pos_ids, int rows, int H, int vocab, int max_pos,
+                           int type_vocab, int type_ext, const float* d_word, const float* d_pos, const float* d_type, const float* d_type_ext,
+                           float* d_out, int* d_err_flag, void* stream);
+int unimm_t_embed_text_backward(const float* d_dsum, const int64_t* d_ids, const int64_t* d_type_ids, const int64_t* d_pos_ids, int rows, int H,
+                                int type_vocab, float* d_dword, float* d_dpos, float* d_dtype, float* d_dtype_ext, void* stream);
+/* g = erf-GELU(t) written as the 16-bit operand of the next GEMM and / or as fp32 (t, the pre-activation, stays for unimm_k_gelu_backward) */
+int unimm_t_gelu(const float* d_t, int64_t n, float* d_g_f32, void* d_g_lp, int lp_kind, void* stream);
+/* value of the likelihood / unlikelihood loss (models/vilbert_dialog.py:1577-1595) from the per-row log p that unimm_k_lm_head_backward
+ * returns: d_out[0] = scale * (sum_{w > 0} -w log p + sum_{w == -1} -log(max(1 - p, 1e-6))) */
+int unimm_t_lm_ul_value(const float* d_logp, const float* d_weight, int n, float scale, float* d_out, void* stream);
+/* fp32 element-wise: op 0: out = a + b, 1: out = a * b, 2: out = a * [b > 0], 3: out = alpha * a, 4: out = a + alpha * b (out may alias a / b) */
+int unimm_t_ew(int op, int64_t n, const float* d_a, const float* d_b, float* d_out, float alpha, void* stream);
+int unimm_t_gather_rows(const float* d_src, int lds, const int32_t* d_idx, int n, int H, float* d_dst, void* stream);
+int unimm_t_scatter_add_rows(const float* d_src, const int32_t* d_idx, int n, int H, float* d_dst, int ldd, void* stream);
+/* weighted NSP cross entropy (models/vilbert_dialog.py:1605-1621) and its gradient grad_scale * d loss / d logits [B, 2] */
+int unimm_t_nsp_ce(const float* d_logits, const int64_t* d_labels, int B, const float* d_nsp_weight, float grad_scale, float* d_loss,
+                   float* d_dlogits, void* stream);
+/* masked image KL (:1569-1574) and its gradient [rows, ldd] (columns >= C and unselected rows are zeroed); the target distribution of row r
+ * is row d_target_row[r] of d_target [., C] (NULL: row r — the reference holds one copy per sequence); d_acc2: 2 floats of scratch */
+int unimm_t_image_kl(const float* d_logits, int ld, const float* d_target, const int32_t* d_target_row, const int64_t* d_image_label, int rows,
+                     int C, float grad_scale, float* d_loss, float* d_dlogits, int ldd, float* d_acc2, void* stream);
+/* AdamW of train.py:347 (pytorch_transformers.optimization.AdamW — third-party, not vendored in the reference; restated from its published
+ * source): m, v updates, p -= lr sqrt(1 - b2^t) / (1 - b1^t) m / (sqrt(v) + eps) (correct_bias), then p -= lr wd p; g is multiplied by
+ * inv_grad_scale first; d_p_lp (optional) receives the refreshed 16-bit operand copy of p. */
+int unimm_t_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, int correct_bias, float inv_grad_scale, void* d_p_lp, int lp_kind, void* stream);
 
 #ifdef __cplusplus
 }

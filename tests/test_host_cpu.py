@@ -110,7 +110,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.unimm_abi_version() == 2
+    assert _lib.lib.unimm_abi_version() == 3
     assert _lib.LIB_PATH.startswith(ROOT)          # in-tree, so the driver sees it loaded
 
 

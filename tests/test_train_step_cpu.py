@@ -1,0 +1,130 @@
+"""CPU: the ORCHESTRATION of the training step (unimm_b200/train_step.py) — layer schedule in reverse, saved activations, fused
+Q|K|V views, padded tensors, parameter groups, AdamW ranges — run over a torch-fp64 statement of the device operations
+(tests/torch_train_ops.py) and compared with torch.autograd of the oracle.  The CUDA kernels behind the real operations are checked
+on the GPU (tests/test_train_step_gpu.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from torch_train_ops import TorchOps
+
+
+def _train_inputs(n=None):
+    g, b = load_golden("train6_perturbed")
+    from unimm_b200.descriptors import descriptors_from_masks
+    desc = descriptors_from_masks(b["txt_attention_mask"], b["co_attention_mask"])
+    sl = slice(0, n)
+    batch = {"tokens": b["tokens"][sl], "segments": b["segments"][sl], "positions": b["positions"][sl], "labels": b["mask"][sl],
+             "weights": b["weights"][sl], "desc": desc[sl], "next_sentence_label": torch.from_numpy(g["next_sentence_label"])[sl],
+             "image_feat": torch.from_numpy(g["image_feat"])[None], "image_loc": torch.from_numpy(g["image_loc"])[None],
+             "image_mask": torch.from_numpy(g["image_mask"])[None], "image_label": torch.from_numpy(g["image_label"])[None],
+             "image_target": torch.from_numpy(g["image_target"])[None], "seq_image": torch.zeros(b["tokens"][sl].shape[0], dtype=torch.int64),
+             "nsp_weight": torch.from_numpy(g["nsp_weight"])}
+    return g, b, batch
+
+
+def oracle_losses_and_grads(cfg, sd, b, g, n, dtype=torch.float64, device="cpu"):
+    """loss and d loss / d parameter from torch.autograd over the oracle's forward (the tied decoder shares the embedding tensor)."""
+    from oracle import vilbert_oracle as vo
+    p = {k: v.to(device, dtype).clone().requires_grad_() for k, v in sd.items() if k != "cls.predictions.decoder.weight"}
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    sl = slice(0, n)
+    nseq = b["tokens"][sl].shape[0]
+    ex = lambda a: torch.from_numpy(a).to(device)[None].expand(nseq, *a.shape)                          # noqa: E731
+    o = vo.forward(p, cfg, b["tokens"][sl].to(device), ex(g["image_feat"]), ex(g["image_loc"]), b["segments"][sl].to(device),
+                   b["positions"][sl].to(device), b["txt_attention_mask"][sl].to(device), ex(g["image_mask"]),
+                   b["co_attention_mask"][sl].to(device), masked_lm_labels=b["mask"][sl].to(device),
+                   next_sentence_label=torch.from_numpy(g["next_sentence_label"])[sl].to(device), image_label=ex(g["image_label"]),
+                   image_target=ex(g["image_target"]), nsp_weight=torch.from_numpy(g["nsp_weight"]).to(device),
+                   lm_weight=b["weights"][sl].to(device), dtype=dtype)
+    loss = o["lm_loss"] + o["nsp_loss"] + o["img_loss"]
+    names = [k for k in p if k != "cls.predictions.decoder.weight"]
+    grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
+    return {k: float(o[k].detach()) for k in ("lm_loss", "nsp_loss", "img_loss")}, dict(zip(names, grads))
+
+
+@pytest.mark.slow
+def test_train_step_orchestration_matches_autograd_of_the_oracle():
+    from oracle import vilbert_oracle as vo   # noqa: F401  (device-independent oracle)
+    from unimm_b200.config import tiny_config
+    from unimm_b200.train_step import TrainStep
+    from unimm_b200.weights import random_state_dict
+    cfg = tiny_config()
+    sd = random_state_dict(cfg, seed=5, perturbed=True)
+    n = 3
+    g, b, batch = _train_inputs(n)
+    ref_loss, ref_grad = oracle_losses_and_grads(cfg, sd, b, g, n)
+    ts = TrainStep(cfg, sd, TorchOps())
+    vals = ts.forward_backward(batch)
+    for k in ("lm_loss", "nsp_loss", "img_loss"):
+        assert abs(vals[k] - ref_loss[k]) < 1e-9, (k, vals[k], ref_loss[k])
+    got = ts.grad_dict()
+    worst = 0.0
+    gmax = max(float(gr.abs().max()) for gr in ref_grad.values() if gr is not None)
+    for name, gr in ref_grad.items():
+        if gr is None:                                    # parameters the forward never touches
+            assert float(got[name].abs().max()) == 0.0, name
+            continue
+        scale = max(float(gr.abs().max()), 1e-6 * gmax)      # key biases: the exact gradient is 0 (softmax is shift invariant)
+        err = float((got[name].double() - gr).abs().max()) / scale
+        worst = max(worst, err)
+        assert err < 1e-8, (name, err)
+    print(f"orchestration vs autograd: worst relative gradient error {worst:.2e} over {len(ref_grad)} tensors")
+    # the optimizer: two steps against the restated pytorch_transformers AdamW with the reference's groups
+    from oracle import adamw as oa
+    lw_path = "/root/reference/config/language_weights.json"
+    state, ref_p = {}, {k: v.double().clone() for k, v in sd.items()}
+    from unimm_b200.train_step import is_language_weight
+    if os.path.exists(lw_path):                           # the group rule against the reference's own list (build container only)
+        lw = set(json.load(open(lw_path)))
+        for k in sd:
+            if k != "cls.predictions.decoder.weight":
+                assert (("bert_pretrained." + k) in lw) == is_language_weight(k), k
+    ts2 = TrainStep(cfg, sd, TorchOps(), lr=3e-5, image_lr=5e-5, warmup_steps=1, t_total=10)
+    for it in range(2):
+        ts2.step(batch)
+        loss_i, grad_i = oracle_losses_and_grads(cfg, {k: v.float() for k, v in ref_p.items()} if False else ref_p, b, g, n)
+        lr_l, lr_v = oa.warmup_linear_nonzero_lr(it, 3e-5, 1, 10), oa.warmup_linear_nonzero_lr(it, 5e-5, 1, 10)
+        for k, gr in grad_i.items():
+            if gr is None:
+                continue
+            lr = lr_l if is_language_weight(k) else lr_v
+            wd = 0.0 if any(nd in k for nd in oa.NO_DECAY) else 0.01
+            oa.adamw_step(ref_p[k], gr, state.setdefault(k, {}), lr, weight_decay=wd)
+        ref_p["cls.predictions.decoder.weight"] = ref_p["bert.embeddings.word_embeddings.weight"]
+    new = ts2.state_dict()
+    for k, v in ref_p.items():
+        d = float((new[k].double() - v).abs().max())
+        assert d < 1e-6, (k, d)           # state_dict() exports fp32
+        moved = float((v - sd[k].double()).abs().max())
+        if not any(m in k for m in ("sep_embeddings", "q_dense")):
+            assert moved > 0, k
+
+
+def test_parameter_groups_and_flat_layout():
+    from unimm_b200.config import tiny_config
+    from unimm_b200.train_step import ParamStore, param_group
+    from unimm_b200.weights import param_shapes
+    cfg = tiny_config()
+    ps = ParamStore(cfg, TorchOps())
+    shapes = param_shapes(cfg)
+    assert set(ps.entries) == set(shapes) - {"cls.predictions.decoder.weight"}
+    # fused Q|K|V spans are gap-free
+    a = "bert.encoder.layer.0.attention.self."
+    w = ps.span(ps.p, a + "query.weight", a + "value.weight")
+    assert tuple(w.shape) == (3 * cfg.hidden_size, cfg.hidden_size)
+    b = "bert.encoder.c_layer.0.biattention."
+    assert tuple(ps.span(ps.p, b + "query2.weight", b + "value2.weight").shape) == (3 * cfg.bi_hidden_size, cfg.hidden_size)
+    assert ps.span(ps.p, b + "query1.bias", b + "value1.bias").numel() == 3 * cfg.bi_hidden_size
+    # the substring rule of train.py:323: LayerNorm1/2.weight of the connection layers DO decay, every bias does not
+    assert param_group("bert.encoder.c_layer.0.biOutput.LayerNorm1.weight") == 2
+    assert param_group("bert.encoder.c_layer.0.biOutput.LayerNorm1.bias") == 3
+    assert param_group("bert.encoder.layer.0.output.LayerNorm.weight") == 1
+    assert param_group("bert.t_pooler.dense.weight") == 2 and param_group("cls.predictions.bias") == 1
+    assert param_group("bert.embeddings.sep_embeddings.weight") == 4
+    for name, (off, pad, shp) in ps.entries.items():
+        assert off % 64 == 0 and all(p >= s for p, s in zip(pad, shp)), name

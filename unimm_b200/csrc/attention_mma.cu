@@ -233,6 +233,11 @@ attn_mma_kernel(AttnArgs a, int kv_rows_max) {
         if (row0 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row0) * a.ldo + col) = pack2<FP16>(o[i][0] * inv0, o[i][1] * inv0);
         if (row1 < Sq) *reinterpret_cast<uint32_t*>(O + static_cast<size_t>(row1) * a.ldo + col) = pack2<FP16>(o[i][2] * inv1, o[i][3] * inv1);
     }
+    if (a.lse != nullptr && t == 0) {   // natural-log domain, softmax scale included: what the backward recomputes P from
+        float* L = a.lse + (static_cast<size_t>(b) * a.heads + h) * Sq;
+        if (row0 < Sq) L[row0] = m_run[0] * a.scale + logf(l_run[0]);
+        if (row1 < Sq) L[row1] = m_run[1] * a.scale + logf(l_run[1]);
+    }
 }
 
 template <int D, bool FP16, int NW>

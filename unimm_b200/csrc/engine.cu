@@ -1624,6 +1624,11 @@ size_t unimm_k_linear_backward_scratch(int M, int N, int K) {
 
 int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
                             float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
+    return unimm_k_linear_backward_acc(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, 0, d_dW, d_db, d_scratch, scratch_bytes, lp_kind, stream);
+}
+
+int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
+                                int accumulate_dx, float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
     UNIMM_CHECK(d_dY && d_X && d_W && d_scratch && M > 0 && N > 0 && K > 0, "bad argument");
     UNIMM_CHECK(N % 64 == 0 && K % 8 == 0 && ldy % 2 == 0, "linear backward: N must be a multiple of 64 (the dgrad contraction), K of 8");
     UNIMM_CHECK(scratch_bytes >= unimm_k_linear_backward_scratch(M, N, K), "scratch smaller than unimm_k_linear_backward_scratch()");
@@ -1645,6 +1650,7 @@ int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X, int ldx
         UNIMM_TRY(transpose_16(static_cast<const bf16*>(d_W), ldw, N, K, WT, N, st));
         GemmEpilogue ep;
         ep.lp_kind = lp_kind; ep.out_f32 = d_dX; ep.ldo_f32 = K; ep.alpha_ptr = scale + 1;
+        if (accumulate_dx) { ep.residual = d_dX; ep.ldr = K; }       // dX += dY W: each element is read and rewritten by the same thread
         UNIMM_TRY(gemm_umma_bf16(dY16, N, WT, N, M, K, N, ep, 0, 0, st));
     }
     if (d_dW != nullptr) {        // dW [N, K] = dY^T [N, M] · X [M, K]: contraction over the rows (zero-padded to a multiple of 64)

@@ -134,17 +134,21 @@ __global__ void cast_scaled_kernel(const float* __restrict__ x, int ldx, int row
         *reinterpret_cast<uint32_t*>(y + r * ldy + c) = pack_lp2(v.x * s, v.y * s, lp_kind);
     }
 }
+// column sums of an [rows, cols] fp32 matrix (bias gradients): each CTA sums a 256-row slab of 128 columns (Kahan inside the slab)
+// and adds its partial to the zeroed output with one atomic per column
 __global__ void column_sums_kernel(const float* __restrict__ x, int ldx, int rows, int cols, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
-    float s = 0.f, comp = 0.f;               // Kahan: rows can be in the tens of thousands
-    for (int r = 0; r < rows; ++r) {
+    const int r0 = blockIdx.y * 256, r1 = min(rows, r0 + 256);
+    float s = 0.f, comp = 0.f;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) {
         const float v = x[static_cast<size_t>(r) * ldx + c] - comp;
         const float t = s + v;
         comp = (t - s) - v;
         s = t;
     }
-    out[c] = s;
+    atomicAdd(out + c, s);
 }
 
 __global__ void segment_sum_kernel(const float* __restrict__ vals, const int* __restrict__ off, int C, float* __restrict__ out) {
@@ -454,7 +458,8 @@ int cast_scaled_lp(const float* x, int ldx, int rows, int cols, const float* sca
 }
 
 int column_sums_f32(const float* x, int ldx, int rows, int cols, float* out, cudaStream_t stream) {
-    column_sums_kernel<<<(cols + 127) / 128, 128, 0, stream>>>(x, ldx, rows, cols, out);
+    UNIMM_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * cols, stream));
+    column_sums_kernel<<<dim3((cols + 127) / 128, (rows + 255) / 256), 128, 0, stream>>>(x, ldx, rows, cols, out);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -131,6 +131,8 @@ struct AttnArgs {
     const float* key_mask;    // [B, Skv] (MASK_KEY_VECTOR)
     float scale;              // 1/sqrt(D)
     int lp_kind;              // encoding of 16-bit q/k/v/o (ignored by the fp32 kernel)
+    float* lse = nullptr;     // optional [B, heads, Sq]: log sum_k exp(scale * q.k) over the allowed keys (mma.sync kernel only; saved
+                              //   for attention_backward_lp)
 };
 int attention_simt_f32(const AttnArgs& a, cudaStream_t stream);
 int attention_simt_lp(const AttnArgs& a, cudaStream_t stream);

@@ -1,0 +1,211 @@
+"""Device operations of the training step (``unimm_b200/train_step.py``): thin, typed wrappers over the kernel-level C ABI
+(``unimm_k_*`` / ``unimm_t_*`` of ``include/unimm_b200.h``).  PyTorch is used for device memory and the stream only; every
+arithmetic operation below is one of this library's CUDA kernels.  There is no CPU path: the constructor refuses a non-CUDA device.
+
+Conventions: ``x32`` = fp32 tensor, ``x16`` = 16-bit GEMM operand (fp16 or bf16 according to ``precision``); matrices are 2-D,
+row-major, possibly column slices of a wider matrix (the leading dimension is taken from ``stride(0)``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import LP_BF16, LP_FP16, check, lib, ptr
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+MASK_TEXT_SELF, MASK_KEY_VECTOR, MASK_CO_INTERVAL = 0, 1, 2
+EW_ADD, EW_MUL, EW_RELU_BWD, EW_SCALE, EW_AXPY = 0, 1, 2, 3, 4
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "row-major 2-D matrix expected"
+    return t.stride(0)
+
+
+class DeviceOps:
+    def __init__(self, device, precision: str = "fp16"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("the training step runs on a CUDA device (B200); there is no CPU path")
+        if precision not in ("fp16", "bf16"):
+            raise ValueError("training precision: 'fp16' or 'bf16' operands (fp32 master weights, accumulators and gradients)")
+        self.precision = precision
+        self.lp_dtype = torch.float16 if precision == "fp16" else torch.bfloat16
+        self.kind = LP_FP16 if precision == "fp16" else LP_BF16
+        self._scratch = None
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty32(self, *shape):
+        return torch.empty(*shape, device=self.device, dtype=torch.float32)
+
+    def zeros32(self, *shape):
+        return torch.zeros(*shape, device=self.device, dtype=torch.float32)
+
+    def empty16(self, *shape):
+        return torch.empty(*shape, device=self.device, dtype=self.lp_dtype)
+
+    def scratch(self, nbytes: int):
+        if self._scratch is None or self._scratch.numel() < nbytes:
+            self._scratch = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=self.device)
+        return self._scratch
+
+    # ------------------------------------------------------------------ element-wise / rows
+    def to_lp(self, x32):
+        x32 = x32.contiguous()
+        out = self.empty16(*x32.shape)
+        check(lib.unimm_k_cast_lp(ptr(x32), ptr(out), x32.numel(), self.kind, self.stream))
+        return out
+
+    def ew(self, op, a, b=None, out=None, alpha=1.0):
+        out = a if out is None else out
+        assert a.is_contiguous() and out.is_contiguous() and (b is None or b.is_contiguous())
+        check(lib.unimm_t_ew(op, a.numel(), ptr(a), ptr(b), ptr(out), float(alpha), self.stream))
+        return out
+
+    def mul(self, a, b):
+        return self.ew(EW_MUL, a, b, out=self.empty32(*a.shape))
+
+    def relu_backward(self, dy, y):
+        return self.ew(EW_RELU_BWD, dy, y, out=dy)
+
+    def gather_rows(self, src32, idx):
+        out = self.empty32(idx.numel(), src32.shape[1])
+        check(lib.unimm_t_gather_rows(ptr(src32), _ld(src32), ptr(idx), idx.numel(), src32.shape[1], ptr(out), self.stream))
+        return out
+
+    def scatter_add_rows(self, src32, idx, dst32):
+        check(lib.unimm_t_scatter_add_rows(ptr(src32), ptr(idx), idx.numel(), src32.shape[1], ptr(dst32), _ld(dst32), self.stream))
+
+    # ------------------------------------------------------------------ embeddings
+    def embed_text_sum(self, ids, seg, pos, word, pos_emb, type_emb, type_ext, type_vocab):
+        rows, H = ids.numel(), word.shape[1]
+        out = self.empty32(rows, H)
+        check(lib.unimm_t_embed_text_sum(ptr(ids), ptr(seg), ptr(pos), rows, H, word.shape[0], pos_emb.shape[0], type_vocab, type_ext.shape[0],
+                                         ptr(word), ptr(pos_emb), ptr(type_emb), ptr(type_ext), ptr(out), None, self.stream))
+        return out
+
+    def embed_text_backward(self, dsum, ids, seg, pos, g_word, g_pos, g_type, g_type_ext, type_vocab):
+        check(lib.unimm_t_embed_text_backward(ptr(dsum), ptr(ids), ptr(seg), ptr(pos), ids.numel(), dsum.shape[1], type_vocab, ptr(g_word),
+                                              ptr(g_pos), ptr(g_type), ptr(g_type_ext), self.stream))
+
+    # ------------------------------------------------------------------ LayerNorm / GELU
+    def layernorm(self, x32, gamma, beta, want32=True, want16=True):
+        rows, H = x32.shape
+        y32 = self.empty32(rows, H) if want32 else None
+        y16 = self.empty16(rows, H) if want16 else None
+        check(lib.unimm_k_layernorm(ptr(x32), _ld(x32), rows, H, ptr(gamma), ptr(beta), ptr(y32), ptr(y16), self.kind, self.stream))
+        return y32, y16
+
+    def layernorm_backward(self, dy, x32, gamma, g_gamma, g_beta):
+        """-> dx; the parameter gradients are written to ``g_gamma`` / ``g_beta``."""
+        rows, H = x32.shape
+        assert dy.is_contiguous() and x32.is_contiguous()
+        dx = self.empty32(rows, H)
+        check(lib.unimm_k_layernorm_backward(ptr(dy), ptr(x32), rows, H, ptr(gamma), ptr(dx), ptr(g_gamma), ptr(g_beta), self.stream))
+        return dx
+
+    def gelu(self, t32, want32=False, want16=True):
+        g32 = self.empty32(*t32.shape) if want32 else None
+        g16 = self.empty16(*t32.shape) if want16 else None
+        check(lib.unimm_t_gelu(ptr(t32), t32.numel(), ptr(g32), ptr(g16), self.kind, self.stream))
+        return g32, g16
+
+    def gelu_backward(self, dy, t32):
+        check(lib.unimm_k_gelu_backward(ptr(dy), ptr(t32), dy.numel(), ptr(dy), self.stream))
+        return dy
+
+    # ------------------------------------------------------------------ projections
+    def linear(self, x16, w16, bias, residual=None, act=ACT_NONE, want32=True, want16=False):
+        """y = act(x W^T + b) (+ residual) on tcgen05 -> (y32 | None, y16 | None)."""
+        M, K = x16.shape
+        N = w16.shape[0]
+        y32 = self.empty32(M, N) if want32 else None
+        y16 = self.empty16(M, N) if want16 else None
+        check(lib.unimm_k_gemm_lp(ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(bias), ptr(residual), _ld(residual) if residual is not None else 0,
+                                  act, ptr(y32), N, ptr(y16), N, 0, 0, self.kind, self.stream))
+        return y32, y16
+
+    def linear_f32(self, x32, w32, bias, residual=None, act=ACT_NONE):
+        """The same in fp32 on the CUDA cores: the handful of tiny projections (poolers, NSP head, the K = 5 location term)."""
+        M, K = x32.shape
+        N = w32.shape[0]
+        y = self.empty32(M, N)
+        check(lib.unimm_k_gemm_f32(ptr(x32), _ld(x32), ptr(w32), _ld(w32), M, N, K, ptr(bias), ptr(residual), _ld(residual) if residual is not None else 0,
+                                   act, ptr(y), N, self.stream))
+        return y
+
+    def linear_backward(self, dy32, x16, w16, g_w, g_b, need_dx=True, dx_accum=None):
+        """dgrad / wgrad / bias gradient of y = x W^T + b.  ``g_w`` [N, K] / ``g_b`` [N] receive the parameter gradients; returns dX
+        (``dx_accum`` += dY W when given)."""
+        M, N = dy32.shape
+        K = x16.shape[1]
+        assert dy32.is_contiguous() and g_w.is_contiguous() and tuple(g_w.shape) == (N, K)
+        nbytes = lib.unimm_k_linear_backward_scratch(M, N, K)
+        sc = self.scratch(nbytes)
+        dx = None
+        if need_dx:
+            dx = dx_accum if dx_accum is not None else self.empty32(M, K)
+            assert dx.is_contiguous() and tuple(dx.shape) == (M, K)
+        check(lib.unimm_k_linear_backward_acc(ptr(dy32), N, ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(dx), 1 if dx_accum is not None else 0,
+                                              ptr(g_w), ptr(g_b), ptr(sc), nbytes, self.kind, self.stream))
+        return dx
+
+    # ------------------------------------------------------------------ attention
+    def attention(self, q16, k16, v16, B, heads, D, Sq, Skv, mask_kind, desc=None, key_mask=None):
+        """-> (context 16-bit [B*Sq, heads*D], lse fp32 [B, heads, Sq])."""
+        o = self.empty16(B * Sq, heads * D)
+        lse = self.empty32(B, heads, Sq)
+        check(lib.unimm_k_attention_lse(ptr(q16), _ld(q16), ptr(k16), _ld(k16), ptr(v16), _ld(v16), ptr(o), heads * D, B, heads, D, Sq, Skv, mask_kind,
+                                        ptr(desc), ptr(key_mask), self.kind, ptr(lse), self.stream))
+        return o, lse
+
+    def attention_backward(self, q16, k16, v16, o16, lse, dO32, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv):
+        """dq / dk / dv: fp32 2-D views (column blocks of the projections' gradient matrices) that receive the result."""
+        assert dO32.is_contiguous()
+        nbytes = lib.unimm_k_attention_backward_scratch(B, heads, D, Sq)
+        sc = self.scratch(nbytes)
+        check(lib.unimm_k_attention_backward(ptr(q16), _ld(q16), ptr(k16), _ld(k16), ptr(v16), _ld(v16), ptr(o16), _ld(o16), ptr(dO32), ptr(lse), B,
+                                             heads, D, Sq, Skv, mask_kind, ptr(desc), ptr(key_mask), self.kind, ptr(dq), _ld(dq), ptr(dk), _ld(dk),
+                                             ptr(dv), _ld(dv), ptr(sc), nbytes, self.stream))
+
+    # ------------------------------------------------------------------ heads / losses
+    def lm_head_loss_backward(self, h16, e16, bias, labels_i32, weight32, grad_scale, g_e, g_bias):
+        """Fused vocabulary GEMM + likelihood / unlikelihood loss, forward and backward: -> (dH fp32, log p per row); dE / dbias are
+        WRITTEN to ``g_e`` / ``g_bias``."""
+        n, K = h16.shape
+        V = e16.shape[0]
+        nbytes = lib.unimm_k_lm_head_backward_scratch(n, V, K)
+        sc = self.scratch(nbytes)
+        dH, logp = self.empty32(n, K), self.empty32(n)
+        check(lib.unimm_k_lm_head_backward(ptr(h16), _ld(h16), ptr(e16), _ld(e16), n, V, K, ptr(bias), ptr(labels_i32), ptr(weight32), float(grad_scale),
+                                           ptr(dH), ptr(g_e), ptr(g_bias), ptr(logp), ptr(sc), nbytes, self.kind, self.stream))
+        return dH, logp
+
+    def lm_ul_value(self, logp, weight32, scale):
+        out = self.empty32(1)
+        check(lib.unimm_t_lm_ul_value(ptr(logp), ptr(weight32), logp.numel(), float(scale), ptr(out), self.stream))
+        return out
+
+    def nsp_ce(self, logits32, labels_i64, nsp_weight, grad_scale):
+        B = logits32.shape[0]
+        assert logits32.is_contiguous() and logits32.shape[1] == 2
+        loss, d = self.empty32(1), self.empty32(B, 2)
+        check(lib.unimm_t_nsp_ce(ptr(logits32), ptr(labels_i64), B, ptr(nsp_weight), float(grad_scale), ptr(loss), ptr(d), self.stream))
+        return loss, d
+
+    def image_kl(self, logits32, C_real, target32, target_row_i32, image_label_i64, grad_scale):
+        rows, ld = logits32.shape
+        loss, d, acc = self.empty32(1), self.empty32(rows, ld), self.empty32(2)
+        check(lib.unimm_t_image_kl(ptr(logits32), ld, ptr(target32), ptr(target_row_i32), ptr(image_label_i64), rows, C_real, float(grad_scale),
+                                   ptr(loss), ptr(d), ld, ptr(acc), self.stream))
+        return loss, d
+
+    # ------------------------------------------------------------------ optimizer
+    def adamw(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, correct_bias, inv_grad_scale, p16):
+        check(lib.unimm_t_adamw(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                int(step), 1 if correct_bias else 0, float(inv_grad_scale), ptr(p16), self.kind, self.stream))
