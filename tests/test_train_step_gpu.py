@@ -1,0 +1,207 @@
+"""GPU: the training step — the attention backward and the small training kernels against torch.autograd in
+fp64 on the same 16-bit operands, then the whole step (forward + three losses + backward + AdamW, unimm_b200/train_step.py over the
+CUDA kernels) against autograd of the oracle and the reference-made loss values of tests/golden/train6_perturbed.npz."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from conftest import golden_state_dict, load_golden  # noqa: E402
+from test_train_step_cpu import _train_inputs, oracle_losses_and_grads  # noqa: E402
+from torch_train_ops import TorchOps  # noqa: E402
+
+from unimm_b200.descriptors import dense_co_mask, dense_text_mask  # noqa: E402
+from unimm_b200.train_ops import MASK_CO_INTERVAL, MASK_KEY_VECTOR, MASK_TEXT_SELF, DeviceOps  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _descs():
+    # generative: (mode 0, ctx, L, last_len); discriminative: (1, 0, L, 0); one truncated sequence (L + last_len > S)
+    return torch.tensor([[0, 40, 47, 7], [1, 0, 93, 0], [0, 150, 153, 3], [0, 247, 252, 5], [1, 0, 256, 0]], dtype=torch.int32)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 6e-3), ("bf16", 3e-2)])
+@pytest.mark.parametrize("case", ["text_self", "image_self", "text_over_image", "image_over_text"])
+def test_attention_backward_matches_autograd(case, precision, tol):
+    ops = DeviceOps(DEV, precision)
+    ref = TorchOps()
+    g = torch.Generator().manual_seed(11)
+    desc = _descs()
+    B = desc.shape[0]
+    S, R = 256, 37
+    key_mask = torch.ones(B, R)
+    key_mask[1, 30:] = 0
+    key_mask[3, 5:] = 0
+    heads, D, Sq, Skv, kind = {"text_self": (12, 64, S, S, MASK_TEXT_SELF), "image_self": (8, 128, R, R, MASK_KEY_VECTOR),
+                               "text_over_image": (8, 128, S, R, MASK_KEY_VECTOR), "image_over_text": (8, 128, R, S, MASK_CO_INTERVAL)}[case]
+    H = heads * D
+    rnd = lambda *s: torch.randn(*s, generator=g).to(ops.lp_dtype)                                       # noqa: E731
+    q, k, v = rnd(B * Sq, H), rnd(B * Skv, H), rnd(B * Skv, H)
+    dO = torch.randn(B * Sq, H, generator=g) * 3e-5                     # gradient-sized values: far below fp16's normal range
+    d_desc = desc.to(DEV) if kind != MASK_KEY_VECTOR else None
+    d_km = key_mask.to(DEV) if kind == MASK_KEY_VECTOR else None
+    o, lse = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), B, heads, D, Sq, Skv, kind, d_desc, d_km)
+    o_ref, lse_ref = ref.attention(q.double(), k.double(), v.double(), B, heads, D, Sq, Skv, kind, desc, key_mask)
+    # rows that may attend nothing (padding) are unconstrained (the reference leaves a plain softmax there; nothing reads them)
+    if kind == MASK_TEXT_SELF:
+        valid = dense_text_mask(desc, S).any(-1).reshape(-1)
+    else:
+        valid = torch.ones(B * Sq, dtype=torch.bool)
+    err_o = (o.float().cpu().double() - o_ref)[valid].abs().max().item()
+    lse_v = valid.view(B, 1, Sq).expand(B, heads, Sq)
+    err_l = (lse.cpu().double() - lse_ref)[lse_v].abs().max().item()
+    print(f"[{precision}] {case}: forward |err| {err_o:.2e}, lse |err| {err_l:.2e}")
+    assert err_o < (4e-3 if precision == "fp16" else 3e-2) and err_l < 2e-3
+    dO = dO * valid[:, None]                                            # no gradient flows into padding rows
+    dq, dk, dv = ops.empty32(B * Sq, H), ops.empty32(B * Skv, H), ops.empty32(B * Skv, H)
+    ops.attention_backward(q.to(DEV), k.to(DEV), v.to(DEV), o, lse, dO.to(DEV), B, heads, D, Sq, Skv, kind, d_desc, d_km, dq, dk, dv)
+    rq, rk, rv = torch.empty(B * Sq, H, dtype=torch.float64), torch.empty(B * Skv, H, dtype=torch.float64), torch.empty(B * Skv, H, dtype=torch.float64)
+    ref.attention_backward(q.double(), k.double(), v.double(), None, None, dO.double(), B, heads, D, Sq, Skv, kind, desc, key_mask, rq, rk, rv)
+    for name, mine, want in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        e = (mine.cpu().double() - want).abs().max().item() / want.abs().max().item()
+        print(f"[{precision}] {case} {name}: max |err| / max |ref| = {e:.3e}")
+        assert e < tol, name
+        assert torch.isfinite(mine).all()
+
+
+def test_small_training_kernels():
+    ops, ref = DeviceOps(DEV, "fp16"), TorchOps()
+    g = torch.Generator().manual_seed(3)
+    # embedding sum and its scatter-add backward
+    V, H, rows = 500, 768, 300
+    word, pos_e, ty, ext = (torch.randn(n, H, generator=g) for n in (V, 64, 2, 10))
+    ids, pos, seg = torch.randint(0, V, (rows,), generator=g), torch.randint(0, 64, (rows,), generator=g), torch.randint(0, 12, (rows,), generator=g)
+    out = ops.embed_text_sum(ids.to(DEV), seg.to(DEV), pos.to(DEV), word.to(DEV), pos_e.to(DEV), ty.to(DEV), ext.to(DEV), 2)
+    want = ref.embed_text_sum(ids, seg, pos, word.double(), pos_e.double(), ty.double(), ext.double(), 2)
+    assert (out.cpu().double() - want).abs().max().item() < 1e-5
+    d = torch.randn(rows, H, generator=g)
+    d[::3] = 0
+    gw, gp, gt, ge = (torch.zeros(n, H, device=DEV) for n in (V, 64, 2, 10))
+    ops.embed_text_backward(d.to(DEV), ids.to(DEV), seg.to(DEV), pos.to(DEV), gw, gp, gt, ge, 2)
+    rw, rp, rt, re_ = (torch.zeros(n, H, dtype=torch.float64) for n in (V, 64, 2, 10))
+    ref.embed_text_backward(d.double(), ids, seg, pos, rw, rp, rt, re_, 2)
+    for a, b in ((gw, rw), (gp, rp), (gt, rt), (ge, re_)):
+        assert (a.cpu().double() - b).abs().max().item() < 2e-4 * max(1.0, b.abs().max().item())
+    # GELU forward (both outputs), element-wise helpers, gather / scatter
+    t = torch.randn(64, 1024, generator=g) * 2
+    g32, g16 = ops.gelu(t.to(DEV), want32=True, want16=True)
+    wantg = ref.gelu(t.double(), want32=True)[0]
+    assert (g32.cpu().double() - wantg).abs().max().item() < 1e-6 and (g16.float().cpu().double() - wantg).abs().max().item() < 4e-3
+    a, b = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    assert torch.equal(ops.mul(a.to(DEV), b.to(DEV)).cpu(), a * b)
+    assert torch.equal(ops.relu_backward(a.to(DEV).clone(), b.to(DEV)).cpu(), a * (b > 0))
+    src = torch.randn(50, 768, generator=g)
+    idx = torch.randperm(50, generator=g)[:20].to(torch.int32)
+    assert torch.equal(ops.gather_rows(src.to(DEV), idx.to(DEV)).cpu(), src[idx.long()])
+    dst = torch.zeros(50, 768, device=DEV)
+    ops.scatter_add_rows(src[:20].to(DEV), idx.to(DEV), dst)
+    assert torch.equal(dst.cpu()[idx.long()], src[:20])
+    # column sums inside linear_backward at a row count that spans many slabs
+    dy = torch.randn(5000, 128, generator=g) * 1e-4
+    x = torch.randn(5000, 64, generator=g).to(torch.float16)
+    w = torch.randn(128, 64, generator=g).to(torch.float16)
+    gwt, gb = torch.empty(128, 64, device=DEV), torch.empty(128, device=DEV)
+    dx = ops.linear_backward(dy.to(DEV), x.to(DEV), w.to(DEV), gwt, gb)
+    assert (gb.cpu().double() - dy.double().sum(0)).abs().max().item() < 1e-6
+    assert (dx.cpu().double() - dy.double() @ w.double()).abs().max().item() < 3e-3 * (dy.double() @ w.double()).abs().max().item()
+    acc = torch.ones(5000, 64, device=DEV)
+    ops.linear_backward(dy.to(DEV), x.to(DEV), w.to(DEV), gwt, gb, dx_accum=acc)
+    assert (acc.cpu() - 1.0 - dx.cpu()).abs().max().item() < 1e-6
+    # NSP cross entropy, image KL
+    logits = torch.randn(37, 2, generator=g)
+    y = torch.randint(0, 2, (37,), generator=g)
+    nw = torch.tensor([2.0, 5.0])
+    loss, dl = ops.nsp_ce(logits.to(DEV), y.to(DEV), nw.to(DEV), 0.7)
+    rl, rd = ref.nsp_ce(logits.double(), y, nw.double(), 0.7)
+    assert abs(loss.item() - rl.item()) < 1e-5 and (dl.cpu().double() - rd).abs().max().item() < 1e-6
+    C, ld, n_img = 1601, 1664, 3
+    vl = torch.randn(3 * 37, ld, generator=g)
+    tgt = torch.rand(n_img * 37, C, generator=g) ** 8
+    tgt /= tgt.sum(-1, keepdim=True)
+    trow = torch.randint(0, n_img * 37, (3 * 37,), generator=g).to(torch.int32)
+    il = torch.where(torch.rand(3 * 37, generator=g) < 0.2, 1, -1)
+    loss, dv = ops.image_kl(vl.to(DEV), C, tgt.to(DEV), trow.to(DEV), il.to(DEV), 1.3)
+    rl, rd = ref.image_kl(vl.double(), C, tgt.double(), trow, il, 1.3)
+    assert abs(loss.item() - rl.item()) < 1e-4 * abs(rl.item()) and (dv.cpu().double() - rd).abs().max().item() < 1e-6
+    # AdamW against the restated pytorch_transformers step
+    from oracle import adamw as oa
+    p, gr = torch.randn(10000, generator=g), torch.randn(10000, generator=g) * 1e-3
+    state, rp = {}, p.double().clone()
+    dp, dm, dv_, d16 = p.to(DEV).clone(), torch.zeros(10000, device=DEV), torch.zeros(10000, device=DEV), torch.empty(10000, device=DEV, dtype=torch.float16)
+    for it in range(1, 4):
+        oa.adamw_step(rp, gr.double(), state, 2e-5, weight_decay=0.01)
+        ops.adamw(dp, gr.to(DEV), dm, dv_, 2e-5, 0.9, 0.999, 1e-6, 0.01, it, True, 1.0, d16)
+    assert (dp.cpu().double() - rp).abs().max().item() < 1e-6 and torch.equal(d16.cpu(), dp.cpu().half())
+
+
+def _compare_grads(got, ref_grad, tol_max, tol_l2, label):
+    """Per tensor: max |err| relative to the tensor's largest gradient, and the relative L2 error.  Tensors whose gradient is
+    (analytically) zero or negligible next to the largest one in the model are measured against 1e-3 of that."""
+    gmax = max(float(gr.abs().max()) for gr in ref_grad.values() if gr is not None)
+    rows = []
+    for name, gr in ref_grad.items():
+        if gr is None:
+            assert float(got[name].abs().max()) == 0.0, name
+            continue
+        assert torch.isfinite(got[name]).all(), name
+        d = got[name].double() - gr.double().cpu()
+        scale = max(float(gr.abs().max()), 1e-3 * gmax)
+        l2 = float(d.norm()) / max(float(gr.double().norm()), 1e-3 * gmax * math.sqrt(gr.numel()))
+        rows.append((float(d.abs().max()) / scale, l2, name))
+    rows.sort(reverse=True)
+    for e, l2, name in rows[:6]:
+        print(f"[{label}]   max-err {e:.3e}  l2-err {l2:.3e}  {name}")
+    worst_l2 = max(r[1] for r in rows)
+    print(f"[{label}] {len(rows)} gradient tensors: worst max-err {rows[0][0]:.3e} ({rows[0][2]}), worst relative L2 error {worst_l2:.3e}, "
+          f"median max-err {sorted(r[0] for r in rows)[len(rows) // 2]:.3e}")
+    assert rows[0][0] < tol_max, rows[0]
+    assert worst_l2 < tol_l2, max(rows, key=lambda r: r[1])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", (2e-2, 1e-2)), ("bf16", (1e-1, 6e-2))])
+def test_train_step_tiny_matches_autograd_of_the_oracle(precision, tol):
+    from unimm_b200.config import tiny_config
+    from unimm_b200.train_step import TrainStep
+    from unimm_b200.weights import random_state_dict
+    cfg = tiny_config()
+    sd = random_state_dict(cfg, seed=5, perturbed=True)
+    n = 6
+    g, b, batch = _train_inputs(n)
+    ref_loss, ref_grad = oracle_losses_and_grads(cfg, sd, b, g, n)
+    ts = TrainStep(cfg, sd, DeviceOps(DEV, precision))
+    vals = ts.forward_backward(batch)
+    print(f"[{precision}] tiny losses {vals} vs {ref_loss}")
+    for k in ("lm_loss", "nsp_loss", "img_loss"):
+        assert abs(vals[k] - ref_loss[k]) < (5e-3 if precision == "fp16" else 3e-2), (k, vals[k], ref_loss[k])
+    _compare_grads(ts.grad_dict(), ref_grad, tol[0], tol[1], precision + " tiny")
+    # two optimizer steps move the loss down on the same batch and keep every parameter finite
+    first = vals["loss"]
+    ts2 = TrainStep(cfg, sd, DeviceOps(DEV, precision), lr=1e-3, image_lr=1e-3, warmup_steps=0)
+    losses = [ts2.step(batch)["loss"] for _ in range(4)]
+    print(f"[{precision}] loss over 4 steps at lr 1e-3: {losses}")
+    assert abs(losses[0] - first) < 1e-2 and losses[-1] < losses[0]
+    assert all(torch.isfinite(v).all() for v in ts2.state_dict().values())
+
+
+def test_train_step_full_config_matches_reference_losses_and_autograd(full_cfg):
+    """12 + 6 + 6 layers, the reference-made batch of train6_perturbed: the three losses against the reference's own values, every
+    gradient against autograd of the oracle (fp32 on the host cores)."""
+    from unimm_b200.train_step import TrainStep
+    g, b, batch = _train_inputs(None)
+    sd = golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+    ts = TrainStep(full_cfg, sd, DeviceOps(DEV, "fp16"))
+    vals = ts.forward_backward(batch)
+    print(f"[fp16] full-config losses {vals} vs reference lm {g['lm_loss'].item():.6f} img {g['img_loss'].item():.6f} nsp {g['nsp_loss'].item():.6f}")
+    assert abs(vals["lm_loss"] - g["lm_loss"].item()) < 2e-2
+    assert abs(vals["img_loss"] - g["img_loss"].item()) < 2e-2
+    assert abs(vals["nsp_loss"] - g["nsp_loss"].item()) < 2e-2
+    n = b["tokens"].shape[0]
+    _, ref_grad = oracle_losses_and_grads(full_cfg, sd, b, g, n, dtype=torch.float32)
+    _compare_grads(ts.grad_dict(), ref_grad, 1e-1, 3e-2, "fp16 full config")

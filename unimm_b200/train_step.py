@@ -339,8 +339,7 @@ class TrainStep:
         feat16 = ops.to_lp(feat32)
         del feat32
         loc16 = ops.to_lp(inp["loc64"])
-        loc_term = ops.linear_f32(inp["loc64"][:, :cfg.loc_size], P._view(P.p, ve + "image_location_embeddings.weight", padded=False),
-                                  P.P(ve + "image_location_embeddings.bias"))
+        loc_term = ops.linear_f32(inp["loc64"], P.P(ve + "image_location_embeddings.weight"), P.P(ve + "image_location_embeddings.bias"))   # K padded 5 -> 64
         v_sum, _ = ops.linear(feat16, P.P16(ve + "image_embeddings.weight"), P.P(ve + "image_embeddings.bias"), residual=loc_term)
         xv32, xv16 = ops.layernorm(v_sum, P.P(ve + "LayerNorm.weight"), P.P(ve + "LayerNorm.bias"))
         # ---- encoder (:842-929)
