@@ -399,6 +399,80 @@ def main_sweep(args):
         dist.destroy_process_group()
 
 
+def main_train_step(args):
+    """BASELINE configs[2] as a whole TRAINING step (train.py:445-463): 240 sequences = 40 images x (1 positive + 5
+    negatives), forward + three losses + backward of every layer + AdamW over the 250 M parameters, unimm_b200.train_step.TrainStep over
+    the library's kernels.  value = sequences / s with the step's inputs resident in HBM; e2e = the same from pinned host tensors (ids,
+    descriptors, labels, one feature / target block per image) with the three loss values read back every step."""
+    from unimm_b200 import synthetic as syn
+    from unimm_b200.config import DEFAULT_CONFIG_PATH, ViLBertConfig
+    from unimm_b200._lib import lib
+    from unimm_b200.train_ops import DeviceOps
+    from unimm_b200.train_step import TrainStep
+    from unimm_b200.weights import random_state_dict
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    batches = []
+    for i in range(3):
+        b = {k: T(v).pin_memory() for k, v in syn.train_batch(1000 + i).items()}
+        b["nsp_weight"] = torch.tensor([5.0, 1.0]).pin_memory()
+        batches.append(b)
+    B = batches[0]["tokens"].shape[0]
+    ts = TrainStep(cfg, random_state_dict(cfg, 0), DeviceOps(dev, args.precision))
+    stream = torch.cuda.current_stream(dev)
+    inps = [ts.upload(b) for b in batches]
+    for i in range(args.warmup):
+        ts.step(inp=inps[i % 3], read_losses=False)
+    torch.cuda.synchronize(dev)
+    lib.unimm_reset_launch_count()
+    sampler = ClockSampler(0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_start()
+    ev0.record(stream)
+    for i in range(args.steps):
+        out = ts.step(inp=inps[i % 3], read_losses=False)
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    launches = int(lib.unimm_launch_count())
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts.step(batches[0])
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for i in range(args.steps):
+        vals = ts.step(batches[i % 3])                         # H2D of every input + forward + backward + AdamW + the loss values read back
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms2 = e0.elapsed_time(e1)
+    h2d = sum(v.numel() * v.element_size() for v in batches[0].values() if torch.is_tensor(v))
+    pk = peaks()
+    # executed FLOPs: forward projections + attention of the dense layout (BASELINE.md 3: 76.30 G per sequence) + the heads, x 3 for
+    # forward + dgrad + wgrad (the attention backward recomputes S and dP in both of its kernels: 7 products against the forward's 2)
+    n_lm = int((batches[0]["labels"] != -1).sum())
+    fwd = B * 76.30e9 + n_lm * (2 * 768 * 768 + 2 * 768 * 30522) + B * 37 * (2 * 1024 * 1024 + 2 * 1024 * 1601)
+    flops = 3.0 * fwd
+    tfl = flops * args.steps / (ms_total * 1e-3) / 1e12
+    line = {"metric": "sequences_per_sec", "value": args.steps * B / (ms_total * 1e-3), "unit": "sequences/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "configs[2] as a full TRAINING step: train.py UniMM-UL, batch 240 = 40 images x 6 sequences (1 positive + 5 "
+                                   "negatives), mixed generative / discriminative masks, mask_prob 0.15, unlikelihood on the negatives; forward + "
+                                   "3 losses + backward + AdamW (4 parameter groups, 250 M parameters); dropout off",
+                       "sequences_per_step": B, "layout": "dense (256 rows per sequence)", "seq_len": 256, "regions": 37,
+                       "model": "bert_base_6layer_6conect, random init (seed 0)", "inputs": "3 distinct batches in rotation, activations + "
+                       "gradients of a step (%.1f GB peak) far larger than L2" % mem_gb,
+                       "losses_of_last_step": vals},
+            "pct_of_bf16_peak": {"model_tflops": tfl, "burst": tfl / pk["burst"], "sustained": tfl / pk["sustained"], "peaks": pk["source"],
+                                 "flop_count": "3 x forward (2 M N K per projection, attention, heads); recomputation not counted"},
+            "e2e": {"value": args.steps * B / (ms2 * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+            "gpu_launches": launches, "peak_memory_gb": mem_gb, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
 def main_dense_workload(args):
     """BASELINE configs 3 / 4 / 5 at their stated sizes on ONE GPU, dense layout (rows differ per sequence: no prefix to share):
       train_fwd  config 3: 240 sequences = 40 images x (1 positive + 5 negatives), mixed gen / dis masks, 15 % masking, UL on negatives;
@@ -750,7 +824,7 @@ if __name__ == "__main__":
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: cuda = the eager-PyTorch-on-B200 bar (extra; the driver's arm is cpu)")
     ap.add_argument("--ref-mode", default="tf32", choices=["tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="steps", choices=["steps", "sweep", "train_fwd", "dis_nsp", "dense_ft"],
+    ap.add_argument("--workload", default="steps", choices=["steps", "sweep", "train_fwd", "train_step", "dis_nsp", "dense_ft"],
                     help="sweep = the whole configs[1] sweep, strong-scaled; train_fwd / dis_nsp / dense_ft = configs 3 / 4 / 5 at their stated sizes (1 GPU)")
     ap.add_argument("--images", type=int, default=2064, help="--workload sweep: images of the sweep")
     ap.add_argument("--no-verify", action="store_true", help="skip the per-step context-equality check of the packer")
@@ -761,6 +835,8 @@ if __name__ == "__main__":
         main_reference(a)
     elif a.workload == "sweep":
         main_sweep(a)
+    elif a.workload == "train_step":
+        main_train_step(a)
     elif a.workload in ("train_fwd", "dis_nsp", "dense_ft"):
         main_dense_workload(a)
     else:

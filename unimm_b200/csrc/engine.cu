@@ -1646,6 +1646,39 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int
     // fp16's normal range), multiplied back out by the GEMM epilogues straight from device memory
     UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st));
     UNIMM_TRY(cast_scaled_lp(d_dY, ldy, M, N, scale, dY16, N, lp_kind, st));
+    static const bool transposed_copies = getenv("UNIMM_BWD_TRANSPOSE") != nullptr && atoi(getenv("UNIMM_BWD_TRANSPOSE")) != 0;
+    if (!transposed_copies) {
+        // No transposed copies: tcgen05 reads an operand whose contraction index is the ROW of the stored matrix as an MN-major tile
+        // (gemm_umma.cu, a_mn / b_mn).  dX [M, K] = dY [M, N] . W [N, K]: W as stored is the B operand [K, N-contraction] MN-major.
+        if (d_dX != nullptr) {
+            GemmEpilogue ep;
+            ep.lp_kind = lp_kind; ep.out_f32 = d_dX; ep.ldo_f32 = K; ep.alpha_ptr = scale + 1; ep.b_mn = true;
+            if (accumulate_dx) { ep.residual = d_dX; ep.ldr = K; }   // dX += dY W: each element is read and rewritten by the same thread
+            UNIMM_TRY(gemm_umma_bf16(dY16, N, static_cast<const bf16*>(d_W), ldw, M, K, N, ep, 0, 0, st));
+        }
+        // dW [N, K] = dY^T [N, M] . X [M, K]: both operands as stored (contraction = their rows, zero-filled beyond M by TMA).  The
+        // output is at most 3072 x 3072 — a handful of tiles — and the contraction tens of thousands of rows long: split it over
+        // enough CTAs to fill the machine, partial products added with atomics onto the zeroed gradient.
+        if (d_dW != nullptr) {
+            const int tn = (K % 256 == 0 || K > 2048) ? 256 : 128;
+            const int tiles = ((N + 127) / 128) * ((K + tn - 1) / tn), num_k = (M + 63) / 64;
+            int sms = 148;
+            { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+            int best = 1;
+            double best_eff = 0.0;
+            for (int sk = 1; sk <= 16 && sk <= num_k; ++sk) {
+                const int total = tiles * sk;
+                const double eff = static_cast<double>(total) / (((total + sms - 1) / sms) * sms);
+                if (eff > best_eff + 0.02) { best_eff = eff; best = sk; }
+            }
+            GemmEpilogue ep;
+            ep.lp_kind = lp_kind; ep.out_f32 = d_dW; ep.ldo_f32 = K; ep.alpha_ptr = scale + 1; ep.a_mn = true; ep.b_mn = true; ep.split_k = best;
+            if (best > 1) UNIMM_CUDA_CHECK(cudaMemsetAsync(d_dW, 0, sizeof(float) * static_cast<size_t>(N) * K, st));
+            UNIMM_TRY(gemm_umma_bf16(dY16, N, static_cast<const bf16*>(d_X), ldx, N, K, M, ep, tn, 0, st));
+        }
+        if (d_db != nullptr) UNIMM_TRY(column_sums_f32(d_dY, ldy, M, N, d_db, st));
+        return 0;
+    }
     if (d_dX != nullptr) {        // dX [M, K] = dY [M, N] · W [N, K]: contraction over N, W operand = W^T (K-major in N)
         UNIMM_TRY(transpose_16(static_cast<const bf16*>(d_W), ldw, N, K, WT, N, st));
         GemmEpilogue ep;

@@ -76,10 +76,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int num_m = ((M + BM - 1) / BM + CS - 1) / CS;     // row blocks of CS x 128 rows (a padding tile is all out of bounds)
     const int num_n = (N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
-    const int num_k1 = K / BK;
+    const int splits = ep.split_k > 1 ? ep.split_k : 1;      // split-K: consecutive tile indices share an output tile
+    const int num_tiles = num_m * num_n * splits;
+    const int num_k1 = (K + BK - 1) / BK;                    // K % 64 != 0 only with both operands MN-major (host-checked): zero-filled rows
     // fp32-class mode: every k-block three times — (a_lo, w_hi), (a_hi, w_lo), (a_hi, w_hi), small terms first — into one accumulator
     const int num_k = ep.split3 ? 3 * num_k1 : num_k1;
+    const int k_per = (num_k + splits - 1) / splits;         // k-blocks per split (the host guarantees no split is empty)
     const uint32_t crank = CS > 1 ? ptx::cluster_ctarank() : 0u;
     const int first_tile = blockIdx.x / CS, tile_step = gridDim.x / CS;
     constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1u);
@@ -117,9 +119,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-                const int m0 = ((tile / num_n) * CS + static_cast<int>(crank)) * BM;
-                const int n0 = (tile % num_n) * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int mn = tile / splits, sp = tile - mn * splits;
+                const int m0 = ((mn / num_n) * CS + static_cast<int>(crank)) * BM;
+                const int n0 = (mn % num_n) * BN;
+                const int kb_end = min(num_k, (sp + 1) * k_per);
+                for (int kb = sp * k_per; kb < kb_end; ++kb) {
                     int ka = kb * BK, kw = kb * BK;          // column of the A box / of the W box
                     if (ep.split3) {
                         const int pass = kb / num_k1, kk = (kb - pass * num_k1) * BK;
@@ -130,14 +134,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (SM2) {
                         // both CTAs' boxes are counted on the leader's barrier, which the leader arms for the pair
                         if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                        ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, m0);
-                        ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kw, n0 + static_cast<int>(crank) * (BN / 2));
+                        if (ep.a_mn) {       // MN-major: 64 x 64 boxes [contraction rows x 64 contiguous M / N elements], 8 KB atoms
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, ka);
+                        } else {
+                            ptx::tma_load_2d_2sm(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, m0);
+                        }
+                        if (ep.b_mn) {
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j)
+                                ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes + j * 8192, &tmB, &full_bar[stage],
+                                                     n0 + static_cast<int>(crank) * (BN / 2) + 64 * j, kw);
+                        } else {
+                            ptx::tma_load_2d_2sm(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kw, n0 + static_cast<int>(crank) * (BN / 2));
+                        }
                         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, m0);
-                    if (CL == 1) ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kw, n0);
+                    if (ep.a_mn) {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            ptx::tma_load_2d(sA + stage * Cfg::kABytes + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, ka);
+                    } else {
+                        ptx::tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], ka, m0);
+                    }
+                    if (CL == 1 && ep.b_mn) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            ptx::tma_load_2d(sB + stage * Cfg::kBBytes + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kw);
+                    } else if (CL == 1) ptx::tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kw, n0);
                     else ptx::tma_load_2d_mc(sB + stage * Cfg::kBBytes + crank * (Cfg::kBBytes / CL), &tmB, &full_bar[stage], kw,
                                              n0 + static_cast<int>(crank) * (BN / CL), kMask);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -147,7 +174,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one() && (!SM2 || crank == 0)) {
-            const uint32_t idesc = ptx::make_idesc_f16(SM2 ? 2 * BM : BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u);
+            // bits 15 / 16 of the instruction descriptor: A / B operand is MN-major
+            const uint32_t idesc = ptx::make_idesc_f16(SM2 ? 2 * BM : BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u) | (ep.a_mn ? (1u << 15) : 0u) |
+                                   (ep.b_mn ? (1u << 16) : 0u);
+            // K-major: 16 elements along K = 32 bytes inside the swizzle atom (+2 in the addr >> 4 field); MN-major: 16 contraction
+            // rows of 128 bytes = two 1024-byte groups (+128), 64-element atoms along M / N 8 KB apart (the leading byte offset)
+            const uint32_t ka_step = ep.a_mn ? 128u : 2u, kb_step = ep.b_mn ? 128u : 2u;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -156,16 +188,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int sp = tile % splits;
+                const int kb_begin = sp * k_per, kb_end = min(num_k, (sp + 1) * k_per);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * Cfg::kABytes));
-                    const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * Cfg::kBBytes));
+                    const uint32_t a_addr = ptx::smem_u32(sA + stage * Cfg::kABytes), b_addr = ptx::smem_u32(sB + stage * Cfg::kBBytes);
+                    const uint64_t da = ep.a_mn ? ptx::make_sw128_mnmajor_desc(a_addr, 8192) : ptx::make_sw128_kmajor_desc(a_addr);
+                    const uint64_t db = ep.b_mn ? ptx::make_sw128_mnmajor_desc(b_addr, 8192) : ptx::make_sw128_kmajor_desc(b_addr);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-                        if (SM2) ptx::umma_f16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else ptx::umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t accum = (kb != kb_begin || k != 0) ? 1u : 0u;
+                        if (SM2) ptx::umma_f16_ss_2sm(tmem_d, da + ka_step * k, db + kb_step * k, idesc, accum);
+                        else ptx::umma_f16_ss(tmem_d, da + ka_step * k, db + kb_step * k, idesc, accum);
                     }
                     if (CL == 1) ptx::umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
                     else if (CL == 2) ptx::umma_commit_mc(&empty_bar[stage], kMask);  // ... in both CTAs (the peer multicasts into this slot too)
@@ -205,8 +240,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-            const int tn = tile % num_n;
-            const int m0 = ((tile / num_n) * CS + static_cast<int>(crank)) * BM;
+            const int mn = tile / splits;
+            const int tn = mn % num_n;
+            const int m0 = ((mn / num_n) * CS + static_cast<int>(crank)) * BM;
             const int n0 = tn * BN + half * HALF_N;
             const int row = m0 + ew * 32 + lane;
             const bool row_ok = row < M;
@@ -489,7 +525,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int i = 0; i < 8; ++i) {
                         const int grow = r0 + 4 * i;
                         if (grow < M) {
-                            if (ep.out_f32 != nullptr)
+                            if (ep.out_f32 != nullptr && splits > 1) {
+                                float* o = ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc;
+                                atomicAdd(o, y[i].x); atomicAdd(o + 1, y[i].y); atomicAdd(o + 2, y[i].z); atomicAdd(o + 3, y[i].w);
+                            } else if (ep.out_f32 != nullptr)
                                 *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc) = y[i];
                             if (ep.out_bf16 != nullptr && ep.out_hilo) {
                                 uint2 hi, lo;
@@ -539,7 +578,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (ep.out_f32 != nullptr) {
                     float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
-                    if (fast_ok && ncols == 32) {
+                    if (splits > 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) atomicAdd(o + j, x[j]);
+                    } else if (fast_ok && ncols == 32) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
                     } else {
@@ -673,12 +716,15 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, 
     using Cfg = GemmCfg<BN, ST, CL == 3>;
     CUtensorMap tmA, tmB;
     const int kcols = ep.split3 ? 2 * K : K;                 // fp32-class mode: hi | lo planes side by side
-    UNIMM_TRY(make_map_bf16(A, M, kcols, lda, BM, &tmA));
-    UNIMM_TRY(make_map_bf16(W, N, kcols, ldw, BN / CS, &tmB));
+    // MN-major operands are [K, M] / [K, N] matrices read in 64 x 64 boxes
+    if (ep.a_mn) UNIMM_TRY(make_map_bf16(A, K, M, lda, 64, &tmA));
+    else UNIMM_TRY(make_map_bf16(A, M, kcols, lda, BM, &tmA));
+    if (ep.b_mn) UNIMM_TRY(make_map_bf16(W, K, N, ldw, 64, &tmB));
+    else UNIMM_TRY(make_map_bf16(W, N, kcols, ldw, BN / CS, &tmB));
     static int max_clusters = 0;
     auto kernel = umma_gemm_kernel<BN, LSE, ST, FRAG, CL>;
     UNIMM_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), Cfg::kSmemBytes));
-    const int tiles = (((M + BM - 1) / BM + CS - 1) / CS) * ((N + BN - 1) / BN);
+    const int tiles = (((M + BM - 1) / BM + CS - 1) / CS) * ((N + BN - 1) / BN) * (ep.split_k > 1 ? ep.split_k : 1);
     if (CL == 1) {
         int grid = tiles < num_sms() ? tiles : num_sms();
         if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
@@ -732,8 +778,27 @@ int gemm_num_sms() { return num_sms(); }
 
 int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep, int tile_n,
                    int max_ctas, cudaStream_t stream) {
-    UNIMM_CHECK(M > 0 && N > 0 && K > 0 && K % BK == 0, "umma gemm: K must be a positive multiple of 64");
+    UNIMM_CHECK(M > 0 && N > 0 && K > 0 && (K % BK == 0 || (ep.a_mn && ep.b_mn)), "umma gemm: K must be a positive multiple of 64");
     const bool lse = ep.partials != nullptr || ep.dz != nullptr;
+    if (ep.a_mn || ep.b_mn || ep.split_k > 1) {
+        UNIMM_CHECK(!lse && !ep.split3 && !ep.w_perm16 && ep.debug_mode == 0, "MN-major operands / split-K: plain epilogue only");
+        UNIMM_CHECK(!ep.a_mn || ((lda & 7) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0), "MN-major A: 16-byte aligned rows");
+        UNIMM_CHECK(!ep.b_mn || ((ldw & 7) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0), "MN-major W: 16-byte aligned rows");
+        GemmEpilogue e2 = ep;
+        if (ep.split_k > 1) {
+            UNIMM_CHECK(ep.out_f32 != nullptr && ep.out_bf16 == nullptr && ep.bias == nullptr && ep.residual == nullptr && ep.act == ACT_NONE,
+                        "split-K accumulates plain fp32 partial products");
+            const int num_k = (K + BK - 1) / BK;
+            int sk = ep.split_k < num_k ? ep.split_k : num_k;
+            const int k_per = (num_k + sk - 1) / sk;
+            e2.split_k = (num_k + k_per - 1) / k_per;          // no empty split
+        }
+        if (tile_n == 0) tile_n = (N % 256 == 0 || N > 2048) ? 256 : 128;
+        const bool pair = M >= 8192 && tile_n == 256;          // tall problems: cta_group::2 pairs (CL = 2's multicast path is K-major only)
+        if (pair) return launch<256, false, 0, false, 3>(A, lda, W, ldw, M, N, K, e2, max_ctas, stream);
+        if (tile_n == 256) return launch<256, false>(A, lda, W, ldw, M, N, K, e2, max_ctas, stream);
+        return launch<128, false>(A, lda, W, ldw, M, N, K, e2, max_ctas, stream);
+    }
     UNIMM_CHECK(ep.dz == nullptr || (ep.dzT != nullptr && ep.lse != nullptr && ep.coef != nullptr && ep.labels != nullptr && ep.bias != nullptr &&
                                      (ep.ldz & 7) == 0 && (ep.dz_cols & 1) == 0 && ep.dz_cols <= ep.ldz && ep.ldzt >= M),
                 "dz epilogue: incomplete arguments");

@@ -41,6 +41,15 @@ struct GemmEpilogue {
     const int* labels = nullptr;   // LSE mode: [M]
     float2* partials = nullptr;    // LSE mode: [M, gemm_umma_lse_tiles(N)]
     float* label_logit = nullptr;  // LSE mode: [M]
+    // operands given TRANSPOSED (MN-major for tcgen05: the non-contracted dimension is the contiguous one), so that the backward's
+    // dgrad  dX = dY W  (W [N, K] as stored = B operand [K_out, N] MN-major)  and  wgrad  dW = dY^T X  (both operands as stored)
+    // need no transposed copies:  a_mn: A is passed as [K, M] row-major (lda = its row stride);  b_mn: W is passed as [K, N] row-major.
+    // With both set the contraction length K (= rows of both) may be any positive number (TMA zero-fills beyond it).
+    bool a_mn = false, b_mn = false;
+    // split the contraction over split_k CTAs per output tile, partial sums added to out_f32 with atomics (out_f32 must hold zeros or
+    // the value to accumulate onto; fp32 output only, no bias / activation / residual): fills the machine when the output is small
+    // and the contraction long — every wgrad of the path (N x K <= 3072 x 3072 outputs over 61 440 rows)
+    int split_k = 1;
 };
 
 // C = A[M,K] · W[N,K]^T, bf16 operands, fp32 accumulation in TMEM (gemm_umma.cu).

@@ -330,6 +330,19 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     return d;
 }
 
+// The same 128-byte-swizzled tile read as an MN-major operand: rows of the tile are CONTRACTION indices, each row holds 64 contiguous
+// M / N elements (what TMA writes from a [K, M] row-major matrix with a 64 x rows box); 8-row groups 1024 B apart (SBO), further
+// 64-element atoms along M / N lbo_bytes apart (LBO).  One MMA (K = 16) covers 16 rows = 2048 B: advance the descriptor by 128.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
 // Instruction descriptor for kind::f16: (fp16 | bf16) x same -> fp32, both operands K-major.
 // fmt: 0 = F16, 1 = BF16 (cute::UMMA::F16F32Format).
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t fmt) {

@@ -172,7 +172,8 @@ class TrainStep:
         self.S, self.R = None, None
 
     # ------------------------------------------------------------------ inputs
-    def _upload(self, batch):
+    def upload(self, batch):
+        """Host batch -> device inputs (one H2D per tensor from the caller's (pinned) memory, a few index arrays built on the host)."""
         ops, cfg = self.ops, self.cfg
         dev, fdt = self.params.p.device, self.params.p.dtype       # fdt: fp32 on the device (fp64 only under the CPU test's torch ops)
         t = lambda x, dt=None: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)          # noqa: E731
@@ -323,9 +324,12 @@ class TrainStep:
         return dxv, dxt
 
     # ------------------------------------------------------------------ the step
-    def forward_backward(self, batch) -> Dict[str, float]:
+    def forward_backward(self, batch=None, inp=None, read_losses: bool = True) -> Dict[str, float]:
+        """Forward, the three losses, backward: the gradients of ``lm_coeff lm + nsp_coeff nsp + img_coeff img`` land in ``params.g``.
+        ``inp``: inputs already on the device (``upload``); ``read_losses=False`` returns device tensors instead of floats."""
         ops, P, cfg = self.ops, self.params, self.cfg
-        inp = self._upload(batch)
+        if inp is None:
+            inp = self.upload(batch)
         B, S, R = inp["B"], inp["S"], inp["R"]
         P.g.zero_()
         saved = []
@@ -425,7 +429,9 @@ class TrainStep:
                             need_dx=False)
         ops.linear_backward(d_vsum, loc16, P.P16(ve + "image_location_embeddings.weight"), P.G(ve + "image_location_embeddings.weight"),
                             P.G(ve + "image_location_embeddings.bias"), need_dx=False)
-        vals = {k: float(v.item()) for k, v in out.items()}              # the step's one device -> host read
+        if not read_losses:
+            return out
+        vals = {k: float(v.item()) for k, v in out.items()}              # the step's device -> host read
         vals.setdefault("lm_loss", 0.0)
         vals["loss"] = self.coeff[0] * vals["lm_loss"] + self.coeff[1] * vals["nsp_loss"] + self.coeff[2] * vals["img_loss"]
         return vals
@@ -443,8 +449,8 @@ class TrainStep:
                           P.p16[a:b])
         self.sched_step += 1
 
-    def step(self, batch) -> Dict[str, float]:
-        vals = self.forward_backward(batch)
+    def step(self, batch=None, inp=None, read_losses: bool = True) -> Dict[str, float]:
+        vals = self.forward_backward(batch, inp, read_losses)
         self.optimizer_step()
         return vals
 
