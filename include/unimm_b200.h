@@ -343,10 +343,16 @@ int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const 
 /* ---- training step (reference train.py:445-463: forward + loss.backward() + optimizer.step()) ----
  * Kernel-level entry points; the layer schedule in reverse and the saved activations are host logic (unimm_b200/train_step.py), as
  * autograd is in the reference.  All gradients are fp32; every tensor-core operand is 16-bit (lp_kind 0 = bf16, 1 = fp16). */
-/* same as unimm_k_linear_backward; accumulate_dx != 0: dX += dY W (the residual branch's gradient is already in d_dX) */
+/* same as unimm_k_linear_backward; accumulate_dx != 0: dX += dY W (the residual branch's gradient is already in d_dX); d_amax (optional):
+ * max |dY| as float bits, left on the device by the kernel that produced dY (the *_amax entry points below, unimm_k_attention_backward) —
+ * the 16-bit operand scale is then derived without a pass over dY */
 int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X_lp, int ldx, const void* d_W_lp, int ldw, int M, int N, int K,
-                                float* d_dX, int accumulate_dx, float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind,
-                                void* stream);
+                                float* d_dX, int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, void* d_scratch,
+                                size_t scratch_bytes, int lp_kind, void* stream);
+/* unimm_k_layernorm_backward / unimm_k_gelu_backward that also leave max |dx| (float bits; zeroed first) in d_amax[0] */
+int unimm_k_layernorm_backward_amax(const float* d_dy, const float* d_x, int rows, int H, const float* d_gamma, float* d_dx, float* d_dgamma,
+                                    float* d_dbeta, float* d_amax, void* stream);
+int unimm_k_gelu_backward_amax(const float* d_dy, const float* d_x, int64_t n, float* d_dx, float* d_amax, void* stream);
 /* mma.sync attention of the dense [B, S] layout (unimm_k_attention impl 1) that also saves the row log-sum-exp d_lse [B, heads, Sq]
  * (natural log, softmax scale included) for the backward. */
 int unimm_k_attention_lse(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B, int heads,
@@ -355,12 +361,13 @@ int unimm_k_attention_lse(const void* d_q, int ldq, const void* d_k, int ldk, co
 /* Backward of softmax(Q K^T / sqrt(D) + mask) V (models/vilbert_dialog.py:395-410, :681-721) from the saved 16-bit q / k / v / o and
  * d_lse: d_dO fp32 contiguous [B*Sq, heads*D] -> d_dq [B*Sq, lddq], d_dk / d_dv [B*Skv, lddk / lddv] fp32 (head h at column h*D, so the
  * three can be the column blocks of one [rows, 3H] matrix).  P is recomputed tile by tile; no [B, heads, Sq, Skv] tensor, no atomics.
- * The masks are the forward's, regenerated from d_desc / d_key_mask. */
+ * The masks are the forward's, regenerated from d_desc / d_key_mask.  d_amax_accum (optional): atomicMax of |dq|, |dk|, |dv| as float bits,
+ * NOT zeroed by the call (the two co-attentions fill column blocks of the same two gradient matrices). */
 size_t unimm_k_attention_backward_scratch(int B, int heads, int D, int Sq);
 int unimm_k_attention_backward(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, const void* d_o, int ldo,
                                const float* d_dO, const float* d_lse, int B, int heads, int D, int Sq, int Skv, int mask_kind,
                                const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind, float* d_dq, int lddq, float* d_dk,
-                               int lddk, float* d_dv, int lddv, void* d_scratch, size_t scratch_bytes, void* stream);
+                               int lddk, float* d_dv, int lddv, float* d_amax_accum, void* d_scratch, size_t scratch_bytes, void* stream);
 /* text embeddings without the LayerNorm (its input is what the backward needs): word + position + (type | type-extension)
  * (models/vilbert_dialog.py:334-352) -> d_out fp32 [rows, H]; and the scatter-add of that sum's gradient into the four tables
  * (accumulating: the word table's gradient also receives the tied decoder's). */

@@ -23,6 +23,15 @@ def _gelu(x):
 class TorchOps:
     precision = "fp64"
 
+    def begin_step(self):
+        pass
+
+    def new_amax_cell(self):
+        return None
+
+    def register_amax(self, t, cell):
+        pass
+
     def empty32(self, *shape):
         return torch.full(shape, float("nan"), dtype=DT)       # reading an "empty" buffer before it is written poisons the result
 
@@ -139,7 +148,7 @@ class TorchOps:
     def attention(self, q, k, v, B, heads, D, Sq, Skv, mask_kind, desc=None, key_mask=None):
         return self._attn(q, k, v, B, heads, D, Sq, Skv, self._add_mask(B, Sq, Skv, mask_kind, desc, key_mask))
 
-    def attention_backward(self, q, k, v, o, lse, dO, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv):
+    def attention_backward(self, q, k, v, o, lse, dO, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv, amax_cell=None):
         qq, kk, vv = (t.detach().clone().requires_grad_() for t in (q, k, v))
         oo, _ = self._attn(qq, kk, vv, B, heads, D, Sq, Skv, self._add_mask(B, Sq, Skv, mask_kind, desc, key_mask))
         a, b, c = torch.autograd.grad(oo, (qq, kk, vv), dO)

@@ -44,6 +44,7 @@ struct BwdArgs {
     float scale;
     const float* inv_scale;         // device: 1 / (scale applied to dO)
     float ds_shift;                 // factor applied to dS before it is rounded to 16 bits
+    unsigned* amax;                 // optional: max |dq|, |dk|, |dv| written (float bits, atomicMax) for the consumer's 16-bit scale
 };
 
 // allowed key set of query row qr: [lo, hi) U {self}, the forward's row_set (attention_mma.cu) — padding rows included, so that
@@ -226,11 +227,18 @@ attn_bwd_dq_kernel(BwdArgs a, int kv_rows) {
     }
     const float f = a.scale * a.inv_scale[0] / a.ds_shift;
     float* DQ = a.dq + static_cast<size_t>(b) * Sq * a.lddq + h * D;
+    float mx = 0.f;
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {
         const int col = i * 8 + 2 * t;
-        if (row[0] < Sq) *reinterpret_cast<float2*>(DQ + static_cast<size_t>(row[0]) * a.lddq + col) = make_float2(dq[i][0] * f, dq[i][1] * f);
-        if (row[1] < Sq) *reinterpret_cast<float2*>(DQ + static_cast<size_t>(row[1]) * a.lddq + col) = make_float2(dq[i][2] * f, dq[i][3] * f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dq[i][e] *= f; mx = fmaxf(mx, fabsf(dq[i][e])); }
+        if (row[0] < Sq) *reinterpret_cast<float2*>(DQ + static_cast<size_t>(row[0]) * a.lddq + col) = make_float2(dq[i][0], dq[i][1]);
+        if (row[1] < Sq) *reinterpret_cast<float2*>(DQ + static_cast<size_t>(row[1]) * a.lddq + col) = make_float2(dq[i][2], dq[i][3]);
+    }
+    if (a.amax != nullptr) {       // rows beyond Sq hold zeros (their dO is zero-staged), so they cannot raise the maximum
+        const unsigned u = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+        if (lane == 0) atomicMax(a.amax, u);
     }
 }
 
@@ -360,16 +368,23 @@ attn_bwd_dkv_kernel(BwdArgs a, int q_rows) {
     const float fv = a.inv_scale[0], fk = a.scale * a.inv_scale[0] / a.ds_shift;
     float* DK = a.dk + static_cast<size_t>(b) * Skv * a.lddk + h * D;
     float* DV = a.dv + static_cast<size_t>(b) * Skv * a.lddv + h * D;
+    float mx = 0.f;
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {
         const int col = i * 8 + 2 * t;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             if (key[r] < Skv) {
-                *reinterpret_cast<float2*>(DK + static_cast<size_t>(key[r]) * a.lddk + col) = make_float2(dk[i][2 * r] * fk, dk[i][2 * r + 1] * fk);
-                *reinterpret_cast<float2*>(DV + static_cast<size_t>(key[r]) * a.lddv + col) = make_float2(dv[i][2 * r] * fv, dv[i][2 * r + 1] * fv);
+                const float2 k2 = make_float2(dk[i][2 * r] * fk, dk[i][2 * r + 1] * fk), v2 = make_float2(dv[i][2 * r] * fv, dv[i][2 * r + 1] * fv);
+                *reinterpret_cast<float2*>(DK + static_cast<size_t>(key[r]) * a.lddk + col) = k2;
+                *reinterpret_cast<float2*>(DV + static_cast<size_t>(key[r]) * a.lddv + col) = v2;
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(k2.x), fabsf(k2.y))), fmaxf(fabsf(v2.x), fabsf(v2.y)));
             }
         }
+    }
+    if (a.amax != nullptr) {
+        const unsigned u = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+        if (lane == 0) atomicMax(a.amax, u);
     }
 }
 
@@ -415,7 +430,7 @@ size_t attention_backward_scratch(int B, int heads, int D, int Sq) {
 }
 
 int attention_backward_lp(const AttnArgs& f, const float* dO, int lddo, const float* lse, float* dq, int lddq, float* dk, int lddk,
-                          float* dv, int lddv, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+                          float* dv, int lddv, void* scratch, size_t scratch_bytes, cudaStream_t stream, float* amax_accum) {
     UNIMM_CHECK(f.B > 0 && f.B <= 65535 && f.heads > 0 && f.Sq > 0 && f.Skv > 0 && f.Sq <= 256 && f.Skv <= 256, "attention backward: bad problem size");
     UNIMM_CHECK(f.D == 64 || f.D == 128, "attention backward: head dim must be 64 or 128");
     UNIMM_CHECK((f.ldq % 8) == 0 && (f.ldk % 8) == 0 && (f.ldv % 8) == 0 && (f.ldo % 2) == 0, "attention backward: rows must be 16-byte aligned");
@@ -443,6 +458,7 @@ int attention_backward_lp(const AttnArgs& f, const float* dO, int lddo, const fl
     a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv;
     a.B = f.B; a.heads = f.heads; a.Sq = f.Sq; a.Skv = f.Skv; a.mask_kind = f.mask_kind; a.desc = f.desc; a.key_mask = f.key_mask;
     a.scale = f.scale; a.inv_scale = sc + 1; a.ds_shift = f.lp_kind == LP_FP16 ? 0.0625f : 1.f;
+    a.amax = reinterpret_cast<unsigned*>(amax_accum);      // NOT zeroed here: several calls may fill column blocks of one gradient matrix
     if (f.lp_kind == LP_FP16) return f.D == 64 ? run_bwd<64, true>(a, stream) : run_bwd<128, true>(a, stream);
     return f.D == 64 ? run_bwd<64, false>(a, stream) : run_bwd<128, false>(a, stream);
 }

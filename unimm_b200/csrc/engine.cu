@@ -1624,11 +1624,12 @@ size_t unimm_k_linear_backward_scratch(int M, int N, int K) {
 
 int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
                             float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
-    return unimm_k_linear_backward_acc(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, 0, d_dW, d_db, d_scratch, scratch_bytes, lp_kind, stream);
+    return unimm_k_linear_backward_acc(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, 0, d_dW, d_db, nullptr, d_scratch, scratch_bytes, lp_kind, stream);
 }
 
 int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
-                                int accumulate_dx, float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
+                                int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, void* d_scratch, size_t scratch_bytes, int lp_kind,
+                                void* stream) {
     UNIMM_CHECK(d_dY && d_X && d_W && d_scratch && M > 0 && N > 0 && K > 0, "bad argument");
     UNIMM_CHECK(N % 64 == 0 && K % 8 == 0 && ldy % 2 == 0, "linear backward: N must be a multiple of 64 (the dgrad contraction), K of 8");
     UNIMM_CHECK(scratch_bytes >= unimm_k_linear_backward_scratch(M, N, K), "scratch smaller than unimm_k_linear_backward_scratch()");
@@ -1644,7 +1645,7 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int
     UNIMM_CHECK(static_cast<size_t>(p - static_cast<char*>(d_scratch)) <= scratch_bytes, "scratch carve overflow");
     // the incoming gradient as a 16-bit operand: fp16 gets a power-of-two scale from its own maximum (gradients are routinely below
     // fp16's normal range), multiplied back out by the GEMM epilogues straight from device memory
-    UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st));
+    UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st, d_amax));
     UNIMM_TRY(cast_scaled_lp(d_dY, ldy, M, N, scale, dY16, N, lp_kind, st));
     static const bool transposed_copies = getenv("UNIMM_BWD_TRANSPOSE") != nullptr && atoi(getenv("UNIMM_BWD_TRANSPOSE")) != 0;
     if (!transposed_copies) {

@@ -436,7 +436,12 @@ int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float al
     return 0;
 }
 
-int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream) {
+int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax) {
+    if (known_amax != nullptr) {      // the producer of x already left max |x| (as float bits) in device memory: no pass over x
+        scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const unsigned*>(known_amax), want_scale, out2);
+        UNIMM_LAUNCH_CHECK(1);
+        return 0;
+    }
     // out2[0] doubles as the atomicMax cell before it receives the scale
     UNIMM_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), stream));
     int grid = static_cast<int>((n + 255) / 256);

@@ -102,9 +102,11 @@ int embed_text_ln_i32(const int32_t* ids, const int32_t* type_ids, const int32_t
 int layernorm_rows(const float* x, int ldx, int rows, int H, const float* gamma, const float* beta, float* y_f32,
                    bf16* y_bf16, int lp_kind, cudaStream_t stream);
 // backward of layernorm_rows (dx may not alias dy; dgamma / dbeta [H] are zeroed here) and of the erf GELU
+// amax_out (optional, device): receives max |dx| as float bits (zeroed here), so that the consumer that turns dx into a 16-bit operand
+// (linear backward) needs no pass of its own over it
 int layernorm_backward(const float* dy, const float* x, int rows, int H, const float* gamma, float* dx, float* dgamma, float* dbeta,
-                       cudaStream_t stream);
-int gelu_backward(const float* dy, const float* x, size_t n, float* dx, cudaStream_t stream);
+                       cudaStream_t stream, float* amax_out = nullptr);
+int gelu_backward(const float* dy, const float* x, size_t n, float* dx, cudaStream_t stream, float* amax_out = nullptr);
 // image location term: out[r, :] = loc[idx(r), 0:5] · Wloc[H,5]^T + bloc  (fp32, K = 5)
 int image_loc_embed(const float* loc, const int* feat_index, int B, int R, int H, const float* Wloc, const float* bloc,
                     float* out, cudaStream_t stream);
@@ -211,7 +213,7 @@ int lm_loss_coef(const float* logp, const float* weight, int n, float scale, flo
 int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float alpha, float* out, cudaStream_t stream);
 // dgrad / wgrad helpers (unimm_k_linear_backward): out2[0] = 2^k with max|x| * 2^k in [2^9, 2^10) (1 when want_scale == 0 or x == 0),
 // out2[1] = 1 / out2[0];  y16 = lp(x * out2[0]);  colsum[j] = sum_i x[i, j]
-int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream);
+int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax = nullptr);
 int cast_scaled_lp(const float* x, int ldx, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind, cudaStream_t stream);
 int column_sums_f32(const float* x, int ldx, int rows, int cols, float* out, cudaStream_t stream);
 // tcgen05 LM head tail: merge the per-tile (max, sum) partials

@@ -315,12 +315,13 @@ int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaS
 template <int NV>
 __global__ void __launch_bounds__(128)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int rows, const float* __restrict__ gamma,
-                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, unsigned* __restrict__ amax) {
     constexpr int H = NV * 128;
     __shared__ float s_dg[H], s_db[H];
     for (int i = threadIdx.x; i < H; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mx = 0.f;
     for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
         float4 xv[NV], gv[NV], dv[NV];
         float s = 0.f;
@@ -356,41 +357,70 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
             o.x = rstd * (gv[i].x - mg - xv[i].x * mgx); o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
             o.z = rstd * (gv[i].z - mg - xv[i].z * mgx); o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
             *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * H + c) = o;
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
             atomicAdd(&s_dg[c], dv[i].x * xv[i].x); atomicAdd(&s_dg[c + 1], dv[i].y * xv[i].y);
             atomicAdd(&s_dg[c + 2], dv[i].z * xv[i].z); atomicAdd(&s_dg[c + 3], dv[i].w * xv[i].w);
             atomicAdd(&s_db[c], dv[i].x); atomicAdd(&s_db[c + 1], dv[i].y); atomicAdd(&s_db[c + 2], dv[i].z); atomicAdd(&s_db[c + 3], dv[i].w);
         }
     }
+    if (amax != nullptr) {
+        const unsigned u = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+        if (lane == 0) atomicMax(amax, u);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < H; i += blockDim.x) { atomicAdd(dgamma + i, s_dg[i]); atomicAdd(dbeta + i, s_db[i]); }
 }
 int layernorm_backward(const float* dy, const float* x, int rows, int H, const float* gamma, float* dx, float* dgamma, float* dbeta,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, float* amax_out) {
     UNIMM_CHECK(rows > 0, "layernorm backward: no rows");
+    unsigned* am = reinterpret_cast<unsigned*>(amax_out);
+    if (am != nullptr) UNIMM_CUDA_CHECK(cudaMemsetAsync(am, 0, sizeof(unsigned), stream));
     UNIMM_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * H, stream));
     UNIMM_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * H, stream));
     int grid = (rows + 3) / 4;
     if (grid > 148 * 4) grid = 148 * 4;
-    if (H == 768) layernorm_bwd_kernel<6><<<grid, 128, 0, stream>>>(dy, x, rows, gamma, dx, dgamma, dbeta);
-    else if (H == 1024) layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(dy, x, rows, gamma, dx, dgamma, dbeta);
+    if (H == 768) layernorm_bwd_kernel<6><<<grid, 128, 0, stream>>>(dy, x, rows, gamma, dx, dgamma, dbeta, am);
+    else if (H == 1024) layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(dy, x, rows, gamma, dx, dgamma, dbeta, am);
     else UNIMM_CHECK(false, "layernorm backward: hidden size must be 768 or 1024");
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
 
 // backward of the exact (erf) GELU (reference :115-121): dx = dy * (Phi(x) + x * phi(x)); in place allowed (dx == dy)
-__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, size_t n, float* __restrict__ dx) {
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const float v = x[i];
-        const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
-        const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
-        dx[i] = dy[i] * (cdf + v * pdf);
+__device__ __forceinline__ float gelu_grad(float v) {
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+    return cdf + v * pdf;
+}
+// dy may alias dx (no __restrict__ on them); 128-bit accesses on the bulk, scalars on the tail
+__global__ void gelu_bwd_kernel(const float* dy, const float* __restrict__ x, size_t n, float* dx, unsigned* __restrict__ amax) {
+    float mx = 0.f;
+    const size_t n4 = n / 4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        float4 d = reinterpret_cast<const float4*>(dy)[i];
+        d.x *= gelu_grad(v.x); d.y *= gelu_grad(v.y); d.z *= gelu_grad(v.z); d.w *= gelu_grad(v.w);
+        reinterpret_cast<float4*>(dx)[i] = d;
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(d.x), fabsf(d.y))), fmaxf(fabsf(d.z), fabsf(d.w)));
+    }
+    for (size_t i = n4 * 4 + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float d = dy[i] * gelu_grad(x[i]);
+        dx[i] = d;
+        mx = fmaxf(mx, fabsf(d));
+    }
+    if (amax != nullptr) {
+        const unsigned u = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+        if ((threadIdx.x & 31) == 0) atomicMax(amax, u);
     }
 }
-int gelu_backward(const float* dy, const float* x, size_t n, float* dx, cudaStream_t stream) {
-    int grid = static_cast<int>((n + 255) / 256);
+int gelu_backward(const float* dy, const float* x, size_t n, float* dx, cudaStream_t stream, float* amax_out) {
+    int grid = static_cast<int>((n / 4 + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    gelu_bwd_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(dy, x, n, dx);
+    unsigned* am = reinterpret_cast<unsigned*>(amax_out);
+    if (am != nullptr) UNIMM_CUDA_CHECK(cudaMemsetAsync(am, 0, sizeof(unsigned), stream));
+    UNIMM_CHECK((reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0,
+                "gelu backward: 16-byte aligned buffers");
+    gelu_bwd_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(dy, x, n, dx, am);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

@@ -34,6 +34,7 @@ class DeviceOps:
         self.lp_dtype = torch.float16 if precision == "fp16" else torch.bfloat16
         self.kind = LP_FP16 if precision == "fp16" else LP_BF16
         self._scratch = None
+        self._amax = {}          # data_ptr of a gradient tensor -> (device cell holding max |x| as float bits, numel); see linear_backward
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -53,6 +54,16 @@ class DeviceOps:
         if self._scratch is None or self._scratch.numel() < nbytes:
             self._scratch = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=self.device)
         return self._scratch
+
+    # max |x| of a gradient, left on the device by the kernel that produced it, saves linear_backward its own pass over the tensor
+    def begin_step(self):
+        self._amax.clear()
+
+    def new_amax_cell(self):
+        return self.zeros32(1)
+
+    def register_amax(self, t, cell):
+        self._amax[t.data_ptr()] = (cell, t.numel())
 
     # ------------------------------------------------------------------ element-wise / rows
     def to_lp(self, x32):
@@ -105,8 +116,9 @@ class DeviceOps:
         """-> dx; the parameter gradients are written to ``g_gamma`` / ``g_beta``."""
         rows, H = x32.shape
         assert dy.is_contiguous() and x32.is_contiguous()
-        dx = self.empty32(rows, H)
-        check(lib.unimm_k_layernorm_backward(ptr(dy), ptr(x32), rows, H, ptr(gamma), ptr(dx), ptr(g_gamma), ptr(g_beta), self.stream))
+        dx, cell = self.empty32(rows, H), self.empty32(1)
+        check(lib.unimm_k_layernorm_backward_amax(ptr(dy), ptr(x32), rows, H, ptr(gamma), ptr(dx), ptr(g_gamma), ptr(g_beta), ptr(cell), self.stream))
+        self.register_amax(dx, cell)
         return dx
 
     def gelu(self, t32, want32=False, want16=True):
@@ -116,7 +128,9 @@ class DeviceOps:
         return g32, g16
 
     def gelu_backward(self, dy, t32):
-        check(lib.unimm_k_gelu_backward(ptr(dy), ptr(t32), dy.numel(), ptr(dy), self.stream))
+        cell = self.empty32(1)
+        check(lib.unimm_k_gelu_backward_amax(ptr(dy), ptr(t32), dy.numel(), ptr(dy), ptr(cell), self.stream))
+        self.register_amax(dy, cell)
         return dy
 
     # ------------------------------------------------------------------ projections
@@ -151,8 +165,11 @@ class DeviceOps:
         if need_dx:
             dx = dx_accum if dx_accum is not None else self.empty32(M, K)
             assert dx.is_contiguous() and tuple(dx.shape) == (M, K)
+        cell, n = self._amax.pop(dy32.data_ptr(), (None, 0))
+        if cell is not None and n != dy32.numel():
+            cell = None
         check(lib.unimm_k_linear_backward_acc(ptr(dy32), N, ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(dx), 1 if dx_accum is not None else 0,
-                                              ptr(g_w), ptr(g_b), ptr(sc), nbytes, self.kind, self.stream))
+                                              ptr(g_w), ptr(g_b), ptr(cell), ptr(sc), nbytes, self.kind, self.stream))
         return dx
 
     # ------------------------------------------------------------------ attention
@@ -164,14 +181,15 @@ class DeviceOps:
                                         ptr(desc), ptr(key_mask), self.kind, ptr(lse), self.stream))
         return o, lse
 
-    def attention_backward(self, q16, k16, v16, o16, lse, dO32, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv):
-        """dq / dk / dv: fp32 2-D views (column blocks of the projections' gradient matrices) that receive the result."""
+    def attention_backward(self, q16, k16, v16, o16, lse, dO32, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv, amax_cell=None):
+        """dq / dk / dv: fp32 2-D views (column blocks of the projections' gradient matrices) that receive the result; ``amax_cell``
+        (``new_amax_cell``) accumulates max |result| for ``register_amax`` on those matrices."""
         assert dO32.is_contiguous()
         nbytes = lib.unimm_k_attention_backward_scratch(B, heads, D, Sq)
         sc = self.scratch(nbytes)
         check(lib.unimm_k_attention_backward(ptr(q16), _ld(q16), ptr(k16), _ld(k16), ptr(v16), _ld(v16), ptr(o16), _ld(o16), ptr(dO32), ptr(lse), B,
                                              heads, D, Sq, Skv, mask_kind, ptr(desc), ptr(key_mask), self.kind, ptr(dq), _ld(dq), ptr(dk), _ld(dk),
-                                             ptr(dv), _ld(dv), ptr(sc), nbytes, self.stream))
+                                             ptr(dv), _ld(dv), ptr(amax_cell), ptr(sc), nbytes, self.stream))
 
     # ------------------------------------------------------------------ heads / losses
     def lm_head_loss_backward(self, h16, e16, bias, labels_i32, weight32, grad_scale, g_e, g_bias):

@@ -262,9 +262,10 @@ class TrainStep:
                                         P.G(a + "output.LayerNorm.bias"))
         dctx = ops.linear_backward(d_pre1, sv["ctx16"], P.P16(a + "output.dense.weight"), P.G(a + "output.dense.weight"), P.G(a + "output.dense.bias"))
         qkv16 = sv["qkv16"]
-        dqkv = ops.empty32(qkv16.shape[0], 3 * H)
+        dqkv, cell = ops.empty32(qkv16.shape[0], 3 * H), ops.new_amax_cell()
         ops.attention_backward(qkv16[:, :H], qkv16[:, H:2 * H], qkv16[:, 2 * H:], sv["ctx16"], sv["lse"], dctx, B, heads, D, S, S, mask_kind, desc,
-                               key_mask, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:])
+                               key_mask, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], cell)
+        ops.register_amax(dqkv, cell)
         wqkv = P.span(P.p16, a + "self.query.weight", a + "self.value.weight")
         return ops.linear_backward(dqkv, sv["x16"], wqkv, P.span(P.g, a + "self.query.weight", a + "self.value.weight"),
                                    P.span(P.g, a + "self.query.bias", a + "self.value.bias"), dx_accum=d_pre1)
@@ -310,13 +311,16 @@ class TrainStep:
         dctx_t = ops.linear_backward(dxt, sv["ctx_t"], P.P16(o + "dense2.weight"), P.G(o + "dense2.weight"), P.G(o + "dense2.bias"))
         qkv1, qkv2 = sv["qkv1"], sv["qkv2"]
         dqkv1, dqkv2 = ops.empty32(qkv1.shape[0], 3 * Hb), ops.empty32(qkv2.shape[0], 3 * Hb)
+        cell = ops.new_amax_cell()         # one bound for both matrices: each of the two attentions fills column blocks of both
         ops.attention_backward(qkv2[:, :Hb], qkv1[:, Hb:2 * Hb], qkv1[:, 2 * Hb:], sv["ctx_t"], sv["lse_t"], dctx_t, B, heads, D, S, R,
-                               MASK_KEY_VECTOR, None, inp["img_mask"], dqkv2[:, :Hb], dqkv1[:, Hb:2 * Hb], dqkv1[:, 2 * Hb:])
+                               MASK_KEY_VECTOR, None, inp["img_mask"], dqkv2[:, :Hb], dqkv1[:, Hb:2 * Hb], dqkv1[:, 2 * Hb:], cell)
         if dctx_v is None:              # no gradient reaches the image stream's output of this layer (cannot happen with the NSP / image losses on)
             dctx_v = ops.zeros32(qkv1.shape[0], Hb)
             dxv = ops.zeros32(qkv1.shape[0], sv["xv16"].shape[1])
         ops.attention_backward(qkv1[:, :Hb], qkv2[:, Hb:2 * Hb], qkv2[:, 2 * Hb:], sv["ctx_v"], sv["lse_v"], dctx_v, B, heads, D, R, S,
-                               MASK_CO_INTERVAL, inp["desc"], None, dqkv1[:, :Hb], dqkv2[:, Hb:2 * Hb], dqkv2[:, 2 * Hb:])
+                               MASK_CO_INTERVAL, inp["desc"], None, dqkv1[:, :Hb], dqkv2[:, Hb:2 * Hb], dqkv2[:, 2 * Hb:], cell)
+        ops.register_amax(dqkv1, cell)
+        ops.register_amax(dqkv2, cell)
         dxv = ops.linear_backward(dqkv1, sv["xv16"], P.span(P.p16, b + "query1.weight", b + "value1.weight"),
                                   P.span(P.g, b + "query1.weight", b + "value1.weight"), P.span(P.g, b + "query1.bias", b + "value1.bias"), dx_accum=dxv)
         dxt = ops.linear_backward(dqkv2, sv["xt16"], P.span(P.p16, b + "query2.weight", b + "value2.weight"),
@@ -330,6 +334,7 @@ class TrainStep:
         ops, P, cfg = self.ops, self.params, self.cfg
         if inp is None:
             inp = self.upload(batch)
+        ops.begin_step()
         B, S, R = inp["B"], inp["S"], inp["R"]
         P.g.zero_()
         saved = []
