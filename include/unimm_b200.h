@@ -259,6 +259,16 @@ int unimm_profile_bytes(unimm_engine_t* e, double* bytes, int ncat);
 int unimm_neural_ndcg(const float* d_y_pred, const float* d_y_true, int rows, int n_opt, float temperature, int max_iter, float tol,
                       float* d_ndcg, float* d_idcg, void* stream);
 int unimm_ensemble_normalise(const float* d_probs, int n_models, int rows, int n_opt, float* d_out, void* stream);
+/* Gradient of the dense-annotation objective (utils/rank_loss.py:518-581 under dense_annotation_finetuning.py:296's
+ * loss.backward()): d_dpred [rows, n_opt] = grad_scale * d neuralNDCG_transposed(y_pred, y_true) / d y_pred (the loss is -mean of the
+ * per-slate NDCG over the slates whose ideal DCG is not 0); d_ndcg (optional) [rows] the per-slate values; d_scratch_count: one int32.
+ * The Sinkhorn iterations are replayed and walked in reverse inside one CTA per slate. */
+int unimm_neural_ndcg_backward(const float* d_y_pred, const float* d_y_true, int rows, int n_opt, float temperature, int max_iter, float tol,
+                               float grad_scale, float* d_dpred, float* d_ndcg, int32_t* d_scratch_count, void* stream);
+/* y_pred of that objective: p0 = softmax(NSP logits [B, 2])[:, 0] (dense_annotation_finetuning.py:267-287), and its backward ADDED onto
+ * d_dlogits_accum [B, 2] */
+int unimm_t_nsp_prob0(const float* d_logits, int B, float* d_p0, void* stream);
+int unimm_t_nsp_prob0_backward(const float* d_logits, const float* d_dp0, int B, float* d_dlogits_accum, void* stream);
 
 /* Ranking metrics of the reference's utils/visdial_metrics.py on the device: d_scores [rows, n_opt]; optional d_gt_index
  * [rows] (sparse metrics), d_relevance [rows, n_opt] (NDCG), d_ranks [rows, n_opt] out (1-based, stable on ties).

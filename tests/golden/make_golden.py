@@ -366,6 +366,30 @@ def main():
              loss=np.array([c[2] for c in cases], dtype=np.float32), ens_probs=probs.numpy(), ens_out=res.numpy())
 
 
+    # ---------------------------------------------------------------- gradient of the dense-annotation objective
+    if want("rankloss_grad"):
+        import importlib
+        from oracle import rank_loss as orl
+        rl = importlib.import_module("utils.rank_loss")
+        g = np.random.RandomState(78)
+        ps, ys, grads, losses = [], [], [], []
+        for kind in range(4):
+            p = g.rand(3, 100).astype(np.float32)
+            if kind == 1:
+                p = (g.rand(3, 100) ** 4).astype(np.float32)            # peaked, NSP-like
+            y = g.choice([0, 0, 0, 0.2, 0.4, 0.6, 0.8, 1.0], size=(3, 100)).astype(np.float32)
+            if kind == 2:
+                y[1] = 0                                                 # a slate without any relevant option: no gradient there
+            if kind == 3:
+                p[0, 10:14] = p[0, 10]                                   # tied scores (abs'(0) = 0)
+            tp = torch.from_numpy(p.copy()).requires_grad_()
+            loss = rl.neuralNDCG_transposed(tp, torch.from_numpy(y.copy()))
+            loss.backward()                                             # dense_annotation_finetuning.py:296
+            mine = orl.neural_ndcg_transposed_grad(p, y)
+            assert np.abs(mine - tp.grad.numpy()).max() < 1e-5 * np.abs(tp.grad.numpy()).max(), kind
+            ps.append(p), ys.append(y), grads.append(tp.grad.numpy().copy()), losses.append(np.float32(loss.detach()))
+        save("rankloss_grad", y_pred=np.stack(ps), y_true=np.stack(ys), grad=np.stack(grads), loss=np.array(losses, dtype=np.float32))
+
     # ---------------------------------------------------------------- bench-shape sweep slice: 3 rounds x 100 candidates of ONE image
     # (val_lm.py:104-137 over several rounds of an image: contexts of different lengths share one feature block).  Inputs are the
     # bench's own synthetic generator (unimm_b200.synthetic.synth_dialog_rounds), rebuilt here with the REFERENCE encoders and

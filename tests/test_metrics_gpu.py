@@ -56,3 +56,33 @@ def test_neural_ndcg_and_ensemble_match_reference_values():
         assert abs(got - float(want)) < 2e-5
     ens = ensemble_normalise(torch.from_numpy(z["ens_probs"]).cuda()).cpu().numpy()
     np.testing.assert_allclose(ens, z["ens_out"], atol=1e-6, rtol=0)
+
+
+def test_neural_ndcg_gradient_matches_reference_autograd():
+    """unimm_neural_ndcg_backward against ``y_pred.grad`` after ``neuralNDCG_transposed(y_pred, y_true).backward()`` of the unmodified
+    reference (tests/golden/rankloss_grad.npz), and the softmax(NSP)[:, 0] chain onto the logits against autograd."""
+    import os
+    import ctypes as C
+    from unimm_b200._lib import check, lib, ptr
+    from unimm_b200.rank_loss import neural_ndcg_loss_backward
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rankloss_grad.npz"))
+    for k, (p, y, want, loss) in enumerate(zip(z["y_pred"], z["y_true"], z["grad"], z["loss"])):
+        d, ndcg = neural_ndcg_loss_backward(torch.from_numpy(p).cuda(), torch.from_numpy(y).cuda())
+        err = np.abs(d.cpu().numpy() - want).max() / np.abs(want).max()
+        valid = (np.power(2.0, y) - 1).sum(-1) != 0
+        got_loss = -float(ndcg.cpu().numpy()[valid].sum() / valid.sum())
+        print(f"neuralNDCG gradient case {k}: max |err| / max |grad| = {err:.2e}; loss {got_loss:.7f} vs {float(loss):.7f}")
+        assert err < 2e-4 and abs(got_loss - float(loss)) < 2e-5
+        assert np.abs(d.cpu().numpy()[~valid]).max(initial=0.0) == 0.0
+    # y_pred = softmax(nsp)[:, 0] and its backward (accumulating)
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(100, 2, generator=g)
+    dp = torch.randn(100, generator=g)
+    x = logits.clone().requires_grad_()
+    torch.softmax(x, -1)[:, 0].backward(dp)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dl, dlog, p0 = logits.cuda(), torch.ones(100, 2, device="cuda"), torch.empty(100, device="cuda")
+    check(lib.unimm_t_nsp_prob0(ptr(dl), 100, ptr(p0), st))
+    check(lib.unimm_t_nsp_prob0_backward(ptr(dl), ptr(dp.cuda()), 100, ptr(dlog), st))
+    assert (p0.cpu() - torch.softmax(logits, -1)[:, 0]).abs().max().item() < 1e-6
+    assert (dlog.cpu() - 1.0 - x.grad).abs().max().item() < 1e-6

@@ -169,3 +169,13 @@ def test_sweep_fixture_sample_matches_reference(full_cfg):
                              dense_text_mask(desc, 256), torch.from_numpy(mask).expand(n, -1), dense_co_mask(desc, 256).unsqueeze(1).repeat(1, 37, 1),
                              masked_lm_labels=torch.from_numpy(r.labels[pick]))
         np.testing.assert_allclose(out["seq_score"].numpy(), g["seq_score"][ri, pick], atol=5 * TOL, rtol=0)
+
+
+def test_rank_loss_gradient_oracle_matches_reference_autograd():
+    """d neuralNDCG_transposed / d y_pred: the hand-derived chain against ``y_pred.grad`` of the unmodified reference."""
+    from oracle import rank_loss as orl
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rankloss_grad.npz"))
+    for p, y, want in zip(z["y_pred"], z["y_true"], z["grad"]):
+        got = orl.neural_ndcg_transposed_grad(p, y)
+        assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+    assert np.abs(z["grad"][2][1]).max() == 0.0          # the slate without a relevant option gets no gradient

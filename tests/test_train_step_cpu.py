@@ -128,3 +128,53 @@ def test_parameter_groups_and_flat_layout():
     assert param_group("bert.embeddings.sep_embeddings.weight") == 4
     for name, (off, pad, shp) in ps.entries.items():
         assert off % 64 == 0 and all(p >= s for p, s in zip(pad, shp)), name
+
+
+@pytest.mark.slow
+def test_dense_annotation_step_orchestration():
+    """dense_annotation_finetuning.py:253-296: loss = neuralNDCG_transposed(softmax(nsp)[:, 0], relevance) + lm + nsp CE (unweighted), no
+    image term — the image head's parameters get no gradient and are left alone by the optimizer."""
+    from oracle import rank_loss as orl
+    from oracle import vilbert_oracle as vo
+    from unimm_b200.config import tiny_config
+    from unimm_b200.train_step import TrainStep
+    from unimm_b200.weights import random_state_dict
+    cfg = tiny_config()
+    sd = random_state_dict(cfg, seed=6, perturbed=True)
+    n = 4
+    g, b, batch = _train_inputs(n)
+    rel = torch.tensor([[0.0, 0.4, 1.0, 0.0]])
+    batch = dict(batch, gt_relevance=rel, nsp_weight=None)
+    p = {k: v.double().clone().requires_grad_() for k, v in sd.items() if k != "cls.predictions.decoder.weight"}
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    ex = lambda a: torch.from_numpy(a)[None].expand(n, *a.shape)                                          # noqa: E731
+    o = vo.forward(p, cfg, b["tokens"][:n], ex(g["image_feat"]), ex(g["image_loc"]), b["segments"][:n], b["positions"][:n],
+                   b["txt_attention_mask"][:n], ex(g["image_mask"]), b["co_attention_mask"][:n], masked_lm_labels=b["mask"][:n],
+                   next_sentence_label=torch.from_numpy(g["next_sentence_label"])[:n], image_label=ex(g["image_label"]),
+                   image_target=ex(g["image_target"]), nsp_weight=None, lm_weight=b["weights"][:n], dtype=torch.float64)
+    p0 = torch.softmax(o["nsp_scores"], -1)[:, 0]
+    dnd = torch.from_numpy(orl.neural_ndcg_transposed_grad(p0.detach().numpy()[None], rel.numpy()))[0]
+    loss = o["lm_loss"] + o["nsp_loss"] + (p0 * dnd).sum()          # the last term's gradient IS the NDCG chain (dnd is a constant)
+    names = [k for k in p if k != "cls.predictions.decoder.weight"]
+    grads = dict(zip(names, torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)))
+    ts = TrainStep(cfg, sd, TorchOps(), img_coeff=0.0)
+    vals = ts.forward_backward(batch)
+    want_nd = float(orl.neural_ndcg_transposed(p0.detach().numpy()[None], rel.numpy())[0])
+    assert abs(vals["ndcg_loss"] - want_nd) < 1e-6 and abs(vals["lm_loss"] - float(o["lm_loss"].detach())) < 1e-9
+    got = ts.grad_dict()
+    gmax = max(float(x.abs().max()) for x in grads.values() if x is not None)
+    for k, gr in grads.items():
+        if gr is None:
+            assert float(got[k].abs().max()) == 0.0, k
+            continue
+        assert float((got[k].double() - gr).abs().max()) < 1e-8 * max(float(gr.abs().max()), 1e-6 * gmax), k
+    assert all(grads[k] is None for k in names if k.startswith("cls.imagePredictions."))
+    before = {k: v.clone() for k, v in ts.state_dict().items()}
+    ts.optimizer_step()
+    after = ts.state_dict()
+    for k in names:
+        changed = not torch.equal(before[k], after[k])
+        if grads[k] is None:
+            assert not changed, k                                  # no gradient: not even weight decay
+        elif float(grads[k].abs().max()) > 1e-6 * gmax:            # (key biases have an analytically zero gradient)
+            assert changed, k

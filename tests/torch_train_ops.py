@@ -187,6 +187,20 @@ class TorchOps:
         (d,) = torch.autograd.grad(loss * grad_scale, x)
         return loss.detach().reshape(1), d
 
+    def nsp_prob0(self, logits):
+        return torch.softmax(logits, -1)[:, 0].clone()
+
+    def nsp_prob0_backward(self, logits, dp0, dlogits_accum):
+        x = logits.detach().clone().requires_grad_()
+        (d,) = torch.autograd.grad(torch.softmax(x, -1)[:, 0], x, dp0)
+        dlogits_accum.add_(d)
+
+    def neural_ndcg_backward(self, y_pred, y_true, grad_scale, temperature=1.0, max_iter=50, tol=1e-6):
+        from oracle import rank_loss as orl
+        g = orl.neural_ndcg_transposed_grad(y_pred.numpy(), y_true.numpy(), temperature, max_iter, tol)
+        _, ndcg, _ = orl.neural_ndcg_transposed(y_pred.numpy(), y_true.numpy(), temperature, max_iter, tol)
+        return torch.from_numpy(g).to(DT) * grad_scale, torch.from_numpy(ndcg).to(DT)
+
     def adamw(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, correct_bias, inv_grad_scale, p16):
         gi = g * inv_grad_scale
         m.mul_(beta1).add_(gi, alpha=1 - beta1)

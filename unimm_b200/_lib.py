@@ -109,6 +109,9 @@ SYMBOLS = {
     "unimm_rank_metrics": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "unimm_neural_ndcg": (C.c_int, [_P, _P, _I, _I, C.c_float, _I, C.c_float, _P, _P, _P]),
     "unimm_ensemble_normalise": (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    "unimm_neural_ndcg_backward": (C.c_int, [_P, _P, _I, _I, C.c_float, _I, C.c_float, C.c_float, _P, _P, _P, _P]),
+    "unimm_t_nsp_prob0": (C.c_int, [_P, _I, _P, _P]),
+    "unimm_t_nsp_prob0_backward": (C.c_int, [_P, _P, _I, _P, _P]),
     "unimm_profile_begin": (C.c_int, [_P]),
     "unimm_profile_end": (C.c_int, [_P, _P, _P, _P, _I]),
     "unimm_profile_bytes": (C.c_int, [_P, _P, _I]),

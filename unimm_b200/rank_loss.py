@@ -1,4 +1,5 @@
-"""Dense-annotation objective pieces on the GPU (reference utils/rank_loss.py:518-581, val.py:152-161) — forward values.
+"""Dense-annotation objective pieces on the GPU (reference utils/rank_loss.py:518-581, val.py:152-161): forward values and the gradient
+of neuralNDCG_transposed with respect to the predicted scores (``neural_ndcg_loss_backward``).
 
 ``neural_ndcg_loss(y_pred, y_true)`` is ``neuralNDCG_transposed(y_pred, y_true)`` with the defaults
 dense_annotation_finetuning.py:288 uses; ``ensemble_normalise(probs)`` is the 5-model NSP ensemble of val.py / evaluate.py.
@@ -30,6 +31,22 @@ def neural_ndcg_loss(y_pred: torch.Tensor, y_true: torch.Tensor, temperature: fl
     valid = idcg != 0
     loss = -(ndcg.sum() / valid.sum()) if bool(valid.any()) else torch.zeros((), device=p.device)
     return (loss, ndcg, idcg) if return_parts else loss
+
+
+def neural_ndcg_loss_backward(y_pred: torch.Tensor, y_true: torch.Tensor, temperature: float = 1.0, max_iter: int = 50, tol: float = 1e-6,
+                              grad_scale: float = 1.0):
+    """-> (d loss / d y_pred * grad_scale  [same shape as y_pred], per-slate ndcg): what ``neuralNDCG_transposed(y_pred, y_true).backward()``
+    leaves in ``y_pred.grad`` (dense_annotation_finetuning.py:288-296), computed by ``unimm_neural_ndcg_backward``."""
+    if not y_pred.is_cuda:
+        raise ValueError("neural_ndcg_loss_backward runs on the device the scores live on (CUDA)")
+    n = y_pred.shape[-1]
+    p = y_pred.detach().reshape(-1, n).float().contiguous()
+    t = y_true.detach().reshape(-1, n).to(p.device, torch.float32).contiguous()
+    d, ndcg = torch.empty_like(p), torch.empty(p.shape[0], device=p.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=p.device)
+    check(lib.unimm_neural_ndcg_backward(ptr(p), ptr(t), p.shape[0], n, temperature, max_iter, tol, float(grad_scale), ptr(d), ptr(ndcg), ptr(cnt),
+                                         _stream(p.device)))
+    return d.view(*y_pred.shape), ndcg
 
 
 def ensemble_normalise(probs: torch.Tensor) -> torch.Tensor:

@@ -223,6 +223,23 @@ class DeviceOps:
                                    ptr(loss), ptr(d), ld, ptr(acc), self.stream))
         return loss, d
 
+    def nsp_prob0(self, logits32):
+        p0 = self.empty32(logits32.shape[0])
+        check(lib.unimm_t_nsp_prob0(ptr(logits32), logits32.shape[0], ptr(p0), self.stream))
+        return p0
+
+    def nsp_prob0_backward(self, logits32, dp0, dlogits_accum):
+        check(lib.unimm_t_nsp_prob0_backward(ptr(logits32), ptr(dp0), logits32.shape[0], ptr(dlogits_accum), self.stream))
+
+    def neural_ndcg_backward(self, y_pred, y_true, grad_scale, temperature=1.0, max_iter=50, tol=1e-6):
+        """-> (grad_scale * d neuralNDCG_transposed / d y_pred, per-slate ndcg)  (utils/rank_loss.py:518-581)."""
+        rows, n = y_pred.shape
+        d, ndcg = self.empty32(rows, n), self.empty32(rows)
+        cnt = torch.empty(1, dtype=torch.int32, device=self.device)
+        check(lib.unimm_neural_ndcg_backward(ptr(y_pred), ptr(y_true), rows, n, temperature, max_iter, tol, float(grad_scale), ptr(d), ptr(ndcg), ptr(cnt),
+                                             self.stream))
+        return d, ndcg
+
     # ------------------------------------------------------------------ optimizer
     def adamw(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, correct_bias, inv_grad_scale, p16):
         check(lib.unimm_t_adamw(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),

@@ -53,9 +53,10 @@ def is_language_weight(name: str) -> bool:
             (name.startswith("cls.predictions.") and name != "cls.predictions.decoder.weight"))
 
 
-def param_group(name: str) -> int:
-    """0 language + decay, 1 language no decay, 2 vision + decay, 3 vision no decay, 4 no gradient (never updated)."""
-    if any(m in name for m in UNUSED_MARKERS):
+def param_group(name: str, unused=()) -> int:
+    """0 language + decay, 1 language no decay, 2 vision + decay, 3 vision no decay, 4 no gradient (never updated: the reference's
+    AdamW skips parameters whose ``grad`` is None — not even weight decay touches them)."""
+    if any(m in name for m in UNUSED_MARKERS) or any(name.startswith(u) for u in unused):
         return 4
     nd = any(s in name for s in NO_DECAY)
     return (0 if is_language_weight(name) else 2) + (1 if nd else 0)
@@ -73,14 +74,14 @@ def warmup_linear_nonzero(step: int, base_lr: float, warmup_steps: int = 10000, 
 class ParamStore:
     """Flat fp32 master parameters, gradients, Adam moments and 16-bit operand copies with per-name views."""
 
-    def __init__(self, cfg: ViLBertConfig, ops):
+    def __init__(self, cfg: ViLBertConfig, ops, unused=()):
         self.cfg, self.ops = cfg, ops
         shapes = param_shapes(cfg)
         by_group = {g: [] for g in range(5)}
         for name, shp in shapes.items():
             if name in TIED:
                 continue
-            by_group[param_group(name)].append((name, tuple(shp)))
+            by_group[param_group(name, unused)].append((name, tuple(shp)))
         self.entries: "OrderedDict[str, tuple]" = OrderedDict()     # name -> (offset, padded shape, real shape)
         self.group_range = {}
         off = 0
@@ -162,7 +163,9 @@ class TrainStep:
                  img_coeff: float = 1.0, warmup_steps: int = 10000, t_total: int = 200000, batch_multiply: int = 1):
         cfg.validate()
         self.cfg, self.ops = cfg, ops
-        self.params = ParamStore(cfg, ops)
+        # a loss whose coefficient is 0 is not part of ``loss`` at all (dense_annotation_finetuning.py:289-293 drops the image term):
+        # its head gets no gradient, and parameters without a gradient are skipped by the optimizer
+        self.params = ParamStore(cfg, ops, unused=("cls.imagePredictions.",) if img_coeff == 0 else ())
         self.params.load_state_dict(state_dict)
         self.lr, self.image_lr, self.weight_decay, self.betas, self.eps = lr, image_lr, weight_decay, betas, eps
         self.coeff = (lm_coeff, nsp_coeff, img_coeff)
@@ -216,6 +219,11 @@ class TrainStep:
         d["nsl"] = up(batch["next_sentence_label"], torch.int64)
         nw = batch.get("nsp_weight")
         d["nsp_weight"] = None if nw is None else up(t(nw).reshape(-1)[:2], fdt)
+        rel = batch.get("gt_relevance")           # dense-annotation fine-tuning: [slates, options] with slates * options == B, in batch order
+        if rel is not None:
+            rel = t(rel).float()
+            assert rel.dim() == 2 and rel.numel() == B, "gt_relevance: [slates, options] covering the batch"
+            d["relevance"] = up(rel, fdt)
         return d
 
     # ------------------------------------------------------------------ layer pieces (forward saves, backward consumes)
@@ -390,6 +398,11 @@ class TrainStep:
         nsp_logits = ops.linear_f32(fused, P._view(P.p, "cls.bi_seq_relationship.weight", padded=False),
                                     P._view(P.p, "cls.bi_seq_relationship.bias", padded=False))
         out["nsp_loss"], d_nsp = ops.nsp_ce(nsp_logits, inp["nsl"], inp["nsp_weight"], nsp_c)
+        if "relevance" in inp:
+            # dense-annotation objective (dense_annotation_finetuning.py:267-293): neuralNDCG_transposed on y_pred = softmax(nsp)[:, 0]
+            p0 = ops.nsp_prob0(nsp_logits)
+            d_p0, out["ndcg"] = ops.neural_ndcg_backward(p0.view(*inp["relevance"].shape), inp["relevance"], 1.0 / self.batch_multiply)
+            ops.nsp_prob0_backward(nsp_logits, d_p0.view(-1), d_nsp)
         d_nsp64 = ops.zeros32(B, 64)
         d_nsp64[:, :2].copy_(d_nsp)
         dfused = ops.linear_backward(d_nsp64, ops.to_lp(fused), P.P16("cls.bi_seq_relationship.weight"), P.G("cls.bi_seq_relationship.weight"),
@@ -402,19 +415,20 @@ class TrainStep:
         ops.scatter_add_rows(dcls_t, inp["cls_rows"], d_xt)
         ops.scatter_add_rows(dcls_v, inp["img0_rows"], d_xv)
         # ---- image head + masked KL (:1085-1088, :1569-1574)
-        ih = "cls.imagePredictions."
-        tv, _ = ops.linear(xv16, P.P16(ih + "transform.dense.weight"), P.P(ih + "transform.dense.bias"))
-        gv32, _ = ops.gelu(tv, want32=True, want16=False)
-        _, hv16 = ops.layernorm(gv32, P.P(ih + "transform.LayerNorm.weight"), P.P(ih + "transform.LayerNorm.bias"), want32=False)
-        v_logits, _ = ops.linear(hv16, P.P16(ih + "decoder.weight"), P.P(ih + "decoder.bias"))
-        out["img_loss"], d_vlog = ops.image_kl(v_logits, cfg.v_target_size, inp["img_target"], inp["img_row_of"], inp["img_label"], img_c)
-        dhv = ops.linear_backward(d_vlog, hv16, P.P16(ih + "decoder.weight"), P.G(ih + "decoder.weight"), P.G(ih + "decoder.bias"))
-        dgv = ops.layernorm_backward(dhv, gv32, P.P(ih + "transform.LayerNorm.weight"), P.G(ih + "transform.LayerNorm.weight"),
-                                     P.G(ih + "transform.LayerNorm.bias"))
-        dtv = ops.gelu_backward(dgv, tv)
-        d_xv = ops.linear_backward(dtv, xv16, P.P16(ih + "transform.dense.weight"), P.G(ih + "transform.dense.weight"),
-                                   P.G(ih + "transform.dense.bias"), dx_accum=d_xv)
-        del tv, gv32, hv16, v_logits, d_vlog, dhv
+        if self.coeff[2] != 0:
+            ih = "cls.imagePredictions."
+            tv, _ = ops.linear(xv16, P.P16(ih + "transform.dense.weight"), P.P(ih + "transform.dense.bias"))
+            gv32, _ = ops.gelu(tv, want32=True, want16=False)
+            _, hv16 = ops.layernorm(gv32, P.P(ih + "transform.LayerNorm.weight"), P.P(ih + "transform.LayerNorm.bias"), want32=False)
+            v_logits, _ = ops.linear(hv16, P.P16(ih + "decoder.weight"), P.P(ih + "decoder.bias"))
+            out["img_loss"], d_vlog = ops.image_kl(v_logits, cfg.v_target_size, inp["img_target"], inp["img_row_of"], inp["img_label"], img_c)
+            dhv = ops.linear_backward(d_vlog, hv16, P.P16(ih + "decoder.weight"), P.G(ih + "decoder.weight"), P.G(ih + "decoder.bias"))
+            dgv = ops.layernorm_backward(dhv, gv32, P.P(ih + "transform.LayerNorm.weight"), P.G(ih + "transform.LayerNorm.weight"),
+                                         P.G(ih + "transform.LayerNorm.bias"))
+            dtv = ops.gelu_backward(dgv, tv)
+            d_xv = ops.linear_backward(dtv, xv16, P.P16(ih + "transform.dense.weight"), P.G(ih + "transform.dense.weight"),
+                                       P.G(ih + "transform.dense.bias"), dx_accum=d_xv)
+            del tv, gv32, hv16, v_logits, d_vlog, dhv
         # ---- encoder, in reverse
         for sv in reversed(saved):
             kind, i = sv["kind"], sv["i"]
@@ -436,9 +450,16 @@ class TrainStep:
                             P.G(ve + "image_location_embeddings.bias"), need_dx=False)
         if not read_losses:
             return out
+        ndcg = out.pop("ndcg", None)
         vals = {k: float(v.item()) for k, v in out.items()}              # the step's device -> host read
         vals.setdefault("lm_loss", 0.0)
+        vals.setdefault("img_loss", 0.0)
         vals["loss"] = self.coeff[0] * vals["lm_loss"] + self.coeff[1] * vals["nsp_loss"] + self.coeff[2] * vals["img_loss"]
+        if ndcg is not None:                                              # -mean of the per-slate NDCG over the slates with a relevant option
+            nd = ndcg.detach().cpu().double()
+            nz = nd != 0
+            vals["ndcg_loss"] = float(-(nd[nz].sum() / nz.sum())) if bool(nz.any()) else 0.0
+            vals["loss"] += vals["ndcg_loss"]
         return vals
 
     def optimizer_step(self):
