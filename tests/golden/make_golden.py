@@ -295,6 +295,46 @@ def main():
              nsp_weight=np.array([[5.0, 1.0]], dtype=np.float32),
              lm_loss=lm_loss.numpy(), img_loss=img_loss.numpy(), nsp_loss=nsp_loss.numpy(), nsp_scores=nsp.numpy())
 
+    # ---------------------------------------------------------------- backward of the train step: the reference's own
+    # autograd on the train6_perturbed batch — loss = lm + nsp + img as train.py:163-168 builds it, loss.backward() as :453 — with the
+    # dropout layers in eval mode.  250 M gradient values do not fit a fixture: per parameter its L2 norm and sum, a few small tensors in full.
+    if want("train6_grads"):
+        sys.path.insert(0, os.path.dirname(HERE))
+        from conftest import load_golden
+        g6, b6 = load_golden("train6_perturbed")
+        extras = dict(next_sentence_label=torch.from_numpy(g6["next_sentence_label"]),
+                      image_label=torch.from_numpy(g6["image_label"]).unsqueeze(0).expand(6, -1).contiguous(),
+                      image_target=torch.from_numpy(g6["image_target"]).unsqueeze(0).expand(6, -1, -1).contiguous(),
+                      nsp_weight=torch.from_numpy(g6["nsp_weight"]))
+        model = get_model(int(g6["weight_seed"]), bool(g6["perturbed"]))
+        model.eval()
+        for prm in model.parameters():
+            prm.grad = None
+        kw = dict(sep_indices=b6["sep_indices"], sep_len=None, token_type_ids=b6["segments"], token_position_ids=b6["positions"],
+                  masked_lm_labels=b6["mask"], attention_mask=b6["txt_attention_mask"], output_nsp_scores=False, output_lm_scores=False,
+                  image_attention_mask=b6["image_mask"], co_attention_mask=b6["co_attention_mask"], lm_weight=b6["weights"], **extras)
+        lm_loss, img_loss, nsp_loss = model(b6["tokens"], b6["image_feat"], b6["image_loc"], **kw)
+        loss = 1.0 * lm_loss.mean() + 1.0 * nsp_loss.mean() + 1.0 * img_loss.mean()                 # train.py:163-168
+        loss.backward()                                                                             # train.py:453 (without the GradScaler factor)
+        names, norms, sums, none = [], [], [], []
+        full = {}
+        keep = ("bert.encoder.layer.11.output.LayerNorm.weight", "bert.encoder.layer.0.attention.self.query.bias",
+                "bert.encoder.c_layer.2.biOutput.LayerNorm1.bias", "bert.encoder.v_layer.3.attention.output.dense.bias",
+                "cls.bi_seq_relationship.weight", "cls.predictions.transform.dense.bias", "bert.embeddings.token_type_embeddings_extension.weight",
+                "bert.v_embeddings.image_location_embeddings.weight", "bert.t_pooler.dense.bias")
+        for n_, prm in model.named_parameters():
+            k = n_[len("bert_pretrained."):] if n_.startswith("bert_pretrained.") else n_
+            names.append(k)
+            if prm.grad is None:
+                none.append(True), norms.append(0.0), sums.append(0.0)
+                continue
+            none.append(False), norms.append(float(prm.grad.double().norm())), sums.append(float(prm.grad.double().sum()))
+            if k in keep:
+                full["grad__" + k] = prm.grad.numpy().copy()
+        assert len(full) == len(keep), sorted(set(keep) - {k[6:] for k in full})
+        save("train6_grads", names=np.array(names), grad_norm=np.array(norms), grad_sum=np.array(sums), grad_none=np.array(none),
+             loss=np.float32(loss.detach()), **full)
+
     # ---------------------------------------------------------------- config 5: dense-annotation fine-tuning forward + loss
     # (dense_annotation_finetuning.py:253 -> train.forward; dataloader_dense_annotations.py:148-172: ONE mode per image,
     # relevance as the token weight -> the LongTensor truncates 0.2..0.8 to 0, relevance 0 makes the option a negative;

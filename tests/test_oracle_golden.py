@@ -179,3 +179,35 @@ def test_rank_loss_gradient_oracle_matches_reference_autograd():
         got = orl.neural_ndcg_transposed_grad(p, y)
         assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
     assert np.abs(z["grad"][2][1]).max() == 0.0          # the slate without a relevant option gets no gradient
+
+
+@pytest.mark.slow
+def test_oracle_autograd_matches_reference_backward(full_cfg):
+    """The checker of the training step's gradients is torch.autograd over the oracle's forward.  Pin it: on the train6_perturbed batch
+    every parameter's gradient (L2 norm, sum, and nine small tensors in full) equals what the UNMODIFIED reference left in ``.grad`` after
+    ``(lm + nsp + img).backward()`` (tests/golden/train6_grads.npz, made by tests/golden/make_golden.py)."""
+    from test_train_step_cpu import _train_inputs, oracle_losses_and_grads
+    from conftest import golden_state_dict
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train6_grads.npz"))
+    g, b, _ = _train_inputs(None)
+    sd = golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+    losses, grads = oracle_losses_and_grads(full_cfg, sd, b, g, b["tokens"].shape[0], dtype=torch.float32)
+    assert abs(sum(losses.values()) - float(z["loss"])) < 1e-4
+    gmax = float(z["grad_norm"].max())
+    seen = 0
+    for name, norm, total, none in zip(z["names"], z["grad_norm"], z["grad_sum"], z["grad_none"]):
+        name = str(name)
+        if name == "cls.predictions.decoder.weight":
+            continue
+        mine = grads[name]
+        if none:
+            assert mine is None, name
+            continue
+        seen += 1
+        assert abs(float(mine.double().norm()) - norm) < 2e-3 * max(norm, 1e-4 * gmax), (name, float(mine.double().norm()), norm)
+        assert abs(float(mine.double().sum()) - total) < 2e-3 * max(norm, 1e-4 * gmax) * np.sqrt(mine.numel()), name
+        key = "grad__" + name
+        if key in z.files:
+            want = z[key]
+            assert np.abs(mine.numpy() - want).max() < 2e-3 * max(np.abs(want).max(), 1e-6 * gmax), name
+    assert seen > 500

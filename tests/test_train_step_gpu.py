@@ -204,4 +204,55 @@ def test_train_step_full_config_matches_reference_losses_and_autograd(full_cfg):
     assert abs(vals["nsp_loss"] - g["nsp_loss"].item()) < 2e-2
     n = b["tokens"].shape[0]
     _, ref_grad = oracle_losses_and_grads(full_cfg, sd, b, g, n, dtype=torch.float32)
-    _compare_grads(ts.grad_dict(), ref_grad, 1e-1, 3e-2, "fp16 full config")
+    got = ts.grad_dict()
+    _compare_grads(got, ref_grad, 1e-1, 3e-2, "fp16 full config")
+    # and directly against what the UNMODIFIED reference left in .grad after loss.backward() on this batch (tests/golden/train6_grads.npz)
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train6_grads.npz"))
+    gmax, worst = float(z["grad_norm"].max()), 0.0
+    for name, norm, none in zip(z["names"], z["grad_norm"], z["grad_none"]):
+        name = str(name)
+        if name == "cls.predictions.decoder.weight" or none:
+            continue
+        worst = max(worst, abs(float(got[name].double().norm()) - norm) / max(norm, 1e-3 * gmax))
+        key = "grad__" + name
+        if key in z.files:
+            want = z[key]
+            e = np.abs(got[name].numpy() - want).max() / max(np.abs(want).max(), 1e-9)
+            print(f"[fp16 full config] vs the reference's own .grad: {name}: max |err| / max |grad| = {e:.3e}")
+            assert e < 1e-1, name
+    print(f"[fp16 full config] gradient L2 norms vs the reference's: worst relative difference {worst:.3e}")
+    assert worst < 5e-2
+
+
+@pytest.mark.parametrize("name", ["ft100gen_perturbed", "ft100dis_perturbed"])
+def test_dense_annotation_training_step_at_size(full_cfg, name):
+    """BASELINE config 5 as a TRAINING step (dense_annotation_finetuning.py:253-296): the 100 options of one annotated round, loss =
+    neuralNDCG_transposed + lm + NSP CE (no image term) — the loss values against the reference's, then backward + AdamW; the image
+    head, which gets no gradient, is not touched by the optimizer."""
+    from unimm_b200.descriptors import descriptors_from_masks
+    from unimm_b200.train_step import TrainStep
+    g, b = load_golden(name)
+    n = b["tokens"].shape[0]
+    sd = golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+    batch = {"tokens": b["tokens"], "segments": b["segments"], "positions": b["positions"], "labels": b["mask"], "weights": b["weights"],
+             "desc": descriptors_from_masks(b["txt_attention_mask"], b["co_attention_mask"]),
+             "next_sentence_label": torch.from_numpy(g["next_sentence_label"]), "image_feat": torch.from_numpy(g["image_feat"])[None],
+             "image_loc": torch.from_numpy(g["image_loc"])[None], "image_mask": torch.from_numpy(g["image_mask"])[None],
+             "image_label": torch.from_numpy(g["image_label"])[None], "image_target": torch.from_numpy(g["image_target"])[None],
+             "seq_image": torch.zeros(n, dtype=torch.int64), "gt_relevance": torch.from_numpy(g["relevance"]).view(1, n)}
+    ts = TrainStep(full_cfg, sd, DeviceOps(DEV, "fp16"), img_coeff=0.0, lr=5e-5, image_lr=5e-5, warmup_steps=0)
+    vals = ts.step(batch)
+    print(f"[fp16] {name}: lm {vals['lm_loss']:.6f}/{g['lm_loss'].item():.6f} nsp {vals['nsp_loss']:.6f}/{float(g['nsp_ce_unweighted']):.6f} "
+          f"neuralNDCG {vals['ndcg_loss']:.6f}/{float(g['neural_ndcg_loss']):.6f} total {vals['loss']:.6f}/{float(g['total_loss']):.6f}")
+    assert abs(vals["lm_loss"] - g["lm_loss"].item()) < 2e-2 and abs(vals["nsp_loss"] - float(g["nsp_ce_unweighted"])) < 2e-2
+    assert abs(vals["ndcg_loss"] - float(g["neural_ndcg_loss"])) < 2e-2 and abs(vals["loss"] - float(g["total_loss"])) < 6e-2
+    new = ts.state_dict()
+    assert all(torch.isfinite(v).all() for v in new.values())
+    for k, v in new.items():
+        if k.startswith("cls.imagePredictions.") or "q_dense" in k or "sep_embeddings" in k:
+            assert torch.equal(v, sd[k].float()), k
+    assert not torch.equal(new["cls.bi_seq_relationship.weight"], sd["cls.bi_seq_relationship.weight"].float())
+    second = ts.step(batch)
+    print(f"[fp16] {name}: total loss after one step at lr 5e-5: {second['loss']:.6f}")
+    assert second["loss"] < vals["loss"]
