@@ -450,6 +450,14 @@ def main_train_step(args):
     ms2 = e0.elapsed_time(e1)
     h2d = sum(v.numel() * v.element_size() for v in batches[0].values() if torch.is_tensor(v))
     pk = peaks()
+    op_table = None
+    if args.profile_ops:                 # one more step with every operation bracketed by events (not part of any timed number above)
+        from unimm_b200.train_ops import TimedOps
+        timed = TimedOps(ts.ops)
+        ts.ops = timed
+        ts.step(inp=inps[0], read_losses=False)
+        op_table = {k: {"calls": n, "ms": round(ms, 3)} for k, (n, ms) in timed.report().items()}
+        ts.ops = timed._ops
     # executed FLOPs: forward projections + attention of the dense layout (76.30 G per sequence) + the heads, x 3 for
     # forward + dgrad + wgrad (the attention backward recomputes S and dP in both of its kernels: 7 products against the forward's 2)
     n_lm = int((batches[0]["labels"] != -1).sum())
@@ -470,6 +478,8 @@ def main_train_step(args):
                                  "flop_count": "3 x forward (2 M N K per projection, attention, heads); recomputation not counted"},
             "e2e": {"value": args.steps * B / (ms2 * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
             "gpu_launches": launches, "peak_memory_gb": mem_gb, "clocks": clocks}
+    if op_table is not None:
+        line["ms_per_operation_of_one_step"] = op_table
     print(json.dumps(line), flush=True)
 
 
@@ -827,6 +837,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="steps", choices=["steps", "sweep", "train_fwd", "train_step", "dis_nsp", "dense_ft"],
                     help="sweep = the whole configs[1] sweep, strong-scaled; train_fwd / dis_nsp / dense_ft = configs 3 / 4 / 5 at their stated sizes (1 GPU)")
     ap.add_argument("--images", type=int, default=2064, help="--workload sweep: images of the sweep")
+    ap.add_argument("--profile-ops", action="store_true", help="--workload train_step: add a per-operation event-timed table of one extra step")
     ap.add_argument("--no-verify", action="store_true", help="skip the per-step context-equality check of the packer")
     ap.add_argument("--no-bf16", action="store_true", help="fp16 runs: skip the nested bf16_mode measurement")
     ap.add_argument("--ref-candidates", type=int, default=100, help="--impl reference: candidates per CPU step")

@@ -63,6 +63,21 @@ __device__ __forceinline__ void row_set(int mask_kind, const SeqDesc& desc, int 
     }
 }
 
+// Rows beyond these bounds are padding: no real query attends such a key, and such a query's dO is exactly zero (nothing labelled can
+// see a padding row, so no gradient ever reaches one — the backward of every row-wise operation maps a zero row to a zero row).  Whole
+// tiles of them are skipped: their dQ / dK / dV are zeros.
+__device__ __forceinline__ void real_extents(int mask_kind, const SeqDesc& d, int Sq, int Skv, int& q_real, int& k_real) {
+    q_real = Sq; k_real = Skv;
+    if (mask_kind == MASK_TEXT_SELF) {
+        const int T = d.mode == 1 ? d.L : d.L + d.last_len;
+        q_real = k_real = max(1, min(T, Skv));          // key 0 stays: the fallback of padding rows reads it (with a zero dO)
+    } else if (mask_kind == MASK_CO_INTERVAL) {
+        int lo, hi;
+        co_interval(d, Skv, lo, hi);
+        if (hi > lo) k_real = hi;
+    }
+}
+
 // KEY_VECTOR: 64-bit words of allowed keys (all ones for the other kinds; "no valid key" = all keys, as the forward)
 __device__ __forceinline__ void build_key_bits(const BwdArgs& a, int b, int kv_rows, unsigned long long* s_bits, int tid, int nthreads) {
     if (tid < 4) s_bits[tid] = 0ull;
@@ -136,16 +151,27 @@ attn_bwd_dq_kernel(BwdArgs a, int kv_rows) {
     const bf16* V = a.v + static_cast<size_t>(b) * Skv * a.ldv + h * D;
     const bf16* G = a.dO + static_cast<size_t>(b) * Sq * a.lddo + h * D;
 
+    SeqDesc desc = {0, 0, 0, 0};
+    if (a.mask_kind != MASK_KEY_VECTOR) desc = a.desc[b];
+    int q_real, k_real;
+    real_extents(a.mask_kind, desc, Sq, Skv, q_real, k_real);
+    if (q0 >= q_real) {                       // a block of padding queries: zeros (block-uniform exit before any barrier)
+        float* DQ = a.dq + static_cast<size_t>(b) * Sq * a.lddq + h * D;
+        for (int i = tid; i < MQT * (D / 4); i += NT) {
+            const int r = q0 + i / (D / 4), c = (i % (D / 4)) * 4;
+            if (r < Sq) *reinterpret_cast<float4*>(DQ + static_cast<size_t>(r) * a.lddq + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    const int kv_stage = min(kv_rows, ((k_real + MKT - 1) / MKT) * MKT);      // rows beyond are never touched (w_end <= kv_stage)
     stage_rows<D>(Qs, Q, a.ldq, q0, MQT, Sq, tid, NT);
     stage_rows<D>(Gs, G, a.lddo, q0, MQT, Sq, tid, NT);
-    stage_rows<D>(Ks, K, a.ldk, 0, kv_rows, Skv, tid, NT);
-    stage_rows<D>(Vs, V, a.ldv, 0, kv_rows, Skv, tid, NT);
+    stage_rows<D>(Ks, K, a.ldk, 0, kv_stage, Skv, tid, NT);
+    stage_rows<D>(Vs, V, a.ldv, 0, kv_stage, Skv, tid, NT);
     build_key_bits(a, b, kv_rows, s_bits, tid, NT);
     cp_async_wait_all();
     __syncthreads();
 
-    SeqDesc desc = {0, 0, 0, 0};
-    if (a.mask_kind != MASK_KEY_VECTOR) desc = a.desc[b];
     const int row[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
     int lo[2], hi[2], self[2];
     float lse2[2], dl[2];
@@ -161,7 +187,7 @@ attn_bwd_dq_kernel(BwdArgs a, int kv_rows) {
     int w_hi = max(max(hi[0], self[0] + 1), max(hi[1], self[1] + 1));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
-    const int w_end = min(((w_hi + MKT - 1) / MKT) * MKT, kv_rows);
+    const int w_end = min(((w_hi + MKT - 1) / MKT) * MKT, kv_stage);
 
     const float sl = a.scale * kLog2e;
     float dq[D / 8][4];
@@ -267,14 +293,29 @@ attn_bwd_dkv_kernel(BwdArgs a, int q_rows) {
     const bf16* V = a.v + static_cast<size_t>(b) * Skv * a.ldv + h * D;
     const bf16* G = a.dO + static_cast<size_t>(b) * Sq * a.lddo + h * D;
 
-    stage_rows<D>(Ks, K, a.ldk, k0, MKT_CTA, Skv, tid, NT);
-    stage_rows<D>(Vs, V, a.ldv, k0, MKT_CTA, Skv, tid, NT);
-    stage_rows<D>(Qs, Q, a.ldq, 0, q_rows, Sq, tid, NT);
-    stage_rows<D>(Gs, G, a.lddo, 0, q_rows, Sq, tid, NT);
     SeqDesc desc = {0, 0, 0, 0};
     if (a.mask_kind != MASK_KEY_VECTOR) desc = a.desc[b];
+    int q_real, k_real;
+    real_extents(a.mask_kind, desc, Sq, Skv, q_real, k_real);
+    if (k0 >= k_real) {                       // a block of keys no real query attends: zeros (block-uniform exit before any barrier)
+        float* DK = a.dk + static_cast<size_t>(b) * Skv * a.lddk + h * D;
+        float* DV = a.dv + static_cast<size_t>(b) * Skv * a.lddv + h * D;
+        for (int i = tid; i < MKT_CTA * (D / 4); i += NT) {
+            const int r = k0 + i / (D / 4), c = (i % (D / 4)) * 4;
+            if (r < Skv) {
+                *reinterpret_cast<float4*>(DK + static_cast<size_t>(r) * a.lddk + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(DV + static_cast<size_t>(r) * a.lddv + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        return;
+    }
+    const int q_lim = min(q_rows, ((q_real + MKT - 1) / MKT) * MKT);          // query tiles beyond hold padding rows only
+    stage_rows<D>(Ks, K, a.ldk, k0, MKT_CTA, Skv, tid, NT);
+    stage_rows<D>(Vs, V, a.ldv, k0, MKT_CTA, Skv, tid, NT);
+    stage_rows<D>(Qs, Q, a.ldq, 0, q_lim, Sq, tid, NT);
+    stage_rows<D>(Gs, G, a.lddo, 0, q_lim, Sq, tid, NT);
     const size_t stat0 = (static_cast<size_t>(b) * a.heads + h) * Sq;
-    for (int r = tid; r < q_rows; r += NT) {
+    for (int r = tid; r < q_lim; r += NT) {
         int l = 0, hh = 0, sf = -1;
         if (r < Sq) row_set(a.mask_kind, desc, Skv, r, l, hh, sf);
         s_lo[r] = l; s_hi[r] = hh; s_self[r] = sf;
@@ -300,7 +341,7 @@ attn_bwd_dkv_kernel(BwdArgs a, int q_rows) {
     }
     const int a_off = (warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + 8 * (lane >> 4);
 
-    for (int t0 = 0; t0 < q_rows; t0 += MKT) {
+    for (int t0 = 0; t0 < q_lim; t0 += MKT) {
         const bf16* q_tile = Qs + static_cast<size_t>(t0) * LD;
         const bf16* g_tile = Gs + static_cast<size_t>(t0) * LD;
         float s[8][4], dp[8][4];
@@ -434,7 +475,8 @@ int attention_backward_lp(const AttnArgs& f, const float* dO, int lddo, const fl
     UNIMM_CHECK(f.B > 0 && f.B <= 65535 && f.heads > 0 && f.Sq > 0 && f.Skv > 0 && f.Sq <= 256 && f.Skv <= 256, "attention backward: bad problem size");
     UNIMM_CHECK(f.D == 64 || f.D == 128, "attention backward: head dim must be 64 or 128");
     UNIMM_CHECK((f.ldq % 8) == 0 && (f.ldk % 8) == 0 && (f.ldv % 8) == 0 && (f.ldo % 2) == 0, "attention backward: rows must be 16-byte aligned");
-    UNIMM_CHECK((lddq % 2) == 0 && (lddk % 2) == 0 && (lddv % 2) == 0 && lddo == f.heads * f.D, "attention backward: dO must be contiguous [rows, heads * D]");
+    UNIMM_CHECK((lddq % 4) == 0 && (lddk % 4) == 0 && (lddv % 4) == 0 && lddo == f.heads * f.D, "attention backward: dO must be contiguous [rows, heads * D], gradient rows 16-byte aligned");
+    UNIMM_CHECK(((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0, "attention backward: 16-byte aligned gradient matrices");
     UNIMM_CHECK(f.mask_kind == MASK_KEY_VECTOR ? f.key_mask != nullptr : f.desc != nullptr, "attention backward: mask operand missing");
     UNIMM_CHECK(dO && lse && dq && dk && dv && scratch, "attention backward: null argument");
     UNIMM_CHECK(scratch_bytes >= attention_backward_scratch(f.B, f.heads, f.D, f.Sq), "attention backward: scratch too small");

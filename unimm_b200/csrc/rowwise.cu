@@ -311,7 +311,8 @@ int split_f32_to_hilo(const float* x, int ldx, int rows, int K, bf16* out, cudaS
 
 // ---- backward of y = LayerNorm(x) * gamma + beta (eps inside the sqrt, biased variance — BertLayerNorm, reference :270-279) ----
 //   xhat = (x - mean) * rstd;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma = sum_rows dy * xhat;  dbeta = sum_rows dy
-// One warp per row; the column sums go through per-block shared accumulators and one atomicAdd per column and block.
+// One warp per row (grid-stride); every lane keeps the column sums of ITS columns in registers over all the rows its warp handles and
+// adds them to the per-block shared accumulators once at the end (one atomic per column, warp and block instead of one per element).
 template <int NV>
 __global__ void __launch_bounds__(128)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int rows, const float* __restrict__ gamma,
@@ -322,12 +323,16 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float mx = 0.f;
+    float4 acc_g[NV], acc_b[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc_g[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
         float4 xv[NV], gv[NV], dv[NV];
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             xv[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * H + (lane + 32 * i) * 4);
+            dv[i] = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * H + (lane + 32 * i) * 4);
             s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
         }
         const float mean = warp_sum(s) * (1.0f / H);
@@ -342,7 +347,6 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (lane + 32 * i) * 4;
-            dv[i] = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * H + c);
             const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
             xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;            // xhat
             gv[i] = make_float4(dv[i].x * gm.x, dv[i].y * gm.y, dv[i].z * gm.z, dv[i].w * gm.w);
@@ -358,10 +362,15 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
             o.z = rstd * (gv[i].z - mg - xv[i].z * mgx); o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
             *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * H + c) = o;
             mx = fmaxf(fmaxf(mx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-            atomicAdd(&s_dg[c], dv[i].x * xv[i].x); atomicAdd(&s_dg[c + 1], dv[i].y * xv[i].y);
-            atomicAdd(&s_dg[c + 2], dv[i].z * xv[i].z); atomicAdd(&s_dg[c + 3], dv[i].w * xv[i].w);
-            atomicAdd(&s_db[c], dv[i].x); atomicAdd(&s_db[c + 1], dv[i].y); atomicAdd(&s_db[c + 2], dv[i].z); atomicAdd(&s_db[c + 3], dv[i].w);
+            acc_g[i].x += dv[i].x * xv[i].x; acc_g[i].y += dv[i].y * xv[i].y; acc_g[i].z += dv[i].z * xv[i].z; acc_g[i].w += dv[i].w * xv[i].w;
+            acc_b[i].x += dv[i].x; acc_b[i].y += dv[i].y; acc_b[i].z += dv[i].z; acc_b[i].w += dv[i].w;
         }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        atomicAdd(&s_dg[c], acc_g[i].x); atomicAdd(&s_dg[c + 1], acc_g[i].y); atomicAdd(&s_dg[c + 2], acc_g[i].z); atomicAdd(&s_dg[c + 3], acc_g[i].w);
+        atomicAdd(&s_db[c], acc_b[i].x); atomicAdd(&s_db[c + 1], acc_b[i].y); atomicAdd(&s_db[c + 2], acc_b[i].z); atomicAdd(&s_db[c + 3], acc_b[i].w);
     }
     if (amax != nullptr) {
         const unsigned u = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));

@@ -244,3 +244,38 @@ class DeviceOps:
     def adamw(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, correct_bias, inv_grad_scale, p16):
         check(lib.unimm_t_adamw(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
                                 int(step), 1 if correct_bias else 0, float(inv_grad_scale), ptr(p16), self.kind, self.stream))
+
+
+class TimedOps:
+    """``DeviceOps`` with every call bracketed by CUDA events on the launch stream: ``report()`` -> per-operation totals of one or
+    more steps (bench.py --workload train_step --profile-ops).  Measurement aid only; the events serialise nothing on one stream."""
+
+    def __init__(self, ops: DeviceOps):
+        self._ops = ops
+        self._events = []
+
+    def __getattr__(self, name):
+        attr = getattr(self._ops, name)
+        if not callable(attr) or name in ("empty32", "zeros32", "empty16", "scratch", "begin_step", "new_amax_cell", "register_amax"):
+            return attr
+
+        def timed(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self._ops.device))
+            out = attr(*a, **kw)
+            e1.record(torch.cuda.current_stream(self._ops.device))
+            key = name
+            if name in ("linear", "linear_backward") and len(a) >= 3:
+                key = f"{name} M={a[0].shape[0]} N={a[2].shape[0] if name == 'linear_backward' else a[1].shape[0]} K={a[1].shape[1]}"
+            self._events.append((key, e0, e1))
+            return out
+        return timed
+
+    def report(self):
+        torch.cuda.synchronize(self._ops.device)
+        agg = {}
+        for key, e0, e1 in self._events:
+            n, ms = agg.get(key, (0, 0.0))
+            agg[key] = (n + 1, ms + e0.elapsed_time(e1))
+        self._events.clear()
+        return dict(sorted(agg.items(), key=lambda kv: -kv[1][1]))
