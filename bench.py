@@ -410,44 +410,62 @@ def main_train_step(args):
     from unimm_b200.train_ops import DeviceOps
     from unimm_b200.train_step import TrainStep
     from unimm_b200.weights import random_state_dict
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    import torch.distributed as dist
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                                 # data parallel: every rank steps on its own 240 sequences, one gradient all-reduce per step
+        dist.init_process_group("nccl", device_id=dev)
     cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
     batches = []
     for i in range(3):
-        b = {k: T(v).pin_memory() for k, v in syn.train_batch(1000 + i).items()}
+        b = {k: T(v).pin_memory() for k, v in syn.train_batch(1000 + 3 * rank + i).items()}
         b["nsp_weight"] = torch.tensor([5.0, 1.0]).pin_memory()
         batches.append(b)
     B = batches[0]["tokens"].shape[0]
     ts = TrainStep(cfg, random_state_dict(cfg, 0), DeviceOps(dev, args.precision))
     stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     inps = [ts.upload(b) for b in batches]
     for i in range(args.warmup):
         ts.step(inp=inps[i % 3], read_losses=False)
-    torch.cuda.synchronize(dev)
+    barrier()
     lib.unimm_reset_launch_count()
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.mark_start()
+    if sampler:
+        sampler.mark_start()
     ev0.record(stream)
     for i in range(args.steps):
         out = ts.step(inp=inps[i % 3], read_losses=False)
     ev1.record(stream)
-    torch.cuda.synchronize(dev)
+    barrier()
     launches = int(lib.unimm_launch_count())
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts.step(batches[0])
-    torch.cuda.synchronize(dev)
+    barrier()
     e0.record(stream)
     for i in range(args.steps):
-        vals = ts.step(batches[i % 3])                         # H2D of every input + forward + backward + AdamW + the loss values read back
+        vals = ts.step(batches[i % 3])                         # H2D of every input + forward + backward + (all-reduce) + AdamW + the loss values read back
     e1.record(stream)
-    torch.cuda.synchronize(dev)
-    ms2 = e0.elapsed_time(e1)
+    barrier()
+    ms2 = max_over_ranks(e0.elapsed_time(e1))
     h2d = sum(v.numel() * v.element_size() for v in batches[0].values() if torch.is_tensor(v))
     pk = peaks()
     op_table = None
@@ -463,24 +481,32 @@ def main_train_step(args):
     n_lm = int((batches[0]["labels"] != -1).sum())
     fwd = B * 76.30e9 + n_lm * (2 * 768 * 768 + 2 * 768 * 30522) + B * 37 * (2 * 1024 * 1024 + 2 * 1024 * 1601)
     flops = 3.0 * fwd
-    tfl = flops * args.steps / (ms_total * 1e-3) / 1e12
-    line = {"metric": "sequences_per_sec", "value": args.steps * B / (ms_total * 1e-3), "unit": "sequences/s", "n_gpus": 1, "steps": args.steps,
+    tfl = flops * args.steps / (ms_total * 1e-3) / 1e12                 # per GPU
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {"metric": "sequences_per_sec", "value": world * args.steps * B / (ms_total * 1e-3), "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "configs[2] as a full TRAINING step: train.py UniMM-UL, batch 240 = 40 images x 6 sequences (1 positive + 5 "
                                    "negatives), mixed generative / discriminative masks, mask_prob 0.15, unlikelihood on the negatives; forward + "
                                    "3 losses + backward + AdamW (4 parameter groups, 250 M parameters); dropout off",
-                       "sequences_per_step": B, "layout": "dense (256 rows per sequence)", "seq_len": 256, "regions": 37,
+                       "sequences_per_step": B * world, "layout": "dense (256 rows per sequence)", "seq_len": 256, "regions": 37,
                        "model": "bert_base_6layer_6conect, random init (seed 0)", "inputs": "3 distinct batches in rotation, activations + "
                        "gradients of a step (%.1f GB peak) far larger than L2" % mem_gb,
                        "losses_of_last_step": vals},
             "pct_of_bf16_peak": {"model_tflops": tfl, "burst": tfl / pk["burst"], "sustained": tfl / pk["sustained"], "peaks": pk["source"],
                                  "flop_count": "3 x forward (2 M N K per projection, attention, heads); recomputation not counted"},
-            "e2e": {"value": args.steps * B / (ms2 * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+            "e2e": {"value": world * args.steps * B / (ms2 * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
             "gpu_launches": launches, "peak_memory_gb": mem_gb, "clocks": clocks}
+    if world > 1:
+        line["config"]["parallelism"] = "dp%d: one process per GPU, 240 sequences per rank and step, ONE NCCL all-reduce of the flat fp32 gradient buffer (%.2f GB) per step, 1 / world folded into AdamW" % (world, 4 * ts.params.group_range[3][1] / 2 ** 30)
     if op_table is not None:
         line["ms_per_operation_of_one_step"] = op_table
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main_dense_workload(args):

@@ -160,7 +160,7 @@ class TrainStep:
 
     def __init__(self, cfg: ViLBertConfig, state_dict: Dict[str, torch.Tensor], ops, lr: float = 2e-5, image_lr: float = 2e-5,
                  weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-6, lm_coeff: float = 1.0, nsp_coeff: float = 1.0,
-                 img_coeff: float = 1.0, warmup_steps: int = 10000, t_total: int = 200000, batch_multiply: int = 1):
+                 img_coeff: float = 1.0, warmup_steps: int = 10000, t_total: int = 200000, batch_multiply: int = 1, process_group=None):
         cfg.validate()
         self.cfg, self.ops = cfg, ops
         # a loss whose coefficient is 0 is not part of ``loss`` at all (dense_annotation_finetuning.py:289-293 drops the image term):
@@ -170,6 +170,15 @@ class TrainStep:
         self.lr, self.image_lr, self.weight_decay, self.betas, self.eps = lr, image_lr, weight_decay, betas, eps
         self.coeff = (lm_coeff, nsp_coeff, img_coeff)
         self.warmup_steps, self.t_total, self.batch_multiply = warmup_steps, t_total, batch_multiply
+        # data parallel (true DDP instead of the reference's DataParallelImbalance scatter / replicate / gather,
+        # utils/data_parallel.py): one process per GPU, every rank runs the step on ITS sequences, the flat gradient buffer is summed
+        # with ONE all-reduce (NCCL over NVLink; gloo in the CPU tests) and the 1 / world factor is folded into AdamW.  The reference
+        # normalises every loss per replica and averages the replicas (models/vilbert_dialog.py:1592-1595, train.py:164): the same
+        # mean of per-replica gradients.
+        self.group = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
         self.opt_step = 0            # AdamW state['step']
         self.sched_step = 0          # scheduler.last_epoch
         self.S, self.R = None, None
@@ -390,6 +399,8 @@ class TrainStep:
             dtt = ops.gelu_backward(dg, tt)
             dx_lm = ops.linear_backward(dtt, x_lm16, P.P16(t_ + "dense.weight"), P.G(t_ + "dense.weight"), P.G(t_ + "dense.bias"))
             ops.scatter_add_rows(dx_lm, inp["lm_rows"], d_xt)
+        else:
+            out["lm_loss"] = ops.zeros32(1)
         # ---- poolers + NSP head + weighted CE (:946-967, :1062-1070, :1605-1621)
         cls_t, cls_v = ops.gather_rows(xt32, inp["cls_rows"]), ops.gather_rows(xv32, inp["img0_rows"])
         pt = ops.linear_f32(cls_t, P.P("bert.t_pooler.dense.weight"), P.P("bert.t_pooler.dense.bias"), act=ACT_RELU)
@@ -448,9 +459,17 @@ class TrainStep:
                             need_dx=False)
         ops.linear_backward(d_vsum, loc16, P.P16(ve + "image_location_embeddings.weight"), P.G(ve + "image_location_embeddings.weight"),
                             P.G(ve + "image_location_embeddings.bias"), need_dx=False)
+        if self.world > 1:
+            a, b = P.group_range[0][0], P.group_range[3][1]               # every parameter that has a gradient, one contiguous range
+            torch.distributed.all_reduce(P.g[a:b], group=self.group)     # sum; optimizer_step divides by the world size
         if not read_losses:
             return out
         ndcg = out.pop("ndcg", None)
+        if self.world > 1:                                                # the mean of the replicas' loss values (train.py:164)
+            keys = sorted(out)
+            packed = torch.cat([out[k].reshape(1) for k in keys])
+            torch.distributed.all_reduce(packed, group=self.group)
+            out = {k: packed[i:i + 1] / self.world for i, k in enumerate(keys)}
         vals = {k: float(v.item()) for k, v in out.items()}              # the step's device -> host read
         vals.setdefault("lm_loss", 0.0)
         vals.setdefault("img_loss", 0.0)
@@ -471,8 +490,8 @@ class TrainStep:
         for g, (lr, wd) in enumerate(((lr_l, self.weight_decay), (lr_l, 0.0), (lr_v, self.weight_decay), (lr_v, 0.0))):
             a, b = P.group_range[g]
             if b > a:
-                ops.adamw(P.p[a:b], P.g[a:b], P.m[a:b], P.v[a:b], lr, self.betas[0], self.betas[1], self.eps, wd, self.opt_step, True, 1.0,
-                          P.p16[a:b])
+                ops.adamw(P.p[a:b], P.g[a:b], P.m[a:b], P.v[a:b], lr, self.betas[0], self.betas[1], self.eps, wd, self.opt_step, True,
+                          1.0 / self.world, P.p16[a:b])
         self.sched_step += 1
 
     def step(self, batch=None, inp=None, read_losses: bool = True) -> Dict[str, float]:
