@@ -355,10 +355,13 @@ int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const 
  * autograd is in the reference.  All gradients are fp32; every tensor-core operand is 16-bit (lp_kind 0 = bf16, 1 = fp16). */
 /* same as unimm_k_linear_backward; accumulate_dx != 0: dX += dY W (the residual branch's gradient is already in d_dX); d_amax (optional):
  * max |dY| as float bits, left on the device by the kernel that produced dY (the *_amax entry points below, unimm_k_attention_backward) —
- * the 16-bit operand scale is then derived without a pass over dY */
+ * the 16-bit operand scale is then derived without a pass over dY; d_gelu_t (optional, fp32 [M, N]): the projection is followed by the erf
+ * GELU and d_dY is the gradient with respect to the GELU's OUTPUT: gelu'(d_gelu_t) is applied in the pass that casts dY and sums its
+ * columns (no separate GELU-backward kernel, no fp32 copy of the pre-activation gradient); d_dX_amax (optional): receives max |dX| as
+ * float bits from the dgrad GEMM's epilogue */
 int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X_lp, int ldx, const void* d_W_lp, int ldw, int M, int N, int K,
-                                float* d_dX, int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, void* d_scratch,
-                                size_t scratch_bytes, int lp_kind, void* stream);
+                                float* d_dX, int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t,
+                                float* d_dX_amax, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream);
 /* unimm_k_layernorm_backward / unimm_k_gelu_backward that also leave max |dx| (float bits; zeroed first) in d_amax[0] */
 int unimm_k_layernorm_backward_amax(const float* d_dy, const float* d_x, int rows, int H, const float* d_gamma, float* d_dx, float* d_dgamma,
                                     float* d_dbeta, float* d_amax, void* stream);
@@ -372,12 +375,14 @@ int unimm_k_attention_lse(const void* d_q, int ldq, const void* d_k, int ldk, co
  * d_lse: d_dO fp32 contiguous [B*Sq, heads*D] -> d_dq [B*Sq, lddq], d_dk / d_dv [B*Skv, lddk / lddv] fp32 (head h at column h*D, so the
  * three can be the column blocks of one [rows, 3H] matrix).  P is recomputed tile by tile; no [B, heads, Sq, Skv] tensor, no atomics.
  * The masks are the forward's, regenerated from d_desc / d_key_mask.  d_amax_accum (optional): atomicMax of |dq|, |dk|, |dv| as float bits,
- * NOT zeroed by the call (the two co-attentions fill column blocks of the same two gradient matrices). */
+ * NOT zeroed by the call (the two co-attentions fill column blocks of the same two gradient matrices); d_dO_amax (optional): max |dO| as
+ * float bits when its producer left it on the device. */
 size_t unimm_k_attention_backward_scratch(int B, int heads, int D, int Sq);
 int unimm_k_attention_backward(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, const void* d_o, int ldo,
                                const float* d_dO, const float* d_lse, int B, int heads, int D, int Sq, int Skv, int mask_kind,
                                const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind, float* d_dq, int lddq, float* d_dk,
-                               int lddk, float* d_dv, int lddv, float* d_amax_accum, void* d_scratch, size_t scratch_bytes, void* stream);
+                               int lddk, float* d_dv, int lddv, float* d_amax_accum, const float* d_dO_amax, void* d_scratch, size_t scratch_bytes,
+                               void* stream);
 /* text embeddings without the LayerNorm (its input is what the backward needs): word + position + (type | type-extension)
  * (models/vilbert_dialog.py:334-352) -> d_out fp32 [rows, H]; and the scatter-add of that sum's gradient into the four tables
  * (accumulating: the word table's gradient also receives the tied decoder's). */

@@ -114,8 +114,10 @@ class TorchOps:
     def linear_f32(self, x, w, bias, residual=None, act=0):
         return self.linear(x, w, bias, residual, act)[0]
 
-    def linear_backward(self, dy, x, w, g_w, g_b, need_dx=True, dx_accum=None):
+    def linear_backward(self, dy, x, w, g_w, g_b, need_dx=True, dx_accum=None, gelu_t=None, dx_amax=False):
         assert tuple(g_w.shape) == (dy.shape[1], x.shape[1])
+        if gelu_t is not None:
+            dy = self.gelu_backward(dy.clone(), gelu_t)
         g_w.copy_(dy.t() @ x)
         if g_b is not None:
             g_b.copy_(dy.sum(0))

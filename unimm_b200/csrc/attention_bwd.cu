@@ -471,7 +471,7 @@ size_t attention_backward_scratch(int B, int heads, int D, int Sq) {
 }
 
 int attention_backward_lp(const AttnArgs& f, const float* dO, int lddo, const float* lse, float* dq, int lddq, float* dk, int lddk,
-                          float* dv, int lddv, void* scratch, size_t scratch_bytes, cudaStream_t stream, float* amax_accum) {
+                          float* dv, int lddv, void* scratch, size_t scratch_bytes, cudaStream_t stream, float* amax_accum, const float* dO_amax) {
     UNIMM_CHECK(f.B > 0 && f.B <= 65535 && f.heads > 0 && f.Sq > 0 && f.Skv > 0 && f.Sq <= 256 && f.Skv <= 256, "attention backward: bad problem size");
     UNIMM_CHECK(f.D == 64 || f.D == 128, "attention backward: head dim must be 64 or 128");
     UNIMM_CHECK((f.ldq % 8) == 0 && (f.ldk % 8) == 0 && (f.ldv % 8) == 0 && (f.ldo % 2) == 0, "attention backward: rows must be 16-byte aligned");
@@ -486,7 +486,7 @@ int attention_backward_lp(const AttnArgs& f, const float* dO, int lddo, const fl
     float* sc = reinterpret_cast<float*>(p);                                  // [0] = scale, [1] = 1 / scale
     bf16* dO16 = reinterpret_cast<bf16*>(p + 256);
     float* delta = reinterpret_cast<float*>(p + 256 + ((2 * rows * H + 255) & ~size_t(255)));
-    UNIMM_TRY(amax_scale(dO, rows * H, f.lp_kind == LP_FP16 ? 1 : 0, sc, stream));
+    UNIMM_TRY(amax_scale(dO, rows * H, f.lp_kind == LP_FP16 ? 1 : 0, sc, stream, dO_amax));
     UNIMM_TRY(cast_scaled_lp(dO, lddo, static_cast<int>(rows), H, sc, dO16, H, f.lp_kind, stream));
     {
         const size_t warps = rows * f.heads;

@@ -1624,12 +1624,13 @@ size_t unimm_k_linear_backward_scratch(int M, int N, int K) {
 
 int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
                             float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
-    return unimm_k_linear_backward_acc(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, 0, d_dW, d_db, nullptr, d_scratch, scratch_bytes, lp_kind, stream);
+    return unimm_k_linear_backward_acc(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, 0, d_dW, d_db, nullptr, nullptr, nullptr, d_scratch, scratch_bytes,
+                                       lp_kind, stream);
 }
 
 int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
-                                int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, void* d_scratch, size_t scratch_bytes, int lp_kind,
-                                void* stream) {
+                                int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t, float* d_dX_amax,
+                                void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
     UNIMM_CHECK(d_dY && d_X && d_W && d_scratch && M > 0 && N > 0 && K > 0, "bad argument");
     UNIMM_CHECK(N % 64 == 0 && K % 8 == 0 && ldy % 2 == 0, "linear backward: N must be a multiple of 64 (the dgrad contraction), K of 8");
     UNIMM_CHECK(scratch_bytes >= unimm_k_linear_backward_scratch(M, N, K), "scratch smaller than unimm_k_linear_backward_scratch()");
@@ -1645,8 +1646,11 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int
     UNIMM_CHECK(static_cast<size_t>(p - static_cast<char*>(d_scratch)) <= scratch_bytes, "scratch carve overflow");
     // the incoming gradient as a 16-bit operand: fp16 gets a power-of-two scale from its own maximum (gradients are routinely below
     // fp16's normal range), multiplied back out by the GEMM epilogues straight from device memory
-    UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st, d_amax));
-    UNIMM_TRY(cast_scaled_lp(d_dY, ldy, M, N, scale, dY16, N, lp_kind, st));
+    // ... and in the same pass over dY: the bias gradient (column sums) and, when dY still has to pass the erf GELU of this projection's
+    // output backwards (d_gelu_t = the saved pre-activation), that derivative (|gelu'| <= 1.13 bounds the scaled values)
+    UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st, d_amax, d_gelu_t != nullptr ? 1.13f : 1.f));
+    UNIMM_TRY(cast_colsum_lp(d_dY, ldy, d_gelu_t, N, M, N, scale, dY16, N, lp_kind, d_db, st));
+    d_db = nullptr;                                              // done
     static const bool transposed_copies = getenv("UNIMM_BWD_TRANSPOSE") != nullptr && atoi(getenv("UNIMM_BWD_TRANSPOSE")) != 0;
     if (!transposed_copies) {
         // No transposed copies: tcgen05 reads an operand whose contraction index is the ROW of the stored matrix as an MN-major tile
@@ -1655,6 +1659,10 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int
             GemmEpilogue ep;
             ep.lp_kind = lp_kind; ep.out_f32 = d_dX; ep.ldo_f32 = K; ep.alpha_ptr = scale + 1; ep.b_mn = true;
             if (accumulate_dx) { ep.residual = d_dX; ep.ldr = K; }   // dX += dY W: each element is read and rewritten by the same thread
+            if (d_dX_amax != nullptr) {                              // max |dX| for whoever turns dX into a 16-bit operand next
+                UNIMM_CUDA_CHECK(cudaMemsetAsync(d_dX_amax, 0, sizeof(float), st));
+                ep.amax_out = reinterpret_cast<unsigned*>(d_dX_amax);
+            }
             UNIMM_TRY(gemm_umma_bf16(dY16, N, static_cast<const bf16*>(d_W), ldw, M, K, N, ep, 0, 0, st));
         }
         // dW [N, K] = dY^T [N, M] . X [M, K]: both operands as stored (contraction = their rows, zero-filled beyond M by TMA).  The
@@ -1685,6 +1693,10 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int
         GemmEpilogue ep;
         ep.lp_kind = lp_kind; ep.out_f32 = d_dX; ep.ldo_f32 = K; ep.alpha_ptr = scale + 1;
         if (accumulate_dx) { ep.residual = d_dX; ep.ldr = K; }       // dX += dY W: each element is read and rewritten by the same thread
+        if (d_dX_amax != nullptr) {
+            UNIMM_CUDA_CHECK(cudaMemsetAsync(d_dX_amax, 0, sizeof(float), st));
+            ep.amax_out = reinterpret_cast<unsigned*>(d_dX_amax);
+        }
         UNIMM_TRY(gemm_umma_bf16(dY16, N, WT, N, M, K, N, ep, 0, 0, st));
     }
     if (d_dW != nullptr) {        // dW [N, K] = dY^T [N, M] · X [M, K]: contraction over the rows (zero-padded to a multiple of 64)

@@ -239,6 +239,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         };
         int acc = 0;
         uint32_t acc_phase = 0;
+        float out_amax = 0.f;                  // ep.amax_out: running max |out| of this thread's stores
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int mn = tile / splits;
             const int tn = mn % num_n;
@@ -525,6 +526,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int i = 0; i < 8; ++i) {
                         const int grow = r0 + 4 * i;
                         if (grow < M) {
+                            if (ep.amax_out != nullptr)
+                                out_amax = fmaxf(fmaxf(out_amax, fmaxf(fabsf(y[i].x), fabsf(y[i].y))), fmaxf(fabsf(y[i].z), fabsf(y[i].w)));
                             if (ep.out_f32 != nullptr && splits > 1) {
                                 float* o = ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc;
                                 atomicAdd(o, y[i].x); atomicAdd(o + 1, y[i].y); atomicAdd(o + 2, y[i].z); atomicAdd(o + 3, y[i].w);
@@ -576,6 +579,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) x[j] += r[j];
                 }
+                if (ep.amax_out != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) out_amax = fmaxf(out_amax, fabsf(x[j]));
+                }
                 if (ep.out_f32 != nullptr) {
                     float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
                     if (splits > 1) {
@@ -624,6 +632,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) arrive_tempty(&tempty_bar[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        }
+        if (ep.amax_out != nullptr) {
+            const unsigned u = __reduce_max_sync(0xffffffffu, __float_as_uint(out_amax));
+            if (lane == 0 && u != 0u) atomicMax(ep.amax_out, u);
         }
     }
     ptx::tc_fence_before();

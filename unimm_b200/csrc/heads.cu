@@ -111,8 +111,8 @@ __global__ void amax_kernel(const float* __restrict__ x, size_t n, unsigned* __r
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((threadIdx.x & 31) == 0) atomicMax(bits, mx);
 }
-__global__ void scale_from_amax_kernel(const unsigned* __restrict__ bits, int want_scale, float* __restrict__ out2) {
-    const float amax = __uint_as_float(*bits);
+__global__ void scale_from_amax_kernel(const unsigned* __restrict__ bits, int want_scale, float* __restrict__ out2, float headroom) {
+    const float amax = __uint_as_float(*bits) * headroom;
     float s = 1.f;
     if (want_scale && amax > 0.f && isfinite(amax)) {
         int e;
@@ -122,6 +122,58 @@ __global__ void scale_from_amax_kernel(const unsigned* __restrict__ bits, int wa
     out2[0] = s;
     out2[1] = 1.f / s;
 }
+__device__ __forceinline__ float gelu_grad_fast(float v) {
+    const float v2 = v * v;
+    float r = fmaf(v2, kGeluC4, kGeluC3);
+    r = fmaf(r, v2, kGeluC2);
+    r = fmaf(r, v2, kGeluC1);
+    r = fmaf(r, v2, kGeluC0);
+    const float cdf = fast_rcp(1.0f + fast_ex2(r * v));
+    return fmaf(v * 0.39894228040143267794f, fast_ex2(-0.72134752044448170368f * v2), cdf);
+}
+
+// One pass over a gradient matrix that is about to become a tensor-core operand: y = lp(v * scale) and colsum += v (the bias gradient),
+// where v = x, or v = x * gelu'(t) when the matrix still has to go back through the erf GELU (models/vilbert_dialog.py:115-121) —
+// the GELU backward, the cast and the bias gradient then read the fp32 gradient once and write 2 bytes per element instead of
+// three reads and an fp32 write.
+template <bool GELU>
+__global__ void __launch_bounds__(256)
+cast_colsum_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ t, int ldt, int rows, int cols, const float* __restrict__ scale,
+                   bf16* __restrict__ y, int ldy, int lp_kind, float* __restrict__ colsum) {
+    // CTA = 64 columns x 128 rows: a warp reads 256 contiguous bytes of one row (two columns per lane), the 8 warps interleave the rows
+    __shared__ float part[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 64 + lane * 2;
+    const float s = scale[0];
+    const int r0 = blockIdx.y * 128, r1 = min(rows, r0 + 128);
+    float a0 = 0.f, a1 = 0.f;
+    if (c < cols) {
+#pragma unroll 4
+        for (int r = r0 + warp; r < r1; r += 8) {
+            float2 v = *reinterpret_cast<const float2*>(x + static_cast<size_t>(r) * ldx + c);
+            if (GELU) {
+                // d/dt [t Phi(t)] = Phi(t) + t phi(t); Phi from the forward's rational fit (common.cuh gelu_fast: 3.5e-6), phi by one ex2
+                const float2 tv = *reinterpret_cast<const float2*>(t + static_cast<size_t>(r) * ldt + c);
+                v.x *= gelu_grad_fast(tv.x);
+                v.y *= gelu_grad_fast(tv.y);
+            }
+            a0 += v.x;
+            a1 += v.y;
+            *reinterpret_cast<uint32_t*>(y + static_cast<size_t>(r) * ldy + c) = pack_lp2(v.x * s, v.y * s, lp_kind);
+        }
+    }
+    if (colsum == nullptr) return;
+    part[warp][lane * 2] = a0;
+    part[warp][lane * 2 + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += part[w][threadIdx.x];
+        atomicAdd(colsum + blockIdx.x * 64 + threadIdx.x, sum);
+    }
+}
+
 __global__ void cast_scaled_kernel(const float* __restrict__ x, int ldx, int rows, int cols, const float* __restrict__ scale,
                                    bf16* __restrict__ y, int ldy, int lp_kind) {
     const float s = scale[0];
@@ -436,9 +488,9 @@ int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float al
     return 0;
 }
 
-int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax) {
+int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax, float headroom) {
     if (known_amax != nullptr) {      // the producer of x already left max |x| (as float bits) in device memory: no pass over x
-        scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const unsigned*>(known_amax), want_scale, out2);
+        scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const unsigned*>(known_amax), want_scale, out2, headroom);
         UNIMM_LAUNCH_CHECK(1);
         return 0;
     }
@@ -447,8 +499,19 @@ int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream
     int grid = static_cast<int>((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     amax_kernel<<<grid < 1 ? 1 : grid, 256, 0, stream>>>(x, n, reinterpret_cast<unsigned*>(out2 + 1));
-    scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const unsigned*>(out2 + 1), want_scale, out2);
+    scale_from_amax_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const unsigned*>(out2 + 1), want_scale, out2, headroom);
     UNIMM_LAUNCH_CHECK(2);
+    return 0;
+}
+
+int cast_colsum_lp(const float* x, int ldx, const float* gelu_t, int ldt, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind,
+                   float* colsum, cudaStream_t stream) {
+    UNIMM_CHECK(rows > 0 && cols % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && (gelu_t == nullptr || ldt % 2 == 0), "cast_colsum: even columns and leading dimensions");
+    if (colsum != nullptr) UNIMM_CUDA_CHECK(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, stream));
+    const dim3 grid((cols + 63) / 64, (rows + 127) / 128);
+    if (gelu_t != nullptr) cast_colsum_kernel<true><<<grid, 256, 0, stream>>>(x, ldx, gelu_t, ldt, rows, cols, scale, y, ldy, lp_kind, colsum);
+    else cast_colsum_kernel<false><<<grid, 256, 0, stream>>>(x, ldx, nullptr, 0, rows, cols, scale, y, ldy, lp_kind, colsum);
+    UNIMM_LAUNCH_CHECK(1);
     return 0;
 }
 

@@ -50,6 +50,9 @@ struct GemmEpilogue {
     // the value to accumulate onto; fp32 output only, no bias / activation / residual): fills the machine when the output is small
     // and the contraction long — every wgrad of the path (N x K <= 3072 x 3072 outputs over 61 440 rows)
     int split_k = 1;
+    // fp32-output paths: max |out| over the whole matrix, as float bits, by atomicMax (one per epilogue warp at the end of the kernel;
+    // the caller zeroes it) — the next consumer's 16-bit operand scale without a pass over the matrix
+    unsigned* amax_out = nullptr;
 };
 
 // C = A[M,K] · W[N,K]^T, bf16 operands, fp32 accumulation in TMEM (gemm_umma.cu).
@@ -213,7 +216,10 @@ int lm_loss_coef(const float* logp, const float* weight, int n, float scale, flo
 int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float alpha, float* out, cudaStream_t stream);
 // dgrad / wgrad helpers (unimm_k_linear_backward): out2[0] = 2^k with max|x| * 2^k in [2^9, 2^10) (1 when want_scale == 0 or x == 0),
 // out2[1] = 1 / out2[0];  y16 = lp(x * out2[0]);  colsum[j] = sum_i x[i, j]
-int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax = nullptr);
+int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax = nullptr, float headroom = 1.f);
+// y = lp(v * scale[0]), colsum (optional, zeroed here) += v, with v = x or x * gelu'(gelu_t) (heads.cu: cast_colsum_kernel)
+int cast_colsum_lp(const float* x, int ldx, const float* gelu_t, int ldt, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind,
+                   float* colsum, cudaStream_t stream);
 int cast_scaled_lp(const float* x, int ldx, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind, cudaStream_t stream);
 int column_sums_f32(const float* x, int ldx, int rows, int cols, float* out, cudaStream_t stream);
 // tcgen05 LM head tail: merge the per-tile (max, sum) partials

@@ -13,7 +13,7 @@ namespace unimm {
 
 size_t attention_backward_scratch(int B, int heads, int D, int Sq);
 int attention_backward_lp(const AttnArgs& f, const float* dO, int lddo, const float* lse, float* dq, int lddq, float* dk, int lddk,
-                          float* dv, int lddv, void* scratch, size_t scratch_bytes, cudaStream_t stream, float* amax_accum);
+                          float* dv, int lddv, void* scratch, size_t scratch_bytes, cudaStream_t stream, float* amax_accum, const float* dO_amax);
 
 namespace {
 
@@ -369,7 +369,8 @@ size_t unimm_k_attention_backward_scratch(int B, int heads, int D, int Sq) { ret
 int unimm_k_attention_backward(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, const void* d_o, int ldo,
                                const float* d_dO, const float* d_lse, int B, int heads, int D, int Sq, int Skv, int mask_kind,
                                const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind, float* d_dq, int lddq, float* d_dk,
-                               int lddk, float* d_dv, int lddv, float* d_amax_accum, void* d_scratch, size_t scratch_bytes, void* stream) {
+                               int lddk, float* d_dv, int lddv, float* d_amax_accum, const float* d_dO_amax, void* d_scratch, size_t scratch_bytes,
+                               void* stream) {
     UNIMM_CHECK(lp_kind == LP_BF16 || lp_kind == LP_FP16, "attention backward: 16-bit tensors only");
     AttnArgs a;
     a.q = d_q; a.ldq = ldq; a.k = d_k; a.ldk = ldk; a.v = d_v; a.ldv = ldv; a.o = const_cast<void*>(d_o); a.ldo = ldo;
@@ -377,7 +378,7 @@ int unimm_k_attention_backward(const void* d_q, int ldq, const void* d_k, int ld
     a.desc = reinterpret_cast<const SeqDesc*>(d_desc); a.key_mask = d_key_mask;
     a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind;
     return attention_backward_lp(a, d_dO, heads * D, d_lse, d_dq, lddq, d_dk, lddk, d_dv, lddv, d_scratch, scratch_bytes,
-                                 static_cast<cudaStream_t>(stream), d_amax_accum);
+                                 static_cast<cudaStream_t>(stream), d_amax_accum, d_dO_amax);
 }
 
 int unimm_k_layernorm_backward_amax(const float* d_dy, const float* d_x, int rows, int H, const float* d_gamma, float* d_dx, float* d_dgamma,

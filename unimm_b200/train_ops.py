@@ -153,9 +153,11 @@ class DeviceOps:
                                    act, ptr(y), N, self.stream))
         return y
 
-    def linear_backward(self, dy32, x16, w16, g_w, g_b, need_dx=True, dx_accum=None):
+    def linear_backward(self, dy32, x16, w16, g_w, g_b, need_dx=True, dx_accum=None, gelu_t=None, dx_amax=False):
         """dgrad / wgrad / bias gradient of y = x W^T + b.  ``g_w`` [N, K] / ``g_b`` [N] receive the parameter gradients; returns dX
-        (``dx_accum`` += dY W when given)."""
+        (``dx_accum`` += dY W when given).  ``gelu_t``: the projection feeds the erf GELU and ``dy32`` is the gradient with respect to
+        the GELU's output — the derivative at the saved pre-activation ``gelu_t`` is applied on the fly.  ``dx_amax``: the dgrad GEMM
+        leaves max |dX| on the device for the next consumer of dX (``register_amax``)."""
         M, N = dy32.shape
         K = x16.shape[1]
         assert dy32.is_contiguous() and g_w.is_contiguous() and tuple(g_w.shape) == (N, K)
@@ -168,8 +170,11 @@ class DeviceOps:
         cell, n = self._amax.pop(dy32.data_ptr(), (None, 0))
         if cell is not None and n != dy32.numel():
             cell = None
+        out_cell = self.empty32(1) if (dx_amax and need_dx) else None
         check(lib.unimm_k_linear_backward_acc(ptr(dy32), N, ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(dx), 1 if dx_accum is not None else 0,
-                                              ptr(g_w), ptr(g_b), ptr(cell), ptr(sc), nbytes, self.kind, self.stream))
+                                              ptr(g_w), ptr(g_b), ptr(cell), ptr(gelu_t), ptr(out_cell), ptr(sc), nbytes, self.kind, self.stream))
+        if out_cell is not None:
+            self.register_amax(dx, out_cell)
         return dx
 
     # ------------------------------------------------------------------ attention
@@ -187,9 +192,12 @@ class DeviceOps:
         assert dO32.is_contiguous()
         nbytes = lib.unimm_k_attention_backward_scratch(B, heads, D, Sq)
         sc = self.scratch(nbytes)
+        known, n = self._amax.pop(dO32.data_ptr(), (None, 0))
+        if known is not None and n != dO32.numel():
+            known = None
         check(lib.unimm_k_attention_backward(ptr(q16), _ld(q16), ptr(k16), _ld(k16), ptr(v16), _ld(v16), ptr(o16), _ld(o16), ptr(dO32), ptr(lse), B,
                                              heads, D, Sq, Skv, mask_kind, ptr(desc), ptr(key_mask), self.kind, ptr(dq), _ld(dq), ptr(dk), _ld(dk),
-                                             ptr(dv), _ld(dv), ptr(amax_cell), ptr(sc), nbytes, self.stream))
+                                             ptr(dv), _ld(dv), ptr(amax_cell), ptr(known), ptr(sc), nbytes, self.stream))
 
     # ------------------------------------------------------------------ heads / losses
     def lm_head_loss_backward(self, h16, e16, bias, labels_i32, weight32, grad_scale, g_e, g_bias):

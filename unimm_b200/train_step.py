@@ -249,11 +249,12 @@ class TrainStep:
     def _ffn_bwd(self, dy, p_int, p_out, sv):
         ops, P = self.ops, self.params
         d_pre = ops.layernorm_backward(dy, sv["ffn_pre"], P.P(p_out + ".LayerNorm.weight"), P.G(p_out + ".LayerNorm.weight"), P.G(p_out + ".LayerNorm.bias"))
-        dg = ops.linear_backward(d_pre, sv["ffn_g16"], P.P16(p_out + ".dense.weight"), P.G(p_out + ".dense.weight"), P.G(p_out + ".dense.bias"))
-        dt = ops.gelu_backward(dg, sv["ffn_t"])
-        # the residual branch's gradient is d_pre itself: accumulate the FFN branch onto it
-        return ops.linear_backward(dt, sv["ffn_x16"], P.P16(p_int + ".dense.weight"), P.G(p_int + ".dense.weight"), P.G(p_int + ".dense.bias"),
-                                   dx_accum=d_pre)
+        dg = ops.linear_backward(d_pre, sv["ffn_g16"], P.P16(p_out + ".dense.weight"), P.G(p_out + ".dense.weight"), P.G(p_out + ".dense.bias"),
+                                 dx_amax=True)
+        # GELU' is applied inside the pass that turns dg into the 16-bit operand of the next two GEMMs.  The residual branch's gradient
+        # is d_pre itself: the FFN branch is accumulated onto it.
+        return ops.linear_backward(dg, sv["ffn_x16"], P.P16(p_int + ".dense.weight"), P.G(p_int + ".dense.weight"), P.G(p_int + ".dense.bias"),
+                                   dx_accum=d_pre, gelu_t=sv["ffn_t"])
 
     def _self_layer_fwd(self, p, x32, x16, B, S, heads, mask_kind, desc, key_mask, sv):
         """BertLayer / BertImageLayer (:479-483, :608-612)."""
@@ -277,7 +278,8 @@ class TrainStep:
         dy1 = self._ffn_bwd(dy, p + "intermediate", p + "output", sv)
         d_pre1 = ops.layernorm_backward(dy1, sv["pre1"], P.P(a + "output.LayerNorm.weight"), P.G(a + "output.LayerNorm.weight"),
                                         P.G(a + "output.LayerNorm.bias"))
-        dctx = ops.linear_backward(d_pre1, sv["ctx16"], P.P16(a + "output.dense.weight"), P.G(a + "output.dense.weight"), P.G(a + "output.dense.bias"))
+        dctx = ops.linear_backward(d_pre1, sv["ctx16"], P.P16(a + "output.dense.weight"), P.G(a + "output.dense.weight"), P.G(a + "output.dense.bias"),
+                                   dx_amax=True)
         qkv16 = sv["qkv16"]
         dqkv, cell = ops.empty32(qkv16.shape[0], 3 * H), ops.new_amax_cell()
         ops.attention_backward(qkv16[:, :H], qkv16[:, H:2 * H], qkv16[:, 2 * H:], sv["ctx16"], sv["lse"], dctx, B, heads, D, S, S, mask_kind, desc,
@@ -322,10 +324,10 @@ class TrainStep:
         if dyv is not None:
             dav = self._ffn_bwd(dyv, p + "v_intermediate", p + "v_output", sv["v"])
             dxv = ops.layernorm_backward(dav, sv["pre_v"], P.P(o + "LayerNorm1.weight"), P.G(o + "LayerNorm1.weight"), P.G(o + "LayerNorm1.bias"))
-            dctx_v = ops.linear_backward(dxv, sv["ctx_v"], P.P16(o + "dense1.weight"), P.G(o + "dense1.weight"), P.G(o + "dense1.bias"))
+            dctx_v = ops.linear_backward(dxv, sv["ctx_v"], P.P16(o + "dense1.weight"), P.G(o + "dense1.weight"), P.G(o + "dense1.bias"), dx_amax=True)
         dat = self._ffn_bwd(dyt, p + "t_intermediate", p + "t_output", sv["t"])
         dxt = ops.layernorm_backward(dat, sv["pre_t"], P.P(o + "LayerNorm2.weight"), P.G(o + "LayerNorm2.weight"), P.G(o + "LayerNorm2.bias"))
-        dctx_t = ops.linear_backward(dxt, sv["ctx_t"], P.P16(o + "dense2.weight"), P.G(o + "dense2.weight"), P.G(o + "dense2.bias"))
+        dctx_t = ops.linear_backward(dxt, sv["ctx_t"], P.P16(o + "dense2.weight"), P.G(o + "dense2.weight"), P.G(o + "dense2.bias"), dx_amax=True)
         qkv1, qkv2 = sv["qkv1"], sv["qkv2"]
         dqkv1, dqkv2 = ops.empty32(qkv1.shape[0], 3 * Hb), ops.empty32(qkv2.shape[0], 3 * Hb)
         cell = ops.new_amax_cell()         # one bound for both matrices: each of the two attentions fills column blocks of both
