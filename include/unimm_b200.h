@@ -283,6 +283,8 @@ void unimm_reset_launch_count(void);
 
 /* ---- single-kernel entry points (used by tests/ to check each kernel against the oracle) ----
  * unimm_k_lm_head_lp scratch: d_partials_scratch holds rows * 2*ceil(V/256) float2, d_label_logit_scratch rows floats. */
+/* unimm_k_gemm_lp: act = 0 none, 1 GELU, 2 ReLU; act | 0x100: d_out_f32 receives the PRE-activation (acc + bias) and d_out_lp the activation
+ * — the training forward keeps the GELU's input for the backward and feeds the next GEMM from one epilogue. */
 int unimm_k_gemm_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias,
                     const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp,
                     int tile_n, int max_ctas, int lp_kind, void* stream);

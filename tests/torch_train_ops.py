@@ -101,8 +101,10 @@ class TorchOps:
         dy.copy_(d)
         return dy
 
-    def linear(self, x, w, bias, residual=None, act=0, want32=True, want16=False):
+    def linear(self, x, w, bias, residual=None, act=0, want32=True, want16=False, pre_act32=False):
         y = x @ w.t() + bias
+        if pre_act32:
+            return y, (_gelu(y) if act == ACT_GELU else torch.relu(y))
         if act == ACT_GELU:
             y = _gelu(y)
         elif act == ACT_RELU:

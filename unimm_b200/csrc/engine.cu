@@ -1502,6 +1502,8 @@ int unimm_k_gemm_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, i
     ep.lp_kind = lp_kind;
     ep.debug_mode = tile_n / 1000;   // microbenchmark hook (scripts/gemm_bench.py): tile_n = 1000*mode + tile
     tile_n %= 1000;
+    ep.pre_act_f32 = (act & 0x100) != 0;      // act | 0x100: d_out_f32 receives the pre-activation, d_out_lp the activation (training forward)
+    act &= 0xff;
     ep.bias = d_bias; ep.residual = d_residual; ep.ldr = ldr; ep.act = act;
     ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32; ep.out_bf16 = static_cast<bf16*>(d_out_lp); ep.ldo_bf16 = ldo_lp;
     return gemm_umma_bf16(static_cast<const bf16*>(d_A), lda, static_cast<const bf16*>(d_W), ldw, M, N, K, ep, tile_n, max_ctas,

@@ -502,6 +502,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { y[i].x += b4.x; y[i].y += b4.y; y[i].z += b4.z; y[i].w += b4.w; }
+                    if (ep.pre_act_f32) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int grow = r0 + 4 * i;
+                            if (grow < M) *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc) = y[i];
+                        }
+                    }
                     if (ep.act == ACT_GELU) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -531,7 +538,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (ep.out_f32 != nullptr && splits > 1) {
                                 float* o = ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc;
                                 atomicAdd(o, y[i].x); atomicAdd(o + 1, y[i].y); atomicAdd(o + 2, y[i].z); atomicAdd(o + 3, y[i].w);
-                            } else if (ep.out_f32 != nullptr)
+                            } else if (ep.out_f32 != nullptr && !ep.pre_act_f32)
                                 *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(grow) * ep.ldo_f32 + cc) = y[i];
                             if (ep.out_bf16 != nullptr && ep.out_hilo) {
                                 uint2 hi, lo;
@@ -562,6 +569,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) x[j] += __ldg(ep.bias + col0 + j);
                 }
+                if (ep.pre_act_f32 && row_ok) {
+                    float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) o[j] = x[j];
+                }
                 if (ep.act == ACT_GELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
@@ -584,7 +597,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) out_amax = fmaxf(out_amax, fabsf(x[j]));
                 }
-                if (ep.out_f32 != nullptr) {
+                if (ep.out_f32 != nullptr && !ep.pre_act_f32) {
                     float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
                     if (splits > 1) {
 #pragma unroll
@@ -792,6 +805,9 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
                    int max_ctas, cudaStream_t stream) {
     UNIMM_CHECK(M > 0 && N > 0 && K > 0 && (K % BK == 0 || (ep.a_mn && ep.b_mn)), "umma gemm: K must be a positive multiple of 64");
     const bool lse = ep.partials != nullptr || ep.dz != nullptr;
+    UNIMM_CHECK(!ep.pre_act_f32 || (ep.out_f32 != nullptr && ep.out_bf16 != nullptr && ep.residual == nullptr && !lse && !ep.w_perm16 &&
+                                    !ep.out_hilo && ep.split_k <= 1 && ep.amax_out == nullptr),
+                "pre-activation output: fp32 pre-activation + 16-bit activation, plain epilogue, no residual");
     if (ep.a_mn || ep.b_mn || ep.split_k > 1) {
         UNIMM_CHECK(!lse && !ep.split3 && !ep.w_perm16 && ep.debug_mode == 0, "MN-major operands / split-K: plain epilogue only");
         UNIMM_CHECK(!ep.a_mn || ((lda & 7) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0), "MN-major A: 16-byte aligned rows");

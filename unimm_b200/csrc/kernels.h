@@ -53,6 +53,9 @@ struct GemmEpilogue {
     // fp32-output paths: max |out| over the whole matrix, as float bits, by atomicMax (one per epilogue warp at the end of the kernel;
     // the caller zeroes it) — the next consumer's 16-bit operand scale without a pass over the matrix
     unsigned* amax_out = nullptr;
+    // out_f32 receives the value BEFORE the activation (acc + bias) while out_bf16 receives act(acc + bias): the training forward keeps
+    // the GELU's pre-activation for the backward and feeds the next GEMM in one epilogue (no residual in this mode)
+    bool pre_act_f32 = false;
 };
 
 // C = A[M,K] · W[N,K]^T, bf16 operands, fp32 accumulation in TMEM (gemm_umma.cu).

@@ -134,8 +134,12 @@ class DeviceOps:
         return dy
 
     # ------------------------------------------------------------------ projections
-    def linear(self, x16, w16, bias, residual=None, act=ACT_NONE, want32=True, want16=False):
-        """y = act(x W^T + b) (+ residual) on tcgen05 -> (y32 | None, y16 | None)."""
+    def linear(self, x16, w16, bias, residual=None, act=ACT_NONE, want32=True, want16=False, pre_act32=False):
+        """y = act(x W^T + b) (+ residual) on tcgen05 -> (y32 | None, y16 | None); ``pre_act32``: y32 = x W^T + b (the activation's input, kept
+        for the backward) while y16 = act(...)."""
+        if pre_act32:
+            assert want32 and want16 and residual is None
+            act = act | 0x100
         M, K = x16.shape
         N = w16.shape[0]
         y32 = self.empty32(M, N) if want32 else None

@@ -33,7 +33,7 @@ import numpy as np
 import torch
 
 from .config import ViLBertConfig
-from .train_ops import ACT_NONE, ACT_RELU, EW_ADD, MASK_CO_INTERVAL, MASK_KEY_VECTOR, MASK_TEXT_SELF
+from .train_ops import ACT_GELU, ACT_NONE, ACT_RELU, EW_ADD, MASK_CO_INTERVAL, MASK_KEY_VECTOR, MASK_TEXT_SELF
 from .weights import param_shapes
 
 NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")            # train.py:323 (substring match, so LayerNorm1/2.weight DO decay)
@@ -239,8 +239,8 @@ class TrainStep:
     def _ffn_fwd(self, x32, x16, p_int, p_out, sv):
         """intermediate.dense -> erf-GELU -> output.dense (+ x) -> LayerNorm  (models/vilbert_dialog.py:452-469)."""
         ops, P = self.ops, self.params
-        t, _ = ops.linear(x16, P.P16(p_int + ".dense.weight"), P.P(p_int + ".dense.bias"))
-        _, g16 = ops.gelu(t)
+        # one epilogue: the pre-activation in fp32 (kept for the backward) and GELU of it as the 16-bit operand of the next GEMM
+        t, g16 = ops.linear(x16, P.P16(p_int + ".dense.weight"), P.P(p_int + ".dense.bias"), act=ACT_GELU, want16=True, pre_act32=True)
         pre, _ = ops.linear(g16, P.P16(p_out + ".dense.weight"), P.P(p_out + ".dense.bias"), residual=x32)
         y32, y16 = ops.layernorm(pre, P.P(p_out + ".LayerNorm.weight"), P.P(p_out + ".LayerNorm.bias"))
         sv.update(ffn_x16=x16, ffn_t=t, ffn_g16=g16, ffn_pre=pre)
