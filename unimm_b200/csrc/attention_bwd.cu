@@ -458,7 +458,9 @@ int run_bwd(const BwdArgs& a, cudaStream_t stream) {
     // 128 rows per CTA when there are that many, 64 for the 37-region side
     if (a.Sq > 64) UNIMM_TRY((launch_dq<D, FP16, 8>(a, stream)));
     else UNIMM_TRY((launch_dq<D, FP16, 4>(a, stream)));
-    if (a.Skv > 64) UNIMM_TRY((launch_dkv<D, FP16, 8>(a, stream)));
+    // UNIMM_DKV_NW4=1 (A/B switch): 64 key rows per CTA everywhere -> two 4-warp CTAs per SM whose staging and compute phases overlap
+    static const bool nw4 = getenv("UNIMM_DKV_NW4") != nullptr && atoi(getenv("UNIMM_DKV_NW4")) != 0;
+    if (a.Skv > 64 && !nw4) UNIMM_TRY((launch_dkv<D, FP16, 8>(a, stream)));
     else UNIMM_TRY((launch_dkv<D, FP16, 4>(a, stream)));
     return 0;
 }
