@@ -136,3 +136,72 @@ def test_val_lm_evaluate_loop_same_metrics_as_the_reference_model(full_cfg):
     assert set(m_ref) == set(m_ours)
     for k in m_ref:
         assert float(m_ref[k]) == pytest.approx(float(m_ours[k]), abs=1e-9), k
+
+
+def test_reference_training_loop_body_trains_through_the_drop_in(full_cfg):
+    """train.py:445-463 with the reference's own pieces — ``train.forward`` (unmodified), ``GradScaler``, ``scaler.scale(loss).backward()``,
+    ``scaler.step(optimizer)`` — over the drop-in after ``enable_training()``: the gradients autograd hands the module's parameters are the
+    device backward's and match what the UNMODIFIED reference model got from the same ``loss.backward()`` (tests/golden/train6_grads.npz);
+    a torch optimizer built from ``named_parameters()`` then updates the device masters in place and the next forward sees them."""
+    import os
+    g, b = load_golden("train6_perturbed")
+    n = b["tokens"].shape[0]
+    enc = ours(full_cfg, g).enable_training("fp16")
+    assert [k for k, _ in enc.named_parameters()] == ["bert_pretrained." + k for k in golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+                                                      if k != "cls.predictions.decoder.weight"]
+    extra = {"next_sentence_labels": torch.from_numpy(g["next_sentence_label"]).unsqueeze(0),
+             "image_target": torch.from_numpy(g["image_target"]).unsqueeze(0).expand(n, -1, -1).unsqueeze(0),
+             "image_label": torch.from_numpy(g["image_label"]).unsqueeze(0).expand(n, -1).unsqueeze(0)}
+    params = {"device": torch.device("cuda"), "nsp_weight": torch.from_numpy(g["nsp_weight"]), "lm_loss_coeff": 1.0, "nsp_loss_coeff": 1.0,
+              "img_loss_coeff": 1.0}
+    optimizer = torch.optim.AdamW([p for p in enc.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01)
+    scaler = torch.cuda.amp.GradScaler()
+    loss, lm_loss, nsp_loss, img_loss = REF["train"].forward(enc, loader_batch(b, extra), params, sample_size=None)
+    assert loss.requires_grad
+    assert abs(lm_loss - g["lm_loss"].item()) < 2e-2 and abs(nsp_loss - g["nsp_loss"].item()) < 2e-2 and abs(img_loss - g["img_loss"].item()) < 2e-2
+    scaler.scale(loss).backward()
+    scale = scaler.get_scale()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train6_grads.npz"))
+    named = dict(enc.named_parameters())
+    gmax, worst, seen = float(z["grad_norm"].max()), 0.0, 0
+    for name, norm, none in zip(z["names"], z["grad_norm"], z["grad_none"]):
+        name = str(name)
+        if name == "cls.predictions.decoder.weight":
+            continue
+        p = named["bert_pretrained." + name]
+        if none:
+            assert p.grad is None, name
+            continue
+        seen += 1
+        worst = max(worst, abs(float(p.grad.double().norm()) / scale - norm) / max(norm, 1e-3 * gmax))
+    print(f"reference loop over the drop-in: {seen} parameter gradients, L2 norms vs the reference model's own: worst relative difference {worst:.3e}")
+    assert seen > 500 and worst < 5e-2
+    before = named["bert_pretrained.bert.encoder.layer.3.output.dense.weight"].detach().clone()
+    scaler.step(optimizer)
+    scaler.update()
+    optimizer.zero_grad()
+    assert not torch.equal(before, named["bert_pretrained.bert.encoder.layer.3.output.dense.weight"].detach())
+    loss2, *_ = REF["train"].forward(enc, loader_batch(b, extra), params, sample_size=None)
+    print(f"loss {loss.item():.5f} -> {loss2.item():.5f} after one torch.optim.AdamW step through the reference's loop body")
+    assert loss2.item() < loss.item()
+    # the NSP scores are a differentiable output too (dense_annotation_finetuning.py:262-293 builds its losses on them in torch)
+    out = enc(b["tokens"], b["image_feat"], b["image_loc"], sep_indices=b["sep_indices"], token_type_ids=b["segments"],
+              token_position_ids=b["positions"], masked_lm_labels=b["mask"], attention_mask=b["txt_attention_mask"],
+              next_sentence_label=torch.from_numpy(g["next_sentence_label"]).cuda(), output_nsp_scores=True,
+              image_attention_mask=b["image_mask"], co_attention_mask=b["co_attention_mask"],
+              image_label=torch.from_numpy(g["image_label"]).unsqueeze(0).expand(n, -1), image_target=torch.from_numpy(g["image_target"]).unsqueeze(0).expand(n, -1, -1),
+              nsp_weight=None, lm_weight=b["weights"])
+    scores = out[3]
+    y = torch.from_numpy(g["next_sentence_label"]).cuda()
+    torch.nn.functional.cross_entropy(scores, y).backward()
+    want = (torch.softmax(scores.detach(), -1) - torch.nn.functional.one_hot(y, 2)).sum(0) / n
+    got = named["bert_pretrained.cls.bi_seq_relationship.bias"].grad
+    assert (got - want).abs().max().item() < 1e-5
+    assert named["bert_pretrained.cls.imagePredictions.decoder.weight"].grad is None        # that loss was not part of this backward
+    # inference through the same module afterwards uses the UPDATED weights
+    enc.eval()
+    with torch.no_grad():
+        o = enc(b["tokens"], b["image_feat"], b["image_loc"], token_type_ids=b["segments"], token_position_ids=b["positions"],
+                masked_lm_labels=b["mask"], attention_mask=b["txt_attention_mask"], image_attention_mask=b["image_mask"],
+                co_attention_mask=b["co_attention_mask"], output_nsp_scores=True)
+    assert (o[3].cpu() - scores.detach().cpu()).abs().max().item() < 2e-2

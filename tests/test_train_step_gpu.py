@@ -256,3 +256,31 @@ def test_dense_annotation_training_step_at_size(full_cfg, name):
     second = ts.step(batch)
     print(f"[fp16] {name}: total loss after one step at lr 5e-5: {second['loss']:.6f}")
     assert second["loss"] < vals["loss"]
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_config3_training_step_at_size(full_cfg, precision):
+    """BASELINE config 3 at its stated size as a whole TRAINING step (train.py:53-92, :445-463): 240 sequences = 40 images x (1 positive +
+    5 negatives) from the reference's own encoders, one feature / target block per image (``seq_image``): the three losses against the
+    reference's values, then backward + AdamW — every updated parameter finite, the loss on the same batch lower after the step."""
+    from conftest import load_golden_multi_image
+    from unimm_b200.descriptors import descriptors_from_masks
+    from unimm_b200.train_step import TrainStep
+    g, b, im = load_golden_multi_image("train240_perturbed")
+    sd = golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
+    batch = {"tokens": b["tokens"], "segments": b["segments"], "positions": b["positions"], "labels": b["mask"], "weights": b["weights"],
+             "desc": descriptors_from_masks(b["txt_attention_mask"], b["co_attention_mask"]), "seq_image": b["seq_image"],
+             "next_sentence_label": torch.from_numpy(g["next_sentence_label"]), "nsp_weight": torch.from_numpy(g["nsp_weight"]), **im}
+    ts = TrainStep(full_cfg, sd, DeviceOps(DEV, precision), lr=1e-4, image_lr=1e-4, warmup_steps=0)
+    vals = ts.step(batch)
+    print(f"[{precision}] config 3 training step, B = 240: lm {vals['lm_loss']:.6f}/{g['lm_loss'].item():.6f} img {vals['img_loss']:.6f}/"
+          f"{g['img_loss'].item():.6f} nsp {vals['nsp_loss']:.6f}/{g['nsp_loss'].item():.6f}")
+    tol = 2e-2 if precision == "fp16" else 3e-2
+    assert abs(vals["lm_loss"] - g["lm_loss"].item()) < tol and abs(vals["img_loss"] - g["img_loss"].item()) < tol
+    assert abs(vals["nsp_loss"] - g["nsp_loss"].item()) < tol
+    gn = ts.params.g[:ts.params.group_range[3][1]]
+    assert torch.isfinite(gn).all() and float(gn.abs().max()) > 0
+    again = ts.step(batch)
+    print(f"[{precision}] loss {vals['loss']:.5f} -> {again['loss']:.5f} after one AdamW step at lr 1e-4")
+    assert again["loss"] < vals["loss"]
+    assert all(torch.isfinite(v).all() for v in ts.state_dict().values())

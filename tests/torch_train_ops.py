@@ -44,6 +44,9 @@ class TorchOps:
     def to_lp(self, x):
         return x.clone()
 
+    def cast_into(self, x, out16):
+        out16.copy_(x)
+
     def ew(self, op, a, b=None, out=None, alpha=1.0):
         out = a if out is None else out
         r = {EW_ADD: lambda: a + b, EW_MUL: lambda: a * b, EW_RELU_BWD: lambda: a * (b > 0), EW_SCALE: lambda: alpha * a,

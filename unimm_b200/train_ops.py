@@ -72,6 +72,10 @@ class DeviceOps:
         check(lib.unimm_k_cast_lp(ptr(x32), ptr(out), x32.numel(), self.kind, self.stream))
         return out
 
+    def cast_into(self, x32, out16):
+        assert x32.is_contiguous() and out16.is_contiguous() and x32.numel() == out16.numel()
+        check(lib.unimm_k_cast_lp(ptr(x32), ptr(out16), x32.numel(), self.kind, self.stream))
+
     def ew(self, op, a, b=None, out=None, alpha=1.0):
         out = a if out is None else out
         assert a.is_contiguous() and out.is_contiguous() and (b is None or b.is_contiguous())

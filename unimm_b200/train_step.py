@@ -33,7 +33,7 @@ import numpy as np
 import torch
 
 from .config import ViLBertConfig
-from .train_ops import ACT_GELU, ACT_NONE, ACT_RELU, EW_ADD, MASK_CO_INTERVAL, MASK_KEY_VECTOR, MASK_TEXT_SELF
+from .train_ops import ACT_GELU, ACT_NONE, ACT_RELU, EW_ADD, EW_SCALE, MASK_CO_INTERVAL, MASK_KEY_VECTOR, MASK_TEXT_SELF
 from .weights import param_shapes
 
 NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")            # train.py:323 (substring match, so LayerNorm1/2.weight DO decay)
@@ -137,7 +137,10 @@ class ParamStore:
         self.refresh_lp()
 
     def refresh_lp(self):
-        self.p16.copy_(self.ops.to_lp(self.p))
+        """The 16-bit operand copies of every parameter from the fp32 masters (after a load, or after an optimizer that is not
+        ``unimm_t_adamw`` updated the masters in place)."""
+        n4 = self.total // 4 * 4
+        self.ops.cast_into(self.p[:n4], self.p16[:n4])
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         out = OrderedDict()
@@ -192,7 +195,7 @@ class TrainStep:
         up = lambda x, dt: t(x).to(dt).contiguous().to(dev, non_blocking=True)                          # noqa: E731
         tokens = t(batch["tokens"])
         B, S = tokens.shape
-        labels, weights = t(batch["labels"]).long(), t(batch["weights"]).long()
+        labels, weights = t(batch["labels"]).long().cpu(), t(batch["weights"]).long().cpu()     # host side: they size the LM-head buffers
         R = t(batch["image_mask"]).shape[-1]
         seq_image = batch.get("seq_image")
         n_img = t(batch["image_feat"]).shape[0]
@@ -200,7 +203,7 @@ class TrainStep:
             seq_image_np = np.arange(B, dtype=np.int64)
             assert n_img == B
         else:
-            seq_image_np = np.asarray(t(seq_image)).astype(np.int64)
+            seq_image_np = np.asarray(t(seq_image).cpu()).astype(np.int64)
         d = {"B": B, "S": S, "R": R}
         d["ids"], d["seg"], d["pos"] = up(tokens, torch.int64), up(batch["segments"], torch.int64), up(batch["positions"], torch.int64)
         d["desc"] = up(batch["desc"], torch.int32)
@@ -219,11 +222,12 @@ class TrainStep:
         d["img_row_of"] = up(row_of, torch.int32)
         d["feat"] = up(t(batch["image_feat"]).reshape(n_img * R, -1), fdt)
         loc = t(batch["image_loc"]).float().reshape(n_img * R, -1)
-        loc64 = torch.zeros(B * R, 64)
-        loc64[:, :loc.shape[1]] = loc[torch.from_numpy(row_of).long()]
+        loc64 = torch.zeros(B * R, 64, device=loc.device)
+        loc64[:, :loc.shape[1]] = loc[torch.from_numpy(row_of).long().to(loc.device)]
         d["loc64"] = up(loc64, fdt)
-        d["img_mask"] = up(t(batch["image_mask"]).float()[torch.from_numpy(seq_image_np)], fdt)
-        d["img_label"] = up(t(batch["image_label"]).long()[torch.from_numpy(seq_image_np)].reshape(-1), torch.int64)
+        pick = lambda x: x[torch.from_numpy(seq_image_np).to(x.device)]                                 # noqa: E731
+        d["img_mask"] = up(pick(t(batch["image_mask"]).float()), fdt)
+        d["img_label"] = up(pick(t(batch["image_label"]).long()).reshape(-1), torch.int64)
         d["img_target"] = up(t(batch["image_target"]).reshape(n_img * R, -1), fdt)
         d["nsl"] = up(batch["next_sentence_label"], torch.int64)
         nw = batch.get("nsp_weight")
@@ -347,12 +351,15 @@ class TrainStep:
         return dxv, dxt
 
     # ------------------------------------------------------------------ the step
-    def forward_backward(self, batch=None, inp=None, read_losses: bool = True) -> Dict[str, float]:
-        """Forward, the three losses, backward: the gradients of ``lm_coeff lm + nsp_coeff nsp + img_coeff img`` land in ``params.g``.
-        ``inp``: inputs already on the device (``upload``); ``read_losses=False`` returns device tensors instead of floats."""
+    def forward(self, batch=None, inp=None, image_head: Optional[bool] = None) -> dict:
+        """The forward of the step: embeddings, encoder (activations saved), the three heads and their loss VALUES, plus the gradients of
+        each loss with respect to its head's output at unit coefficient (the fused loss kernels produce them in the same pass).  Returns
+        the state ``backward`` consumes; ``state["out"]`` holds the losses as one-element device tensors."""
         ops, P, cfg = self.ops, self.params, self.cfg
         if inp is None:
             inp = self.upload(batch)
+        if image_head is None:
+            image_head = self.coeff[2] != 0
         ops.begin_step()
         B, S, R = inp["B"], inp["S"], inp["R"]
         P.g.zero_()
@@ -382,10 +389,10 @@ class TrainStep:
             else:
                 xv32, xv16, xt32, xt16 = self._conn_layer_fwd(f"bert.encoder.c_layer.{i}.", xv32, xv16, xt32, xt16, inp, sv)
             saved.append(sv)
-        lm_c, nsp_c, img_c = (c / self.batch_multiply for c in self.coeff)
-        d_xt, d_xv = ops.zeros32(B * S, cfg.hidden_size), ops.zeros32(B * R, cfg.v_hidden_size)
+        st = {"inp": inp, "saved": saved, "e_sum": e_sum, "v_sum": v_sum, "feat16": feat16, "loc16": loc16, "xv16": xv16}
         out = {}
-        # ---- masked-LM head + likelihood / unlikelihood loss (:982-986, :1023-1026, :1577-1595), labelled rows only
+        # ---- masked-LM head + likelihood / unlikelihood loss (:982-986, :1023-1026, :1577-1595), labelled rows only.  The fused vocabulary
+        # kernel is forward AND backward of the decoder + loss in one: it runs here with the loss's own normalisation (1 / #weighted tokens)
         if inp["n_lm"] > 0:
             t_ = "cls.predictions.transform."
             x_lm = ops.gather_rows(xt32, inp["lm_rows"])
@@ -394,13 +401,10 @@ class TrainStep:
             g32, _ = ops.gelu(tt, want32=True, want16=False)
             _, h16 = ops.layernorm(g32, P.P(t_ + "LayerNorm.weight"), P.P(t_ + "LayerNorm.bias"), want32=False)
             dH, logp = ops.lm_head_loss_backward(h16, P.P16("bert.embeddings.word_embeddings.weight"), P.P("cls.predictions.bias"), inp["lm_labels"],
-                                                 inp["lm_weight"], lm_c / inp["lm_denom"], P.G("bert.embeddings.word_embeddings.weight"),
+                                                 inp["lm_weight"], 1.0 / inp["lm_denom"], P.G("bert.embeddings.word_embeddings.weight"),
                                                  P.G("cls.predictions.bias"))
             out["lm_loss"] = ops.lm_ul_value(logp, inp["lm_weight"], 1.0 / inp["lm_denom"])
-            dg = ops.layernorm_backward(dH, g32, P.P(t_ + "LayerNorm.weight"), P.G(t_ + "LayerNorm.weight"), P.G(t_ + "LayerNorm.bias"))
-            dtt = ops.gelu_backward(dg, tt)
-            dx_lm = ops.linear_backward(dtt, x_lm16, P.P16(t_ + "dense.weight"), P.G(t_ + "dense.weight"), P.G(t_ + "dense.bias"))
-            ops.scatter_add_rows(dx_lm, inp["lm_rows"], d_xt)
+            st.update(lm=(x_lm16, tt, g32, dH))
         else:
             out["lm_loss"] = ops.zeros32(1)
         # ---- poolers + NSP head + weighted CE (:946-967, :1062-1070, :1605-1621)
@@ -410,11 +414,51 @@ class TrainStep:
         fused = ops.mul(pt, pv)
         nsp_logits = ops.linear_f32(fused, P._view(P.p, "cls.bi_seq_relationship.weight", padded=False),
                                     P._view(P.p, "cls.bi_seq_relationship.bias", padded=False))
-        out["nsp_loss"], d_nsp = ops.nsp_ce(nsp_logits, inp["nsl"], inp["nsp_weight"], nsp_c)
-        if "relevance" in inp:
+        out["nsp_loss"], d_nsp = ops.nsp_ce(nsp_logits, inp["nsl"], inp["nsp_weight"], 1.0)
+        st.update(nsp=(cls_t, cls_v, pt, pv, fused, nsp_logits, d_nsp))
+        # ---- image head + masked KL (:1085-1088, :1569-1574)
+        if image_head:
+            ih = "cls.imagePredictions."
+            tv, _ = ops.linear(xv16, P.P16(ih + "transform.dense.weight"), P.P(ih + "transform.dense.bias"))
+            gv32, _ = ops.gelu(tv, want32=True, want16=False)
+            _, hv16 = ops.layernorm(gv32, P.P(ih + "transform.LayerNorm.weight"), P.P(ih + "transform.LayerNorm.bias"), want32=False)
+            v_logits, _ = ops.linear(hv16, P.P16(ih + "decoder.weight"), P.P(ih + "decoder.bias"))
+            out["img_loss"], d_vlog = ops.image_kl(v_logits, cfg.v_target_size, inp["img_target"], inp["img_row_of"], inp["img_label"], 1.0)
+            del v_logits
+            st.update(img=(tv, gv32, hv16, d_vlog))
+        st["out"] = out
+        return st
+
+    def backward(self, st: dict, lm_c: float = 1.0, nsp_c: float = 1.0, img_c: float = 1.0, d_nsp_logits=None, ndcg_scale: float = 0.0) -> dict:
+        """The backward of ``forward``'s state for ``lm_c lm + nsp_c nsp + img_c img`` (+ ``<d_nsp_logits, nsp logits>`` for a caller that
+        differentiates through the NSP scores itself, + ``ndcg_scale neuralNDCG_transposed`` when the batch carries ``gt_relevance``): every
+        parameter gradient lands in ``params.g``.  Consumes the state."""
+        ops, P, cfg = self.ops, self.params, self.cfg
+        inp, saved = st["inp"], st["saved"]
+        B, S, R = inp["B"], inp["S"], inp["R"]
+        e, ve = "bert.embeddings.", "bert.v_embeddings."
+        extra = {}
+        d_xt, d_xv = ops.zeros32(B * S, cfg.hidden_size), ops.zeros32(B * R, cfg.v_hidden_size)
+        if "lm" in st:
+            t_ = "cls.predictions.transform."
+            x_lm16, tt, g32, dH = st.pop("lm")
+            if lm_c != 1.0:                       # the decoder's gradients were written at unit coefficient by the forward's fused kernel
+                ops.ew(EW_SCALE, dH, alpha=lm_c)
+                ops.ew(EW_SCALE, P.G("bert.embeddings.word_embeddings.weight").view(-1), alpha=lm_c)
+                ops.ew(EW_SCALE, P.G("cls.predictions.bias"), alpha=lm_c)
+            dg = ops.layernorm_backward(dH, g32, P.P(t_ + "LayerNorm.weight"), P.G(t_ + "LayerNorm.weight"), P.G(t_ + "LayerNorm.bias"))
+            dtt = ops.gelu_backward(dg, tt)
+            dx_lm = ops.linear_backward(dtt, x_lm16, P.P16(t_ + "dense.weight"), P.G(t_ + "dense.weight"), P.G(t_ + "dense.bias"))
+            ops.scatter_add_rows(dx_lm, inp["lm_rows"], d_xt)
+        cls_t, cls_v, pt, pv, fused, nsp_logits, d_nsp = st.pop("nsp")
+        if nsp_c != 1.0:
+            ops.ew(EW_SCALE, d_nsp.view(-1), alpha=nsp_c)
+        if d_nsp_logits is not None:
+            ops.ew(EW_ADD, d_nsp.view(-1), d_nsp_logits.reshape(-1).contiguous())
+        if "relevance" in inp and ndcg_scale != 0.0:
             # dense-annotation objective (dense_annotation_finetuning.py:267-293): neuralNDCG_transposed on y_pred = softmax(nsp)[:, 0]
             p0 = ops.nsp_prob0(nsp_logits)
-            d_p0, out["ndcg"] = ops.neural_ndcg_backward(p0.view(*inp["relevance"].shape), inp["relevance"], 1.0 / self.batch_multiply)
+            d_p0, extra["ndcg"] = ops.neural_ndcg_backward(p0.view(*inp["relevance"].shape), inp["relevance"], ndcg_scale)
             ops.nsp_prob0_backward(nsp_logits, d_p0.view(-1), d_nsp)
         d_nsp64 = ops.zeros32(B, 64)
         d_nsp64[:, :2].copy_(d_nsp)
@@ -427,21 +471,18 @@ class TrainStep:
                                      P.G("bert.v_pooler.dense.bias"))
         ops.scatter_add_rows(dcls_t, inp["cls_rows"], d_xt)
         ops.scatter_add_rows(dcls_v, inp["img0_rows"], d_xv)
-        # ---- image head + masked KL (:1085-1088, :1569-1574)
-        if self.coeff[2] != 0:
+        if "img" in st and img_c != 0.0:
             ih = "cls.imagePredictions."
-            tv, _ = ops.linear(xv16, P.P16(ih + "transform.dense.weight"), P.P(ih + "transform.dense.bias"))
-            gv32, _ = ops.gelu(tv, want32=True, want16=False)
-            _, hv16 = ops.layernorm(gv32, P.P(ih + "transform.LayerNorm.weight"), P.P(ih + "transform.LayerNorm.bias"), want32=False)
-            v_logits, _ = ops.linear(hv16, P.P16(ih + "decoder.weight"), P.P(ih + "decoder.bias"))
-            out["img_loss"], d_vlog = ops.image_kl(v_logits, cfg.v_target_size, inp["img_target"], inp["img_row_of"], inp["img_label"], img_c)
+            tv, gv32, hv16, d_vlog = st.pop("img")
+            if img_c != 1.0:
+                ops.ew(EW_SCALE, d_vlog.view(-1), alpha=img_c)
             dhv = ops.linear_backward(d_vlog, hv16, P.P16(ih + "decoder.weight"), P.G(ih + "decoder.weight"), P.G(ih + "decoder.bias"))
             dgv = ops.layernorm_backward(dhv, gv32, P.P(ih + "transform.LayerNorm.weight"), P.G(ih + "transform.LayerNorm.weight"),
                                          P.G(ih + "transform.LayerNorm.bias"))
             dtv = ops.gelu_backward(dgv, tv)
-            d_xv = ops.linear_backward(dtv, xv16, P.P16(ih + "transform.dense.weight"), P.G(ih + "transform.dense.weight"),
+            d_xv = ops.linear_backward(dtv, st["xv16"], P.P16(ih + "transform.dense.weight"), P.G(ih + "transform.dense.weight"),
                                        P.G(ih + "transform.dense.bias"), dx_accum=d_xv)
-            del tv, gv32, hv16, v_logits, d_vlog, dhv
+            del tv, gv32, hv16, d_vlog, dhv
         # ---- encoder, in reverse
         for sv in reversed(saved):
             kind, i = sv["kind"], sv["i"]
@@ -453,17 +494,28 @@ class TrainStep:
                 d_xv, d_xt = self._conn_layer_bwd(f"bert.encoder.c_layer.{i}.", d_xv, d_xt, inp, sv)
             sv.clear()
         # ---- embeddings
-        d_esum = ops.layernorm_backward(d_xt, e_sum, P.P(e + "LayerNorm.weight"), P.G(e + "LayerNorm.weight"), P.G(e + "LayerNorm.bias"))
+        d_esum = ops.layernorm_backward(d_xt, st["e_sum"], P.P(e + "LayerNorm.weight"), P.G(e + "LayerNorm.weight"), P.G(e + "LayerNorm.bias"))
         ops.embed_text_backward(d_esum, inp["ids"], inp["seg"], inp["pos"], P.G(e + "word_embeddings.weight"), P.G(e + "position_embeddings.weight"),
                                 P.G(e + "token_type_embeddings.weight"), P.G(e + "token_type_embeddings_extension.weight"), cfg.type_vocab_size)
-        d_vsum = ops.layernorm_backward(d_xv, v_sum, P.P(ve + "LayerNorm.weight"), P.G(ve + "LayerNorm.weight"), P.G(ve + "LayerNorm.bias"))
-        ops.linear_backward(d_vsum, feat16, P.P16(ve + "image_embeddings.weight"), P.G(ve + "image_embeddings.weight"), P.G(ve + "image_embeddings.bias"),
-                            need_dx=False)
-        ops.linear_backward(d_vsum, loc16, P.P16(ve + "image_location_embeddings.weight"), P.G(ve + "image_location_embeddings.weight"),
+        d_vsum = ops.layernorm_backward(d_xv, st["v_sum"], P.P(ve + "LayerNorm.weight"), P.G(ve + "LayerNorm.weight"), P.G(ve + "LayerNorm.bias"))
+        ops.linear_backward(d_vsum, st["feat16"], P.P16(ve + "image_embeddings.weight"), P.G(ve + "image_embeddings.weight"),
+                            P.G(ve + "image_embeddings.bias"), need_dx=False)
+        ops.linear_backward(d_vsum, st["loc16"], P.P16(ve + "image_location_embeddings.weight"), P.G(ve + "image_location_embeddings.weight"),
                             P.G(ve + "image_location_embeddings.bias"), need_dx=False)
         if self.world > 1:
             a, b = P.group_range[0][0], P.group_range[3][1]               # every parameter that has a gradient, one contiguous range
             torch.distributed.all_reduce(P.g[a:b], group=self.group)     # sum; optimizer_step divides by the world size
+        st.clear()
+        return extra
+
+    def forward_backward(self, batch=None, inp=None, read_losses: bool = True) -> Dict[str, float]:
+        """Forward, the three losses, backward: the gradients of ``lm_coeff lm + nsp_coeff nsp + img_coeff img`` (each ``/ batch_multiply``;
+        ``+ neuralNDCG_transposed`` when the batch carries ``gt_relevance``) land in ``params.g``.  ``inp``: inputs already on the device
+        (``upload``); ``read_losses=False`` returns device tensors instead of floats."""
+        st = self.forward(batch, inp)
+        out = st["out"]
+        lm_c, nsp_c, img_c = (c / self.batch_multiply for c in self.coeff)
+        out.update(self.backward(st, lm_c, nsp_c, img_c, ndcg_scale=1.0 / self.batch_multiply))
         if not read_losses:
             return out
         ndcg = out.pop("ndcg", None)

@@ -5,8 +5,11 @@ Same constructor argument (the model JSON), same ``forward`` keyword set and ret
 and a reference checkpoint work unchanged — but the body runs in ``libunimm_b200.so``.
 
 Differences that are deliberate and visible:
-  * inference only (forward + losses); no autograd graph is built (SURVEY.md §8f lists backward as next);
-  * dropout is the identity (the reference's ``.eval()`` behaviour);
+  * by default inference only (forward + losses) — after ``enable_training()`` the loss branch IS differentiable: the three losses (and the
+    NSP scores) come out of a ``torch.autograd.Function`` whose backward runs the device backward of ``unimm_b200.train_step`` and hands
+    every parameter its gradient, so the reference's own loop (``scaler.scale(loss).backward(); scaler.step(optimizer)``,
+    train.py:453-463, dense_annotation_finetuning.py:253-300) trains through these kernels with ANY torch optimizer;
+  * dropout is the identity (the reference's ``.eval()`` behaviour), in training too;
   * dense masks are converted to 4-integer descriptors and verified (sequences truncated at max_seq_len included); any other
     mask pattern raises;
   * ``score()`` is the fast entry: per-sequence log-likelihoods without the [B,S,30522] logits that
@@ -43,6 +46,36 @@ def _build_param_tree(root: nn.Module, cfg: ViLBertConfig) -> None:
         mod.register_parameter(leaf, param)
 
 
+class _TrainBridge(torch.autograd.Function):
+    """Splices the device training step into torch.autograd: forward = ``TrainStep.forward`` (already run by the module; its state rides on
+    the context), backward = ``TrainStep.backward`` with the incoming gradients of the three losses as coefficients (plus the gradient with
+    respect to the NSP scores, which dense_annotation_finetuning.py differentiates through itself), returning each parameter's gradient."""
+
+    @staticmethod
+    def forward(ctx, module, state, *params):
+        ctx.module, ctx.state = module, state
+        out, dev = state["out"], state["nsp"][5].device
+        img = out["img_loss"] if "img_loss" in out else torch.zeros(1, device=dev)
+        return out["lm_loss"].clone(), img.clone(), out["nsp_loss"].clone(), state["nsp"][5].clone()
+
+    @staticmethod
+    def backward(ctx, g_lm, g_img, g_nsp, g_scores):
+        module, st = ctx.module, ctx.state
+        if st is None or "inp" not in st:
+            raise RuntimeError("the device training step keeps ONE forward's activations: backward was already run for this forward")
+        ctx.state = None
+        ts = module._train
+        val = lambda g: 0.0 if g is None else float(g.reshape(-1)[0].item())                          # noqa: E731
+        lm_c, img_c, nsp_c = val(g_lm), val(g_img), val(g_nsp)
+        had_image_head = "img" in st
+        ts.backward(st, lm_c, nsp_c, img_c, d_nsp_logits=None if g_scores is None else g_scores.to(torch.float32))
+        grads = []
+        for name, _ in module._train_params:
+            dead = module._train_group[name] == 4 or (name.startswith("cls.imagePredictions.") and (img_c == 0.0 or not had_image_head))
+            grads.append(None if dead else ts.params._view(ts.params.g, name, padded=False).clone())
+        return (None, None) + tuple(grads)
+
+
 class VisualDialogEncoder(nn.Module):
     def __init__(self, config_path, precision: str = "fp32", max_sequences: int = 128, device: Optional[int] = None,
                  verify_masks: bool = True):
@@ -54,6 +87,51 @@ class VisualDialogEncoder(nn.Module):
         self.verify_masks = verify_masks
         self._engine: Optional[Engine] = None
         self._dirty = True
+        self._train = None
+
+    # ------------------------------------------------------------------ training (SURVEY.md 8f item 1 behind the reference's own loop)
+    def enable_training(self, precision: str = "fp16", device: Optional[int] = None):
+        """Make the loss branch differentiable.  The module's Parameters become fp32 views of the device training step's flat master
+        buffer (same names, shapes and values; ``requires_grad=True``), so an optimizer built from ``named_parameters()`` AFTER this call
+        updates the masters in place; every training forward refreshes the 16-bit operand copies from them.  Returns ``self``."""
+        from .train_ops import DeviceOps
+        from .train_step import TrainStep, param_group
+        from .weights import strip_prefix
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        sd = strip_prefix({k: v.detach().cpu() for k, v in self.state_dict().items()})
+        self._train = TrainStep(self.config, sd, DeviceOps(dev, precision))
+        P = self._train.params
+        made, self._train_params, self._train_group = {}, [], {}
+        for name in param_shapes(self.config):
+            *path, leaf = name.split(".")
+            mod = self.bert_pretrained
+            for p in path:
+                mod = mod._modules[p]
+            if name in TIED:
+                param = made[TIED[name]]
+            else:
+                param = nn.Parameter(P._view(P.p, name, padded=False), requires_grad=True)
+                self._train_params.append((name, param))
+                self._train_group[name] = param_group(name)
+            made[name] = param
+            mod._parameters[leaf] = param
+        self._dirty = True
+        return self
+
+    def _training_forward(self, input_ids, image_feat, image_loc, token_type_ids, token_position_ids, desc, masked_lm_labels,
+                          next_sentence_label, image_attention_mask, image_label, image_target, nsp_weight, lm_weight, output_nsp_scores):
+        ts = self._train
+        ts.params.refresh_lp()                                   # the optimizer wrote the fp32 masters since the last forward
+        if lm_weight is None:
+            raise ValueError("the device training step implements the likelihood / unlikelihood loss: pass lm_weight (train.forward does)")
+        batch = {"tokens": input_ids, "segments": token_type_ids, "positions": token_position_ids, "labels": masked_lm_labels,
+                 "weights": lm_weight, "desc": desc, "next_sentence_label": next_sentence_label, "image_feat": image_feat,
+                 "image_loc": image_loc, "image_mask": image_attention_mask, "image_label": image_label, "image_target": image_target,
+                 "nsp_weight": nsp_weight}
+        state = ts.forward(batch, image_head=True)
+        lm, img, nsp, scores = _TrainBridge.apply(self, state, *[p for _, p in self._train_params])
+        self._dirty = True                                       # the inference engine's copy of the weights is stale from here on
+        return (lm, img, nsp) + ((scores,) if output_nsp_scores else ())
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -109,12 +187,39 @@ class VisualDialogEncoder(nn.Module):
         return {k: torch.cat(v, 0) for k, v in outs.items()}
 
     # ------------------------------------------------------------------ reference signature
-    @torch.no_grad()
     def forward(self, input_ids, image_feat, image_loc, sep_indices=None, sep_len=None, token_type_ids=None,
                 token_position_ids=None, attention_mask=None, masked_lm_labels=None, next_sentence_label=None,
                 head_mask=None, random_round_indices=None, output_nsp_scores=False, output_lm_scores=False,
                 image_attention_mask=None, co_attention_mask=None, image_label=None, image_target=None, nsp_weight=None,
                 lm_weight=None):
+        differentiable = (self._train is not None and torch.is_grad_enabled() and next_sentence_label is not None and
+                          masked_lm_labels is not None and image_target is not None)
+        if not differentiable:
+            with torch.no_grad():
+                return self._inference_forward(input_ids, image_feat, image_loc, token_type_ids, token_position_ids, attention_mask,
+                                               masked_lm_labels, next_sentence_label, output_nsp_scores, output_lm_scores,
+                                               image_attention_mask, co_attention_mask, image_label, image_target, nsp_weight, lm_weight)
+        if output_lm_scores:
+            raise NotImplementedError("the training branch does not materialise [B, S, 30522] logits (train.py's training call does not ask)")
+        B, S = input_ids.shape
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        if token_position_ids is None:
+            token_position_ids = torch.arange(S, dtype=torch.long, device=input_ids.device).unsqueeze(0).expand(B, S)
+        if image_attention_mask is None:
+            image_attention_mask = torch.ones(image_feat.shape[:2])
+        if attention_mask is None or co_attention_mask is None:
+            raise ValueError("attention_mask and co_attention_mask are required (the reference callers always pass them)")
+        dev = self._train.params.p.device
+        am = attention_mask if attention_mask.dtype in (torch.bool, torch.uint8) else attention_mask != 0
+        desc = descriptors_from_masks(am.to(dev, non_blocking=True), co_attention_mask.to(dev, non_blocking=True), verify=self.verify_masks)
+        return self._training_forward(input_ids, image_feat, image_loc, token_type_ids, token_position_ids, desc, masked_lm_labels,
+                                      next_sentence_label, image_attention_mask, image_label, image_target, nsp_weight, lm_weight,
+                                      output_nsp_scores)
+
+    def _inference_forward(self, input_ids, image_feat, image_loc, token_type_ids, token_position_ids, attention_mask, masked_lm_labels,
+                           next_sentence_label, output_nsp_scores, output_lm_scores, image_attention_mask, co_attention_mask, image_label,
+                           image_target, nsp_weight, lm_weight):
         eng = self.engine()
         B, S = input_ids.shape
         if token_type_ids is None:
