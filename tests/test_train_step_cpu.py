@@ -27,7 +27,7 @@ def _train_inputs(n=None):
     return g, b, batch
 
 
-def oracle_losses_and_grads(cfg, sd, b, g, n, dtype=torch.float64, device="cpu"):
+def oracle_losses_and_grads(cfg, sd, b, g, n, dtype=torch.float64, device="cpu", coeff=(1.0, 1.0, 1.0)):
     """loss and d loss / d parameter from torch.autograd over the oracle's forward (the tied decoder shares the embedding tensor)."""
     from oracle import vilbert_oracle as vo
     p = {k: v.to(device, dtype).clone().requires_grad_() for k, v in sd.items() if k != "cls.predictions.decoder.weight"}
@@ -41,7 +41,7 @@ def oracle_losses_and_grads(cfg, sd, b, g, n, dtype=torch.float64, device="cpu")
                    next_sentence_label=torch.from_numpy(g["next_sentence_label"])[sl].to(device), image_label=ex(g["image_label"]),
                    image_target=ex(g["image_target"]), nsp_weight=torch.from_numpy(g["nsp_weight"]).to(device),
                    lm_weight=b["weights"][sl].to(device), dtype=dtype)
-    loss = o["lm_loss"] + o["nsp_loss"] + o["img_loss"]
+    loss = coeff[0] * o["lm_loss"] + coeff[1] * o["nsp_loss"] + coeff[2] * o["img_loss"]          # train.py:167-168
     names = [k for k in p if k != "cls.predictions.decoder.weight"]
     grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
     return {k: float(o[k].detach()) for k in ("lm_loss", "nsp_loss", "img_loss")}, dict(zip(names, grads))
@@ -74,6 +74,14 @@ def test_train_step_orchestration_matches_autograd_of_the_oracle():
         worst = max(worst, err)
         assert err < 1e-8, (name, err)
     print(f"orchestration vs autograd: worst relative gradient error {worst:.2e} over {len(ref_grad)} tensors")
+    # loss coefficients other than 1 (train.py:167-168) and gradient accumulation's 1 / batch_multiply (train.py:451)
+    _, ref_c = oracle_losses_and_grads(cfg, sd, b, g, n, coeff=(0.35, 0.65, 0.25))
+    tsc = TrainStep(cfg, sd, TorchOps(), lm_coeff=0.7, nsp_coeff=1.3, img_coeff=0.5, batch_multiply=2)
+    tsc.forward_backward(batch)
+    gotc = tsc.grad_dict()
+    for name, gr in ref_c.items():
+        if gr is not None:
+            assert float((gotc[name].double() - gr).abs().max()) < 1e-8 * max(float(gr.abs().max()), 1e-6 * gmax), name
     # the optimizer: two steps against the restated pytorch_transformers AdamW with the reference's groups
     from oracle import adamw as oa
     lw_path = "/root/reference/config/language_weights.json"
@@ -178,3 +186,44 @@ def test_dense_annotation_step_orchestration():
             assert not changed, k                                  # no gradient: not even weight decay
         elif float(grads[k].abs().max()) > 1e-6 * gmax:            # (key biases have an analytically zero gradient)
             assert changed, k
+
+
+@pytest.mark.slow
+def test_gradient_accumulation_and_resume():
+    """train.py:451-463: loss / batch_multiply, optimizer every batch_multiply-th iteration (and at iteration 0), scheduler every iteration;
+    and a checkpoint of the optimizer state resumes bit-identically."""
+    from unimm_b200.config import tiny_config
+    from unimm_b200.train_step import TrainStep
+    from unimm_b200.weights import random_state_dict
+    cfg = tiny_config()
+    sd = random_state_dict(cfg, seed=5, perturbed=True)
+    _, _, batch = _train_inputs(4)
+    halves = [{k: (v[:2] if torch.is_tensor(v) and v.shape[:1] == (4,) else v) for k, v in batch.items()},
+              {k: (v[2:] if torch.is_tensor(v) and v.shape[:1] == (4,) else v) for k, v in batch.items()}]
+    kw = dict(lr=1e-3, image_lr=1e-3, warmup_steps=0)
+    acc = TrainStep(cfg, sd, TorchOps(), batch_multiply=2, **kw)
+    acc.step(halves[0])                                  # iteration 0 steps on its own (the reference's `or iter_id == 0`)
+    assert acc.opt_step == 1 and acc.sched_step == 1
+    p_after0 = acc.params.p.clone()
+    acc.step(halves[1])                                  # iteration 1: accumulate only
+    assert acc.opt_step == 1 and acc.sched_step == 2 and torch.equal(acc.params.p, p_after0)
+    acc.step(halves[0])                                  # iteration 2: steps on the sum of iterations 1 and 2
+    assert acc.opt_step == 2 and acc.sched_step == 3
+    # the same three iterations by hand
+    ref = TrainStep(cfg, sd, TorchOps(), batch_multiply=2, **kw)
+    ref.forward_backward(halves[0]); ref.optimizer_step()
+    ref.forward_backward(halves[1]); g1 = ref.params.g.clone(); ref.sched_step += 1
+    ref.forward_backward(halves[0]); ref.params.g.add_(g1); ref.optimizer_step()
+    assert float((ref.params.p - acc.params.p).abs().max()) < 1e-12
+    # resume: model + optimizer state into a fresh object, one more step on both
+    resumed = TrainStep(cfg, acc.state_dict(), TorchOps(), batch_multiply=2, **kw)
+    resumed.params.p.copy_(acc.params.p)                 # state_dict() exports fp32; carry the test's fp64 masters over exactly
+    resumed.params.refresh_lp()
+    resumed.load_optimizer_state_dict(acc.optimizer_state_dict())
+    resumed.params.m.copy_(acc.params.m); resumed.params.v.copy_(acc.params.v)
+    a, b = acc.step(halves[1]), resumed.step(halves[1])
+    a2, b2 = acc.step(halves[0]), resumed.step(halves[0])
+    assert a == b and a2 == b2 and resumed.opt_step == acc.opt_step == 3
+    assert float((resumed.params.p - acc.params.p).abs().max()) == 0.0
+    osd = acc.optimizer_state_dict()
+    assert set(osd["exp_avg"]) == set(acc.params.entries) and osd["exp_avg"]["cls.bi_seq_relationship.weight"].shape == (2, 1024)

@@ -75,7 +75,7 @@ class ParamStore:
     """Flat fp32 master parameters, gradients, Adam moments and 16-bit operand copies with per-name views."""
 
     def __init__(self, cfg: ViLBertConfig, ops, unused=()):
-        self.cfg, self.ops = cfg, ops
+        self.cfg, self.ops, self.unused = cfg, ops, tuple(unused)
         shapes = param_shapes(cfg)
         by_group = {g: [] for g in range(5)}
         for name, shp in shapes.items():
@@ -182,6 +182,7 @@ class TrainStep:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        self.iter_id, self._acc = 0, None
         self.opt_step = 0            # AdamW state['step']
         self.sched_step = 0          # scheduler.last_epoch
         self.S, self.R = None, None
@@ -350,6 +351,30 @@ class TrainStep:
                                   P.span(P.g, b + "query2.weight", b + "value2.weight"), P.span(P.g, b + "query2.bias", b + "value2.bias"), dx_accum=dxt)
         return dxv, dxt
 
+    # ------------------------------------------------------------------ data parallel: gradient all-reduce overlapped with the backward
+    def _layer_ranges(self, prefix: str):
+        """Flat-buffer ranges (one per parameter group) of the parameters whose names start with ``prefix``: a layer's tensors are
+        consecutive inside each group."""
+        P = self.params
+        spans = {}
+        for name, (off, pad, _) in P.entries.items():
+            if name.startswith(prefix):
+                g = param_group(name, P.unused)
+                if g == 4:
+                    continue
+                lo, hi = spans.get(g, (off, off))
+                spans[g] = (min(lo, off), max(hi, off + (int(np.prod(pad)) + 63) // 64 * 64))
+        return list(spans.values())
+
+    def _reduce_async(self, prefix: str, st: dict) -> None:
+        """The gradients of the layer ``prefix`` are final: start their all-reduce now (NCCL runs it on its own stream beside the rest of
+        the backward); ``backward`` waits for all of them before it returns."""
+        if self.world <= 1:
+            return
+        for a, b in self._layer_ranges(prefix):
+            st["reduced"].append((a, b))
+            st["handles"].append(torch.distributed.all_reduce(self.params.g[a:b], group=self.group, async_op=True))
+
     # ------------------------------------------------------------------ the step
     def forward(self, batch=None, inp=None, image_head: Optional[bool] = None) -> dict:
         """The forward of the step: embeddings, encoder (activations saved), the three heads and their loss VALUES, plus the gradients of
@@ -389,7 +414,8 @@ class TrainStep:
             else:
                 xv32, xv16, xt32, xt16 = self._conn_layer_fwd(f"bert.encoder.c_layer.{i}.", xv32, xv16, xt32, xt16, inp, sv)
             saved.append(sv)
-        st = {"inp": inp, "saved": saved, "e_sum": e_sum, "v_sum": v_sum, "feat16": feat16, "loc16": loc16, "xv16": xv16}
+        st = {"inp": inp, "saved": saved, "e_sum": e_sum, "v_sum": v_sum, "feat16": feat16, "loc16": loc16, "xv16": xv16, "handles": [],
+              "reduced": []}
         out = {}
         # ---- masked-LM head + likelihood / unlikelihood loss (:982-986, :1023-1026, :1577-1595), labelled rows only.  The fused vocabulary
         # kernel is forward AND backward of the decoder + loss in one: it runs here with the loss's own normalisation (1 / #weighted tokens)
@@ -486,13 +512,15 @@ class TrainStep:
         # ---- encoder, in reverse
         for sv in reversed(saved):
             kind, i = sv["kind"], sv["i"]
+            prefix = {"t": "bert.encoder.layer.", "v": "bert.encoder.v_layer.", "c": "bert.encoder.c_layer."}[kind] + f"{i}."
             if kind == "t":
-                d_xt = self._self_layer_bwd(f"bert.encoder.layer.{i}.", d_xt, inp["desc"], None, sv)
+                d_xt = self._self_layer_bwd(prefix, d_xt, inp["desc"], None, sv)
             elif kind == "v":
-                d_xv = self._self_layer_bwd(f"bert.encoder.v_layer.{i}.", d_xv, None, inp["img_mask"], sv)
+                d_xv = self._self_layer_bwd(prefix, d_xv, None, inp["img_mask"], sv)
             else:
-                d_xv, d_xt = self._conn_layer_bwd(f"bert.encoder.c_layer.{i}.", d_xv, d_xt, inp, sv)
+                d_xv, d_xt = self._conn_layer_bwd(prefix, d_xv, d_xt, inp, sv)
             sv.clear()
+            self._reduce_async(prefix, st)
         # ---- embeddings
         d_esum = ops.layernorm_backward(d_xt, st["e_sum"], P.P(e + "LayerNorm.weight"), P.G(e + "LayerNorm.weight"), P.G(e + "LayerNorm.bias"))
         ops.embed_text_backward(d_esum, inp["ids"], inp["seg"], inp["pos"], P.G(e + "word_embeddings.weight"), P.G(e + "position_embeddings.weight"),
@@ -503,8 +531,16 @@ class TrainStep:
         ops.linear_backward(d_vsum, st["loc16"], P.P16(ve + "image_location_embeddings.weight"), P.G(ve + "image_location_embeddings.weight"),
                             P.G(ve + "image_location_embeddings.bias"), need_dx=False)
         if self.world > 1:
-            a, b = P.group_range[0][0], P.group_range[3][1]               # every parameter that has a gradient, one contiguous range
-            torch.distributed.all_reduce(P.g[a:b], group=self.group)     # sum; optimizer_step divides by the world size
+            # what the per-layer all-reduces above have not covered (embeddings, poolers, heads): the gaps of the range that holds every
+            # parameter with a gradient.  Sums; optimizer_step divides by the world size.
+            lo, hi = P.group_range[0][0], P.group_range[3][1]
+            pos = lo
+            for a, b in sorted(st["reduced"]) + [(hi, hi)]:
+                if a > pos:
+                    st["handles"].append(torch.distributed.all_reduce(P.g[pos:a], group=self.group, async_op=True))
+                pos = max(pos, b)
+            for h in st["handles"]:
+                h.wait()
         st.clear()
         return extra
 
@@ -549,9 +585,44 @@ class TrainStep:
         self.sched_step += 1
 
     def step(self, batch=None, inp=None, read_losses: bool = True) -> Dict[str, float]:
+        """One iteration of train.py:445-463.  With ``batch_multiply`` k > 1 the gradients of k calls are summed (every loss already carries
+        1 / k) and the optimizer steps when ``iter_id % k == 0`` — iteration 0 included, as the reference's ``or iter_id == 0`` has it —
+        while the scheduler advances on every call (train.py:455-463)."""
         vals = self.forward_backward(batch, inp, read_losses)
-        self.optimizer_step()
+        k = self.batch_multiply
+        if k > 1:
+            P, ops = self.params, self.ops
+            if self._acc is None:
+                self._acc = ops.zeros32(P.total)
+            ops.ew(EW_ADD, self._acc, P.g)
+            if self.iter_id % k == 0:
+                P.g.copy_(self._acc)
+                self._acc.zero_()
+                self.optimizer_step()
+            else:
+                self.sched_step += 1
+        else:
+            self.optimizer_step()
+        self.iter_id += 1
         return vals
+
+    # ------------------------------------------------------------------ checkpoint / resume (train.py:503-505 saves model, optimizer, scheduler)
+    def optimizer_state_dict(self) -> dict:
+        """Adam moments per parameter (reference key layout, real shapes, fp32 on the host) and the step counters."""
+        P = self.params
+        return {"exp_avg": {n: P._view(P.m, n, padded=False).detach().clone().cpu() for n in P.entries},
+                "exp_avg_sq": {n: P._view(P.v, n, padded=False).detach().clone().cpu() for n in P.entries},
+                "step": self.opt_step, "scheduler_last_epoch": self.sched_step, "iter_id": self.iter_id}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        P = self.params
+        for n in P.entries:
+            for flat, key in ((P.m, "exp_avg"), (P.v, "exp_avg_sq")):
+                dst = P._view(flat, n, padded=False)
+                dst.copy_(sd[key][n].to(dst.device, dst.dtype))
+        self.opt_step, self.sched_step, self.iter_id = int(sd["step"]), int(sd["scheduler_last_epoch"]), int(sd.get("iter_id", 0))
+        if self._acc is not None:
+            self._acc.zero_()
 
     def state_dict(self):
         return self.params.state_dict()
