@@ -360,10 +360,12 @@ int unimm_k_attention(const void* d_q, int ldq, const void* d_k, int ldk, const 
  * the 16-bit operand scale is then derived without a pass over dY; d_gelu_t (optional, fp32 [M, N]): the projection is followed by the erf
  * GELU and d_dY is the gradient with respect to the GELU's OUTPUT: gelu'(d_gelu_t) is applied in the pass that casts dY and sums its
  * columns (no separate GELU-backward kernel, no fp32 copy of the pre-activation gradient); d_dX_amax (optional): receives max |dX| as
- * float bits from the dgrad GEMM's epilogue */
+ * float bits from the dgrad GEMM's epilogue; drop_p > 0: the projection's OUTPUT went through nn.Dropout (unimm_t_gemm_drop with the same
+ * seed): the same keep-mask / (1 - p) is applied to dY in that pass */
 int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X_lp, int ldx, const void* d_W_lp, int ldw, int M, int N, int K,
                                 float* d_dX, int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t,
-                                float* d_dX_amax, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream);
+                                float* d_dX_amax, uint32_t drop_seed, float drop_p, void* d_scratch, size_t scratch_bytes, int lp_kind,
+                                void* stream);
 /* unimm_k_layernorm_backward / unimm_k_gelu_backward that also leave max |dx| (float bits; zeroed first) in d_amax[0] */
 int unimm_k_layernorm_backward_amax(const float* d_dy, const float* d_x, int rows, int H, const float* d_gamma, float* d_dx, float* d_dgamma,
                                     float* d_dbeta, float* d_amax, void* stream);
@@ -372,7 +374,7 @@ int unimm_k_gelu_backward_amax(const float* d_dy, const float* d_x, int64_t n, f
  * (natural log, softmax scale included) for the backward. */
 int unimm_k_attention_lse(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B, int heads,
                           int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind,
-                          float* d_lse, void* stream);
+                          float* d_lse, uint32_t drop_seed, float drop_p, void* stream);
 /* Backward of softmax(Q K^T / sqrt(D) + mask) V (models/vilbert_dialog.py:395-410, :681-721) from the saved 16-bit q / k / v / o and
  * d_lse: d_dO fp32 contiguous [B*Sq, heads*D] -> d_dq [B*Sq, lddq], d_dk / d_dv [B*Skv, lddk / lddv] fp32 (head h at column h*D, so the
  * three can be the column blocks of one [rows, 3H] matrix).  P is recomputed tile by tile; no [B, heads, Sq, Skv] tensor, no atomics.
@@ -383,8 +385,17 @@ size_t unimm_k_attention_backward_scratch(int B, int heads, int D, int Sq);
 int unimm_k_attention_backward(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, const void* d_o, int ldo,
                                const float* d_dO, const float* d_lse, int B, int heads, int D, int Sq, int Skv, int mask_kind,
                                const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind, float* d_dq, int lddq, float* d_dk,
-                               int lddk, float* d_dv, int lddv, float* d_amax_accum, const float* d_dO_amax, void* d_scratch, size_t scratch_bytes,
-                               void* stream);
+                               int lddk, float* d_dv, int lddv, float* d_amax_accum, const float* d_dO_amax, uint32_t drop_seed, float drop_p,
+                               void* d_scratch, size_t scratch_bytes, void* stream);
+/* nn.Dropout of the reference's training mode (models/vilbert_dialog.py:355, :405, :424, :467, :534, :553, :596, :693, :716, :746, :749,
+ * :1065, :1491), counter-based: element i is kept iff lowbias32(lowbias32(i ^ seed) + seed) >= p 2^32 and then scaled by 1 / (1 - p), so the
+ * backward regenerates every mask from (seed, i).  unimm_t_dropout: y = dropout(x) as fp32 and / or 16-bit (forward; applied to a gradient
+ * in place it is the backward).  unimm_t_gemm_drop: out = dropout(A W^T + bias) + residual, the mask applied in the GEMM epilogue
+ * (element index row * N + column).  unimm_k_attention_lse / _backward take (drop_seed, drop_p) for the probabilities' dropout
+ * (index ((b heads + h) Sq + q) Skv + k); drop_p = 0 everywhere = the reference in eval mode. */
+int unimm_t_dropout(const float* d_x, int64_t n, uint32_t seed, float p, float* d_y_f32, void* d_y_lp, int lp_kind, void* stream);
+int unimm_t_gemm_drop(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias, const float* d_residual,
+                      int ldr, uint32_t drop_seed, float drop_p, float* d_out_f32, int ldo_f32, int lp_kind, void* stream);
 /* text embeddings without the LayerNorm (its input is what the backward needs): word + position + (type | type-extension)
  * (models/vilbert_dialog.py:334-352) -> d_out fp32 [rows, H]; and the scatter-add of that sum's gradient into the four tables
  * (accumulating: the word table's gradient also receives the tied decoder's). */

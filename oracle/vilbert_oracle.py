@@ -18,7 +18,10 @@ built by the reference's own ``utils/data_utils.encode_input_*`` and commits the
 ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this file against them.
 
 Dropout: every ``nn.Dropout`` on the path is the identity here (the reference's eval mode;
-SURVEY.md §7 "Dropout").
+SURVEY.md §7 "Dropout") unless the caller passes ``drop``: a callable ``(site, tensor) -> tensor`` invoked at exactly the
+reference's ``nn.Dropout`` call sites (models/vilbert_dialog.py:355, :405, :424, :467, :534, :553, :596, :693, :716, :746, :749,
+:1065, :1491) with a stable site name — the training-step tests use it to apply the SAME keep-masks the device step draws, so
+that the step with dropout on can be checked against ``torch.autograd`` exactly.
 """
 from __future__ import annotations
 
@@ -56,7 +59,11 @@ def additive_mask(mask: torch.Tensor, dtype) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- embeddings
-def text_embeddings(sd, cfg, input_ids, token_type_ids, position_ids, dtype) -> torch.Tensor:
+def _nodrop(site, x):
+    return x
+
+
+def text_embeddings(sd, cfg, input_ids, token_type_ids, position_ids, dtype, drop=_nodrop) -> torch.Tensor:
     """BertEmbeddingsDialog.forward (models/vilbert_dialog.py:326-356).
 
     Segment ids >= type_vocab_size select ``token_type_embeddings_extension[id - type_vocab_size]``,
@@ -72,14 +79,14 @@ def text_embeddings(sd, cfg, input_ids, token_type_ids, position_ids, dtype) -> 
     base = F.embedding(base_ids, _w(sd, p + "token_type_embeddings.weight", dtype))
     ext = F.embedding(ext_ids, _w(sd, p + "token_type_embeddings_extension.weight", dtype))
     types = torch.where(is_ext.unsqueeze(-1), ext, base)
-    return layer_norm(sd, p + "LayerNorm", words + pos + types)
+    return drop("emb.txt", layer_norm(sd, p + "LayerNorm", words + pos + types))                  # :354-355
 
 
-def image_embeddings(sd, image_feat, image_loc) -> torch.Tensor:
+def image_embeddings(sd, image_feat, image_loc, drop=_nodrop) -> torch.Tensor:
     """BertImageEmbeddings.forward (models/vilbert_dialog.py:1487-1493)."""
     p = "bert.v_embeddings."
-    return layer_norm(sd, p + "LayerNorm",
-                      linear(sd, p + "image_embeddings", image_feat) + linear(sd, p + "image_location_embeddings", image_loc))
+    return drop("emb.img", layer_norm(sd, p + "LayerNorm",
+                                      linear(sd, p + "image_embeddings", image_feat) + linear(sd, p + "image_location_embeddings", image_loc)))
 
 
 # --------------------------------------------------------------------------- attention
@@ -93,27 +100,27 @@ def _merge_heads(x: torch.Tensor) -> torch.Tensor:
     return x.permute(0, 2, 1, 3).reshape(b, s, h * d)
 
 
-def attention(q, k, v, heads: int, add_mask: Optional[torch.Tensor]) -> torch.Tensor:
-    """softmax(Q K^T / sqrt(d) + mask) V; scale before mask (models/vilbert_dialog.py:395-410)."""
+def attention(q, k, v, heads: int, add_mask: Optional[torch.Tensor], drop=_nodrop, site: str = "") -> torch.Tensor:
+    """softmax(Q K^T / sqrt(d) + mask) V; scale before mask, dropout on the probabilities (models/vilbert_dialog.py:395-410)."""
     qh, kh, vh = _split_heads(q, heads), _split_heads(k, heads), _split_heads(v, heads)
     scores = torch.matmul(qh, kh.transpose(-1, -2)) / math.sqrt(qh.shape[-1])
     if add_mask is not None:
         scores = scores + add_mask
-    probs = torch.softmax(scores, dim=-1)
+    probs = drop(site, torch.softmax(scores, dim=-1))
     return _merge_heads(torch.matmul(probs, vh))
 
 
-def transformer_layer(sd, p: str, x, add_mask, heads: int) -> torch.Tensor:
+def transformer_layer(sd, p: str, x, add_mask, heads: int, drop=_nodrop) -> torch.Tensor:
     """BertLayer / BertImageLayer (models/vilbert_dialog.py:479-483, :608-612)."""
     a = p + "attention."
     ctx = attention(linear(sd, a + "self.query", x), linear(sd, a + "self.key", x), linear(sd, a + "self.value", x),
-                    heads, add_mask)
-    att = layer_norm(sd, a + "output.LayerNorm", linear(sd, a + "output.dense", ctx) + x)       # :422-426
+                    heads, add_mask, drop, a + "probs")
+    att = layer_norm(sd, a + "output.LayerNorm", drop(a + "output", linear(sd, a + "output.dense", ctx)) + x)       # :422-426
     inter = gelu(linear(sd, p + "intermediate.dense", att))                                      # :452-455
-    return layer_norm(sd, p + "output.LayerNorm", linear(sd, p + "output.dense", inter) + att)   # :465-469
+    return layer_norm(sd, p + "output.LayerNorm", drop(p + "output", linear(sd, p + "output.dense", inter)) + att)   # :465-469
 
 
-def connection_layer(sd, cfg, p: str, img, img_add_mask, txt, co_add_mask):
+def connection_layer(sd, cfg, p: str, img, img_add_mask, txt, co_add_mask, drop=_nodrop):
     """BertConnectionLayer.forward (models/vilbert_dialog.py:770-783).
 
     BertBiAttention (:655-723): stream 1 = image, stream 2 = text.  Text queries attend image keys
@@ -126,15 +133,15 @@ def connection_layer(sd, cfg, p: str, img, img_add_mask, txt, co_add_mask):
     heads = cfg.bi_num_attention_heads
     q1, k1, v1 = linear(sd, b + "query1", img), linear(sd, b + "key1", img), linear(sd, b + "value1", img)
     q2, k2, v2 = linear(sd, b + "query2", txt), linear(sd, b + "key2", txt), linear(sd, b + "value2", txt)
-    ctx_txt_over_img = attention(q2, k1, v1, heads, img_add_mask)      # context_layer1 [B,S,Hb]
-    ctx_img_over_txt = attention(q1, k2, v2, heads, co_add_mask)       # context_layer2 [B,R,Hb]
+    ctx_txt_over_img = attention(q2, k1, v1, heads, img_add_mask, drop, b + "probs1")      # context_layer1 [B,S,Hb], dropout1 :693
+    ctx_img_over_txt = attention(q1, k2, v2, heads, co_add_mask, drop, b + "probs2")       # context_layer2 [B,R,Hb], dropout2 :716
     o = p + "biOutput."
-    img_att = layer_norm(sd, o + "LayerNorm1", linear(sd, o + "dense1", ctx_img_over_txt) + img)
-    txt_att = layer_norm(sd, o + "LayerNorm2", linear(sd, o + "dense2", ctx_txt_over_img) + txt)
+    img_att = layer_norm(sd, o + "LayerNorm1", drop(o + "dense1", linear(sd, o + "dense1", ctx_img_over_txt)) + img)    # :745-747
+    txt_att = layer_norm(sd, o + "LayerNorm2", drop(o + "dense2", linear(sd, o + "dense2", ctx_txt_over_img)) + txt)    # :748-750
     img_out = layer_norm(sd, p + "v_output.LayerNorm",
-                         linear(sd, p + "v_output.dense", gelu(linear(sd, p + "v_intermediate.dense", img_att))) + img_att)
+                         drop(p + "v_output", linear(sd, p + "v_output.dense", gelu(linear(sd, p + "v_intermediate.dense", img_att)))) + img_att)
     txt_out = layer_norm(sd, p + "t_output.LayerNorm",
-                         linear(sd, p + "t_output.dense", gelu(linear(sd, p + "t_intermediate.dense", txt_att))) + txt_att)
+                         drop(p + "t_output", linear(sd, p + "t_output.dense", gelu(linear(sd, p + "t_intermediate.dense", txt_att)))) + txt_att)
     return img_out, txt_out
 
 
@@ -149,14 +156,14 @@ def layer_schedule(cfg):
     return order
 
 
-def encoder(sd, cfg, txt, img, txt_add_mask, img_add_mask, co_add_mask, taps: Optional[dict] = None):
+def encoder(sd, cfg, txt, img, txt_add_mask, img_add_mask, co_add_mask, taps: Optional[dict] = None, drop=_nodrop):
     for kind, i in layer_schedule(cfg):
         if kind == "t":
-            txt = transformer_layer(sd, f"bert.encoder.layer.{i}.", txt, txt_add_mask, cfg.num_attention_heads)
+            txt = transformer_layer(sd, f"bert.encoder.layer.{i}.", txt, txt_add_mask, cfg.num_attention_heads, drop)
         elif kind == "v":
-            img = transformer_layer(sd, f"bert.encoder.v_layer.{i}.", img, img_add_mask, cfg.v_num_attention_heads)
+            img = transformer_layer(sd, f"bert.encoder.v_layer.{i}.", img, img_add_mask, cfg.v_num_attention_heads, drop)
         else:
-            img, txt = connection_layer(sd, cfg, f"bert.encoder.c_layer.{i}.", img, img_add_mask, txt, co_add_mask)
+            img, txt = connection_layer(sd, cfg, f"bert.encoder.c_layer.{i}.", img, img_add_mask, txt, co_add_mask, drop)
         if taps is not None:
             taps[f"{kind}{i}.txt"] = txt
             taps[f"{kind}{i}.img"] = img
@@ -176,11 +183,11 @@ def lm_logits(sd, rows: torch.Tensor) -> torch.Tensor:
     return F.linear(h, _w(sd, "cls.predictions.decoder.weight", h.dtype)) + _w(sd, "cls.predictions.bias", h.dtype)
 
 
-def nsp_logits(sd, txt, img) -> torch.Tensor:
-    """Poolers (:946-967) and the 'mul' fusion NSP head (:1062-1070)."""
+def nsp_logits(sd, txt, img, drop=_nodrop) -> torch.Tensor:
+    """Poolers (:946-967) and the 'mul' fusion NSP head with its dropout on the fused vector (:1062-1070)."""
     pt = torch.relu(linear(sd, "bert.t_pooler.dense", txt[:, 0]))
     pv = torch.relu(linear(sd, "bert.v_pooler.dense", img[:, 0]))
-    return linear(sd, "cls.bi_seq_relationship", pt * pv)
+    return linear(sd, "cls.bi_seq_relationship", drop("nsp.pooled", pt * pv))
 
 
 def image_logits(sd, img) -> torch.Tensor:
@@ -195,7 +202,7 @@ def forward(sd: Dict[str, torch.Tensor], cfg, input_ids, image_feat, image_loc, 
             attention_mask, image_attention_mask, co_attention_mask,
             masked_lm_labels=None, next_sentence_label=None, image_label=None, image_target=None,
             nsp_weight=None, lm_weight=None, dtype=torch.float32, full_logits: bool = False,
-            taps: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+            taps: Optional[dict] = None, drop=_nodrop) -> Dict[str, torch.Tensor]:
     """BertModel.forward + BertForMultiModalPreTraining.forward (models/vilbert_dialog.py:1359-1472, :1519-1626).
 
     Returns a dict: ``sequence_output_t`` [B,S,H], ``sequence_output_v``, ``nsp_scores`` [B,2],
@@ -212,12 +219,12 @@ def forward(sd: Dict[str, torch.Tensor], cfg, input_ids, image_feat, image_loc, 
     img_add = additive_mask(image_attention_mask[:, None, None, :], dtype)     # :1405-1406,1423
     co_add = additive_mask(co_attention_mask[:, None, :, :], dtype)            # :1427-1431
 
-    txt = text_embeddings(sd, cfg, input_ids, token_type_ids, position_ids, dtype)
-    img = image_embeddings(sd, image_feat, image_loc)
+    txt = text_embeddings(sd, cfg, input_ids, token_type_ids, position_ids, dtype, drop)
+    img = image_embeddings(sd, image_feat, image_loc, drop)
     if taps is not None:
         taps["emb.txt"], taps["emb.img"] = txt, img
-    txt, img = encoder(sd, cfg, txt, img, txt_add, img_add, co_add, taps)
-    out = {"sequence_output_t": txt, "sequence_output_v": img, "nsp_scores": nsp_logits(sd, txt, img)}
+    txt, img = encoder(sd, cfg, txt, img, txt_add, img_add, co_add, taps, drop)
+    out = {"sequence_output_t": txt, "sequence_output_v": img, "nsp_scores": nsp_logits(sd, txt, img, drop)}
 
     B, S, _ = txt.shape
     if full_logits:

@@ -227,3 +227,47 @@ def test_gradient_accumulation_and_resume():
     assert float((resumed.params.p - acc.params.p).abs().max()) == 0.0
     osd = acc.optimizer_state_dict()
     assert set(osd["exp_avg"]) == set(acc.params.entries) and osd["exp_avg"]["cls.bi_seq_relationship.weight"].shape == (2, 1024)
+
+
+@pytest.mark.slow
+def test_train_step_with_dropout_matches_autograd_under_the_same_masks():
+    """Dropout on (p = 0.1 at every nn.Dropout site of the reference): the step draws counter-based keep-masks (site, forward number,
+    element index) and regenerates them in the backward; the oracle, given the SAME masks at the reference's dropout call sites,
+    must have the same losses and gradients."""
+    from torch_train_ops import keep_mask
+    from unimm_b200.config import tiny_config
+    from unimm_b200.train_step import TrainStep, site_seed
+    from unimm_b200.weights import random_state_dict
+    from oracle import vilbert_oracle as vo
+    cfg = tiny_config()
+    sd = random_state_dict(cfg, seed=5, perturbed=True)
+    n = 3
+    g, b, batch = _train_inputs(n)
+    ts = TrainStep(cfg, sd, TorchOps(), dropout=0.1, seed=1234)
+    vals = ts.forward_backward(batch)
+    sites = []
+
+    def drop(site, x):
+        sites.append(site)
+        return x * keep_mask((site_seed(1234 + 0, site), 0.1), tuple(x.shape))      # forward number 0
+
+    p = {k: v.double().clone().requires_grad_() for k, v in sd.items() if k != "cls.predictions.decoder.weight"}
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    ex = lambda a: torch.from_numpy(a)[None].expand(n, *a.shape)                                          # noqa: E731
+    o = vo.forward(p, cfg, b["tokens"][:n], ex(g["image_feat"]), ex(g["image_loc"]), b["segments"][:n], b["positions"][:n],
+                   b["txt_attention_mask"][:n], ex(g["image_mask"]), b["co_attention_mask"][:n], masked_lm_labels=b["mask"][:n],
+                   next_sentence_label=torch.from_numpy(g["next_sentence_label"])[:n], image_label=ex(g["image_label"]),
+                   image_target=ex(g["image_target"]), nsp_weight=torch.from_numpy(g["nsp_weight"]), lm_weight=b["weights"][:n],
+                   dtype=torch.float64, drop=drop)
+    assert len(sites) == len(set(sites)) == 2 + 3 * (cfg.num_hidden_layers + cfg.v_num_hidden_layers) + 6 * len(cfg.v_biattention_id) + 1
+    for k in ("lm_loss", "nsp_loss", "img_loss"):
+        assert abs(vals[k] - float(o[k].detach())) < 1e-9, k
+    names = [k for k in p if k != "cls.predictions.decoder.weight"]
+    grads = dict(zip(names, torch.autograd.grad(o["lm_loss"] + o["nsp_loss"] + o["img_loss"], [p[k] for k in names], allow_unused=True)))
+    got = ts.grad_dict()
+    gmax = max(float(x.abs().max()) for x in grads.values() if x is not None)
+    for k, gr in grads.items():
+        if gr is not None:
+            assert float((got[k].double() - gr).abs().max()) < 1e-8 * max(float(gr.abs().max()), 1e-6 * gmax), k
+    # the next forward draws different masks; dropout off reproduces the eval-mode losses
+    assert ts.forward_backward(batch)["lm_loss"] != vals["lm_loss"]

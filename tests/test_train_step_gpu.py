@@ -284,3 +284,88 @@ def test_config3_training_step_at_size(full_cfg, precision):
     print(f"[{precision}] loss {vals['loss']:.5f} -> {again['loss']:.5f} after one AdamW step at lr 1e-4")
     assert again["loss"] < vals["loss"]
     assert all(torch.isfinite(v).all() for v in ts.state_dict().values())
+
+
+def test_dropout_kernels_regenerate_the_reference_masks():
+    """Counter-based dropout: the element-wise kernel, the GEMM epilogue, the cast pass of the linear backward and the three attention
+    kernels all draw mask(seed, i) = tests/torch_train_ops.py::keep_mask — checked against torch with that mask applied."""
+    from torch_train_ops import keep_mask
+    ops, ref = DeviceOps(DEV, "fp16"), TorchOps()
+    g = torch.Generator().manual_seed(21)
+    drop = (0x9E3779B1, 0.1)
+    x = torch.randn(300, 768, generator=g)
+    y32, y16 = ops.dropout(x.to(DEV), drop)
+    want = x.double() * keep_mask(drop, x.shape)
+    assert (y32.cpu().double() - want).abs().max().item() < 1e-6 and abs(float((y32 == 0).float().mean()) - 0.1) < 0.01
+    assert (y16.float().cpu().double() - want).abs().max().item() < 4e-3
+    dy = torch.randn(300, 768, generator=g)
+    assert (ops.dropout_backward(dy.to(DEV).clone(), drop).cpu().double() - dy.double() * keep_mask(drop, dy.shape)).abs().max().item() < 1e-6
+    # projection with output dropout + residual, and its backward
+    M, N, K = 1000, 768, 1024
+    a, w = torch.randn(M, K, generator=g).half(), (0.03 * torch.randn(N, K, generator=g)).half()
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    out, _ = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), residual=res.to(DEV), drop=drop)
+    want = (a.double() @ w.double().t() + bias.double()) * keep_mask(drop, (M, N)) + res.double()
+    assert (out.cpu().double() - want).abs().max().item() < 2e-2
+    dyl = torch.randn(M, N, generator=g) * 1e-4
+    gw, gb = torch.empty(N, K, device=DEV), torch.empty(N, device=DEV)
+    dx = ops.linear_backward(dyl.to(DEV), a.to(DEV), w.to(DEV), gw, gb, drop=drop)
+    dym = dyl.double() * keep_mask(drop, (M, N))
+    for name, mine, wantg in (("dx", dx, dym @ w.double()), ("dw", gw, dym.t() @ a.double()), ("db", gb, dym.sum(0))):
+        e = (mine.cpu().double() - wantg).abs().max().item() / wantg.abs().max().item()
+        assert e < 4e-3, (name, e)
+    # attention with dropout on the probabilities: forward and backward, two mask families
+    desc = _descs()
+    B, S, R = desc.shape[0], 256, 37
+    km = torch.ones(B, R)
+    km[1, 30:] = 0
+    for heads, D, Sq, Skv, kind in ((12, 64, S, S, MASK_TEXT_SELF), (8, 128, R, S, MASK_CO_INTERVAL), (8, 128, S, R, MASK_KEY_VECTOR)):
+        H = heads * D
+        q, k, v = (torch.randn(n, H, generator=g).half() for n in (B * Sq, B * Skv, B * Skv))
+        d_desc = desc.to(DEV) if kind != MASK_KEY_VECTOR else None
+        d_km = km.to(DEV) if kind == MASK_KEY_VECTOR else None
+        o, lse = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), B, heads, D, Sq, Skv, kind, d_desc, d_km, drop=drop)
+        o_ref, _ = ref.attention(q.double(), k.double(), v.double(), B, heads, D, Sq, Skv, kind, desc, km, drop=drop)
+        valid = dense_text_mask(desc, S).any(-1).reshape(-1) if kind == MASK_TEXT_SELF else torch.ones(B * Sq, dtype=torch.bool)
+        assert (o.float().cpu().double() - o_ref)[valid].abs().max().item() < 6e-3
+        dO = torch.randn(B * Sq, H, generator=g) * 3e-5 * valid[:, None]
+        dq, dk, dv = ops.empty32(B * Sq, H), ops.empty32(B * Skv, H), ops.empty32(B * Skv, H)
+        ops.attention_backward(q.to(DEV), k.to(DEV), v.to(DEV), o, lse, dO.to(DEV), B, heads, D, Sq, Skv, kind, d_desc, d_km, dq, dk, dv, drop=drop)
+        rq, rk, rv = (torch.empty(n, H, dtype=torch.float64) for n in (B * Sq, B * Skv, B * Skv))
+        ref.attention_backward(q.double(), k.double(), v.double(), None, None, dO.double(), B, heads, D, Sq, Skv, kind, desc, km, rq, rk, rv, drop=drop)
+        for name, mine, wantg in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+            e = (mine.cpu().double() - wantg).abs().max().item() / wantg.abs().max().item()
+            print(f"attention with dropout, mask kind {kind} {name}: max |err| / max |ref| = {e:.3e}")
+            assert e < 6e-3, (kind, name)
+
+
+def test_train_step_with_dropout_matches_autograd_under_the_same_masks_gpu():
+    """The whole step with p = 0.1 at every nn.Dropout site of the reference, against autograd of the oracle given the same masks."""
+    from torch_train_ops import keep_mask
+    from oracle import vilbert_oracle as vo
+    from unimm_b200.config import tiny_config
+    from unimm_b200.train_step import TrainStep, site_seed
+    from unimm_b200.weights import random_state_dict
+    cfg = tiny_config()
+    sd = random_state_dict(cfg, seed=5, perturbed=True)
+    n = 4
+    g, b, batch = _train_inputs(n)
+    ts = TrainStep(cfg, sd, DeviceOps(DEV, "fp16"), dropout=0.1, seed=77)
+    vals = ts.forward_backward(batch)
+    p = {k: v.double().clone().requires_grad_() for k, v in sd.items() if k != "cls.predictions.decoder.weight"}
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    ex = lambda a: torch.from_numpy(a)[None].expand(n, *a.shape)                                          # noqa: E731
+    o = vo.forward(p, cfg, b["tokens"][:n], ex(g["image_feat"]), ex(g["image_loc"]), b["segments"][:n], b["positions"][:n],
+                   b["txt_attention_mask"][:n], ex(g["image_mask"]), b["co_attention_mask"][:n], masked_lm_labels=b["mask"][:n],
+                   next_sentence_label=torch.from_numpy(g["next_sentence_label"])[:n], image_label=ex(g["image_label"]),
+                   image_target=ex(g["image_target"]), nsp_weight=torch.from_numpy(g["nsp_weight"]), lm_weight=b["weights"][:n],
+                   dtype=torch.float64, drop=lambda site, x: x * keep_mask((site_seed(77, site), 0.1), tuple(x.shape)))
+    print(f"[fp16, dropout 0.1] losses {vals} vs oracle with the same masks lm {float(o['lm_loss']):.6f} nsp {float(o['nsp_loss']):.6f} "
+          f"img {float(o['img_loss']):.6f}")
+    for k in ("lm_loss", "nsp_loss", "img_loss"):
+        assert abs(vals[k] - float(o[k].detach())) < 5e-3, k
+    names = [k for k in p if k != "cls.predictions.decoder.weight"]
+    grads = dict(zip(names, torch.autograd.grad(o["lm_loss"] + o["nsp_loss"] + o["img_loss"], [p[k] for k in names], allow_unused=True)))
+    _compare_grads(ts.grad_dict(), grads, 3e-2, 1e-2, "fp16 tiny, dropout 0.1")
+    ts_off = TrainStep(cfg, sd, DeviceOps(DEV, "fp16"))
+    assert abs(ts_off.forward_backward(batch)["lm_loss"] - vals["lm_loss"]) > 1e-4            # the masks really were applied

@@ -8,12 +8,35 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 
 from unimm_b200.descriptors import dense_co_mask, dense_text_mask
 from unimm_b200.train_ops import ACT_GELU, ACT_RELU, EW_ADD, EW_AXPY, EW_MUL, EW_RELU_BWD, EW_SCALE, MASK_CO_INTERVAL, MASK_KEY_VECTOR, MASK_TEXT_SELF
 
 DT = torch.float64
+
+
+def _lowbias32(x):
+    x = x.astype(np.uint64)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846CA68B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def keep_mask(drop, shape):
+    """The keep-mask the device kernels regenerate (csrc/common.cuh: drop_keep): element i of the flattened tensor is kept iff
+    lowbias32(lowbias32(i ^ seed) + seed) >= p * 2^32; kept values are scaled by 1 / (1 - p)."""
+    seed, p = drop
+    n = int(np.prod(shape))
+    assert n < 2 ** 32
+    idx = np.arange(n, dtype=np.uint64)
+    h = _lowbias32((_lowbias32(idx ^ np.uint64(seed)) + np.uint64(seed)) & np.uint64(0xFFFFFFFF))
+    keep = h >= np.uint64(min(int(p * 4294967296.0), 0xFFFFFFFF))
+    return torch.from_numpy(keep.reshape(shape)).to(DT) / (1.0 - p)
 
 
 def _gelu(x):
@@ -104,8 +127,18 @@ class TorchOps:
         dy.copy_(d)
         return dy
 
-    def linear(self, x, w, bias, residual=None, act=0, want32=True, want16=False, pre_act32=False):
+    def dropout(self, x, drop, want16=True):
+        y = x * keep_mask(drop, x.shape)
+        return y, (y.clone() if want16 else None)
+
+    def dropout_backward(self, dy, drop):
+        dy.mul_(keep_mask(drop, dy.shape))
+        return dy
+
+    def linear(self, x, w, bias, residual=None, act=0, want32=True, want16=False, pre_act32=False, drop=None):
         y = x @ w.t() + bias
+        if drop is not None:
+            y = y * keep_mask(drop, y.shape)
         if pre_act32:
             return y, (_gelu(y) if act == ACT_GELU else torch.relu(y))
         if act == ACT_GELU:
@@ -119,8 +152,10 @@ class TorchOps:
     def linear_f32(self, x, w, bias, residual=None, act=0):
         return self.linear(x, w, bias, residual, act)[0]
 
-    def linear_backward(self, dy, x, w, g_w, g_b, need_dx=True, dx_accum=None, gelu_t=None, dx_amax=False):
+    def linear_backward(self, dy, x, w, g_w, g_b, need_dx=True, dx_accum=None, gelu_t=None, dx_amax=False, drop=None):
         assert tuple(g_w.shape) == (dy.shape[1], x.shape[1])
+        if drop is not None:
+            dy = dy * keep_mask(drop, dy.shape)
         if gelu_t is not None:
             dy = self.gelu_backward(dy.clone(), gelu_t)
         g_w.copy_(dy.t() @ x)
@@ -144,20 +179,23 @@ class TorchOps:
             m = key_mask.to(DT)[:, None, None, :].expand(B, 1, Sq, Skv)
         return (1.0 - m) * -10000.0
 
-    def _attn(self, q, k, v, B, heads, D, Sq, Skv, add):
+    def _attn(self, q, k, v, B, heads, D, Sq, Skv, add, drop=None):
         qh = q.reshape(B, Sq, heads, D).permute(0, 2, 1, 3)
         kh = k.reshape(B, Skv, heads, D).permute(0, 2, 1, 3)
         vh = v.reshape(B, Skv, heads, D).permute(0, 2, 1, 3)
         s = qh @ kh.transpose(-1, -2) / math.sqrt(D) + add
-        o = torch.softmax(s, -1) @ vh
+        pr = torch.softmax(s, -1)
+        if drop is not None:
+            pr = pr * keep_mask(drop, (B, heads, Sq, Skv))
+        o = pr @ vh
         return o.permute(0, 2, 1, 3).reshape(B * Sq, heads * D), torch.logsumexp(s, -1)
 
-    def attention(self, q, k, v, B, heads, D, Sq, Skv, mask_kind, desc=None, key_mask=None):
-        return self._attn(q, k, v, B, heads, D, Sq, Skv, self._add_mask(B, Sq, Skv, mask_kind, desc, key_mask))
+    def attention(self, q, k, v, B, heads, D, Sq, Skv, mask_kind, desc=None, key_mask=None, drop=None):
+        return self._attn(q, k, v, B, heads, D, Sq, Skv, self._add_mask(B, Sq, Skv, mask_kind, desc, key_mask), drop)
 
-    def attention_backward(self, q, k, v, o, lse, dO, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv, amax_cell=None):
+    def attention_backward(self, q, k, v, o, lse, dO, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv, amax_cell=None, drop=None):
         qq, kk, vv = (t.detach().clone().requires_grad_() for t in (q, k, v))
-        oo, _ = self._attn(qq, kk, vv, B, heads, D, Sq, Skv, self._add_mask(B, Sq, Skv, mask_kind, desc, key_mask))
+        oo, _ = self._attn(qq, kk, vv, B, heads, D, Sq, Skv, self._add_mask(B, Sq, Skv, mask_kind, desc, key_mask), drop)
         a, b, c = torch.autograd.grad(oo, (qq, kk, vv), dO)
         dq.copy_(a)
         dk.copy_(b)

@@ -135,13 +135,16 @@ SYMBOLS = {
     "unimm_k_attention_cross_jobs": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P]),
     "unimm_k_attention": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     # training step
-    "unimm_k_linear_backward_acc": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, C.c_size_t, _I, _P]),
+    "unimm_k_linear_backward_acc": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, C.c_uint32, C.c_float, _P, C.c_size_t, _I,
+                                              _P]),
+    "unimm_t_dropout": (C.c_int, [_P, C.c_int64, C.c_uint32, C.c_float, _P, _P, _I, _P]),
+    "unimm_t_gemm_drop": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, C.c_uint32, C.c_float, _P, _I, _I, _P]),
     "unimm_k_layernorm_backward_amax": (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "unimm_k_gelu_backward_amax": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
-    "unimm_k_attention_lse": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "unimm_k_attention_lse": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, C.c_uint32, C.c_float, _P]),
     "unimm_k_attention_backward_scratch": (C.c_size_t, [_I, _I, _I, _I]),
     "unimm_k_attention_backward": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _P, _I,
-                                             _P, _P, _P, C.c_size_t, _P]),
+                                             _P, _P, C.c_uint32, C.c_float, _P, C.c_size_t, _P]),
     "unimm_t_embed_text_sum": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "unimm_t_embed_text_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "unimm_t_gelu": (C.c_int, [_P, C.c_int64, _P, _P, _I, _P]),

@@ -45,6 +45,8 @@ struct BwdArgs {
     const float* inv_scale;         // device: 1 / (scale applied to dO)
     float ds_shift;                 // factor applied to dS before it is rounded to 16 bits
     unsigned* amax;                 // optional: max |dq|, |dk|, |dv| written (float bits, atomicMax) for the consumer's 16-bit scale
+    DropArgs drop;                  // dropout on the probabilities in the forward: O = (P o mask / (1 - p)) V, so dP = (dO V^T) o mask / (1 - p),
+                                    //   dV = (P o mask / (1 - p))^T dO, and delta = rowsum(dO o O) as before
 };
 
 // allowed key set of query row qr: [lo, hi) U {self}, the forward's row_set (attention_mma.cu) — padding rows included, so that
@@ -190,6 +192,8 @@ attn_bwd_dq_kernel(BwdArgs a, int kv_rows) {
     const int w_end = min(((w_hi + MKT - 1) / MKT) * MKT, kv_stage);
 
     const float sl = a.scale * kLog2e;
+    const uint32_t drop_row[2] = {((static_cast<uint32_t>(b) * a.heads + h) * Sq + min(row[0], Sq - 1)) * Skv,
+                                  ((static_cast<uint32_t>(b) * a.heads + h) * Sq + min(row[1], Sq - 1)) * Skv};
     float dq[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -231,7 +235,10 @@ attn_bwd_dq_kernel(BwdArgs a, int kv_rows) {
                 const int kc = nb * 8 + 2 * t + (e & 1), key = t0 + kc;
                 const bool ok = (((key >= lo[r]) & (key < hi[r])) | (key == self[r])) & static_cast<bool>((bits >> kc) & 1ull);
                 const float p = ok ? fast_exp2(fmaf(s[nb][e], sl, -lse2[r])) : 0.f;
-                s[nb][e] = p * (dp[nb][e] - dl[r]) * a.ds_shift;
+                float dpv = dp[nb][e];
+                if (a.drop.thresh != 0u)
+                    dpv = drop_keep(a.drop.seed, drop_row[r] + static_cast<uint32_t>(key), a.drop.thresh) ? dpv * a.drop.scale : 0.f;
+                s[nb][e] = p * (dpv - dl[r]) * a.ds_shift;
             }
         }
         // dQ += dS K
@@ -333,6 +340,7 @@ attn_bwd_dkv_kernel(BwdArgs a, int q_rows) {
     for (int r = 0; r < 2; ++r) key_ok[r] = key[r] < Skv && ((s_bits[(key[r] >> 6) & 3] >> (key[r] & 63)) & 1ull);
 
     const float sl = a.scale * kLog2e;
+    const uint32_t drop_bh = (static_cast<uint32_t>(b) * a.heads + h) * Sq;
     float dk[D / 8][4], dv[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {
@@ -377,8 +385,11 @@ attn_bwd_dkv_kernel(BwdArgs a, int q_rows) {
                 const int qc = t0 + nb * 8 + 2 * t + (e & 1);
                 const bool ok = key_ok[r] & (((key[r] >= s_lo[qc]) & (key[r] < s_hi[qc])) | (key[r] == s_self[qc]));
                 const float p = ok ? fast_exp2(fmaf(s[nb][e], sl, -s_lse[qc])) : 0.f;
-                s[nb][e] = p;
-                dp[nb][e] = p * (dp[nb][e] - s_dl[qc]) * a.ds_shift;
+                float mk = 1.f;
+                if (a.drop.thresh != 0u)
+                    mk = drop_keep(a.drop.seed, (drop_bh + static_cast<uint32_t>(qc)) * Skv + static_cast<uint32_t>(key[r]), a.drop.thresh) ? a.drop.scale : 0.f;
+                s[nb][e] = p * mk;                                       // P^T after dropout: the operand of dV
+                dp[nb][e] = p * (dp[nb][e] * mk - s_dl[qc]) * a.ds_shift;
             }
         }
         // dV += P^T dO,  dK += dS^T Q   (contraction over the tile's 64 queries)
@@ -502,6 +513,8 @@ int attention_backward_lp(const AttnArgs& f, const float* dO, int lddo, const fl
     a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv;
     a.B = f.B; a.heads = f.heads; a.Sq = f.Sq; a.Skv = f.Skv; a.mask_kind = f.mask_kind; a.desc = f.desc; a.key_mask = f.key_mask;
     a.scale = f.scale; a.inv_scale = sc + 1; a.ds_shift = f.lp_kind == LP_FP16 ? 0.0625f : 1.f;
+    a.drop = f.drop;
+    UNIMM_CHECK(f.drop.thresh == 0u || static_cast<double>(f.B) * f.heads * f.Sq * f.Skv < 4294967296.0, "attention dropout: 32-bit element index");
     a.amax = reinterpret_cast<unsigned*>(amax_accum);      // NOT zeroed here: several calls may fill column blocks of one gradient matrix
     if (f.lp_kind == LP_FP16) return f.D == 64 ? run_bwd<64, true>(a, stream) : run_bwd<128, true>(a, stream);
     return f.D == 64 ? run_bwd<64, false>(a, stream) : run_bwd<128, false>(a, stream);

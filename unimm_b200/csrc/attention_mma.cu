@@ -194,6 +194,17 @@ attn_mma_kernel(AttnArgs a, int kv_rows_max) {
             l_run[0] += s[nb][0] + s[nb][1];
             l_run[1] += s[nb][2] + s[nb][3];
         }
+        if (a.drop.thresh != 0u) {          // training: dropout on the probabilities (the row sums above stay those of the full softmax)
+            const uint32_t r0i = ((static_cast<uint32_t>(b) * a.heads + h) * Sq + min(q0 + warp * 16 + g, Sq - 1)) * Skv + t0 + 2 * t;
+            const uint32_t r1i = ((static_cast<uint32_t>(b) * a.heads + h) * Sq + min(q0 + warp * 16 + g + 8, Sq - 1)) * Skv + t0 + 2 * t;
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                if (!drop_keep(a.drop.seed, r0i + nb * 8, a.drop.thresh)) s[nb][0] = 0.f;
+                if (!drop_keep(a.drop.seed, r0i + nb * 8 + 1, a.drop.thresh)) s[nb][1] = 0.f;
+                if (!drop_keep(a.drop.seed, r1i + nb * 8, a.drop.thresh)) s[nb][2] = 0.f;
+                if (!drop_keep(a.drop.seed, r1i + nb * 8 + 1, a.drop.thresh)) s[nb][3] = 0.f;
+            }
+        }
         if (__any_sync(0xffffffffu, corr[0] != 1.f || corr[1] != 1.f)) {
 #pragma unroll
             for (int i = 0; i < D / 8; ++i) {
@@ -224,8 +235,8 @@ attn_mma_kernel(AttnArgs a, int kv_rows_max) {
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
     }
-    const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
-    const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+    const float inv0 = l_run[0] > 0.f ? a.drop.scale / l_run[0] : 0.f;      // drop.scale = 1 / (1 - p), 1 without dropout
+    const float inv1 = l_run[1] > 0.f ? a.drop.scale / l_run[1] : 0.f;
     const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {

@@ -251,6 +251,29 @@ __device__ __forceinline__ bf16 lp_from_f32(float v, int kind) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Counter-based dropout (training step): element i of a tensor at one dropout site of one forward is kept iff
+// lowbias32(lowbias32(i ^ seed) + seed) >= p * 2^32 — a pure function of (seed, i), so the backward regenerates the mask instead of
+// storing it (tests/torch_train_ops.py::keep_mask is the same function in numpy).  Kept values are scaled by 1 / (1 - p).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t idx, uint32_t thresh) { return lowbias32(lowbias32(idx ^ seed) + seed) >= thresh; }
+struct DropArgs {
+    uint32_t seed = 0, thresh = 0;   // thresh = 0: dropout off
+    float scale = 1.f;               // 1 / (1 - p)
+};
+inline DropArgs make_drop(uint32_t seed, float p) {
+    DropArgs d;
+    if (p > 0.f) {
+        const double t = static_cast<double>(p) * 4294967296.0;
+        d.seed = seed; d.thresh = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t); d.scale = 1.f / (1.f - p);
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sequence descriptor: the 4 integers that regenerate every dense attention mask of the reference
 // (utils/data_utils.py:149-210 generative, :353-354 discriminative).
 //   mode      0 = generative, 1 = discriminative

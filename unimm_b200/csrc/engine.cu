@@ -1626,13 +1626,13 @@ size_t unimm_k_linear_backward_scratch(int M, int N, int K) {
 
 int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
                             float* d_dW, float* d_db, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
-    return unimm_k_linear_backward_acc(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, 0, d_dW, d_db, nullptr, nullptr, nullptr, d_scratch, scratch_bytes,
-                                       lp_kind, stream);
+    return unimm_k_linear_backward_acc(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, 0, d_dW, d_db, nullptr, nullptr, nullptr, 0u, 0.f, d_scratch,
+                                       scratch_bytes, lp_kind, stream);
 }
 
 int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
                                 int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t, float* d_dX_amax,
-                                void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
+                                uint32_t drop_seed, float drop_p, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
     UNIMM_CHECK(d_dY && d_X && d_W && d_scratch && M > 0 && N > 0 && K > 0, "bad argument");
     UNIMM_CHECK(N % 64 == 0 && K % 8 == 0 && ldy % 2 == 0, "linear backward: N must be a multiple of 64 (the dgrad contraction), K of 8");
     UNIMM_CHECK(scratch_bytes >= unimm_k_linear_backward_scratch(M, N, K), "scratch smaller than unimm_k_linear_backward_scratch()");
@@ -1651,7 +1651,8 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int
     // ... and in the same pass over dY: the bias gradient (column sums) and, when dY still has to pass the erf GELU of this projection's
     // output backwards (d_gelu_t = the saved pre-activation), that derivative (|gelu'| <= 1.13 bounds the scaled values)
     UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st, d_amax, d_gelu_t != nullptr ? 1.13f : 1.f));
-    UNIMM_TRY(cast_colsum_lp(d_dY, ldy, d_gelu_t, N, M, N, scale, dY16, N, lp_kind, d_db, st));
+    UNIMM_CHECK(drop_p <= 0.f || (d_gelu_t == nullptr && static_cast<double>(M) * N < 4294967296.0), "output dropout: not in front of a GELU; 32-bit index");
+    UNIMM_TRY(cast_colsum_lp(d_dY, ldy, d_gelu_t, N, M, N, scale, dY16, N, lp_kind, d_db, st, make_drop(drop_seed, drop_p)));
     d_db = nullptr;                                              // done
     static const bool transposed_copies = getenv("UNIMM_BWD_TRANSPOSE") != nullptr && atoi(getenv("UNIMM_BWD_TRANSPOSE")) != 0;
     if (!transposed_copies) {

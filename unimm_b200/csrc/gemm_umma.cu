@@ -502,6 +502,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { y[i].x += b4.x; y[i].y += b4.y; y[i].z += b4.z; y[i].w += b4.w; }
+                    if (ep.drop.thresh != 0u) {             // dropout on the projection's output, before the residual joins
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t i0 = static_cast<uint32_t>(r0 + 4 * i) * static_cast<uint32_t>(N) + static_cast<uint32_t>(cc);
+                            y[i].x = drop_keep(ep.drop.seed, i0, ep.drop.thresh) ? y[i].x * ep.drop.scale : 0.f;
+                            y[i].y = drop_keep(ep.drop.seed, i0 + 1u, ep.drop.thresh) ? y[i].y * ep.drop.scale : 0.f;
+                            y[i].z = drop_keep(ep.drop.seed, i0 + 2u, ep.drop.thresh) ? y[i].z * ep.drop.scale : 0.f;
+                            y[i].w = drop_keep(ep.drop.seed, i0 + 3u, ep.drop.thresh) ? y[i].w * ep.drop.scale : 0.f;
+                        }
+                    }
                     if (ep.pre_act_f32) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -568,6 +578,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) x[j] += __ldg(ep.bias + col0 + j);
+                }
+                if (ep.drop.thresh != 0u) {
+                    const uint32_t i0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(N) + static_cast<uint32_t>(col0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = drop_keep(ep.drop.seed, i0 + j, ep.drop.thresh) ? x[j] * ep.drop.scale : 0.f;
                 }
                 if (ep.pre_act_f32 && row_ok) {
                     float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
@@ -808,6 +823,9 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     UNIMM_CHECK(!ep.pre_act_f32 || (ep.out_f32 != nullptr && ep.out_bf16 != nullptr && ep.residual == nullptr && !lse && !ep.w_perm16 &&
                                     !ep.out_hilo && ep.split_k <= 1 && ep.amax_out == nullptr),
                 "pre-activation output: fp32 pre-activation + 16-bit activation, plain epilogue, no residual");
+    UNIMM_CHECK(ep.drop.thresh == 0u || (!lse && !ep.w_perm16 && !ep.out_hilo && ep.act == ACT_NONE && ep.split_k <= 1 && ep.out_f32 != nullptr &&
+                                         ep.out_bf16 == nullptr && static_cast<double>(M) * N < 4294967296.0),
+                "output dropout: plain fp32-output epilogue without activation");
     if (ep.a_mn || ep.b_mn || ep.split_k > 1) {
         UNIMM_CHECK(!lse && !ep.split3 && !ep.w_perm16 && ep.debug_mode == 0, "MN-major operands / split-K: plain epilogue only");
         UNIMM_CHECK(!ep.a_mn || ((lda & 7) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0), "MN-major A: 16-byte aligned rows");

@@ -139,7 +139,7 @@ __device__ __forceinline__ float gelu_grad_fast(float v) {
 template <bool GELU>
 __global__ void __launch_bounds__(256)
 cast_colsum_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ t, int ldt, int rows, int cols, const float* __restrict__ scale,
-                   bf16* __restrict__ y, int ldy, int lp_kind, float* __restrict__ colsum) {
+                   bf16* __restrict__ y, int ldy, int lp_kind, float* __restrict__ colsum, DropArgs drop) {
     // CTA = 64 columns x 128 rows: a warp reads 256 contiguous bytes of one row (two columns per lane), the 8 warps interleave the rows
     __shared__ float part[8][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -151,6 +151,11 @@ cast_colsum_kernel(const float* __restrict__ x, int ldx, const float* __restrict
 #pragma unroll 4
         for (int r = r0 + warp; r < r1; r += 8) {
             float2 v = *reinterpret_cast<const float2*>(x + static_cast<size_t>(r) * ldx + c);
+            if (drop.thresh != 0u) {        // the projection's output went through dropout: the same keep-mask on its gradient
+                const uint32_t i0 = static_cast<uint32_t>(r) * static_cast<uint32_t>(cols) + static_cast<uint32_t>(c);
+                v.x = drop_keep(drop.seed, i0, drop.thresh) ? v.x * drop.scale : 0.f;
+                v.y = drop_keep(drop.seed, i0 + 1u, drop.thresh) ? v.y * drop.scale : 0.f;
+            }
             if (GELU) {
                 // d/dt [t Phi(t)] = Phi(t) + t phi(t); Phi from the forward's rational fit (common.cuh gelu_fast: 3.5e-6), phi by one ex2
                 const float2 tv = *reinterpret_cast<const float2*>(t + static_cast<size_t>(r) * ldt + c);
@@ -505,12 +510,12 @@ int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream
 }
 
 int cast_colsum_lp(const float* x, int ldx, const float* gelu_t, int ldt, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind,
-                   float* colsum, cudaStream_t stream) {
+                   float* colsum, cudaStream_t stream, DropArgs drop) {
     UNIMM_CHECK(rows > 0 && cols % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && (gelu_t == nullptr || ldt % 2 == 0), "cast_colsum: even columns and leading dimensions");
     if (colsum != nullptr) UNIMM_CUDA_CHECK(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, stream));
     const dim3 grid((cols + 63) / 64, (rows + 127) / 128);
-    if (gelu_t != nullptr) cast_colsum_kernel<true><<<grid, 256, 0, stream>>>(x, ldx, gelu_t, ldt, rows, cols, scale, y, ldy, lp_kind, colsum);
-    else cast_colsum_kernel<false><<<grid, 256, 0, stream>>>(x, ldx, nullptr, 0, rows, cols, scale, y, ldy, lp_kind, colsum);
+    if (gelu_t != nullptr) cast_colsum_kernel<true><<<grid, 256, 0, stream>>>(x, ldx, gelu_t, ldt, rows, cols, scale, y, ldy, lp_kind, colsum, drop);
+    else cast_colsum_kernel<false><<<grid, 256, 0, stream>>>(x, ldx, nullptr, 0, rows, cols, scale, y, ldy, lp_kind, colsum, drop);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

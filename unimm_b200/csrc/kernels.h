@@ -56,6 +56,9 @@ struct GemmEpilogue {
     // out_f32 receives the value BEFORE the activation (acc + bias) while out_bf16 receives act(acc + bias): the training forward keeps
     // the GELU's pre-activation for the backward and feeds the next GEMM in one epilogue (no residual in this mode)
     bool pre_act_f32 = false;
+    // training forward: dropout on (acc + bias) BEFORE the residual is added (models/vilbert_dialog.py:424, :467, :553, :596, :746, :749);
+    // element index = row * N + column
+    DropArgs drop;
 };
 
 // C = A[M,K] · W[N,K]^T, bf16 operands, fp32 accumulation in TMEM (gemm_umma.cu).
@@ -148,6 +151,8 @@ struct AttnArgs {
     const float* key_mask;    // [B, Skv] (MASK_KEY_VECTOR)
     float scale;              // 1/sqrt(D)
     int lp_kind;              // encoding of 16-bit q/k/v/o (ignored by the fp32 kernel)
+    DropArgs drop;            // dropout on the attention probabilities (training; mma.sync kernel and its backward); element index
+                              //   ((b * heads + h) * Sq + q) * Skv + k
     float* lse = nullptr;     // optional [B, heads, Sq]: log sum_k exp(scale * q.k) over the allowed keys (mma.sync kernel only; saved
                               //   for attention_backward_lp)
 };
@@ -222,7 +227,7 @@ int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float al
 int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax = nullptr, float headroom = 1.f);
 // y = lp(v * scale[0]), colsum (optional, zeroed here) += v, with v = x or x * gelu'(gelu_t) (heads.cu: cast_colsum_kernel)
 int cast_colsum_lp(const float* x, int ldx, const float* gelu_t, int ldt, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind,
-                   float* colsum, cudaStream_t stream);
+                   float* colsum, cudaStream_t stream, DropArgs drop = DropArgs());
 int cast_scaled_lp(const float* x, int ldx, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind, cudaStream_t stream);
 int column_sums_f32(const float* x, int ldx, int rows, int cols, float* out, cudaStream_t stream);
 // tcgen05 LM head tail: merge the per-tile (max, sum) partials

@@ -119,6 +119,15 @@ lm_ul_value_kernel(const float* __restrict__ logp, const float* __restrict__ w, 
     if (threadIdx.x == 0) out[0] = s * scale;
 }
 
+// y = x o keep-mask / (1 - p) (forward and, applied to the gradient, backward of nn.Dropout); y32 may alias x
+__global__ void dropout_kernel(const float* x, size_t n, DropArgs d, float* y32, bf16* __restrict__ y16, int lp_kind) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = drop_keep(d.seed, static_cast<uint32_t>(i), d.thresh) ? x[i] * d.scale : 0.f;
+        if (y32 != nullptr) y32[i] = v;
+        if (y16 != nullptr) y16[i] = lp_from_f32(v, lp_kind);
+    }
+}
+
 // element-wise helpers on fp32 vectors: 0: out = a + b, 1: out = a * b, 2: out = a * [b > 0] (ReLU backward from the ReLU's output),
 // 3: out = alpha * a, 4: out = a + alpha * b
 __global__ void ew_kernel(int op, size_t n, const float* a, const float* b, float* out, float alpha) {
@@ -293,6 +302,22 @@ int unimm_t_lm_ul_value(const float* d_logp, const float* d_weight, int n, float
     return 0;
 }
 
+int unimm_t_dropout(const float* d_x, int64_t n, uint32_t seed, float p, float* d_y_f32, void* d_y_lp, int lp_kind, void* stream) {
+    UNIMM_CHECK(d_x && (d_y_f32 || d_y_lp) && n > 0 && n < (int64_t(1) << 32) && p > 0.f && p < 1.f, "dropout: 0 < p < 1, fewer than 2^32 elements");
+    dropout_kernel<<<grid_for(static_cast<size_t>(n)), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, static_cast<size_t>(n), make_drop(seed, p), d_y_f32,
+                                                                                                    static_cast<bf16*>(d_y_lp), lp_kind);
+    UNIMM_LAUNCH_CHECK(1);
+    return 0;
+}
+
+int unimm_t_gemm_drop(const void* d_A, int lda, const void* d_W, int ldw, int M, int N, int K, const float* d_bias, const float* d_residual, int ldr,
+                      uint32_t drop_seed, float drop_p, float* d_out_f32, int ldo_f32, int lp_kind, void* stream) {
+    GemmEpilogue ep;
+    ep.lp_kind = lp_kind; ep.bias = d_bias; ep.residual = d_residual; ep.ldr = ldr; ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32;
+    ep.drop = make_drop(drop_seed, drop_p);
+    return gemm_umma_bf16(static_cast<const bf16*>(d_A), lda, static_cast<const bf16*>(d_W), ldw, M, N, K, ep, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
 int unimm_t_ew(int op, int64_t n, const float* d_a, const float* d_b, float* d_out, float alpha, void* stream) {
     UNIMM_CHECK(op >= 0 && op <= 4 && n > 0 && d_a && d_out && (op == 3 || d_b), "bad argument");
     ew_kernel<<<grid_for(static_cast<size_t>(n)), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, static_cast<size_t>(n), d_a, d_b, d_out, alpha);
@@ -354,13 +379,15 @@ int unimm_t_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t 
 
 int unimm_k_attention_lse(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o, int ldo, int B, int heads,
                           int D, int Sq, int Skv, int mask_kind, const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind,
-                          float* d_lse, void* stream) {
+                          float* d_lse, uint32_t drop_seed, float drop_p, void* stream) {
     UNIMM_CHECK(lp_kind == LP_BF16 || lp_kind == LP_FP16, "attention: 16-bit tensors only");
     AttnArgs a;
     a.q = d_q; a.ldq = ldq; a.k = d_k; a.ldk = ldk; a.v = d_v; a.ldv = ldv; a.o = d_o; a.ldo = ldo;
     a.B = B; a.heads = heads; a.D = D; a.Sq = Sq; a.Skv = Skv; a.mask_kind = mask_kind;
     a.desc = reinterpret_cast<const SeqDesc*>(d_desc); a.key_mask = d_key_mask;
     a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind; a.lse = d_lse;
+    a.drop = make_drop(drop_seed, drop_p);
+    UNIMM_CHECK(drop_p <= 0.f || static_cast<double>(B) * heads * Sq * Skv < 4294967296.0, "attention dropout: 32-bit element index");
     return attention_mma_lp(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -369,14 +396,15 @@ size_t unimm_k_attention_backward_scratch(int B, int heads, int D, int Sq) { ret
 int unimm_k_attention_backward(const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, const void* d_o, int ldo,
                                const float* d_dO, const float* d_lse, int B, int heads, int D, int Sq, int Skv, int mask_kind,
                                const unimm_seq_desc_t* d_desc, const float* d_key_mask, int lp_kind, float* d_dq, int lddq, float* d_dk,
-                               int lddk, float* d_dv, int lddv, float* d_amax_accum, const float* d_dO_amax, void* d_scratch, size_t scratch_bytes,
-                               void* stream) {
+                               int lddk, float* d_dv, int lddv, float* d_amax_accum, const float* d_dO_amax, uint32_t drop_seed, float drop_p,
+                               void* d_scratch, size_t scratch_bytes, void* stream) {
     UNIMM_CHECK(lp_kind == LP_BF16 || lp_kind == LP_FP16, "attention backward: 16-bit tensors only");
     AttnArgs a;
     a.q = d_q; a.ldq = ldq; a.k = d_k; a.ldk = ldk; a.v = d_v; a.ldv = ldv; a.o = const_cast<void*>(d_o); a.ldo = ldo;
     a.B = B; a.heads = heads; a.D = D; a.Sq = Sq; a.Skv = Skv; a.mask_kind = mask_kind;
     a.desc = reinterpret_cast<const SeqDesc*>(d_desc); a.key_mask = d_key_mask;
     a.scale = 1.0f / sqrtf(static_cast<float>(D)); a.lp_kind = lp_kind;
+    a.drop = make_drop(drop_seed, drop_p);
     return attention_backward_lp(a, d_dO, heads * D, d_lse, d_dq, lddq, d_dk, lddk, d_dv, lddv, d_scratch, scratch_bytes,
                                  static_cast<cudaStream_t>(stream), d_amax_accum, d_dO_amax);
 }

@@ -138,7 +138,21 @@ class DeviceOps:
         return dy
 
     # ------------------------------------------------------------------ projections
-    def linear(self, x16, w16, bias, residual=None, act=ACT_NONE, want32=True, want16=False, pre_act32=False):
+    def dropout(self, x32, drop, want16=True):
+        """nn.Dropout with the counter-based mask of ``drop = (seed, p)`` -> (y32, y16 | None)."""
+        seed, p = drop
+        y32 = self.empty32(*x32.shape)
+        y16 = self.empty16(*x32.shape) if want16 else None
+        check(lib.unimm_t_dropout(ptr(x32), x32.numel(), seed, float(p), ptr(y32), ptr(y16), self.kind, self.stream))
+        return y32, y16
+
+    def dropout_backward(self, dy32, drop):
+        seed, p = drop
+        assert dy32.is_contiguous()
+        check(lib.unimm_t_dropout(ptr(dy32), dy32.numel(), seed, float(p), ptr(dy32), None, self.kind, self.stream))
+        return dy32
+
+    def linear(self, x16, w16, bias, residual=None, act=ACT_NONE, want32=True, want16=False, pre_act32=False, drop=None):
         """y = act(x W^T + b) (+ residual) on tcgen05 -> (y32 | None, y16 | None); ``pre_act32``: y32 = x W^T + b (the activation's input, kept
         for the backward) while y16 = act(...)."""
         if pre_act32:
@@ -146,6 +160,12 @@ class DeviceOps:
             act = act | 0x100
         M, K = x16.shape
         N = w16.shape[0]
+        if drop is not None:          # out = dropout(x W^T + b) + residual: the mask is applied in the GEMM epilogue
+            assert act == ACT_NONE and want32 and not want16
+            y32 = self.empty32(M, N)
+            check(lib.unimm_t_gemm_drop(ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(bias), ptr(residual),
+                                        _ld(residual) if residual is not None else 0, drop[0], float(drop[1]), ptr(y32), N, self.kind, self.stream))
+            return y32, None
         y32 = self.empty32(M, N) if want32 else None
         y16 = self.empty16(M, N) if want16 else None
         check(lib.unimm_k_gemm_lp(ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(bias), ptr(residual), _ld(residual) if residual is not None else 0,
@@ -161,7 +181,7 @@ class DeviceOps:
                                    act, ptr(y), N, self.stream))
         return y
 
-    def linear_backward(self, dy32, x16, w16, g_w, g_b, need_dx=True, dx_accum=None, gelu_t=None, dx_amax=False):
+    def linear_backward(self, dy32, x16, w16, g_w, g_b, need_dx=True, dx_accum=None, gelu_t=None, dx_amax=False, drop=None):
         """dgrad / wgrad / bias gradient of y = x W^T + b.  ``g_w`` [N, K] / ``g_b`` [N] receive the parameter gradients; returns dX
         (``dx_accum`` += dY W when given).  ``gelu_t``: the projection feeds the erf GELU and ``dy32`` is the gradient with respect to
         the GELU's output — the derivative at the saved pre-activation ``gelu_t`` is applied on the fly.  ``dx_amax``: the dgrad GEMM
@@ -180,21 +200,23 @@ class DeviceOps:
             cell = None
         out_cell = self.empty32(1) if (dx_amax and need_dx) else None
         check(lib.unimm_k_linear_backward_acc(ptr(dy32), N, ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(dx), 1 if dx_accum is not None else 0,
-                                              ptr(g_w), ptr(g_b), ptr(cell), ptr(gelu_t), ptr(out_cell), ptr(sc), nbytes, self.kind, self.stream))
+                                              ptr(g_w), ptr(g_b), ptr(cell), ptr(gelu_t), ptr(out_cell), drop[0] if drop else 0, float(drop[1]) if drop else 0.0,
+                                              ptr(sc), nbytes, self.kind, self.stream))
         if out_cell is not None:
             self.register_amax(dx, out_cell)
         return dx
 
     # ------------------------------------------------------------------ attention
-    def attention(self, q16, k16, v16, B, heads, D, Sq, Skv, mask_kind, desc=None, key_mask=None):
+    def attention(self, q16, k16, v16, B, heads, D, Sq, Skv, mask_kind, desc=None, key_mask=None, drop=None):
         """-> (context 16-bit [B*Sq, heads*D], lse fp32 [B, heads, Sq])."""
         o = self.empty16(B * Sq, heads * D)
         lse = self.empty32(B, heads, Sq)
         check(lib.unimm_k_attention_lse(ptr(q16), _ld(q16), ptr(k16), _ld(k16), ptr(v16), _ld(v16), ptr(o), heads * D, B, heads, D, Sq, Skv, mask_kind,
-                                        ptr(desc), ptr(key_mask), self.kind, ptr(lse), self.stream))
+                                        ptr(desc), ptr(key_mask), self.kind, ptr(lse), drop[0] if drop else 0, float(drop[1]) if drop else 0.0, self.stream))
         return o, lse
 
-    def attention_backward(self, q16, k16, v16, o16, lse, dO32, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv, amax_cell=None):
+    def attention_backward(self, q16, k16, v16, o16, lse, dO32, B, heads, D, Sq, Skv, mask_kind, desc, key_mask, dq, dk, dv, amax_cell=None,
+                           drop=None):
         """dq / dk / dv: fp32 2-D views (column blocks of the projections' gradient matrices) that receive the result; ``amax_cell``
         (``new_amax_cell``) accumulates max |result| for ``register_amax`` on those matrices."""
         assert dO32.is_contiguous()
@@ -205,7 +227,8 @@ class DeviceOps:
             known = None
         check(lib.unimm_k_attention_backward(ptr(q16), _ld(q16), ptr(k16), _ld(k16), ptr(v16), _ld(v16), ptr(o16), _ld(o16), ptr(dO32), ptr(lse), B,
                                              heads, D, Sq, Skv, mask_kind, ptr(desc), ptr(key_mask), self.kind, ptr(dq), _ld(dq), ptr(dk), _ld(dk),
-                                             ptr(dv), _ld(dv), ptr(amax_cell), ptr(known), ptr(sc), nbytes, self.stream))
+                                             ptr(dv), _ld(dv), ptr(amax_cell), ptr(known), drop[0] if drop else 0, float(drop[1]) if drop else 0.0, ptr(sc),
+                                             nbytes, self.stream))
 
     # ------------------------------------------------------------------ heads / losses
     def lm_head_loss_backward(self, h16, e16, bias, labels_i32, weight32, grad_scale, g_e, g_bias):

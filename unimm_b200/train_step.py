@@ -29,6 +29,8 @@ from __future__ import annotations
 from collections import OrderedDict
 from typing import Dict, Optional
 
+import zlib
+
 import numpy as np
 import torch
 
@@ -60,6 +62,12 @@ def param_group(name: str, unused=()) -> int:
         return 4
     nd = any(s in name for s in NO_DECAY)
     return (0 if is_language_weight(name) else 2) + (1 if nd else 0)
+
+
+def site_seed(base: int, site: str) -> int:
+    """32-bit seed of one dropout call site for one forward: the keep-mask of element i is a pure function of (this seed, i)
+    (``drop_keep`` in csrc/common.cuh), so the backward regenerates it instead of storing it."""
+    return (zlib.crc32(site.encode()) ^ ((int(base) * 2654435761) & 0xFFFFFFFF)) & 0xFFFFFFFF
 
 
 def warmup_linear_nonzero(step: int, base_lr: float, warmup_steps: int = 10000, t_total: int = 200000, min_lr: float = 1e-5) -> float:
@@ -163,7 +171,8 @@ class TrainStep:
 
     def __init__(self, cfg: ViLBertConfig, state_dict: Dict[str, torch.Tensor], ops, lr: float = 2e-5, image_lr: float = 2e-5,
                  weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-6, lm_coeff: float = 1.0, nsp_coeff: float = 1.0,
-                 img_coeff: float = 1.0, warmup_steps: int = 10000, t_total: int = 200000, batch_multiply: int = 1, process_group=None):
+                 img_coeff: float = 1.0, warmup_steps: int = 10000, t_total: int = 200000, batch_multiply: int = 1, process_group=None,
+                 dropout: float = 0.0, seed: int = 0):
         cfg.validate()
         self.cfg, self.ops = cfg, ops
         # a loss whose coefficient is 0 is not part of ``loss`` at all (dense_annotation_finetuning.py:289-293 drops the image term):
@@ -183,6 +192,10 @@ class TrainStep:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.iter_id, self._acc = 0, None
+        # every nn.Dropout of the reference's training mode (hidden 0.1, attention probabilities 0.1, the fused pooled vector 0.1:
+        # models/vilbert_dialog.py:355, :405, :424, :467, :534, :553, :596, :693, :716, :746, :749, :1065, :1491) with ONE probability;
+        # 0 = the reference in eval mode.  Masks are counter-based (site, forward number, element index), regenerated in the backward.
+        self.dropout, self.seed, self._forwards, self._seed_base = float(dropout), int(seed), 0, 0
         self.opt_step = 0            # AdamW state['step']
         self.sched_step = 0          # scheduler.last_epoch
         self.S, self.R = None, None
@@ -240,22 +253,26 @@ class TrainStep:
             d["relevance"] = up(rel, fdt)
         return d
 
+    def _drop(self, site: str):
+        return None if self.dropout <= 0.0 else (site_seed(self._seed_base, site), self.dropout)
+
     # ------------------------------------------------------------------ layer pieces (forward saves, backward consumes)
     def _ffn_fwd(self, x32, x16, p_int, p_out, sv):
         """intermediate.dense -> erf-GELU -> output.dense (+ x) -> LayerNorm  (models/vilbert_dialog.py:452-469)."""
         ops, P = self.ops, self.params
         # one epilogue: the pre-activation in fp32 (kept for the backward) and GELU of it as the 16-bit operand of the next GEMM
         t, g16 = ops.linear(x16, P.P16(p_int + ".dense.weight"), P.P(p_int + ".dense.bias"), act=ACT_GELU, want16=True, pre_act32=True)
-        pre, _ = ops.linear(g16, P.P16(p_out + ".dense.weight"), P.P(p_out + ".dense.bias"), residual=x32)
+        d_out = self._drop(p_out)
+        pre, _ = ops.linear(g16, P.P16(p_out + ".dense.weight"), P.P(p_out + ".dense.bias"), residual=x32, drop=d_out)
         y32, y16 = ops.layernorm(pre, P.P(p_out + ".LayerNorm.weight"), P.P(p_out + ".LayerNorm.bias"))
-        sv.update(ffn_x16=x16, ffn_t=t, ffn_g16=g16, ffn_pre=pre)
+        sv.update(ffn_x16=x16, ffn_t=t, ffn_g16=g16, ffn_pre=pre, ffn_drop=d_out)
         return y32, y16
 
     def _ffn_bwd(self, dy, p_int, p_out, sv):
         ops, P = self.ops, self.params
         d_pre = ops.layernorm_backward(dy, sv["ffn_pre"], P.P(p_out + ".LayerNorm.weight"), P.G(p_out + ".LayerNorm.weight"), P.G(p_out + ".LayerNorm.bias"))
         dg = ops.linear_backward(d_pre, sv["ffn_g16"], P.P16(p_out + ".dense.weight"), P.G(p_out + ".dense.weight"), P.G(p_out + ".dense.bias"),
-                                 dx_amax=True)
+                                 dx_amax=True, drop=sv["ffn_drop"])
         # GELU' is applied inside the pass that turns dg into the 16-bit operand of the next two GEMMs.  The residual branch's gradient
         # is d_pre itself: the FFN branch is accumulated onto it.
         return ops.linear_backward(dg, sv["ffn_x16"], P.P16(p_int + ".dense.weight"), P.G(p_int + ".dense.weight"), P.G(p_int + ".dense.bias"),
@@ -270,10 +287,11 @@ class TrainStep:
         wqkv = P.span(P.p16, a + "self.query.weight", a + "self.value.weight")
         bqkv = P.span(P.p, a + "self.query.bias", a + "self.value.bias")
         _, qkv16 = ops.linear(x16, wqkv, bqkv, want32=False, want16=True)
-        ctx16, lse = ops.attention(qkv16[:, :H], qkv16[:, H:2 * H], qkv16[:, 2 * H:], B, heads, D, S, S, mask_kind, desc, key_mask)
-        pre1, _ = ops.linear(ctx16, P.P16(a + "output.dense.weight"), P.P(a + "output.dense.bias"), residual=x32)
+        d_probs, d_att = self._drop(a + "probs"), self._drop(a + "output")
+        ctx16, lse = ops.attention(qkv16[:, :H], qkv16[:, H:2 * H], qkv16[:, 2 * H:], B, heads, D, S, S, mask_kind, desc, key_mask, drop=d_probs)
+        pre1, _ = ops.linear(ctx16, P.P16(a + "output.dense.weight"), P.P(a + "output.dense.bias"), residual=x32, drop=d_att)
         y1, y1_16 = ops.layernorm(pre1, P.P(a + "output.LayerNorm.weight"), P.P(a + "output.LayerNorm.bias"))
-        sv.update(x16=x16, qkv16=qkv16, ctx16=ctx16, lse=lse, pre1=pre1, dims=(B, S, heads, D, H, mask_kind))
+        sv.update(x16=x16, qkv16=qkv16, ctx16=ctx16, lse=lse, pre1=pre1, dims=(B, S, heads, D, H, mask_kind), drop_probs=d_probs, drop_att=d_att)
         return self._ffn_fwd(y1, y1_16, p + "intermediate", p + "output", sv)
 
     def _self_layer_bwd(self, p, dy, desc, key_mask, sv):
@@ -284,11 +302,11 @@ class TrainStep:
         d_pre1 = ops.layernorm_backward(dy1, sv["pre1"], P.P(a + "output.LayerNorm.weight"), P.G(a + "output.LayerNorm.weight"),
                                         P.G(a + "output.LayerNorm.bias"))
         dctx = ops.linear_backward(d_pre1, sv["ctx16"], P.P16(a + "output.dense.weight"), P.G(a + "output.dense.weight"), P.G(a + "output.dense.bias"),
-                                   dx_amax=True)
+                                   dx_amax=True, drop=sv["drop_att"])
         qkv16 = sv["qkv16"]
         dqkv, cell = ops.empty32(qkv16.shape[0], 3 * H), ops.new_amax_cell()
         ops.attention_backward(qkv16[:, :H], qkv16[:, H:2 * H], qkv16[:, 2 * H:], sv["ctx16"], sv["lse"], dctx, B, heads, D, S, S, mask_kind, desc,
-                               key_mask, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], cell)
+                               key_mask, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], cell, drop=sv["drop_probs"])
         ops.register_amax(dqkv, cell)
         wqkv = P.span(P.p16, a + "self.query.weight", a + "self.value.weight")
         return ops.linear_backward(dqkv, sv["x16"], wqkv, P.span(P.g, a + "self.query.weight", a + "self.value.weight"),
@@ -306,15 +324,18 @@ class TrainStep:
         _, qkv2 = ops.linear(xt16, P.span(P.p16, b + "query2.weight", b + "value2.weight"), P.span(P.p, b + "query2.bias", b + "value2.bias"),
                              want32=False, want16=True)
         # text queries over image keys (image padding mask), image queries over text keys (co-attention interval)
-        ctx_t, lse_t = ops.attention(qkv2[:, :Hb], qkv1[:, Hb:2 * Hb], qkv1[:, 2 * Hb:], B, heads, D, S, R, MASK_KEY_VECTOR, None, inp["img_mask"])
-        ctx_v, lse_v = ops.attention(qkv1[:, :Hb], qkv2[:, Hb:2 * Hb], qkv2[:, 2 * Hb:], B, heads, D, R, S, MASK_CO_INTERVAL, inp["desc"], None)
         o = p + "biOutput."
-        pre_v, _ = ops.linear(ctx_v, P.P16(o + "dense1.weight"), P.P(o + "dense1.bias"), residual=xv32)
+        dr = {k: self._drop(n) for k, n in (("p1", b + "probs1"), ("p2", b + "probs2"), ("d1", o + "dense1"), ("d2", o + "dense2"))}
+        ctx_t, lse_t = ops.attention(qkv2[:, :Hb], qkv1[:, Hb:2 * Hb], qkv1[:, 2 * Hb:], B, heads, D, S, R, MASK_KEY_VECTOR, None, inp["img_mask"],
+                                     drop=dr["p1"])
+        ctx_v, lse_v = ops.attention(qkv1[:, :Hb], qkv2[:, Hb:2 * Hb], qkv2[:, 2 * Hb:], B, heads, D, R, S, MASK_CO_INTERVAL, inp["desc"], None,
+                                     drop=dr["p2"])
+        pre_v, _ = ops.linear(ctx_v, P.P16(o + "dense1.weight"), P.P(o + "dense1.bias"), residual=xv32, drop=dr["d1"])
         av32, av16 = ops.layernorm(pre_v, P.P(o + "LayerNorm1.weight"), P.P(o + "LayerNorm1.bias"))
-        pre_t, _ = ops.linear(ctx_t, P.P16(o + "dense2.weight"), P.P(o + "dense2.bias"), residual=xt32)
+        pre_t, _ = ops.linear(ctx_t, P.P16(o + "dense2.weight"), P.P(o + "dense2.bias"), residual=xt32, drop=dr["d2"])
         at32, at16 = ops.layernorm(pre_t, P.P(o + "LayerNorm2.weight"), P.P(o + "LayerNorm2.bias"))
         sv.update(xv16=xv16, xt16=xt16, qkv1=qkv1, qkv2=qkv2, ctx_t=ctx_t, lse_t=lse_t, ctx_v=ctx_v, lse_v=lse_v, pre_v=pre_v, pre_t=pre_t,
-                  v={}, t={})
+                  v={}, t={}, dr=dr)
         yv32, yv16 = self._ffn_fwd(av32, av16, p + "v_intermediate", p + "v_output", sv["v"])
         yt32, yt16 = self._ffn_fwd(at32, at16, p + "t_intermediate", p + "t_output", sv["t"])
         return yv32, yv16, yt32, yt16
@@ -329,20 +350,22 @@ class TrainStep:
         if dyv is not None:
             dav = self._ffn_bwd(dyv, p + "v_intermediate", p + "v_output", sv["v"])
             dxv = ops.layernorm_backward(dav, sv["pre_v"], P.P(o + "LayerNorm1.weight"), P.G(o + "LayerNorm1.weight"), P.G(o + "LayerNorm1.bias"))
-            dctx_v = ops.linear_backward(dxv, sv["ctx_v"], P.P16(o + "dense1.weight"), P.G(o + "dense1.weight"), P.G(o + "dense1.bias"), dx_amax=True)
+            dctx_v = ops.linear_backward(dxv, sv["ctx_v"], P.P16(o + "dense1.weight"), P.G(o + "dense1.weight"), P.G(o + "dense1.bias"), dx_amax=True,
+                                         drop=sv["dr"]["d1"])
         dat = self._ffn_bwd(dyt, p + "t_intermediate", p + "t_output", sv["t"])
         dxt = ops.layernorm_backward(dat, sv["pre_t"], P.P(o + "LayerNorm2.weight"), P.G(o + "LayerNorm2.weight"), P.G(o + "LayerNorm2.bias"))
-        dctx_t = ops.linear_backward(dxt, sv["ctx_t"], P.P16(o + "dense2.weight"), P.G(o + "dense2.weight"), P.G(o + "dense2.bias"), dx_amax=True)
+        dctx_t = ops.linear_backward(dxt, sv["ctx_t"], P.P16(o + "dense2.weight"), P.G(o + "dense2.weight"), P.G(o + "dense2.bias"), dx_amax=True,
+                                     drop=sv["dr"]["d2"])
         qkv1, qkv2 = sv["qkv1"], sv["qkv2"]
         dqkv1, dqkv2 = ops.empty32(qkv1.shape[0], 3 * Hb), ops.empty32(qkv2.shape[0], 3 * Hb)
         cell = ops.new_amax_cell()         # one bound for both matrices: each of the two attentions fills column blocks of both
         ops.attention_backward(qkv2[:, :Hb], qkv1[:, Hb:2 * Hb], qkv1[:, 2 * Hb:], sv["ctx_t"], sv["lse_t"], dctx_t, B, heads, D, S, R,
-                               MASK_KEY_VECTOR, None, inp["img_mask"], dqkv2[:, :Hb], dqkv1[:, Hb:2 * Hb], dqkv1[:, 2 * Hb:], cell)
+                               MASK_KEY_VECTOR, None, inp["img_mask"], dqkv2[:, :Hb], dqkv1[:, Hb:2 * Hb], dqkv1[:, 2 * Hb:], cell, drop=sv["dr"]["p1"])
         if dctx_v is None:              # no gradient reaches the image stream's output of this layer (cannot happen with the NSP / image losses on)
             dctx_v = ops.zeros32(qkv1.shape[0], Hb)
             dxv = ops.zeros32(qkv1.shape[0], sv["xv16"].shape[1])
         ops.attention_backward(qkv1[:, :Hb], qkv2[:, Hb:2 * Hb], qkv2[:, 2 * Hb:], sv["ctx_v"], sv["lse_v"], dctx_v, B, heads, D, R, S,
-                               MASK_CO_INTERVAL, inp["desc"], None, dqkv1[:, :Hb], dqkv2[:, Hb:2 * Hb], dqkv2[:, 2 * Hb:], cell)
+                               MASK_CO_INTERVAL, inp["desc"], None, dqkv1[:, :Hb], dqkv2[:, Hb:2 * Hb], dqkv2[:, 2 * Hb:], cell, drop=sv["dr"]["p2"])
         ops.register_amax(dqkv1, cell)
         ops.register_amax(dqkv2, cell)
         dxv = ops.linear_backward(dqkv1, sv["xv16"], P.span(P.p16, b + "query1.weight", b + "value1.weight"),
@@ -386,6 +409,8 @@ class TrainStep:
         if image_head is None:
             image_head = self.coeff[2] != 0
         ops.begin_step()
+        self._seed_base = self.seed + self._forwards            # a fresh set of dropout masks per forward
+        self._forwards += 1
         B, S, R = inp["B"], inp["S"], inp["R"]
         P.g.zero_()
         saved = []
@@ -394,6 +419,9 @@ class TrainStep:
         e_sum = ops.embed_text_sum(inp["ids"], inp["seg"], inp["pos"], P.P(e + "word_embeddings.weight"), P.P(e + "position_embeddings.weight"),
                                    P.P(e + "token_type_embeddings.weight"), P.P(e + "token_type_embeddings_extension.weight"), cfg.type_vocab_size)
         xt32, xt16 = ops.layernorm(e_sum, P.P(e + "LayerNorm.weight"), P.P(e + "LayerNorm.bias"))
+        d_emb_t, d_emb_v = self._drop("emb.txt"), self._drop("emb.img")
+        if d_emb_t is not None:
+            xt32, xt16 = ops.dropout(xt32, d_emb_t)
         ve = "bert.v_embeddings."
         feat32 = ops.gather_rows(inp["feat"], inp["img_row_of"])                      # one block per image -> one per sequence
         feat16 = ops.to_lp(feat32)
@@ -402,6 +430,8 @@ class TrainStep:
         loc_term = ops.linear_f32(inp["loc64"], P.P(ve + "image_location_embeddings.weight"), P.P(ve + "image_location_embeddings.bias"))   # K padded 5 -> 64
         v_sum, _ = ops.linear(feat16, P.P16(ve + "image_embeddings.weight"), P.P(ve + "image_embeddings.bias"), residual=loc_term)
         xv32, xv16 = ops.layernorm(v_sum, P.P(ve + "LayerNorm.weight"), P.P(ve + "LayerNorm.bias"))
+        if d_emb_v is not None:
+            xv32, xv16 = ops.dropout(xv32, d_emb_v)
         # ---- encoder (:842-929)
         for kind, i in cfg.layer_schedule():
             sv = {"kind": kind, "i": i}
@@ -415,7 +445,7 @@ class TrainStep:
                 xv32, xv16, xt32, xt16 = self._conn_layer_fwd(f"bert.encoder.c_layer.{i}.", xv32, xv16, xt32, xt16, inp, sv)
             saved.append(sv)
         st = {"inp": inp, "saved": saved, "e_sum": e_sum, "v_sum": v_sum, "feat16": feat16, "loc16": loc16, "xv16": xv16, "handles": [],
-              "reduced": []}
+              "reduced": [], "drop_emb": (d_emb_t, d_emb_v)}
         out = {}
         # ---- masked-LM head + likelihood / unlikelihood loss (:982-986, :1023-1026, :1577-1595), labelled rows only.  The fused vocabulary
         # kernel is forward AND backward of the decoder + loss in one: it runs here with the loss's own normalisation (1 / #weighted tokens)
@@ -438,10 +468,13 @@ class TrainStep:
         pt = ops.linear_f32(cls_t, P.P("bert.t_pooler.dense.weight"), P.P("bert.t_pooler.dense.bias"), act=ACT_RELU)
         pv = ops.linear_f32(cls_v, P.P("bert.v_pooler.dense.weight"), P.P("bert.v_pooler.dense.bias"), act=ACT_RELU)
         fused = ops.mul(pt, pv)
+        d_pool = self._drop("nsp.pooled")
+        if d_pool is not None:
+            fused, _ = ops.dropout(fused, d_pool, want16=False)
         nsp_logits = ops.linear_f32(fused, P._view(P.p, "cls.bi_seq_relationship.weight", padded=False),
                                     P._view(P.p, "cls.bi_seq_relationship.bias", padded=False))
         out["nsp_loss"], d_nsp = ops.nsp_ce(nsp_logits, inp["nsl"], inp["nsp_weight"], 1.0)
-        st.update(nsp=(cls_t, cls_v, pt, pv, fused, nsp_logits, d_nsp))
+        st.update(nsp=(cls_t, cls_v, pt, pv, fused, nsp_logits, d_nsp), drop_pool=d_pool)
         # ---- image head + masked KL (:1085-1088, :1569-1574)
         if image_head:
             ih = "cls.imagePredictions."
@@ -490,6 +523,8 @@ class TrainStep:
         d_nsp64[:, :2].copy_(d_nsp)
         dfused = ops.linear_backward(d_nsp64, ops.to_lp(fused), P.P16("cls.bi_seq_relationship.weight"), P.G("cls.bi_seq_relationship.weight"),
                                      P.G("cls.bi_seq_relationship.bias"))
+        if st["drop_pool"] is not None:
+            ops.dropout_backward(dfused, st["drop_pool"])
         dpt, dpv = ops.relu_backward(ops.mul(dfused, pv), pt), ops.relu_backward(ops.mul(dfused, pt), pv)
         dcls_t = ops.linear_backward(dpt, ops.to_lp(cls_t), P.P16("bert.t_pooler.dense.weight"), P.G("bert.t_pooler.dense.weight"),
                                      P.G("bert.t_pooler.dense.bias"))
@@ -522,6 +557,9 @@ class TrainStep:
             sv.clear()
             self._reduce_async(prefix, st)
         # ---- embeddings
+        if st["drop_emb"][0] is not None:
+            ops.dropout_backward(d_xt, st["drop_emb"][0])
+            ops.dropout_backward(d_xv, st["drop_emb"][1])
         d_esum = ops.layernorm_backward(d_xt, st["e_sum"], P.P(e + "LayerNorm.weight"), P.G(e + "LayerNorm.weight"), P.G(e + "LayerNorm.bias"))
         ops.embed_text_backward(d_esum, inp["ids"], inp["seg"], inp["pos"], P.G(e + "word_embeddings.weight"), P.G(e + "position_embeddings.weight"),
                                 P.G(e + "token_type_embeddings.weight"), P.G(e + "token_type_embeddings_extension.weight"), cfg.type_vocab_size)
