@@ -424,7 +424,7 @@ def main_train_step(args):
         b["nsp_weight"] = torch.tensor([5.0, 1.0]).pin_memory()
         batches.append(b)
     B = batches[0]["tokens"].shape[0]
-    ts = TrainStep(cfg, random_state_dict(cfg, 0), DeviceOps(dev, args.precision))
+    ts = TrainStep(cfg, random_state_dict(cfg, 0), DeviceOps(dev, args.precision), dropout=args.dropout, seed=1 + rank)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -491,7 +491,8 @@ def main_train_step(args):
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "configs[2] as a full TRAINING step: train.py UniMM-UL, batch 240 = 40 images x 6 sequences (1 positive + 5 "
                                    "negatives), mixed generative / discriminative masks, mask_prob 0.15, unlikelihood on the negatives; forward + "
-                                   "3 losses + backward + AdamW (4 parameter groups, 250 M parameters); dropout off",
+                                   "3 losses + backward + AdamW (4 parameter groups, 250 M parameters); dropout %g at every nn.Dropout site of the reference "
+                                   "(hidden states, attention probabilities, pooled vector)" % args.dropout,
                        "sequences_per_step": B * world, "layout": "dense (256 rows per sequence)", "seq_len": 256, "regions": 37,
                        "model": "bert_base_6layer_6conect, random init (seed 0)", "inputs": "3 distinct batches in rotation, activations + "
                        "gradients of a step (%.1f GB peak) far larger than L2" % mem_gb,
@@ -863,6 +864,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="steps", choices=["steps", "sweep", "train_fwd", "train_step", "dis_nsp", "dense_ft"],
                     help="sweep = the whole configs[1] sweep, strong-scaled; train_fwd / dis_nsp / dense_ft = configs 3 / 4 / 5 at their stated sizes (1 GPU)")
     ap.add_argument("--images", type=int, default=2064, help="--workload sweep: images of the sweep")
+    ap.add_argument("--dropout", type=float, default=0.1, help="--workload train_step: dropout probability (reference config: 0.1 everywhere; 0 = eval-mode step)")
     ap.add_argument("--profile-ops", action="store_true", help="--workload train_step: add a per-operation event-timed table of one extra step")
     ap.add_argument("--no-verify", action="store_true", help="skip the per-step context-equality check of the packer")
     ap.add_argument("--no-bf16", action="store_true", help="fp16 runs: skip the nested bf16_mode measurement")

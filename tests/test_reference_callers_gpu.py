@@ -146,7 +146,7 @@ def test_reference_training_loop_body_trains_through_the_drop_in(full_cfg):
     import os
     g, b = load_golden("train6_perturbed")
     n = b["tokens"].shape[0]
-    enc = ours(full_cfg, g).enable_training("fp16")
+    enc = ours(full_cfg, g).enable_training("fp16").eval()       # eval(): dropout off, as in the fixture; gradients still flow
     assert [k for k, _ in enc.named_parameters()] == ["bert_pretrained." + k for k in golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"])
                                                       if k != "cls.predictions.decoder.weight"]
     extra = {"next_sentence_labels": torch.from_numpy(g["next_sentence_label"]).unsqueeze(0),
@@ -198,6 +198,12 @@ def test_reference_training_loop_body_trains_through_the_drop_in(full_cfg):
     got = named["bert_pretrained.cls.bi_seq_relationship.bias"].grad
     assert (got - want).abs().max().item() < 1e-5
     assert named["bert_pretrained.cls.imagePredictions.decoder.weight"].grad is None        # that loss was not part of this backward
+    # train() mode: dropout on -> a different loss on the same batch
+    enc.train()
+    loss3, *_ = REF["train"].forward(enc, loader_batch(b, extra), params, sample_size=None)
+    assert abs(loss3.item() - loss2.item()) > 1e-3
+    loss3.backward()
+    optimizer.zero_grad()
     # inference through the same module afterwards uses the UPDATED weights
     enc.eval()
     with torch.no_grad():

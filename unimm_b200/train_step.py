@@ -16,8 +16,9 @@ What replaces what
 
 Every arithmetic operation is a kernel of ``libunimm_b200.so`` reached through ``ops`` (``unimm_b200.train_ops.DeviceOps``);
 ``tests/`` substitutes a torch-fp64 statement of the same operations to check this file's orchestration against ``torch.autograd``
-of the oracle on the CPU.  Dropout (``hidden_dropout_prob`` 0.1 in training mode) is NOT applied: the step is the reference's with
-its dropout layers in eval mode.
+of the oracle on the CPU.  Dropout: ``TrainStep(dropout=0.1)`` applies the reference's training-mode ``nn.Dropout`` at every one of its call
+sites with counter-based masks that the backward regenerates (``site_seed``, csrc/common.cuh ``drop_keep``); the default 0 is the reference
+with its dropout layers in eval mode.
 
 Layout: Q | K | V weights of a layer are adjacent in the flat buffer, so the fused ``[3H, K]`` projection and its gradient are
 views; three tensors are stored padded to tensor-core friendly shapes (their padding stays exactly zero under AdamW): the NSP head

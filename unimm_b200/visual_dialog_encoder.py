@@ -9,7 +9,8 @@ Differences that are deliberate and visible:
     NSP scores) come out of a ``torch.autograd.Function`` whose backward runs the device backward of ``unimm_b200.train_step`` and hands
     every parameter its gradient, so the reference's own loop (``scaler.scale(loss).backward(); scaler.step(optimizer)``,
     train.py:453-463, dense_annotation_finetuning.py:253-300) trains through these kernels with ANY torch optimizer;
-  * dropout is the identity (the reference's ``.eval()`` behaviour), in training too;
+  * dropout is the identity on the inference paths (the reference's ``.eval()`` behaviour); the differentiable branch applies it in
+    ``train()`` mode with this library's counter-based masks (not torch's RNG stream);
   * dense masks are converted to 4-integer descriptors and verified (sequences truncated at max_seq_len included); any other
     mask pattern raises;
   * ``score()`` is the fast entry: per-sequence log-likelihoods without the [B,S,30522] logits that
@@ -90,8 +91,9 @@ class VisualDialogEncoder(nn.Module):
         self._train = None
 
     # ------------------------------------------------------------------ training (SURVEY.md 8f item 1 behind the reference's own loop)
-    def enable_training(self, precision: str = "fp16", device: Optional[int] = None):
-        """Make the loss branch differentiable.  The module's Parameters become fp32 views of the device training step's flat master
+    def enable_training(self, precision: str = "fp16", device: Optional[int] = None, dropout: float = 0.1):
+        """Make the loss branch differentiable.  ``dropout`` (the reference's 0.1 at every nn.Dropout site) is applied while the module is
+        in ``train()`` mode and not in ``eval()`` mode, as nn.Dropout behaves.  The module's Parameters become fp32 views of the device training step's flat master
         buffer (same names, shapes and values; ``requires_grad=True``), so an optimizer built from ``named_parameters()`` AFTER this call
         updates the masters in place; every training forward refreshes the 16-bit operand copies from them.  Returns ``self``."""
         from .train_ops import DeviceOps
@@ -100,6 +102,7 @@ class VisualDialogEncoder(nn.Module):
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         sd = strip_prefix({k: v.detach().cpu() for k, v in self.state_dict().items()})
         self._train = TrainStep(self.config, sd, DeviceOps(dev, precision))
+        self._train_dropout = float(dropout)
         P = self._train.params
         made, self._train_params, self._train_group = {}, [], {}
         for name in param_shapes(self.config):
@@ -121,6 +124,7 @@ class VisualDialogEncoder(nn.Module):
     def _training_forward(self, input_ids, image_feat, image_loc, token_type_ids, token_position_ids, desc, masked_lm_labels,
                           next_sentence_label, image_attention_mask, image_label, image_target, nsp_weight, lm_weight, output_nsp_scores):
         ts = self._train
+        ts.dropout = self._train_dropout if self.training else 0.0
         ts.params.refresh_lp()                                   # the optimizer wrote the fp32 masters since the last forward
         if lm_weight is None:
             raise ValueError("the device training step implements the likelihood / unlikelihood loss: pass lm_weight (train.forward does)")
