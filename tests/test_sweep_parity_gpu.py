@@ -20,13 +20,11 @@ from unimm_b200.engine import Engine  # noqa: E402
 from unimm_b200.flat_packer import FlatPacker, ImageArrays  # noqa: E402
 
 TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 2e-2}            # BASELINE.json north_star — not widened for any mode
-# Measured on these 300-candidate fixtures: fp32 3e-5, fp16 5e-3, bf16 2.0e-2 .. 2.3e-2 (maximum over the 100 candidates of a
-# round).  Real bf16 — every GEMM operand rounded once to a 7-bit mantissa, 24 layers deep, fp32 residual stream / LayerNorm /
-# softmax / log-sum-exp — sits AT the north star's 2e-2: it passes on config 1 (tests/test_parity_gpu.py: 1.7e-2 dense, 1.8e-2
-# packed) and exceeds it by 2-13 % here.  Getting reliably inside would take two MMA passes per GEMM (bf16 hi + lo weights);
-# fp16 runs the same tcgen05 instruction at the same rate and is 4x inside.  The bf16 cases below therefore stay asserted against
-# 2e-2 and are marked xfail (non-strict) instead of loosening the bound: the row "bf16 <= 2e-2" is NOT met at this shape.
-BF16_AT_BOUND = "bf16 mode measures 2.0e-2 .. 2.3e-2 on the 300-candidate fixtures: at / above the north star's 2e-2 (see the comment above)"
+# Measured on these 300-candidate fixtures (maximum over the 100 candidates of a round): fp32 3e-5, fp16 5e-3, bf16 1.1e-2 .. 1.5e-2.
+# The bf16 mode writes LayerNorm outputs — bounded by construction — and the weights of the projections that read them as fp16, and
+# everything of unbounded range (Q / K / V, attention context, GELU outputs, image features, their weights) as bf16, with an fp32
+# residual stream (engine.cu: mix16).  With bf16 for EVERY operand (UNIMM_BF16_PURE=1, round 2's first version) the same cases
+# measure 2.0e-2 .. 2.3e-2, at / above the bound; tests/bf16_rounding_study.py is the CPU study that located the error.
 _ENG = {}
 
 
@@ -41,7 +39,7 @@ def engine(cfg, seed, perturbed, precision, max_sequences):
     return _ENG[key]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", pytest.param("bf16", marks=pytest.mark.xfail(reason=BF16_AT_BOUND, strict=False))])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", ["sweep3x100_perturbed", "sweep3x100_default"])
 def test_bench_step_reproduces_reference_scores(full_cfg, name, precision):
     from oracle import visdial_metrics as om
@@ -80,6 +78,36 @@ def test_bench_step_reproduces_reference_scores(full_cfg, name, precision):
     out2 = torch.zeros(300).pin_memory()
     eng.score_packed_host(v2, out2)
     assert (out2 - out[1000:1300]).abs().max().item() < (1e-5 if precision == "fp32" else 6e-3)
+    pk.close()
+
+
+@pytest.mark.parametrize("switch", ["UNIMM_LM_HP", "UNIMM_BF16_PURE"])
+def test_bf16_switches(full_cfg, switch, monkeypatch):
+    """UNIMM_LM_HP=1: the LM head of the bf16 mode at the fp32-class precision (split3 over fp16 hi | lo planes, fed from the fp32
+    residual stream) — inside the bound, and not the same numbers as the default.  UNIMM_BF16_PURE=1: bf16 for every operand — the
+    variant the default replaced; it must still run and stay within 3e-2 (it measures 2.0e-2 .. 2.3e-2: NOT a north-star claim)."""
+    import os
+
+    from conftest import GOLDEN_DIR
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "sweep3x100_default.npz")))
+    (f, l, m), rs = syn.synth_dialog_rounds(int(g["image_id"]), rounds=tuple(int(r) for r in g["round_ids"]))
+    pk = FlatPacker()
+    view = pk.pack([ImageArrays.from_rounds(rs, f, l, m)], scores_only=True, share_first_mask=True, verify_shared=True)
+    base = torch.zeros(300).pin_memory()
+    engine(full_cfg, g["weight_seed"], g["perturbed"], "bf16", 8 * 52).score_packed_host(view, base)
+    monkeypatch.setenv(switch, "1")
+    for e in _ENG.values():
+        e.close()
+    _ENG.clear()                                               # the switches are read when the engine is created
+    out = torch.zeros(300).pin_memory()
+    engine(full_cfg, g["weight_seed"], g["perturbed"], "bf16", 8 * 52).score_packed_host(view, out)
+    for e in _ENG.values():
+        e.close()
+    _ENG.clear()
+    err = np.abs(out.numpy().reshape(3, 100) - g["seq_score"]).max()
+    print(f"[bf16, {switch}=1] max |seq_score err| {err:.3e}; max |difference from the default| {(out - base).abs().max().item():.3e}")
+    assert err < (TOL["bf16"] if switch == "UNIMM_LM_HP" else 3e-2)
+    assert (out - base).abs().max().item() > 1e-4
     pk.close()
 
 

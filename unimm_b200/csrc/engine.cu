@@ -52,6 +52,8 @@ struct Linear {
     const bf16* wlp = nullptr;   // [N,K] bf16 (bf16 mode)
     const bf16* wlp_ln = nullptr;  // [N,K] rows permuted for the LayerNorm-fused cluster GEMM (gemm_umma_ln.cu)
     const bf16* wlp_p16 = nullptr; // [N,K] rows permuted for the smem-free 16-bit-output epilogue (gemm_umma.cu)
+    int in_kind = LP_BF16;         // encoding of wlp / wlp_ln / wlp_p16, hence of the A operand this projection takes
+    const bf16* whl = nullptr;     // [N,2K] fp16 hi | lo planes kept NEXT TO the 16-bit copy (the LM head of the bf16 mode, lm_hp)
     const float* b = nullptr;    // [N]
 };
 struct LayerNormP {
@@ -200,7 +202,24 @@ struct unimm_engine {
     // tcgen05 passes into one fp32 accumulator (gemm_umma.cu split3); UNIMM_FP32_SIMT=1 keeps the CUDA-core sgemm instead
     bool tc32_ = false;
     bool tc32() const { return tc32_; }
-    int act_kind() const { return tc32() ? LP_HILO : lp_kind(); }      // what the LayerNorm / embedding kernels write next to fp32
+    // bf16 mode, mixed operand formats (mix16, the default; UNIMM_BF16_PURE=1 turns it off): a LayerNorm output is bounded by
+    // |gamma| sqrt(H - 1) + |beta| whatever the checkpoint's activations do, so its 16-bit copy — and the weights of the projections
+    // that read it (Q | K | V, FFN-1, the co-attention projections, the LM / image heads) — are fp16: same tcgen05 rate, 3 more
+    // mantissa bits.  Everything whose range is NOT bounded by construction (Q / K / V, attention context, GELU outputs, image
+    // features, and the weights multiplying them) stays bf16; the residual stream is fp32.  tcgen05 kind::f16 wants A and B in one
+    // format, so the format is a property of the projection (Linear::in_kind), and every GEMM converts on its way out.
+    bool mix16 = false;
+    int ln_kind() const { return prec == UNIMM_PREC_BF16 && mix16 ? LP_FP16 : lp_kind(); }
+    int act_kind() const { return tc32() ? LP_HILO : ln_kind(); }      // what the LayerNorm / embedding kernels write next to fp32
+    // UNIMM_LM_HP=1 (16-bit modes with the fp32 residual stream, off by default): the LM head (transform, LayerNorm, vocabulary GEMM +
+    // log-sum-exp: 5 % of a scoring step) at the fp32-class precision — the same split3 tcgen05 passes over fp16 hi | lo planes, fed
+    // from the fp32 residual stream.  A third of the PURE bf16 mode's error variance is made in this head
+    // (tests/bf16_rounding_study.py); with mix16 it buys < 10 % more for 8.5 % of the step, hence a switch and not the default.
+    bool lm_hp = false;
+    bool lm32() const { return tc32() || (lp() && lm_hp); }
+    const bf16* planes_of(const Linear& L) const { return tc32() ? L.wlp : L.whl; }
+    bf16* lm_split = nullptr;          // [Mt, 2H] planes of the gathered labelled rows (lm_hp)
+    bf16* g_h_hl = nullptr;            // [Mt, 2H] planes of the transformed rows (lm_hp)
     // dense layout in the fp32-class mode: job lists / per-row intervals built from the descriptors (attention_split.cu)
     int *dj_text = nullptr, *dj_i2t = nullptr, *dj_img = nullptr, *dj_row_iv = nullptr;
     // attention over fp16 hi | lo planes: q / k / v point at hi planes of rows `ld` wide whose lo plane lies lo_in columns further;
@@ -218,7 +237,8 @@ struct unimm_engine {
         *out = &it->second;
         return 0;
     }
-    int make_linear(const std::vector<std::string>& names, int N_each, int K, Linear* L, bool keep_f32_only = false);
+    // ln_input: the projection's A operand is a LayerNorm output (ln_kind()); otherwise an unbounded 16-bit tensor (lp_kind())
+    int make_linear(const std::vector<std::string>& names, int N_each, int K, Linear* L, bool ln_input, bool keep_f32_only = false);
     int make_ln(const std::string& name, int H, LayerNormP* ln);
     int make_ln_weight(Linear* L);
     int finalize();
@@ -261,6 +281,7 @@ struct unimm_engine {
     int conn_layer(const ConnLayer& L, int Mt, int Mv, const AttnCtx& ac, cudaStream_t st, bool image_out = true);
     int run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st);
     // d_rows == nullptr: src's rows [0, n) are the labelled rows already
+    int lm_transform_rows(const ActBuf& src, const int* d_rows, int n, cudaStream_t st);
     int lm_head_rows(const ActBuf& src, const int* d_rows, const int* d_labels, int n, cudaStream_t st);
     // n_u unique rows (of src, or src[d_urows]) serve n (row, label) entries: entry i reads unique row d_uidx[i]
     int lm_head_shared(const ActBuf& src, const int* d_urows, int n_u, const int* d_uidx, const int* d_labels, int n, cudaStream_t st);
@@ -295,8 +316,9 @@ int unimm_engine::make_ln(const std::string& name, int H, LayerNormP* ln) {
 
 // Concatenate one or more nn.Linear weights along the output dimension ([sum N, K]) and, in bf16 mode,
 // cast the packed matrix once.
-int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each, int K, Linear* L, bool keep_f32_only) {
+int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each, int K, Linear* L, bool ln_input, bool keep_f32_only) {
     const int parts = static_cast<int>(names.size());
+    L->in_kind = ln_input ? ln_kind() : lp_kind();
     L->N = N_each * parts;
     L->K = K;
     float *w = nullptr, *b = nullptr;
@@ -327,7 +349,7 @@ int unimm_engine::make_linear(const std::vector<std::string>& names, int N_each,
     if (lp() && !keep_f32_only) {
         bf16* h = nullptr;
         UNIMM_TRY(dalloc(&h, static_cast<size_t>(L->N) * K));
-        UNIMM_TRY(cast_f32_to_lp(w, h, static_cast<size_t>(L->N) * K, lp_kind(), 0));
+        UNIMM_TRY(cast_f32_to_lp(w, h, static_cast<size_t>(L->N) * K, L->in_kind, 0));
         L->wlp = h;
         if (frag_epilogue && L->N % 32 == 0 && K % 8 == 0) {
             bf16* hp = nullptr;
@@ -397,7 +419,7 @@ int unimm_engine::finalize() {
     UNIMM_TRY(get("bert.embeddings.token_type_embeddings.weight", &t, {c.type_vocab_size, H})); type_emb = t->p;
     UNIMM_TRY(get("bert.embeddings.token_type_embeddings_extension.weight", &t, {10, H})); type_ext_emb = t->p;
     UNIMM_TRY(make_ln("bert.embeddings.LayerNorm", H, &emb_ln));
-    UNIMM_TRY(make_linear({"bert.v_embeddings.image_embeddings"}, Hv, c.v_feature_size, &img_emb));
+    UNIMM_TRY(make_linear({"bert.v_embeddings.image_embeddings"}, Hv, c.v_feature_size, &img_emb, false));
     UNIMM_TRY(get("bert.v_embeddings.image_location_embeddings.weight", &t, {Hv, 5})); loc_w = t->p;
     UNIMM_TRY(get("bert.v_embeddings.image_location_embeddings.bias", &t, {Hv})); loc_b = t->p;
     UNIMM_TRY(make_ln("bert.v_embeddings.LayerNorm", Hv, &vemb_ln));
@@ -406,39 +428,39 @@ int unimm_engine::finalize() {
     for (int i = 0; i < c.num_hidden_layers; ++i) {
         const std::string p = "bert.encoder.layer." + std::to_string(i) + ".";
         SelfLayer& L = t_layers[i];
-        UNIMM_TRY(make_linear({p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, H, H, &L.qkv));
-        UNIMM_TRY(make_linear({p + "attention.output.dense"}, H, H, &L.out));
+        UNIMM_TRY(make_linear({p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, H, H, &L.qkv, true));
+        UNIMM_TRY(make_linear({p + "attention.output.dense"}, H, H, &L.out, false));
         UNIMM_TRY(make_ln(p + "attention.output.LayerNorm", H, &L.ln1));
-        UNIMM_TRY(make_linear({p + "intermediate.dense"}, I, H, &L.ffn1));
-        UNIMM_TRY(make_linear({p + "output.dense"}, H, I, &L.ffn2));
+        UNIMM_TRY(make_linear({p + "intermediate.dense"}, I, H, &L.ffn1, true));
+        UNIMM_TRY(make_linear({p + "output.dense"}, H, I, &L.ffn2, false));
         UNIMM_TRY(make_ln(p + "output.LayerNorm", H, &L.ln2));
     }
     v_layers.resize(c.v_num_hidden_layers);
     for (int i = 0; i < c.v_num_hidden_layers; ++i) {
         const std::string p = "bert.encoder.v_layer." + std::to_string(i) + ".";
         SelfLayer& L = v_layers[i];
-        UNIMM_TRY(make_linear({p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, Hv, Hv, &L.qkv));
-        UNIMM_TRY(make_linear({p + "attention.output.dense"}, Hv, Hv, &L.out));
+        UNIMM_TRY(make_linear({p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, Hv, Hv, &L.qkv, true));
+        UNIMM_TRY(make_linear({p + "attention.output.dense"}, Hv, Hv, &L.out, false));
         UNIMM_TRY(make_ln(p + "attention.output.LayerNorm", Hv, &L.ln1));
-        UNIMM_TRY(make_linear({p + "intermediate.dense"}, Iv, Hv, &L.ffn1));
-        UNIMM_TRY(make_linear({p + "output.dense"}, Hv, Iv, &L.ffn2));
+        UNIMM_TRY(make_linear({p + "intermediate.dense"}, Iv, Hv, &L.ffn1, true));
+        UNIMM_TRY(make_linear({p + "output.dense"}, Hv, Iv, &L.ffn2, false));
         UNIMM_TRY(make_ln(p + "output.LayerNorm", Hv, &L.ln2));
     }
     c_layers.resize(c.num_connections);
     for (int i = 0; i < c.num_connections; ++i) {
         const std::string p = "bert.encoder.c_layer." + std::to_string(i) + ".";
         ConnLayer& L = c_layers[i];
-        UNIMM_TRY(make_linear({p + "biattention.query1", p + "biattention.key1", p + "biattention.value1"}, Hb, Hv, &L.qkv_v));
-        UNIMM_TRY(make_linear({p + "biattention.query2", p + "biattention.key2", p + "biattention.value2"}, Hb, H, &L.qkv_t));
-        UNIMM_TRY(make_linear({p + "biOutput.dense1"}, Hv, Hb, &L.dense1));
+        UNIMM_TRY(make_linear({p + "biattention.query1", p + "biattention.key1", p + "biattention.value1"}, Hb, Hv, &L.qkv_v, true));
+        UNIMM_TRY(make_linear({p + "biattention.query2", p + "biattention.key2", p + "biattention.value2"}, Hb, H, &L.qkv_t, true));
+        UNIMM_TRY(make_linear({p + "biOutput.dense1"}, Hv, Hb, &L.dense1, false));
         UNIMM_TRY(make_ln(p + "biOutput.LayerNorm1", Hv, &L.ln1));
-        UNIMM_TRY(make_linear({p + "biOutput.dense2"}, H, Hb, &L.dense2));
+        UNIMM_TRY(make_linear({p + "biOutput.dense2"}, H, Hb, &L.dense2, false));
         UNIMM_TRY(make_ln(p + "biOutput.LayerNorm2", H, &L.ln2));
-        UNIMM_TRY(make_linear({p + "v_intermediate.dense"}, Iv, Hv, &L.v_ffn1));
-        UNIMM_TRY(make_linear({p + "v_output.dense"}, Hv, Iv, &L.v_ffn2));
+        UNIMM_TRY(make_linear({p + "v_intermediate.dense"}, Iv, Hv, &L.v_ffn1, true));
+        UNIMM_TRY(make_linear({p + "v_output.dense"}, Hv, Iv, &L.v_ffn2, false));
         UNIMM_TRY(make_ln(p + "v_output.LayerNorm", Hv, &L.v_ln));
-        UNIMM_TRY(make_linear({p + "t_intermediate.dense"}, I, H, &L.t_ffn1));
-        UNIMM_TRY(make_linear({p + "t_output.dense"}, H, I, &L.t_ffn2));
+        UNIMM_TRY(make_linear({p + "t_intermediate.dense"}, I, H, &L.t_ffn1, true));
+        UNIMM_TRY(make_linear({p + "t_output.dense"}, H, I, &L.t_ffn2, false));
         UNIMM_TRY(make_ln(p + "t_output.LayerNorm", H, &L.t_ln));
     }
     UNIMM_TRY(make_pool_linear("bert.t_pooler.dense", Hb, H, &t_pool));
@@ -446,7 +468,14 @@ int unimm_engine::finalize() {
     UNIMM_TRY(get("cls.bi_seq_relationship.weight", &t, {2, Hb})); nsp_w = t->p;
     UNIMM_TRY(get("cls.bi_seq_relationship.bias", &t, {2})); nsp_b = t->p;
 
-    UNIMM_TRY(make_linear({"cls.predictions.transform.dense"}, H, H, &lm_transform));
+    UNIMM_TRY(make_linear({"cls.predictions.transform.dense"}, H, H, &lm_transform, true));
+    if (lp() && lm_hp) {
+        UNIMM_CHECK(H % 64 == 0 && !(fuse_ln && res16), "the fp32-class LM head needs H % 64 == 0 and the fp32 residual stream");
+        bf16* h = nullptr;
+        UNIMM_TRY(dalloc(&h, static_cast<size_t>(H) * 2 * H));
+        UNIMM_TRY(split_f32_to_hilo(lm_transform.w32, H, H, H, h, 0));
+        lm_transform.whl = h;
+    }
     UNIMM_TRY(make_ln("cls.predictions.transform.LayerNorm", H, &lm_ln));
     // tied decoder (reference :1020): accept either key, insist they agree when both are present (compared below)
     {
@@ -469,8 +498,15 @@ int unimm_engine::finalize() {
         if (lp()) {
             bf16* h = nullptr;
             UNIMM_TRY(dalloc(&h, static_cast<size_t>(c.vocab_size) * H));
-            UNIMM_TRY(cast_f32_to_lp(lm_decoder.w32, h, static_cast<size_t>(c.vocab_size) * H, lp_kind(), 0));
+            lm_decoder.in_kind = ln_kind();
+            UNIMM_TRY(cast_f32_to_lp(lm_decoder.w32, h, static_cast<size_t>(c.vocab_size) * H, ln_kind(), 0));
             lm_decoder.wlp = h;
+            if (lm_hp) {
+                bf16* hl = nullptr;
+                UNIMM_TRY(dalloc(&hl, static_cast<size_t>(c.vocab_size) * 2 * H));
+                UNIMM_TRY(split_f32_to_hilo(lm_decoder.w32, H, c.vocab_size, H, hl, 0));
+                lm_decoder.whl = hl;
+            }
         } else if (tc32()) {
             bf16* h = nullptr;
             UNIMM_TRY(dalloc(&h, static_cast<size_t>(c.vocab_size) * 2 * H));
@@ -478,9 +514,9 @@ int unimm_engine::finalize() {
             lm_decoder.wlp = h;
         }
     }
-    UNIMM_TRY(make_linear({"cls.imagePredictions.transform.dense"}, Hv, Hv, &img_transform));
+    UNIMM_TRY(make_linear({"cls.imagePredictions.transform.dense"}, Hv, Hv, &img_transform, true));
     UNIMM_TRY(make_ln("cls.imagePredictions.transform.LayerNorm", Hv, &img_ln));
-    UNIMM_TRY(make_linear({"cls.imagePredictions.decoder"}, c.v_target_size, Hv, &img_decoder));
+    UNIMM_TRY(make_linear({"cls.imagePredictions.decoder"}, c.v_target_size, Hv, &img_decoder, true));
     UNIMM_TRY(make_ln_weight(&img_emb));
     for (auto& L : t_layers) { UNIMM_TRY(make_ln_weight(&L.out)); UNIMM_TRY(make_ln_weight(&L.ffn2)); }
     for (auto& L : v_layers) { UNIMM_TRY(make_ln_weight(&L.out)); UNIMM_TRY(make_ln_weight(&L.ffn2)); }
@@ -529,6 +565,7 @@ int unimm_engine::alloc_workspace() {
     UNIMM_TRY(dalloc(&g_h.f, Mt * H)); g_h.ld = H;
     if (lp()) { UNIMM_TRY(dalloc(&g_in.h, Mt * H)); UNIMM_TRY(dalloc(&g_h.h, Mt * H)); }
     if (tc32()) UNIMM_TRY(dalloc(&g_h.h, Mt * H * 2));
+    if (lp() && lm_hp) { UNIMM_TRY(dalloc(&lm_split, Mt * H * 2)); UNIMM_TRY(dalloc(&g_h_hl, Mt * H * 2)); }
     UNIMM_TRY(dalloc(&g_t1, Mt * H));
     UNIMM_TRY(dalloc(&g_labels, Mt));
     UNIMM_TRY(dalloc(&label_logit, Mt));
@@ -578,6 +615,7 @@ int unimm_engine::linear(const ActBuf& x, int M, const Linear& L, int act, const
     ep.ldr = ldr;
     ep.act = act;
     ep.lp_kind = lp_kind();
+    if (lp()) ep.in_kind = L.in_kind;
     // algorithmic bytes: A + W once, every output (and the residual) once
     const double mn = static_cast<double>(M) * L.N;
     Prof prof(this, CAT_GEMM, 2.0 * M * L.N * L.K, st,
@@ -627,7 +665,7 @@ int unimm_engine::linear_ln(const ActBuf& x, int M, const Linear& L, const float
     if (lp() && fuse_ln) {
         GemmLnEpilogue ep;
         ep.bias = L.b; ep.residual = residual; ep.ldr = ldr; ep.gamma = ln.g; ep.beta = ln.b;
-        ep.out_f32 = out.f; ep.ldo_f32 = out.ld; ep.out_lp = out.h; ep.ldo_lp = out.ld; ep.lp_kind = lp_kind();
+        ep.out_f32 = out.f; ep.ldo_f32 = out.ld; ep.out_lp = out.h; ep.ldo_lp = out.ld; ep.lp_kind = ln_kind(); ep.in_kind = L.in_kind;
         if (res16 && residual == out.f && ldr == out.ld) {   // the stream's own previous value: use (and update) its 16-bit copy only
             ep.residual = nullptr; ep.residual_lp = out.h; ep.ldr_lp = out.ld; ep.out_f32 = nullptr;
         }
@@ -985,7 +1023,7 @@ int unimm_engine::forward(const unimm_batch_t& in, const unimm_outputs_t& out, c
         UNIMM_TRY(linear(xt, Mt, lm_transform, ACT_GELU, nullptr, 0, pre_t, H, nullptr, 0, st));
         ActBuf hh;
         hh.f = pre_t; hh.h = lp() ? static_cast<bf16*>(ffn_t) : nullptr; hh.ld = H;
-        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mt) * (H), st); UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, lm_ln.g, lm_ln.b, hh.f, hh.h, lp_kind(), st)); }
+        { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (Mt) * (H), st); UNIMM_TRY(layernorm_rows(pre_t, H, Mt, H, lm_ln.g, lm_ln.b, hh.f, hh.h, ln_kind(), st)); }
         UNIMM_TRY(linear(hh, Mt, lm_decoder, ACT_NONE, nullptr, 0, out.d_prediction_scores_t, c.vocab_size, nullptr, 0, st));
     }
     return 0;
@@ -1030,26 +1068,45 @@ int unimm_engine::run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st
 }
 
 // gathered LM head (reference :982-986, :1023-1026 on the labelled rows only): fills row_logp / row_ul [n]
-int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* d_labels, int n, cudaStream_t st) {
-    const unimm_config_t& c = cfg;
-    const int H = c.hidden_size;
+// transform + LayerNorm of the LM head (reference :982-986) on n rows of src (gathered through d_rows when given): g_h.f and the
+// operand of the vocabulary GEMM (16-bit rows, or fp16 hi | lo planes in the fp32-class mode and in the bf16 mode's lm_hp head)
+int unimm_engine::lm_transform_rows(const ActBuf& src, const int* d_rows, int n, cudaStream_t st) {
+    const int H = cfg.hidden_size;
+    if (lp() && lm_hp) {
+        UNIMM_CHECK(src.f != nullptr, "fp32-class LM head: the fp32 residual stream is not live");
+        { Prof prof(this, CAT_ROWWISE, 8.0 * n * H, st); UNIMM_TRY(split_f32_to_hilo(src.f, src.ld, n, H, lm_split, st, d_rows)); }
+        GemmEpilogue ep;
+        ep.bias = lm_transform.b; ep.act = ACT_GELU_ERF; ep.lp_kind = LP_FP16; ep.split3 = 1; ep.out_f32 = g_t1; ep.ldo_f32 = H;
+        { Prof prof(this, CAT_GEMM, 2.0 * n * H * H, st); UNIMM_TRY(gemm_umma_bf16(lm_split, 2 * H, lm_transform.whl, 2 * H, n, H, H, ep, 0, 0, st)); }
+        Prof prof(this, CAT_ROWWISE, 12.0 * n * H, st);
+        return layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h_hl, LP_HILO, st);
+    }
     if (d_rows != nullptr)
         UNIMM_TRY(gather_rows(lp() ? nullptr : src.f, lp() ? src.h : nullptr, d_rows, n, H, lp() ? nullptr : g_in.f, lp() ? g_in.h : nullptr, st));
     UNIMM_TRY(linear(d_rows != nullptr ? g_in : src, n, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, act_kind(), st)); }
+    Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n) * (H), st);
+    return layernorm_rows(g_t1, H, n, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, act_kind(), st);
+}
+
+// gathered LM head (reference :982-986, :1023-1026 on the labelled rows only): fills row_logp / row_ul [n]
+int unimm_engine::lm_head_rows(const ActBuf& src, const int* d_rows, const int* d_labels, int n, cudaStream_t st) {
+    const unimm_config_t& c = cfg;
+    const int H = c.hidden_size;
+    UNIMM_TRY(lm_transform_rows(src, d_rows, n, st));
     if (lp() || tc32()) {
-        // the vocabulary GEMM with the online log-sum-exp epilogue: logits never leave TMEM / registers (fp32-class mode: the same
-        // epilogue over the three-pass accumulator)
+        // the vocabulary GEMM with the online log-sum-exp epilogue: logits never leave TMEM / registers (fp32-class mode and lm_hp:
+        // the same epilogue over the three-pass accumulator)
         GemmEpilogue ep;
         ep.bias = lm_decoder.b;
         ep.labels = d_labels;
         ep.partials = partials;
         ep.label_logit = label_logit;
-        ep.lp_kind = tc32() ? LP_FP16 : lp_kind();
-        ep.split3 = tc32() ? 1 : 0;
-        const int ld = tc32() ? 2 * H : H;
+        ep.lp_kind = lm32() ? LP_FP16 : ln_kind();
+        ep.split3 = lm32() ? 1 : 0;
+        const int ld = lm32() ? 2 * H : H;
+        const bf16* a = lm32() && !tc32() ? g_h_hl : g_h.h;
         Prof prof(this, CAT_LMHEAD, 2.0 * n * c.vocab_size * H, st);
-        UNIMM_TRY(gemm_umma_bf16(g_h.h, ld, lm_decoder.wlp, ld, n, c.vocab_size, H, ep, 256, 0, st));
+        UNIMM_TRY(gemm_umma_bf16(a, ld, lm32() ? planes_of(lm_decoder) : lm_decoder.wlp, ld, n, c.vocab_size, H, ep, 256, 0, st));
         UNIMM_TRY(lse_from_partials(partials, gemm_umma_lse_tiles(c.vocab_size), label_logit, n, row_logp, row_ul, st));
     } else {
         for (int r0 = 0; r0 < n; r0 += kLogitRows) {
@@ -1073,10 +1130,7 @@ int unimm_engine::lm_head_shared(const ActBuf& src, const int* d_urows, int n_u,
     const unimm_config_t& c = cfg;
     const int H = c.hidden_size;
     UNIMM_CHECK(lp() || tc32(), "shared labelled rows need a tensor-core mode");
-    if (d_urows != nullptr) UNIMM_TRY(gather_rows(lp() ? nullptr : src.f, lp() ? src.h : nullptr, d_urows, n_u, H, lp() ? nullptr : g_in.f,
-                                                  lp() ? g_in.h : nullptr, st));
-    UNIMM_TRY(linear(d_urows != nullptr ? g_in : src, n_u, lm_transform, ACT_GELU, nullptr, 0, g_t1, H, nullptr, 0, st));
-    { Prof prof(this, CAT_ROWWISE, (8.0 + esz()) * (n_u) * (H), st); UNIMM_TRY(layernorm_rows(g_t1, H, n_u, H, lm_ln.g, lm_ln.b, g_h.f, g_h.h, act_kind(), st)); }
+    UNIMM_TRY(lm_transform_rows(src, d_urows, n_u, st));
     UNIMM_CUDA_CHECK(cudaMemsetAsync(g_labels, 0, sizeof(int) * n_u, st));      // the fused epilogue's label pick is unused here
     {
         GemmEpilogue ep;
@@ -1084,15 +1138,16 @@ int unimm_engine::lm_head_shared(const ActBuf& src, const int* d_urows, int n_u,
         ep.labels = g_labels;
         ep.partials = partials;
         ep.label_logit = label_logit;
-        ep.lp_kind = tc32() ? LP_FP16 : lp_kind();
-        ep.split3 = tc32() ? 1 : 0;
-        const int ld = tc32() ? 2 * H : H;
+        ep.lp_kind = lm32() ? LP_FP16 : ln_kind();
+        ep.split3 = lm32() ? 1 : 0;
+        const int ld = lm32() ? 2 * H : H;
+        const bf16* a = lm32() && !tc32() ? g_h_hl : g_h.h;
         Prof prof(this, CAT_LMHEAD, 2.0 * n_u * c.vocab_size * H, st);
-        UNIMM_TRY(gemm_umma_bf16(g_h.h, ld, lm_decoder.wlp, ld, n_u, c.vocab_size, H, ep, 256, 0, st));
+        UNIMM_TRY(gemm_umma_bf16(a, ld, lm32() ? planes_of(lm_decoder) : lm_decoder.wlp, ld, n_u, c.vocab_size, H, ep, 256, 0, st));
     }
     UNIMM_TRY(lse_merge(partials, gemm_umma_lse_tiles(c.vocab_size), n_u, lse_u, st));
-    if (tc32()) UNIMM_TRY(label_scores_f32(g_h.f, H, lm_decoder.w32, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, row_logp, row_ul, st));
-    else UNIMM_TRY(label_scores(g_h.h, H, lm_decoder.wlp, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, lp_kind(), row_logp, row_ul, st));
+    if (lm32()) UNIMM_TRY(label_scores_f32(g_h.f, H, lm_decoder.w32, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, row_logp, row_ul, st));
+    else UNIMM_TRY(label_scores(g_h.h, H, lm_decoder.wlp, H, lm_decoder.b, d_uidx, d_labels, lse_u, n, H, ln_kind(), row_logp, row_ul, st));
     return 0;
 }
 
@@ -1206,6 +1261,10 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     if (const char* f = getenv("UNIMM_FP32_SIMT")) e->tc32_ = e->tc32_ && atoi(f) == 0;
     e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
     if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
+    e->mix16 = precision == UNIMM_PREC_BF16;
+    if (const char* f = getenv("UNIMM_BF16_PURE")) e->mix16 = e->mix16 && atoi(f) == 0;
+    e->lm_hp = false;
+    if (const char* f = getenv("UNIMM_LM_HP")) e->lm_hp = atoi(f) != 0 && e->lp() && !e->res16;
     *out = e;
     return 0;
 }

@@ -175,7 +175,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one() && (!SM2 || crank == 0)) {
             // bits 15 / 16 of the instruction descriptor: A / B operand is MN-major
-            const uint32_t idesc = ptx::make_idesc_f16(SM2 ? 2 * BM : BM, BN, ep.lp_kind == LP_FP16 ? 0u : 1u) | (ep.a_mn ? (1u << 15) : 0u) |
+            const uint32_t idesc = ptx::make_idesc_f16(SM2 ? 2 * BM : BM, BN, (ep.in_kind < 0 ? ep.lp_kind : ep.in_kind) == LP_FP16 ? 0u : 1u) | (ep.a_mn ? (1u << 15) : 0u) |
                                    (ep.b_mn ? (1u << 16) : 0u);
             // K-major: 16 elements along K = 32 bytes inside the swizzle atom (+2 in the addr >> 4 field); MN-major: 16 contraction
             // rows of 128 bytes = two 1024-byte groups (+128), 64-element atoms along M / N 8 KB apart (the leading byte offset)

@@ -23,6 +23,8 @@ struct GemmEpilogue {
     int act = ACT_NONE;
     int debug_mode = 0;            // microbenchmark only: 1 = row-per-thread stores, 2 = no stores, 3 = no epilogue work
     int lp_kind = LP_BF16;         // encoding of the 16-bit operands and of out_bf16 (LP_BF16 / LP_FP16)
+    int in_kind = -1;              // encoding of the A / W operands when it differs from out_bf16's (-1: lp_kind) — the bf16 mode reads
+                                   // LayerNorm outputs as fp16 and writes Q | K | V / GELU outputs as bf16
     int split3 = 0;                // fp32-class mode: A [M, 2K] and W [N, 2K] are fp16 hi | lo planes (LP_HILO); three passes per k-block
     bool out_hilo = false;         // write out_bf16 as fp16 hi | lo planes instead of one 16-bit value: hi at column c, lo at column
     int hilo_off = 0;              //   hilo_off + c of the same row (0 = N: an [M, 2N] matrix)
@@ -81,7 +83,8 @@ struct GemmLnEpilogue {
     int ldo_f32 = 0;
     bf16* out_lp = nullptr;           // [M, ldo_lp] 16-bit GEMM-operand copy (optional)
     int ldo_lp = 0;
-    int lp_kind = LP_BF16;
+    int lp_kind = LP_BF16;            // encoding of out_lp (and of residual_lp)
+    int in_kind = -1;                 // encoding of the A / W operands when it differs (-1: lp_kind)
     bool a_multicast = true;          // the cluster's CTAs share the activation box by TMA multicast (UNIMM_LN_MULTICAST=0 disables)
 };
 // W must be the row-permuted copy produced by permute_weight_rows_ln (see gemm_umma_ln.cu: the permutation makes each
