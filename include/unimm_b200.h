@@ -284,7 +284,9 @@ void unimm_reset_launch_count(void);
 /* ---- single-kernel entry points (used by tests/ to check each kernel against the oracle) ----
  * unimm_k_lm_head_lp scratch: d_partials_scratch holds rows * 2*ceil(V/256) float2, d_label_logit_scratch rows floats. */
 /* unimm_k_gemm_lp: act = 0 none, 1 GELU, 2 ReLU; act | 0x100: d_out_f32 receives the PRE-activation (acc + bias) and d_out_lp the activation
- * — the training forward keeps the GELU's input for the backward and feeds the next GEMM from one epilogue. */
+ * — the training forward keeps the GELU's input for the backward and feeds the next GEMM from one epilogue; act | 0x200: the same with
+ * the pre-activation stored as 16-bit values of lp_kind's encoding (d_out_f32 then points at a 16-bit [M, ldo_f32] matrix, ldo_f32 % 4 == 0);
+ * unimm_k_linear_backward_acc / _phase take such a matrix as d_gelu_t when called with lp_kind | 0x100. */
 int unimm_k_gemm_lp(const void* d_A_lp, int lda, const void* d_W_lp, int ldw, int M, int N, int K, const float* d_bias,
                     const float* d_residual, int ldr, int act, float* d_out_f32, int ldo_f32, void* d_out_lp, int ldo_lp,
                     int tile_n, int max_ctas, int lp_kind, void* stream);
@@ -366,6 +368,14 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X_lp, 
                                 float* d_dX, int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t,
                                 float* d_dX_amax, uint32_t drop_seed, float drop_p, void* d_scratch, size_t scratch_bytes, int lp_kind,
                                 void* stream);
+/* unimm_k_linear_backward_acc in two halves, so that the caller can put the wgrad GEMM on a second stream beside the (HBM-bound) work that
+ * follows the dgrad: phase 1 = the pass over dY (16-bit copy and scale into d_scratch, bias gradient) + dgrad; phase 2 = wgrad alone from
+ * the d_scratch a phase-1 call of the same shape filled; phase 0 = both (unimm_k_linear_backward_acc).  The caller orders the two streams
+ * (phase 2 after phase 1's pass; the scratch not reused before phase 2 has run) — autograd's stream bookkeeping in the reference. */
+int unimm_k_linear_backward_phase(const float* d_dY, int ldy, const void* d_X_lp, int ldx, const void* d_W_lp, int ldw, int M, int N, int K,
+                                  float* d_dX, int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t,
+                                  float* d_dX_amax, uint32_t drop_seed, float drop_p, void* d_scratch, size_t scratch_bytes, int lp_kind,
+                                  int phase, void* stream);
 /* unimm_k_layernorm_backward / unimm_k_gelu_backward that also leave max |dx| (float bits; zeroed first) in d_amax[0] */
 int unimm_k_layernorm_backward_amax(const float* d_dy, const float* d_x, int rows, int H, const float* d_gamma, float* d_dx, float* d_dgamma,
                                     float* d_dbeta, float* d_amax, void* stream);

@@ -22,6 +22,45 @@ from unimm_b200.train_ops import MASK_CO_INTERVAL, MASK_KEY_VECTOR, MASK_TEXT_SE
 DEV = "cuda:0"
 
 
+@pytest.mark.parametrize("precision,ulp", [("fp16", 2.0 ** -11), ("bf16", 2.0 ** -8)])
+def test_ffn1_pre_activation_kept_as_16_bit_values(precision, ulp, monkeypatch):
+    """The FFN-1 forward keeps GELU's input for the backward.  Default: as 16-bit values (the epilogue's pre_act_lp variant; the
+    backward's pass over dY reads them, cast_colsum_kernel<2>); UNIMM_PRE16=0: as fp32.  Same activation either way, the stored value
+    within one rounding, and the gradients of the projection in front of the GELU agree to the operand rounding."""
+    from unimm_b200.train_ops import ACT_GELU
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 4500, 128, 256
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    x16 = torch.randn(M, K, generator=g).to(dt).to(DEV)
+    w16 = (torch.randn(N, K, generator=g) * 0.2).to(dt).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    dy = (torch.randn(M, N, generator=g) * 1e-3).to(DEV)
+    ops16 = DeviceOps(DEV, precision)
+    monkeypatch.setenv("UNIMM_PRE16", "0")
+    ops32 = DeviceOps(DEV, precision)
+    assert ops16.pre16 and not ops32.pre16
+    t16, a16 = ops16.linear(x16, w16, bias, act=ACT_GELU, want16=True, pre_act32=True)
+    t32, a32 = ops32.linear(x16, w16, bias, act=ACT_GELU, want16=True, pre_act32=True)
+    assert t16.dtype == dt and t32.dtype == torch.float32
+    want = x16.double() @ w16.double().t() + bias.double()
+    assert (t32.double() - want).abs().max().item() < 1e-4 * want.abs().max().item()
+    assert ((t16.double() - t32.double()).abs() <= ulp * t32.double().abs() + 1e-7).all()
+    assert torch.equal(a16, a32)
+    out = []
+    for ops, t in ((ops16, t16), (ops32, t32)):
+        gw, gb = torch.empty(N, K, device=DEV), torch.empty(N, device=DEV)
+        dx = ops.linear_backward(dy.clone(), x16, w16, gw, gb, gelu_t=t)
+        out.append((dx, gw, gb))
+    torch.cuda.synchronize()
+    td = t32.double()
+    dpre = dy.double() * (0.5 * (1 + torch.erf(td / math.sqrt(2))) + td * torch.exp(-0.5 * td * td) / math.sqrt(2 * math.pi))
+    ref = (dpre @ w16.double(), dpre.t() @ x16.double(), dpre.sum(0))
+    for name, a, b, r in zip(("dX", "dW", "db"), out[0], out[1], ref):
+        e16, e32 = ((v.double() - r).abs().max().item() / r.abs().max().item() for v in (a, b))
+        print(f"[{precision}] {name}: 16-bit pre-activation {e16:.2e}, fp32 pre-activation {e32:.2e} (of the largest reference value)")
+        assert e16 < (3e-3 if precision == "fp16" else 2e-2) and e32 < (3e-3 if precision == "fp16" else 2e-2)
+
+
 def _descs():
     # generative: (mode 0, ctx, L, last_len); discriminative: (1, 0, L, 0); one truncated sequence (L + last_len > S)
     return torch.tensor([[0, 40, 47, 7], [1, 0, 93, 0], [0, 150, 153, 3], [0, 247, 252, 5], [1, 0, 256, 0]], dtype=torch.int32)

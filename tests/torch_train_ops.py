@@ -46,6 +46,9 @@ def _gelu(x):
 class TorchOps:
     precision = "fp64"
 
+    def join_side(self):            # DeviceOps orders its second (wgrad) stream here; one stream in this restatement
+        pass
+
     def begin_step(self):
         pass
 

@@ -137,6 +137,8 @@ SYMBOLS = {
     # training step
     "unimm_k_linear_backward_acc": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, C.c_uint32, C.c_float, _P, C.c_size_t, _I,
                                               _P]),
+    "unimm_k_linear_backward_phase": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, C.c_uint32, C.c_float, _P, C.c_size_t, _I,
+                                                _I, _P]),
     "unimm_t_dropout": (C.c_int, [_P, C.c_int64, C.c_uint32, C.c_float, _P, _P, _I, _P]),
     "unimm_t_gemm_drop": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _I, C.c_uint32, C.c_float, _P, _I, _I, _P]),
     "unimm_k_layernorm_backward_amax": (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -1561,7 +1561,8 @@ int unimm_k_gemm_lp(const void* d_A, int lda, const void* d_W, int ldw, int M, i
     ep.lp_kind = lp_kind;
     ep.debug_mode = tile_n / 1000;   // microbenchmark hook (scripts/gemm_bench.py): tile_n = 1000*mode + tile
     tile_n %= 1000;
-    ep.pre_act_f32 = (act & 0x100) != 0;      // act | 0x100: d_out_f32 receives the pre-activation, d_out_lp the activation (training forward)
+    ep.pre_act_f32 = (act & 0x300) != 0;      // act | 0x100: d_out_f32 receives the pre-activation, d_out_lp the activation (training forward)
+    ep.pre_act_lp = (act & 0x200) != 0;       // act | 0x200: the same, d_out_f32 pointing at a 16-bit [M, ldo_f32] matrix (lp_kind's encoding)
     act &= 0xff;
     ep.bias = d_bias; ep.residual = d_residual; ep.ldr = ldr; ep.act = act;
     ep.out_f32 = d_out_f32; ep.ldo_f32 = ldo_f32; ep.out_bf16 = static_cast<bf16*>(d_out_lp); ep.ldo_bf16 = ldo_lp;
@@ -1692,6 +1693,21 @@ int unimm_k_linear_backward(const float* d_dY, int ldy, const void* d_X, int ldx
 int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
                                 int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t, float* d_dX_amax,
                                 uint32_t drop_seed, float drop_p, void* d_scratch, size_t scratch_bytes, int lp_kind, void* stream) {
+    return unimm_k_linear_backward_phase(d_dY, ldy, d_X, ldx, d_W, ldw, M, N, K, d_dX, accumulate_dx, d_dW, d_db, d_amax, d_gelu_t, d_dX_amax, drop_seed,
+                                         drop_p, d_scratch, scratch_bytes, lp_kind, 0, stream);
+}
+
+// phase 0: everything on `stream`.  phase 1: the pass over dY (16-bit copy + scale into the scratch, bias gradient) and the dgrad GEMM.
+// phase 2: the wgrad GEMM alone, from the scratch a phase-1 call with the same shape filled — so that a caller can run it on a second
+// stream beside whatever follows the dgrad (unimm_b200/train_ops.py: the HBM-bound LayerNorm / cast passes hide under it).
+int unimm_k_linear_backward_phase(const float* d_dY, int ldy, const void* d_X, int ldx, const void* d_W, int ldw, int M, int N, int K, float* d_dX,
+                                  int accumulate_dx, float* d_dW, float* d_db, const float* d_amax, const float* d_gelu_t, float* d_dX_amax,
+                                  uint32_t drop_seed, float drop_p, void* d_scratch, size_t scratch_bytes, int lp_kind, int phase, void* stream) {
+    UNIMM_CHECK(phase >= 0 && phase <= 2, "phase: 0 = all, 1 = cast + dgrad, 2 = wgrad from the scratch");
+    const int gelu_t_kind = (lp_kind & 0x100) != 0 ? (lp_kind & 0xff) : -1;     // lp_kind | 0x100: d_gelu_t points at 16-bit values
+    lp_kind &= 0xff;
+    if (phase == 1) d_dW = nullptr;
+    if (phase == 2) { d_dX = nullptr; d_db = nullptr; }
     UNIMM_CHECK(d_dY && d_X && d_W && d_scratch && M > 0 && N > 0 && K > 0, "bad argument");
     UNIMM_CHECK(N % 64 == 0 && K % 8 == 0 && ldy % 2 == 0, "linear backward: N must be a multiple of 64 (the dgrad contraction), K of 8");
     UNIMM_CHECK(scratch_bytes >= unimm_k_linear_backward_scratch(M, N, K), "scratch smaller than unimm_k_linear_backward_scratch()");
@@ -1709,11 +1725,14 @@ int unimm_k_linear_backward_acc(const float* d_dY, int ldy, const void* d_X, int
     // fp16's normal range), multiplied back out by the GEMM epilogues straight from device memory
     // ... and in the same pass over dY: the bias gradient (column sums) and, when dY still has to pass the erf GELU of this projection's
     // output backwards (d_gelu_t = the saved pre-activation), that derivative (|gelu'| <= 1.13 bounds the scaled values)
-    UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st, d_amax, d_gelu_t != nullptr ? 1.13f : 1.f));
-    UNIMM_CHECK(drop_p <= 0.f || (d_gelu_t == nullptr && static_cast<double>(M) * N < 4294967296.0), "output dropout: not in front of a GELU; 32-bit index");
-    UNIMM_TRY(cast_colsum_lp(d_dY, ldy, d_gelu_t, N, M, N, scale, dY16, N, lp_kind, d_db, st, make_drop(drop_seed, drop_p)));
+    if (phase != 2) {
+        UNIMM_TRY(amax_scale(d_dY, static_cast<size_t>(M) * ldy, lp_kind == LP_FP16 ? 1 : 0, scale, st, d_amax, d_gelu_t != nullptr ? 1.13f : 1.f));
+        UNIMM_CHECK(drop_p <= 0.f || (d_gelu_t == nullptr && static_cast<double>(M) * N < 4294967296.0), "output dropout: not in front of a GELU; 32-bit index");
+        UNIMM_TRY(cast_colsum_lp(d_dY, ldy, d_gelu_t, N, M, N, scale, dY16, N, lp_kind, d_db, st, make_drop(drop_seed, drop_p), gelu_t_kind));
+    }
     d_db = nullptr;                                              // done
     static const bool transposed_copies = getenv("UNIMM_BWD_TRANSPOSE") != nullptr && atoi(getenv("UNIMM_BWD_TRANSPOSE")) != 0;
+    UNIMM_CHECK(phase == 0 || !transposed_copies, "UNIMM_BWD_TRANSPOSE (the first version's transposed copies) runs as one phase");
     if (!transposed_copies) {
         // No transposed copies: tcgen05 reads an operand whose contraction index is the ROW of the stored matrix as an MN-major tile
         // (gemm_umma.cu, a_mn / b_mn).  dX [M, K] = dY [M, N] . W [N, K]: W as stored is the B operand [K, N-contraction] MN-major.

@@ -512,7 +512,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             y[i].w = drop_keep(ep.drop.seed, i0 + 3u, ep.drop.thresh) ? y[i].w * ep.drop.scale : 0.f;
                         }
                     }
-                    if (ep.pre_act_f32) {
+                    if (ep.pre_act_f32 && ep.pre_act_lp) {      // the pre-activation as 16-bit values (out_f32 points at them)
+                        bf16* pre = reinterpret_cast<bf16*>(ep.out_f32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int grow = r0 + 4 * i;
+                            if (grow < M)
+                                *reinterpret_cast<uint2*>(pre + static_cast<size_t>(grow) * ep.ldo_f32 + cc) =
+                                    make_uint2(pack_lp2(y[i].x, y[i].y, ep.lp_kind), pack_lp2(y[i].z, y[i].w, ep.lp_kind));
+                        }
+                    } else if (ep.pre_act_f32) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int grow = r0 + 4 * i;
@@ -584,7 +593,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = drop_keep(ep.drop.seed, i0 + j, ep.drop.thresh) ? x[j] * ep.drop.scale : 0.f;
                 }
-                if (ep.pre_act_f32 && row_ok) {
+                if (ep.pre_act_f32 && ep.pre_act_lp && row_ok) {
+                    bf16* o = reinterpret_cast<bf16*>(ep.out_f32) + static_cast<size_t>(row) * ep.ldo_f32 + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) o[j] = lp_from_f32(x[j], ep.lp_kind);
+                } else if (ep.pre_act_f32 && row_ok) {
                     float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ldo_f32 + col0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -823,6 +837,7 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     UNIMM_CHECK(!ep.pre_act_f32 || (ep.out_f32 != nullptr && ep.out_bf16 != nullptr && ep.residual == nullptr && !lse && !ep.w_perm16 &&
                                     !ep.out_hilo && ep.split_k <= 1 && ep.amax_out == nullptr),
                 "pre-activation output: fp32 pre-activation + 16-bit activation, plain epilogue, no residual");
+    UNIMM_CHECK(!ep.pre_act_lp || (ep.pre_act_f32 && ep.ldo_f32 % 4 == 0), "16-bit pre-activation: a variant of the pre-activation epilogue, rows 8-byte aligned");
     UNIMM_CHECK(ep.drop.thresh == 0u || (!lse && !ep.w_perm16 && !ep.out_hilo && ep.act == ACT_NONE && ep.split_k <= 1 && ep.out_f32 != nullptr &&
                                          ep.out_bf16 == nullptr && static_cast<double>(M) * N < 4294967296.0),
                 "output dropout: plain fp32-output epilogue without activation");

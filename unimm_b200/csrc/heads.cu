@@ -136,10 +136,11 @@ __device__ __forceinline__ float gelu_grad_fast(float v) {
 // where v = x, or v = x * gelu'(t) when the matrix still has to go back through the erf GELU (models/vilbert_dialog.py:115-121) —
 // the GELU backward, the cast and the bias gradient then read the fp32 gradient once and write 2 bytes per element instead of
 // three reads and an fp32 write.
-template <bool GELU>
+// GELU: 0 = none, 1 = pre-activation t in fp32, 2 = t as 16-bit values (encoding t_kind; the training forward's pre_act_lp epilogue)
+template <int GELU>
 __global__ void __launch_bounds__(256)
 cast_colsum_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ t, int ldt, int rows, int cols, const float* __restrict__ scale,
-                   bf16* __restrict__ y, int ldy, int lp_kind, float* __restrict__ colsum, DropArgs drop) {
+                   bf16* __restrict__ y, int ldy, int lp_kind, float* __restrict__ colsum, DropArgs drop, int t_kind) {
     // CTA = 64 columns x 128 rows: a warp reads 256 contiguous bytes of one row (two columns per lane), the 8 warps interleave the rows
     __shared__ float part[8][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,9 +157,16 @@ cast_colsum_kernel(const float* __restrict__ x, int ldx, const float* __restrict
                 v.x = drop_keep(drop.seed, i0, drop.thresh) ? v.x * drop.scale : 0.f;
                 v.y = drop_keep(drop.seed, i0 + 1u, drop.thresh) ? v.y * drop.scale : 0.f;
             }
-            if (GELU) {
+            if (GELU != 0) {
                 // d/dt [t Phi(t)] = Phi(t) + t phi(t); Phi from the forward's rational fit (common.cuh gelu_fast: 3.5e-6), phi by one ex2
-                const float2 tv = *reinterpret_cast<const float2*>(t + static_cast<size_t>(r) * ldt + c);
+                float2 tv;
+                if (GELU == 1) {
+                    tv = *reinterpret_cast<const float2*>(t + static_cast<size_t>(r) * ldt + c);
+                } else {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const bf16*>(t) + static_cast<size_t>(r) * ldt + c);
+                    tv = t_kind == LP_FP16 ? __half22float2(*reinterpret_cast<const __half2*>(&w))
+                                           : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+                }
                 v.x *= gelu_grad_fast(tv.x);
                 v.y *= gelu_grad_fast(tv.y);
             }
@@ -510,12 +518,14 @@ int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream
 }
 
 int cast_colsum_lp(const float* x, int ldx, const float* gelu_t, int ldt, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind,
-                   float* colsum, cudaStream_t stream, DropArgs drop) {
+                   float* colsum, cudaStream_t stream, DropArgs drop, int gelu_t_kind) {
     UNIMM_CHECK(rows > 0 && cols % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && (gelu_t == nullptr || ldt % 2 == 0), "cast_colsum: even columns and leading dimensions");
     if (colsum != nullptr) UNIMM_CUDA_CHECK(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, stream));
     const dim3 grid((cols + 63) / 64, (rows + 127) / 128);
-    if (gelu_t != nullptr) cast_colsum_kernel<true><<<grid, 256, 0, stream>>>(x, ldx, gelu_t, ldt, rows, cols, scale, y, ldy, lp_kind, colsum, drop);
-    else cast_colsum_kernel<false><<<grid, 256, 0, stream>>>(x, ldx, nullptr, 0, rows, cols, scale, y, ldy, lp_kind, colsum, drop);
+    if (gelu_t != nullptr && gelu_t_kind >= 0)
+        cast_colsum_kernel<2><<<grid, 256, 0, stream>>>(x, ldx, gelu_t, ldt, rows, cols, scale, y, ldy, lp_kind, colsum, drop, gelu_t_kind);
+    else if (gelu_t != nullptr) cast_colsum_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, gelu_t, ldt, rows, cols, scale, y, ldy, lp_kind, colsum, drop, -1);
+    else cast_colsum_kernel<0><<<grid, 256, 0, stream>>>(x, ldx, nullptr, 0, rows, cols, scale, y, ldy, lp_kind, colsum, drop, -1);
     UNIMM_LAUNCH_CHECK(1);
     return 0;
 }

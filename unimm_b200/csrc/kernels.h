@@ -58,6 +58,9 @@ struct GemmEpilogue {
     // out_f32 receives the value BEFORE the activation (acc + bias) while out_bf16 receives act(acc + bias): the training forward keeps
     // the GELU's pre-activation for the backward and feeds the next GEMM in one epilogue (no residual in this mode)
     bool pre_act_f32 = false;
+    // the same with the pre-activation stored as 16-bit values in lp_kind's encoding: out_f32 then POINTS AT a 16-bit [M, ldo_f32] matrix
+    // (half the write traffic of the FFN-1 forward and half the read traffic of its backward's pass; gelu' moves by < 1e-3)
+    bool pre_act_lp = false;
     // training forward: dropout on (acc + bias) BEFORE the residual is added (models/vilbert_dialog.py:424, :467, :553, :596, :746, :749);
     // element index = row * N + column
     DropArgs drop;
@@ -229,8 +232,9 @@ int row_sums_16(const bf16* x, int ld, int rows, int cols, int lp_kind, float al
 // out2[1] = 1 / out2[0];  y16 = lp(x * out2[0]);  colsum[j] = sum_i x[i, j]
 int amax_scale(const float* x, size_t n, int want_scale, float* out2, cudaStream_t stream, const float* known_amax = nullptr, float headroom = 1.f);
 // y = lp(v * scale[0]), colsum (optional, zeroed here) += v, with v = x or x * gelu'(gelu_t) (heads.cu: cast_colsum_kernel)
+// gelu_t_kind: -1 = gelu_t is fp32; LP_BF16 / LP_FP16 = gelu_t points at 16-bit values of that encoding
 int cast_colsum_lp(const float* x, int ldx, const float* gelu_t, int ldt, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind,
-                   float* colsum, cudaStream_t stream, DropArgs drop = DropArgs());
+                   float* colsum, cudaStream_t stream, DropArgs drop = DropArgs(), int gelu_t_kind = -1);
 int cast_scaled_lp(const float* x, int ldx, int rows, int cols, const float* scale, bf16* y, int ldy, int lp_kind, cudaStream_t stream);
 int column_sums_f32(const float* x, int ldx, int rows, int cols, float* out, cudaStream_t stream);
 // tcgen05 LM head tail: merge the per-tile (max, sum) partials

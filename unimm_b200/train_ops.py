@@ -8,6 +8,7 @@ row-major, possibly column slices of a wider matrix (the leading dimension is ta
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -34,6 +35,15 @@ class DeviceOps:
         self.lp_dtype = torch.float16 if precision == "fp16" else torch.bfloat16
         self.kind = LP_FP16 if precision == "fp16" else LP_BF16
         self._scratch = None
+        # UNIMM_WGRAD_STREAM=1: wgrad GEMMs on a second stream, see linear_backward.  Measured +1 % on the power-capped step (115.8 -> 114.7 ms,
+        # profiles/r02_v10_wgrad_stream_ab.txt): not worth a second stream's hazards by default
+        self.wgrad_stream = os.environ.get("UNIMM_WGRAD_STREAM", "0") != "0"
+        self._side = None
+        self._lb_scratch = [None, None]      # two scratch slots: the wgrad of call i still reads slot i % 2 while call i + 1 fills the other
+        self._lb_done = [None, None]         # event: the wgrad that last read the slot has finished
+        self._lb_calls = 0
+        self._lb_last = None
+        self.pre16 = os.environ.get("UNIMM_PRE16", "1") != "0"
         self._amax = {}          # data_ptr of a gradient tensor -> (device cell holding max |x| as float bits, numel); see linear_backward
 
     # ------------------------------------------------------------------ plumbing
@@ -54,6 +64,28 @@ class DeviceOps:
         if self._scratch is None or self._scratch.numel() < nbytes:
             self._scratch = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=self.device)
         return self._scratch
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def _lb_slot(self, nbytes: int):
+        """The scratch slot of the next split linear_backward; the main stream first waits for the wgrad that last read it."""
+        i = self._lb_calls & 1
+        self._lb_calls += 1
+        if self._lb_done[i] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._lb_done[i])
+        sc = self._lb_scratch[i]
+        if sc is None or sc.numel() < nbytes:
+            self._lb_scratch[i] = sc = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=self.device)   # the old one is idle: waited above
+        return sc
+
+    def join_side(self):
+        """Everything the second stream was given (wgrad GEMMs) is ordered before whatever the main stream does next."""
+        if self._lb_last is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._lb_last)
+            self._lb_last = None
 
     # max |x| of a gradient, left on the device by the kernel that produced it, saves linear_backward its own pass over the tensor
     def begin_step(self):
@@ -155,11 +187,18 @@ class DeviceOps:
     def linear(self, x16, w16, bias, residual=None, act=ACT_NONE, want32=True, want16=False, pre_act32=False, drop=None):
         """y = act(x W^T + b) (+ residual) on tcgen05 -> (y32 | None, y16 | None); ``pre_act32``: y32 = x W^T + b (the activation's input, kept
         for the backward) while y16 = act(...)."""
-        if pre_act32:
-            assert want32 and want16 and residual is None
-            act = act | 0x100
         M, K = x16.shape
         N = w16.shape[0]
+        if pre_act32:
+            assert want32 and want16 and residual is None
+            if self.pre16 and N % 4 == 0 and drop is None:
+                # the pre-activation only ever meets gelu' in the backward (linear_backward, gelu_t): kept as 16-bit values — half the
+                # write traffic of this epilogue and half the read traffic of the backward's pass (UNIMM_PRE16=0: fp32)
+                t16, y16 = self.empty16(M, N), self.empty16(M, N)
+                check(lib.unimm_k_gemm_lp(ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(bias), None, 0, act | 0x200, ptr(t16), N, ptr(y16), N, 0, 0,
+                                          self.kind, self.stream))
+                return t16, y16
+            act = act | 0x100
         if drop is not None:          # out = dropout(x W^T + b) + residual: the mask is applied in the GEMM epilogue
             assert act == ACT_NONE and want32 and not want16
             y32 = self.empty32(M, N)
@@ -190,7 +229,8 @@ class DeviceOps:
         K = x16.shape[1]
         assert dy32.is_contiguous() and g_w.is_contiguous() and tuple(g_w.shape) == (N, K)
         nbytes = lib.unimm_k_linear_backward_scratch(M, N, K)
-        sc = self.scratch(nbytes)
+        split = self.wgrad_stream and need_dx and M >= 4096          # small projections: not worth two launches' bookkeeping
+        sc = self._lb_slot(nbytes) if split else self.scratch(nbytes)
         dx = None
         if need_dx:
             dx = dx_accum if dx_accum is not None else self.empty32(M, K)
@@ -199,9 +239,26 @@ class DeviceOps:
         if cell is not None and n != dy32.numel():
             cell = None
         out_cell = self.empty32(1) if (dx_amax and need_dx) else None
-        check(lib.unimm_k_linear_backward_acc(ptr(dy32), N, ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(dx), 1 if dx_accum is not None else 0,
-                                              ptr(g_w), ptr(g_b), ptr(cell), ptr(gelu_t), ptr(out_cell), drop[0] if drop else 0, float(drop[1]) if drop else 0.0,
-                                              ptr(sc), nbytes, self.kind, self.stream))
+        args = (ptr(dy32), N, ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(dx), 1 if dx_accum is not None else 0, ptr(g_w), ptr(g_b), ptr(cell),
+                ptr(gelu_t), ptr(out_cell), drop[0] if drop else 0, float(drop[1]) if drop else 0.0, ptr(sc), nbytes,
+                self.kind | (0x100 if gelu_t is not None and gelu_t.dtype != torch.float32 else 0))      # | 0x100: 16-bit pre-activation
+        if not split:
+            check(lib.unimm_k_linear_backward_acc(*args, self.stream))
+        else:
+            # The wgrad GEMM's result is needed only when the gradients are consumed (all-reduce / optimizer): it runs on a second stream,
+            # after this call's dgrad, beside what the backward does next on the main stream — the LayerNorm backward, the next
+            # projection's pass over its dY — which is HBM-bound and leaves the tensor cores idle.  join_side() is the barrier.
+            main, side = torch.cuda.current_stream(self.device), self._side_stream()
+            check(lib.unimm_k_linear_backward_phase(*args, 1, C.c_void_p(main.cuda_stream)))
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            check(lib.unimm_k_linear_backward_phase(*args, 2, C.c_void_p(side.cuda_stream)))
+            done = torch.cuda.Event()
+            done.record(side)
+            self._lb_done[(self._lb_calls - 1) & 1] = done
+            self._lb_last = done
+            x16.record_stream(side)                                   # a saved activation: freed by the caller while the wgrad may still read it
         if out_cell is not None:
             self.register_amax(dx, out_cell)
         return dx
@@ -295,7 +352,7 @@ class TimedOps:
 
     def __getattr__(self, name):
         attr = getattr(self._ops, name)
-        if not callable(attr) or name in ("empty32", "zeros32", "empty16", "scratch", "begin_step", "new_amax_cell", "register_amax"):
+        if not callable(attr) or name in ("empty32", "zeros32", "empty16", "scratch", "begin_step", "new_amax_cell", "register_amax", "join_side"):
             return attr
 
         def timed(*a, **kw):

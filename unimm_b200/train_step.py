@@ -395,6 +395,7 @@ class TrainStep:
         the backward); ``backward`` waits for all of them before it returns."""
         if self.world <= 1:
             return
+        self.ops.join_side()                     # the layer's wgrad GEMMs run on a second stream (train_ops.linear_backward)
         for a, b in self._layer_ranges(prefix):
             st["reduced"].append((a, b))
             st["handles"].append(torch.distributed.all_reduce(self.params.g[a:b], group=self.group, async_op=True))
@@ -569,6 +570,7 @@ class TrainStep:
                             P.G(ve + "image_embeddings.bias"), need_dx=False)
         ops.linear_backward(d_vsum, st["loc16"], P.P16(ve + "image_location_embeddings.weight"), P.G(ve + "image_location_embeddings.weight"),
                             P.G(ve + "image_location_embeddings.bias"), need_dx=False)
+        ops.join_side()
         if self.world > 1:
             # what the per-layer all-reduces above have not covered (embeddings, poolers, heads): the gaps of the range that holds every
             # parameter with a gradient.  Sums; optimizer_step divides by the world size.
