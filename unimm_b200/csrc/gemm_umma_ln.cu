@@ -629,6 +629,13 @@ int gemm_umma_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
         if (N == 768) return split == 3 ? launch_ln<3, true, 256>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, true, 192>(A, lda, W, ldw, M, K, ep, stream);
         return launch_ln<4, true, 256>(A, lda, W, ldw, M, K, ep, stream);
     }
+    // fp32 residual (the bf16 mode's stream): the same cta_group::2 pairs, the residual precharged by both CTAs' epilogue warps.
+    // Same-box A/B of the bf16 step (profiles/r02_v12_ln_pair_f32_ab.txt): 298.3 k -> 305.2 k candidates / s; UNIMM_LN_PAIR_F32=0 opts out
+    static const bool pair_f32 = getenv("UNIMM_LN_PAIR_F32") == nullptr || atoi(getenv("UNIMM_LN_PAIR_F32")) != 0;
+    if (pair_f32 && N == 768 && M >= 8192 && split == 3) {
+        ep.a_multicast = false;
+        return launch_ln<3, false, 256, false, true>(A, lda, W, ldw, M, K, ep, stream);
+    }
     if (N == 768) return split == 3 ? launch_ln<3, false, 256>(A, lda, W, ldw, M, K, ep, stream) : launch_ln<4, false, 192>(A, lda, W, ldw, M, K, ep, stream);
     return launch_ln<4, false, 256>(A, lda, W, ldw, M, K, ep, stream);
 }
