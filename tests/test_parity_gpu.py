@@ -41,6 +41,32 @@ def run_engine(eng, batch, want, **extra):
                        batch["image_mask"], masked_lm_labels=batch["mask"], want=want, **extra)
 
 
+def test_bf16_mode_keeps_the_range_that_fp16_lacks(full_cfg):
+    """What the bf16 mode is for.  Its LayerNorm-bounded operands are fp16 (engine.cu: mix16), but every tensor of unbounded range stays
+    bf16: a checkpoint whose FFN activations exceed fp16's 65504 (here: one layer's intermediate.dense scaled by 3e5 and its output.dense
+    by 1 / 3e5 — GELU outputs up to ~1e6) is still scored within the bf16 bound, while the fp16 mode saturates them."""
+    from oracle import vilbert_oracle as vo
+    g, batch = load_golden("gen8_default")
+    sd = dict(golden_state_dict(full_cfg, g["weight_seed"], g["perturbed"]))
+    p, s = "bert.encoder.layer.3.", 3e5
+    sd[p + "intermediate.dense.weight"] = sd[p + "intermediate.dense.weight"] * s
+    sd[p + "intermediate.dense.bias"] = sd[p + "intermediate.dense.bias"] * s
+    sd[p + "output.dense.weight"] = sd[p + "output.dense.weight"] / s
+    want = vo.score_candidates(sd, full_cfg, batch, chunk=8, full_logits=False)[0].numpy()
+    for e in _ENGINES.values():
+        e.close()
+    _ENGINES.clear()
+    torch.cuda.empty_cache()
+    err = {}
+    for precision in ("bf16", "fp16"):
+        eng = Engine(full_cfg, sd, precision=precision, max_sequences=16)
+        err[precision] = float(np.abs(run_engine(eng, batch, ("seq_score",))["seq_score"].cpu().numpy() - want).max())
+        eng.close()
+    print(f"FFN activations beyond fp16's range: seq_score err bf16 mode {err['bf16']:.3e}, fp16 mode {err['fp16']:.3e}")
+    assert err["bf16"] < TOL["bf16"]
+    assert err["fp16"] > 10 * TOL["fp16"]
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", ["gen8_perturbed", "gen8_default"])
 def test_generative_scores(full_cfg, name, precision):
