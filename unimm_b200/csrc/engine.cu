@@ -1061,8 +1061,8 @@ int unimm_engine::run_encoder(int Mt, int Mv, const AttnCtx& ac, cudaStream_t st
     }
     if (lp() && fuse_ln && res16) {   // the poolers and the optional sequence outputs read the fp32 view
         Prof prof(this, CAT_ROWWISE, 6.0 * (static_cast<double>(Mt) * xt.ld + static_cast<double>(Mv) * xv.ld), st);
-        UNIMM_TRY(cast_lp_to_f32(xt.h, xt.f, static_cast<size_t>(Mt) * xt.ld, lp_kind(), st));
-        UNIMM_TRY(cast_lp_to_f32(xv.h, xv.f, static_cast<size_t>(Mv) * xv.ld, lp_kind(), st));
+        UNIMM_TRY(cast_lp_to_f32(xt.h, xt.f, static_cast<size_t>(Mt) * xt.ld, ln_kind(), st));
+        UNIMM_TRY(cast_lp_to_f32(xv.h, xv.f, static_cast<size_t>(Mv) * xv.ld, ln_kind(), st));
     }
     return 0;
 }
@@ -1259,12 +1259,15 @@ int unimm_create(const unimm_config_t* cfg, int device, int precision, int max_s
     if (const char* f = getenv("UNIMM_LM_DEDUP")) e->lm_dedup = atoi(f) != 0;
     e->tc32_ = precision == UNIMM_PREC_FP32;
     if (const char* f = getenv("UNIMM_FP32_SIMT")) e->tc32_ = e->tc32_ && atoi(f) == 0;
-    e->res16 = e->fuse_ln && precision == UNIMM_PREC_FP16;
-    if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     e->mix16 = precision == UNIMM_PREC_BF16;
     if (const char* f = getenv("UNIMM_BF16_PURE")) e->mix16 = e->mix16 && atoi(f) == 0;
     e->lm_hp = false;
-    if (const char* f = getenv("UNIMM_LM_HP")) e->lm_hp = atoi(f) != 0 && e->lp() && !e->res16;
+    if (const char* f = getenv("UNIMM_LM_HP")) e->lm_hp = atoi(f) != 0 && e->lp();
+    // 16-bit residual stream: the residual of a LayerNorm-fused projection is the previous LayerNorm's own 16-bit output, added on the
+    // tensor core.  That copy is fp16 in the fp16 mode AND in the bf16 mode's mixed formats (11 significant bits either way); with bf16
+    // for every operand it would be an 8-bit residual stream, and the fp32-class LM head wants the fp32 stream: both keep fp32.
+    e->res16 = e->fuse_ln && (precision == UNIMM_PREC_FP16 || (precision == UNIMM_PREC_BF16 && e->mix16)) && !e->lm_hp;
+    if (const char* f = getenv("UNIMM_RES16")) e->res16 = e->res16 && atoi(f) != 0;
     *out = e;
     return 0;
 }

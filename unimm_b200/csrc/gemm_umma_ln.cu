@@ -205,7 +205,10 @@ umma_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ptx::elect_one() && m_r == 0) {
             const uint32_t in_fmt = (ep.in_kind < 0 ? ep.lp_kind : ep.in_kind) == LP_FP16 ? 0u : 1u;
             const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BN, in_fmt);
-            const uint32_t idesc_r = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BK, in_fmt);   // N = 64: one diagonal block
+            // the residual x identity k-blocks are instructions of their own: they read the RESIDUAL's format (out_lp's), which may differ
+            // from the A / W format of the projection itself (bf16 mode: fp16 LayerNorm outputs, bf16 projection operands) — tcgen05
+            // only wants one format per instruction, and both kinds accumulate into the same fp32 TMEM columns
+            const uint32_t idesc_r = ptx::make_idesc_f16(PAIR ? 2 * BM : BM, BK, ep.lp_kind == LP_FP16 ? 0u : 1u);   // N = 64: one diagonal block
             const uint64_t di = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sI));
             if (RES16) {
                 ptx::mbar_wait(ident_bar, 0);
@@ -544,7 +547,6 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int K, cons
     UNIMM_TRY(gemm_make_map(W, CS * BN, K, ldw, PAIR ? BN / 2 : BN, &tmB));
     if (RES16) {
         const bf16* ident = nullptr;
-        UNIMM_CHECK(ep.in_kind < 0 || ep.in_kind == ep.lp_kind, "the 16-bit residual is added as identity k-blocks: one operand format");
         UNIMM_TRY(identity_for(ep.lp_kind, &ident));
         UNIMM_TRY(gemm_make_map(ep.residual_lp, M, CS * BN, ep.ldr_lp, BM, &tmR));
         UNIMM_TRY(gemm_make_map(ident, IDN, IDN, IDN, PAIR ? 32 : 64, &tmI));          // top-left 64 x 64 block: the row order is 32-periodic
