@@ -206,8 +206,9 @@ struct unimm_engine {
     // |gamma| sqrt(H - 1) + |beta| whatever the checkpoint's activations do, so its 16-bit copy — and the weights of the projections
     // that read it (Q | K | V, FFN-1, the co-attention projections, the LM / image heads) — are fp16: same tcgen05 rate, 3 more
     // mantissa bits.  Everything whose range is NOT bounded by construction (Q / K / V, attention context, GELU outputs, image
-    // features, and the weights multiplying them) stays bf16; the residual stream is fp32.  tcgen05 kind::f16 wants A and B in one
-    // format, so the format is a property of the projection (Linear::in_kind), and every GEMM converts on its way out.
+    // features, and the weights multiplying them) stays bf16; the residual stream is the fp16 LayerNorm output (res16), fp32 on
+    // request.  tcgen05 kind::f16 wants A and B in one format, so the format is a property of the projection (Linear::in_kind),
+    // and every GEMM converts on its way out.
     bool mix16 = false;
     int ln_kind() const { return prec == UNIMM_PREC_BF16 && mix16 ? LP_FP16 : lp_kind(); }
     int act_kind() const { return tc32() ? LP_HILO : ln_kind(); }      // what the LayerNorm / embedding kernels write next to fp32
