@@ -287,6 +287,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             f32x2::unpack(f32x2::add(f32x2::pack(__uint_as_float(f[c & 1][reg]), __uint_as_float(f[c & 1][reg + 1])),
                                                      f32x2::pack(bb[m], bb[m + 1])), y[m], y[m + 1]);
                         }
+                        const int grow = m0 + ew * 32 + 8 * k + r8;
+                        if (ep.pre_act_lp && grow < M) {    // training forward: the activation's input as 16-bit values (out_f32 points at them)
+                            uint4 pp;
+                            pp.x = pack_lp2(y[0], y[1], ep.lp_kind); pp.y = pack_lp2(y[2], y[3], ep.lp_kind);
+                            pp.z = pack_lp2(y[4], y[5], ep.lp_kind); pp.w = pack_lp2(y[6], y[7], ep.lp_kind);
+                            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out_f32) + static_cast<size_t>(grow) * ep.ldo_f32 + col0 + 8 * a4) = pp;
+                        }
                         if (ep.act == ACT_GELU) {
 #pragma unroll
                             for (int m = 0; m < 8; m += 2) gelu_fast2(y[m], y[m + 1]);
@@ -300,7 +307,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         uint4 pk;
                         pk.x = pack_lp2(y[0], y[1], ep.lp_kind); pk.y = pack_lp2(y[2], y[3], ep.lp_kind);
                         pk.z = pack_lp2(y[4], y[5], ep.lp_kind); pk.w = pack_lp2(y[6], y[7], ep.lp_kind);
-                        const int grow = m0 + ew * 32 + 8 * k + r8;
                         if (grow < M) *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(grow) * ep.ldo_bf16 + col0 + 8 * a4) = pk;
                     }
                 }
@@ -834,7 +840,7 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
                    int max_ctas, cudaStream_t stream) {
     UNIMM_CHECK(M > 0 && N > 0 && K > 0 && (K % BK == 0 || (ep.a_mn && ep.b_mn)), "umma gemm: K must be a positive multiple of 64");
     const bool lse = ep.partials != nullptr || ep.dz != nullptr;
-    UNIMM_CHECK(!ep.pre_act_f32 || (ep.out_f32 != nullptr && ep.out_bf16 != nullptr && ep.residual == nullptr && !lse && !ep.w_perm16 &&
+    UNIMM_CHECK(!ep.pre_act_f32 || (ep.out_f32 != nullptr && ep.out_bf16 != nullptr && ep.residual == nullptr && !lse && (!ep.w_perm16 || ep.pre_act_lp) &&
                                     !ep.out_hilo && ep.split_k <= 1 && ep.amax_out == nullptr),
                 "pre-activation output: fp32 pre-activation + 16-bit activation, plain epilogue, no residual");
     UNIMM_CHECK(!ep.pre_act_lp || (ep.pre_act_f32 && ep.ldo_f32 % 4 == 0), "16-bit pre-activation: a variant of the pre-activation epilogue, rows 8-byte aligned");
@@ -891,7 +897,8 @@ int gemm_umma_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N,
     }
     if (ep.w_perm16) {
         auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-        UNIMM_CHECK(ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && N % 32 == 0 && (ep.ldo_bf16 & 7) == 0 &&
+        UNIMM_CHECK(!ep.pre_act_lp || ((ep.ldo_f32 & 7) == 0 && a16(ep.out_f32)), "16-bit pre-activation of the fragment epilogue: 16-byte aligned rows");
+        UNIMM_CHECK(ep.out_bf16 != nullptr && (ep.out_f32 == nullptr || ep.pre_act_lp) && ep.residual == nullptr && N % 32 == 0 && (ep.ldo_bf16 & 7) == 0 &&
                         a16(ep.out_bf16) && (ep.bias == nullptr || a16(ep.bias)) && ep.debug_mode == 0,
                     "fragment-ordered weights need a 16-bit-only, 16-byte aligned output with N % 32 == 0");
         if (tile_n == 256 && mc) return launch<256, false, 0, true, 2>(A, lda, W, ldw, M, N, K, ep, max_ctas, stream);

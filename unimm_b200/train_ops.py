@@ -44,6 +44,8 @@ class DeviceOps:
         self._lb_calls = 0
         self._lb_last = None
         self.pre16 = os.environ.get("UNIMM_PRE16", "1") != "0"
+        self.pre16_perm = os.environ.get("UNIMM_PRE16_PERM", "1") != "0"     # FFN-1 forward through the fragment-ordered epilogue (linear, pre_act32)
+        self._wperm = {}
         self._amax = {}          # data_ptr of a gradient tensor -> (device cell holding max |x| as float bits, numel); see linear_backward
 
     # ------------------------------------------------------------------ plumbing
@@ -195,8 +197,18 @@ class DeviceOps:
                 # the pre-activation only ever meets gelu' in the backward (linear_backward, gelu_t): kept as 16-bit values — half the
                 # write traffic of this epilogue and half the read traffic of the backward's pass (UNIMM_PRE16=0: fp32)
                 t16, y16 = self.empty16(M, N), self.empty16(M, N)
-                check(lib.unimm_k_gemm_lp(ptr(x16), _ld(x16), ptr(w16), _ld(w16), M, N, K, ptr(bias), None, 0, act | 0x200, ptr(t16), N, ptr(y16), N, 0, 0,
-                                          self.kind, self.stream))
+                kind, w = self.kind, w16
+                if self.pre16_perm and N % 32 == 0 and K % 8 == 0 and w16.is_contiguous():
+                    # the scoring engine's fragment-ordered weights: a thread's TMEM fragment is then 8 consecutive output columns and both
+                    # 16-bit outputs leave as 16-byte stores without the shared-memory transpose.  The permuted copy is made per call
+                    # (the weights change every step; 4.7 MB for an FFN-1 matrix, a few microseconds)
+                    w = self._wperm.get((N, K))
+                    if w is None:
+                        w = self._wperm[(N, K)] = self.empty16(N, K)
+                    check(lib.unimm_k_permute_w(ptr(w16), ptr(w), N, K, 1, self.stream))
+                    kind = self.kind | 0x100
+                check(lib.unimm_k_gemm_lp(ptr(x16), _ld(x16), ptr(w), K, M, N, K, ptr(bias), None, 0, act | 0x200, ptr(t16), N, ptr(y16), N, 0, 0,
+                                          kind, self.stream))
                 return t16, y16
             act = act | 0x100
         if drop is not None:          # out = dropout(x W^T + b) + residual: the mask is applied in the GEMM epilogue
