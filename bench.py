@@ -201,6 +201,64 @@ def cpu_reference_rate(n_candidates, steps=1, warmup=0):
     return n_candidates * len(times) / total, total / len(times), torch.get_num_threads()
 
 
+def reference_module_rate(n_candidates, steps=1, warmup=0):
+    """The UNMODIFIED reference module on the host cores, driven as val_lm.py:104-137 drives it: VisualDialogEncoder.forward with
+    train.forward's keyword set (train.py:142-161) on chunks of 25, output_lm_scores=True (full-vocabulary logits), cross_entropy with
+    ignore_index -1, sum over positions.  Needs a reference checkout — baseline/_ref/reference, the git-ignored copy that
+    __graft_entry__.build() / scripts/make_ref_copy.py make in the build container and that travels to the GPU box, or /root/reference
+    — and returns None without one (the caller then times the oracle port).  Same synthetic rounds, weights and chunking as
+    cpu_reference_rate."""
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    import contextlib
+    try:
+        import ref_callers as rc
+        root = rc.reference_root()
+        if root is None:
+            return None
+        with contextlib.redirect_stdout(sys.stderr):         # the reference prints while importing / constructing: stdout carries ONE JSON line
+            ref = rc.import_reference(root)
+    except Exception as e:          # a checkout that does not import here is the same as none: the port is timed and the line says so
+        print(f"[bench] reference checkout not usable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return None
+    from unimm_b200 import synthetic as syn
+    from unimm_b200.config import DEFAULT_CONFIG_PATH, ViLBertConfig
+    from unimm_b200.descriptors import dense_co_mask, dense_text_mask
+    from unimm_b200.weights import random_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = ViLBertConfig.from_json_file(DEFAULT_CONFIG_PATH)
+    with contextlib.redirect_stdout(sys.stderr):
+        model = rc.build_reference_encoder(ref, root, {"bert_pretrained." + k: v for k, v in random_state_dict(cfg, 0).items()})
+    rng = np.random.RandomState(0)
+    feat, loc, mask = (torch.from_numpy(a) for a in syn.synth_image(rng))
+    times = []
+    for it in range(warmup + steps):
+        r = syn.encode_round_gen(syn.synth_context(rng, 10), syn.synth_answers(rng, n_candidates))
+        tokens, segments, positions, labels, desc, _ = syn.stack_rounds([r])
+        n = tokens.shape[0]
+        txt_mask, co_mask = dense_text_mask(desc, 256), dense_co_mask(desc, 256).long().unsqueeze(1).repeat(1, 37, 1)
+        t0 = time.perf_counter()
+        scores = []
+        with torch.no_grad():
+            for s0 in range(0, n, 25):
+                sl = slice(s0, min(n, s0 + 25))
+                m = sl.stop - sl.start
+                out = model(tokens[sl].long(), feat.expand(m, -1, -1).contiguous(), loc.expand(m, -1, -1).contiguous(),
+                            sep_indices=None, sep_len=None, token_type_ids=segments[sl].long(), token_position_ids=positions[sl].long(),
+                            masked_lm_labels=labels[sl].long(), attention_mask=txt_mask[sl], next_sentence_label=None, output_nsp_scores=True,
+                            output_lm_scores=True, image_attention_mask=mask.expand(m, -1).contiguous(), co_attention_mask=co_mask[sl],
+                            image_label=None, image_target=None, nsp_weight=None, lm_weight=None)
+                lm = out[-1]
+                a, b, c = lm.size()
+                nll = F.cross_entropy(lm.view(a * b, c), labels[sl].long().view(-1), ignore_index=-1, reduction="none").view(a, b)
+                scores.append(-nll.sum(-1))
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return n_candidates * len(times) / total, total / len(times), torch.get_num_threads()
+
+
 def eager_gpu_rate(mode, steps, warmup, chunk=250):
     """SURVEY.md §8(d) / BASELINE.md §4 "second on-box bar": the reference's forward as eager PyTorch on ONE B200 (the oracle's
     functional restatement on cuda tensors: cuBLAS / ATen kernels, dense masks, full-vocabulary logits as val_lm.py:121-137),
@@ -256,15 +314,19 @@ def main_reference(args):
                                                 "kernels; not the product path, not the driver's reference arm)", "mode": args.ref_mode}}), flush=True)
         return
     per_step = args.ref_candidates          # one 100-candidate round per step, chunks of 25
-    rate, sec, cores = cpu_reference_rate(per_step, steps=args.steps, warmup=min(args.warmup, 1))
+    got = None if args.ref_port else reference_module_rate(per_step, steps=args.steps, warmup=min(args.warmup, 1))
+    kind = "reference" if got is not None else "port"
+    what = ("the UNMODIFIED reference module (baseline/_ref) driven as val_lm.py:104-137" if got is not None
+            else "the CPU port of the reference path (oracle/), not the unmodified module: no reference checkout on this box")
+    rate, sec, cores = got if got is not None else cpu_reference_rate(per_step, steps=args.steps, warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": "candidates_scored_per_sec", "value": rate, "unit": "candidates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": "configs[1] synthetic VisDial val sweep, generative scoring (bounded CPU sample: one round-10 dialog "
-                                   "round of %d candidates per step; the CPU port of the reference path, not the unmodified module)" % per_step,
+                                   "round of %d candidates per step; %s)" % (per_step, what),
                        "candidates_per_step": per_step, "seq_len": 256, "regions": 37, "model": "bert_base_6layer_6conect random init",
                        "cpu_warmup_steps": min(args.warmup, 1)},
-            "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": kind,
                              "sample": f"{args.steps} steps x {per_step} candidates of a round-10 dialog, chunks of 25, full-vocab logits "
                                        "+ cross_entropy as val_lm.py:121-137"},
             "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -837,8 +899,9 @@ def main_ours(args):
         }
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
-            rate, sec, cores = cpu_reference_rate(args.cpu_sample)
-            line["cpu_baseline"] = {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port",
+            got = reference_module_rate(args.cpu_sample)          # the unmodified reference module when a checkout travelled with the repo
+            rate, sec, cores = got if got is not None else cpu_reference_rate(args.cpu_sample)
+            line["cpu_baseline"] = {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "reference" if got is not None else "port",
                                     "sample": f"{args.cpu_sample} candidates of one round-10 dialog in chunks of <=25, full-vocab logits + "
                                               f"cross_entropy as val_lm.py:121-137 ({sec:.1f} s)"}
         print(json.dumps(line), flush=True)
@@ -870,6 +933,7 @@ if __name__ == "__main__":
     ap.add_argument("--profile-ops", action="store_true", help="--workload train_step: add a per-operation event-timed table of one extra step")
     ap.add_argument("--no-verify", action="store_true", help="skip the per-step context-equality check of the packer")
     ap.add_argument("--no-bf16", action="store_true", help="fp16 runs: skip the nested bf16_mode measurement")
+    ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port even when a reference checkout is present")
     ap.add_argument("--ref-candidates", type=int, default=100, help="--impl reference: candidates per CPU step")
     a = ap.parse_args()
     if a.impl == "reference":
