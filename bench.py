@@ -202,6 +202,15 @@ def cpu_reference_rate(n_candidates, steps=1, warmup=0):
 
 
 def reference_module_rate(n_candidates, steps=1, warmup=0):
+    """_reference_module_rate, or None (-> the caller times the oracle port) when the checkout is absent or does not run here."""
+    try:
+        return _reference_module_rate(n_candidates, steps, warmup)
+    except Exception as e:
+        print(f"[bench] reference module not usable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return None
+
+
+def _reference_module_rate(n_candidates, steps=1, warmup=0):
     """The UNMODIFIED reference module on the host cores, driven as val_lm.py:104-137 drives it: VisualDialogEncoder.forward with
     train.forward's keyword set (train.py:142-161) on chunks of 25, output_lm_scores=True (full-vocabulary logits), cross_entropy with
     ignore_index -1, sum over positions.  Needs a reference checkout — baseline/_ref/reference, the git-ignored copy that
